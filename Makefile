@@ -1,0 +1,20 @@
+# Builds libpcnn.so (hand-written sm_100a CUDA kernels + C ABI) in-tree.
+NVCC ?= nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr
+SRC := $(wildcard poisson_cnn_b200/csrc/*.cu)
+OBJ := $(patsubst poisson_cnn_b200/csrc/%.cu,build/%.o,$(SRC))
+LIB := poisson_cnn_b200/libpcnn.so
+
+all: $(LIB)
+
+build/%.o: poisson_cnn_b200/csrc/%.cu poisson_cnn_b200/csrc/pcnn_common.cuh include/pcnn.h
+	@mkdir -p build
+	$(NVCC) $(NVCCFLAGS) -Xptxas -v -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
+
+$(LIB): $(OBJ)
+	$(NVCC) -shared $(ARCH) -o $@ $(OBJ) -lcudart
+
+clean:
+	rm -rf build $(LIB)
+.PHONY: all clean

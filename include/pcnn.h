@@ -1,0 +1,177 @@
+/* pcnn.h -- C ABI of libpcnn.so: hand-written sm_100a CUDA kernels for the batched-inference hot
+ * path of aligirayhanozbay/poisson_CNN (Poisson_CNN_Legacy forward, FD Laplacian residual, DST
+ * direct solve).
+ *
+ * The reference is pure Python on TensorFlow and has no FFI of its own; each entry point below
+ * replaces the TensorFlow op call site(s) cited next to it (paths relative to
+ * /root/reference/poisson_CNN/).  The host side (poisson_cnn_b200/, Python, ctypes) mirrors the
+ * reference's poisson_CNN.models call surface and drives these functions.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - the library never allocates device memory and never synchronises: all work is enqueued on
+ *     the caller's stream (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - the caller owns every buffer; the library borrows them for the duration of the call;
+ *   - every function returns 0 on success or a negative pcnn_status; pcnn_last_error() returns a
+ *     thread-local message for the last failure.  No C++ exception crosses the ABI;
+ *   - tensors are NCHW ("channels_first", the reference's data_format), fp32, dense unless a
+ *     *_bstride (batch stride, in elements) argument says otherwise.
+ */
+#ifndef PCNN_H_
+#define PCNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCNN_VERSION 100
+
+typedef enum {
+    PCNN_OK = 0,
+    PCNN_ERR_INVALID_ARGUMENT = -1,
+    PCNN_ERR_CUDA = -2,
+    PCNN_ERR_UNSUPPORTED = -3
+} pcnn_status;
+
+/* activations: utils/convert_tf_object_names.py evals "tf.nn.leaky_relu" (alpha 0.2) / "tf.nn.tanh" */
+enum { PCNN_ACT_LINEAR = 0, PCNN_ACT_LEAKY_RELU = 1, PCNN_ACT_TANH = 2 };
+/* tf.pad modes: utils/apply_advanced_padding_and_call_conv_layer.py:6,18 */
+enum { PCNN_PAD_CONSTANT = 0, PCNN_PAD_SYMMETRIC = 1, PCNN_PAD_REFLECT = 2 };
+/* SpatialPyramidPool pooling_type: layers/SpatialPyramidPool.py:11-14 */
+enum { PCNN_POOL_AVG = 0, PCNN_POOL_MAX = 1 };
+/* HPNN bc_type: models/Homogeneous_Poisson_NN_Legacy.py:106-113 */
+enum { PCNN_BC_DIRICHLET = 0, PCNN_BC_NEUMANN = 1 };
+
+int pcnn_version(void);
+const char* pcnn_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+long long pcnn_launch_count(void);
+
+/* ---- convolution ---------------------------------------------------------------------------
+ * tf.pad(mode) + Conv2D(VALID) + bias + activation, then (optionally, in this order) the
+ * inference BatchNorm affine that follows the conv, the residual add of blocks/resnet.py:37, and a
+ * per-(sample,channel) scale (the dx-MLP einsum, models/Homogeneous_Poisson_NN_Legacy.py:231).
+ * Replaces utils/apply_advanced_padding_and_call_conv_layer.py:17-20, blocks/resnet.py:29-39 and
+ * the Keras BatchNormalization calls.  Conv1D (models/Dirichlet_BC_NN_Legacy.py:52-64) is the
+ * H == 1, kh == 1 case.
+ *   in        [B, Cin, H, W]   (batch stride in_bstride elements)
+ *   kernel    [kh, kw, Cin, Cout]  Keras layout; cross-correlation, pad left k/2, right k/2-(1-k%2)
+ *   bias      [Cout] or NULL
+ *   bn_scale, bn_shift [Cout] or NULL:  v = v*bn_scale + bn_shift  (gamma/sqrt(var+1e-3), beta-mean*scale)
+ *   residual  [B, Cout, H, W] or NULL (batch stride res_bstride), added after BN
+ *   out_scale [B, Cout] or NULL, multiplied last
+ *   out       [B, Cout, H, W]  (batch stride out_bstride)
+ */
+int pcnn_conv2d_f32(const float* in, const float* kernel, const float* bias, const float* bn_scale,
+                    const float* bn_shift, const float* residual, const float* out_scale, float* out,
+                    int B, int Cin, int Cout, int H, int W, int kh, int kw, int pad_mode,
+                    float pad_value, int act, int64_t in_bstride, int64_t out_bstride,
+                    int64_t res_bstride, void* stream);
+
+/* ---- pooling / upsampling -------------------------------------------------------------------
+ * AveragePooling2D(pool=s, stride=s, 'same'): out = ceil(N/s), pad_before = floor((out*s-N)/2),
+ * divisor = number of valid cells.  Replaces utils/get_pooling_method.py:3-6 as used by
+ * blocks/bottleneck_block.py:36-37,72 and layers/Scaling.py:29.   out [B,C,ceil(H/s),ceil(W/s)] dense. */
+int pcnn_avgpool_same_f32(const float* in, float* out, int B, int C, int H, int W, int s,
+                          int64_t in_bstride, void* stream);
+
+/* tf.nn.conv2d_transpose(in, kernel[kh,kw,Cout,Cin], out_shape, strides=stride, 'SAME') + bias +
+ * activation (layers/deconvupscale.py:100-109).  out = (accumulate ? out : 0) + alpha * result, so
+ * the 8-way merge sum of models/Homogeneous_Poisson_NN_Legacy.py:222 needs no extra pass. */
+int pcnn_deconv_same_f32(const float* in, const float* kernel, const float* bias, float* out, int B,
+                         int Cin, int Cout, int ih, int iw, int oh, int ow, int kh, int kw,
+                         int stride, int act, float alpha, int accumulate, int64_t out_bstride,
+                         void* stream);
+
+/* tf.image.resize(method, antialias=False) (layers/Upsample.py:56-59), separable gather form:
+ * out[y,x] = sum_{a,b} wy[y,a]*wx[x,b]*in[iy[y,a], ix[x,b]].  The per-axis tables (taps = 1 nearest,
+ * 2 bilinear, 4 bicubic incl. TF's 1024-step Keys table) are built by the host and live on the
+ * device.  out = (accumulate ? out : 0) + alpha * result. */
+int pcnn_resize_f32(const float* in, const int32_t* iy, const float* wy, const int32_t* ix,
+                    const float* wx, int taps, float* out, int B, int C, int ih, int iw, int oh,
+                    int ow, float alpha, int accumulate, int64_t out_bstride, void* stream);
+
+/* SpatialPyramidPool.call (layers/SpatialPyramidPool.py:48-66): every bin is reduced over channels
+ * AND space.  boxes [nbins,4] = (y0,y1,x0,x1) from split_indices (dataset/utils/split_indices.py);
+ * out [B,nbins].  An empty box gives -inf (max) / NaN (avg) like tf.reduce_*. */
+int pcnn_spp_f32(const float* in, const int32_t* boxes, float* out, int B, int C, int H, int W,
+                 int nbins, int mode, void* stream);
+
+/* tf.keras.layers.Dense: y = act(x @ kernel + bias); x [B,nin], kernel [nin,nout]. */
+int pcnn_dense_f32(const float* x, const float* kernel, const float* bias, float* y, int B, int nin,
+                   int nout, int act, void* stream);
+
+/* ---- per-sample normalisation (dataset/utils/set_max_magnitude.py:4-50) ------------------- */
+/* maxabs[b] = max |x[b,:]| ; n elements per sample */
+int pcnn_maxabs_f32(const float* x, float* maxabs, int B, int64_t n, void* stream);
+/* y[b,:] = x[b,:] * (1 / maxabs[b])   (the reference multiplies by the quotient 1.0/max) */
+int pcnn_scale_inv_f32(const float* x, const float* maxabs, float* y, int B, int64_t n, void* stream);
+
+/* ---- model glue ---------------------------------------------------------------------------- */
+/* concat(rhs, cos(pi*linspace) along x, along y): models/Homogeneous_Poisson_NN_Legacy.py:172-180,196-198.
+ * posx [H], posy [W] host-built tables; out [B,3,H,W]. */
+int pcnn_hpnn_input_f32(const float* rhs, const float* posx, const float* posy, float* out, int B,
+                        int H, int W, void* stream);
+/* concat(bc, pos_nd[...,0,:]) -> [B,3,n] (models/Dirichlet_BC_NN_Legacy.py:132,136); posx0 = posx[0] */
+int pcnn_dbcnn_input_f32(const float* bc, float posx0, const float* posy, float* out, int B, int n,
+                         void* stream);
+/* einsum('bmy,mx,bm->bmxy') + concat(pos_nd) (models/Dirichlet_BC_NN_Legacy.py:151-154):
+ * h [B,M,n], sinh_basis [M,xres], modew [B,M] -> out [B,M+2,xres,n] */
+int pcnn_dbcnn_expand_f32(const float* h, const float* sinh_basis, const float* modew,
+                          const float* posx, const float* posy, float* out, int B, int M, int xres,
+                          int n, void* stream);
+/* out = raw * (1/maxabs[b]); out[:, :, 0, :] = bc   (models/Dirichlet_BC_NN_Legacy.py:158-160) */
+int pcnn_dbcnn_finalize_f32(const float* raw, const float* maxabs, const float* bc, float* out, int B,
+                            int xres, int n, void* stream);
+/* Scaling multiply + boundary ring (layers/Scaling.py:55, models/Homogeneous_Poisson_NN_Legacy.py:251):
+ * out = pad((y*(1+s[b]))[1:-1,1:-1], 1, CONSTANT 0 | SYMMETRIC); s may be NULL. */
+int pcnn_hpnn_finalize_f32(const float* y, const float* s, float* out, int B, int H, int W,
+                           int bc_type, int64_t y_bstride, void* stream);
+/* Inputs of the two MLPs: out [B,3+nextra] = [dx, L0, L1, extra...] with L = dx*(n-1)
+ * (models/Homogeneous_Poisson_NN_Legacy.py:193,202); normalize != 0 divides L0,L1 by max(L0,L1)
+ * (models/Dirichlet_BC_NN_Legacy.py:129-130,142; extra = the SPP vector). */
+int pcnn_dense_input_f32(const float* dx, const float* extra, float* out, int B, int n0, int n1,
+                         int nextra, int normalize, void* stream);
+/* Poisson_CNN_Legacy.call tail (models/Poisson_CNN_Legacy.py:30-47) with the rot90/flip of
+ * dataset/utils/flip_and_rotate_tensor.py folded into the indexing:
+ * pred[b,i,j] = L[b,i,j]*ml + R[b,nx-1-i,j]*mr + T[b,ny-1-j,i]*mt + Bt[b,j,i]*mb
+ *             + hp[b,i,j] * (dx[b]*(max(nx,ny)-1))^2 * mrhs
+ * L,R [B,nx,ny]; T,Bt [B,ny,nx]; m* [B] = max|.| of the raw inputs (1/scaling factor). */
+int pcnn_merge_f32(const float* hp, const float* L, const float* T, const float* R, const float* Bt,
+                   const float* dx, const float* mrhs, const float* ml, const float* mt,
+                   const float* mr, const float* mb, float* out, int B, int nx, int ny, void* stream);
+
+/* ---- checks -------------------------------------------------------------------------------- */
+/* linear_operator_loss.__call__ (losses/physics_informed_loss.py:35-50): central-difference
+ * Laplacian (stencil 3: [1,-2,1]; stencil 5: [-1/12,4/3,-5/2,4/3,-1/12] per direction, weights
+ * 1/dx_d^2, dataset/utils/build_fd_coefficients.py:5-42) of sol against the interior of rhs.
+ * grid_spacings [B,2].  sq_sum[b] = sum over interior of (rhs - Lap(sol))^2 (double),
+ * divided by rhs_maxabs[b]^2 when rhs_maxabs != NULL (the reference's normalize=True).
+ * The loss is sum(sq_sum)/(B*interior points). */
+int pcnn_laplacian_residual_f32(const float* rhs, const float* sol, const float* grid_spacings,
+                                const float* rhs_maxabs, double* sq_sum, int B, int H, int W,
+                                int stencil, void* stream);
+/* JacobiIterationLayer (layers/JacobiIterationLayer.py:44-66), stencil [3,3] orders [2,2]:
+ * one sweep cur -> next; ring copied unchanged.  grid_spacings [B,2]. */
+int pcnn_jacobi_sweep_f32(const float* cur, const float* rhs, const float* grid_spacings, float* next,
+                          int B, int H, int W, void* stream);
+
+/* Direct solve of the reference's ground-truth system (dataset/solvers/multigrid.py:98-150,
+ * dataset/solvers/cholesky.py:45-119) with a DST-I eigen-decomposition, in double precision:
+ * A u = -dx^2 f + adjacent BCs on the interior, ring := BCs (left/right written last).
+ * rhs [B,nx,ny] fp32; left,right [B,ny]; top,bottom [B,nx]; dx [B]; out [B,nx,ny] fp32.
+ * sx [(nx-2)^2], sy [(ny-2)^2] double sine matrices and work (2*B*(nx-2)*(ny-2) doubles) are
+ * caller-provided (pcnn_dst_workspace_bytes / pcnn_dst_sine_matrix). */
+size_t pcnn_dst_workspace_bytes(int B, int nx, int ny);
+int pcnn_dst_sine_matrix(double* s, int m, void* stream);
+int pcnn_dst_solve(const float* rhs, const float* left, const float* top, const float* right,
+                   const float* bottom, const float* dx, const double* sx, const double* sy,
+                   double* work, float* out, int B, int nx, int ny, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCNN_H_ */

@@ -1,0 +1,76 @@
+"""ctypes binding of libpcnn.so (include/pcnn.h).
+
+There is deliberately NO fallback: if the shared library is missing or a symbol cannot be bound,
+importing this module raises, and every product entry point that computes goes through it.
+"""
+import ctypes
+import os
+from ctypes import c_int, c_int64, c_float, c_void_p, c_size_t, c_char_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpcnn.so")
+
+P = c_void_p  # every device pointer crosses the ABI as a plain address
+
+# name -> (restype, argtypes); mirrors include/pcnn.h one to one
+SIGNATURES = {
+    "pcnn_version": (c_int, []),
+    "pcnn_last_error": (c_char_p, []),
+    "pcnn_launch_count": (ctypes.c_longlong, []),
+    "pcnn_conv2d_f32": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_int, c_float, c_int, c_int64, c_int64, c_int64, P]),
+    "pcnn_avgpool_same_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int64, P]),
+    "pcnn_deconv_same_f32": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_int, c_int, c_float, c_int, c_int64, P]),
+    "pcnn_resize_f32": (c_int, [P, P, P, P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_float, c_int, c_int64, P]),
+    "pcnn_spp_f32": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "pcnn_dense_f32": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    "pcnn_maxabs_f32": (c_int, [P, P, c_int, c_int64, P]),
+    "pcnn_scale_inv_f32": (c_int, [P, P, P, c_int, c_int64, P]),
+    "pcnn_hpnn_input_f32": (c_int, [P, P, P, P, c_int, c_int, c_int, P]),
+    "pcnn_dbcnn_input_f32": (c_int, [P, c_float, P, P, c_int, c_int, P]),
+    "pcnn_dbcnn_expand_f32": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    "pcnn_dbcnn_finalize_f32": (c_int, [P, P, P, P, c_int, c_int, c_int, P]),
+    "pcnn_hpnn_finalize_f32": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int64, P]),
+    "pcnn_dense_input_f32": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    "pcnn_merge_f32": (c_int, [P] * 12 + [c_int, c_int, c_int, P]),
+    "pcnn_laplacian_residual_f32": (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    "pcnn_jacobi_sweep_f32": (c_int, [P, P, P, P, c_int, c_int, c_int, P]),
+    "pcnn_dst_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pcnn_dst_sine_matrix": (c_int, [P, c_int, P]),
+    "pcnn_dst_solve": (c_int, [P] * 10 + [c_int, c_int, c_int, P]),
+}
+
+
+class PcnnError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            "poisson_cnn_b200: %s not found. Build it with `make` (or `python -c 'import __graft_entry__ as g; "
+            "g.build()'`) -- there is no CPU or PyTorch fallback for the compute path." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    if lib.pcnn_version() < 100:
+        raise ImportError("libpcnn.so is older than the Python host side; rebuild")
+    return lib
+
+
+lib = _load()
+
+
+def check(status, what=""):
+    """Turn a negative pcnn_status into the exception the reference would have raised:
+    ValueError for bad arguments/configs, RuntimeError for CUDA failures."""
+    if status == 0:
+        return
+    msg = lib.pcnn_last_error().decode("utf-8", "replace")
+    if status == -1 or status == -3:
+        raise ValueError("%s: %s" % (what or "pcnn", msg))
+    raise PcnnError("%s: %s" % (what or "pcnn", msg))

@@ -1,0 +1,127 @@
+"""Dirichlet_BC_NN_Legacy_2 on hand-written CUDA kernels.
+
+Same constructor kwargs / call convention as poisson_CNN/models/Dirichlet_BC_NN_Legacy.py:14-166:
+model([bc, dx, x_output_resolution]) with bc [B,1,n], dx [B,1] -> [B,1,x_res,n].
+"""
+import copy
+import warnings
+
+import torch
+
+from .. import ops
+from .. import weights as W
+from ..config import activation_enum, padding_enum, PAD_CONSTANT, ACT_TANH
+from ._base import WeightedModel
+
+
+class Dirichlet_BC_NN_Legacy_2(WeightedModel):
+    def __init__(self, data_format="channels_first", boundary_conv_config=None, spp_config=None,
+                 domain_info_mlp_config=None, final_convolutions_config=None, postsmoother_iterations=0,
+                 use_batchnorm=False):
+        super().__init__()
+        self.ndims = 2
+        if data_format != "channels_first":
+            raise NotImplementedError("the CUDA path is channels_first (every shipped config)")
+        self.data_format = data_format
+        self.use_batchnorm = use_batchnorm
+        if boundary_conv_config is None:
+            raise ValueError("Provide a config for the boundary convolutions.")
+        if spp_config is None:
+            raise ValueError("Provide a config for the Spatial Pyramid Pooling.")
+        if final_convolutions_config is None:
+            raise ValueError("Provide a config for the domain convolutions.")
+        if domain_info_mlp_config is None:
+            raise ValueError("Provide a config for the domain info MLP.")
+        assert boundary_conv_config["filters"][-1] == domain_info_mlp_config["units"][-1]
+        if boundary_conv_config["filters"][-1] > 27:
+            warnings.warn(str(boundary_conv_config["filters"][-1]) + " sinh modes chosen may lead to NaN values with float32 precision. Consider using fewer than 28 when using float32.")
+        self.x_dir_nmodes = domain_info_mlp_config["units"][-1]
+
+        self._cfg = copy.deepcopy({
+            "use_batchnorm": use_batchnorm, "boundary_conv_config": boundary_conv_config, "spp_config": spp_config,
+            "domain_info_mlp_config": domain_info_mlp_config, "final_convolutions_config": final_convolutions_config})
+
+        bcfg = copy.deepcopy(boundary_conv_config)
+        self.boundary_pad = padding_enum(bcfg.pop("padding_mode", "CONSTANT"))
+        self.boundary_pad_value = bcfg.pop("constant_padding_value", 0.0)
+        self.boundary_act = activation_enum(bcfg.get("activation"))
+        self.n_boundary = len(bcfg["filters"])
+
+        self.spp_levels = copy.deepcopy(spp_config["levels"])
+        ptype = spp_config.get("pooling_type", "average").lower()
+        if ptype in ("average", "avg"):
+            self.spp_mode = ops.POOL_AVG
+        elif ptype == "max":
+            self.spp_mode = ops.POOL_MAX
+        else:
+            raise ValueError("unknown SPP pooling_type " + ptype)
+
+        self.mlp_acts = [activation_enum(a) for a in domain_info_mlp_config["activations"]]
+        self.n_mlp = len(domain_info_mlp_config["units"])
+
+        fin = copy.deepcopy(final_convolutions_config)
+        self.final_pad = padding_enum(fin.pop("padding_mode", "CONSTANT"))
+        self.final_pad_value = fin.pop("constant_padding_value", 0.0)
+        self.final_regular_conv_stages = fin.pop("final_regular_conv_stages", 2)
+        self.final_act = activation_enum(fin.get("activation"))
+        self.n_final = len(fin["filters"])
+        self.postsmoother_iterations = postsmoother_iterations
+
+    def weight_specs(self, prefix=""):
+        return W.dbcnn_weight_specs(self._cfg, prefix)
+
+    def _resnet1d(self, x, name, act, pad, pad_value, use_bn):
+        k0, b0 = self.conv(name + "/conv0")
+        k1, b1 = self.conv(name + "/conv1")
+        k2, b2 = self.conv(name + "/conv2")
+        t = ops.conv1d(x, k0, b0, act, pad, pad_value, bn=self.bn(name + "/bn0") if use_bn else None)
+        t = ops.conv1d(t, k1, b1, act, pad, pad_value, bn=self.bn(name + "/bn1") if use_bn else None, residual=x)
+        return ops.conv1d(t, k2, b2, act, pad, pad_value)
+
+    def _resnet2d(self, x, name, act):
+        k0, b0 = self.conv(name + "/conv0")
+        k1, b1 = self.conv(name + "/conv1")
+        k2, b2 = self.conv(name + "/conv2")
+        t = ops.conv2d(x, k0, b0, act, PAD_CONSTANT, 0.0)
+        t = ops.conv2d(t, k1, b1, act, PAD_CONSTANT, 0.0, residual=x)
+        return ops.conv2d(t, k2, b2, act, PAD_CONSTANT, 0.0)
+
+    def raw_forward(self, bc, dx, x_res):
+        """Everything up to (not including) the final max-normalisation; returns (raw [B,1,x_res,n], max|raw| [B])."""
+        if bc.dim() != 3 or bc.shape[1] != 1:
+            raise ValueError("bc must be [batch, 1, n] (channels_first)")
+        if dx.dim() != 2 or dx.shape[1] != 1 or dx.shape[0] != bc.shape[0]:
+            raise ValueError("dx must be [batch, 1]")
+        x_res = int(x_res)
+        B, _, n = bc.shape
+        h = ops.dbcnn_input(bc, x_res)
+        for k in range(self.n_boundary):
+            kk, bb = self.conv("boundary/%d/conv" % k)
+            h = ops.conv1d(h, kk, bb, self.boundary_act, self.boundary_pad, self.boundary_pad_value,
+                           bn=self.bn("boundary/%d/bn" % k) if self.use_batchnorm else None)
+            h = self._resnet1d(h, "boundary/%d/resnet" % k, self.boundary_act, self.boundary_pad,
+                               self.boundary_pad_value, self.use_batchnorm)
+        spp = ops.spatial_pyramid_pool(h, self.spp_levels, self.spp_mode, ndims=1)
+        v = ops.dense_input(dx, x_res, n, extra=spp, normalize=True)
+        for i in range(self.n_mlp):
+            v = ops.dense(v, *self.conv("mlp/%d" % i), self.mlp_acts[i])
+        out = ops.dbcnn_expand(h, v, x_res)
+        S, nreg = self.n_final, self.final_regular_conv_stages
+        for k in range(S - nreg):
+            kk, bb = self.conv("final/%d/conv" % k)
+            out = ops.conv2d(out, kk, bb, self.final_act, self.final_pad, self.final_pad_value)
+            out = self._resnet2d(out, "final/%d/resnet" % k, self.final_act)
+        for k in range(S - nreg, S):
+            kk, bb = self.conv("final/%d/conv" % k)
+            out = ops.conv2d(out, kk, bb, ACT_TANH, PAD_CONSTANT, 0.0)
+        return out, ops.maxabs(out)
+
+    def __call__(self, inp):
+        bc, dx, x_res = inp
+        raw, m = self.raw_forward(bc, dx, x_res)
+        out = ops.dbcnn_finalize(raw, m, bc)
+        if self.postsmoother_iterations > 0:
+            out = ops.jacobi(out, torch.zeros_like(out), torch.cat([dx, dx], 1), self.postsmoother_iterations)
+        return out
+
+    call = __call__

@@ -1,0 +1,233 @@
+"""Homogeneous_Poisson_NN_Legacy on hand-written CUDA kernels.
+
+Same constructor kwargs, call convention and error behaviour as the reference class
+(poisson_CNN/models/Homogeneous_Poisson_NN_Legacy.py:10-257); every tensor op goes through
+libpcnn.so.  model([rhs, dx]) -> [B,1,H,W] on the device/stream of the inputs, no host sync.
+"""
+import copy
+
+import torch
+
+from .. import ops
+from .. import weights as W
+from ..config import (activation_enum, padding_enum, resize_enum, get_init_arguments_from_config,
+                      process_normalizations, process_output_scaling_modes, bottleneck_output_size,
+                      ACT_LEAKY_RELU, ACT_LINEAR, PAD_CONSTANT)
+from ._base import WeightedModel
+
+
+class _Bottleneck:
+    """One resolution branch (poisson_CNN/blocks/bottleneck_block.py:8-118), config only."""
+
+    def __init__(self, kind, index, ndims, downsampling_factor, filters, conv_kernel_size, deconv_kernel_size=None,
+                 data_format="channels_first", conv_activation=None, conv_use_bias=True, use_resnet=False,
+                 padding_mode="constant", constant_padding_value=0.0, n_convs=1, upsampling_factor=None,
+                 conv_initializer_constraint_regularizer_options=None, downsampling_method="conv",
+                 conv_downsampling_kernel_size=None, pool_downsampling_method="max", use_batchnorm=False,
+                 batchnorm_trainable=True, resize_method="bilinear", deconv_activation=None, deconv_use_bias=True,
+                 deconv_initializer_constraint_regularizer_options=None):
+        self.kind, self.index = kind, index
+        self.downsampling_factor = downsampling_factor
+        self.upsampling_factor = downsampling_factor if upsampling_factor is None else upsampling_factor
+        self.filters = filters
+        self.ksize = conv_kernel_size
+        self.deconv_ksize = deconv_kernel_size
+        self.act = activation_enum(conv_activation)
+        self.deconv_act = activation_enum(deconv_activation)
+        self.pad = padding_enum(padding_mode)
+        self.pad_value = constant_padding_value
+        self.n_convs = n_convs
+        self.use_batchnorm = use_batchnorm
+        self.resize_method = resize_enum(resize_method) if kind == "multilinear" else None
+        method = downsampling_method.lower()
+        if method not in ("conv", "pool"):
+            raise ValueError("Downsampling method can only be conv or pool")
+        if method != "pool" or not use_resnet:
+            raise NotImplementedError("only downsampling_method='pool' with use_resnet=True (every shipped config) is built")
+        if pool_downsampling_method.lower() not in ("average", "avg"):
+            raise NotImplementedError("only average pooling (every shipped config) is built")
+
+
+class Homogeneous_Poisson_NN_Legacy(WeightedModel):
+    def __init__(self, data_format="channels_first", final_convolutions_config=None,
+                 pre_bottleneck_convolutions_config=None, bottleneck_deconv_config=None,
+                 bottleneck_multilinear_config=None, input_normalization=None, output_scaling=None,
+                 use_batchnorm=False, postsmoother_iterations=5, use_scaling=False,
+                 use_positional_embeddings=True, scaling_config=None, gradient_accumulation_steps=None,
+                 bc_type="dirichlet"):
+        super().__init__()
+        self.ndims = 2
+        if data_format != "channels_first":
+            raise NotImplementedError("the CUDA path is channels_first (every shipped config)")
+        self.data_format = data_format
+        self.gradient_accumulation_steps = gradient_accumulation_steps
+        self.input_normalization = process_normalizations(input_normalization)
+        self.output_scaling = process_output_scaling_modes(output_scaling)
+        self.use_batchnorm = use_batchnorm
+        self.use_positional_embeddings = use_positional_embeddings
+
+        if pre_bottleneck_convolutions_config is None:
+            raise ValueError("Provide a config for pre bottleneck convolutions")
+        if (bottleneck_deconv_config is None) or (bottleneck_multilinear_config is None):
+            raise ValueError("Provide a config for bottleneck blocks")
+        if final_convolutions_config is None:
+            raise ValueError("Provide a config for final convolutions")
+        if use_scaling and scaling_config is None:
+            raise ValueError("use_scaling=True needs a scaling_config")
+        if bc_type.lower() not in ("dirichlet", "neumann"):
+            raise ValueError("bc_type can only be neumann or dirichlet.")
+        self.bc_type = ops.BC_DIRICHLET if bc_type.lower() == "dirichlet" else ops.BC_NEUMANN
+
+        # keep a JSON-like copy for weight_specs()
+        self._cfg = copy.deepcopy({
+            "use_batchnorm": use_batchnorm, "use_scaling": use_scaling,
+            "use_positional_embeddings": use_positional_embeddings,
+            "pre_bottleneck_convolutions_config": pre_bottleneck_convolutions_config,
+            "bottleneck_deconv_config": bottleneck_deconv_config,
+            "bottleneck_multilinear_config": bottleneck_multilinear_config,
+            "final_convolutions_config": final_convolutions_config, "scaling_config": scaling_config})
+
+        pre = copy.deepcopy(pre_bottleneck_convolutions_config)
+        self.pre_pad = padding_enum(pre.pop("padding_mode", "CONSTANT"))
+        self.pre_pad_value = pre.pop("constant_padding_value", 0.0)
+        self.pre_act = activation_enum(pre.get("activation"))
+        self.n_pre = len(pre["filters"])
+
+        assert bottleneck_deconv_config["filters"] == bottleneck_multilinear_config["filters"]
+        self.filters = bottleneck_deconv_config["filters"]
+        f_cfg = ["downsampling_factors", "upsampling_factors", "conv_kernel_sizes", "deconv_kernel_sizes", "n_convs"]
+        f_arg = ["downsampling_factor", "upsampling_factor", "conv_kernel_size", "deconv_kernel_size", "n_convs"]
+        dcfg = bottleneck_deconv_config
+        self.bottleneck_deconv_blocks = [
+            _Bottleneck("deconv", k, ndims=2, data_format=data_format, use_batchnorm=use_batchnorm,
+                        **get_init_arguments_from_config(dcfg, k, f_cfg, f_arg))
+            for k in range(len(dcfg["downsampling_factors"]))]
+        self.bottleneck_deconv_blocks.sort(key=lambda b: b.downsampling_factor, reverse=True)
+        mcfg = bottleneck_multilinear_config
+        f_cfg = ["downsampling_factors", "upsampling_factors", "conv_kernel_sizes", "n_convs"] + (["resize_methods"] if "resize_methods" in mcfg else [])
+        f_arg = ["downsampling_factor", "upsampling_factor", "conv_kernel_size", "n_convs"] + (["resize_method"] if "resize_methods" in mcfg else [])
+        self.bottleneck_multilinear_blocks = [
+            _Bottleneck("multilinear", k, ndims=2, data_format=data_format, use_batchnorm=use_batchnorm,
+                        **get_init_arguments_from_config(mcfg, k, f_cfg, f_arg))
+            for k in range(len(mcfg["downsampling_factors"]))]
+        self.bottleneck_multilinear_blocks.sort(key=lambda b: b.downsampling_factor, reverse=True)
+
+        fin = copy.deepcopy(final_convolutions_config)
+        self.final_pad = padding_enum(fin.pop("padding_mode", "CONSTANT"))
+        self.final_pad_value = fin.pop("constant_padding_value", 0.0)
+        self.final_regular_conv_stages = fin.pop("final_regular_conv_stages", 2)
+        self.final_act = activation_enum(fin.get("activation"))
+        self.n_final = len(fin["filters"])
+
+        self.postsmoother_iterations = postsmoother_iterations
+        self.use_scaling = use_scaling
+        if use_scaling:
+            sc = dict(scaling_config)
+            self.scaling_stages = sc.get("stages", 2)
+            self.scaling_ratio = sc.get("downsampling_ratio_per_stage", 2)
+            self.scaling_levels = copy.deepcopy(sc.get("spp_levels", [[2, 2], 3, 5]))
+            self.scaling_act = activation_enum(sc.get("activation"))
+            if sc.get("kernel_size", 3) % 2 == 0:
+                raise NotImplementedError("Scaling: even kernel sizes with Keras 'same' padding are not built")
+
+    def weight_specs(self, prefix=""):
+        return W.hpnn_weight_specs(self._cfg, prefix)
+
+    # ------------------------------------------------------------------ building blocks
+    def _resnet(self, x, name, act, pad, pad_value, use_bn, out_scale=None):
+        """blocks/resnet.py:29-39 with BN and the residual add fused into the conv epilogues."""
+        k0, b0 = self.conv(name + "/conv0")
+        k1, b1 = self.conv(name + "/conv1")
+        k2, b2 = self.conv(name + "/conv2")
+        t = ops.conv2d(x, k0, b0, act, pad, pad_value, bn=self.bn(name + "/bn0") if use_bn else None)
+        t = ops.conv2d(t, k1, b1, act, pad, pad_value, bn=self.bn(name + "/bn1") if use_bn else None, residual=x)
+        return ops.conv2d(t, k2, b2, act, pad, pad_value, out_scale=out_scale)
+
+    def _bottleneck(self, blk, x0, merged, first, alpha):
+        name = "bottleneck_%s/%d" % (blk.kind, blk.index)
+        H, Wd = x0.shape[2], x0.shape[3]
+        h = ops.avgpool_same(x0, blk.downsampling_factor)
+        k, b = self.conv(name + "/conv0")
+        h = ops.conv2d(h, k, b, blk.act, blk.pad, blk.pad_value)
+        for r in range(1, blk.n_convs):
+            h = self._resnet(h, "%s/resnet%d" % (name, r), blk.act, blk.pad, blk.pad_value, blk.use_batchnorm)
+        out_hw = (bottleneck_output_size(H, blk.downsampling_factor, blk.upsampling_factor),
+                  bottleneck_output_size(Wd, blk.downsampling_factor, blk.upsampling_factor))
+        if out_hw != (H, Wd):
+            raise ValueError("bottleneck branch ds=%d would produce %s for a %s grid; the merge needs equal shapes"
+                             % (blk.downsampling_factor, out_hw, (H, Wd)))
+        if blk.kind == "deconv":
+            dk, db = self.conv(name + "/deconv")
+            ops.deconv_same(h, dk, db, out_hw, blk.upsampling_factor, blk.deconv_act, alpha, out=merged, accumulate=not first)
+        else:
+            ops.resize(h, out_hw, blk.resize_method, alpha, out=merged, accumulate=not first)
+
+    # ------------------------------------------------------------------ forward
+    def __call__(self, inp):
+        rhs, dx = inp
+        if rhs.dim() != 4 or rhs.shape[1] != 1:
+            raise ValueError("rhs must be [batch, 1, nx, ny] (channels_first)")
+        if dx.dim() != 2 or dx.shape[1] != 1 or dx.shape[0] != rhs.shape[0]:
+            raise ValueError("dx must be [batch, 1]")
+        B, _, H, Wd = rhs.shape
+        F = self.filters
+
+        x = ops.hpnn_input(rhs) if self.use_positional_embeddings else rhs
+        for k in range(self.n_pre):
+            kk, bb = self.conv("pre_bottleneck/%d" % k)
+            x = ops.conv2d(x, kk, bb, self.pre_act, self.pre_pad, self.pre_pad_value,
+                           bn=self.bn("pre_bottleneck/%d/bn" % k) if self.use_batchnorm else None)
+        x0 = x
+
+        # concat(non_bottleneck_conv(x0), merged) is assembled in place: channels [0,F) and [F,2F)
+        cat = torch.empty((B, 2 * F, H, Wd), device=rhs.device, dtype=torch.float32)
+        merged = cat[:, F:]
+        blocks = self.bottleneck_deconv_blocks + self.bottleneck_multilinear_blocks
+        alpha = 1.0 / float(len(blocks) * F)
+        for i, blk in enumerate(blocks):
+            self._bottleneck(blk, x0, merged, i == 0, alpha)
+        kk, bb = self.conv("non_bottleneck_conv")
+        ops.conv2d(x0, kk, bb, ACT_LEAKY_RELU, PAD_CONSTANT, 0.0, out=cat[:, :F])
+        kk, bb = self.conv("post_merge_conv")
+        y = ops.conv2d(cat, kk, bb, ACT_LEAKY_RELU, PAD_CONSTANT, 0.0)
+
+        # dx MLP -> per-(sample, channel) scale, applied in the epilogue of post_merge_resnet's last conv
+        d = ops.dense_input(dx, H, Wd)
+        d = ops.dense(d, *self.conv("dx_dense/0"), ACT_LEAKY_RELU)
+        d = ops.dense(d, *self.conv("dx_dense/1"), ACT_LEAKY_RELU)
+        d = ops.dense(d, *self.conv("dx_dense/2"), ACT_LINEAR)
+        y = self._resnet(y, "post_merge_resnet", ACT_LEAKY_RELU, PAD_CONSTANT, 0.0, False, out_scale=d)
+
+        S, nreg = self.n_final, self.final_regular_conv_stages
+        cat2 = torch.empty((B, 2, H, Wd), device=rhs.device, dtype=torch.float32) if self.use_scaling else None
+        for k in range(S - nreg):
+            kk, bb = self.conv("final/%d/conv" % k)
+            y = ops.conv2d(y, kk, bb, self.final_act, self.final_pad, self.final_pad_value)
+            y = self._resnet(y, "final/%d/resnet" % k, self.final_act, PAD_CONSTANT, 0.0, False)
+        for k in range(S - nreg, S):
+            kk, bb = self.conv("final/%d/conv" % k)
+            last = (k == S - 1) and self.use_scaling and kk.shape[3] == 1
+            y = ops.conv2d(y, kk, bb, ACT_LINEAR, PAD_CONSTANT, 0.0, out=cat2[:, 0:1] if last else None)
+
+        s = None
+        if self.use_scaling:
+            if y.data_ptr() != cat2.data_ptr():
+                cat2[:, 0:1].copy_(y)
+                y = cat2[:, 0:1]
+            cat2[:, 1:2].copy_(rhs)
+            h = cat2
+            for st in range(self.scaling_stages):
+                kk, bb = self.conv("scaling/conv%d" % st)
+                h = ops.conv2d(h, kk, bb, self.scaling_act, PAD_CONSTANT, 0.0)
+                h = ops.avgpool_same(h, self.scaling_ratio)
+            v = ops.spatial_pyramid_pool(h, self.scaling_levels, ops.POOL_MAX, ndims=2)
+            v = ops.dense(v, *self.conv("scaling/dense0"), ACT_LEAKY_RELU)
+            v = ops.dense(v, *self.conv("scaling/dense1"), ACT_LEAKY_RELU)
+            s = ops.dense(v, *self.conv("scaling/dense2"), ACT_LINEAR).reshape(B)
+
+        out = ops.hpnn_finalize(y, s, self.bc_type)
+        if self.postsmoother_iterations > 0:
+            out = ops.jacobi(out, rhs, torch.cat([dx, dx], 1), self.postsmoother_iterations)
+        return out
+
+    call = __call__

@@ -1,0 +1,79 @@
+"""Poisson_CNN_Legacy: homogeneous-RHS network + Dirichlet-BC network on all four edges, merged.
+
+Mirrors poisson_CNN/models/Poisson_CNN_Legacy.py:5-51: model([rhs, left, top, right, bottom, dx])
+with rhs [B,1,nx,ny], left/right [B,1,ny], top/bottom [B,1,nx], dx [B,1] -> [B,1,nx,ny].
+The DBCNN weights are shared by the four boundaries, so the four calls are batched (4B when
+nx == ny, otherwise 2B + 2B); the rot90/flip of flip_and_rotate_tensor and the 1/scaling-factor
+rescales are folded into the final merge kernel.
+"""
+import torch
+
+from .. import ops
+from ._base import WeightedModel
+
+
+class Poisson_CNN_Legacy(WeightedModel):
+    def __init__(self, hpnn, dbcnn, jacobi_iterations=0):
+        super().__init__()
+        self.hpnn = hpnn
+        self.dbcnn = dbcnn
+        self.data_format = hpnn.data_format
+        self.jacobi_iterations = jacobi_iterations
+
+    def weight_specs(self, prefix=""):
+        hs, hm = self.hpnn.weight_specs(prefix + "hpnn/")
+        ds, dm = self.dbcnn.weight_specs(prefix + "dbcnn/")
+        return {**hs, **ds}, {**hm, **dm}
+
+    def load_weights(self, source, prefix="", device=None):
+        from .. import weights as W
+        if isinstance(source, str):
+            source = W.load_npz(source)
+        self.hpnn.load_weights(source, prefix + "hpnn/", device)
+        self.dbcnn.load_weights(source, prefix + "dbcnn/", device)
+        self.device = self.hpnn.device
+        return self
+
+    def get_weights_dict(self, prefix=""):
+        return {**self.hpnn.get_weights_dict(prefix + "hpnn/"), **self.dbcnn.get_weights_dict(prefix + "dbcnn/")}
+
+    def __call__(self, inp):
+        rhs, left, top, right, bottom, dx = inp
+        if rhs.dim() != 4 or rhs.shape[1] != 1:
+            raise ValueError("rhs must be [batch, 1, nx, ny] (channels_first)")
+        B, _, nx, ny = rhs.shape
+        for t, n, name in ((left, ny, "left"), (right, ny, "right"), (top, nx, "top"), (bottom, nx, "bottom")):
+            if tuple(t.shape) != (B, 1, n):
+                raise ValueError("%s boundary must be [batch, 1, %d], got %s" % (name, n, tuple(t.shape)))
+
+        # per-sample max-normalisation of the five inputs (set_max_magnitude_in_batch_and_return_scaling_factors)
+        mrhs = ops.maxabs(rhs)
+        rhs_n = ops.scale_inv(rhs, mrhs)
+        ml, mt, mr, mb = ops.maxabs(left), ops.maxabs(top), ops.maxabs(right), ops.maxabs(bottom)
+
+        hp = self.hpnn([rhs_n, dx])
+
+        if nx == ny:
+            bcs = torch.empty((4 * B, 1, ny), device=rhs.device, dtype=torch.float32)
+            for i, (t, m) in enumerate(((left, ml), (top, mt), (right, mr), (bottom, mb))):
+                ops.scale_inv(t, m, out=bcs[i * B:(i + 1) * B])
+            res = self.dbcnn([bcs, dx.repeat(4, 1), nx])
+            L, T, R, Bt = (res[i * B:(i + 1) * B] for i in range(4))
+        else:
+            lr = torch.empty((2 * B, 1, ny), device=rhs.device, dtype=torch.float32)
+            ops.scale_inv(left, ml, out=lr[:B]); ops.scale_inv(right, mr, out=lr[B:])
+            tb = torch.empty((2 * B, 1, nx), device=rhs.device, dtype=torch.float32)
+            ops.scale_inv(top, mt, out=tb[:B]); ops.scale_inv(bottom, mb, out=tb[B:])
+            dx2 = dx.repeat(2, 1)
+            res_lr = self.dbcnn([lr, dx2, nx])
+            res_tb = self.dbcnn([tb, dx2, ny])
+            L, R = res_lr[:B], res_lr[B:]
+            T, Bt = res_tb[:B], res_tb[B:]
+
+        pred = ops.merge(hp, L, T, R, Bt, dx, mrhs, ml, mt, mr, mb)
+        if self.jacobi_iterations > 0:
+            # the reference passes the max-normalised rhs here (it rebinds `rhs`, Poisson_CNN_Legacy.py:23,49)
+            pred = ops.jacobi(pred, rhs_n, torch.cat([dx, dx], 1), self.jacobi_iterations)
+        return pred
+
+    call = __call__

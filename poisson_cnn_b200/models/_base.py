@@ -1,0 +1,79 @@
+"""Shared weight handling of the hot-path models."""
+import numpy as np
+import torch
+
+from .. import weights as W
+
+BN_EPS = 1e-3   # tf.keras.layers.BatchNormalization default epsilon
+
+
+class WeightedModel:
+    """Holds name-addressed device tensors; BatchNorm statistics are folded to (scale, shift) once.
+
+    The reference creates its variables on the first call and fills them with
+    model.load_weights(checkpoint_prefix) (poisson_CNN/train/utils.py:12-15).  Here
+    load_weights() accepts an .npz written by weights.save_npz(), or a {name: array} dict.
+    """
+
+    def __init__(self):
+        self._w = {}
+        self._bn = {}
+        self.device = None
+        self.precision = "fp32"
+
+    # -- to be provided by subclasses
+    def weight_specs(self, prefix=""):
+        raise NotImplementedError
+
+    def load_weights(self, source, prefix="", device=None):
+        if isinstance(source, str):
+            source = W.load_npz(source)
+        if device is None:
+            device = self.device or torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        specs, _ = self.weight_specs(prefix)
+        missing = [k for k in specs if k not in source]
+        if missing:
+            raise ValueError("load_weights: %d variables missing, e.g. %s" % (len(missing), missing[:3]))
+        self._w, self._bn = {}, {}
+        for name, shape in specs.items():
+            a = np.asarray(source[name], dtype=np.float32)
+            if tuple(a.shape) != tuple(shape):
+                raise ValueError("load_weights: %s has shape %s, expected %s" % (name, a.shape, shape))
+            self._w[name[len(prefix):]] = torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        # fold BN: y = gamma*(x-mean)/sqrt(var+eps)+beta = x*scale + shift
+        for name in list(self._w):
+            if name.endswith("/gamma"):
+                base = name[:-len("/gamma")]
+                g, b, m, v = (self._w[base + "/" + k] for k in ("gamma", "beta", "mean", "var"))
+                scale = g / torch.sqrt(v + BN_EPS)
+                self._bn[base] = (scale.contiguous(), (b - m * scale).contiguous())
+        self._on_weights_loaded()
+        return self
+
+    def _on_weights_loaded(self):
+        pass
+
+    def init_synthetic_weights(self, seed=0, device=None):
+        """Seeded random weights (no trained weights ship with the reference)."""
+        return self.load_weights(W.synthetic_weights(self.weight_specs(), seed=seed), device=device)
+
+    def w(self, name):
+        try:
+            return self._w[name]
+        except KeyError:
+            if not self._w:
+                raise RuntimeError("model has no weights: call load_weights() or init_synthetic_weights() first")
+            raise
+
+    def conv(self, name):
+        return self._w[name + "/kernel"], self._w.get(name + "/bias")
+
+    def bn(self, name):
+        return self._bn.get(name)
+
+    def get_weights_dict(self, prefix=""):
+        return {prefix + k: v.detach().cpu().numpy() for k, v in self._w.items()}
+
+    def count_params(self):
+        return W.count_parameters(self.weight_specs()[0])

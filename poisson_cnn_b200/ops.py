@@ -1,0 +1,423 @@
+"""Thin torch-tensor front end over the C ABI (include/pcnn.h).
+
+torch is used only for device memory and streams; every function here enqueues hand-written CUDA
+kernels from libpcnn.so on torch's current stream and returns without synchronising.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check
+from .config import (ACT_LINEAR, PAD_CONSTANT, RESIZE_NEAREST, RESIZE_BILINEAR, RESIZE_BICUBIC)
+
+POOL_AVG, POOL_MAX = 0, 1
+BC_DIRICHLET, BC_NEUMANN = 0, 1
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t, name, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError("%s must be a CUDA tensor (the hot path has no CPU implementation)" % name)
+    if t.dtype != dtype:
+        raise ValueError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t
+
+
+def _nchw_bstride(t, name):
+    """Accept dense NCHW tensors or channel-slices of one (batch stride may exceed C*H*W)."""
+    _chk(t, name)
+    B, C, H, W = t.shape
+    sb, sc, sh, sw = t.stride()
+    if not ((sw == 1 or W == 1) and (sh == W or H == 1) and (sc == H * W or C == 1)):
+        raise ValueError("%s must be NCHW-contiguous within a sample (strides %s)" % (name, t.stride()))
+    return sb if B > 1 else C * H * W
+
+
+def conv2d(x, kernel, bias=None, act=ACT_LINEAR, pad_mode=PAD_CONSTANT, pad_value=0.0, bn=None,
+           residual=None, out_scale=None, out=None):
+    """pad + VALID conv + bias + act [+ BN affine] [+ residual] [* out_scale].  x [B,Cin,H,W],
+    kernel [kh,kw,Cin,Cout] (Keras layout)."""
+    in_bs = _nchw_bstride(x, "x")
+    _chk(kernel, "kernel")
+    B, Cin, H, W = x.shape
+    kh, kw, kcin, Cout = kernel.shape
+    if kcin != Cin:
+        raise ValueError("conv2d: kernel expects %d input channels, got %d" % (kcin, Cin))
+    if out is None:
+        out = torch.empty((B, Cout, H, W), device=x.device, dtype=torch.float32)
+    out_bs = _nchw_bstride(out, "out")
+    res_bs = _nchw_bstride(residual, "residual") if residual is not None else 0
+    bn_s, bn_t = (bn if bn is not None else (None, None))
+    timed = KERNEL_TIMER is not None and KERNEL_TIMER.match(Cin, Cout, kh, kw, H, W)
+    if timed:
+        KERNEL_TIMER.start()
+    check(lib.pcnn_conv2d_f32(_p(x), _p(kernel.contiguous()), _p(bias), _p(bn_s), _p(bn_t), _p(residual),
+                              _p(out_scale), _p(out), B, Cin, Cout, H, W, kh, kw, int(pad_mode),
+                              float(pad_value), int(act), in_bs, out_bs, res_bs, _stream()), "conv2d")
+    if timed:
+        KERNEL_TIMER.stop(2.0 * B * H * W * kh * kw * Cin * Cout)
+    return out
+
+
+class KernelTimer:
+    """CUDA-event timer around the launches of one conv shape (bench.py's live roofline measurement).
+    Events are recorded on the launching stream; durations are read after the timed region."""
+
+    def __init__(self, cin, cout, k):
+        self.key = (cin, cout, k)
+        self.events, self.flops = [], []
+
+    def match(self, cin, cout, kh, kw, H, W):
+        return (cin, cout, kh) == self.key and kh == kw
+
+    def start(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self._s = e
+
+    def stop(self, flops):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.events.append((self._s, e))
+        self.flops.append(flops)
+
+    def summary(self):
+        ms = [a.elapsed_time(b) for a, b in self.events]
+        if not ms:
+            return None
+        return {"launches": len(ms), "avg_ms": sum(ms) / len(ms), "flops_per_launch": sum(self.flops) / len(self.flops)}
+
+
+KERNEL_TIMER = None
+
+
+def conv1d(x, kernel, bias=None, act=ACT_LINEAR, pad_mode=PAD_CONSTANT, pad_value=0.0, bn=None, residual=None):
+    """Conv1D as the H == 1 case.  x [B,C,n], kernel [k,Cin,Cout]."""
+    r = None if residual is None else residual.unsqueeze(2)
+    return conv2d(x.unsqueeze(2), kernel.unsqueeze(0), bias, act, pad_mode, pad_value, bn, r).squeeze(2)
+
+
+def avgpool_same(x, s):
+    in_bs = _nchw_bstride(x, "x")
+    B, C, H, W = x.shape
+    out = torch.empty((B, C, -(-H // s), -(-W // s)), device=x.device, dtype=torch.float32)
+    check(lib.pcnn_avgpool_same_f32(_p(x), _p(out), B, C, H, W, int(s), in_bs, _stream()), "avgpool_same")
+    return out
+
+
+def deconv_same(x, kernel, bias, out_hw, stride, act=ACT_LINEAR, alpha=1.0, out=None, accumulate=False):
+    _chk(x, "x"); _chk(kernel, "kernel")
+    x = x.contiguous()
+    B, Cin, ih, iw = x.shape
+    kh, kw, Cout, kcin = kernel.shape
+    if kcin != Cin:
+        raise ValueError("deconv_same: kernel expects %d input channels, got %d" % (kcin, Cin))
+    oh, ow = int(out_hw[0]), int(out_hw[1])
+    if out is None:
+        out = torch.empty((B, Cout, oh, ow), device=x.device, dtype=torch.float32)
+        accumulate = False
+    out_bs = _nchw_bstride(out, "out")
+    check(lib.pcnn_deconv_same_f32(_p(x), _p(kernel.contiguous()), _p(bias), _p(out), B, Cin, Cout, ih, iw, oh, ow,
+                                   kh, kw, int(stride), int(act), float(alpha), int(bool(accumulate)), out_bs,
+                                   _stream()), "deconv_same")
+    return out
+
+
+# ---- host-built tables (tiny, cached per device) -------------------------------------------------
+_cache = {}
+
+
+def _cached(key, build):
+    if key not in _cache:
+        _cache[key] = build()
+    return _cache[key]
+
+
+def _bicubic_table():
+    # TF resize_bicubic CPU kernel: 1024-step Keys (a=-0.5) table in float32
+    n = 1024
+    a = np.float32(-0.5)
+    x = np.arange(n + 1, dtype=np.float32) / np.float32(n)
+    t0 = ((a + np.float32(2)) * x - (a + np.float32(3))) * x * x + np.float32(1)
+    x1 = x + np.float32(1)
+    t1 = ((a * x1 - np.float32(5) * a) * x1 + np.float32(8) * a) * x1 - np.float32(4) * a
+    tab = np.empty(2 * (n + 1), dtype=np.float32)
+    tab[0::2], tab[1::2] = t0, t1
+    return tab
+
+
+def resize_axis_table(n_in, n_out, method):
+    """Per-axis gather indices / weights of tf.image.resize (half-pixel centres, antialias=False)."""
+    scale = np.float32(n_in) / np.float32(n_out)
+    o = np.arange(n_out, dtype=np.float32)
+    if method == RESIZE_NEAREST:
+        idx = np.clip(np.floor((o + np.float32(0.5)) * scale).astype(np.int64), 0, n_in - 1)
+        return idx[:, None].astype(np.int32), np.ones((n_out, 1), np.float32)
+    src = (o + np.float32(0.5)) * scale - np.float32(0.5)
+    fl = np.floor(src)
+    if method == RESIZE_BILINEAR:
+        lo = np.maximum(fl.astype(np.int64), 0)
+        hi = np.minimum(np.ceil(src).astype(np.int64), n_in - 1)
+        lerp = (src - fl).astype(np.float32)
+        return np.stack([lo, hi], 1).astype(np.int32), np.stack([np.float32(1) - lerp, lerp], 1).astype(np.float32)
+    if method == RESIZE_BICUBIC:
+        tab = _cached("bicubic_tab", _bicubic_table)
+        n = 1024
+        loc = fl.astype(np.int64)
+        off = np.rint((src - fl) * np.float32(n)).astype(np.int64)
+        w = np.stack([tab[off * 2 + 1], tab[off * 2], tab[(n - off) * 2], tab[(n - off) * 2 + 1]], 1)
+        raw = np.stack([loc - 1, loc, loc + 1, loc + 2], 1)
+        idx = np.clip(raw, 0, n_in - 1)
+        w = np.where(idx == raw, w, np.float32(0)).astype(np.float32)
+        s = w.sum(1, dtype=np.float32)
+        ok = np.abs(s) >= 1000.0 * np.finfo(np.float32).tiny
+        w = np.where(ok[:, None], w * (np.float32(1) / np.where(ok, s, np.float32(1)))[:, None], w).astype(np.float32)
+        return idx.astype(np.int32), w
+    raise ValueError("resize method %r" % (method,))
+
+
+def _resize_tables(device, n_in, n_out, method):
+    def build():
+        idx, w = resize_axis_table(n_in, n_out, method)
+        return (torch.from_numpy(np.ascontiguousarray(idx)).to(device), torch.from_numpy(np.ascontiguousarray(w)).to(device))
+    return _cached(("resize", str(device), n_in, n_out, method), build)
+
+
+def resize(x, out_hw, method, alpha=1.0, out=None, accumulate=False):
+    _chk(x, "x")
+    x = x.contiguous()
+    B, C, ih, iw = x.shape
+    oh, ow = int(out_hw[0]), int(out_hw[1])
+    iy, wy = _resize_tables(x.device, ih, oh, method)
+    ix, wx = _resize_tables(x.device, iw, ow, method)
+    if out is None:
+        out = torch.empty((B, C, oh, ow), device=x.device, dtype=torch.float32)
+        accumulate = False
+    out_bs = _nchw_bstride(out, "out")
+    check(lib.pcnn_resize_f32(_p(x), _p(iy), _p(wy), _p(ix), _p(wx), iy.shape[1], _p(out), B, C, ih, iw, oh, ow,
+                              float(alpha), int(bool(accumulate)), out_bs, _stream()), "resize")
+    return out
+
+
+def split_indices(n, sections):
+    """poisson_CNN/dataset/utils/split_indices.py:4-26 (numpy.array_split boundaries)."""
+    per, extra = n // sections, n % sections
+    return np.cumsum([0] + [per + 1] * extra + [per] * (sections - extra))
+
+
+def spp_boxes(levels, H, W, ndims):
+    """Bin boxes (y0,y1,x0,x1) in the order SpatialPyramidPool.call emits them (meshgrid 'ij')."""
+    boxes = []
+    for lv in levels:
+        if isinstance(lv, int):
+            lv = [lv] * ndims
+        elif len(lv) == 1:
+            lv = [lv[0]] * ndims
+        elif len(lv) != ndims:
+            raise ValueError("Each SPP level must have a pool size with ndims or 1 element(s). Got " + str(len(lv)))
+        if ndims == 1:
+            ex = split_indices(W, lv[0])
+            boxes += [(0, H, int(ex[i]), int(ex[i + 1])) for i in range(lv[0])]
+        else:
+            ey, ex = split_indices(H, lv[0]), split_indices(W, lv[1])
+            boxes += [(int(ey[i]), int(ey[i + 1]), int(ex[j]), int(ex[j + 1])) for i in range(lv[0]) for j in range(lv[1])]
+    return np.asarray(boxes, dtype=np.int32)
+
+
+def spatial_pyramid_pool(x, levels, mode, ndims=2):
+    """x [B,C,H,W] (ndims=2) or [B,C,n] (ndims=1) -> [B, sum(bins)]."""
+    _chk(x, "x")
+    if ndims == 1:
+        x = x.unsqueeze(2)
+    x = x.contiguous()
+    B, C, H, W = x.shape
+    key = ("spp", str(x.device), repr(levels), H, W, ndims)
+    boxes = _cached(key, lambda: torch.from_numpy(spp_boxes(levels, H, W, ndims)).to(x.device))
+    out = torch.empty((B, boxes.shape[0]), device=x.device, dtype=torch.float32)
+    check(lib.pcnn_spp_f32(_p(x), _p(boxes), _p(out), B, C, H, W, boxes.shape[0], int(mode), _stream()), "spp")
+    return out
+
+
+def dense(x, kernel, bias, act=ACT_LINEAR):
+    _chk(x, "x"); _chk(kernel, "kernel")
+    x = x.contiguous()
+    B, nin = x.shape
+    if kernel.shape[0] != nin:
+        raise ValueError("dense: kernel expects %d inputs, got %d" % (kernel.shape[0], nin))
+    y = torch.empty((B, kernel.shape[1]), device=x.device, dtype=torch.float32)
+    check(lib.pcnn_dense_f32(_p(x), _p(kernel.contiguous()), _p(bias), _p(y), B, nin, kernel.shape[1], int(act), _stream()), "dense")
+    return y
+
+
+def maxabs(x):
+    """max |x| per sample -> [B]."""
+    _chk(x, "x")
+    x = x.contiguous()
+    B = x.shape[0]
+    out = torch.empty((B,), device=x.device, dtype=torch.float32)
+    check(lib.pcnn_maxabs_f32(_p(x), _p(out), B, x.numel() // B, _stream()), "maxabs")
+    return out
+
+
+def scale_inv(x, m, out=None):
+    """x * (1/m[b]) per sample (set_max_magnitude with max_magnitude 1.0)."""
+    _chk(x, "x"); _chk(m, "m")
+    x = x.contiguous()
+    y = torch.empty_like(x) if out is None else out
+    if not y.is_contiguous() or y.shape != x.shape:
+        raise ValueError("scale_inv: out must be contiguous and shaped like x")
+    B = x.shape[0]
+    check(lib.pcnn_scale_inv_f32(_p(x), _p(m), _p(y), B, x.numel() // B, _stream()), "scale_inv")
+    return y
+
+
+def tf_linspace01(n):
+    """tf.linspace(0., 1., n) in float32: start + i*step, last element := stop."""
+    if n == 1:
+        return np.zeros(1, np.float32)
+    step = np.float32(1.0) / np.float32(n - 1)
+    v = np.arange(n, dtype=np.float32) * step
+    v[-1] = np.float32(1.0)
+    return v
+
+
+def position_table(device, n):
+    """cos(pi * linspace(0,1,n)), float32 (generate_position_embeddings)."""
+    return _cached(("pos", str(device), n),
+                   lambda: torch.from_numpy(np.cos(np.float32(math.pi) * tf_linspace01(n)).astype(np.float32)).to(device))
+
+
+def sinh_basis_table(device, n_modes, x_res):
+    """build_series_x_dir_components (poisson_CNN/models/Dirichlet_BC_NN_Legacy.py:106-112), float32."""
+    def build():
+        xbar = tf_linspace01(x_res)
+        modes = np.arange(1, n_modes + 1, dtype=np.float32)
+        arg = modes[:, None] * (np.float32(math.pi) * (xbar - np.float32(1)))[None, :]
+        s = np.sinh(arg.astype(np.float32)).astype(np.float32)
+        s = s * (np.float32(1.0) / np.abs(s).max(1, keepdims=True))
+        return torch.from_numpy(np.ascontiguousarray(s.astype(np.float32))).to(device)
+    return _cached(("sinh", str(device), n_modes, x_res), build)
+
+
+def hpnn_input(rhs):
+    _chk(rhs, "rhs")
+    rhs = rhs.contiguous()
+    B, _, H, W = rhs.shape
+    out = torch.empty((B, 3, H, W), device=rhs.device, dtype=torch.float32)
+    check(lib.pcnn_hpnn_input_f32(_p(rhs), _p(position_table(rhs.device, H)), _p(position_table(rhs.device, W)),
+                                  _p(out), B, H, W, _stream()), "hpnn_input")
+    return out
+
+
+def dbcnn_input(bc, x_res):
+    _chk(bc, "bc")
+    bc = bc.contiguous()
+    B, _, n = bc.shape
+    out = torch.empty((B, 3, n), device=bc.device, dtype=torch.float32)
+    posx0 = float(np.cos(np.float32(math.pi) * tf_linspace01(x_res)[:1])[0])
+    check(lib.pcnn_dbcnn_input_f32(_p(bc), posx0, _p(position_table(bc.device, n)), _p(out), B, n, _stream()), "dbcnn_input")
+    return out
+
+
+def dbcnn_expand(h, modew, x_res):
+    _chk(h, "h"); _chk(modew, "modew")
+    h, modew = h.contiguous(), modew.contiguous()
+    B, M, n = h.shape
+    S = sinh_basis_table(h.device, M, x_res)
+    out = torch.empty((B, M + 2, x_res, n), device=h.device, dtype=torch.float32)
+    check(lib.pcnn_dbcnn_expand_f32(_p(h), _p(S), _p(modew), _p(position_table(h.device, x_res)),
+                                    _p(position_table(h.device, n)), _p(out), B, M, x_res, n, _stream()), "dbcnn_expand")
+    return out
+
+
+def dbcnn_finalize(raw, m, bc):
+    raw, bc = raw.contiguous(), bc.contiguous()
+    B, _, xres, n = raw.shape
+    out = torch.empty_like(raw)
+    check(lib.pcnn_dbcnn_finalize_f32(_p(raw), _p(m), _p(bc), _p(out), B, xres, n, _stream()), "dbcnn_finalize")
+    return out
+
+
+def hpnn_finalize(y, s, bc_type):
+    """y [B,1,H,W] (may be channel 0 of a wider buffer); s [B] or None."""
+    ybs = _nchw_bstride(y, "y")
+    B, _, H, W = y.shape
+    out = torch.empty((B, 1, H, W), device=y.device, dtype=torch.float32)
+    check(lib.pcnn_hpnn_finalize_f32(_p(y), _p(s), _p(out), B, H, W, int(bc_type), ybs, _stream()), "hpnn_finalize")
+    return out
+
+
+def dense_input(dx, n0, n1, extra=None, normalize=False):
+    """[dx, dx*(n0-1), dx*(n1-1), extra...] -> [B, 3+nextra]; normalize divides the sizes by their max."""
+    _chk(dx, "dx")
+    dx = dx.contiguous()
+    B = dx.shape[0]
+    ne = 0 if extra is None else extra.shape[1]
+    if extra is not None:
+        extra = _chk(extra, "extra").contiguous()
+    out = torch.empty((B, 3 + ne), device=dx.device, dtype=torch.float32)
+    check(lib.pcnn_dense_input_f32(_p(dx), _p(extra), _p(out), B, int(n0), int(n1), ne, int(bool(normalize)), _stream()), "dense_input")
+    return out
+
+
+def merge(hp, L, T, R, Bt, dx, mrhs, ml, mt, mr, mb):
+    B, _, nx, ny = hp.shape
+    out = torch.empty_like(hp)
+    args = [t.contiguous() for t in (hp, L, T, R, Bt, dx, mrhs, ml, mt, mr, mb)]
+    check(lib.pcnn_merge_f32(*[_p(t) for t in args], _p(out), B, nx, ny, _stream()), "merge")
+    return out
+
+
+def laplacian_residual(rhs, sol, grid_spacings, stencil=3, rhs_maxabs=None):
+    """Per-sample sum of squared residuals (float64) [B]."""
+    _chk(rhs, "rhs"); _chk(sol, "sol"); _chk(grid_spacings, "grid_spacings")
+    rhs, sol, gs = rhs.contiguous(), sol.contiguous(), grid_spacings.contiguous()
+    if rhs.shape != sol.shape or rhs.shape[1] != 1:
+        raise ValueError("laplacian_residual: rhs and solution must both be [B,1,H,W]")
+    B, _, H, W = rhs.shape
+    out = torch.empty((B,), device=rhs.device, dtype=torch.float64)
+    check(lib.pcnn_laplacian_residual_f32(_p(rhs), _p(sol), _p(gs), _p(rhs_maxabs), _p(out), B, H, W, int(stencil),
+                                          _stream()), "laplacian_residual")
+    return out
+
+
+def jacobi(guess, rhs, grid_spacings, n_iter):
+    cur = guess.contiguous()
+    rhs, gs = rhs.contiguous(), grid_spacings.contiguous()
+    B, _, H, W = cur.shape
+    for _ in range(n_iter):
+        nxt = torch.empty_like(cur)
+        check(lib.pcnn_jacobi_sweep_f32(_p(cur), _p(rhs), _p(gs), _p(nxt), B, H, W, _stream()), "jacobi_sweep")
+        cur = nxt
+    return cur
+
+
+def dst_solve(rhs, left, top, right, bottom, dx):
+    """DST-I direct solve of the reference's ground-truth system.  rhs [B,1,nx,ny] -> [B,1,nx,ny]."""
+    for t, nme in ((rhs, "rhs"), (left, "left"), (top, "top"), (right, "right"), (bottom, "bottom"), (dx, "dx")):
+        _chk(t, nme)
+    B, _, nx, ny = rhs.shape
+    dev = rhs.device
+
+    def sine(m):
+        def build():
+            s = torch.empty((m, m), device=dev, dtype=torch.float64)
+            check(lib.pcnn_dst_sine_matrix(_p(s), m, _stream()), "dst_sine_matrix")
+            return s
+        return _cached(("dst_sine", str(dev), m), build)
+    sx, sy = sine(nx - 2), sine(ny - 2)
+    work = torch.empty((lib.pcnn_dst_workspace_bytes(B, nx, ny) // 8,), device=dev, dtype=torch.float64)
+    out = torch.empty_like(rhs)
+    check(lib.pcnn_dst_solve(_p(rhs.contiguous()), _p(left.contiguous()), _p(top.contiguous()), _p(right.contiguous()),
+                             _p(bottom.contiguous()), _p(dx.contiguous()), _p(sx), _p(sy), _p(work), _p(out), B, nx, ny,
+                             _stream()), "dst_solve")
+    return out

@@ -1,0 +1,166 @@
+"""CPU tests of the host side: the C ABI loads and exports every symbol include/pcnn.h declares, config
+plumbing mirrors the reference helpers, weight specs, resize/SPP tables against the oracle, and
+the world_size-2 (gloo) sharding path."""
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import ROOT, pcnn_configs
+from oracle import poisson_oracle as O
+
+
+def test_cabi_exports_every_declared_symbol():
+    import ctypes
+    hdr = open(os.path.join(ROOT, "include", "pcnn.h")).read()
+    declared = set(re.findall(r"\b(pcnn_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(os.path.join(ROOT, "poisson_cnn_b200", "libpcnn.so"))
+    for name in declared:
+        assert hasattr(lib, name), name
+    from poisson_cnn_b200 import _lib
+    assert set(_lib.SIGNATURES) == declared
+    assert _lib.lib.pcnn_version() == 100
+
+
+def test_cabi_rejects_bad_arguments_without_gpu():
+    from poisson_cnn_b200 import _lib
+    # argument validation happens before any CUDA call, so it works on a CPU-only box
+    st = _lib.lib.pcnn_conv2d_f32(None, None, None, None, None, None, None, None, 1, 1, 1, 1, 1, 1, 1, 0, 0.0, 0, 0, 0, 0, None)
+    assert st == -1
+    assert b"null pointer" in _lib.lib.pcnn_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(st, "conv2d")
+
+
+def test_product_has_no_cpu_fallback():
+    from poisson_cnn_b200 import ops
+    with pytest.raises(ValueError, match="CUDA tensor"):
+        ops.conv2d(torch.zeros(1, 1, 4, 4), torch.zeros(3, 3, 1, 1))
+    # the product package must not import the oracle
+    import subprocess, sys
+    code = "import sys; import poisson_cnn_b200.models, poisson_cnn_b200.losses, poisson_cnn_b200.solvers; print(any(m.startswith('oracle') for m in sys.modules))"
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert out.stdout.strip() == "False", out.stderr
+
+
+def test_config_helpers():
+    from poisson_cnn_b200 import config as C
+    cfg = {"key1": 3, "key2": [0, 1, 2, 3, 4], "key3": [6, 7, 8, 9, 10]}
+    assert C.get_init_arguments_from_config(cfg, 2, ["key2", "key3"], ["key2p", "key3p"]) == {"key1": 3, "key2p": 2, "key3p": 8}
+    conv = C.convert_tf_object_names({"a": "tf.nn.leaky_relu", "b": ["tf.nn.tanh", "tanh", 3], "c": {"d": "linear"}})
+    assert C.activation_enum(conv["a"]) == C.ACT_LEAKY_RELU and C.activation_enum(conv["b"][0]) == C.ACT_TANH
+    assert conv["b"][1] == "tanh" and conv["c"]["d"] == "linear"
+    with pytest.raises(ValueError):
+        C.convert_tf_object_names("tf.nn.relu")
+    with pytest.raises(ValueError):
+        C.activation_enum("tf.nn.softmax")
+    assert C.process_normalizations(None) == {"rhs_max_magnitude": False}
+    assert C.process_normalizations({"rhs_max_magnitude": True})["rhs_max_magnitude"] == 1.0
+    assert C.process_output_scaling_modes({"soln_max_magnitude": True})["max_domain_size_squared"] is False
+    # float64 truncation of int((N/ds)*us): exact for the shipped factors, off by one for ds=50 at e.g. N=29
+    for n in range(1, 600):
+        for ds in (2, 3, 4, 8, 16, 32, 64, 128):
+            assert C.bottleneck_output_size(n, ds, ds) == n
+    assert C.bottleneck_output_size(29, 50, 50) == 28
+
+
+def test_model_construction_errors_and_param_counts():
+    from poisson_cnn_b200 import models, convert_tf_object_names
+    hp, db = pcnn_configs()
+    hp, db = convert_tf_object_names(hp), convert_tf_object_names(db)
+    h = models.Homogeneous_Poisson_NN_Legacy(**hp)
+    d = models.Dirichlet_BC_NN_Legacy_2(**db)
+    p = models.Poisson_CNN_Legacy(h, d)
+    assert (h.count_params(), d.count_params(), p.count_params()) == (5559108, 483878, 6042986)
+    assert p.data_format == "channels_first" and p.hpnn is h and p.dbcnn is d
+    assert [b.downsampling_factor for b in h.bottleneck_deconv_blocks] == [16, 8, 4, 3, 2]
+    assert [b.downsampling_factor for b in h.bottleneck_multilinear_blocks] == [128, 64, 32]
+    for missing in ("pre_bottleneck_convolutions_config", "bottleneck_deconv_config", "final_convolutions_config"):
+        with pytest.raises(ValueError):
+            models.Homogeneous_Poisson_NN_Legacy(**{k: v for k, v in hp.items() if k != missing})
+    with pytest.raises(ValueError):
+        models.Homogeneous_Poisson_NN_Legacy(**dict(hp, bc_type="robin"))
+    for missing in ("boundary_conv_config", "spp_config", "domain_info_mlp_config", "final_convolutions_config"):
+        with pytest.raises(ValueError):
+            models.Dirichlet_BC_NN_Legacy_2(**{k: v for k, v in db.items() if k != missing})
+    with pytest.raises(RuntimeError):
+        h.w("pre_bottleneck/0/kernel")       # no weights loaded yet
+
+
+def test_weights_npz_roundtrip(tmp_path):
+    from poisson_cnn_b200 import weights as W
+    hp, db = pcnn_configs()
+    sm = W.dbcnn_weight_specs(db, "dbcnn/")
+    w = W.synthetic_weights(sm, seed=3)
+    assert set(w) == set(sm[0]) and all(w[k].shape == tuple(sm[0][k]) for k in w)
+    w2 = W.synthetic_weights(sm, seed=3)
+    assert all(np.array_equal(w[k], w2[k]) for k in w)              # deterministic
+    path = str(tmp_path / "w.npz")
+    W.save_npz(path, w)
+    back = W.load_npz(path)
+    assert set(back) == set(w) and all(np.array_equal(back[k], w[k]) for k in w)
+
+
+def test_host_tables_match_oracle():
+    from poisson_cnn_b200 import ops
+    from poisson_cnn_b200.config import resize_enum
+    for n_in, n_out in ((2, 256), (4, 200), (8, 300), (5, 5), (7, 3)):
+        for m in ("nearest", "bilinear", "bicubic"):
+            i0, w0 = O.resize_axis_weights(n_in, n_out, m)
+            i1, w1 = ops.resize_axis_table(n_in, n_out, resize_enum(m))
+            np.testing.assert_array_equal(i0, i1)
+            np.testing.assert_allclose(w0, w1, atol=1e-7)
+    b = ops.spp_boxes([[2, 2], 3, 5], 10, 13, 2)
+    assert b.shape == (38, 4) and tuple(b[0]) == (0, 5, 0, 7) and tuple(b[3]) == (5, 10, 7, 13)
+    b1 = ops.spp_boxes([2, 3, 4, 5, 8, 11, 15, 30, 45], 1, 229, 1)
+    assert b1.shape == (123, 4) and tuple(b1[0]) == (0, 1, 0, 115)
+    np.testing.assert_allclose(ops.tf_linspace01(7), O.tf_linspace01(7, torch.float32).numpy(), atol=0)
+
+
+def test_shard_bounds_cover_batch():
+    from poisson_cnn_b200.sharding import shard_bounds, bucket_by_shape
+    for n in (1, 7, 16, 128, 256):
+        for ws in (1, 2, 4, 8):
+            spans = [shard_bounds(n, ws, r) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(ws - 1))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+    assert bucket_by_shape([(384, 128), (512, 256), (384, 128)]) == {(384, 128): [0, 2], (512, 256): [1]}
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from poisson_cnn_b200.sharding import init_from_env, shard_problem, ErrorStats
+    from poisson_cnn_b200.synthetic import make_problem
+    init_from_env("gloo")
+    full = make_problem(5, 12, 9, seed=9)
+    mine = shard_problem(full, world, rank)
+    noise = torch.full_like(mine["rhs"], 1e-3 * (rank + 1))
+    st = ErrorStats().update(mine["rhs"] + noise, mine["rhs"]).combine().result()
+    q.put((rank, mine["rhs"].shape[0], st))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_sharding_and_stats():
+    import torch.multiprocessing as mp
+    from poisson_cnn_b200.synthetic import make_problem
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(60) for p in procs]
+    assert [r[1] for r in res] == [3, 2]                       # 5 samples -> 3 + 2
+    full = make_problem(5, 12, 9, seed=9)["rhs"].double()
+    sq_err = 3 * 108 * 1e-6 + 2 * 108 * 4e-6
+    expect = (sq_err / float(full.pow(2).sum())) ** 0.5
+    for r in res:                                              # both ranks hold the combined statistics
+        assert r[2]["samples"] == 5
+        assert abs(r[2]["rel_l2"] - expect) < 1e-3 * expect
+        assert abs(r[2]["max_abs_err"] - 2e-3) < 1e-6
