@@ -171,6 +171,35 @@ int pcnn_dst_solve(const float* rhs, const float* left, const float* top, const 
                    const float* bottom, const float* dx, const double* sx, const double* sy,
                    double* work, float* out, int B, int nx, int ny, void* stream);
 
+/* ---- tensor-core path (tcgen05 / TMEM / TMA bulk copies), csrc/conv_tc.cu ---------------------
+ * Activations live in the "BLK8" layout: fp16 [B][Cpad/8][H+14][W+14][8] with Cpad = round_up(C,16)
+ * and a 7-pixel halo materialised in memory (zero = CONSTANT padding; pcnn_blk8_halo_fill mirrors it
+ * for SYMMETRIC).  pcnn_blk8_bytes gives the allocation size (incl. slack read by partial tiles);
+ * buffers must start zeroed, the kernels never write the halo or the channel padding. */
+size_t pcnn_blk8_bytes(int B, int C, int H, int W);
+/* NCHW fp32 [B,C,H,W] (batch stride in_bstride) -> channels [c_offset, c_offset+C) of a BLK8 buffer
+ * holding c_total channels (c_offset multiple of 8: this is how concat is assembled in place). */
+int pcnn_to_blk8(const float* in, void* out, int B, int C, int H, int W, int c_total, int c_offset,
+                 int64_t in_bstride, void* stream);
+int pcnn_from_blk8(const void* in, float* out, int B, int C, int H, int W, int c_total, int c_offset,
+                   int64_t out_bstride, void* stream);
+/* tf.pad ring of width pad (<= 7) around the interior: mode PCNN_PAD_CONSTANT writes zeros,
+ * PCNN_PAD_SYMMETRIC mirrors (utils/apply_advanced_padding_and_call_conv_layer.py:18). */
+int pcnn_blk8_halo_fill(void* buf, int B, int C, int H, int W, int pad, int mode, void* stream);
+/* Keras kernel [k,k,Cin,Cout] fp32 -> fp16 operand image of the row-group GEMM:
+ * [ceil(Cin/16)][k][2][(k+6)*32][8] (see conv_tc.cu).  Done once per layer at load time. */
+size_t pcnn_conv_tc_packed_weight_bytes(int kh, int kw, int Cin);
+int pcnn_conv_tc_pack_weights(const float* kernel, void* packed, int kh, int kw, int Cin, int Cout,
+                              void* stream);
+/* Same operator as pcnn_conv2d_f32 (pad + VALID conv + bias + act [+BN] [+residual] [*out_scale]) on
+ * tcgen05 tensor cores: FP16 operands, FP32 accumulation in TMEM.  in/out/residual are BLK8 buffers
+ * with Cin_total / Cout_total / Cres_total channels; the padding mode is whatever the halo of `in`
+ * holds.  Odd k <= 15, Cout <= 32.  num_sms: CTAs of the persistent grid (<= 0: 148). */
+int pcnn_conv2d_tc(const void* in, const void* wpack, const float* bias, const float* bn_scale,
+                   const float* bn_shift, const void* residual, const float* out_scale, void* out,
+                   int B, int Cin_total, int Cout, int Cout_total, int Cres_total, int H, int W, int k,
+                   int act, int num_sms, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,517 @@
+// Tensor-core convolution for sm_100a: tcgen05.mma (kind::f16, FP16 operands, FP32 accumulation in
+// TMEM), operands staged in shared memory by the TMA bulk-copy engine (cp.async.bulk + mbarrier),
+// warp-specialised persistent CTAs, fused epilogue (bias, activation, BatchNorm affine, residual,
+// per-(sample,channel) scale) that writes the next layer's operand layout directly.
+//
+// ---------------------------------------------------------------------------------------------
+// Formulation ("row-group transposed implicit GEMM")
+//   The layers have only <= 32 output channels, so the usual pixels-as-M / Cout-as-N GEMM would be
+//   bound by shared-memory operand bandwidth (N = 32 -> A re-read every 16 cycles).  Instead the
+//   WEIGHTS are the M operand and the PIXELS the N operand:
+//       D[(r, co), x] = sum_{rho, dx, ci} A_{rho,dx}[(r, co), ci] * X[y0 + rho - pad, x + dx - pad, ci]
+//   with M = 128 = 4 output rows r x 32 channels co, N = up to 256 pixels of one image row segment,
+//   K = 16 input channels per MMA.  For input row rho (0 <= rho < kh+3) and column tap dx the A tile
+//   is  A[(r,co)] = W[dy = rho - r, dx, ci, co]  (zero when dy is outside [0,kh)).  With the M rows
+//   ordered m = (3-r)*32 + co and the weights packed per (ci-chunk, dx) as Wd[z = dy+3][co] with 3
+//   zero z-rows on both ends, that A tile is the CONTIGUOUS window of Wd starting at row rho*32, so
+//   one packed array per (chunk, dx) serves all kh+3 input rows by moving the descriptor start
+//   address.  Cost: (kh+3)/kh more MMAs than the minimum, in exchange for a 128x256x16 MMA shape
+//   (96 B/cycle of shared-memory operand traffic, inside the 128 B/cycle budget), no im2col, no
+//   epilogue reduction, and an accumulator whose lanes are (row, channel) and columns are pixels.
+//
+// Data layout ("BLK8"): activations are fp16 [B][C/8][H+14][W+14][8]: channel planes of 8, a 7-pixel
+//   halo materialised in global memory (zero for CONSTANT padding, mirrored by pcnn_blk8_halo_fill
+//   for SYMMETRIC), 16 bytes per pixel per plane.  A row segment of one plane is contiguous, so every
+//   operand load is a plain 1-D bulk copy and the kernel is padding-agnostic.  In shared memory the
+//   same bytes are a K-major no-swizzle UMMA operand: rows (pixels) 16 B apart, 8-row core matrices
+//   128 B apart (SBO), the two 8-channel K halves one plane apart (LBO); a column tap is a +16 B
+//   start-address shift.
+//
+// Warp roles (224 threads): 0 = input-row producer, 1 = weight producer, 2 = MMA issuer (+TMEM
+//   alloc), 3..6 = epilogue (TMEM lane quarter = warp % 4).  Two 256-column accumulators in TMEM let
+//   the epilogue of tile t overlap the MMAs of tile t+1.
+#include <cuda_fp16.h>
+
+#include "pcnn_common.cuh"
+
+namespace pcnn {
+namespace tc {
+
+constexpr int HALO = 7;            // materialised halo of the BLK8 layout (kernel sizes up to 15)
+constexpr int ROWS_PER_TILE = 4;   // output rows per tile (M = 4 x 32)
+constexpr int COUT_PAD = 32;
+constexpr int NUM_THREADS = 224;
+constexpr int ZPAD = ROWS_PER_TILE - 1;   // zero z-rows on each side of the packed weights
+constexpr unsigned long long SPIN_LIMIT_NS = 4000000000ull;   // a stuck pipeline traps instead of hanging the GPU
+
+struct Params {
+    const __half* in;        // BLK8 [B][c8_in][Hp][P][8]
+    const __half* wpack;     // [C16][kw][2][(kh+6)*32][8]
+    const float* bias;       // [32] (zero padded) or null
+    const float* bn_scale;   // [32] or null
+    const float* bn_shift;
+    const __half* residual;  // BLK8 like out, or null
+    const float* out_scale;  // [B][Cout] or null
+    __half* out;             // BLK8 [B][c8_out][Hp][P][8]
+    int B, H, W, Hp, P;
+    int c8_in, c8_out, c8_res;
+    int c16;                 // input-channel chunks of 16
+    int cout;                // true output channels
+    int kh, kw, pad;
+    int act;
+    int n_tile;              // MMA N (multiple of 16, <= 256)
+    int tiles_x, tiles_y, num_tiles;
+    int row_slots;           // ring of input-row slots (>= kh+3)
+    int w_stages;
+    uint32_t rowplane_bytes; // bytes of one plane of one row window in smem (multiple of 128)
+    uint32_t row_copy_bytes; // (n_tile + kw - 1) * 16
+    uint32_t wstage_bytes;   // 2 * (kh+6) * 512
+    uint32_t idesc;
+};
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (!mbar_try_wait(bar, parity)) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > SPIN_LIMIT_NS) {
+            printf("pcnn conv_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    // carve-up: [row slots][weight stages][epilogue staging 4 x 2176 B][barriers][tmem ptr]
+    uint8_t* s_rows = smem;
+    const uint32_t row_slot_bytes = 2 * p.rowplane_bytes;
+    uint8_t* s_w = s_rows + (size_t)p.row_slots * row_slot_bytes;
+    uint8_t* s_stage = s_w + (size_t)p.w_stages * p.wstage_bytes;
+    constexpr int STAGE_PLANE = 32 * 16 + 16;   // 32 px x 16 B, +16 B so the 4 planes hit different banks
+    constexpr int STAGE_WARP = 4 * STAGE_PLANE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + 4 * STAGE_WARP);
+    uint64_t* row_full = bars;
+    uint64_t* row_empty = row_full + p.row_slots;
+    uint64_t* w_full = row_empty + p.row_slots;
+    uint64_t* w_empty = w_full + p.w_stages;
+    uint64_t* acc_full = w_empty + p.w_stages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int R = p.kh + ZPAD;   // input rows per tile
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.row_slots; ++i) { mbar_init(row_full + i, 1); mbar_init(row_empty + i, 1); }
+        for (int i = 0; i < p.w_stages; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {   // TMEM: 512 columns = two 256-column fp32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ================= input-row producer =================
+        if (lane == 0) {
+            uint32_t g = 0;   // running row counter -> ring slot / phase
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                const int tx = t % p.tiles_x;
+                const int ty = (t / p.tiles_x) % p.tiles_y;
+                const int b = t / (p.tiles_x * p.tiles_y);
+                const int x0 = tx * p.n_tile, y0 = ty * ROWS_PER_TILE;
+                const int col0 = x0 + HALO - p.pad;
+                for (int c = 0; c < p.c16; ++c) {
+                    for (int rho = 0; rho < R; ++rho, ++g) {
+                        const uint32_t slot = g % p.row_slots, ph = (g / p.row_slots) & 1;
+                        mbar_wait(row_empty + slot, ph ^ 1);
+                        mbar_expect_tx(row_full + slot, 2 * p.row_copy_bytes);
+                        const int prow = min(y0 + rho + HALO - p.pad, p.Hp - 1);
+                        const uint32_t dst = smem_u32(s_rows + (size_t)slot * row_slot_bytes);
+#pragma unroll
+                        for (int pl = 0; pl < 2; ++pl) {
+                            const __half* src = p.in + ((((size_t)b * p.c8_in + (2 * c + pl)) * p.Hp + prow) * p.P + col0) * 8;
+                            bulk_copy_g2s(dst + pl * p.rowplane_bytes, src, p.row_copy_bytes, row_full + slot);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= weight producer =================
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                for (int c = 0; c < p.c16; ++c) {
+                    for (int dx = 0; dx < p.kw; ++dx, ++g) {
+                        const uint32_t st = g % p.w_stages, ph = (g / p.w_stages) & 1;
+                        mbar_wait(w_empty + st, ph ^ 1);
+                        mbar_expect_tx(w_full + st, p.wstage_bytes);
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) + ((size_t)c * p.kw + dx) * p.wstage_bytes;
+                        bulk_copy_g2s(smem_u32(s_w + (size_t)st * p.wstage_bytes), src, p.wstage_bytes, w_full + st);
+                    }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t grow = 0, gw = 0, it = 0;
+            const uint32_t a_lbo = (uint32_t)(p.kh + 2 * ZPAD) * 512u;   // K-half (plane) stride of the packed weights
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+                const uint32_t acc = it & 1, acc_ph = (it >> 1) & 1;
+                mbar_wait(acc_empty + acc, acc_ph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                uint32_t first = 1;
+                for (int c = 0; c < p.c16; ++c, grow += R) {
+                    for (int dx = 0; dx < p.kw; ++dx, ++gw) {
+                        const uint32_t st = gw % p.w_stages, wph = (gw / p.w_stages) & 1;
+                        mbar_wait(w_full + st, wph);
+                        tc_fence_after();
+                        const uint32_t wbase = smem_u32(s_w + (size_t)st * p.wstage_bytes);
+                        for (int rho = 0; rho < R; ++rho) {
+                            const uint32_t g = grow + rho;
+                            const uint32_t slot = g % p.row_slots, rph = (g / p.row_slots) & 1;
+                            if (dx == 0) { mbar_wait(row_full + slot, rph); tc_fence_after(); }
+                            const uint32_t rbase = smem_u32(s_rows + (size_t)slot * row_slot_bytes);
+                            const uint64_t a_desc = make_desc(wbase + rho * 512u, a_lbo, 128u);
+                            const uint64_t b_desc = make_desc(rbase + dx * 16u, p.rowplane_bytes, 128u);
+                            tc_mma_f16(d_tmem, a_desc, b_desc, p.idesc, first ? 0u : 1u);
+                            first = 0;
+                            if (dx == p.kw - 1) tc_commit(row_empty + slot);   // row no longer needed
+                        }
+                        tc_commit(w_empty + st);
+                    }
+                }
+                tc_commit(acc_full + acc);
+            }
+        }
+    } else {
+        // ================= epilogue (warps 3..6) =================
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int r = (ROWS_PER_TILE - 1) - q;  // output row within the tile (M rows are (3-r)*32 + co)
+        const int co = lane;
+        uint8_t* stage = s_stage + (warp - 3) * STAGE_WARP;
+        const float bias = (p.bias && co < p.cout) ? p.bias[co] : 0.f;
+        const float bns = (p.bn_scale && co < p.cout) ? p.bn_scale[co] : 1.f;
+        const float bnt = (p.bn_shift && co < p.cout) ? p.bn_shift[co] : 0.f;
+        const int planes_out = (p.cout + 7) / 8;
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+            const int tx = t % p.tiles_x;
+            const int ty = (t / p.tiles_x) % p.tiles_y;
+            const int b = t / (p.tiles_x * p.tiles_y);
+            const int x0 = tx * p.n_tile, y = ty * ROWS_PER_TILE + r;
+            const uint32_t acc = it & 1, acc_ph = (it >> 1) & 1;
+            const float osc = (p.out_scale && co < p.cout) ? p.out_scale[(size_t)b * p.cout + co] : 1.f;
+            mbar_wait(acc_full + acc, acc_ph);
+            tc_fence_after();
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
+            for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr0 + c0, v);
+                if (y < p.H) {
+                    // bias -> activation -> BN affine -> per-(b,c) scale, then fp16 into the transpose buffer
+                    __half* srow = reinterpret_cast<__half*>(stage + (co >> 3) * STAGE_PLANE) + (co & 7);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float f = __uint_as_float(v[j]) + bias;
+                        f = apply_act(f, p.act);
+                        f = fmaf(f, bns, bnt);
+                        f *= osc;
+                        if (co >= p.cout) f = 0.f;
+                        srow[j * 8] = __float2half_rn(f);
+                    }
+                    __syncwarp();
+                    const int x = x0 + c0 + lane;
+                    for (int pl = 0; pl < planes_out; ++pl) {
+                        uint4 val = *reinterpret_cast<const uint4*>(stage + pl * STAGE_PLANE + lane * 16);
+                        if (x < p.W && c0 + lane < p.n_tile) {
+                            const size_t off = ((((size_t)b * p.c8_out + pl) * p.Hp + (y + HALO)) * p.P + (x + HALO)) * 8;
+                            if (p.residual) {
+                                const size_t roff = ((((size_t)b * p.c8_res + pl) * p.Hp + (y + HALO)) * p.P + (x + HALO)) * 8;
+                                const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + roff);
+                                const __half2* a2 = reinterpret_cast<const __half2*>(&val);
+                                const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
+                                uint4 o;
+                                __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 fa = __half22float2(a2[e]), fr = __half22float2(r2[e]);
+                                    o2[e] = __floats2half2_rn(fa.x + fr.x, fa.y + fr.y);
+                                }
+                                val = o;
+                            }
+                            *reinterpret_cast<uint4*>(p.out + off) = val;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(acc_empty + acc);
+        }
+    }
+
+    // teardown: everyone done with TMEM before it is released
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// ---------------------------------------------------------------- layout / packing kernels
+// Keras kernel [kh][kw][Cin][Cout] fp32 -> packed fp16 [C16][kw][2][(kh+6)*32][8]
+__global__ void pack_weights_kernel(const float* __restrict__ k, __half* __restrict__ out, int kh, int kw,
+                                    int Cin, int Cout, int c16, long long total) {
+    const int Z = kh + 2 * ZPAD;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int e = idx & 7;
+        long long t = idx >> 3;
+        const int co = t % COUT_PAD; t /= COUT_PAD;
+        const int z = t % Z; t /= Z;
+        const int pl = t & 1; t >>= 1;
+        const int dx = t % kw;
+        const int c = t / kw;
+        const int ci = c * 16 + pl * 8 + e, dy = z - ZPAD;
+        float v = 0.f;
+        if (dy >= 0 && dy < kh && ci < Cin && co < Cout) v = k[(((long long)dy * kw + dx) * Cin + ci) * Cout + co];
+        out[idx] = __float2half_rn(v);
+    }
+}
+
+// NCHW fp32 -> BLK8 fp16 interior (planes [plane0, plane0 + ceil(C/8)))
+__global__ void to_blk8_kernel(const float* __restrict__ in, __half* __restrict__ out, int C, int H, int W,
+                               int Hp, int P, int c8_total, int plane0, long long in_bstride, long long total) {
+    const int np = (C + 7) / 8;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = idx % W;
+        long long t = idx / W;
+        const int y = t % H; t /= H;
+        const int pl = t % np;
+        const long long b = t / np;
+        __align__(16) __half h[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = pl * 8 + e;
+            h[e] = __float2half_rn(c < C ? __ldg(in + b * in_bstride + ((long long)c * H + y) * W + x) : 0.f);
+        }
+        const size_t off = ((((size_t)b * c8_total + plane0 + pl) * Hp + (y + HALO)) * P + (x + HALO)) * 8;
+        *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(h);
+    }
+}
+
+// BLK8 fp16 -> NCHW fp32
+__global__ void from_blk8_kernel(const __half* __restrict__ in, float* __restrict__ out, int C, int H, int W,
+                                 int Hp, int P, int c8_total, int plane0, long long out_bstride, long long total) {
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = idx % W;
+        long long t = idx / W;
+        const int y = t % H; t /= H;
+        const int c = t % C;
+        const long long b = t / C;
+        const size_t off = ((((size_t)b * c8_total + plane0 + (c >> 3)) * Hp + (y + HALO)) * P + (x + HALO)) * 8 + (c & 7);
+        out[b * out_bstride + ((long long)c * H + y) * W + x] = __half2float(in[off]);
+    }
+}
+
+// halo fill of a BLK8 buffer: pad-wide ring around the interior, zero or SYMMETRIC mirror
+__global__ void blk8_halo_fill_kernel(__half* __restrict__ buf, int H, int W, int Hp, int P, int planes_total,
+                                      int pad, int mode, long long total) {
+    const int hw = W + 2 * pad, hh = H + 2 * pad;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int xx = idx % hw;
+        long long t = idx / hw;
+        const int yy = t % hh;
+        const long long bp = t / hh;   // (b, plane) flattened
+        const int y = yy - pad, x = xx - pad;
+        if (y >= 0 && y < H && x >= 0 && x < W) continue;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (mode == PCNN_PAD_SYMMETRIC) {
+            const int sy = pad_src_index(y, H, PCNN_PAD_SYMMETRIC), sx = pad_src_index(x, W, PCNN_PAD_SYMMETRIC);
+            v = *reinterpret_cast<const uint4*>(buf + (((size_t)bp * Hp + (sy + HALO)) * P + (sx + HALO)) * 8);
+        }
+        *reinterpret_cast<uint4*>(buf + (((size_t)bp * Hp + (y + HALO)) * P + (x + HALO)) * 8) = v;
+    }
+}
+
+static inline int grid_for(long long total, int block = 256, int cap = 148 * 16) {
+    long long g = (total + block - 1) / block;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace tc
+}  // namespace pcnn
+
+using namespace pcnn;
+using namespace pcnn::tc;
+
+extern "C" size_t pcnn_blk8_bytes(int B, int C, int H, int W) {
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+    const size_t planes = (size_t)((C + 15) / 16) * 2;
+    // + slack: the last tile's row window may run a few hundred pixels past the final row
+    return ((size_t)B * planes * (H + 2 * HALO) * (W + 2 * HALO) * 8 + 8192) * sizeof(__half);
+}
+
+extern "C" size_t pcnn_conv_tc_packed_weight_bytes(int kh, int kw, int Cin) {
+    return (size_t)((Cin + 15) / 16) * kw * 2 * (kh + 2 * ZPAD) * COUT_PAD * 8 * sizeof(__half);
+}
+
+extern "C" int pcnn_conv_tc_pack_weights(const float* kernel, void* packed, int kh, int kw, int Cin, int Cout, void* stream) {
+    PCNN_CHECK_ARG(kernel && packed, "conv_tc_pack_weights: null pointer");
+    PCNN_CHECK_ARG(kh == kw && (kh & 1) && kh >= 1 && kh <= 2 * HALO + 1, "conv_tc: kernel %dx%d not supported (odd, square, <= 15)", kh, kw);
+    PCNN_CHECK_ARG(Cout >= 1 && Cout <= COUT_PAD && Cin >= 1, "conv_tc: Cout %d not in [1,32]", Cout);
+    const int c16 = (Cin + 15) / 16;
+    const long long total = (long long)c16 * kw * 2 * (kh + 2 * ZPAD) * COUT_PAD * 8;
+    pack_weights_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(kernel, (__half*)packed, kh, kw, Cin, Cout, c16, total);
+    PCNN_CHECK_LAUNCH();
+    return PCNN_OK;
+}
+
+extern "C" int pcnn_to_blk8(const float* in, void* out, int B, int C, int H, int W, int c_total, int c_offset,
+                            int64_t in_bstride, void* stream) {
+    PCNN_CHECK_ARG(in && out && B > 0 && C > 0 && (c_offset % 8) == 0 && c_offset + C <= ((c_total + 15) / 16) * 16, "to_blk8: bad argument");
+    const int c8_total = ((c_total + 15) / 16) * 2;
+    const long long total = (long long)B * ((C + 7) / 8) * H * W;
+    to_blk8_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(in, (__half*)out, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, in_bstride, total);
+    PCNN_CHECK_LAUNCH();
+    return PCNN_OK;
+}
+
+extern "C" int pcnn_from_blk8(const void* in, float* out, int B, int C, int H, int W, int c_total, int c_offset,
+                              int64_t out_bstride, void* stream) {
+    PCNN_CHECK_ARG(in && out && B > 0 && C > 0 && (c_offset % 8) == 0, "from_blk8: bad argument");
+    const int c8_total = ((c_total + 15) / 16) * 2;
+    const long long total = (long long)B * C * H * W;
+    from_blk8_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const __half*)in, out, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, out_bstride, total);
+    PCNN_CHECK_LAUNCH();
+    return PCNN_OK;
+}
+
+extern "C" int pcnn_blk8_halo_fill(void* buf, int B, int C, int H, int W, int pad, int mode, void* stream) {
+    PCNN_CHECK_ARG(buf && B > 0 && C > 0 && pad >= 0 && pad <= HALO, "blk8_halo_fill: bad argument");
+    PCNN_CHECK_ARG(mode == PCNN_PAD_CONSTANT || mode == PCNN_PAD_SYMMETRIC, "blk8_halo_fill: mode must be CONSTANT(0) or SYMMETRIC");
+    if (mode == PCNN_PAD_SYMMETRIC) PCNN_CHECK_ARG(pad <= H && pad <= W, "blk8_halo_fill: SYMMETRIC pad %d larger than the tensor (%d,%d)", pad, H, W);
+    if (pad == 0) return PCNN_OK;
+    const int planes = ((C + 15) / 16) * 2;
+    const long long total = (long long)B * planes * (H + 2 * pad) * (W + 2 * pad);
+    blk8_halo_fill_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((__half*)buf, H, W, H + 2 * HALO, W + 2 * HALO, planes, pad, mode, total);
+    PCNN_CHECK_LAUNCH();
+    return PCNN_OK;
+}
+
+extern "C" int pcnn_conv2d_tc(const void* in, const void* wpack, const float* bias, const float* bn_scale,
+                              const float* bn_shift, const void* residual, const float* out_scale, void* out,
+                              int B, int Cin_total, int Cout, int Cout_total, int Cres_total, int H, int W, int k,
+                              int act, int num_sms, void* stream) {
+    PCNN_CHECK_ARG(in && wpack && out, "conv2d_tc: null pointer");
+    PCNN_CHECK_ARG((k & 1) && k >= 1 && k <= 2 * HALO + 1, "conv2d_tc: kernel size %d not supported (odd, <= 15)", k);
+    PCNN_CHECK_ARG(Cout >= 1 && Cout <= COUT_PAD && Cout <= Cout_total, "conv2d_tc: Cout %d not in [1,32]", Cout);
+    PCNN_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cin_total > 0, "conv2d_tc: bad shape");
+    PCNN_CHECK_ARG((bn_scale == nullptr) == (bn_shift == nullptr), "conv2d_tc: bn_scale/bn_shift must come together");
+    Params p;
+    p.in = (const __half*)in; p.wpack = (const __half*)wpack; p.bias = bias; p.bn_scale = bn_scale; p.bn_shift = bn_shift;
+    p.residual = (const __half*)residual; p.out_scale = out_scale; p.out = (__half*)out;
+    p.B = B; p.H = H; p.W = W; p.Hp = H + 2 * HALO; p.P = W + 2 * HALO;
+    p.c16 = (Cin_total + 15) / 16;
+    p.c8_in = p.c16 * 2; p.c8_out = ((Cout_total + 15) / 16) * 2; p.c8_res = ((Cres_total + 15) / 16) * 2;
+    p.cout = Cout; p.kh = k; p.kw = k; p.pad = k / 2; p.act = act;
+    p.n_tile = W >= 256 ? 256 : ((W + 15) / 16) * 16;
+    p.tiles_x = ceil_div(W, p.n_tile); p.tiles_y = ceil_div(H, ROWS_PER_TILE);
+    p.num_tiles = B * p.tiles_x * p.tiles_y;
+    p.row_copy_bytes = (uint32_t)(p.n_tile + k - 1) * 16u;
+    p.rowplane_bytes = (p.row_copy_bytes + 127u) & ~127u;
+    p.wstage_bytes = 2u * (uint32_t)(k + 2 * ZPAD) * 512u;
+    // instruction descriptor: D=F32, A=B=F16, both K-major, N = n_tile, M = 128
+    p.idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // shared-memory plan: as many row slots as fit (>= kh+3, ideally 2x for full double buffering)
+    const size_t kMax = 227 * 1024;
+    const size_t fixed = 4 * (4 * (32 * 16 + 16)) + 1024;
+    const int R = k + ZPAD;
+    int w_stages = 3;
+    size_t avail = kMax - fixed - (size_t)w_stages * p.wstage_bytes;
+    int slots = (int)(avail / (2 * p.rowplane_bytes));
+    if (slots < R) { w_stages = 2; avail = kMax - fixed - (size_t)w_stages * p.wstage_bytes; slots = (int)(avail / (2 * p.rowplane_bytes)); }
+    PCNN_CHECK_ARG(slots >= R, "conv2d_tc: tile does not fit in shared memory (k=%d, n_tile=%d)", k, p.n_tile);
+    if (slots > 2 * R) slots = 2 * R;
+    p.row_slots = slots; p.w_stages = w_stages;
+    const size_t smem = (size_t)slots * 2 * p.rowplane_bytes + (size_t)w_stages * p.wstage_bytes + fixed;
+    PCNN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax));
+    if (num_sms <= 0) num_sms = 148;
+    const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    conv_tc_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(p);
+    PCNN_CHECK_LAUNCH();
+    return PCNN_OK;
+}

@@ -421,3 +421,110 @@ def dst_solve(rhs, left, top, right, bottom, dx):
                              _p(bottom.contiguous()), _p(dx.contiguous()), _p(sx), _p(sy), _p(work), _p(out), B, nx, ny,
                              _stream()), "dst_solve")
     return out
+
+
+# =================================================================================================
+# tensor-core path: BLK8 fp16 activations + tcgen05 convolution (csrc/conv_tc.cu)
+# =================================================================================================
+class Blk8:
+    """fp16 activation in the BLK8 layout [B][Cpad/8][H+14][W+14][8] (7-pixel halo in memory).
+    `halo` records what the halo currently holds: ("zero", 7) after allocation, or (mode, pad)."""
+
+    __slots__ = ("buf", "B", "C", "H", "W", "halo")
+
+    def __init__(self, B, C, H, W, device):
+        nbytes = lib.pcnn_blk8_bytes(B, C, H, W)
+        if nbytes == 0:
+            raise ValueError("Blk8: bad shape")
+        self.buf = torch.zeros(nbytes // 2, dtype=torch.float16, device=device)
+        self.B, self.C, self.H, self.W = B, C, H, W
+        self.halo = (PAD_CONSTANT, 7)
+
+    @property
+    def device(self):
+        return self.buf.device
+
+
+def to_blk8(x, out=None, c_total=None, c_offset=0):
+    """NCHW fp32 -> BLK8 (optionally into channels [c_offset, c_offset+C) of a wider buffer)."""
+    in_bs = _nchw_bstride(x, "x")
+    B, C, H, W = x.shape
+    if out is None:
+        out = Blk8(B, c_total or C, H, W, x.device)
+    if (out.B, out.H, out.W) != (B, H, W):
+        raise ValueError("to_blk8: destination shape mismatch")
+    check(lib.pcnn_to_blk8(_p(x), _p(out.buf), B, C, H, W, out.C, int(c_offset), in_bs, _stream()), "to_blk8")
+    return out
+
+
+def from_blk8(t, C=None, c_offset=0, out=None):
+    C = t.C if C is None else C
+    if out is None:
+        out = torch.empty((t.B, C, t.H, t.W), device=t.device, dtype=torch.float32)
+    out_bs = _nchw_bstride(out, "out")
+    check(lib.pcnn_from_blk8(_p(t.buf), _p(out), t.B, C, t.H, t.W, t.C, int(c_offset), out_bs, _stream()), "from_blk8")
+    return out
+
+
+def blk8_halo_fill(t, pad, mode):
+    """Make the halo of `t` hold tf.pad(mode) of width pad (no-op if it already does)."""
+    pad, mode = int(pad), int(mode)
+    cur_mode, cur_pad = t.halo
+    if mode == PAD_CONSTANT and cur_mode == PAD_CONSTANT:
+        return t                      # zero halo is 7 wide from allocation and never written
+    if (cur_mode, cur_pad) == (mode, pad):
+        return t
+    if mode == PAD_CONSTANT:
+        pad = 7
+    check(lib.pcnn_blk8_halo_fill(_p(t.buf), t.B, t.C, t.H, t.W, pad, mode, _stream()), "blk8_halo_fill")
+    t.halo = (mode, pad)
+    return t
+
+
+def pack_conv_weights_tc(kernel):
+    """Keras [k,k,Cin,Cout] fp32 -> packed fp16 operand image (done once per layer)."""
+    _chk(kernel, "kernel")
+    kh, kw, Cin, Cout = kernel.shape
+    n = lib.pcnn_conv_tc_packed_weight_bytes(kh, kw, Cin)
+    packed = torch.empty(n // 2, dtype=torch.float16, device=kernel.device)
+    check(lib.pcnn_conv_tc_pack_weights(_p(kernel.contiguous()), _p(packed), kh, kw, Cin, Cout, _stream()), "conv_tc_pack_weights")
+    return {"packed": packed, "k": kh, "cin": Cin, "cout": Cout}
+
+
+_NUM_SMS = {}
+
+
+def _num_sms(device):
+    if device not in _NUM_SMS:
+        _NUM_SMS[device] = torch.cuda.get_device_properties(device).multi_processor_count
+    return _NUM_SMS[device]
+
+
+def conv2d_tc(x, wp, bias=None, act=ACT_LINEAR, pad_mode=PAD_CONSTANT, bn=None, residual=None, out_scale=None,
+              out=None, out_channels_total=None):
+    """tcgen05 convolution on BLK8 tensors.  x: Blk8 with >= wp['cin'] channels; returns a Blk8."""
+    if not isinstance(x, Blk8):
+        raise ValueError("conv2d_tc: x must be a Blk8 tensor (use to_blk8)")
+    k, cout = wp["k"], wp["cout"]
+    if -(-wp["cin"] // 16) != -(-x.C // 16):
+        raise ValueError("conv2d_tc: kernel expects %d input channels, tensor holds %d" % (wp["cin"], x.C))
+    blk8_halo_fill(x, k // 2, pad_mode)
+    if out is None:
+        out = Blk8(x.B, out_channels_total or cout, x.H, x.W, x.device)
+    if (out.B, out.H, out.W) != (x.B, x.H, x.W):
+        raise ValueError("conv2d_tc: destination shape mismatch")
+    if residual is not None and (residual.B, residual.H, residual.W) != (x.B, x.H, x.W):
+        raise ValueError("conv2d_tc: residual shape mismatch")
+    bn_s, bn_t = (bn if bn is not None else (None, None))
+    timed = KERNEL_TIMER is not None and KERNEL_TIMER.match(wp["cin"], cout, k, k, x.H, x.W)
+    if timed:
+        KERNEL_TIMER.start()
+    check(lib.pcnn_conv2d_tc(_p(x.buf), _p(wp["packed"]), _p(bias), _p(bn_s), _p(bn_t),
+                             None if residual is None else _p(residual.buf), _p(out_scale), _p(out.buf),
+                             x.B, x.C, cout, out.C, 0 if residual is None else residual.C, x.H, x.W, k, int(act),
+                             _num_sms(x.device), _stream()), "conv2d_tc")
+    if timed:
+        KERNEL_TIMER.stop(2.0 * x.B * x.H * x.W * k * k * wp["cin"] * cout)
+    if out.halo[0] != PAD_CONSTANT:
+        out.halo = (out.halo[0], -1)          # interior changed: a mirrored halo is stale
+    return out

@@ -1,0 +1,112 @@
+"""GPU tests of the tensor-core path (tcgen05 conv on BLK8 fp16 tensors) against the oracle.
+Operands are rounded to fp16 (11-bit significand, the same as TF32) and accumulated in fp32, so a
+single conv matches the float64 oracle to ~3e-4 relative; the oracle evaluated on fp16-rounded
+inputs/weights matches to ~1e-5 (accumulation order only)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import rel_l2
+from oracle import poisson_oracle as O
+
+pytestmark = pytest.mark.gpu
+ACTS = {0: "linear", 1: "leaky_relu", 2: "tanh"}
+
+
+def dev(t):
+    return torch.as_tensor(t).float().cuda()
+
+
+def h16(t):
+    return t.half().double()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from poisson_cnn_b200 import ops as _ops
+    return _ops
+
+
+def test_blk8_roundtrip_and_halo(ops):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 13, 9, 21, generator=g)
+    t = ops.to_blk8(dev(x))
+    back = ops.from_blk8(t)
+    assert back.shape == x.shape
+    np.testing.assert_array_equal(back.cpu().numpy(), x.half().float().numpy())
+    # raw buffer: halo zero, SYMMETRIC fill mirrors the interior
+    Hp, P = 9 + 14, 21 + 14
+    raw = lambda: t.buf[: 2 * 2 * Hp * P * 8].view(2, 2, Hp, P, 8).float().cpu()
+    r0 = raw()
+    assert float(r0[:, :, :7].abs().max()) == 0 and float(r0[:, :, :, :7].abs().max()) == 0
+    ops.blk8_halo_fill(t, 5, 1)
+    r1 = raw()
+    ref = O.advanced_pad(x.half().float(), [11, 11], "SYMMETRIC")              # pad 5 each side
+    got = r1[:, :, 2:2 + 19, 2:2 + 31].permute(0, 1, 4, 2, 3).reshape(2, 16, 19, 31)[:, :13]
+    np.testing.assert_array_equal(got.numpy(), ref.numpy())
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W,k,act", [
+    (2, 32, 32, 8, 256, 15, 1),       # the dominant layer shape: full 256-wide tiles
+    (1, 32, 32, 7, 300, 15, 1),       # ragged: H not a multiple of 4, two column tiles
+    (2, 32, 28, 12, 64, 13, 1),
+    (1, 64, 32, 9, 80, 7, 1),         # post_merge_conv: 4 K-chunks
+    (2, 29, 23, 20, 21, 7, 2),        # DBCNN first 2-D conv, odd channel counts, tanh
+    (1, 16, 16, 16, 40, 5, 0),
+    (3, 12, 8, 5, 33, 3, 1),
+    (1, 32, 32, 4, 16, 1, 0),         # 1x1
+])
+def test_conv2d_tc_parity(ops, B, Cin, Cout, H, W, k, act):
+    g = torch.Generator().manual_seed(B * 1000 + Cin * 10 + k)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    kern = torch.randn(k, k, Cin, Cout, generator=g) / (k * Cin ** 0.5)
+    bias = torch.randn(Cout, generator=g) * 0.1
+    wp = ops.pack_conv_weights_tc(dev(kern))
+    out = ops.conv2d_tc(ops.to_blk8(dev(x)), wp, dev(bias), act)
+    got = ops.from_blk8(out)
+    assert got.shape == (B, Cout, H, W)
+    ref16 = O.conv_nd(h16(x), h16(kern), bias.double(), ACTS[act], "CONSTANT", 0.0)    # same operand rounding
+    assert rel_l2(got, ref16) < 6e-4      # fp16 output rounding (2^-11) + accumulation order
+    ref = O.conv_nd(x.double(), kern.double(), bias.double(), ACTS[act], "CONSTANT", 0.0)
+    assert rel_l2(got, ref) < 2e-3
+
+
+def test_conv2d_tc_symmetric_bn_residual_scale_concat(ops):
+    g = torch.Generator().manual_seed(9)
+    B, C, H, W, k = 2, 32, 18, 50, 11
+    x = torch.randn(B, C, H, W, generator=g)
+    res = torch.randn(B, C, H, W, generator=g)
+    kern = torch.randn(k, k, C, C, generator=g) / (k * C ** 0.5)
+    bias = torch.randn(C, generator=g) * 0.1
+    s = torch.rand(C, generator=g) + 0.5
+    t = torch.randn(C, generator=g) * 0.1
+    scale = torch.randn(B, C, generator=g)
+    ref = O.conv_nd(h16(x), h16(kern), bias.double(), "leaky_relu", "SYMMETRIC")
+    ref = (ref * s.double().view(1, C, 1, 1) + t.double().view(1, C, 1, 1)) * scale.double().view(B, C, 1, 1)
+    ref = h16(ref.float()) + h16(res)
+    wp = ops.pack_conv_weights_tc(dev(kern))
+    # write into channels [32, 64) of a 64-channel buffer (in-place concat), read residual from another
+    out = ops.Blk8(B, 64, H, W, torch.device("cuda"))
+    xin = ops.to_blk8(dev(x))
+    rin = ops.to_blk8(dev(res))
+    tmp = ops.conv2d_tc(xin, wp, dev(bias), 1, pad_mode=1, bn=(dev(s), dev(t)), residual=rin, out_scale=dev(scale))
+    assert rel_l2(ops.from_blk8(tmp), ref) < 1e-3
+    assert xin.halo == (1, 5)
+    # a CONSTANT consumer after a SYMMETRIC one must see zeros again
+    ref0 = O.conv_nd(h16(x), h16(kern), bias.double(), "linear", "CONSTANT")
+    again = ops.conv2d_tc(xin, wp, dev(bias), 0, pad_mode=0)
+    assert rel_l2(ops.from_blk8(again), ref0) < 6e-4
+
+
+def test_conv2d_tc_chain_matches_fp32_path(ops):
+    """Three chained TC convs stay in BLK8 (no re-layout) and track the strict-FP32 kernels to fp16 accuracy."""
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 32, 24, 70, generator=g)
+    kerns = [torch.randn(7, 7, 32, 32, generator=g) / (7 * 32 ** 0.5) * 1.4 for _ in range(3)]
+    biases = [torch.randn(32, generator=g) * 0.1 for _ in range(3)]
+    a = dev(x)
+    t = ops.to_blk8(a)
+    for kern, bias in zip(kerns, biases):
+        a = ops.conv2d(a, dev(kern), dev(bias), 1, 0, 0.0)
+        t = ops.conv2d_tc(t, ops.pack_conv_weights_tc(dev(kern)), dev(bias), 1)
+    assert rel_l2(ops.from_blk8(t), a) < 2e-3
