@@ -186,6 +186,9 @@ int pcnn_from_blk8(const void* in, float* out, int B, int C, int H, int W, int c
 /* tf.pad ring of width pad (<= 7) around the interior: mode PCNN_PAD_CONSTANT writes zeros,
  * PCNN_PAD_SYMMETRIC mirrors (utils/apply_advanced_padding_and_call_conv_layer.py:18). */
 int pcnn_blk8_halo_fill(void* buf, int B, int C, int H, int W, int pad, int mode, void* stream);
+/* pcnn_dbcnn_expand_f32 writing the BLK8 layout directly (the [B,29,H,W] fp32 tensor never exists). */
+int pcnn_dbcnn_expand_blk8(const float* h, const float* sinh_basis, const float* modew, const float* posx,
+                           const float* posy, void* out, int B, int M, int xres, int n, void* stream);
 /* Keras kernel [k,k,Cin,Cout] fp32 -> fp16 operand image of the row-group GEMM:
  * [ceil(Cin/16)][k][2][(k+6)*32][8] (see conv_tc.cu).  Done once per layer at load time. */
 size_t pcnn_conv_tc_packed_weight_bytes(int kh, int kw, int Cin);

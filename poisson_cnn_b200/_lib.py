@@ -47,6 +47,7 @@ SIGNATURES = {
     "pcnn_conv_tc_packed_weight_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pcnn_conv_tc_pack_weights": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "pcnn_conv2d_tc": (c_int, [P] * 8 + [c_int] * 10 + [P]),
+    "pcnn_dbcnn_expand_blk8": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
 }
 
 

@@ -219,33 +219,45 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
     } else if (warp == 2) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            uint32_t grow = 0, gw = 0, it = 0;
+            // The single issuing thread is the critical path: everything per MMA is incremental
+            // (descriptor low words advance by constants, ring slots wrap by compare, no div/mod).
             const uint32_t a_lbo = (uint32_t)(p.kh + 2 * ZPAD) * 512u;   // K-half (plane) stride of the packed weights
+            const uint32_t a_hi = (uint32_t)(make_desc(0, a_lbo, 128u) >> 32);
+            const uint32_t b_hi = (uint32_t)(make_desc(0, p.rowplane_bytes, 128u) >> 32);
+            const uint32_t a_lo_lbo = ((a_lbo >> 4) & 0x3FFF) << 16, b_lo_lbo = ((p.rowplane_bytes >> 4) & 0x3FFF) << 16;
+            const uint32_t rows_base16 = smem_u32(s_rows) >> 4, w_base16 = smem_u32(s_w) >> 4;
+            const uint32_t slot16 = row_slot_bytes >> 4, wstage16 = p.wstage_bytes >> 4;
+            const uint32_t nslots = p.row_slots, nwst = p.w_stages;
+            uint32_t slot0 = 0, slot0_ph = 0;    // ring position/phase of the current chunk's row 0
+            uint32_t wst = 0, wph = 0, it = 0;
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
                 const uint32_t acc = it & 1, acc_ph = (it >> 1) & 1;
                 mbar_wait(acc_empty + acc, acc_ph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
-                uint32_t first = 1;
-                for (int c = 0; c < p.c16; ++c, grow += R) {
-                    for (int dx = 0; dx < p.kw; ++dx, ++gw) {
-                        const uint32_t st = gw % p.w_stages, wph = (gw / p.w_stages) & 1;
-                        mbar_wait(w_full + st, wph);
+                uint32_t accum = 0;
+                for (int c = 0; c < p.c16; ++c) {
+                    for (int dx = 0; dx < p.kw; ++dx) {
+                        mbar_wait(w_full + wst, wph);
                         tc_fence_after();
-                        const uint32_t wbase = smem_u32(s_w + (size_t)st * p.wstage_bytes);
+                        uint32_t a_lo = ((w_base16 + wst * wstage16) & 0x3FFF) | a_lo_lbo;
+                        uint32_t slot = slot0, ph = slot0_ph;
+                        uint32_t b_lo = ((rows_base16 + slot * slot16 + dx) & 0x3FFF) | b_lo_lbo;
+                        const bool first_dx = (dx == 0), last_dx = (dx == p.kw - 1);
                         for (int rho = 0; rho < R; ++rho) {
-                            const uint32_t g = grow + rho;
-                            const uint32_t slot = g % p.row_slots, rph = (g / p.row_slots) & 1;
-                            if (dx == 0) { mbar_wait(row_full + slot, rph); tc_fence_after(); }
-                            const uint32_t rbase = smem_u32(s_rows + (size_t)slot * row_slot_bytes);
-                            const uint64_t a_desc = make_desc(wbase + rho * 512u, a_lbo, 128u);
-                            const uint64_t b_desc = make_desc(rbase + dx * 16u, p.rowplane_bytes, 128u);
-                            tc_mma_f16(d_tmem, a_desc, b_desc, p.idesc, first ? 0u : 1u);
-                            first = 0;
-                            if (dx == p.kw - 1) tc_commit(row_empty + slot);   // row no longer needed
+                            if (first_dx) { mbar_wait(row_full + slot, ph); tc_fence_after(); }
+                            tc_mma_f16(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, accum);
+                            accum = 1;
+                            if (last_dx) tc_commit(row_empty + slot);   // row no longer needed
+                            a_lo += 32;                                  // next A window: +512 B
+                            b_lo += slot16;
+                            if (++slot == nslots) { slot = 0; ph ^= 1; b_lo -= nslots * slot16; }
                         }
-                        tc_commit(w_empty + st);
+                        tc_commit(w_empty + wst);
+                        if (++wst == nwst) { wst = 0; wph ^= 1; }
                     }
+                    slot0 += R;
+                    if (slot0 >= nslots) { slot0 -= nslots; slot0_ph ^= 1; }
                 }
                 tc_commit(acc_full + acc);
             }
@@ -405,6 +417,35 @@ __global__ void blk8_halo_fill_kernel(__half* __restrict__ buf, int H, int W, in
     }
 }
 
+// DBCNN mode expansion straight into BLK8: out[b, m, x, y] = h[b,m,y] * S[m,x] * w[b,m]; channels M, M+1 = pos
+__global__ void dbcnn_expand_blk8_kernel(const float* __restrict__ h, const float* __restrict__ S,
+                                         const float* __restrict__ mw, const float* __restrict__ posx,
+                                         const float* __restrict__ posy, __half* __restrict__ out, int M,
+                                         int xres, int n, int c8_total, long long total) {
+    const int Hp = xres + 2 * HALO, P = n + 2 * HALO;
+    const int np = (M + 2 + 7) / 8;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int y = idx % n;
+        long long t = idx / n;
+        const int x = t % xres; t /= xres;
+        const int pl = t % np;
+        const long long b = t / np;
+        __align__(16) __half v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int m = pl * 8 + e;
+            float f = 0.f;
+            if (m < M) f = __ldg(h + (b * M + m) * n + y) * __ldg(S + (long long)m * xres + x) * __ldg(mw + b * M + m);
+            else if (m == M) f = __ldg(posx + x);
+            else if (m == M + 1) f = __ldg(posy + y);
+            v[e] = __float2half_rn(f);
+        }
+        const size_t off = ((((size_t)b * c8_total + pl) * Hp + (x + HALO)) * P + (y + HALO)) * 8;
+        *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(v);
+    }
+}
+
 static inline int grid_for(long long total, int block = 256, int cap = 148 * 16) {
     long long g = (total + block - 1) / block;
     if (g > cap) g = cap;
@@ -468,6 +509,16 @@ extern "C" int pcnn_blk8_halo_fill(void* buf, int B, int C, int H, int W, int pa
     const int planes = ((C + 15) / 16) * 2;
     const long long total = (long long)B * planes * (H + 2 * pad) * (W + 2 * pad);
     blk8_halo_fill_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((__half*)buf, H, W, H + 2 * HALO, W + 2 * HALO, planes, pad, mode, total);
+    PCNN_CHECK_LAUNCH();
+    return PCNN_OK;
+}
+
+extern "C" int pcnn_dbcnn_expand_blk8(const float* h, const float* sinh_basis, const float* modew, const float* posx,
+                                      const float* posy, void* out, int B, int M, int xres, int n, void* stream) {
+    PCNN_CHECK_ARG(h && sinh_basis && modew && posx && posy && out && B > 0 && M > 0, "dbcnn_expand_blk8: bad argument");
+    const int c8_total = ((M + 2 + 15) / 16) * 2;
+    const long long total = (long long)B * ((M + 2 + 7) / 8) * xres * n;
+    dbcnn_expand_blk8_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(h, sinh_basis, modew, posx, posy, (__half*)out, M, xres, n, c8_total, total);
     PCNN_CHECK_LAUNCH();
     return PCNN_OK;
 }

@@ -86,6 +86,11 @@ class Dirichlet_BC_NN_Legacy_2(WeightedModel):
         t = ops.conv2d(t, k1, b1, act, PAD_CONSTANT, 0.0, residual=x)
         return ops.conv2d(t, k2, b2, act, PAD_CONSTANT, 0.0)
 
+    def _tc_supported(self):
+        fin = self._cfg["final_convolutions_config"]
+        return (all(k % 2 == 1 and k <= 15 for k in fin["kernel_sizes"]) and max(fin["filters"]) <= 32
+                and self.x_dir_nmodes + 2 <= 32 and self.final_pad == PAD_CONSTANT and float(self.final_pad_value) == 0.0)
+
     def raw_forward(self, bc, dx, x_res):
         """Everything up to (not including) the final max-normalisation; returns (raw [B,1,x_res,n], max|raw| [B])."""
         if bc.dim() != 3 or bc.shape[1] != 1:
@@ -105,8 +110,26 @@ class Dirichlet_BC_NN_Legacy_2(WeightedModel):
         v = ops.dense_input(dx, x_res, n, extra=spp, normalize=True)
         for i in range(self.n_mlp):
             v = ops.dense(v, *self.conv("mlp/%d" % i), self.mlp_acts[i])
-        out = ops.dbcnn_expand(h, v, x_res)
         S, nreg = self.n_final, self.final_regular_conv_stages
+        if self.precision == "tc":
+            if not self._tc_supported():
+                raise NotImplementedError("precision='tc' covers odd kernels <= 15, <= 32 filters, zero CONSTANT padding")
+            # the [B,29,x_res,n] mode expansion is produced directly in the tensor-core operand layout
+            t = ops.dbcnn_expand_blk8(h, v, x_res)
+            for k in range(S - nreg):
+                wp, bb = self.tc_conv("final/%d/conv" % k)
+                t = ops.conv2d_tc(t, wp, bb, self.final_act, PAD_CONSTANT)
+                name = "final/%d/resnet" % k
+                (w0, b0), (w1, b1), (w2, b2) = (self.tc_conv(name + "/conv%d" % i) for i in range(3))
+                u = ops.conv2d_tc(t, w0, b0, self.final_act, PAD_CONSTANT)
+                u = ops.conv2d_tc(u, w1, b1, self.final_act, PAD_CONSTANT, residual=t)
+                t = ops.conv2d_tc(u, w2, b2, self.final_act, PAD_CONSTANT)
+            out = ops.from_blk8(t, C=self.conv("final/%d/conv" % (S - nreg))[0].shape[2])
+            for k in range(S - nreg, S):
+                kk, bb = self.conv("final/%d/conv" % k)
+                out = ops.conv2d(out, kk, bb, ACT_TANH, PAD_CONSTANT, 0.0)
+            return out, ops.maxabs(out)
+        out = ops.dbcnn_expand(h, v, x_res)
         for k in range(S - nreg):
             kk, bb = self.conv("final/%d/conv" % k)
             out = ops.conv2d(out, kk, bb, self.final_act, self.final_pad, self.final_pad_value)

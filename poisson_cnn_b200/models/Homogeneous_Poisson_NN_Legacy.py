@@ -162,6 +162,110 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
         else:
             ops.resize(h, out_hw, blk.resize_method, alpha, out=merged, accumulate=not first)
 
+    # ------------------------------------------------------------------ tensor-core building blocks
+    def _conv_tc(self, x, name, act, pad, bn_name=None, residual=None, out_scale=None, out=None, out_c_offset=0):
+        wp, bias = self.tc_conv(name)
+        return ops.conv2d_tc(x, wp, bias, act, pad, bn=self.bn(bn_name) if bn_name else None, residual=residual,
+                             out_scale=out_scale, out=out, out_c_offset=out_c_offset)
+
+    def _resnet_tc(self, x, name, act, pad, use_bn, out_scale=None):
+        t = self._conv_tc(x, name + "/conv0", act, pad, name + "/bn0" if use_bn else None)
+        t = self._conv_tc(t, name + "/conv1", act, pad, name + "/bn1" if use_bn else None, residual=x)
+        return self._conv_tc(t, name + "/conv2", act, pad, out_scale=out_scale)
+
+    def _tc_ok(self, ksize, pad_value=0.0):
+        return ksize % 2 == 1 and ksize <= 15 and float(pad_value) == 0.0
+
+    def _call_tc(self, rhs, dx):
+        """Same graph as the FP32 path with every heavy convolution on tcgen05 (BLK8 fp16 activations).
+        FP32 kernels keep: the 3-channel first conv, pooling / upsampling / merge, the 2..8-pixel
+        multilinear branches, the last two linear convs, Scaling and the boundary ring."""
+        B, _, H, Wd = rhs.shape
+        F = self.filters
+        dev = rhs.device
+        x = ops.hpnn_input(rhs) if self.use_positional_embeddings else rhs
+        kk, bb = self.conv("pre_bottleneck/0")
+        x = ops.conv2d(x, kk, bb, self.pre_act, self.pre_pad, self.pre_pad_value,
+                       bn=self.bn("pre_bottleneck/0/bn") if self.use_batchnorm else None)
+        t = ops.to_blk8(x)
+        for k in range(1, self.n_pre):
+            t = self._conv_tc(t, "pre_bottleneck/%d" % k, self.pre_act, self.pre_pad,
+                              "pre_bottleneck/%d/bn" % k if self.use_batchnorm else None)
+        x0 = t                                   # BLK8, F channels
+        x0_f32 = ops.from_blk8(x0)               # pooling pyramid reads NCHW fp32
+
+        merged = torch.empty((B, F, H, Wd), device=dev, dtype=torch.float32)
+        blocks = self.bottleneck_deconv_blocks + self.bottleneck_multilinear_blocks
+        alpha = 1.0 / float(len(blocks) * F)
+        for i, blk in enumerate(blocks):
+            ph, pw = -(-H // blk.downsampling_factor), -(-Wd // blk.downsampling_factor)
+            if blk.kind == "deconv" and min(ph, pw) >= 16:
+                name = "bottleneck_%s/%d" % (blk.kind, blk.index)
+                h = ops.to_blk8(ops.avgpool_same(x0_f32, blk.downsampling_factor))
+                h = self._conv_tc(h, name + "/conv0", blk.act, blk.pad)
+                for r in range(1, blk.n_convs):
+                    h = self._resnet_tc(h, "%s/resnet%d" % (name, r), blk.act, blk.pad, blk.use_batchnorm)
+                dk, db = self.conv(name + "/deconv")
+                ops.deconv_same(ops.from_blk8(h), dk, db, (H, Wd), blk.upsampling_factor, blk.deconv_act, alpha,
+                                out=merged, accumulate=(i != 0))
+            else:
+                self._bottleneck(blk, x0_f32, merged, i == 0, alpha)
+
+        cat = ops.Blk8(B, 2 * F, H, Wd, dev)
+        self._conv_tc(x0, "non_bottleneck_conv", ACT_LEAKY_RELU, PAD_CONSTANT, out=cat)
+        ops.to_blk8(merged, out=cat, c_offset=F)
+        y = self._conv_tc(cat, "post_merge_conv", ACT_LEAKY_RELU, PAD_CONSTANT)
+
+        d = ops.dense_input(dx, H, Wd)
+        d = ops.dense(d, *self.conv("dx_dense/0"), ACT_LEAKY_RELU)
+        d = ops.dense(d, *self.conv("dx_dense/1"), ACT_LEAKY_RELU)
+        d = ops.dense(d, *self.conv("dx_dense/2"), ACT_LINEAR)
+        y = self._resnet_tc(y, "post_merge_resnet", ACT_LEAKY_RELU, PAD_CONSTANT, False, out_scale=d)
+
+        S, nreg = self.n_final, self.final_regular_conv_stages
+        for k in range(S - nreg):
+            y = self._conv_tc(y, "final/%d/conv" % k, self.final_act, self.final_pad)
+            y = self._resnet_tc(y, "final/%d/resnet" % k, self.final_act, PAD_CONSTANT, False)
+        y = ops.from_blk8(y, C=self.conv("final/%d/conv" % (S - nreg))[0].shape[2])
+        return self._tail(y, rhs, dx, S - nreg)
+
+    def _tail(self, y, rhs, dx, first_regular):
+        """The last linear convs, Scaling, boundary ring and post-smoother (FP32 kernels)."""
+        B, _, H, Wd = rhs.shape
+        S = self.n_final
+        cat2 = torch.empty((B, 2, H, Wd), device=rhs.device, dtype=torch.float32) if self.use_scaling else None
+        for k in range(first_regular, S):
+            kk, bb = self.conv("final/%d/conv" % k)
+            last = (k == S - 1) and self.use_scaling and kk.shape[3] == 1
+            y = ops.conv2d(y, kk, bb, ACT_LINEAR, PAD_CONSTANT, 0.0, out=cat2[:, 0:1] if last else None)
+        s = None
+        if self.use_scaling:
+            if y.data_ptr() != cat2.data_ptr():
+                cat2[:, 0:1].copy_(y)
+                y = cat2[:, 0:1]
+            cat2[:, 1:2].copy_(rhs)
+            h = cat2
+            for st in range(self.scaling_stages):
+                kk, bb = self.conv("scaling/conv%d" % st)
+                h = ops.conv2d(h, kk, bb, self.scaling_act, PAD_CONSTANT, 0.0)
+                h = ops.avgpool_same(h, self.scaling_ratio)
+            v = ops.spatial_pyramid_pool(h, self.scaling_levels, ops.POOL_MAX, ndims=2)
+            v = ops.dense(v, *self.conv("scaling/dense0"), ACT_LEAKY_RELU)
+            v = ops.dense(v, *self.conv("scaling/dense1"), ACT_LEAKY_RELU)
+            s = ops.dense(v, *self.conv("scaling/dense2"), ACT_LINEAR).reshape(B)
+        out = ops.hpnn_finalize(y, s, self.bc_type)
+        if self.postsmoother_iterations > 0:
+            out = ops.jacobi(out, rhs, torch.cat([dx, dx], 1), self.postsmoother_iterations)
+        return out
+
+    def _tc_supported(self):
+        ks = list(self._cfg["pre_bottleneck_convolutions_config"]["kernel_sizes"]) + \
+            list(self._cfg["final_convolutions_config"]["kernel_sizes"]) + \
+            list(self._cfg["bottleneck_deconv_config"]["conv_kernel_sizes"])
+        return (all(self._tc_ok(k) for k in ks) and self.filters <= 32 and float(self.pre_pad_value) == 0.0
+                and float(self.final_pad_value) == 0.0 and self.pre_pad in (0, 1) and self.final_pad == 0
+                and max(self._cfg["final_convolutions_config"]["filters"]) <= 32 and self.n_pre >= 2)
+
     # ------------------------------------------------------------------ forward
     def __call__(self, inp):
         rhs, dx = inp
@@ -171,6 +275,10 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
             raise ValueError("dx must be [batch, 1]")
         B, _, H, Wd = rhs.shape
         F = self.filters
+        if self.precision == "tc":
+            if not self._tc_supported():
+                raise NotImplementedError("precision='tc' covers odd kernels <= 15, <= 32 filters, zero CONSTANT / SYMMETRIC padding")
+            return self._call_tc(rhs, dx)
 
         x = ops.hpnn_input(rhs) if self.use_positional_embeddings else rhs
         for k in range(self.n_pre):
@@ -199,35 +307,10 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
         y = self._resnet(y, "post_merge_resnet", ACT_LEAKY_RELU, PAD_CONSTANT, 0.0, False, out_scale=d)
 
         S, nreg = self.n_final, self.final_regular_conv_stages
-        cat2 = torch.empty((B, 2, H, Wd), device=rhs.device, dtype=torch.float32) if self.use_scaling else None
         for k in range(S - nreg):
             kk, bb = self.conv("final/%d/conv" % k)
             y = ops.conv2d(y, kk, bb, self.final_act, self.final_pad, self.final_pad_value)
             y = self._resnet(y, "final/%d/resnet" % k, self.final_act, PAD_CONSTANT, 0.0, False)
-        for k in range(S - nreg, S):
-            kk, bb = self.conv("final/%d/conv" % k)
-            last = (k == S - 1) and self.use_scaling and kk.shape[3] == 1
-            y = ops.conv2d(y, kk, bb, ACT_LINEAR, PAD_CONSTANT, 0.0, out=cat2[:, 0:1] if last else None)
-
-        s = None
-        if self.use_scaling:
-            if y.data_ptr() != cat2.data_ptr():
-                cat2[:, 0:1].copy_(y)
-                y = cat2[:, 0:1]
-            cat2[:, 1:2].copy_(rhs)
-            h = cat2
-            for st in range(self.scaling_stages):
-                kk, bb = self.conv("scaling/conv%d" % st)
-                h = ops.conv2d(h, kk, bb, self.scaling_act, PAD_CONSTANT, 0.0)
-                h = ops.avgpool_same(h, self.scaling_ratio)
-            v = ops.spatial_pyramid_pool(h, self.scaling_levels, ops.POOL_MAX, ndims=2)
-            v = ops.dense(v, *self.conv("scaling/dense0"), ACT_LEAKY_RELU)
-            v = ops.dense(v, *self.conv("scaling/dense1"), ACT_LEAKY_RELU)
-            s = ops.dense(v, *self.conv("scaling/dense2"), ACT_LINEAR).reshape(B)
-
-        out = ops.hpnn_finalize(y, s, self.bc_type)
-        if self.postsmoother_iterations > 0:
-            out = ops.jacobi(out, rhs, torch.cat([dx, dx], 1), self.postsmoother_iterations)
-        return out
+        return self._tail(y, rhs, dx, S - nreg)
 
     call = __call__

@@ -18,6 +18,7 @@ class WeightedModel:
     def __init__(self):
         self._w = {}
         self._bn = {}
+        self._tc = {}
         self.device = None
         self.precision = "fp32"
 
@@ -52,7 +53,27 @@ class WeightedModel:
         return self
 
     def _on_weights_loaded(self):
-        pass
+        self._tc = {}
+
+    PRECISIONS = ("fp32", "tc")
+
+    def set_precision(self, precision):
+        """'fp32': strict FP32 CUDA-core kernels (rel-L2 <= 1e-5 vs the reference arithmetic);
+        'tc': tcgen05 tensor cores, FP16 operands (11-bit significand like TF32), FP32 accumulation."""
+        if precision not in self.PRECISIONS:
+            raise ValueError("precision must be one of %s" % (self.PRECISIONS,))
+        self.precision = precision
+        for sub in ("hpnn", "dbcnn"):
+            if hasattr(self, sub):
+                getattr(self, sub).set_precision(precision)
+        return self
+
+    def tc_conv(self, name):
+        """(packed fp16 operand image, bias) of a conv layer for the tensor-core kernel, packed once."""
+        from .. import ops
+        if name not in self._tc:
+            self._tc[name] = ops.pack_conv_weights_tc(self._w[name + "/kernel"])
+        return self._tc[name], self._w.get(name + "/bias")
 
     def init_synthetic_weights(self, seed=0, device=None):
         """Seeded random weights (no trained weights ship with the reference)."""

@@ -426,23 +426,49 @@ def dst_solve(rhs, left, top, right, bottom, dx):
 # =================================================================================================
 # tensor-core path: BLK8 fp16 activations + tcgen05 convolution (csrc/conv_tc.cu)
 # =================================================================================================
+_BLK8_POOL = {}     # (device, B, C, H, W) -> [(buffer, halo_state)]: recycled buffers keep their zero channel padding
+
+
 class Blk8:
     """fp16 activation in the BLK8 layout [B][Cpad/8][H+14][W+14][8] (7-pixel halo in memory).
-    `halo` records what the halo currently holds: ("zero", 7) after allocation, or (mode, pad)."""
+    `halo` records what the halo currently holds: (PAD_CONSTANT, 7) after allocation, (mode, pad) after a
+    halo fill, (mode, -1) when a mirrored halo went stale.  Buffers are recycled through a pool keyed by
+    the exact shape, so steady-state inference neither allocates nor re-zeroes them."""
 
-    __slots__ = ("buf", "B", "C", "H", "W", "halo")
+    __slots__ = ("buf", "B", "C", "H", "W", "halo", "_key")
 
     def __init__(self, B, C, H, W, device):
         nbytes = lib.pcnn_blk8_bytes(B, C, H, W)
         if nbytes == 0:
             raise ValueError("Blk8: bad shape")
-        self.buf = torch.zeros(nbytes // 2, dtype=torch.float16, device=device)
+        self._key = (str(device), B, C, H, W)
+        pool = _BLK8_POOL.get(self._key)
+        if pool:
+            self.buf, self.halo = pool.pop()
+        else:
+            self.buf = torch.zeros(nbytes // 2, dtype=torch.float16, device=device)
+            self.halo = (PAD_CONSTANT, 7)
         self.B, self.C, self.H, self.W = B, C, H, W
-        self.halo = (PAD_CONSTANT, 7)
+
+    def __del__(self):
+        try:
+            _BLK8_POOL.setdefault(self._key, []).append((self.buf, self.halo))
+        except Exception:
+            pass
 
     @property
     def device(self):
         return self.buf.device
+
+    def plane_ptr(self, c_offset):
+        """Device address of channel plane c_offset/8 of sample 0 (in-place concat)."""
+        if c_offset % 8:
+            raise ValueError("channel offset must be a multiple of 8")
+        return self.buf.data_ptr() + (c_offset // 8) * (self.H + 14) * (self.W + 14) * 16
+
+
+def blk8_pool_clear():
+    _BLK8_POOL.clear()
 
 
 def to_blk8(x, out=None, c_total=None, c_offset=0):
@@ -501,7 +527,7 @@ def _num_sms(device):
 
 
 def conv2d_tc(x, wp, bias=None, act=ACT_LINEAR, pad_mode=PAD_CONSTANT, bn=None, residual=None, out_scale=None,
-              out=None, out_channels_total=None):
+              out=None, out_channels_total=None, out_c_offset=0):
     """tcgen05 convolution on BLK8 tensors.  x: Blk8 with >= wp['cin'] channels; returns a Blk8."""
     if not isinstance(x, Blk8):
         raise ValueError("conv2d_tc: x must be a Blk8 tensor (use to_blk8)")
@@ -520,11 +546,25 @@ def conv2d_tc(x, wp, bias=None, act=ACT_LINEAR, pad_mode=PAD_CONSTANT, bn=None, 
     if timed:
         KERNEL_TIMER.start()
     check(lib.pcnn_conv2d_tc(_p(x.buf), _p(wp["packed"]), _p(bias), _p(bn_s), _p(bn_t),
-                             None if residual is None else _p(residual.buf), _p(out_scale), _p(out.buf),
+                             None if residual is None else _p(residual.buf), _p(out_scale), out.plane_ptr(out_c_offset),
                              x.B, x.C, cout, out.C, 0 if residual is None else residual.C, x.H, x.W, k, int(act),
                              _num_sms(x.device), _stream()), "conv2d_tc")
     if timed:
         KERNEL_TIMER.stop(2.0 * x.B * x.H * x.W * k * k * wp["cin"] * cout)
     if out.halo[0] != PAD_CONSTANT:
         out.halo = (out.halo[0], -1)          # interior changed: a mirrored halo is stale
+    return out
+
+
+def dbcnn_expand_blk8(h, modew, x_res):
+    """einsum('bmy,mx,bm->bmxy') + concat(pos) written straight into a BLK8 tensor [B, M+2, x_res, n]."""
+    _chk(h, "h"); _chk(modew, "modew")
+    h, modew = h.contiguous(), modew.contiguous()
+    B, M, n = h.shape
+    S = sinh_basis_table(h.device, M, x_res)
+    out = Blk8(B, M + 2, x_res, n, h.device)
+    check(lib.pcnn_dbcnn_expand_blk8(_p(h), _p(S), _p(modew), _p(position_table(h.device, x_res)),
+                                     _p(position_table(h.device, n)), _p(out.buf), B, M, x_res, n, _stream()), "dbcnn_expand_blk8")
+    if out.halo[0] != PAD_CONSTANT:
+        out.halo = (out.halo[0], -1)
     return out

@@ -110,3 +110,42 @@ def test_conv2d_tc_chain_matches_fp32_path(ops):
         a = ops.conv2d(a, dev(kern), dev(bias), 1, 0, 0.0)
         t = ops.conv2d_tc(t, ops.pack_conv_weights_tc(dev(kern)), dev(bias), 1)
     assert rel_l2(ops.from_blk8(t), a) < 2e-3
+
+
+# ------------------------------------------------------------------ whole models in tensor-core mode
+def _models(hp_cfg, db_cfg, w):
+    from poisson_cnn_b200 import convert_tf_object_names, models
+    hp = models.Homogeneous_Poisson_NN_Legacy(**convert_tf_object_names(hp_cfg))
+    db = models.Dirichlet_BC_NN_Legacy_2(**convert_tf_object_names(db_cfg))
+    return models.Poisson_CNN_Legacy(hp, db).load_weights(w).set_precision("tc")
+
+
+# Tensor-core mode budget (BASELINE.json north_star): rel-L2 <= 2e-3 vs the reference arithmetic.
+TC_TOL = 2e-3
+
+
+def test_models_tc_mode_vs_oracle():
+    import os
+    from tests.helpers import GOLDEN, pcnn_configs, all_weights
+    from poisson_cnn_b200.synthetic import make_problem
+    hp, db = pcnn_configs()
+    w = all_weights(hp, db)
+    model = _models(hp, db, w)
+    keys = ("rhs", "left", "top", "right", "bottom", "dx")
+    g = np.load(os.path.join(GOLDEN, "pcnn_112x120.npz"))
+    out = model([dev(g[k]) for k in keys])
+    e_pcnn = rel_l2(out, g["out"])
+    fp32 = model.set_precision("fp32")([dev(g[k]) for k in keys])
+    model.set_precision("tc")
+    print("PCNN 112x120 tc vs oracle: %.3e   (tc vs fp32 path: %.3e)" % (e_pcnn, rel_l2(out, fp32)))
+    # DBCNN alone, square grid
+    p = make_problem(2, 96, 96, seed=51, magnitudes=False)
+    ref = O.dbcnn_forward(db, w, p["left"].double(), p["dx"].double(), 96, "dbcnn/")
+    e_db = rel_l2(model.dbcnn([dev(p["left"]), dev(p["dx"]), 96]), ref)
+    # HPNN alone
+    p = make_problem(2, 128, 112, seed=52, magnitudes=False)
+    ref = O.hpnn_forward(hp, w, p["rhs"].double(), p["dx"].double(), "hpnn/")
+    e_hp = rel_l2(model.hpnn([dev(p["rhs"]), dev(p["dx"])]), ref)
+    print("tc-mode rel-L2 vs float64 oracle: pcnn %.3e  dbcnn %.3e  hpnn %.3e" % (e_pcnn, e_db, e_hp))
+    assert e_pcnn < TC_TOL and e_db < TC_TOL
+    assert e_hp < 2 * TC_TOL     # HPNN alone is deeper (45 convs) than the merged average; see DESIGN.md precision budget
