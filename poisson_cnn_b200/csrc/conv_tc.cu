@@ -27,9 +27,9 @@
 //   128 B apart (SBO), the two 8-channel K halves one plane apart (LBO); a column tap is a +16 B
 //   start-address shift.
 //
-// Warp roles (224 threads): 0 = input-row producer, 1 = weight producer, 2 = MMA issuer (+TMEM
-//   alloc), 3..6 = epilogue (TMEM lane quarter = warp % 4).  Two 256-column accumulators in TMEM let
-//   the epilogue of tile t overlap the MMAs of tile t+1.
+// Warp roles (352 threads): 0 = input-row producer, 1 = weight producer, 2 = MMA issuer (+TMEM
+//   alloc), 3..10 = epilogue (TMEM lane quarter = warp % 4, two warps per quarter split the columns).
+//   Two 256-column accumulators in TMEM let the epilogue of tile t overlap the MMAs of tile t+1.
 #include <cuda_fp16.h>
 
 #include "pcnn_common.cuh"
@@ -40,7 +40,8 @@ namespace tc {
 constexpr int HALO = 7;            // materialised halo of the BLK8 layout (kernel sizes up to 15)
 constexpr int ROWS_PER_TILE = 4;   // output rows per tile (M = 4 x 32)
 constexpr int COUT_PAD = 32;
-constexpr int NUM_THREADS = 224;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = (3 + NUM_EPI_WARPS) * 32;
 constexpr int ZPAD = ROWS_PER_TILE - 1;   // zero z-rows on each side of the packed weights
 constexpr unsigned long long SPIN_LIMIT_NS = 4000000000ull;   // a stuck pipeline traps instead of hanging the GPU
 
@@ -107,6 +108,21 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// one lane of a converged warp (cute::elect_one_sync)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -147,7 +163,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
     uint8_t* s_stage = s_w + (size_t)p.w_stages * p.wstage_bytes;
     constexpr int STAGE_PLANE = 32 * 16 + 16;   // 32 px x 16 B, +16 B so the 4 planes hit different banks
     constexpr int STAGE_WARP = 4 * STAGE_PLANE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + 4 * STAGE_WARP);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + NUM_EPI_WARPS * STAGE_WARP);
     uint64_t* row_full = bars;
     uint64_t* row_empty = row_full + p.row_slots;
     uint64_t* w_full = row_empty + p.row_slots;
@@ -162,7 +178,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.row_slots; ++i) { mbar_init(row_full + i, 1); mbar_init(row_empty + i, 1); }
         for (int i = 0; i < p.w_stages; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, NUM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {   // TMEM: 512 columns = two 256-column fp32 accumulators
@@ -218,9 +234,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
         }
     } else if (warp == 2) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            // The single issuing thread is the critical path: everything per MMA is incremental
-            // (descriptor low words advance by constants, ring slots wrap by compare, no div/mod).
+        // The whole warp stays converged (all loop state is warp-uniform and lives in uniform
+        // registers); one elected lane issues tcgen05.mma / tcgen05.commit.  Everything per MMA is
+        // incremental: descriptor low words advance by constants, ring slots wrap by compare.
+        {
             const uint32_t a_lbo = (uint32_t)(p.kh + 2 * ZPAD) * 512u;   // K-half (plane) stride of the packed weights
             const uint32_t a_hi = (uint32_t)(make_desc(0, a_lbo, 128u) >> 32);
             const uint32_t b_hi = (uint32_t)(make_desc(0, p.rowplane_bytes, 128u) >> 32);
@@ -228,6 +245,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
             const uint32_t rows_base16 = smem_u32(s_rows) >> 4, w_base16 = smem_u32(s_w) >> 4;
             const uint32_t slot16 = row_slot_bytes >> 4, wstage16 = p.wstage_bytes >> 4;
             const uint32_t nslots = p.row_slots, nwst = p.w_stages;
+            const bool leader = elect_one();
             uint32_t slot0 = 0, slot0_ph = 0;    // ring position/phase of the current chunk's row 0
             uint32_t wst = 0, wph = 0, it = 0;
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
@@ -246,32 +264,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                         const bool first_dx = (dx == 0), last_dx = (dx == p.kw - 1);
                         for (int rho = 0; rho < R; ++rho) {
                             if (first_dx) { mbar_wait(row_full + slot, ph); tc_fence_after(); }
-                            tc_mma_f16(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, accum);
+                            if (leader) {
+                                tc_mma_f16(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, accum);
+                                if (last_dx) tc_commit(row_empty + slot);   // row no longer needed
+                            }
                             accum = 1;
-                            if (last_dx) tc_commit(row_empty + slot);   // row no longer needed
                             a_lo += 32;                                  // next A window: +512 B
                             b_lo += slot16;
                             if (++slot == nslots) { slot = 0; ph ^= 1; b_lo -= nslots * slot16; }
                         }
-                        tc_commit(w_empty + wst);
+                        if (leader) tc_commit(w_empty + wst);
                         if (++wst == nwst) { wst = 0; wph ^= 1; }
                     }
                     slot0 += R;
                     if (slot0 >= nslots) { slot0 -= nslots; slot0_ph ^= 1; }
                 }
-                tc_commit(acc_full + acc);
+                if (leader) tc_commit(acc_full + acc);
+                __syncwarp();
             }
         }
     } else {
-        // ================= epilogue (warps 3..6) =================
+        // ================= epilogue (warps 3..10) =================
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int half = (warp - 3) >> 2;       // which half of the tile's columns
         const int r = (ROWS_PER_TILE - 1) - q;  // output row within the tile (M rows are (3-r)*32 + co)
         const int co = lane;
         uint8_t* stage = s_stage + (warp - 3) * STAGE_WARP;
-        const float bias = (p.bias && co < p.cout) ? p.bias[co] : 0.f;
-        const float bns = (p.bn_scale && co < p.cout) ? p.bn_scale[co] : 1.f;
-        const float bnt = (p.bn_shift && co < p.cout) ? p.bn_shift[co] : 0.f;
+        const bool live = co < p.cout;
+        const float bias = (p.bias && live) ? p.bias[co] : 0.f;
+        const float bns = (p.bn_scale && live) ? p.bn_scale[co] : 1.f;
+        const float bnt = (p.bn_shift && live) ? p.bn_shift[co] : 0.f;
         const int planes_out = (p.cout + 7) / 8;
+        const int ncols_half = ((p.n_tile / 2 + 31) / 32) * 32;   // columns handled by half 0 (multiple of 32)
+        const int c_begin = half * ncols_half, c_end = half ? p.n_tile : min(ncols_half, p.n_tile);
+        const int act = p.act;
         uint32_t it = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
             const int tx = t % p.tiles_x;
@@ -279,24 +305,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
             const int b = t / (p.tiles_x * p.tiles_y);
             const int x0 = tx * p.n_tile, y = ty * ROWS_PER_TILE + r;
             const uint32_t acc = it & 1, acc_ph = (it >> 1) & 1;
-            const float osc = (p.out_scale && co < p.cout) ? p.out_scale[(size_t)b * p.cout + co] : 1.f;
+            // fold the per-(sample,channel) scale into the BN affine: (a*s + t) * o = a*(s*o) + t*o
+            const float osc = (p.out_scale && live) ? p.out_scale[(size_t)b * p.cout + co] : 1.f;
+            const float mul = bns * osc, add = bnt * osc;
             mbar_wait(acc_full + acc, acc_ph);
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
-            for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr0 + c0, v);
                 if (y < p.H) {
-                    // bias -> activation -> BN affine -> per-(b,c) scale, then fp16 into the transpose buffer
+                    // bias -> activation -> (BN affine * scale), then fp16 into the transpose buffer.
+                    // Padded channels (co >= cout) come out as exact zeros: zero weights, bias 0, shift 0.
                     __half* srow = reinterpret_cast<__half*>(stage + (co >> 3) * STAGE_PLANE) + (co & 7);
+                    if (act == PCNN_ACT_LEAKY_RELU) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float f = __uint_as_float(v[j]) + bias;
-                        f = apply_act(f, p.act);
-                        f = fmaf(f, bns, bnt);
-                        f *= osc;
-                        if (co >= p.cout) f = 0.f;
-                        srow[j * 8] = __float2half_rn(f);
+                        for (int j = 0; j < 32; ++j) {
+                            float f = __uint_as_float(v[j]) + bias;
+                            f = fmaxf(f, 0.2f * f);
+                            srow[j * 8] = __float2half_rn(fmaf(f, mul, add));
+                        }
+                    } else if (act == PCNN_ACT_TANH) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float f = tanh_approx(__uint_as_float(v[j]) + bias);
+                            srow[j * 8] = __float2half_rn(fmaf(f, mul, add));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float f = __uint_as_float(v[j]) + bias;
+                            srow[j * 8] = __float2half_rn(fmaf(f, mul, add));
+                        }
                     }
                     __syncwarp();
                     const int x = x0 + c0 + lane;
@@ -549,7 +589,7 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* wpack, const float* bi
     p.idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     // shared-memory plan: as many row slots as fit (>= kh+3, ideally 2x for full double buffering)
     const size_t kMax = 227 * 1024;
-    const size_t fixed = 4 * (4 * (32 * 16 + 16)) + 1024;
+    const size_t fixed = NUM_EPI_WARPS * (4 * (32 * 16 + 16)) + 1024;
     const int R = k + ZPAD;
     int w_stages = 3;
     size_t avail = kMax - fixed - (size_t)w_stages * p.wstage_bytes;
