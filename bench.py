@@ -254,7 +254,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "solutions/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"fp32": "f32", "tc": "f16"}.get(args.precision, args.precision), "data": "synthetic",
+            "vs_baseline": None, "dtype": {"fp32": "f32", "tc": "f16", "tc3": "f16 hi+lo split (3 MMAs), f32 accumulate"}.get(args.precision, args.precision), "data": "synthetic",
             "config": {"workload": "Poisson_CNN_Legacy forward (HPNN + 4x DBCNN merged), batch %d per GPU, %dx%d grids, pcnn_end_to_end architecture, precision mode %s" % (B, nx, ny, args.precision),
                        "per_gpu_batch": B, "global_batch": B * world, "grid": [nx, ny], "parallelism": "batch-sharded x%d" % world,
                        "l2": "inputs+activations per step (%.1f GB) exceed the 126 MB L2" % (B * nx * ny * 4 * 32 / 1e9),

@@ -179,29 +179,37 @@ int pcnn_dst_solve(const float* rhs, const float* left, const float* top, const 
 size_t pcnn_blk8_bytes(int B, int C, int H, int W);
 /* NCHW fp32 [B,C,H,W] (batch stride in_bstride) -> channels [c_offset, c_offset+C) of a BLK8 buffer
  * holding c_total channels (c_offset multiple of 8: this is how concat is assembled in place). */
-int pcnn_to_blk8(const float* in, void* out, int B, int C, int H, int W, int c_total, int c_offset,
-                 int64_t in_bstride, void* stream);
-int pcnn_from_blk8(const void* in, float* out, int B, int C, int H, int W, int c_total, int c_offset,
-                   int64_t out_bstride, void* stream);
+int pcnn_to_blk8(const float* in, void* out, void* out_lo, int B, int C, int H, int W, int c_total,
+                 int c_offset, int64_t in_bstride, void* stream);
+int pcnn_from_blk8(const void* in, const void* in_lo, float* out, int B, int C, int H, int W, int c_total,
+                   int c_offset, int64_t out_bstride, void* stream);
 /* tf.pad ring of width pad (<= 7) around the interior: mode PCNN_PAD_CONSTANT writes zeros,
  * PCNN_PAD_SYMMETRIC mirrors (utils/apply_advanced_padding_and_call_conv_layer.py:18). */
 int pcnn_blk8_halo_fill(void* buf, int B, int C, int H, int W, int pad, int mode, void* stream);
 /* pcnn_dbcnn_expand_f32 writing the BLK8 layout directly (the [B,29,H,W] fp32 tensor never exists). */
 int pcnn_dbcnn_expand_blk8(const float* h, const float* sinh_basis, const float* modew, const float* posx,
-                           const float* posy, void* out, int B, int M, int xres, int n, void* stream);
+                           const float* posy, void* out, void* out_lo, int B, int M, int xres, int n,
+                           void* stream);
 /* Keras kernel [k,k,Cin,Cout] fp32 -> fp16 operand image of the row-group GEMM:
  * [ceil(Cin/16)][k][2][(k+6)*32][8] (see conv_tc.cu).  Done once per layer at load time. */
-size_t pcnn_conv_tc_packed_weight_bytes(int kh, int kw, int Cin);
+size_t pcnn_conv_tc_packed_weight_bytes(int kh, int kw, int Cin, int nsplit);
 int pcnn_conv_tc_pack_weights(const float* kernel, void* packed, int kh, int kw, int Cin, int Cout,
-                              void* stream);
+                              int nsplit, void* stream);
 /* Same operator as pcnn_conv2d_f32 (pad + VALID conv + bias + act [+BN] [+residual] [*out_scale]) on
  * tcgen05 tensor cores: FP16 operands, FP32 accumulation in TMEM.  in/out/residual are BLK8 buffers
  * with Cin_total / Cout_total / Cres_total channels; the padding mode is whatever the halo of `in`
- * holds.  Odd k <= 15, Cout <= 32.  num_sms: CTAs of the persistent grid (<= 0: 148). */
-int pcnn_conv2d_tc(const void* in, const void* wpack, const float* bias, const float* bn_scale,
-                   const float* bn_shift, const void* residual, const float* out_scale, void* out,
-                   int B, int Cin_total, int Cout, int Cout_total, int Cres_total, int H, int W, int k,
-                   int act, int num_sms, void* stream);
+ * holds.  Odd k <= 15, Cout <= 32.  num_sms: CTAs of the persistent grid (<= 0: 148).
+ *
+ * Split precision (nsplit = 2): every BLK8 tensor is a pair of buffers x = hi + lo (lo = the fp16
+ * rounding remainder of hi, written by the producers) and the weights are packed as W_hi and W_lo;
+ * the kernel issues three MMAs per (chunk, tap, row): x_hi*W_hi + x_hi*W_lo + x_lo*W_hi, i.e. ~22
+ * significand bits at 3x the tensor work.  nsplit = 1: single FP16 pass (11 bits, like TF32); the
+ * *_lo pointers are NULL. */
+int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpack, const float* bias,
+                   const float* bn_scale, const float* bn_shift, const void* residual,
+                   const void* residual_lo, const float* out_scale, void* out, void* out_lo, int B,
+                   int Cin_total, int Cout, int Cout_total, int Cres_total, int H, int W, int k, int act,
+                   int nsplit, int num_sms, void* stream);
 
 #ifdef __cplusplus
 }

@@ -46,14 +46,19 @@ constexpr int ZPAD = ROWS_PER_TILE - 1;   // zero z-rows on each side of the pac
 constexpr unsigned long long SPIN_LIMIT_NS = 4000000000ull;   // a stuck pipeline traps instead of hanging the GPU
 
 struct Params {
-    const __half* in;        // BLK8 [B][c8_in][Hp][P][8]
-    const __half* wpack;     // [C16][kw][2][(kh+6)*32][8]
+    const __half* in;        // BLK8 [B][c8_in][Hp][P][8]  (hi part)
+    const __half* in_lo;     // lo part (split precision) or null
+    const __half* wpack;     // [nsplit][C16][kw][2][(kh+6)*32][8]  (hi image, then lo image)
     const float* bias;       // [32] (zero padded) or null
     const float* bn_scale;   // [32] or null
     const float* bn_shift;
     const __half* residual;  // BLK8 like out, or null
+    const __half* residual_lo;
     const float* out_scale;  // [B][Cout] or null
     __half* out;             // BLK8 [B][c8_out][Hp][P][8]
+    __half* out_lo;          // lo part of the output (split precision) or null
+    int nsplit;              // 1: single FP16 pass; 2: hi/lo operands, 3 MMAs per (chunk,tap,row)
+    int nv;                  // virtual K-chunks = c16 * (nsplit == 2 ? 3 : 1)
     int B, H, W, Hp, P;
     int c8_in, c8_out, c8_res;
     int c16;                 // input-channel chunks of 16
@@ -200,7 +205,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                 const int b = t / (p.tiles_x * p.tiles_y);
                 const int x0 = tx * p.n_tile, y0 = ty * ROWS_PER_TILE;
                 const int col0 = x0 + HALO - p.pad;
-                for (int c = 0; c < p.c16; ++c) {
+                for (int v = 0; v < p.nv; ++v) {
+                    // split precision: per chunk c the passes are (x_hi,W_hi), (x_hi,W_lo), (x_lo,W_hi)
+                    const int c = (p.nsplit == 2) ? v / 3 : v;
+                    const __half* inp = (p.nsplit == 2 && (v % 3) == 2) ? p.in_lo : p.in;
                     for (int rho = 0; rho < R; ++rho, ++g) {
                         const uint32_t slot = g % p.row_slots, ph = (g / p.row_slots) & 1;
                         mbar_wait(row_empty + slot, ph ^ 1);
@@ -209,7 +217,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                         const uint32_t dst = smem_u32(s_rows + (size_t)slot * row_slot_bytes);
 #pragma unroll
                         for (int pl = 0; pl < 2; ++pl) {
-                            const __half* src = p.in + ((((size_t)b * p.c8_in + (2 * c + pl)) * p.Hp + prow) * p.P + col0) * 8;
+                            const __half* src = inp + ((((size_t)b * p.c8_in + (2 * c + pl)) * p.Hp + prow) * p.P + col0) * 8;
                             bulk_copy_g2s(dst + pl * p.rowplane_bytes, src, p.row_copy_bytes, row_full + slot);
                         }
                     }
@@ -221,12 +229,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
         if (lane == 0) {
             uint32_t g = 0;
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-                for (int c = 0; c < p.c16; ++c) {
+                for (int v = 0; v < p.nv; ++v) {
+                    const int c = (p.nsplit == 2) ? v / 3 : v;
+                    const int wsel = (p.nsplit == 2 && (v % 3) == 1) ? 1 : 0;   // W_lo only in the middle pass
                     for (int dx = 0; dx < p.kw; ++dx, ++g) {
                         const uint32_t st = g % p.w_stages, ph = (g / p.w_stages) & 1;
                         mbar_wait(w_empty + st, ph ^ 1);
                         mbar_expect_tx(w_full + st, p.wstage_bytes);
-                        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) + ((size_t)c * p.kw + dx) * p.wstage_bytes;
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) + (((size_t)wsel * p.c16 + c) * p.kw + dx) * p.wstage_bytes;
                         bulk_copy_g2s(smem_u32(s_w + (size_t)st * p.wstage_bytes), src, p.wstage_bytes, w_full + st);
                     }
                 }
@@ -254,7 +264,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
                 uint32_t accum = 0;
-                for (int c = 0; c < p.c16; ++c) {
+                for (int c = 0; c < p.nv; ++c) {
                     for (int dx = 0; dx < p.kw; ++dx) {
                         mbar_wait(w_full + wst, wph);
                         tc_fence_after();
@@ -315,53 +325,62 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                 uint32_t v[32];
                 tmem_ld32(taddr0 + c0, v);
                 if (y < p.H) {
-                    // bias -> activation -> (BN affine * scale), then fp16 into the transpose buffer.
-                    // Padded channels (co >= cout) come out as exact zeros: zero weights, bias 0, shift 0.
+                    const int x = x0 + c0 + lane;
+                    const bool xok = (x < p.W) && (c0 + lane < p.n_tile);
                     __half* srow = reinterpret_cast<__half*>(stage + (co >> 3) * STAGE_PLANE) + (co & 7);
+                    // bias -> activation -> (BN affine * scale).  Padded channels (co >= cout) come out
+                    // as exact zeros: zero weights, bias 0, shift 0.
                     if (act == PCNN_ACT_LEAKY_RELU) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             float f = __uint_as_float(v[j]) + bias;
                             f = fmaxf(f, 0.2f * f);
-                            srow[j * 8] = __float2half_rn(fmaf(f, mul, add));
+                            v[j] = __float_as_uint(fmaf(f, mul, add));
                         }
                     } else if (act == PCNN_ACT_TANH) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const float f = tanh_approx(__uint_as_float(v[j]) + bias);
-                            srow[j * 8] = __float2half_rn(fmaf(f, mul, add));
+                            const float a = __uint_as_float(v[j]) + bias;
+                            const float f = (p.nsplit == 2) ? tanhf(a) : tanh_approx(a);
+                            v[j] = __float_as_uint(fmaf(f, mul, add));
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float f = __uint_as_float(v[j]) + bias;
-                            srow[j * 8] = __float2half_rn(fmaf(f, mul, add));
-                        }
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]) + bias, mul, add));
                     }
-                    __syncwarp();
-                    const int x = x0 + c0 + lane;
-                    for (int pl = 0; pl < planes_out; ++pl) {
-                        uint4 val = *reinterpret_cast<const uint4*>(stage + pl * STAGE_PLANE + lane * 16);
-                        if (x < p.W && c0 + lane < p.n_tile) {
-                            const size_t off = ((((size_t)b * p.c8_out + pl) * p.Hp + (y + HALO)) * p.P + (x + HALO)) * 8;
-                            if (p.residual) {
-                                const size_t roff = ((((size_t)b * p.c8_res + pl) * p.Hp + (y + HALO)) * p.P + (x + HALO)) * 8;
-                                const uint4 rv = *reinterpret_cast<const uint4*>(p.residual + roff);
-                                const __half2* a2 = reinterpret_cast<const __half2*>(&val);
-                                const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
-                                uint4 o;
-                                __half2* o2 = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float2 fa = __half22float2(a2[e]), fr = __half22float2(r2[e]);
-                                    o2[e] = __floats2half2_rn(fa.x + fr.x, fa.y + fr.y);
-                                }
-                                val = o;
+                    if (p.residual) {
+                        // residual: coalesced 16-B loads -> transpose buffer -> per-(channel, pixel) fp32 add
+                        for (int part = 0; part < p.nsplit; ++part) {
+                            const __half* rsrc = part ? p.residual_lo : p.residual;
+                            for (int pl = 0; pl < planes_out; ++pl) {
+                                uint4 rv = make_uint4(0, 0, 0, 0);
+                                if (xok) rv = *reinterpret_cast<const uint4*>(rsrc + ((((size_t)b * p.c8_res + pl) * p.Hp + (y + HALO)) * p.P + (x + HALO)) * 8);
+                                *reinterpret_cast<uint4*>(stage + pl * STAGE_PLANE + lane * 16) = rv;
                             }
-                            *reinterpret_cast<uint4*>(p.out + off) = val;
+                            __syncwarp();
+                            if (live) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __half2float(srow[j * 8]));
+                            }
+                            __syncwarp();
                         }
                     }
-                    __syncwarp();
+                    for (int part = 0; part < p.nsplit; ++part) {
+                        // fp16 (hi), then the rounding remainder (lo), through the transpose buffer
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const __half h = __float2half_rn(__uint_as_float(v[j]));
+                            srow[j * 8] = h;
+                            v[j] = __float_as_uint(__uint_as_float(v[j]) - __half2float(h));
+                        }
+                        __syncwarp();
+                        __half* dst = part ? p.out_lo : p.out;
+                        for (int pl = 0; pl < planes_out; ++pl) {
+                            const uint4 val = *reinterpret_cast<const uint4*>(stage + pl * STAGE_PLANE + lane * 16);
+                            if (xok) *reinterpret_cast<uint4*>(dst + ((((size_t)b * p.c8_out + pl) * p.Hp + (y + HALO)) * p.P + (x + HALO)) * 8) = val;
+                        }
+                        __syncwarp();
+                    }
                 }
             }
             tc_fence_before();
@@ -381,7 +400,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
 // ---------------------------------------------------------------- layout / packing kernels
 // Keras kernel [kh][kw][Cin][Cout] fp32 -> packed fp16 [C16][kw][2][(kh+6)*32][8]
 __global__ void pack_weights_kernel(const float* __restrict__ k, __half* __restrict__ out, int kh, int kw,
-                                    int Cin, int Cout, int c16, long long total) {
+                                    int Cin, int Cout, int c16, long long total, int nsplit) {
     const int Z = kh + 2 * ZPAD;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -395,12 +414,14 @@ __global__ void pack_weights_kernel(const float* __restrict__ k, __half* __restr
         const int ci = c * 16 + pl * 8 + e, dy = z - ZPAD;
         float v = 0.f;
         if (dy >= 0 && dy < kh && ci < Cin && co < Cout) v = k[(((long long)dy * kw + dx) * Cin + ci) * Cout + co];
-        out[idx] = __float2half_rn(v);
+        const __half h = __float2half_rn(v);
+        out[idx] = h;
+        if (nsplit == 2) out[total + idx] = __float2half_rn(v - __half2float(h));
     }
 }
 
 // NCHW fp32 -> BLK8 fp16 interior (planes [plane0, plane0 + ceil(C/8)))
-__global__ void to_blk8_kernel(const float* __restrict__ in, __half* __restrict__ out, int C, int H, int W,
+__global__ void to_blk8_kernel(const float* __restrict__ in, __half* __restrict__ out, __half* __restrict__ out_lo, int C, int H, int W,
                                int Hp, int P, int c8_total, int plane0, long long in_bstride, long long total) {
     const int np = (C + 7) / 8;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -411,18 +432,22 @@ __global__ void to_blk8_kernel(const float* __restrict__ in, __half* __restrict_
         const int pl = t % np;
         const long long b = t / np;
         __align__(16) __half h[8];
+        __align__(16) __half l[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int c = pl * 8 + e;
-            h[e] = __float2half_rn(c < C ? __ldg(in + b * in_bstride + ((long long)c * H + y) * W + x) : 0.f);
+            const float f = c < C ? __ldg(in + b * in_bstride + ((long long)c * H + y) * W + x) : 0.f;
+            h[e] = __float2half_rn(f);
+            l[e] = __float2half_rn(f - __half2float(h[e]));
         }
         const size_t off = ((((size_t)b * c8_total + plane0 + pl) * Hp + (y + HALO)) * P + (x + HALO)) * 8;
         *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(h);
+        if (out_lo) *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(l);
     }
 }
 
 // BLK8 fp16 -> NCHW fp32
-__global__ void from_blk8_kernel(const __half* __restrict__ in, float* __restrict__ out, int C, int H, int W,
+__global__ void from_blk8_kernel(const __half* __restrict__ in, const __half* __restrict__ in_lo, float* __restrict__ out, int C, int H, int W,
                                  int Hp, int P, int c8_total, int plane0, long long out_bstride, long long total) {
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -432,7 +457,9 @@ __global__ void from_blk8_kernel(const __half* __restrict__ in, float* __restric
         const int c = t % C;
         const long long b = t / C;
         const size_t off = ((((size_t)b * c8_total + plane0 + (c >> 3)) * Hp + (y + HALO)) * P + (x + HALO)) * 8 + (c & 7);
-        out[b * out_bstride + ((long long)c * H + y) * W + x] = __half2float(in[off]);
+        float f = __half2float(in[off]);
+        if (in_lo) f += __half2float(in_lo[off]);
+        out[b * out_bstride + ((long long)c * H + y) * W + x] = f;
     }
 }
 
@@ -460,8 +487,8 @@ __global__ void blk8_halo_fill_kernel(__half* __restrict__ buf, int H, int W, in
 // DBCNN mode expansion straight into BLK8: out[b, m, x, y] = h[b,m,y] * S[m,x] * w[b,m]; channels M, M+1 = pos
 __global__ void dbcnn_expand_blk8_kernel(const float* __restrict__ h, const float* __restrict__ S,
                                          const float* __restrict__ mw, const float* __restrict__ posx,
-                                         const float* __restrict__ posy, __half* __restrict__ out, int M,
-                                         int xres, int n, int c8_total, long long total) {
+                                         const float* __restrict__ posy, __half* __restrict__ out,
+                                         __half* __restrict__ out_lo, int M, int xres, int n, int c8_total, long long total) {
     const int Hp = xres + 2 * HALO, P = n + 2 * HALO;
     const int np = (M + 2 + 7) / 8;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -472,6 +499,7 @@ __global__ void dbcnn_expand_blk8_kernel(const float* __restrict__ h, const floa
         const int pl = t % np;
         const long long b = t / np;
         __align__(16) __half v[8];
+        __align__(16) __half l[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int m = pl * 8 + e;
@@ -480,9 +508,11 @@ __global__ void dbcnn_expand_blk8_kernel(const float* __restrict__ h, const floa
             else if (m == M) f = __ldg(posx + x);
             else if (m == M + 1) f = __ldg(posy + y);
             v[e] = __float2half_rn(f);
+            l[e] = __float2half_rn(f - __half2float(v[e]));
         }
         const size_t off = ((((size_t)b * c8_total + pl) * Hp + (x + HALO)) * P + (y + HALO)) * 8;
         *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(v);
+        if (out_lo) *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(l);
     }
 }
 
@@ -506,37 +536,38 @@ extern "C" size_t pcnn_blk8_bytes(int B, int C, int H, int W) {
     return ((size_t)B * planes * (H + 2 * HALO) * (W + 2 * HALO) * 8 + 8192) * sizeof(__half);
 }
 
-extern "C" size_t pcnn_conv_tc_packed_weight_bytes(int kh, int kw, int Cin) {
-    return (size_t)((Cin + 15) / 16) * kw * 2 * (kh + 2 * ZPAD) * COUT_PAD * 8 * sizeof(__half);
+extern "C" size_t pcnn_conv_tc_packed_weight_bytes(int kh, int kw, int Cin, int nsplit) {
+    return (size_t)(nsplit == 2 ? 2 : 1) * ((Cin + 15) / 16) * kw * 2 * (kh + 2 * ZPAD) * COUT_PAD * 8 * sizeof(__half);
 }
 
-extern "C" int pcnn_conv_tc_pack_weights(const float* kernel, void* packed, int kh, int kw, int Cin, int Cout, void* stream) {
+extern "C" int pcnn_conv_tc_pack_weights(const float* kernel, void* packed, int kh, int kw, int Cin, int Cout, int nsplit, void* stream) {
+    PCNN_CHECK_ARG(nsplit == 1 || nsplit == 2, "conv_tc_pack_weights: nsplit must be 1 or 2");
     PCNN_CHECK_ARG(kernel && packed, "conv_tc_pack_weights: null pointer");
     PCNN_CHECK_ARG(kh == kw && (kh & 1) && kh >= 1 && kh <= 2 * HALO + 1, "conv_tc: kernel %dx%d not supported (odd, square, <= 15)", kh, kw);
     PCNN_CHECK_ARG(Cout >= 1 && Cout <= COUT_PAD && Cin >= 1, "conv_tc: Cout %d not in [1,32]", Cout);
     const int c16 = (Cin + 15) / 16;
     const long long total = (long long)c16 * kw * 2 * (kh + 2 * ZPAD) * COUT_PAD * 8;
-    pack_weights_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(kernel, (__half*)packed, kh, kw, Cin, Cout, c16, total);
+    pack_weights_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(kernel, (__half*)packed, kh, kw, Cin, Cout, c16, total, nsplit);
     PCNN_CHECK_LAUNCH();
     return PCNN_OK;
 }
 
-extern "C" int pcnn_to_blk8(const float* in, void* out, int B, int C, int H, int W, int c_total, int c_offset,
+extern "C" int pcnn_to_blk8(const float* in, void* out, void* out_lo, int B, int C, int H, int W, int c_total, int c_offset,
                             int64_t in_bstride, void* stream) {
     PCNN_CHECK_ARG(in && out && B > 0 && C > 0 && (c_offset % 8) == 0 && c_offset + C <= ((c_total + 15) / 16) * 16, "to_blk8: bad argument");
     const int c8_total = ((c_total + 15) / 16) * 2;
     const long long total = (long long)B * ((C + 7) / 8) * H * W;
-    to_blk8_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(in, (__half*)out, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, in_bstride, total);
+    to_blk8_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(in, (__half*)out, (__half*)out_lo, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, in_bstride, total);
     PCNN_CHECK_LAUNCH();
     return PCNN_OK;
 }
 
-extern "C" int pcnn_from_blk8(const void* in, float* out, int B, int C, int H, int W, int c_total, int c_offset,
+extern "C" int pcnn_from_blk8(const void* in, const void* in_lo, float* out, int B, int C, int H, int W, int c_total, int c_offset,
                               int64_t out_bstride, void* stream) {
     PCNN_CHECK_ARG(in && out && B > 0 && C > 0 && (c_offset % 8) == 0, "from_blk8: bad argument");
     const int c8_total = ((c_total + 15) / 16) * 2;
     const long long total = (long long)B * C * H * W;
-    from_blk8_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const __half*)in, out, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, out_bstride, total);
+    from_blk8_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const __half*)in, (const __half*)in_lo, out, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, out_bstride, total);
     PCNN_CHECK_LAUNCH();
     return PCNN_OK;
 }
@@ -554,29 +585,34 @@ extern "C" int pcnn_blk8_halo_fill(void* buf, int B, int C, int H, int W, int pa
 }
 
 extern "C" int pcnn_dbcnn_expand_blk8(const float* h, const float* sinh_basis, const float* modew, const float* posx,
-                                      const float* posy, void* out, int B, int M, int xres, int n, void* stream) {
+                                      const float* posy, void* out, void* out_lo, int B, int M, int xres, int n, void* stream) {
     PCNN_CHECK_ARG(h && sinh_basis && modew && posx && posy && out && B > 0 && M > 0, "dbcnn_expand_blk8: bad argument");
     const int c8_total = ((M + 2 + 15) / 16) * 2;
     const long long total = (long long)B * ((M + 2 + 7) / 8) * xres * n;
-    dbcnn_expand_blk8_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(h, sinh_basis, modew, posx, posy, (__half*)out, M, xres, n, c8_total, total);
+    dbcnn_expand_blk8_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(h, sinh_basis, modew, posx, posy, (__half*)out, (__half*)out_lo, M, xres, n, c8_total, total);
     PCNN_CHECK_LAUNCH();
     return PCNN_OK;
 }
 
-extern "C" int pcnn_conv2d_tc(const void* in, const void* wpack, const float* bias, const float* bn_scale,
-                              const float* bn_shift, const void* residual, const float* out_scale, void* out,
-                              int B, int Cin_total, int Cout, int Cout_total, int Cres_total, int H, int W, int k,
-                              int act, int num_sms, void* stream) {
+extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpack, const float* bias, const float* bn_scale,
+                              const float* bn_shift, const void* residual, const void* residual_lo, const float* out_scale,
+                              void* out, void* out_lo, int B, int Cin_total, int Cout, int Cout_total, int Cres_total,
+                              int H, int W, int k, int act, int nsplit, int num_sms, void* stream) {
     PCNN_CHECK_ARG(in && wpack && out, "conv2d_tc: null pointer");
+    PCNN_CHECK_ARG(nsplit == 1 || nsplit == 2, "conv2d_tc: nsplit must be 1 or 2");
+    if (nsplit == 2) PCNN_CHECK_ARG(in_lo && out_lo && (!residual || residual_lo), "conv2d_tc: split precision needs the lo buffers");
     PCNN_CHECK_ARG((k & 1) && k >= 1 && k <= 2 * HALO + 1, "conv2d_tc: kernel size %d not supported (odd, <= 15)", k);
     PCNN_CHECK_ARG(Cout >= 1 && Cout <= COUT_PAD && Cout <= Cout_total, "conv2d_tc: Cout %d not in [1,32]", Cout);
     PCNN_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cin_total > 0, "conv2d_tc: bad shape");
     PCNN_CHECK_ARG((bn_scale == nullptr) == (bn_shift == nullptr), "conv2d_tc: bn_scale/bn_shift must come together");
     Params p;
-    p.in = (const __half*)in; p.wpack = (const __half*)wpack; p.bias = bias; p.bn_scale = bn_scale; p.bn_shift = bn_shift;
-    p.residual = (const __half*)residual; p.out_scale = out_scale; p.out = (__half*)out;
+    p.in = (const __half*)in; p.in_lo = (const __half*)in_lo; p.wpack = (const __half*)wpack; p.bias = bias;
+    p.bn_scale = bn_scale; p.bn_shift = bn_shift;
+    p.residual = (const __half*)residual; p.residual_lo = (const __half*)residual_lo; p.out_scale = out_scale;
+    p.out = (__half*)out; p.out_lo = (__half*)out_lo; p.nsplit = nsplit;
     p.B = B; p.H = H; p.W = W; p.Hp = H + 2 * HALO; p.P = W + 2 * HALO;
     p.c16 = (Cin_total + 15) / 16;
+    p.nv = p.c16 * (nsplit == 2 ? 3 : 1);
     p.c8_in = p.c16 * 2; p.c8_out = ((Cout_total + 15) / 16) * 2; p.c8_res = ((Cres_total + 15) / 16) * 2;
     p.cout = Cout; p.kh = k; p.kw = k; p.pad = k / 2; p.act = act;
     p.n_tile = W >= 256 ? 256 : ((W + 15) / 16) * 16;

@@ -111,11 +111,11 @@ class Dirichlet_BC_NN_Legacy_2(WeightedModel):
         for i in range(self.n_mlp):
             v = ops.dense(v, *self.conv("mlp/%d" % i), self.mlp_acts[i])
         S, nreg = self.n_final, self.final_regular_conv_stages
-        if self.precision == "tc":
+        if self.precision in ("tc", "tc3"):
             if not self._tc_supported():
                 raise NotImplementedError("precision='tc' covers odd kernels <= 15, <= 32 filters, zero CONSTANT padding")
             # the [B,29,x_res,n] mode expansion is produced directly in the tensor-core operand layout
-            t = ops.dbcnn_expand_blk8(h, v, x_res)
+            t = ops.dbcnn_expand_blk8(h, v, x_res, split=self.tc_split)
             for k in range(S - nreg):
                 wp, bb = self.tc_conv("final/%d/conv" % k)
                 t = ops.conv2d_tc(t, wp, bb, self.final_act, PAD_CONSTANT)

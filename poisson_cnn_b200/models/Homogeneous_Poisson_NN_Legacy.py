@@ -187,7 +187,8 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
         kk, bb = self.conv("pre_bottleneck/0")
         x = ops.conv2d(x, kk, bb, self.pre_act, self.pre_pad, self.pre_pad_value,
                        bn=self.bn("pre_bottleneck/0/bn") if self.use_batchnorm else None)
-        t = ops.to_blk8(x)
+        split = self.tc_split
+        t = ops.to_blk8(x, split=split)
         for k in range(1, self.n_pre):
             t = self._conv_tc(t, "pre_bottleneck/%d" % k, self.pre_act, self.pre_pad,
                               "pre_bottleneck/%d/bn" % k if self.use_batchnorm else None)
@@ -201,7 +202,7 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
             ph, pw = -(-H // blk.downsampling_factor), -(-Wd // blk.downsampling_factor)
             if blk.kind == "deconv" and min(ph, pw) >= 16:
                 name = "bottleneck_%s/%d" % (blk.kind, blk.index)
-                h = ops.to_blk8(ops.avgpool_same(x0_f32, blk.downsampling_factor))
+                h = ops.to_blk8(ops.avgpool_same(x0_f32, blk.downsampling_factor), split=split)
                 h = self._conv_tc(h, name + "/conv0", blk.act, blk.pad)
                 for r in range(1, blk.n_convs):
                     h = self._resnet_tc(h, "%s/resnet%d" % (name, r), blk.act, blk.pad, blk.use_batchnorm)
@@ -211,7 +212,7 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
             else:
                 self._bottleneck(blk, x0_f32, merged, i == 0, alpha)
 
-        cat = ops.Blk8(B, 2 * F, H, Wd, dev)
+        cat = ops.Blk8(B, 2 * F, H, Wd, dev, split=split)
         self._conv_tc(x0, "non_bottleneck_conv", ACT_LEAKY_RELU, PAD_CONSTANT, out=cat)
         ops.to_blk8(merged, out=cat, c_offset=F)
         y = self._conv_tc(cat, "post_merge_conv", ACT_LEAKY_RELU, PAD_CONSTANT)
@@ -275,7 +276,7 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
             raise ValueError("dx must be [batch, 1]")
         B, _, H, Wd = rhs.shape
         F = self.filters
-        if self.precision == "tc":
+        if self.precision in ("tc", "tc3"):
             if not self._tc_supported():
                 raise NotImplementedError("precision='tc' covers odd kernels <= 15, <= 32 filters, zero CONSTANT / SYMMETRIC padding")
             return self._call_tc(rhs, dx)

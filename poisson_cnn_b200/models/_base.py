@@ -55,11 +55,13 @@ class WeightedModel:
     def _on_weights_loaded(self):
         self._tc = {}
 
-    PRECISIONS = ("fp32", "tc")
+    PRECISIONS = ("fp32", "tc", "tc3")
 
     def set_precision(self, precision):
         """'fp32': strict FP32 CUDA-core kernels (rel-L2 <= 1e-5 vs the reference arithmetic);
-        'tc': tcgen05 tensor cores, FP16 operands (11-bit significand like TF32), FP32 accumulation."""
+        'tc'  : tcgen05 tensor cores, one pass of FP16 operands (11-bit significand like TF32), FP32 accumulation;
+        'tc3' : tcgen05 with split FP16 operands (x = hi + lo, W = hi + lo; three MMAs per product term),
+                ~22 significand bits -- the error-compensated mode that holds the 2e-3 budget on any input."""
         if precision not in self.PRECISIONS:
             raise ValueError("precision must be one of %s" % (self.PRECISIONS,))
         self.precision = precision
@@ -71,9 +73,15 @@ class WeightedModel:
     def tc_conv(self, name):
         """(packed fp16 operand image, bias) of a conv layer for the tensor-core kernel, packed once."""
         from .. import ops
-        if name not in self._tc:
-            self._tc[name] = ops.pack_conv_weights_tc(self._w[name + "/kernel"])
-        return self._tc[name], self._w.get(name + "/bias")
+        nsplit = 2 if self.precision == "tc3" else 1
+        key = (name, nsplit)
+        if key not in self._tc:
+            self._tc[key] = ops.pack_conv_weights_tc(self._w[name + "/kernel"], nsplit)
+        return self._tc[key], self._w.get(name + "/bias")
+
+    @property
+    def tc_split(self):
+        return self.precision == "tc3"
 
     def init_synthetic_weights(self, seed=0, device=None):
         """Seeded random weights (no trained weights ship with the reference)."""

@@ -426,33 +426,47 @@ def dst_solve(rhs, left, top, right, bottom, dx):
 # =================================================================================================
 # tensor-core path: BLK8 fp16 activations + tcgen05 convolution (csrc/conv_tc.cu)
 # =================================================================================================
-_BLK8_POOL = {}     # (device, B, C, H, W) -> [(buffer, halo_state)]: recycled buffers keep their zero channel padding
+_BLK8_POOL = {}     # (device, B, C, H, W) -> [buffer]: recycled buffers keep their zero halo / channel padding
+
+
+def _blk8_buffer(key, nbytes, device):
+    pool = _BLK8_POOL.get(key)
+    if pool:
+        buf, dirty_halo = pool.pop()
+        if dirty_halo:                  # a mirrored halo from the previous user: back to zeros (halo only)
+            _, B, C, H, W = key
+            check(lib.pcnn_blk8_halo_fill(_p(buf), B, C, H, W, 7, PAD_CONSTANT, _stream()), "blk8_halo_fill")
+        return buf
+    return torch.zeros(nbytes // 2, dtype=torch.float16, device=device)
 
 
 class Blk8:
     """fp16 activation in the BLK8 layout [B][Cpad/8][H+14][W+14][8] (7-pixel halo in memory).
+    split=True keeps a second buffer `lo` with the fp16 rounding remainder (x = hi + lo, ~22 bits).
     `halo` records what the halo currently holds: (PAD_CONSTANT, 7) after allocation, (mode, pad) after a
     halo fill, (mode, -1) when a mirrored halo went stale.  Buffers are recycled through a pool keyed by
     the exact shape, so steady-state inference neither allocates nor re-zeroes them."""
 
-    __slots__ = ("buf", "B", "C", "H", "W", "halo", "_key")
+    __slots__ = ("buf", "lo", "B", "C", "H", "W", "halo", "_key")
 
-    def __init__(self, B, C, H, W, device):
+    def __init__(self, B, C, H, W, device, split=False):
         nbytes = lib.pcnn_blk8_bytes(B, C, H, W)
         if nbytes == 0:
             raise ValueError("Blk8: bad shape")
         self._key = (str(device), B, C, H, W)
-        pool = _BLK8_POOL.get(self._key)
-        if pool:
-            self.buf, self.halo = pool.pop()
-        else:
-            self.buf = torch.zeros(nbytes // 2, dtype=torch.float16, device=device)
-            self.halo = (PAD_CONSTANT, 7)
+        self.buf = _blk8_buffer(self._key, nbytes, device)
+        self.lo = _blk8_buffer(self._key, nbytes, device) if split else None
         self.B, self.C, self.H, self.W = B, C, H, W
+        self.halo = (PAD_CONSTANT, 7)
 
     def __del__(self):
         try:
-            _BLK8_POOL.setdefault(self._key, []).append((self.buf, self.halo))
+            # a mirrored halo must not leak into the next user: such buffers are re-zeroed on reuse
+            dirty = self.halo[0] != PAD_CONSTANT
+            pool = _BLK8_POOL.setdefault(self._key, [])
+            pool.append((self.buf, dirty))
+            if self.lo is not None:
+                pool.append((self.lo, dirty))
         except Exception:
             pass
 
@@ -460,26 +474,38 @@ class Blk8:
     def device(self):
         return self.buf.device
 
-    def plane_ptr(self, c_offset):
-        """Device address of channel plane c_offset/8 of sample 0 (in-place concat)."""
+    @property
+    def split(self):
+        return self.lo is not None
+
+    def _plane_off(self, c_offset):
         if c_offset % 8:
             raise ValueError("channel offset must be a multiple of 8")
-        return self.buf.data_ptr() + (c_offset // 8) * (self.H + 14) * (self.W + 14) * 16
+        return (c_offset // 8) * (self.H + 14) * (self.W + 14) * 16
+
+    def plane_ptr(self, c_offset):
+        """Device address of channel plane c_offset/8 of sample 0 (in-place concat)."""
+        return self.buf.data_ptr() + self._plane_off(c_offset)
+
+    def plane_ptr_lo(self, c_offset):
+        return None if self.lo is None else self.lo.data_ptr() + self._plane_off(c_offset)
 
 
 def blk8_pool_clear():
     _BLK8_POOL.clear()
 
 
-def to_blk8(x, out=None, c_total=None, c_offset=0):
+def to_blk8(x, out=None, c_total=None, c_offset=0, split=False):
     """NCHW fp32 -> BLK8 (optionally into channels [c_offset, c_offset+C) of a wider buffer)."""
     in_bs = _nchw_bstride(x, "x")
     B, C, H, W = x.shape
     if out is None:
-        out = Blk8(B, c_total or C, H, W, x.device)
+        out = Blk8(B, c_total or C, H, W, x.device, split=split)
     if (out.B, out.H, out.W) != (B, H, W):
         raise ValueError("to_blk8: destination shape mismatch")
-    check(lib.pcnn_to_blk8(_p(x), _p(out.buf), B, C, H, W, out.C, int(c_offset), in_bs, _stream()), "to_blk8")
+    check(lib.pcnn_to_blk8(_p(x), _p(out.buf), _p(out.lo), B, C, H, W, out.C, int(c_offset), in_bs, _stream()), "to_blk8")
+    if out.halo[0] != PAD_CONSTANT:
+        out.halo = (out.halo[0], -1)
     return out
 
 
@@ -488,7 +514,7 @@ def from_blk8(t, C=None, c_offset=0, out=None):
     if out is None:
         out = torch.empty((t.B, C, t.H, t.W), device=t.device, dtype=torch.float32)
     out_bs = _nchw_bstride(out, "out")
-    check(lib.pcnn_from_blk8(_p(t.buf), _p(out), t.B, C, t.H, t.W, t.C, int(c_offset), out_bs, _stream()), "from_blk8")
+    check(lib.pcnn_from_blk8(_p(t.buf), _p(t.lo), _p(out), t.B, C, t.H, t.W, t.C, int(c_offset), out_bs, _stream()), "from_blk8")
     return out
 
 
@@ -502,19 +528,21 @@ def blk8_halo_fill(t, pad, mode):
         return t
     if mode == PAD_CONSTANT:
         pad = 7
-    check(lib.pcnn_blk8_halo_fill(_p(t.buf), t.B, t.C, t.H, t.W, pad, mode, _stream()), "blk8_halo_fill")
+    for b in (t.buf, t.lo):
+        if b is not None:
+            check(lib.pcnn_blk8_halo_fill(_p(b), t.B, t.C, t.H, t.W, pad, mode, _stream()), "blk8_halo_fill")
     t.halo = (mode, pad)
     return t
 
 
-def pack_conv_weights_tc(kernel):
-    """Keras [k,k,Cin,Cout] fp32 -> packed fp16 operand image (done once per layer)."""
+def pack_conv_weights_tc(kernel, nsplit=1):
+    """Keras [k,k,Cin,Cout] fp32 -> packed fp16 operand image (done once per layer); nsplit=2 adds W_lo."""
     _chk(kernel, "kernel")
     kh, kw, Cin, Cout = kernel.shape
-    n = lib.pcnn_conv_tc_packed_weight_bytes(kh, kw, Cin)
+    n = lib.pcnn_conv_tc_packed_weight_bytes(kh, kw, Cin, int(nsplit))
     packed = torch.empty(n // 2, dtype=torch.float16, device=kernel.device)
-    check(lib.pcnn_conv_tc_pack_weights(_p(kernel.contiguous()), _p(packed), kh, kw, Cin, Cout, _stream()), "conv_tc_pack_weights")
-    return {"packed": packed, "k": kh, "cin": Cin, "cout": Cout}
+    check(lib.pcnn_conv_tc_pack_weights(_p(kernel.contiguous()), _p(packed), kh, kw, Cin, Cout, int(nsplit), _stream()), "conv_tc_pack_weights")
+    return {"packed": packed, "k": kh, "cin": Cin, "cout": Cout, "nsplit": int(nsplit)}
 
 
 _NUM_SMS = {}
@@ -528,27 +556,33 @@ def _num_sms(device):
 
 def conv2d_tc(x, wp, bias=None, act=ACT_LINEAR, pad_mode=PAD_CONSTANT, bn=None, residual=None, out_scale=None,
               out=None, out_channels_total=None, out_c_offset=0):
-    """tcgen05 convolution on BLK8 tensors.  x: Blk8 with >= wp['cin'] channels; returns a Blk8."""
+    """tcgen05 convolution on BLK8 tensors.  x: Blk8 with >= wp['cin'] channels; returns a Blk8.
+    Split precision is selected by the packed weights (wp['nsplit'] == 2 needs split tensors)."""
     if not isinstance(x, Blk8):
         raise ValueError("conv2d_tc: x must be a Blk8 tensor (use to_blk8)")
-    k, cout = wp["k"], wp["cout"]
+    k, cout, nsplit = wp["k"], wp["cout"], wp["nsplit"]
     if -(-wp["cin"] // 16) != -(-x.C // 16):
         raise ValueError("conv2d_tc: kernel expects %d input channels, tensor holds %d" % (wp["cin"], x.C))
+    split = nsplit == 2
+    if split and not x.split:
+        raise ValueError("conv2d_tc: split-precision weights need a split (hi+lo) input tensor")
     blk8_halo_fill(x, k // 2, pad_mode)
     if out is None:
-        out = Blk8(x.B, out_channels_total or cout, x.H, x.W, x.device)
-    if (out.B, out.H, out.W) != (x.B, x.H, x.W):
-        raise ValueError("conv2d_tc: destination shape mismatch")
-    if residual is not None and (residual.B, residual.H, residual.W) != (x.B, x.H, x.W):
-        raise ValueError("conv2d_tc: residual shape mismatch")
+        out = Blk8(x.B, out_channels_total or cout, x.H, x.W, x.device, split=split)
+    if (out.B, out.H, out.W) != (x.B, x.H, x.W) or (split and not out.split):
+        raise ValueError("conv2d_tc: destination shape / precision mismatch")
+    if residual is not None and ((residual.B, residual.H, residual.W) != (x.B, x.H, x.W) or (split and not residual.split)):
+        raise ValueError("conv2d_tc: residual shape / precision mismatch")
     bn_s, bn_t = (bn if bn is not None else (None, None))
     timed = KERNEL_TIMER is not None and KERNEL_TIMER.match(wp["cin"], cout, k, k, x.H, x.W)
     if timed:
         KERNEL_TIMER.start()
-    check(lib.pcnn_conv2d_tc(_p(x.buf), _p(wp["packed"]), _p(bias), _p(bn_s), _p(bn_t),
-                             None if residual is None else _p(residual.buf), _p(out_scale), out.plane_ptr(out_c_offset),
+    check(lib.pcnn_conv2d_tc(_p(x.buf), _p(x.lo) if split else None, _p(wp["packed"]), _p(bias), _p(bn_s), _p(bn_t),
+                             None if residual is None else _p(residual.buf),
+                             None if (residual is None or not split) else _p(residual.lo), _p(out_scale),
+                             out.plane_ptr(out_c_offset), out.plane_ptr_lo(out_c_offset) if split else None,
                              x.B, x.C, cout, out.C, 0 if residual is None else residual.C, x.H, x.W, k, int(act),
-                             _num_sms(x.device), _stream()), "conv2d_tc")
+                             nsplit, _num_sms(x.device), _stream()), "conv2d_tc")
     if timed:
         KERNEL_TIMER.stop(2.0 * x.B * x.H * x.W * k * k * wp["cin"] * cout)
     if out.halo[0] != PAD_CONSTANT:
@@ -556,15 +590,13 @@ def conv2d_tc(x, wp, bias=None, act=ACT_LINEAR, pad_mode=PAD_CONSTANT, bn=None, 
     return out
 
 
-def dbcnn_expand_blk8(h, modew, x_res):
+def dbcnn_expand_blk8(h, modew, x_res, split=False):
     """einsum('bmy,mx,bm->bmxy') + concat(pos) written straight into a BLK8 tensor [B, M+2, x_res, n]."""
     _chk(h, "h"); _chk(modew, "modew")
     h, modew = h.contiguous(), modew.contiguous()
     B, M, n = h.shape
     S = sinh_basis_table(h.device, M, x_res)
-    out = Blk8(B, M + 2, x_res, n, h.device)
+    out = Blk8(B, M + 2, x_res, n, h.device, split=split)
     check(lib.pcnn_dbcnn_expand_blk8(_p(h), _p(S), _p(modew), _p(position_table(h.device, x_res)),
-                                     _p(position_table(h.device, n)), _p(out.buf), B, M, x_res, n, _stream()), "dbcnn_expand_blk8")
-    if out.halo[0] != PAD_CONSTANT:
-        out.halo = (out.halo[0], -1)
+                                     _p(position_table(h.device, n)), _p(out.buf), _p(out.lo), B, M, x_res, n, _stream()), "dbcnn_expand_blk8")
     return out

@@ -149,3 +149,41 @@ def test_models_tc_mode_vs_oracle():
     print("tc-mode rel-L2 vs float64 oracle: pcnn %.3e  dbcnn %.3e  hpnn %.3e" % (e_pcnn, e_db, e_hp))
     assert e_pcnn < TC_TOL and e_db < TC_TOL
     assert e_hp < 2 * TC_TOL     # HPNN alone is deeper (45 convs) than the merged average; see DESIGN.md precision budget
+
+
+# ------------------------------------------------------------------ split precision (tc3)
+@pytest.mark.parametrize("B,Cin,Cout,H,W,k,act", [
+    (2, 32, 32, 8, 256, 15, 1),
+    (1, 64, 32, 9, 80, 7, 1),
+    (2, 29, 23, 20, 21, 7, 2),
+    (3, 12, 8, 5, 33, 3, 0),
+])
+def test_conv2d_tc3_parity(ops, B, Cin, Cout, H, W, k, act):
+    """hi/lo split operands, three MMAs: ~22 significand bits -> FP32-class agreement with the oracle."""
+    g = torch.Generator().manual_seed(B * 1000 + Cin * 10 + k + 1)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    kern = torch.randn(k, k, Cin, Cout, generator=g) / (k * Cin ** 0.5)
+    bias = torch.randn(Cout, generator=g) * 0.1
+    res = torch.randn(B, Cout, H, W, generator=g)
+    wp = ops.pack_conv_weights_tc(dev(kern), nsplit=2)
+    out = ops.conv2d_tc(ops.to_blk8(dev(x), split=True), wp, dev(bias), act, residual=ops.to_blk8(dev(res), split=True))
+    got = ops.from_blk8(out)
+    ref = O.conv_nd(x.double(), kern.double(), bias.double(), ACTS[act], "CONSTANT", 0.0) + res.double()
+    assert rel_l2(got, ref) < 5e-6
+
+
+def test_models_tc3_mode_vs_oracle():
+    import os
+    from tests.helpers import GOLDEN, pcnn_configs, all_weights
+    from poisson_cnn_b200.synthetic import make_problem
+    hp, db = pcnn_configs()
+    w = all_weights(hp, db)
+    model = _models(hp, db, w).set_precision("tc3")
+    keys = ("rhs", "left", "top", "right", "bottom", "dx")
+    g = np.load(os.path.join(GOLDEN, "pcnn_112x120.npz"))
+    e_pcnn = rel_l2(model([dev(g[k]) for k in keys]), g["out"])
+    p = make_problem(2, 128, 112, seed=52, magnitudes=False)
+    ref = O.hpnn_forward(hp, w, p["rhs"].double(), p["dx"].double(), "hpnn/")
+    e_hp = rel_l2(model.hpnn([dev(p["rhs"]), dev(p["dx"])]), ref)
+    print("tc3-mode rel-L2 vs float64 oracle: pcnn %.3e  hpnn %.3e" % (e_pcnn, e_hp))
+    assert e_pcnn < 1e-4 and e_hp < 1e-4      # two orders inside the 2e-3 tensor-core budget
