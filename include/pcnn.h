@@ -193,8 +193,10 @@ int pcnn_dbcnn_expand_blk8(const float* h, const float* sinh_basis, const float*
 /* Keras kernel [k,k,Cin,Cout] fp32 -> fp16 operand image of the row-group GEMM:
  * [ceil(Cin/16)][k][2][(k+6)*32][8] (see conv_tc.cu).  Done once per layer at load time. */
 size_t pcnn_conv_tc_packed_weight_bytes(int kh, int kw, int Cin, int nsplit);
+/* scale: a power of two applied to the weights before rounding (keeps W_hi and W_lo in fp16's
+ * normal range); pass its reciprocal as acc_scale to pcnn_conv2d_tc, which undoes it exactly. */
 int pcnn_conv_tc_pack_weights(const float* kernel, void* packed, int kh, int kw, int Cin, int Cout,
-                              int nsplit, void* stream);
+                              int nsplit, float scale, void* stream);
 /* Same operator as pcnn_conv2d_f32 (pad + VALID conv + bias + act [+BN] [+residual] [*out_scale]) on
  * tcgen05 tensor cores: FP16 operands, FP32 accumulation in TMEM.  in/out/residual are BLK8 buffers
  * with Cin_total / Cout_total / Cres_total channels; the padding mode is whatever the halo of `in`
@@ -209,7 +211,7 @@ int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpack, const f
                    const float* bn_scale, const float* bn_shift, const void* residual,
                    const void* residual_lo, const float* out_scale, void* out, void* out_lo, int B,
                    int Cin_total, int Cout, int Cout_total, int Cres_total, int H, int W, int k, int act,
-                   int nsplit, int num_sms, void* stream);
+                   int nsplit, float acc_scale, int num_sms, void* stream);
 
 #ifdef __cplusplus
 }

@@ -57,6 +57,7 @@ struct Params {
     const float* out_scale;  // [B][Cout] or null
     __half* out;             // BLK8 [B][c8_out][Hp][P][8]
     __half* out_lo;          // lo part of the output (split precision) or null
+    float acc_scale;         // exact power of two undoing the weight pre-scaling (applied to the accumulator)
     int nsplit;              // 1: single FP16 pass; 2: hi/lo operands, 3 MMAs per (chunk,tap,row)
     int nv;                  // virtual K-chunks = c16 * (nsplit == 2 ? 3 : 1)
     int B, H, W, Hp, P;
@@ -308,6 +309,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
         const int ncols_half = ((p.n_tile / 2 + 31) / 32) * 32;   // columns handled by half 0 (multiple of 32)
         const int c_begin = half * ncols_half, c_end = half ? p.n_tile : min(ncols_half, p.n_tile);
         const int act = p.act;
+        const float asc = p.acc_scale;
         uint32_t it = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
             const int tx = t % p.tiles_x;
@@ -333,20 +335,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                     if (act == PCNN_ACT_LEAKY_RELU) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            float f = __uint_as_float(v[j]) + bias;
+                            float f = fmaf(__uint_as_float(v[j]), asc, bias);
                             f = fmaxf(f, 0.2f * f);
                             v[j] = __float_as_uint(fmaf(f, mul, add));
                         }
                     } else if (act == PCNN_ACT_TANH) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const float a = __uint_as_float(v[j]) + bias;
+                            const float a = fmaf(__uint_as_float(v[j]), asc, bias);
                             const float f = (p.nsplit == 2) ? tanhf(a) : tanh_approx(a);
                             v[j] = __float_as_uint(fmaf(f, mul, add));
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]) + bias, mul, add));
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(fmaf(__uint_as_float(v[j]), asc, bias), mul, add));
                     }
                     if (p.residual) {
                         // residual: coalesced 16-B loads -> transpose buffer -> per-(channel, pixel) fp32 add
@@ -400,7 +402,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
 // ---------------------------------------------------------------- layout / packing kernels
 // Keras kernel [kh][kw][Cin][Cout] fp32 -> packed fp16 [C16][kw][2][(kh+6)*32][8]
 __global__ void pack_weights_kernel(const float* __restrict__ k, __half* __restrict__ out, int kh, int kw,
-                                    int Cin, int Cout, int c16, long long total, int nsplit) {
+                                    int Cin, int Cout, int c16, long long total, int nsplit, float scale) {
     const int Z = kh + 2 * ZPAD;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -413,7 +415,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ k, __half* __restr
         const int c = t / kw;
         const int ci = c * 16 + pl * 8 + e, dy = z - ZPAD;
         float v = 0.f;
-        if (dy >= 0 && dy < kh && ci < Cin && co < Cout) v = k[(((long long)dy * kw + dx) * Cin + ci) * Cout + co];
+        if (dy >= 0 && dy < kh && ci < Cin && co < Cout) v = scale * k[(((long long)dy * kw + dx) * Cin + ci) * Cout + co];
         const __half h = __float2half_rn(v);
         out[idx] = h;
         if (nsplit == 2) out[total + idx] = __float2half_rn(v - __half2float(h));
@@ -540,14 +542,16 @@ extern "C" size_t pcnn_conv_tc_packed_weight_bytes(int kh, int kw, int Cin, int 
     return (size_t)(nsplit == 2 ? 2 : 1) * ((Cin + 15) / 16) * kw * 2 * (kh + 2 * ZPAD) * COUT_PAD * 8 * sizeof(__half);
 }
 
-extern "C" int pcnn_conv_tc_pack_weights(const float* kernel, void* packed, int kh, int kw, int Cin, int Cout, int nsplit, void* stream) {
+extern "C" int pcnn_conv_tc_pack_weights(const float* kernel, void* packed, int kh, int kw, int Cin, int Cout, int nsplit,
+                                         float scale, void* stream) {
+    PCNN_CHECK_ARG(scale > 0.f, "conv_tc_pack_weights: scale must be positive (a power of two)");
     PCNN_CHECK_ARG(nsplit == 1 || nsplit == 2, "conv_tc_pack_weights: nsplit must be 1 or 2");
     PCNN_CHECK_ARG(kernel && packed, "conv_tc_pack_weights: null pointer");
     PCNN_CHECK_ARG(kh == kw && (kh & 1) && kh >= 1 && kh <= 2 * HALO + 1, "conv_tc: kernel %dx%d not supported (odd, square, <= 15)", kh, kw);
     PCNN_CHECK_ARG(Cout >= 1 && Cout <= COUT_PAD && Cin >= 1, "conv_tc: Cout %d not in [1,32]", Cout);
     const int c16 = (Cin + 15) / 16;
     const long long total = (long long)c16 * kw * 2 * (kh + 2 * ZPAD) * COUT_PAD * 8;
-    pack_weights_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(kernel, (__half*)packed, kh, kw, Cin, Cout, c16, total, nsplit);
+    pack_weights_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(kernel, (__half*)packed, kh, kw, Cin, Cout, c16, total, nsplit, scale);
     PCNN_CHECK_LAUNCH();
     return PCNN_OK;
 }
@@ -597,7 +601,7 @@ extern "C" int pcnn_dbcnn_expand_blk8(const float* h, const float* sinh_basis, c
 extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpack, const float* bias, const float* bn_scale,
                               const float* bn_shift, const void* residual, const void* residual_lo, const float* out_scale,
                               void* out, void* out_lo, int B, int Cin_total, int Cout, int Cout_total, int Cres_total,
-                              int H, int W, int k, int act, int nsplit, int num_sms, void* stream) {
+                              int H, int W, int k, int act, int nsplit, float acc_scale, int num_sms, void* stream) {
     PCNN_CHECK_ARG(in && wpack && out, "conv2d_tc: null pointer");
     PCNN_CHECK_ARG(nsplit == 1 || nsplit == 2, "conv2d_tc: nsplit must be 1 or 2");
     if (nsplit == 2) PCNN_CHECK_ARG(in_lo && out_lo && (!residual || residual_lo), "conv2d_tc: split precision needs the lo buffers");
@@ -609,7 +613,7 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
     p.in = (const __half*)in; p.in_lo = (const __half*)in_lo; p.wpack = (const __half*)wpack; p.bias = bias;
     p.bn_scale = bn_scale; p.bn_shift = bn_shift;
     p.residual = (const __half*)residual; p.residual_lo = (const __half*)residual_lo; p.out_scale = out_scale;
-    p.out = (__half*)out; p.out_lo = (__half*)out_lo; p.nsplit = nsplit;
+    p.out = (__half*)out; p.out_lo = (__half*)out_lo; p.nsplit = nsplit; p.acc_scale = acc_scale;
     p.B = B; p.H = H; p.W = W; p.Hp = H + 2 * HALO; p.P = W + 2 * HALO;
     p.c16 = (Cin_total + 15) / 16;
     p.nv = p.c16 * (nsplit == 2 ? 3 : 1);

@@ -541,8 +541,12 @@ def pack_conv_weights_tc(kernel, nsplit=1):
     kh, kw, Cin, Cout = kernel.shape
     n = lib.pcnn_conv_tc_packed_weight_bytes(kh, kw, Cin, int(nsplit))
     packed = torch.empty(n // 2, dtype=torch.float16, device=kernel.device)
-    check(lib.pcnn_conv_tc_pack_weights(_p(kernel.contiguous()), _p(packed), kh, kw, Cin, Cout, int(nsplit), _stream()), "conv_tc_pack_weights")
-    return {"packed": packed, "k": kh, "cin": Cin, "cout": Cout, "nsplit": int(nsplit)}
+    # power-of-two pre-scale so that max|W| lands near 2^9: W_hi and the remainder W_lo (~2^-12 |W|) both stay in
+    # fp16's normal range; the kernel multiplies the accumulator by 1/scale (exact).  One host sync at pack time.
+    wmax = float(kernel.abs().max())
+    scale = 2.0 ** max(-24, min(24, math.floor(math.log2(512.0 / wmax)))) if wmax > 0 and math.isfinite(wmax) else 1.0
+    check(lib.pcnn_conv_tc_pack_weights(_p(kernel.contiguous()), _p(packed), kh, kw, Cin, Cout, int(nsplit), scale, _stream()), "conv_tc_pack_weights")
+    return {"packed": packed, "k": kh, "cin": Cin, "cout": Cout, "nsplit": int(nsplit), "acc_scale": 1.0 / scale}
 
 
 _NUM_SMS = {}
@@ -582,7 +586,7 @@ def conv2d_tc(x, wp, bias=None, act=ACT_LINEAR, pad_mode=PAD_CONSTANT, bn=None, 
                              None if (residual is None or not split) else _p(residual.lo), _p(out_scale),
                              out.plane_ptr(out_c_offset), out.plane_ptr_lo(out_c_offset) if split else None,
                              x.B, x.C, cout, out.C, 0 if residual is None else residual.C, x.H, x.W, k, int(act),
-                             nsplit, _num_sms(x.device), _stream()), "conv2d_tc")
+                             nsplit, wp["acc_scale"], _num_sms(x.device), _stream()), "conv2d_tc")
     if timed:
         KERNEL_TIMER.stop(2.0 * x.B * x.H * x.W * k * k * wp["cin"] * cout)
     if out.halo[0] != PAD_CONSTANT:
