@@ -227,9 +227,15 @@ def run_ours(args):
     roofline = None
     if ks:
         ach = ks["flops_per_launch"] / (ks["avg_ms"] * 1e-3) / 1e12
+        kk = args.roofline_kernel[2]
+        issue_factor = {"tc": 1.0, "tc3": 3.0}.get(args.precision, 0.0) * (kk + 3.0) / kk   # MMAs issued per algorithmic MAC
         roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
                     "frac": ach / peaks["tflops"], "traffic": None, "kernel": "conv2d %d->%d k%d (%s)" % (args.roofline_kernel + (args.precision,)),
-                    "launches_timed": ks["launches"], "avg_launch_ms": ks["avg_ms"], "peak_source": peaks["source"] + " bf16 sustained"}
+                    "launches_timed": ks["launches"], "avg_launch_ms": ks["avg_ms"], "peak_source": peaks["source"] + " bf16 sustained",
+                    "algorithmic_flops_per_launch": ks["flops_per_launch"],
+                    "mma_issued_tflops": ach * issue_factor if issue_factor else None,
+                    "mma_issued_frac": ach * issue_factor / peaks["tflops"] if issue_factor else None,
+                    "note": "achieved/frac count ALGORITHMIC conv FLOPs once; the kernel issues (k+3)/k x that in MMAs (row-group zero padding) and 3x in tc3 (hi/lo operand split)"}
 
     # ---------------- accuracy + residual of what was timed (outside the timed region) ----------------
     acc = None
@@ -248,6 +254,25 @@ def run_ours(args):
             cpu_baseline = {"value": val, "unit": "solutions/s", "cores": threads, "kind": "port",
                             "sample": "%d single-sample %dx%d Poisson_CNN forwards, torch-CPU fp32 oracle (TensorFlow reference not installable offline)" % (n, nx, ny)}
 
+    # ---------------- the other precision modes, briefly (N=1 only; informational) ----------------
+    other = {}
+    if world == 1 and args.other_modes:
+        for mode in [m for m in args.other_modes.split(",") if m and m != args.precision]:
+            model.set_precision(mode)
+            nst = 1 if mode == "fp32" else 2
+            o = model(dev_in)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(nst):
+                o = model(dev_in)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / nst
+            nchk = min(B, args.check_samples)
+            err = float((o[:nchk].double().cpu() - ref).norm() / ref.norm())
+            other[mode] = {"value": B / (ms / 1000.0), "ms_per_step": ms, "rel_l2_vs_oracle_f64": err, "steps": nst}
+        model.set_precision(args.precision)
+
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -265,6 +290,7 @@ def run_ours(args):
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "accuracy": acc,
+            "other_modes": other,
             "model_tflops": value / world * pcnn_flops(nx, ny) / 1e12,
             "frac_of_bf16_sustained_peak": value / world * pcnn_flops(nx, ny) / 1e12 / peaks["tflops"],
         }
@@ -281,7 +307,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="samples per GPU per step (BASELINE configs[1]: 256)")
     ap.add_argument("--grid", type=int, default=256)
-    ap.add_argument("--precision", default=os.environ.get("PCNN_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("PCNN_PRECISION", "tc3"), choices=["fp32", "tc", "tc3"],
+                    help="tc3 (default): tcgen05 with split-FP16 operands, holds the 2e-3 budget; tc: single FP16 pass; fp32: strict CUDA-core path")
+    ap.add_argument("--other-modes", default="tc,fp32", help="comma list of extra precision modes timed briefly at N=1 (reported under other_modes)")
     ap.add_argument("--check-samples", type=int, default=2)
     ap.add_argument("--cpu-budget-s", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
