@@ -13,12 +13,15 @@ from ._base import WeightedModel
 
 
 class Poisson_CNN_Legacy(WeightedModel):
-    def __init__(self, hpnn, dbcnn, jacobi_iterations=0):
+    def __init__(self, hpnn, dbcnn, jacobi_iterations=0, max_microbatch=64):
         super().__init__()
         self.hpnn = hpnn
         self.dbcnn = dbcnn
         self.data_format = hpnn.data_format
         self.jacobi_iterations = jacobi_iterations
+        # samples are independent end to end, so a large batch is processed in slices of this many samples:
+        # bounds activation memory (the DBCNN sees 4x the slice) without changing any result
+        self.max_microbatch = max_microbatch
 
     def weight_specs(self, prefix=""):
         hs, hm = self.hpnn.weight_specs(prefix + "hpnn/")
@@ -45,6 +48,17 @@ class Poisson_CNN_Legacy(WeightedModel):
         for t, n, name in ((left, ny, "left"), (right, ny, "right"), (top, nx, "top"), (bottom, nx, "bottom")):
             if tuple(t.shape) != (B, 1, n):
                 raise ValueError("%s boundary must be [batch, 1, %d], got %s" % (name, n, tuple(t.shape)))
+        mb = self.max_microbatch
+        if mb and B > mb:
+            out = torch.empty((B, 1, nx, ny), device=rhs.device, dtype=torch.float32)
+            for lo in range(0, B, mb):
+                out[lo:lo + mb] = self._forward([t[lo:lo + mb] for t in (rhs, left, top, right, bottom, dx)])
+            return out
+        return self._forward([rhs, left, top, right, bottom, dx])
+
+    def _forward(self, inp):
+        rhs, left, top, right, bottom, dx = inp
+        B, _, nx, ny = rhs.shape
 
         # per-sample max-normalisation of the five inputs (set_max_magnitude_in_batch_and_return_scaling_factors)
         mrhs = ops.maxabs(rhs)
