@@ -128,6 +128,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        torch.set_num_threads(os.cpu_count() or 1)
     from poisson_cnn_b200 import load_experiment, weights as W
     cfg = load_experiment("pcnn_end_to_end")
     hp_cfg, db_cfg = cfg["hpnn_model"], cfg["dbcnn_model"]

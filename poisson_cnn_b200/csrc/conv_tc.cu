@@ -266,23 +266,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                 const uint32_t d_tmem = tmem_base + acc * 256;
                 uint32_t accum = 0;
                 for (int c = 0; c < p.nv; ++c) {
+                    // rows of this chunk occupy ring slots [slot0, slot0+R) mod nslots: split at the wrap
+                    // point so the inner loops carry no wrap test
+                    const int n1 = min((int)(nslots - slot0), R);
                     for (int dx = 0; dx < p.kw; ++dx) {
                         mbar_wait(w_full + wst, wph);
                         tc_fence_after();
                         uint32_t a_lo = ((w_base16 + wst * wstage16) & 0x3FFF) | a_lo_lbo;
-                        uint32_t slot = slot0, ph = slot0_ph;
-                        uint32_t b_lo = ((rows_base16 + slot * slot16 + dx) & 0x3FFF) | b_lo_lbo;
                         const bool first_dx = (dx == 0), last_dx = (dx == p.kw - 1);
-                        for (int rho = 0; rho < R; ++rho) {
-                            if (first_dx) { mbar_wait(row_full + slot, ph); tc_fence_after(); }
-                            if (leader) {
-                                tc_mma_f16(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, accum);
-                                if (last_dx) tc_commit(row_empty + slot);   // row no longer needed
+#pragma unroll 1
+                        for (int seg = 0; seg < 2; ++seg) {
+                            const int nrow = seg ? R - n1 : n1;
+                            uint32_t slot = seg ? 0u : slot0;
+                            const uint32_t ph = seg ? (slot0_ph ^ 1u) : slot0_ph;
+                            uint32_t b_lo = ((rows_base16 + slot * slot16 + dx) & 0x3FFF) | b_lo_lbo;
+                            if (first_dx) {
+                                for (int i = 0; i < nrow; ++i) {
+                                    mbar_wait(row_full + slot, ph);
+                                    tc_fence_after();
+                                    if (leader) {
+                                        tc_mma_f16(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, accum);
+                                        if (last_dx) tc_commit(row_empty + slot);   // 1x1 kernels: first tap is also the last
+                                    }
+                                    accum = 1; a_lo += 32; b_lo += slot16; ++slot;
+                                }
+                            } else if (last_dx) {
+                                for (int i = 0; i < nrow; ++i) {
+                                    if (leader) {
+                                        tc_mma_f16(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, 1u);
+                                        tc_commit(row_empty + slot);   // row no longer needed
+                                    }
+                                    a_lo += 32; b_lo += slot16; ++slot;
+                                }
+                            } else if (leader) {
+#pragma unroll 4
+                                for (int i = 0; i < nrow; ++i) {
+                                    tc_mma_f16(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, 1u);
+                                    a_lo += 32; b_lo += slot16;
+                                }
+                            } else {
+                                a_lo += 32u * nrow;
                             }
-                            accum = 1;
-                            a_lo += 32;                                  // next A window: +512 B
-                            b_lo += slot16;
-                            if (++slot == nslots) { slot = 0; ph ^= 1; b_lo -= nslots * slot16; }
                         }
                         if (leader) tc_commit(w_empty + wst);
                         if (++wst == nwst) { wst = 0; wph ^= 1; }
