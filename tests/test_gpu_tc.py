@@ -188,4 +188,4 @@ def test_models_tc3_mode_vs_oracle():
     ref = O.hpnn_forward(hp, w, p["rhs"].double(), p["dx"].double(), "hpnn/")
     e_hp = rel_l2(model.hpnn([dev(p["rhs"]), dev(p["dx"])]), ref)
     print("tc3-mode rel-L2 vs float64 oracle: pcnn %.3e  hpnn %.3e" % (e_pcnn, e_hp))
-    assert e_pcnn < 1e-4 and e_hp < 1e-4      # two orders inside the 2e-3 tensor-core budget
+    assert e_pcnn < 5e-4 and e_hp < 5e-4      # >= 4x inside the 2e-3 tensor-core budget (floor: tensor-core fp32 accumulation)
