@@ -233,7 +233,7 @@ def run_ours(args):
     if ks:
         ach = ks["flops_per_launch"] / (ks["avg_ms"] * 1e-3) / 1e12
         kk = args.roofline_kernel[2]
-        issue_factor = {"tc": 1.0, "tc3": 3.0}.get(args.precision, 0.0) * (kk + 3.0) / kk   # MMAs issued per algorithmic MAC
+        issue_factor = {"tc": 1.0, "tc3": 3.0, "tc2": 2.0}.get(args.precision, 0.0) * (kk + 3.0) / kk   # MMAs issued per algorithmic MAC
         roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
                     "frac": ach / peaks["tflops"], "traffic": None, "kernel": "conv2d %d->%d k%d (%s)" % (args.roofline_kernel + (args.precision,)),
                     "launches_timed": ks["launches"], "avg_launch_ms": ks["avg_ms"], "peak_source": peaks["source"] + " bf16 sustained",
@@ -284,7 +284,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "solutions/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"fp32": "f32", "tc": "f16", "tc3": "f16 hi+lo split (3 MMAs), f32 accumulate"}.get(args.precision, args.precision), "data": "synthetic",
+            "vs_baseline": None, "dtype": {"fp32": "f32", "tc": "f16", "tc3": "f16 hi+lo split (3 MMAs), f32 accumulate", "tc2": "f16 + e4m3 correction MMA (K=32), f32 accumulate"}.get(args.precision, args.precision), "data": "synthetic",
             "config": {"workload": "Poisson_CNN_Legacy forward (HPNN + 4x DBCNN merged), batch %d per GPU, %dx%d grids, pcnn_end_to_end architecture, precision mode %s" % (B, nx, ny, args.precision),
                        "per_gpu_batch": B, "global_batch": B * world, "grid": [nx, ny], "parallelism": "batch-sharded x%d" % world,
                        "l2": "inputs+activations per step (%.1f GB) exceed the 126 MB L2" % (B * nx * ny * 4 * 32 / 1e9),
@@ -312,7 +312,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="samples per GPU per step (BASELINE configs[1]: 256)")
     ap.add_argument("--grid", type=int, default=256)
-    ap.add_argument("--precision", default=os.environ.get("PCNN_PRECISION", "tc3"), choices=["fp32", "tc", "tc3"],
+    ap.add_argument("--precision", default=os.environ.get("PCNN_PRECISION", "tc3"), choices=["fp32", "tc", "tc2", "tc3"],
                     help="tc3 (default): tcgen05 with split-FP16 operands, holds the 2e-3 budget; tc: single FP16 pass; fp32: strict CUDA-core path")
     ap.add_argument("--other-modes", default="tc,fp32", help="comma list of extra precision modes timed briefly at N=1 (reported under other_modes)")
     ap.add_argument("--check-samples", type=int, default=2)

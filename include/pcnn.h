@@ -179,17 +179,19 @@ int pcnn_dst_solve(const float* rhs, const float* left, const float* top, const 
 size_t pcnn_blk8_bytes(int B, int C, int H, int W);
 /* NCHW fp32 [B,C,H,W] (batch stride in_bstride) -> channels [c_offset, c_offset+C) of a BLK8 buffer
  * holding c_total channels (c_offset multiple of 8: this is how concat is assembled in place). */
-int pcnn_to_blk8(const float* in, void* out, void* out_lo, int B, int C, int H, int W, int c_total,
+/* mode = precision mode of the tensor (see pcnn_conv2d_tc): 1 fp16 only; 2 second buffer = fp16
+ * remainder; 3 second buffer = e4m3 planes (2c: x, 2c+1: remainder * 2^11, 16 channels each). */
+int pcnn_to_blk8(const float* in, void* out, void* out_lo, int mode, int B, int C, int H, int W, int c_total,
                  int c_offset, int64_t in_bstride, void* stream);
-int pcnn_from_blk8(const void* in, const void* in_lo, float* out, int B, int C, int H, int W, int c_total,
-                   int c_offset, int64_t out_bstride, void* stream);
+int pcnn_from_blk8(const void* in, const void* in_lo, int mode, float* out, int B, int C, int H, int W,
+                   int c_total, int c_offset, int64_t out_bstride, void* stream);
 /* tf.pad ring of width pad (<= 7) around the interior: mode PCNN_PAD_CONSTANT writes zeros,
  * PCNN_PAD_SYMMETRIC mirrors (utils/apply_advanced_padding_and_call_conv_layer.py:18). */
 int pcnn_blk8_halo_fill(void* buf, int B, int C, int H, int W, int pad, int mode, void* stream);
 /* pcnn_dbcnn_expand_f32 writing the BLK8 layout directly (the [B,29,H,W] fp32 tensor never exists). */
 int pcnn_dbcnn_expand_blk8(const float* h, const float* sinh_basis, const float* modew, const float* posx,
-                           const float* posy, void* out, void* out_lo, int B, int M, int xres, int n,
-                           void* stream);
+                           const float* posy, void* out, void* out_lo, int mode, int B, int M, int xres,
+                           int n, void* stream);
 /* Keras kernel [k,k,Cin,Cout] fp32 -> fp16 operand image of the row-group GEMM:
  * [ceil(Cin/16)][k][2][(k+6)*32][8] (see conv_tc.cu).  Done once per layer at load time. */
 size_t pcnn_conv_tc_packed_weight_bytes(int kh, int kw, int Cin, int nsplit);
@@ -206,7 +208,11 @@ int pcnn_conv_tc_pack_weights(const float* kernel, void* packed, int kh, int kw,
  * rounding remainder of hi, written by the producers) and the weights are packed as W_hi and W_lo;
  * the kernel issues three MMAs per (chunk, tap, row): x_hi*W_hi + x_hi*W_lo + x_lo*W_hi, i.e. ~22
  * significand bits at 3x the tensor work.  nsplit = 1: single FP16 pass (11 bits, like TF32); the
- * *_lo pointers are NULL. */
+ * *_lo pointers are NULL.
+ * nsplit = 3: the two correction terms are evaluated by ONE e4m3 MMA of K = 32,
+ * [e4m3(x) ; e4m3(x_lo*2^11)] * [e4m3(W_lo) ; e4m3(W*2^-11)], into the same accumulator: 2x the tensor
+ * work of a single pass, ~15 significand bits.  The *_lo pointers are then the fp8 "q" buffers
+ * (same byte geometry as a BLK8 buffer: 16 B per pixel per plane). */
 int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpack, const float* bias,
                    const float* bn_scale, const float* bn_shift, const void* residual,
                    const void* residual_lo, const float* out_scale, void* out, void* out_lo, int B,

@@ -31,6 +31,7 @@
 //   alloc), 3..10 = epilogue (TMEM lane quarter = warp % 4, two warps per quarter split the columns).
 //   Two 256-column accumulators in TMEM let the epilogue of tile t overlap the MMAs of tile t+1.
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 #include "pcnn_common.cuh"
 
@@ -43,6 +44,7 @@ constexpr int COUT_PAD = 32;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = (3 + NUM_EPI_WARPS) * 32;
 constexpr int ZPAD = ROWS_PER_TILE - 1;   // zero z-rows on each side of the packed weights
+constexpr float LO_SCALE = 2048.f;        // 2^11: brings the fp16 rounding remainder into e4m3's range (mode 3)
 constexpr unsigned long long SPIN_LIMIT_NS = 4000000000ull;   // a stuck pipeline traps instead of hanging the GPU
 
 struct Params {
@@ -58,8 +60,10 @@ struct Params {
     __half* out;             // BLK8 [B][c8_out][Hp][P][8]
     __half* out_lo;          // lo part of the output (split precision) or null
     float acc_scale;         // exact power of two undoing the weight pre-scaling (applied to the accumulator)
-    int nsplit;              // 1: single FP16 pass; 2: hi/lo operands, 3 MMAs per (chunk,tap,row)
-    int nv;                  // virtual K-chunks = c16 * (nsplit == 2 ? 3 : 1)
+    int nsplit;              // precision mode: 1 single FP16 pass; 2 hi/lo fp16 split (3 MMAs per term);
+                             // 3 fp16 main pass + ONE e4m3 K=32 MMA for both correction terms (in_lo/out_lo/residual_lo
+                             // then point at the fp8 "q" buffers: planes 2c = e4m3(x), 2c+1 = e4m3((x - hi) * 2^11))
+    int nv;                  // virtual K-chunks = c16 * {1, 3, 2}
     int B, H, W, Hp, P;
     int c8_in, c8_out, c8_res;
     int c16;                 // input-channel chunks of 16
@@ -141,6 +145,16 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same shape with e4m3 operands: K = 32 per instruction at the same cycle cost (2x the fp16 rate)
+__device__ __forceinline__ void tc_mma_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ uint8_t to_e4m3(float f) { return (uint8_t)__nv_cvt_float_to_fp8(f, __NV_SATFINITE, __NV_E4M3); }
+__device__ __forceinline__ float from_e4m3(uint8_t b) { return __half2float(__half(__nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)b, __NV_E4M3))); }
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
@@ -208,8 +222,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                 const int col0 = x0 + HALO - p.pad;
                 for (int v = 0; v < p.nv; ++v) {
                     // split precision: per chunk c the passes are (x_hi,W_hi), (x_hi,W_lo), (x_lo,W_hi)
-                    const int c = (p.nsplit == 2) ? v / 3 : v;
-                    const __half* inp = (p.nsplit == 2 && (v % 3) == 2) ? p.in_lo : p.in;
+                    const int c = (p.nsplit == 2) ? v / 3 : (p.nsplit == 3 ? v >> 1 : v);
+                    const __half* inp = ((p.nsplit == 2 && (v % 3) == 2) || (p.nsplit == 3 && (v & 1))) ? p.in_lo : p.in;
                     for (int rho = 0; rho < R; ++rho, ++g) {
                         const uint32_t slot = g % p.row_slots, ph = (g / p.row_slots) & 1;
                         mbar_wait(row_empty + slot, ph ^ 1);
@@ -231,8 +245,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
             uint32_t g = 0;
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
                 for (int v = 0; v < p.nv; ++v) {
-                    const int c = (p.nsplit == 2) ? v / 3 : v;
-                    const int wsel = (p.nsplit == 2 && (v % 3) == 1) ? 1 : 0;   // W_lo only in the middle pass
+                    const int c = (p.nsplit == 2) ? v / 3 : (p.nsplit == 3 ? v >> 1 : v);
+                    const int wsel = ((p.nsplit == 2 && (v % 3) == 1) || (p.nsplit == 3 && (v & 1))) ? 1 : 0;   // second weight image
                     for (int dx = 0; dx < p.kw; ++dx, ++g) {
                         const uint32_t st = g % p.w_stages, ph = (g / p.w_stages) & 1;
                         mbar_wait(w_empty + st, ph ^ 1);
@@ -269,6 +283,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                     // rows of this chunk occupy ring slots [slot0, slot0+R) mod nslots: split at the wrap
                     // point so the inner loops carry no wrap test
                     const int n1 = min((int)(nslots - slot0), R);
+                    const bool f8 = (p.nsplit == 3) && (c & 1);    // correction pass: e4m3 operands, K = 32
                     for (int dx = 0; dx < p.kw; ++dx) {
                         mbar_wait(w_full + wst, wph);
                         tc_fence_after();
@@ -285,7 +300,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                                     mbar_wait(row_full + slot, ph);
                                     tc_fence_after();
                                     if (leader) {
-                                        tc_mma_f16(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, accum);
+                                        if (f8) tc_mma_f8(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, accum);
+                                        else tc_mma_f16(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, accum);
                                         if (last_dx) tc_commit(row_empty + slot);   // 1x1 kernels: first tap is also the last
                                     }
                                     accum = 1; a_lo += 32; b_lo += slot16; ++slot;
@@ -293,15 +309,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                             } else if (last_dx) {
                                 for (int i = 0; i < nrow; ++i) {
                                     if (leader) {
-                                        tc_mma_f16(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, 1u);
+                                        if (f8) tc_mma_f8(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, 1u);
+                                        else tc_mma_f16(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, 1u);
                                         tc_commit(row_empty + slot);   // row no longer needed
                                     }
                                     a_lo += 32; b_lo += slot16; ++slot;
                                 }
-                            } else if (leader) {
+                            } else if (leader && !f8) {
 #pragma unroll 4
                                 for (int i = 0; i < nrow; ++i) {
                                     tc_mma_f16(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, 1u);
+                                    a_lo += 32; b_lo += slot16;
+                                }
+                            } else if (leader) {
+#pragma unroll 4
+                                for (int i = 0; i < nrow; ++i) {
+                                    tc_mma_f8(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, 1u);
                                     a_lo += 32; b_lo += slot16;
                                 }
                             } else {
@@ -367,16 +390,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float a = fmaf(__uint_as_float(v[j]), asc, bias);
-                            const float f = (p.nsplit == 2) ? tanhf(a) : tanh_approx(a);
+                            const float f = (p.nsplit >= 2) ? tanhf(a) : tanh_approx(a);
                             v[j] = __float_as_uint(fmaf(f, mul, add));
                         }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(fmaf(__uint_as_float(v[j]), asc, bias), mul, add));
                     }
+                    constexpr int QGRP = 32 * 16 + 16;   // stride of a 16-channel fp8 group in the transpose buffer
+                    const int qgroups = (p.cout + 15) / 16;
+                    uint8_t* qrow = stage + (co >> 4) * QGRP + (co & 15);
                     if (p.residual) {
                         // residual: coalesced 16-B loads -> transpose buffer -> per-(channel, pixel) fp32 add
-                        for (int part = 0; part < p.nsplit; ++part) {
+                        const int nparts = (p.nsplit == 2) ? 2 : 1;
+                        for (int part = 0; part < nparts; ++part) {
                             const __half* rsrc = part ? p.residual_lo : p.residual;
                             for (int pl = 0; pl < planes_out; ++pl) {
                                 uint4 rv = make_uint4(0, 0, 0, 0);
@@ -390,8 +417,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                             }
                             __syncwarp();
                         }
+                        if (p.nsplit == 3) {   // remainder of the residual: e4m3 plane 2g+1, scaled by 2^11
+                            const uint8_t* rq = reinterpret_cast<const uint8_t*>(p.residual_lo);
+                            for (int g = 0; g < qgroups; ++g) {
+                                uint4 rv = make_uint4(0, 0, 0, 0);
+                                if (xok) rv = *reinterpret_cast<const uint4*>(rq + ((((size_t)b * p.c8_res + 2 * g + 1) * p.Hp + (y + HALO)) * p.P + (x + HALO)) * 16);
+                                *reinterpret_cast<uint4*>(stage + g * QGRP + lane * 16) = rv;
+                            }
+                            __syncwarp();
+                            if (live) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(from_e4m3(qrow[j * 16]), 1.0f / LO_SCALE, __uint_as_float(v[j])));
+                            }
+                            __syncwarp();
+                        }
                     }
-                    for (int part = 0; part < p.nsplit; ++part) {
+                    if (p.nsplit == 3) {
+                        // e4m3(x) for the next layer's correction MMA (plane 2g of the q buffer)
+                        uint8_t* dq = reinterpret_cast<uint8_t*>(p.out_lo);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) qrow[j * 16] = to_e4m3(__uint_as_float(v[j]));
+                        __syncwarp();
+                        for (int g = 0; g < qgroups; ++g) {
+                            const uint4 val = *reinterpret_cast<const uint4*>(stage + g * QGRP + lane * 16);
+                            if (xok) *reinterpret_cast<uint4*>(dq + ((((size_t)b * p.c8_out + 2 * g) * p.Hp + (y + HALO)) * p.P + (x + HALO)) * 16) = val;
+                        }
+                        __syncwarp();
+                    }
+                    const int nparts_out = (p.nsplit == 2) ? 2 : 1;
+                    for (int part = 0; part < nparts_out; ++part) {
                         // fp16 (hi), then the rounding remainder (lo), through the transpose buffer
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -404,6 +458,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                         for (int pl = 0; pl < planes_out; ++pl) {
                             const uint4 val = *reinterpret_cast<const uint4*>(stage + pl * STAGE_PLANE + lane * 16);
                             if (xok) *reinterpret_cast<uint4*>(dst + ((((size_t)b * p.c8_out + pl) * p.Hp + (y + HALO)) * p.P + (x + HALO)) * 8) = val;
+                        }
+                        __syncwarp();
+                    }
+                    if (p.nsplit == 3) {
+                        // e4m3((x - hi) * 2^11): plane 2g+1 of the q buffer
+                        uint8_t* dq = reinterpret_cast<uint8_t*>(p.out_lo);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) qrow[j * 16] = to_e4m3(__uint_as_float(v[j]) * LO_SCALE);
+                        __syncwarp();
+                        for (int g = 0; g < qgroups; ++g) {
+                            const uint4 val = *reinterpret_cast<const uint4*>(stage + g * QGRP + lane * 16);
+                            if (xok) *reinterpret_cast<uint4*>(dq + ((((size_t)b * p.c8_out + 2 * g + 1) * p.Hp + (y + HALO)) * p.P + (x + HALO)) * 16) = val;
                         }
                         __syncwarp();
                     }
@@ -443,6 +509,16 @@ __global__ void pack_weights_kernel(const float* __restrict__ k, __half* __restr
         const __half h = __float2half_rn(v);
         out[idx] = h;
         if (nsplit == 2) out[total + idx] = __float2half_rn(v - __half2float(h));
+        if (nsplit == 3) {
+            // fp8 image [c][dx][plane][z][co][16]: plane 0 = e4m3(W_lo) pairs with e4m3(x),
+            // plane 1 = e4m3(W * 2^-11) pairs with e4m3(x_lo * 2^11); ci16 = pl*8+e of the fp16 image
+            uint8_t* q = reinterpret_cast<uint8_t*>(out + total);
+            const long long stage_elems = 2LL * Z * COUT_PAD * 8;             // fp16 elements per (c,dx) stage == bytes / 2
+            const long long base = ((long long)c * kw + dx) * stage_elems * 2; // byte offset of the (c,dx) stage
+            const int ci16 = pl * 8 + e;
+            q[base + (((long long)0 * Z + z) * COUT_PAD + co) * 16 + ci16] = to_e4m3(v - __half2float(h));
+            q[base + (((long long)1 * Z + z) * COUT_PAD + co) * 16 + ci16] = to_e4m3(v * (1.0f / LO_SCALE));
+        }
     }
 }
 
@@ -472,9 +548,36 @@ __global__ void to_blk8_kernel(const float* __restrict__ in, __half* __restrict_
     }
 }
 
+// mode 3 companion of to_blk8: fp8 planes 2c = e4m3(x), 2c+1 = e4m3((x - fp16(x)) * 2^11), 16 channels each
+__global__ void to_q8_kernel(const float* __restrict__ in, uint8_t* __restrict__ outq, int C, int H, int W,
+                             int Hp, int P, int c8_total, int plane0, long long in_bstride, long long total) {
+    const int nc = (C + 15) / 16;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int x = idx % W;
+        long long t = idx / W;
+        const int y = t % H; t /= H;
+        const int cc = t % nc;
+        const long long b = t / nc;
+        __align__(16) uint8_t a8[16];
+        __align__(16) uint8_t l8[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const int c = cc * 16 + e;
+            const float f = c < C ? __ldg(in + b * in_bstride + ((long long)c * H + y) * W + x) : 0.f;
+            a8[e] = to_e4m3(f);
+            l8[e] = to_e4m3((f - __half2float(__float2half_rn(f))) * LO_SCALE);
+        }
+        const size_t off0 = ((((size_t)b * c8_total + plane0 + 2 * cc) * Hp + (y + HALO)) * P + (x + HALO)) * 16;
+        const size_t off1 = ((((size_t)b * c8_total + plane0 + 2 * cc + 1) * Hp + (y + HALO)) * P + (x + HALO)) * 16;
+        *reinterpret_cast<uint4*>(outq + off0) = *reinterpret_cast<const uint4*>(a8);
+        *reinterpret_cast<uint4*>(outq + off1) = *reinterpret_cast<const uint4*>(l8);
+    }
+}
+
 // BLK8 fp16 -> NCHW fp32
 __global__ void from_blk8_kernel(const __half* __restrict__ in, const __half* __restrict__ in_lo, float* __restrict__ out, int C, int H, int W,
-                                 int Hp, int P, int c8_total, int plane0, long long out_bstride, long long total) {
+                                 int Hp, int P, int c8_total, int plane0, long long out_bstride, long long total, int mode) {
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int x = idx % W;
@@ -484,7 +587,11 @@ __global__ void from_blk8_kernel(const __half* __restrict__ in, const __half* __
         const long long b = t / C;
         const size_t off = ((((size_t)b * c8_total + plane0 + (c >> 3)) * Hp + (y + HALO)) * P + (x + HALO)) * 8 + (c & 7);
         float f = __half2float(in[off]);
-        if (in_lo) f += __half2float(in_lo[off]);
+        if (in_lo && mode == 2) f += __half2float(in_lo[off]);
+        if (in_lo && mode == 3) {
+            const size_t qoff = ((((size_t)b * c8_total + plane0 + 2 * (c >> 4) + 1) * Hp + (y + HALO)) * P + (x + HALO)) * 16 + (c & 15);
+            f += from_e4m3(reinterpret_cast<const uint8_t*>(in_lo)[qoff]) * (1.0f / LO_SCALE);
+        }
         out[b * out_bstride + ((long long)c * H + y) * W + x] = f;
     }
 }
@@ -514,7 +621,7 @@ __global__ void blk8_halo_fill_kernel(__half* __restrict__ buf, int H, int W, in
 __global__ void dbcnn_expand_blk8_kernel(const float* __restrict__ h, const float* __restrict__ S,
                                          const float* __restrict__ mw, const float* __restrict__ posx,
                                          const float* __restrict__ posy, __half* __restrict__ out,
-                                         __half* __restrict__ out_lo, int M, int xres, int n, int c8_total, long long total) {
+                                         __half* __restrict__ out_lo, int M, int xres, int n, int c8_total, long long total, int mode) {
     const int Hp = xres + 2 * HALO, P = n + 2 * HALO;
     const int np = (M + 2 + 7) / 8;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -538,7 +645,23 @@ __global__ void dbcnn_expand_blk8_kernel(const float* __restrict__ h, const floa
         }
         const size_t off = ((((size_t)b * c8_total + pl) * Hp + (x + HALO)) * P + (y + HALO)) * 8;
         *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(v);
-        if (out_lo) *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(l);
+        if (out_lo && mode == 2) *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(l);
+        if (out_lo && mode == 3) {
+            // fp8 planes 2(pl/2), 2(pl/2)+1, bytes [8*(pl&1), +8): each thread fills its half of the 16-channel groups
+            uint8_t* q = reinterpret_cast<uint8_t*>(out_lo);
+            __align__(8) uint8_t a8[8];
+            __align__(8) uint8_t l8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float f = __half2float(v[e]) + __half2float(l[e]);   // == the fp32 value to within 2^-22
+                a8[e] = to_e4m3(f);
+                l8[e] = to_e4m3((f - __half2float(v[e])) * LO_SCALE);
+            }
+            const size_t q0 = ((((size_t)b * c8_total + 2 * (pl >> 1)) * Hp + (x + HALO)) * P + (y + HALO)) * 16 + 8 * (pl & 1);
+            const size_t q1 = ((((size_t)b * c8_total + 2 * (pl >> 1) + 1) * Hp + (x + HALO)) * P + (y + HALO)) * 16 + 8 * (pl & 1);
+            *reinterpret_cast<uint2*>(q + q0) = *reinterpret_cast<const uint2*>(a8);
+            *reinterpret_cast<uint2*>(q + q1) = *reinterpret_cast<const uint2*>(l8);
+        }
     }
 }
 
@@ -563,13 +686,13 @@ extern "C" size_t pcnn_blk8_bytes(int B, int C, int H, int W) {
 }
 
 extern "C" size_t pcnn_conv_tc_packed_weight_bytes(int kh, int kw, int Cin, int nsplit) {
-    return (size_t)(nsplit == 2 ? 2 : 1) * ((Cin + 15) / 16) * kw * 2 * (kh + 2 * ZPAD) * COUT_PAD * 8 * sizeof(__half);
+    return (size_t)(nsplit >= 2 ? 2 : 1) * ((Cin + 15) / 16) * kw * 2 * (kh + 2 * ZPAD) * COUT_PAD * 8 * sizeof(__half);
 }
 
 extern "C" int pcnn_conv_tc_pack_weights(const float* kernel, void* packed, int kh, int kw, int Cin, int Cout, int nsplit,
                                          float scale, void* stream) {
     PCNN_CHECK_ARG(scale > 0.f, "conv_tc_pack_weights: scale must be positive (a power of two)");
-    PCNN_CHECK_ARG(nsplit == 1 || nsplit == 2, "conv_tc_pack_weights: nsplit must be 1 or 2");
+    PCNN_CHECK_ARG(nsplit >= 1 && nsplit <= 3, "conv_tc_pack_weights: precision mode must be 1, 2 or 3");
     PCNN_CHECK_ARG(kernel && packed, "conv_tc_pack_weights: null pointer");
     PCNN_CHECK_ARG(kh == kw && (kh & 1) && kh >= 1 && kh <= 2 * HALO + 1, "conv_tc: kernel %dx%d not supported (odd, square, <= 15)", kh, kw);
     PCNN_CHECK_ARG(Cout >= 1 && Cout <= COUT_PAD && Cin >= 1, "conv_tc: Cout %d not in [1,32]", Cout);
@@ -580,22 +703,30 @@ extern "C" int pcnn_conv_tc_pack_weights(const float* kernel, void* packed, int 
     return PCNN_OK;
 }
 
-extern "C" int pcnn_to_blk8(const float* in, void* out, void* out_lo, int B, int C, int H, int W, int c_total, int c_offset,
+extern "C" int pcnn_to_blk8(const float* in, void* out, void* out_lo, int mode, int B, int C, int H, int W, int c_total, int c_offset,
                             int64_t in_bstride, void* stream) {
+    PCNN_CHECK_ARG(mode >= 1 && mode <= 3 && (mode == 1 || out_lo), "to_blk8: precision mode 2/3 needs the second buffer");
+    PCNN_CHECK_ARG(mode != 3 || (c_offset % 16) == 0, "to_blk8: mode 3 needs a channel offset that is a multiple of 16");
     PCNN_CHECK_ARG(in && out && B > 0 && C > 0 && (c_offset % 8) == 0 && c_offset + C <= ((c_total + 15) / 16) * 16, "to_blk8: bad argument");
     const int c8_total = ((c_total + 15) / 16) * 2;
     const long long total = (long long)B * ((C + 7) / 8) * H * W;
-    to_blk8_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(in, (__half*)out, (__half*)out_lo, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, in_bstride, total);
+    to_blk8_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(in, (__half*)out, mode == 2 ? (__half*)out_lo : nullptr, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, in_bstride, total);
     PCNN_CHECK_LAUNCH();
+    if (mode == 3) {
+        const long long tq = (long long)B * ((C + 15) / 16) * H * W;
+        to_q8_kernel<<<grid_for(tq), 256, 0, (cudaStream_t)stream>>>(in, (uint8_t*)out_lo, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, in_bstride, tq);
+        PCNN_CHECK_LAUNCH();
+    }
     return PCNN_OK;
 }
 
-extern "C" int pcnn_from_blk8(const void* in, const void* in_lo, float* out, int B, int C, int H, int W, int c_total, int c_offset,
+extern "C" int pcnn_from_blk8(const void* in, const void* in_lo, int mode, float* out, int B, int C, int H, int W, int c_total, int c_offset,
                               int64_t out_bstride, void* stream) {
+    PCNN_CHECK_ARG(mode >= 1 && mode <= 3, "from_blk8: bad precision mode");
     PCNN_CHECK_ARG(in && out && B > 0 && C > 0 && (c_offset % 8) == 0, "from_blk8: bad argument");
     const int c8_total = ((c_total + 15) / 16) * 2;
     const long long total = (long long)B * C * H * W;
-    from_blk8_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const __half*)in, (const __half*)in_lo, out, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, out_bstride, total);
+    from_blk8_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const __half*)in, mode >= 2 ? (const __half*)in_lo : nullptr, out, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, out_bstride, total, mode);
     PCNN_CHECK_LAUNCH();
     return PCNN_OK;
 }
@@ -613,11 +744,11 @@ extern "C" int pcnn_blk8_halo_fill(void* buf, int B, int C, int H, int W, int pa
 }
 
 extern "C" int pcnn_dbcnn_expand_blk8(const float* h, const float* sinh_basis, const float* modew, const float* posx,
-                                      const float* posy, void* out, void* out_lo, int B, int M, int xres, int n, void* stream) {
+                                      const float* posy, void* out, void* out_lo, int mode, int B, int M, int xres, int n, void* stream) {
     PCNN_CHECK_ARG(h && sinh_basis && modew && posx && posy && out && B > 0 && M > 0, "dbcnn_expand_blk8: bad argument");
     const int c8_total = ((M + 2 + 15) / 16) * 2;
     const long long total = (long long)B * ((M + 2 + 7) / 8) * xres * n;
-    dbcnn_expand_blk8_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(h, sinh_basis, modew, posx, posy, (__half*)out, (__half*)out_lo, M, xres, n, c8_total, total);
+    dbcnn_expand_blk8_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(h, sinh_basis, modew, posx, posy, (__half*)out, (__half*)out_lo, M, xres, n, c8_total, total, mode);
     PCNN_CHECK_LAUNCH();
     return PCNN_OK;
 }
@@ -627,8 +758,8 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
                               void* out, void* out_lo, int B, int Cin_total, int Cout, int Cout_total, int Cres_total,
                               int H, int W, int k, int act, int nsplit, float acc_scale, int num_sms, void* stream) {
     PCNN_CHECK_ARG(in && wpack && out, "conv2d_tc: null pointer");
-    PCNN_CHECK_ARG(nsplit == 1 || nsplit == 2, "conv2d_tc: nsplit must be 1 or 2");
-    if (nsplit == 2) PCNN_CHECK_ARG(in_lo && out_lo && (!residual || residual_lo), "conv2d_tc: split precision needs the lo buffers");
+    PCNN_CHECK_ARG(nsplit >= 1 && nsplit <= 3, "conv2d_tc: precision mode must be 1, 2 or 3");
+    if (nsplit >= 2) PCNN_CHECK_ARG(in_lo && out_lo && (!residual || residual_lo), "conv2d_tc: split precision needs the lo buffers");
     PCNN_CHECK_ARG((k & 1) && k >= 1 && k <= 2 * HALO + 1, "conv2d_tc: kernel size %d not supported (odd, <= 15)", k);
     PCNN_CHECK_ARG(Cout >= 1 && Cout <= COUT_PAD && Cout <= Cout_total, "conv2d_tc: Cout %d not in [1,32]", Cout);
     PCNN_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cin_total > 0, "conv2d_tc: bad shape");
@@ -640,7 +771,7 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
     p.out = (__half*)out; p.out_lo = (__half*)out_lo; p.nsplit = nsplit; p.acc_scale = acc_scale;
     p.B = B; p.H = H; p.W = W; p.Hp = H + 2 * HALO; p.P = W + 2 * HALO;
     p.c16 = (Cin_total + 15) / 16;
-    p.nv = p.c16 * (nsplit == 2 ? 3 : 1);
+    p.nv = p.c16 * (nsplit == 2 ? 3 : (nsplit == 3 ? 2 : 1));
     p.c8_in = p.c16 * 2; p.c8_out = ((Cout_total + 15) / 16) * 2; p.c8_res = ((Cres_total + 15) / 16) * 2;
     p.cout = Cout; p.kh = k; p.kw = k; p.pad = k / 2; p.act = act;
     p.n_tile = W >= 256 ? 256 : ((W + 15) / 16) * 16;

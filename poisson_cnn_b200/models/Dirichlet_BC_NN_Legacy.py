@@ -111,7 +111,7 @@ class Dirichlet_BC_NN_Legacy_2(WeightedModel):
         for i in range(self.n_mlp):
             v = ops.dense(v, *self.conv("mlp/%d" % i), self.mlp_acts[i])
         S, nreg = self.n_final, self.final_regular_conv_stages
-        if self.precision in ("tc", "tc3"):
+        if self.precision in ("tc", "tc2", "tc3"):
             if not self._tc_supported():
                 raise NotImplementedError("precision='tc' covers odd kernels <= 15, <= 32 filters, zero CONSTANT padding")
             # the [B,29,x_res,n] mode expansion is produced directly in the tensor-core operand layout

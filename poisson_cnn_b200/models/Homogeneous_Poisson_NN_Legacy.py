@@ -276,7 +276,7 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
             raise ValueError("dx must be [batch, 1]")
         B, _, H, Wd = rhs.shape
         F = self.filters
-        if self.precision in ("tc", "tc3"):
+        if self.precision in ("tc", "tc2", "tc3"):
             if not self._tc_supported():
                 raise NotImplementedError("precision='tc' covers odd kernels <= 15, <= 32 filters, zero CONSTANT / SYMMETRIC padding")
             return self._call_tc(rhs, dx)

@@ -55,13 +55,16 @@ class WeightedModel:
     def _on_weights_loaded(self):
         self._tc = {}
 
-    PRECISIONS = ("fp32", "tc", "tc3")
+    PRECISIONS = ("fp32", "tc", "tc2", "tc3")
+    _TC_MODE = {"tc": 1, "tc3": 2, "tc2": 3}
 
     def set_precision(self, precision):
         """'fp32': strict FP32 CUDA-core kernels (rel-L2 <= 1e-5 vs the reference arithmetic);
         'tc'  : tcgen05 tensor cores, one pass of FP16 operands (11-bit significand like TF32), FP32 accumulation;
         'tc3' : tcgen05 with split FP16 operands (x = hi + lo, W = hi + lo; three MMAs per product term),
-                ~22 significand bits -- the error-compensated mode that holds the 2e-3 budget on any input."""
+                ~22 significand bits -- the error-compensated mode that holds the 2e-3 budget on any input;
+        'tc2' : FP16 main pass + ONE e4m3 K=32 MMA for both correction terms (2x the tensor work of 'tc',
+                ~15 significand bits)."""
         if precision not in self.PRECISIONS:
             raise ValueError("precision must be one of %s" % (self.PRECISIONS,))
         self.precision = precision
@@ -73,7 +76,7 @@ class WeightedModel:
     def tc_conv(self, name):
         """(packed fp16 operand image, bias) of a conv layer for the tensor-core kernel, packed once."""
         from .. import ops
-        nsplit = 2 if self.precision == "tc3" else 1
+        nsplit = self._TC_MODE[self.precision]
         key = (name, nsplit)
         if key not in self._tc:
             self._tc[key] = ops.pack_conv_weights_tc(self._w[name + "/kernel"], nsplit)
@@ -81,7 +84,8 @@ class WeightedModel:
 
     @property
     def tc_split(self):
-        return self.precision == "tc3"
+        """precision mode of the BLK8 tensors (ops.Blk8 split argument): 1, 2 (tc3) or 3 (tc2)"""
+        return self._TC_MODE.get(self.precision, 1)
 
     def init_synthetic_weights(self, seed=0, device=None):
         """Seeded random weights (no trained weights ship with the reference)."""

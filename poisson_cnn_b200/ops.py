@@ -442,20 +442,25 @@ def _blk8_buffer(key, nbytes, device):
 
 class Blk8:
     """fp16 activation in the BLK8 layout [B][Cpad/8][H+14][W+14][8] (7-pixel halo in memory).
-    split=True keeps a second buffer `lo` with the fp16 rounding remainder (x = hi + lo, ~22 bits).
+    split selects the precision mode of the tensor: False/1 fp16 only; True/2 a second buffer `lo` with the
+    fp16 rounding remainder (x = hi + lo, ~22 bits); 3 a second buffer of e4m3 planes (e4m3(x) and
+    e4m3((x-hi)*2^11), 16 channels per plane) feeding the single fp8 correction MMA.
     `halo` records what the halo currently holds: (PAD_CONSTANT, 7) after allocation, (mode, pad) after a
     halo fill, (mode, -1) when a mirrored halo went stale.  Buffers are recycled through a pool keyed by
     the exact shape, so steady-state inference neither allocates nor re-zeroes them."""
 
-    __slots__ = ("buf", "lo", "B", "C", "H", "W", "halo", "_key")
+    __slots__ = ("buf", "lo", "mode", "B", "C", "H", "W", "halo", "_key")
 
     def __init__(self, B, C, H, W, device, split=False):
         nbytes = lib.pcnn_blk8_bytes(B, C, H, W)
         if nbytes == 0:
             raise ValueError("Blk8: bad shape")
+        self.mode = int(split) if split not in (True, False) else (2 if split else 1)
+        if self.mode not in (1, 2, 3):
+            raise ValueError("Blk8: precision mode must be 1, 2 or 3")
         self._key = (str(device), B, C, H, W)
         self.buf = _blk8_buffer(self._key, nbytes, device)
-        self.lo = _blk8_buffer(self._key, nbytes, device) if split else None
+        self.lo = _blk8_buffer(self._key, nbytes, device) if self.mode >= 2 else None
         self.B, self.C, self.H, self.W = B, C, H, W
         self.halo = (PAD_CONSTANT, 7)
 
@@ -503,7 +508,7 @@ def to_blk8(x, out=None, c_total=None, c_offset=0, split=False):
         out = Blk8(B, c_total or C, H, W, x.device, split=split)
     if (out.B, out.H, out.W) != (B, H, W):
         raise ValueError("to_blk8: destination shape mismatch")
-    check(lib.pcnn_to_blk8(_p(x), _p(out.buf), _p(out.lo), B, C, H, W, out.C, int(c_offset), in_bs, _stream()), "to_blk8")
+    check(lib.pcnn_to_blk8(_p(x), _p(out.buf), _p(out.lo), out.mode, B, C, H, W, out.C, int(c_offset), in_bs, _stream()), "to_blk8")
     if out.halo[0] != PAD_CONSTANT:
         out.halo = (out.halo[0], -1)
     return out
@@ -514,7 +519,7 @@ def from_blk8(t, C=None, c_offset=0, out=None):
     if out is None:
         out = torch.empty((t.B, C, t.H, t.W), device=t.device, dtype=torch.float32)
     out_bs = _nchw_bstride(out, "out")
-    check(lib.pcnn_from_blk8(_p(t.buf), _p(t.lo), _p(out), t.B, C, t.H, t.W, t.C, int(c_offset), out_bs, _stream()), "from_blk8")
+    check(lib.pcnn_from_blk8(_p(t.buf), _p(t.lo), t.mode, _p(out), t.B, C, t.H, t.W, t.C, int(c_offset), out_bs, _stream()), "from_blk8")
     return out
 
 
@@ -567,15 +572,15 @@ def conv2d_tc(x, wp, bias=None, act=ACT_LINEAR, pad_mode=PAD_CONSTANT, bn=None, 
     k, cout, nsplit = wp["k"], wp["cout"], wp["nsplit"]
     if -(-wp["cin"] // 16) != -(-x.C // 16):
         raise ValueError("conv2d_tc: kernel expects %d input channels, tensor holds %d" % (wp["cin"], x.C))
-    split = nsplit == 2
-    if split and not x.split:
-        raise ValueError("conv2d_tc: split-precision weights need a split (hi+lo) input tensor")
+    split = nsplit >= 2
+    if x.mode != nsplit:
+        raise ValueError("conv2d_tc: weights packed for precision mode %d, input tensor is mode %d" % (nsplit, x.mode))
     blk8_halo_fill(x, k // 2, pad_mode)
     if out is None:
-        out = Blk8(x.B, out_channels_total or cout, x.H, x.W, x.device, split=split)
-    if (out.B, out.H, out.W) != (x.B, x.H, x.W) or (split and not out.split):
+        out = Blk8(x.B, out_channels_total or cout, x.H, x.W, x.device, split=nsplit)
+    if (out.B, out.H, out.W) != (x.B, x.H, x.W) or out.mode != nsplit:
         raise ValueError("conv2d_tc: destination shape / precision mismatch")
-    if residual is not None and ((residual.B, residual.H, residual.W) != (x.B, x.H, x.W) or (split and not residual.split)):
+    if residual is not None and ((residual.B, residual.H, residual.W) != (x.B, x.H, x.W) or residual.mode != nsplit):
         raise ValueError("conv2d_tc: residual shape / precision mismatch")
     bn_s, bn_t = (bn if bn is not None else (None, None))
     timed = KERNEL_TIMER is not None and KERNEL_TIMER.match(wp["cin"], cout, k, k, x.H, x.W)
@@ -602,5 +607,5 @@ def dbcnn_expand_blk8(h, modew, x_res, split=False):
     S = sinh_basis_table(h.device, M, x_res)
     out = Blk8(B, M + 2, x_res, n, h.device, split=split)
     check(lib.pcnn_dbcnn_expand_blk8(_p(h), _p(S), _p(modew), _p(position_table(h.device, x_res)),
-                                     _p(position_table(h.device, n)), _p(out.buf), _p(out.lo), B, M, x_res, n, _stream()), "dbcnn_expand_blk8")
+                                     _p(position_table(h.device, n)), _p(out.buf), _p(out.lo), out.mode, B, M, x_res, n, _stream()), "dbcnn_expand_blk8")
     return out
