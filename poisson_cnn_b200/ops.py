@@ -455,7 +455,7 @@ class Blk8:
         nbytes = lib.pcnn_blk8_bytes(B, C, H, W)
         if nbytes == 0:
             raise ValueError("Blk8: bad shape")
-        self.mode = int(split) if split not in (True, False) else (2 if split else 1)
+        self.mode = (2 if split else 1) if isinstance(split, bool) else int(split)
         if self.mode not in (1, 2, 3):
             raise ValueError("Blk8: precision mode must be 1, 2 or 3")
         self._key = (str(device), B, C, H, W)
