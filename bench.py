@@ -312,9 +312,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="samples per GPU per step (BASELINE configs[1]: 256)")
     ap.add_argument("--grid", type=int, default=256)
-    ap.add_argument("--precision", default=os.environ.get("PCNN_PRECISION", "tc3"), choices=["fp32", "tc", "tc2", "tc3"],
-                    help="tc3 (default): tcgen05 with split-FP16 operands, holds the 2e-3 budget; tc: single FP16 pass; fp32: strict CUDA-core path")
-    ap.add_argument("--other-modes", default="tc,fp32", help="comma list of extra precision modes timed briefly at N=1 (reported under other_modes)")
+    ap.add_argument("--precision", default=os.environ.get("PCNN_PRECISION", "tc2"), choices=["fp32", "tc", "tc2", "tc3"],
+                    help="tc2 (default): tcgen05, fp16 main MMA + one e4m3 correction MMA, holds the 2e-3 budget; tc3: hi/lo fp16 split; tc: single FP16 pass; fp32: strict CUDA-core path")
+    ap.add_argument("--other-modes", default="tc,tc3,fp32", help="comma list of extra precision modes timed briefly at N=1 (reported under other_modes)")
     ap.add_argument("--check-samples", type=int, default=2)
     ap.add_argument("--cpu-budget-s", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

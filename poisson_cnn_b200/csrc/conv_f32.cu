@@ -141,6 +141,64 @@ __global__ void __launch_bounds__(256) conv2d_f32_kernel(const ConvF32Params p) 
     }
 }
 
+// Small-map variant (H*W <= 64: the 2x2 .. 8x8 maps of the ds = 32/64/128 branches and the Scaling
+// tail): one CTA per sample keeps the whole padded input in shared memory; thread = (output channel,
+// pixel group), weights read coalesced across channels.  The 8x64-pixel tile kernel above would spend
+// >85 % of its lanes on pixels that do not exist.
+__global__ void __launch_bounds__(256) conv2d_small_f32_kernel(const ConvF32Params p) {
+    extern __shared__ float smem[];
+    const int b = blockIdx.x;
+    const int ph = p.H + p.kh - 1, pw = p.W + p.kw - 1;
+    const int pad_t = p.kh / 2, pad_l = p.kw / 2;
+    const float* inb = p.in + (long long)b * p.in_bstride;
+    for (int idx = threadIdx.x; idx < p.Cin * ph * pw; idx += blockDim.x) {
+        const int ci = idx / (ph * pw);
+        const int rem = idx - ci * ph * pw;
+        const int yy = rem / pw - pad_t, xx = rem % pw - pad_l;
+        const bool inside = (yy >= 0) & (yy < p.H) & (xx >= 0) & (xx < p.W);
+        float v = p.pad_value;
+        if (inside || p.pad_mode != PCNN_PAD_CONSTANT)
+            v = __ldg(inb + ((long long)ci * p.H + pad_src_index(yy, p.H, p.pad_mode)) * p.W + pad_src_index(xx, p.W, p.pad_mode));
+        smem[idx] = v;
+    }
+    __syncthreads();
+    const int npix = p.H * p.W;
+    const int co = threadIdx.x % 32, pg = threadIdx.x / 32;   // 8 pixel groups
+    if (co >= p.Cout) return;
+    float acc[8];
+    int poff[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        acc[i] = 0.f;
+        const int pidx = pg + 8 * i;
+        poff[i] = pidx < npix ? (pidx / p.W) * pw + (pidx % p.W) : 0;
+    }
+    for (int ci = 0; ci < p.Cin; ++ci) {
+        const float* sin = smem + ci * ph * pw;
+        for (int dy = 0; dy < p.kh; ++dy)
+            for (int dx = 0; dx < p.kw; ++dx) {
+                const float w = __ldg(p.kernel + (((long long)dy * p.kw + dx) * p.Cin + ci) * p.Cout + co);
+                const float* s0 = sin + dy * pw + dx;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaf(s0[poff[i]], w, acc[i]);
+            }
+    }
+    const float bias = p.bias ? __ldg(p.bias + co) : 0.f;
+    const float bs = p.bn_scale ? __ldg(p.bn_scale + co) : 1.f, bt = p.bn_shift ? __ldg(p.bn_shift + co) : 0.f;
+    const float os = p.out_scale ? __ldg(p.out_scale + (long long)b * p.Cout + co) : 1.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int pidx = pg + 8 * i;
+        if (pidx >= npix) break;
+        float v = apply_act(acc[i] + bias, p.act);
+        if (p.bn_scale) v = fmaf(v, bs, bt);
+        const long long off = (long long)co * npix + pidx;
+        if (p.residual) v += __ldg(p.residual + (long long)b * p.res_bstride + off);
+        if (p.out_scale) v *= os;
+        p.out[(long long)b * p.out_bstride + off] = v;
+    }
+}
+
 }  // namespace pcnn
 
 extern "C" int pcnn_conv2d_f32(const float* in, const float* kernel, const float* bias,
@@ -169,6 +227,17 @@ extern "C" int pcnn_conv2d_f32(const float* in, const float* kernel, const float
     p.in_bstride = in_bstride; p.out_bstride = out_bstride; p.res_bstride = res_bstride;
     const int ngroups = ceil_div(Cout, CO);
     PCNN_CHECK_ARG(ngroups <= 4, "conv2d_f32: Cout %d > 32 not supported", Cout);
+    {
+        const size_t small_smem = (size_t)Cin * (H + kh - 1) * (W + kw - 1) * sizeof(float);
+        if (H * W <= 64 && small_smem <= 160 * 1024) {
+            p.cop = 0; p.tile_rows = 0; p.pitch = 0; p.ci_chunk = 0;
+            if (small_smem > 48 * 1024)
+                PCNN_CHECK_CUDA(cudaFuncSetAttribute(conv2d_small_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            conv2d_small_f32_kernel<<<B, 256, small_smem, (cudaStream_t)stream>>>(p);
+            PCNN_CHECK_LAUNCH();
+            return PCNN_OK;
+        }
+    }
     p.cop = ngroups * CO;
     p.tile_rows = TILE_H + kh - 1;
     int cols = TILE_W + kw - 1;

@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(256) deconv_ks_kernel(const float* __restrict_
                                                         int Cout, int ih, int iw, int oh, int ow, int s, int pbh, int pbw,
                                                         int act, float alpha, int accumulate, long long out_bstride) {
     extern __shared__ float sm[];
-    float* s_w = sm;                    // [32 co][32 ci] (zero padded)
-    float* s_o = sm + 32 * 32;          // [32 co][32*s + 1] output row segment
+    float* s_w = sm;                    // [s column phases][32 co][32 ci] (zero padded), loaded once
+    float* s_o = sm + s * 32 * 32;      // [32 co][32*s + 1] output row segment
     const int pitch = 32 * s + 1;
     const int b = blockIdx.z;
     const int Yp = blockIdx.y;          // padded output row = i*s + ty
@@ -121,22 +121,21 @@ __global__ void __launch_bounds__(256) deconv_ks_kernel(const float* __restrict_
     const int j0 = blockIdx.x * 32;
     const int px = threadIdx.x & 31, cg = threadIdx.x >> 5;
     const int j = j0 + px;
+    const float* kp = kernel + (long long)ty * s * Cout * Cin;      // [tx][Cout][Cin]
+    for (int e = threadIdx.x; e < s * 32 * 32; e += 256) {
+        const int tx = e >> 10, co = (e >> 5) & 31, ci = e & 31;
+        s_w[e] = (co < Cout && ci < Cin) ? __ldg(kp + ((long long)tx * Cout + co) * Cin + ci) : 0.f;
+    }
     float x[32];
 #pragma unroll
     for (int ci = 0; ci < 32; ++ci)
         x[ci] = (j < iw && ci < Cin) ? __ldg(in + (((long long)b * Cin + ci) * ih + i) * iw + j) : 0.f;
+    __syncthreads();
     for (int tx = 0; tx < s; ++tx) {
-        __syncthreads();
-        const float* kp = kernel + ((long long)ty * s + tx) * Cout * Cin;      // [Cout][Cin]
-        for (int e = threadIdx.x; e < 32 * 32; e += 256) {
-            const int co = e >> 5, ci = e & 31;
-            s_w[e] = (co < Cout && ci < Cin) ? __ldg(kp + co * Cin + ci) : 0.f;
-        }
-        __syncthreads();
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const float4* wr = reinterpret_cast<const float4*>(s_w + (cg * 4 + c) * 32);
+            const float4* wr = reinterpret_cast<const float4*>(s_w + (tx * 32 + cg * 4 + c) * 32);
 #pragma unroll
             for (int q4 = 0; q4 < 8; ++q4) {
                 const float4 w = wr[q4];
@@ -183,6 +182,40 @@ __global__ void resize_kernel(const float* __restrict__ in, const int* __restric
             const float* row = src + (long long)__ldg(iy + Y * taps + a) * iw;
             float r = 0.f;   // TF interpolates along x first, then along y
             for (int q = 0; q < taps; ++q) r = fmaf(__ldg(row + __ldg(ix + X * taps + q)), __ldg(wx + X * taps + q), r);
+            acc = fmaf(r, __ldg(wy + Y * taps + a), acc);
+        }
+        acc *= alpha;
+        float* o = out + (long long)b * out_bstride + ((long long)c * oh + Y) * ow + X;
+        *o = accumulate ? (*o + acc) : acc;
+    }
+}
+
+// Small-source variant (the ds = 32/64/128 branches upsample 2x2..8x8 maps): the whole [C,ih,iw] source of
+// one sample sits in shared memory and the read-modify-write of `out` is a coalesced stream.
+__global__ void __launch_bounds__(256) resize_small_kernel(const float* __restrict__ in, const int* __restrict__ iy,
+                                                           const float* __restrict__ wy, const int* __restrict__ ix,
+                                                           const float* __restrict__ wx, int taps, float* __restrict__ out,
+                                                           int C, int ih, int iw, int oh, int ow, int rows_per_cta,
+                                                           float alpha, int accumulate, long long out_bstride) {
+    extern __shared__ float ssrc[];
+    const int b = blockIdx.y;
+    const int Y0 = blockIdx.x * rows_per_cta;
+    const int nsrc = C * ih * iw;
+    for (int i = threadIdx.x; i < nsrc; i += blockDim.x) ssrc[i] = __ldg(in + (long long)b * nsrc + i);
+    __syncthreads();
+    const int rows = min(rows_per_cta, oh - Y0);
+    const int total = C * rows * ow;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int X = idx % ow;
+        int t = idx / ow;
+        const int Y = Y0 + t % rows;
+        const int c = t / rows;
+        const float* src = ssrc + c * ih * iw;
+        float acc = 0.f;
+        for (int a = 0; a < taps; ++a) {
+            const float* row = src + __ldg(iy + Y * taps + a) * iw;
+            float r = 0.f;
+            for (int q = 0; q < taps; ++q) r = fmaf(row[__ldg(ix + X * taps + q)], __ldg(wx + X * taps + q), r);
             acc = fmaf(r, __ldg(wy + Y * taps + a), acc);
         }
         acc *= alpha;
@@ -422,8 +455,8 @@ extern "C" int pcnn_deconv_same_f32(const float* in, const float* kernel, const 
                    "deconv_same_f32: output_shape (%d,%d) inconsistent with input (%d,%d) at stride %d (TF raises)", oh, ow, ih, iw, stride);
     const int pbh = max((ih - 1) * stride + kh - oh, 0) / 2;
     const int pbw = max((iw - 1) * stride + kw - ow, 0) / 2;
-    if (kh == stride && kw == stride && Cin <= 32 && Cout <= 32 && stride <= 32 && B <= 65535 && ih * stride <= 65535) {
-        const size_t smem = (32 * 32 + 32 * (32 * stride + 1)) * sizeof(float);
+    if (kh == stride && kw == stride && Cin <= 32 && Cout <= 32 && stride <= 16 && B <= 65535 && ih * stride <= 65535) {
+        const size_t smem = ((size_t)stride * 32 * 32 + 32 * (32 * stride + 1)) * sizeof(float);
         if (smem > 48 * 1024)
             PCNN_CHECK_CUDA(cudaFuncSetAttribute(deconv_ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(ceil_div(iw, 32), ih * stride, B);
@@ -442,6 +475,13 @@ extern "C" int pcnn_resize_f32(const float* in, const int32_t* iy, const float* 
                                int oh, int ow, float alpha, int accumulate, int64_t out_bstride,
                                void* stream) {
     PCNN_CHECK_ARG(in && iy && wy && ix && wx && out && taps >= 1 && taps <= 4, "resize_f32: bad argument");
+    if ((size_t)C * ih * iw * sizeof(float) <= 32 * 1024 && B <= 65535) {
+        const int rows_per_cta = 4;
+        resize_small_kernel<<<dim3(ceil_div(oh, rows_per_cta), B), 256, (size_t)C * ih * iw * sizeof(float), (cudaStream_t)stream>>>(
+            in, iy, wy, ix, wx, taps, out, C, ih, iw, oh, ow, rows_per_cta, alpha, accumulate, out_bstride);
+        PCNN_CHECK_LAUNCH();
+        return PCNN_OK;
+    }
     const long long total = (long long)B * C * oh * ow;
     resize_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(in, iy, wy, ix, wx, taps, out, C, ih, iw, oh, ow, alpha, accumulate, out_bstride, total);
     PCNN_CHECK_LAUNCH();

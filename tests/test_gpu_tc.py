@@ -213,7 +213,7 @@ def test_conv2d_tc2_parity(ops, B, Cin, Cout, H, W, k, act):
     ref = O.conv_nd(x.double(), kern.double(), bias.double(), ACTS[act], "CONSTANT", 0.0) + res.double()
     err = rel_l2(got, ref)
     print("tc2 conv k%d %d->%d rel-L2 %.2e" % (k, Cin, Cout, err))
-    assert err < 8e-5
+    assert err < 3e-5
 
 
 def test_models_tc2_mode_vs_oracle():
@@ -230,4 +230,4 @@ def test_models_tc2_mode_vs_oracle():
     ref = O.hpnn_forward(hp, w, p["rhs"].double(), p["dx"].double(), "hpnn/")
     e_hp = rel_l2(model.hpnn([dev(p["rhs"]), dev(p["dx"])]), ref)
     print("tc2-mode rel-L2 vs float64 oracle: pcnn %.3e  hpnn %.3e" % (e_pcnn, e_hp))
-    assert e_pcnn < 1e-3 and e_hp < 1e-3      # >= 2x inside the 2e-3 tensor-core budget
+    assert e_pcnn < 5e-4 and e_hp < 5e-4      # >= 4x inside the 2e-3 tensor-core budget
