@@ -148,8 +148,12 @@ __global__ void __launch_bounds__(256) conv2d_f32_kernel(const ConvF32Params p) 
 __global__ void __launch_bounds__(256) conv2d_small_f32_kernel(const ConvF32Params p) {
     extern __shared__ float smem[];
     const int b = blockIdx.x;
+    const int co0 = blockIdx.y * 8;             // 8 output channels per CTA (4 CTAs per sample at Cout = 32)
     const int ph = p.H + p.kh - 1, pw = p.W + p.kw - 1;
     const int pad_t = p.kh / 2, pad_l = p.kw / 2;
+    const int taps = p.kh * p.kw;
+    float* s_in = smem;                          // [Cin][ph][pw]
+    float* s_w = smem + p.Cin * ph * pw;         // [Cin][taps][8]
     const float* inb = p.in + (long long)b * p.in_bstride;
     for (int idx = threadIdx.x; idx < p.Cin * ph * pw; idx += blockDim.x) {
         const int ci = idx / (ph * pw);
@@ -159,36 +163,43 @@ __global__ void __launch_bounds__(256) conv2d_small_f32_kernel(const ConvF32Para
         float v = p.pad_value;
         if (inside || p.pad_mode != PCNN_PAD_CONSTANT)
             v = __ldg(inb + ((long long)ci * p.H + pad_src_index(yy, p.H, p.pad_mode)) * p.W + pad_src_index(xx, p.W, p.pad_mode));
-        smem[idx] = v;
+        s_in[idx] = v;
+    }
+    for (int idx = threadIdx.x; idx < p.Cin * taps * 8; idx += blockDim.x) {
+        const int c = idx & 7;
+        const int t = (idx >> 3) % taps, ci = (idx >> 3) / taps;
+        s_w[idx] = (co0 + c < p.Cout) ? __ldg(p.kernel + ((long long)t * p.Cin + ci) * p.Cout + co0 + c) : 0.f;
     }
     __syncthreads();
     const int npix = p.H * p.W;
-    const int co = threadIdx.x % 32, pg = threadIdx.x / 32;   // 8 pixel groups
-    if (co >= p.Cout) return;
-    float acc[8];
-    int poff[8];
+    // thread = (channel c of 8, pixel slot of 32): pixels pslot and pslot + 32
+    const int c = threadIdx.x & 7, pslot = threadIdx.x >> 3;
+    const int co = co0 + c;
+    float acc[2] = {0.f, 0.f};
+    int poff[2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        acc[i] = 0.f;
-        const int pidx = pg + 8 * i;
+    for (int i = 0; i < 2; ++i) {
+        const int pidx = pslot + 32 * i;
         poff[i] = pidx < npix ? (pidx / p.W) * pw + (pidx % p.W) : 0;
     }
     for (int ci = 0; ci < p.Cin; ++ci) {
-        const float* sin = smem + ci * ph * pw;
+        const float* sin = s_in + ci * ph * pw;
+        const float* sw = s_w + ci * taps * 8 + c;
         for (int dy = 0; dy < p.kh; ++dy)
             for (int dx = 0; dx < p.kw; ++dx) {
-                const float w = __ldg(p.kernel + (((long long)dy * p.kw + dx) * p.Cin + ci) * p.Cout + co);
+                const float w = sw[(dy * p.kw + dx) * 8];
                 const float* s0 = sin + dy * pw + dx;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] = fmaf(s0[poff[i]], w, acc[i]);
+                acc[0] = fmaf(s0[poff[0]], w, acc[0]);
+                acc[1] = fmaf(s0[poff[1]], w, acc[1]);
             }
     }
+    if (co >= p.Cout) return;
     const float bias = p.bias ? __ldg(p.bias + co) : 0.f;
     const float bs = p.bn_scale ? __ldg(p.bn_scale + co) : 1.f, bt = p.bn_shift ? __ldg(p.bn_shift + co) : 0.f;
     const float os = p.out_scale ? __ldg(p.out_scale + (long long)b * p.Cout + co) : 1.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int pidx = pg + 8 * i;
+    for (int i = 0; i < 2; ++i) {
+        const int pidx = pslot + 32 * i;
         if (pidx >= npix) break;
         float v = apply_act(acc[i] + bias, p.act);
         if (p.bn_scale) v = fmaf(v, bs, bt);
@@ -228,12 +239,12 @@ extern "C" int pcnn_conv2d_f32(const float* in, const float* kernel, const float
     const int ngroups = ceil_div(Cout, CO);
     PCNN_CHECK_ARG(ngroups <= 4, "conv2d_f32: Cout %d > 32 not supported", Cout);
     {
-        const size_t small_smem = (size_t)Cin * (H + kh - 1) * (W + kw - 1) * sizeof(float);
+        const size_t small_smem = ((size_t)Cin * (H + kh - 1) * (W + kw - 1) + (size_t)Cin * kh * kw * 8) * sizeof(float);
         if (H * W <= 64 && small_smem <= 160 * 1024) {
             p.cop = 0; p.tile_rows = 0; p.pitch = 0; p.ci_chunk = 0;
             if (small_smem > 48 * 1024)
                 PCNN_CHECK_CUDA(cudaFuncSetAttribute(conv2d_small_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            conv2d_small_f32_kernel<<<B, 256, small_smem, (cudaStream_t)stream>>>(p);
+            conv2d_small_f32_kernel<<<dim3(B, ceil_div(Cout, 8)), 256, small_smem, (cudaStream_t)stream>>>(p);
             PCNN_CHECK_LAUNCH();
             return PCNN_OK;
         }

@@ -105,19 +105,18 @@ __global__ void deconv_same_kernel(const float* __restrict__ in, const float* __
 // pixels; the 32 input vectors stay in registers while the s column-phase matrices stream through
 // shared memory; results are staged in shared memory so the read-modify-write of `out` is coalesced.
 // threads: 32 pixels x 8 groups of 4 output channels.
+constexpr int DK_ROWS = 4;   // low-res rows per CTA (amortises the phase-matrix load)
 __global__ void __launch_bounds__(256) deconv_ks_kernel(const float* __restrict__ in, const float* __restrict__ kernel,
                                                         const float* __restrict__ bias, float* __restrict__ out, int Cin,
                                                         int Cout, int ih, int iw, int oh, int ow, int s, int pbh, int pbw,
                                                         int act, float alpha, int accumulate, long long out_bstride) {
     extern __shared__ float sm[];
-    float* s_w = sm;                    // [s column phases][32 co][32 ci] (zero padded), loaded once
+    float* s_w = sm;                    // [s column phases][32 co][32 ci] (zero padded), loaded once per CTA
     float* s_o = sm + s * 32 * 32;      // [32 co][32*s + 1] output row segment
     const int pitch = 32 * s + 1;
     const int b = blockIdx.z;
-    const int Yp = blockIdx.y;          // padded output row = i*s + ty
-    const int i = Yp / s, ty = Yp - i * s;
-    const int Y = Yp - pbh;
-    if (Y < 0 || Y >= oh) return;       // block-uniform
+    // blockIdx.y = (group of DK_ROWS low-res rows, row phase ty): the s phase matrices are reused for every row
+    const int ty = blockIdx.y % s, ig = blockIdx.y / s;
     const int j0 = blockIdx.x * 32;
     const int px = threadIdx.x & 31, cg = threadIdx.x >> 5;
     const int j = j0 + px;
@@ -126,40 +125,44 @@ __global__ void __launch_bounds__(256) deconv_ks_kernel(const float* __restrict_
         const int tx = e >> 10, co = (e >> 5) & 31, ci = e & 31;
         s_w[e] = (co < Cout && ci < Cin) ? __ldg(kp + ((long long)tx * Cout + co) * Cin + ci) : 0.f;
     }
-    float x[32];
-#pragma unroll
-    for (int ci = 0; ci < 32; ++ci)
-        x[ci] = (j < iw && ci < Cin) ? __ldg(in + (((long long)b * Cin + ci) * ih + i) * iw + j) : 0.f;
-    __syncthreads();
-    for (int tx = 0; tx < s; ++tx) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float4* wr = reinterpret_cast<const float4*>(s_w + (tx * 32 + cg * 4 + c) * 32);
-#pragma unroll
-            for (int q4 = 0; q4 < 8; ++q4) {
-                const float4 w = wr[q4];
-                acc[c] = fmaf(x[4 * q4 + 0], w.x, acc[c]);
-                acc[c] = fmaf(x[4 * q4 + 1], w.y, acc[c]);
-                acc[c] = fmaf(x[4 * q4 + 2], w.z, acc[c]);
-                acc[c] = fmaf(x[4 * q4 + 3], w.w, acc[c]);
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) s_o[(cg * 4 + c) * pitch + px * s + tx] = acc[c];
-    }
-    __syncthreads();
-    // coalesced epilogue: out[b, co, Y, X] (op)= alpha * act(v + bias)
     const int X0 = j0 * s - pbw;
     const int ncol = 32 * s;
-    for (int e = threadIdx.x; e < Cout * ncol; e += 256) {
-        const int co = e / ncol, c = e - co * ncol;
-        const int X = X0 + c;
-        if (X < 0 || X >= ow || j0 + c / s >= iw) continue;
-        float v = s_o[co * pitch + c] + (bias ? __ldg(bias + co) : 0.f);
-        v = apply_act(v, act) * alpha;
-        float* o = out + (long long)b * out_bstride + ((long long)co * oh + Y) * ow + X;
-        *o = accumulate ? (*o + v) : v;
+    for (int i = ig * DK_ROWS; i < min((ig + 1) * DK_ROWS, ih); ++i) {
+        const int Y = i * s + ty - pbh;
+        if (Y < 0 || Y >= oh) continue;     // block-uniform
+        float x[32];
+#pragma unroll
+        for (int ci = 0; ci < 32; ++ci)
+            x[ci] = (j < iw && ci < Cin) ? __ldg(in + (((long long)b * Cin + ci) * ih + i) * iw + j) : 0.f;
+        __syncthreads();                    // weights visible / previous row's epilogue finished with s_o
+        for (int tx = 0; tx < s; ++tx) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float4* wr = reinterpret_cast<const float4*>(s_w + (tx * 32 + cg * 4 + c) * 32);
+#pragma unroll
+                for (int q4 = 0; q4 < 8; ++q4) {
+                    const float4 w = wr[q4];
+                    acc[c] = fmaf(x[4 * q4 + 0], w.x, acc[c]);
+                    acc[c] = fmaf(x[4 * q4 + 1], w.y, acc[c]);
+                    acc[c] = fmaf(x[4 * q4 + 2], w.z, acc[c]);
+                    acc[c] = fmaf(x[4 * q4 + 3], w.w, acc[c]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s_o[(cg * 4 + c) * pitch + px * s + tx] = acc[c];
+        }
+        __syncthreads();
+        // coalesced epilogue: out[b, co, Y, X] (op)= alpha * act(v + bias)
+        for (int e = threadIdx.x; e < Cout * ncol; e += 256) {
+            const int co = e / ncol, c = e - co * ncol;
+            const int X = X0 + c;
+            if (X < 0 || X >= ow || j0 + c / s >= iw) continue;
+            float v = s_o[co * pitch + c] + (bias ? __ldg(bias + co) : 0.f);
+            v = apply_act(v, act) * alpha;
+            float* o = out + (long long)b * out_bstride + ((long long)co * oh + Y) * ow + X;
+            *o = accumulate ? (*o + v) : v;
+        }
     }
 }
 
@@ -459,7 +462,7 @@ extern "C" int pcnn_deconv_same_f32(const float* in, const float* kernel, const 
         const size_t smem = ((size_t)stride * 32 * 32 + 32 * (32 * stride + 1)) * sizeof(float);
         if (smem > 48 * 1024)
             PCNN_CHECK_CUDA(cudaFuncSetAttribute(deconv_ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid(ceil_div(iw, 32), ih * stride, B);
+        dim3 grid(ceil_div(iw, 32), ceil_div(ih, DK_ROWS) * stride, B);
         deconv_ks_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(in, kernel, bias, out, Cin, Cout, ih, iw, oh, ow, stride, pbh, pbw, act, alpha, accumulate, out_bstride);
         PCNN_CHECK_LAUNCH();
         return PCNN_OK;
