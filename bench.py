@@ -199,8 +199,10 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         out = model(dev_in)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1000.0 / args.steps   # CPU time to enqueue one step (no sync inside)
     e1.record()
     barrier()
     ops.KERNEL_TIMER = None
@@ -234,8 +236,13 @@ def run_ours(args):
         ach = ks["flops_per_launch"] / (ks["avg_ms"] * 1e-3) / 1e12
         kk = args.roofline_kernel[2]
         issue_factor = {"tc": 1.0, "tc3": 3.0, "tc2": 2.0}.get(args.precision, 0.0) * (kk + 3.0) / kk   # MMAs issued per algorithmic MAC
+        # DRAM bytes per launch of this kernel from the ncu --set full captures (profiles/r01_conv_tc_k15_*_b32_full_raw.csv:
+        # dram__bytes_read.sum + dram__bytes_write.sum at 32 samples per launch), scaled to the samples per launch here
+        per_sample = {"tc": (151.436032e6 + 94.614272e6) / 32, "tc2": (303.551488e6 + 228.785920e6) / 32}.get(args.precision)
+        samples_per_launch = min(B, getattr(model, "max_microbatch", B) or B)
+        traffic = per_sample * samples_per_launch if (per_sample and args.roofline_kernel == (32, 32, 15) and (nx, ny) == (256, 256)) else None
         roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["tflops"], "traffic": None, "kernel": "conv2d %d->%d k%d (%s)" % (args.roofline_kernel + (args.precision,)),
+                    "frac": ach / peaks["tflops"], "traffic": traffic, "kernel": "conv2d %d->%d k%d (%s)" % (args.roofline_kernel + (args.precision,)),
                     "launches_timed": ks["launches"], "avg_launch_ms": ks["avg_ms"], "peak_source": peaks["source"] + " bf16 sustained",
                     "algorithmic_flops_per_launch": ks["flops_per_launch"],
                     "mma_issued_tflops": ach * issue_factor if issue_factor else None,
@@ -291,6 +298,7 @@ def run_ours(args):
                        "flop_per_solution": pcnn_flops(nx, ny)},
             "e2e": {"value": e2e_value, "unit": "solutions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_host.numel() * 4, "steps": e2e_steps},
             "gpu_launches": int(launches),
+            "host_enqueue_ms_per_step": host_enqueue_ms,
             "clocks": sampler.result(),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
