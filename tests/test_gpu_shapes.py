@@ -38,9 +38,11 @@ def test_variable_aspect_grids_tc2_tracks_fp32(model, nx, ny, B):
     out = model.set_precision("tc2")(inp)
     assert out.shape == (B, 1, nx, ny) and bool(torch.isfinite(out).all())
     assert rel_l2(out, ref) < 2e-3          # tensor-core budget; typically ~3e-4
-    # homogeneity: the merged model normalises its inputs per sample and undoes it exactly
-    out3 = model([t * 3.0 if i < 5 else t for i, t in enumerate(inp)])
-    assert rel_l2(out3, 3.0 * out) < 1e-5
+    # homogeneity: the merged model normalises its inputs per sample and undoes it; with a power-of-two factor
+    # every intermediate is bit-identical, so the outputs must scale exactly (a factor like 3 perturbs the
+    # normalised inputs by an ulp, which this chaotic seeded network amplifies to ~1e-4 in tensor-core mode)
+    out4 = model([t * 4.0 if i < 5 else t for i, t in enumerate(inp)])
+    assert rel_l2(out4, 4.0 * out) < 1e-6
     model.set_precision("fp32")
 
 
