@@ -522,146 +522,141 @@ __global__ void pack_weights_kernel(const float* __restrict__ k, __half* __restr
     }
 }
 
-// NCHW fp32 -> BLK8 fp16 interior (planes [plane0, plane0 + ceil(C/8)))
-__global__ void to_blk8_kernel(const float* __restrict__ in, __half* __restrict__ out, __half* __restrict__ out_lo, int C, int H, int W,
-                               int Hp, int P, int c8_total, int plane0, long long in_bstride, long long total) {
-    const int np = (C + 7) / 8;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int x = idx % W;
-        long long t = idx / W;
-        const int y = t % H; t /= H;
-        const int pl = t % np;
-        const long long b = t / np;
-        __align__(16) __half h[8];
-        __align__(16) __half l[8];
+// NCHW fp32 -> BLK8 fp16 interior (planes [plane0, plane0 + ceil(C/8))).  grid (ceil(W/128), H, B*np): no
+// per-element div/mod; each thread reads 8 channel planes (coalesced along x) and writes one 16-byte pixel.
+__global__ void __launch_bounds__(128) to_blk8_kernel(const float* __restrict__ in, __half* __restrict__ out,
+                                                      __half* __restrict__ out_lo, int C, int H, int W, int Hp, int P,
+                                                      int c8_total, int plane0, long long in_bstride, int np) {
+    const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const int b = blockIdx.z / np, pl = blockIdx.z - b * np;
+    __align__(16) __half h[8];
+    __align__(16) __half l[8];
+    const float* src = in + (long long)b * in_bstride + ((long long)(pl * 8) * H + y) * W + x;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int c = pl * 8 + e;
-            const float f = c < C ? __ldg(in + b * in_bstride + ((long long)c * H + y) * W + x) : 0.f;
-            h[e] = __float2half_rn(f);
-            l[e] = __float2half_rn(f - __half2float(h[e]));
-        }
-        const size_t off = ((((size_t)b * c8_total + plane0 + pl) * Hp + (y + HALO)) * P + (x + HALO)) * 8;
-        *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(h);
-        if (out_lo) *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(l);
+    for (int e = 0; e < 8; ++e) {
+        const float f = (pl * 8 + e < C) ? __ldg(src + (long long)e * H * W) : 0.f;
+        h[e] = __float2half_rn(f);
+        l[e] = __float2half_rn(f - __half2float(h[e]));
     }
+    const size_t off = ((((size_t)b * c8_total + plane0 + pl) * Hp + (y + HALO)) * P + (x + HALO)) * 8;
+    *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(h);
+    if (out_lo) *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(l);
 }
 
 // mode 3 companion of to_blk8: fp8 planes 2c = e4m3(x), 2c+1 = e4m3((x - fp16(x)) * 2^11), 16 channels each
-__global__ void to_q8_kernel(const float* __restrict__ in, uint8_t* __restrict__ outq, int C, int H, int W,
-                             int Hp, int P, int c8_total, int plane0, long long in_bstride, long long total) {
-    const int nc = (C + 15) / 16;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int x = idx % W;
-        long long t = idx / W;
-        const int y = t % H; t /= H;
-        const int cc = t % nc;
-        const long long b = t / nc;
-        __align__(16) uint8_t a8[16];
-        __align__(16) uint8_t l8[16];
+__global__ void __launch_bounds__(128) to_q8_kernel(const float* __restrict__ in, uint8_t* __restrict__ outq, int C, int H,
+                                                    int W, int Hp, int P, int c8_total, int plane0, long long in_bstride, int nc) {
+    const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const int b = blockIdx.z / nc, cc = blockIdx.z - b * nc;
+    __align__(16) uint8_t a8[16];
+    __align__(16) uint8_t l8[16];
+    const float* src = in + (long long)b * in_bstride + ((long long)(cc * 16) * H + y) * W + x;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            const int c = cc * 16 + e;
-            const float f = c < C ? __ldg(in + b * in_bstride + ((long long)c * H + y) * W + x) : 0.f;
-            a8[e] = to_e4m3(f);
-            l8[e] = to_e4m3((f - __half2float(__float2half_rn(f))) * LO_SCALE);
-        }
-        const size_t off0 = ((((size_t)b * c8_total + plane0 + 2 * cc) * Hp + (y + HALO)) * P + (x + HALO)) * 16;
-        const size_t off1 = ((((size_t)b * c8_total + plane0 + 2 * cc + 1) * Hp + (y + HALO)) * P + (x + HALO)) * 16;
-        *reinterpret_cast<uint4*>(outq + off0) = *reinterpret_cast<const uint4*>(a8);
-        *reinterpret_cast<uint4*>(outq + off1) = *reinterpret_cast<const uint4*>(l8);
+    for (int e = 0; e < 16; ++e) {
+        const float f = (cc * 16 + e < C) ? __ldg(src + (long long)e * H * W) : 0.f;
+        a8[e] = to_e4m3(f);
+        l8[e] = to_e4m3((f - __half2float(__float2half_rn(f))) * LO_SCALE);
     }
+    const size_t off0 = ((((size_t)b * c8_total + plane0 + 2 * cc) * Hp + (y + HALO)) * P + (x + HALO)) * 16;
+    const size_t off1 = off0 + (size_t)Hp * P * 16;
+    *reinterpret_cast<uint4*>(outq + off0) = *reinterpret_cast<const uint4*>(a8);
+    *reinterpret_cast<uint4*>(outq + off1) = *reinterpret_cast<const uint4*>(l8);
 }
 
-// BLK8 fp16 -> NCHW fp32
-__global__ void from_blk8_kernel(const __half* __restrict__ in, const __half* __restrict__ in_lo, float* __restrict__ out, int C, int H, int W,
-                                 int Hp, int P, int c8_total, int plane0, long long out_bstride, long long total, int mode) {
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int x = idx % W;
-        long long t = idx / W;
-        const int y = t % H; t /= H;
-        const int c = t % C;
-        const long long b = t / C;
-        const size_t off = ((((size_t)b * c8_total + plane0 + (c >> 3)) * Hp + (y + HALO)) * P + (x + HALO)) * 8 + (c & 7);
-        float f = __half2float(in[off]);
-        if (in_lo && mode == 2) f += __half2float(in_lo[off]);
-        if (in_lo && mode == 3) {
-            const size_t qoff = ((((size_t)b * c8_total + plane0 + 2 * (c >> 4) + 1) * Hp + (y + HALO)) * P + (x + HALO)) * 16 + (c & 15);
-            f += from_e4m3(reinterpret_cast<const uint8_t*>(in_lo)[qoff]) * (1.0f / LO_SCALE);
-        }
-        out[b * out_bstride + ((long long)c * H + y) * W + x] = f;
+// BLK8 fp16 (+ remainder buffer) -> NCHW fp32.  grid (ceil(W/128), H, B*np): one 16-byte pixel read per thread,
+// eight coalesced channel-plane writes.
+__global__ void __launch_bounds__(128) from_blk8_kernel(const __half* __restrict__ in, const __half* __restrict__ in_lo,
+                                                        float* __restrict__ out, int C, int H, int W, int Hp, int P,
+                                                        int c8_total, int plane0, long long out_bstride, int np, int mode) {
+    const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const int b = blockIdx.z / np, pl = blockIdx.z - b * np;
+    const size_t off = ((((size_t)b * c8_total + plane0 + pl) * Hp + (y + HALO)) * P + (x + HALO)) * 8;
+    const uint4 hv = *reinterpret_cast<const uint4*>(in + off);
+    const __half* h = reinterpret_cast<const __half*>(&hv);
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = __half2float(h[e]);
+    if (in_lo && mode == 2) {
+        const uint4 lv = *reinterpret_cast<const uint4*>(in_lo + off);
+        const __half* l = reinterpret_cast<const __half*>(&lv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] += __half2float(l[e]);
     }
+    if (in_lo && mode == 3) {
+        // channel c lives in fp8 plane 2*(c/16)+1 at byte c%16: this 8-channel plane is half of one 16-byte pixel
+        const size_t qoff = ((((size_t)b * c8_total + plane0 + 2 * (pl >> 1) + 1) * Hp + (y + HALO)) * P + (x + HALO)) * 16 + 8 * (pl & 1);
+        const uint2 qv = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(in_lo) + qoff);
+        const uint8_t* q = reinterpret_cast<const uint8_t*>(&qv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] += from_e4m3(q[e]) * (1.0f / LO_SCALE);
+    }
+    float* dst = out + (long long)b * out_bstride + ((long long)(pl * 8) * H + y) * W + x;
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        if (pl * 8 + e < C) dst[(long long)e * H * W] = f[e];
 }
 
-// halo fill of a BLK8 buffer: pad-wide ring around the interior, zero or SYMMETRIC mirror
-__global__ void blk8_halo_fill_kernel(__half* __restrict__ buf, int H, int W, int Hp, int P, int planes_total,
-                                      int pad, int mode, long long total) {
-    const int hw = W + 2 * pad, hh = H + 2 * pad;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int xx = idx % hw;
-        long long t = idx / hw;
-        const int yy = t % hh;
-        const long long bp = t / hh;   // (b, plane) flattened
-        const int y = yy - pad, x = xx - pad;
-        if (y >= 0 && y < H && x >= 0 && x < W) continue;
+// halo fill of a BLK8 buffer: pad-wide ring around the interior, zero or SYMMETRIC mirror.
+// grid (1, H + 2*pad, B*planes): interior rows only touch their 2*pad edge pixels.
+__global__ void __launch_bounds__(128) blk8_halo_fill_kernel(__half* __restrict__ buf, int H, int W, int Hp, int P, int pad, int mode) {
+    const int y = (int)blockIdx.y - pad;
+    const size_t plane = (size_t)blockIdx.z * Hp * P;
+    const bool edge_row = (y < 0) || (y >= H);
+    const int n = edge_row ? W + 2 * pad : 2 * pad;
+    const int sy = (mode == PCNN_PAD_SYMMETRIC) ? pad_src_index(y, H, PCNN_PAD_SYMMETRIC) : 0;
+    for (int i = threadIdx.x; i < n; i += 128) {
+        const int x = edge_row ? i - pad : (i < pad ? i - pad : W + (i - pad));
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (mode == PCNN_PAD_SYMMETRIC) {
-            const int sy = pad_src_index(y, H, PCNN_PAD_SYMMETRIC), sx = pad_src_index(x, W, PCNN_PAD_SYMMETRIC);
-            v = *reinterpret_cast<const uint4*>(buf + (((size_t)bp * Hp + (sy + HALO)) * P + (sx + HALO)) * 8);
-        }
-        *reinterpret_cast<uint4*>(buf + (((size_t)bp * Hp + (y + HALO)) * P + (x + HALO)) * 8) = v;
+        if (mode == PCNN_PAD_SYMMETRIC)
+            v = *reinterpret_cast<const uint4*>(buf + (plane + (size_t)(sy + HALO) * P + (pad_src_index(x, W, PCNN_PAD_SYMMETRIC) + HALO)) * 8);
+        *reinterpret_cast<uint4*>(buf + (plane + (size_t)(y + HALO) * P + (x + HALO)) * 8) = v;
     }
 }
 
-// DBCNN mode expansion straight into BLK8: out[b, m, x, y] = h[b,m,y] * S[m,x] * w[b,m]; channels M, M+1 = pos
-__global__ void dbcnn_expand_blk8_kernel(const float* __restrict__ h, const float* __restrict__ S,
-                                         const float* __restrict__ mw, const float* __restrict__ posx,
-                                         const float* __restrict__ posy, __half* __restrict__ out,
-                                         __half* __restrict__ out_lo, int M, int xres, int n, int c8_total, long long total, int mode) {
+// DBCNN mode expansion straight into BLK8: out[b, m, x, y] = h[b,m,y] * S[m,x] * w[b,m]; channels M, M+1 = pos.
+// grid (ceil(n/128), xres, B*np), thread = one 16-byte pixel of one plane.
+__global__ void __launch_bounds__(128) dbcnn_expand_blk8_kernel(const float* __restrict__ h, const float* __restrict__ S,
+                                                                const float* __restrict__ mw, const float* __restrict__ posx,
+                                                                const float* __restrict__ posy, __half* __restrict__ out,
+                                                                __half* __restrict__ out_lo, int M, int xres, int n,
+                                                                int c8_total, int np, int mode) {
+    const int y = blockIdx.x * 128 + threadIdx.x, x = blockIdx.y;
+    if (y >= n) return;
     const int Hp = xres + 2 * HALO, P = n + 2 * HALO;
-    const int np = (M + 2 + 7) / 8;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int y = idx % n;
-        long long t = idx / n;
-        const int x = t % xres; t /= xres;
-        const int pl = t % np;
-        const long long b = t / np;
-        __align__(16) __half v[8];
-        __align__(16) __half l[8];
+    const int b = blockIdx.z / np, pl = blockIdx.z - b * np;
+    __align__(16) __half v[8];
+    __align__(16) __half l[8];
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int m = pl * 8 + e;
+        f[e] = 0.f;
+        if (m < M) f[e] = __ldg(h + ((long long)b * M + m) * n + y) * __ldg(S + (long long)m * xres + x) * __ldg(mw + (long long)b * M + m);
+        else if (m == M) f[e] = __ldg(posx + x);
+        else if (m == M + 1) f[e] = __ldg(posy + y);
+        v[e] = __float2half_rn(f[e]);
+        l[e] = __float2half_rn(f[e] - __half2float(v[e]));
+    }
+    const size_t off = ((((size_t)b * c8_total + pl) * Hp + (x + HALO)) * P + (y + HALO)) * 8;
+    *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(v);
+    if (out_lo && mode == 2) *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(l);
+    if (out_lo && mode == 3) {
+        // fp8 planes 2(pl/2), 2(pl/2)+1, bytes [8*(pl&1), +8): each thread fills its half of the 16-channel group
+        uint8_t* q = reinterpret_cast<uint8_t*>(out_lo);
+        __align__(8) uint8_t a8[8];
+        __align__(8) uint8_t l8[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int m = pl * 8 + e;
-            float f = 0.f;
-            if (m < M) f = __ldg(h + (b * M + m) * n + y) * __ldg(S + (long long)m * xres + x) * __ldg(mw + b * M + m);
-            else if (m == M) f = __ldg(posx + x);
-            else if (m == M + 1) f = __ldg(posy + y);
-            v[e] = __float2half_rn(f);
-            l[e] = __float2half_rn(f - __half2float(v[e]));
+            a8[e] = to_e4m3(f[e]);
+            l8[e] = to_e4m3((f[e] - __half2float(v[e])) * LO_SCALE);
         }
-        const size_t off = ((((size_t)b * c8_total + pl) * Hp + (x + HALO)) * P + (y + HALO)) * 8;
-        *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(v);
-        if (out_lo && mode == 2) *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(l);
-        if (out_lo && mode == 3) {
-            // fp8 planes 2(pl/2), 2(pl/2)+1, bytes [8*(pl&1), +8): each thread fills its half of the 16-channel groups
-            uint8_t* q = reinterpret_cast<uint8_t*>(out_lo);
-            __align__(8) uint8_t a8[8];
-            __align__(8) uint8_t l8[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float f = __half2float(v[e]) + __half2float(l[e]);   // == the fp32 value to within 2^-22
-                a8[e] = to_e4m3(f);
-                l8[e] = to_e4m3((f - __half2float(v[e])) * LO_SCALE);
-            }
-            const size_t q0 = ((((size_t)b * c8_total + 2 * (pl >> 1)) * Hp + (x + HALO)) * P + (y + HALO)) * 16 + 8 * (pl & 1);
-            const size_t q1 = ((((size_t)b * c8_total + 2 * (pl >> 1) + 1) * Hp + (x + HALO)) * P + (y + HALO)) * 16 + 8 * (pl & 1);
-            *reinterpret_cast<uint2*>(q + q0) = *reinterpret_cast<const uint2*>(a8);
-            *reinterpret_cast<uint2*>(q + q1) = *reinterpret_cast<const uint2*>(l8);
-        }
+        const size_t q0 = ((((size_t)b * c8_total + 2 * (pl >> 1)) * Hp + (x + HALO)) * P + (y + HALO)) * 16 + 8 * (pl & 1);
+        const size_t q1 = q0 + (size_t)Hp * P * 16;
+        *reinterpret_cast<uint2*>(q + q0) = *reinterpret_cast<const uint2*>(a8);
+        *reinterpret_cast<uint2*>(q + q1) = *reinterpret_cast<const uint2*>(l8);
     }
 }
 
@@ -709,12 +704,12 @@ extern "C" int pcnn_to_blk8(const float* in, void* out, void* out_lo, int mode, 
     PCNN_CHECK_ARG(mode != 3 || (c_offset % 16) == 0, "to_blk8: mode 3 needs a channel offset that is a multiple of 16");
     PCNN_CHECK_ARG(in && out && B > 0 && C > 0 && (c_offset % 8) == 0 && c_offset + C <= ((c_total + 15) / 16) * 16, "to_blk8: bad argument");
     const int c8_total = ((c_total + 15) / 16) * 2;
-    const long long total = (long long)B * ((C + 7) / 8) * H * W;
-    to_blk8_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(in, (__half*)out, mode == 2 ? (__half*)out_lo : nullptr, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, in_bstride, total);
+    const int np = (C + 7) / 8, nc = (C + 15) / 16;
+    PCNN_CHECK_ARG(H <= 65535 && (long long)B * np <= 65535, "to_blk8: grid too large (H %d, B*planes %lld)", H, (long long)B * np);
+    to_blk8_kernel<<<dim3(ceil_div(W, 128), H, B * np), 128, 0, (cudaStream_t)stream>>>(in, (__half*)out, mode == 2 ? (__half*)out_lo : nullptr, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, in_bstride, np);
     PCNN_CHECK_LAUNCH();
     if (mode == 3) {
-        const long long tq = (long long)B * ((C + 15) / 16) * H * W;
-        to_q8_kernel<<<grid_for(tq), 256, 0, (cudaStream_t)stream>>>(in, (uint8_t*)out_lo, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, in_bstride, tq);
+        to_q8_kernel<<<dim3(ceil_div(W, 128), H, B * nc), 128, 0, (cudaStream_t)stream>>>(in, (uint8_t*)out_lo, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, in_bstride, nc);
         PCNN_CHECK_LAUNCH();
     }
     return PCNN_OK;
@@ -723,10 +718,12 @@ extern "C" int pcnn_to_blk8(const float* in, void* out, void* out_lo, int mode, 
 extern "C" int pcnn_from_blk8(const void* in, const void* in_lo, int mode, float* out, int B, int C, int H, int W, int c_total, int c_offset,
                               int64_t out_bstride, void* stream) {
     PCNN_CHECK_ARG(mode >= 1 && mode <= 3, "from_blk8: bad precision mode");
+    PCNN_CHECK_ARG(mode != 3 || (c_offset % 16) == 0, "from_blk8: mode 3 needs a channel offset that is a multiple of 16");
     PCNN_CHECK_ARG(in && out && B > 0 && C > 0 && (c_offset % 8) == 0, "from_blk8: bad argument");
     const int c8_total = ((c_total + 15) / 16) * 2;
-    const long long total = (long long)B * C * H * W;
-    from_blk8_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const __half*)in, mode >= 2 ? (const __half*)in_lo : nullptr, out, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, out_bstride, total, mode);
+    const int np = (C + 7) / 8;
+    PCNN_CHECK_ARG(H <= 65535 && (long long)B * np <= 65535, "from_blk8: grid too large");
+    from_blk8_kernel<<<dim3(ceil_div(W, 128), H, B * np), 128, 0, (cudaStream_t)stream>>>((const __half*)in, mode >= 2 ? (const __half*)in_lo : nullptr, out, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, out_bstride, np, mode);
     PCNN_CHECK_LAUNCH();
     return PCNN_OK;
 }
@@ -737,8 +734,8 @@ extern "C" int pcnn_blk8_halo_fill(void* buf, int B, int C, int H, int W, int pa
     if (mode == PCNN_PAD_SYMMETRIC) PCNN_CHECK_ARG(pad <= H && pad <= W, "blk8_halo_fill: SYMMETRIC pad %d larger than the tensor (%d,%d)", pad, H, W);
     if (pad == 0) return PCNN_OK;
     const int planes = ((C + 15) / 16) * 2;
-    const long long total = (long long)B * planes * (H + 2 * pad) * (W + 2 * pad);
-    blk8_halo_fill_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((__half*)buf, H, W, H + 2 * HALO, W + 2 * HALO, planes, pad, mode, total);
+    PCNN_CHECK_ARG(H + 2 * pad <= 65535 && (long long)B * planes <= 65535, "blk8_halo_fill: grid too large");
+    blk8_halo_fill_kernel<<<dim3(1, H + 2 * pad, B * planes), 128, 0, (cudaStream_t)stream>>>((__half*)buf, H, W, H + 2 * HALO, W + 2 * HALO, pad, mode);
     PCNN_CHECK_LAUNCH();
     return PCNN_OK;
 }
@@ -747,8 +744,9 @@ extern "C" int pcnn_dbcnn_expand_blk8(const float* h, const float* sinh_basis, c
                                       const float* posy, void* out, void* out_lo, int mode, int B, int M, int xres, int n, void* stream) {
     PCNN_CHECK_ARG(h && sinh_basis && modew && posx && posy && out && B > 0 && M > 0, "dbcnn_expand_blk8: bad argument");
     const int c8_total = ((M + 2 + 15) / 16) * 2;
-    const long long total = (long long)B * ((M + 2 + 7) / 8) * xres * n;
-    dbcnn_expand_blk8_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(h, sinh_basis, modew, posx, posy, (__half*)out, (__half*)out_lo, M, xres, n, c8_total, total, mode);
+    const int np = (M + 2 + 7) / 8;
+    PCNN_CHECK_ARG(xres <= 65535 && (long long)B * np <= 65535, "dbcnn_expand_blk8: grid too large");
+    dbcnn_expand_blk8_kernel<<<dim3(ceil_div(n, 128), xres, B * np), 128, 0, (cudaStream_t)stream>>>(h, sinh_basis, modew, posx, posy, (__half*)out, (__half*)out_lo, M, xres, n, c8_total, np, mode);
     PCNN_CHECK_LAUNCH();
     return PCNN_OK;
 }

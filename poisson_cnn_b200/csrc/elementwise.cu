@@ -21,48 +21,39 @@ void set_error(const char* fmt, ...) {
 }
 
 // ------------------------------------------------------------------ avg pool (SAME, pool=stride=s)
-__global__ void avgpool_thread_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
-                                      int H, int W, int oh, int ow, int s, int pt, int pl,
-                                      long long in_bstride, long long total) {
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int ox = idx % ow;
-        long long t = idx / ow;
-        const int oy = t % oh; t /= oh;
-        const int c = t % C;
-        const int b = t / C;
-        const int ys = max(oy * s - pt, 0), ye = min(oy * s - pt + s, H);
-        const int xs = max(ox * s - pl, 0), xe = min(ox * s - pl + s, W);
-        const float* src = in + (long long)b * in_bstride + (long long)c * H * W;
-        float acc = 0.f;
-        for (int y = ys; y < ye; ++y)
-            for (int x = xs; x < xe; ++x) acc += __ldg(src + (long long)y * W + x);
-        out[idx] = acc / (float)((ye - ys) * (xe - xs));
-    }
+// grid (ceil(ow/128), oh, B*C): no per-element div/mod.  Small windows: one thread per output.
+__global__ void __launch_bounds__(128) avgpool_thread_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
+                                                             int H, int W, int oh, int ow, int s, int pt, int pl,
+                                                             long long in_bstride) {
+    const int ox = blockIdx.x * 128 + threadIdx.x, oy = blockIdx.y;
+    if (ox >= ow) return;
+    const int b = blockIdx.z / C, c = blockIdx.z - b * C;
+    const int ys = max(oy * s - pt, 0), ye = min(oy * s - pt + s, H);
+    const int xs = max(ox * s - pl, 0), xe = min(ox * s - pl + s, W);
+    const float* src = in + (long long)b * in_bstride + (long long)c * H * W;
+    float acc = 0.f;
+    for (int y = ys; y < ye; ++y)
+        for (int x = xs; x < xe; ++x) acc += __ldg(src + (long long)y * W + x);
+    out[((long long)blockIdx.z * oh + oy) * ow + ox] = acc / (float)((ye - ys) * (xe - xs));
 }
 
-__global__ void avgpool_warp_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
-                                    int H, int W, int oh, int ow, int s, int pt, int pl,
-                                    long long in_bstride, long long total) {
+// Large windows: one warp per output, lanes stride the window columns (coalesced rows).
+// grid (ceil(ow/8), oh, B*C), 8 warps per CTA.
+__global__ void __launch_bounds__(256) avgpool_warp_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
+                                                           int H, int W, int oh, int ow, int s, int pt, int pl,
+                                                           long long in_bstride) {
     const int lane = threadIdx.x & 31;
-    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long idx = warp; idx < total; idx += nwarps) {
-        const int ox = idx % ow;
-        long long t = idx / ow;
-        const int oy = t % oh; t /= oh;
-        const int c = t % C;
-        const int b = t / C;
-        const int ys = max(oy * s - pt, 0), ye = min(oy * s - pt + s, H);
-        const int xs = max(ox * s - pl, 0), xe = min(ox * s - pl + s, W);
-        const int wcols = xe - xs;
-        const float* src = in + (long long)b * in_bstride + (long long)c * H * W;
-        float acc = 0.f;
-        for (int y = ys; y < ye; ++y)
-            for (int x = xs + lane; x < xe; x += 32) acc += __ldg(src + (long long)y * W + x);
-        acc = warp_sum(acc);
-        if (lane == 0) out[idx] = acc / (float)((ye - ys) * wcols);
-    }
+    const int ox = blockIdx.x * 8 + (threadIdx.x >> 5), oy = blockIdx.y;
+    if (ox >= ow) return;
+    const int b = blockIdx.z / C, c = blockIdx.z - b * C;
+    const int ys = max(oy * s - pt, 0), ye = min(oy * s - pt + s, H);
+    const int xs = max(ox * s - pl, 0), xe = min(ox * s - pl + s, W);
+    const float* src = in + (long long)b * in_bstride + (long long)c * H * W;
+    float acc = 0.f;
+    for (int y = ys; y < ye; ++y)
+        for (int x = xs + lane; x < xe; x += 32) acc += __ldg(src + (long long)y * W + x);
+    acc = warp_sum(acc);
+    if (lane == 0) out[((long long)blockIdx.z * oh + oy) * ow + ox] = acc / (float)((ye - ys) * (xe - xs));
 }
 
 // ------------------------------------------------------------------ transpose conv (SAME)
@@ -207,23 +198,33 @@ __global__ void __launch_bounds__(256) resize_small_kernel(const float* __restri
     for (int i = threadIdx.x; i < nsrc; i += blockDim.x) ssrc[i] = __ldg(in + (long long)b * nsrc + i);
     __syncthreads();
     const int rows = min(rows_per_cta, oh - Y0);
-    const int total = C * rows * ow;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int X = idx % ow;
-        int t = idx / ow;
-        const int Y = Y0 + t % rows;
-        const int c = t / rows;
-        const float* src = ssrc + c * ih * iw;
-        float acc = 0.f;
-        for (int a = 0; a < taps; ++a) {
-            const float* row = src + __ldg(iy + Y * taps + a) * iw;
-            float r = 0.f;
-            for (int q = 0; q < taps; ++q) r = fmaf(row[__ldg(ix + X * taps + q)], __ldg(wx + X * taps + q), r);
-            acc = fmaf(r, __ldg(wy + Y * taps + a), acc);
+    for (int X = threadIdx.x; X < ow; X += blockDim.x) {
+        int xi[4]; float xw[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { xi[q] = q < taps ? __ldg(ix + X * taps + q) : 0; xw[q] = q < taps ? __ldg(wx + X * taps + q) : 0.f; }
+        for (int r = 0; r < rows; ++r) {
+            const int Y = Y0 + r;
+            int yi[4]; float yw[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) { yi[a] = a < taps ? __ldg(iy + Y * taps + a) * iw : 0; yw[a] = a < taps ? __ldg(wy + Y * taps + a) : 0.f; }
+            for (int c = 0; c < C; ++c) {
+                const float* src = ssrc + c * ih * iw;
+                float acc = 0.f;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    if (a < taps) {
+                        float rr = 0.f;   // TF interpolates along x first, then along y
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (q < taps) rr = fmaf(src[yi[a] + xi[q]], xw[q], rr);
+                        acc = fmaf(rr, yw[a], acc);
+                    }
+                }
+                acc *= alpha;
+                float* o = out + (long long)b * out_bstride + ((long long)c * oh + Y) * ow + X;
+                *o = accumulate ? (*o + acc) : acc;
+            }
         }
-        acc *= alpha;
-        float* o = out + (long long)b * out_bstride + ((long long)c * oh + Y) * ow + X;
-        *o = accumulate ? (*o + acc) : acc;
     }
 }
 
@@ -439,11 +440,11 @@ extern "C" int pcnn_avgpool_same_f32(const float* in, float* out, int B, int C, 
     PCNN_CHECK_ARG(in && out && B > 0 && C > 0 && H > 0 && W > 0 && s > 0, "avgpool_same_f32: bad argument");
     const int oh = ceil_div(H, s), ow = ceil_div(W, s);
     const int pt = (oh * s - H) / 2, pl = (ow * s - W) / 2;
-    const long long total = (long long)B * C * oh * ow;
+    PCNN_CHECK_ARG(oh <= 65535 && (long long)B * C <= 65535, "avgpool_same_f32: grid too large");
     if (s <= 4) {
-        avgpool_thread_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(in, out, C, H, W, oh, ow, s, pt, pl, in_bstride, total);
+        avgpool_thread_kernel<<<dim3(ceil_div(ow, 128), oh, B * C), 128, 0, (cudaStream_t)stream>>>(in, out, C, H, W, oh, ow, s, pt, pl, in_bstride);
     } else {
-        avgpool_warp_kernel<<<grid_for(total * 32), 256, 0, (cudaStream_t)stream>>>(in, out, C, H, W, oh, ow, s, pt, pl, in_bstride, total);
+        avgpool_warp_kernel<<<dim3(ceil_div(ow, 8), oh, B * C), 256, 0, (cudaStream_t)stream>>>(in, out, C, H, W, oh, ow, s, pt, pl, in_bstride);
     }
     PCNN_CHECK_LAUNCH();
     return PCNN_OK;
