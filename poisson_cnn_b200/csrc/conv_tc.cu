@@ -42,6 +42,7 @@ constexpr int HALO = 7;            // materialised halo of the BLK8 layout (kern
 constexpr int ROWS_PER_TILE = 4;   // output rows per tile (M = 4 x 32)
 constexpr int COUT_PAD = 32;
 constexpr int NUM_EPI_WARPS = 8;
+constexpr int STAGE_PX = 16;          // pixels per pass through an epilogue warp's transpose buffer
 constexpr int NUM_THREADS = (3 + NUM_EPI_WARPS) * 32;
 constexpr int ZPAD = ROWS_PER_TILE - 1;   // zero z-rows on each side of the packed weights
 constexpr float LO_SCALE = 2048.f;        // 2^11: brings the fp16 rounding remainder into e4m3's range (mode 3)
@@ -74,6 +75,7 @@ struct Params {
     int tiles_x, tiles_y, num_tiles;
     int row_slots;           // ring of input-row slots (>= kh+3)
     int w_stages;
+    int w_resident;          // 1: all nv*kw weight stages fit in shared memory -> loaded once per CTA, reused by every tile
     uint32_t rowplane_bytes; // bytes of one plane of one row window in smem (multiple of 128)
     uint32_t row_copy_bytes; // (n_tile + kw - 1) * 16
     uint32_t wstage_bytes;   // 2 * (kh+6) * 512
@@ -133,6 +135,13 @@ __device__ __forceinline__ float tanh_approx(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// tanh to ~1e-7 absolute without the slow libm path: odd polynomial near 0, 1 - 2/(e^{2x}+1) elsewhere
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float ax = fabsf(x);
+    if (ax < 0.08f) { const float x2 = x * x; return x * fmaf(x2, fmaf(x2, 0.13333334f, -0.33333334f), 1.0f); }
+    const float e = __expf(2.0f * fminf(ax, 15.0f));
+    return copysignf(1.0f - __fdividef(2.0f, e + 1.0f), x);
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -181,7 +190,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
     const uint32_t row_slot_bytes = 2 * p.rowplane_bytes;
     uint8_t* s_w = s_rows + (size_t)p.row_slots * row_slot_bytes;
     uint8_t* s_stage = s_w + (size_t)p.w_stages * p.wstage_bytes;
-    constexpr int STAGE_PLANE = 32 * 16 + 16;   // 32 px x 16 B, +16 B so the 4 planes hit different banks
+    constexpr int STAGE_PLANE = STAGE_PX * 16 + 16;   // 16 px x 16 B, +16 B so the 4 planes hit different banks
     constexpr int STAGE_WARP = 4 * STAGE_PLANE;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + NUM_EPI_WARPS * STAGE_WARP);
     uint64_t* row_full = bars;
@@ -244,6 +253,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
         if (lane == 0) {
             uint32_t g = 0;
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                if (p.w_resident && t != (int)blockIdx.x) break;    // resident weights: one pass fills every stage
                 for (int v = 0; v < p.nv; ++v) {
                     const int c = (p.nsplit == 2) ? v / 3 : (p.nsplit == 3 ? v >> 1 : v);
                     const int wsel = ((p.nsplit == 2 && (v % 3) == 1) || (p.nsplit == 3 && (v & 1))) ? 1 : 0;   // second weight image
@@ -285,7 +295,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                     const int n1 = min((int)(nslots - slot0), R);
                     const bool f8 = (p.nsplit == 3) && (c & 1);    // correction pass: e4m3 operands, K = 32
                     for (int dx = 0; dx < p.kw; ++dx) {
-                        mbar_wait(w_full + wst, wph);
+                        mbar_wait(w_full + wst, p.w_resident ? 0u : wph);   // resident stages complete once and stay
                         tc_fence_after();
                         uint32_t a_lo = ((w_base16 + wst * wstage16) & 0x3FFF) | a_lo_lbo;
                         const bool first_dx = (dx == 0), last_dx = (dx == p.kw - 1);
@@ -331,7 +341,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                                 a_lo += 32u * nrow;
                             }
                         }
-                        if (leader) tc_commit(w_empty + wst);
+                        if (leader && !p.w_resident) tc_commit(w_empty + wst);
                         if (++wst == nwst) { wst = 0; wph ^= 1; }
                     }
                     slot0 += R;
@@ -374,8 +384,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                 uint32_t v[32];
                 tmem_ld32(taddr0 + c0, v);
                 if (y < p.H) {
-                    const int x = x0 + c0 + lane;
-                    const bool xok = (x < p.W) && (c0 + lane < p.n_tile);
                     __half* srow = reinterpret_cast<__half*>(stage + (co >> 3) * STAGE_PLANE) + (co & 7);
                     // bias -> activation -> (BN affine * scale).  Padded channels (co >= cout) come out
                     // as exact zeros: zero weights, bias 0, shift 0.
@@ -390,88 +398,111 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float a = fmaf(__uint_as_float(v[j]), asc, bias);
-                            const float f = (p.nsplit >= 2) ? tanhf(a) : tanh_approx(a);
+                            const float f = (p.nsplit >= 2) ? tanh_fast(a) : tanh_approx(a);
                             v[j] = __float_as_uint(fmaf(f, mul, add));
                         }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(fmaf(__uint_as_float(v[j]), asc, bias), mul, add));
                     }
-                    constexpr int QGRP = 32 * 16 + 16;   // stride of a 16-channel fp8 group in the transpose buffer
+                    // ---- residual add (fp32) and stores, 16 pixels per pass through the transpose buffer:
+                    //      thread = (channel, 16 pixels) on the way in; lane = (pixel, plane parity) on the way out
+                    constexpr int QGRP = STAGE_PX * 16 + 16;   // stride of a 16-channel fp8 group in the transpose buffer
                     const int qgroups = (p.cout + 15) / 16;
                     uint8_t* qrow = stage + (co >> 4) * QGRP + (co & 15);
-                    if (p.residual) {
-                        // residual: coalesced 16-B loads -> transpose buffer -> per-(channel, pixel) fp32 add
-                        const int nparts = (p.nsplit == 2) ? 2 : 1;
-                        for (int part = 0; part < nparts; ++part) {
-                            const __half* rsrc = part ? p.residual_lo : p.residual;
-                            for (int pl = 0; pl < planes_out; ++pl) {
-                                uint4 rv = make_uint4(0, 0, 0, 0);
-                                if (xok) rv = *reinterpret_cast<const uint4*>(rsrc + ((((size_t)b * p.c8_res + pl) * p.Hp + (y + HALO)) * p.P + (x + HALO)) * 8);
-                                *reinterpret_cast<uint4*>(stage + pl * STAGE_PLANE + lane * 16) = rv;
+                    const int px = lane & 15, psel = lane >> 4;
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int x = x0 + c0 + STAGE_PX * h2 + px;
+                        const bool xok = (x < p.W) && (c0 + STAGE_PX * h2 + px < p.n_tile);
+                        const size_t pix = (size_t)(y + HALO) * p.P + (x + HALO);
+                        if (p.residual) {
+                            const int nparts = (p.nsplit == 2) ? 2 : 1;
+                            for (int part = 0; part < nparts; ++part) {
+                                const __half* rsrc = part ? p.residual_lo : p.residual;
+                                for (int pl2 = 0; pl2 < planes_out; pl2 += 2) {
+                                    const int pl = pl2 + psel;
+                                    if (pl < planes_out) {
+                                        uint4 rv = make_uint4(0, 0, 0, 0);
+                                        if (xok) rv = *reinterpret_cast<const uint4*>(rsrc + (((size_t)b * p.c8_res + pl) * p.Hp * p.P + pix) * 8);
+                                        *reinterpret_cast<uint4*>(stage + pl * STAGE_PLANE + px * 16) = rv;
+                                    }
+                                }
+                                __syncwarp();
+                                if (live) {
+#pragma unroll
+                                    for (int jj = 0; jj < STAGE_PX; ++jj)
+                                        v[STAGE_PX * h2 + jj] = __float_as_uint(__uint_as_float(v[STAGE_PX * h2 + jj]) + __half2float(srow[jj * 8]));
+                                }
+                                __syncwarp();
+                            }
+                            if (p.nsplit == 3) {   // remainder of the residual: e4m3 plane 2g+1, scaled by 2^11
+                                const uint8_t* rq = reinterpret_cast<const uint8_t*>(p.residual_lo);
+                                for (int g2 = 0; g2 < qgroups; g2 += 2) {
+                                    const int g = g2 + psel;
+                                    if (g < qgroups) {
+                                        uint4 rv = make_uint4(0, 0, 0, 0);
+                                        if (xok) rv = *reinterpret_cast<const uint4*>(rq + (((size_t)b * p.c8_res + 2 * g + 1) * p.Hp * p.P + pix) * 16);
+                                        *reinterpret_cast<uint4*>(stage + g * QGRP + px * 16) = rv;
+                                    }
+                                }
+                                __syncwarp();
+                                if (live) {
+#pragma unroll
+                                    for (int jj = 0; jj < STAGE_PX; ++jj)
+                                        v[STAGE_PX * h2 + jj] = __float_as_uint(fmaf(from_e4m3(qrow[jj * 16]), 1.0f / LO_SCALE, __uint_as_float(v[STAGE_PX * h2 + jj])));
+                                }
+                                __syncwarp();
+                            }
+                        }
+                        if (p.nsplit == 3) {
+                            // e4m3(x) for the next layer's correction MMA (plane 2g of the q buffer)
+                            uint8_t* dq = reinterpret_cast<uint8_t*>(p.out_lo);
+#pragma unroll
+                            for (int jj = 0; jj < STAGE_PX; ++jj) qrow[jj * 16] = to_e4m3(__uint_as_float(v[STAGE_PX * h2 + jj]));
+                            __syncwarp();
+                            for (int g2 = 0; g2 < qgroups; g2 += 2) {
+                                const int g = g2 + psel;
+                                if (g < qgroups && xok)
+                                    *reinterpret_cast<uint4*>(dq + (((size_t)b * p.c8_out + 2 * g) * p.Hp * p.P + pix) * 16) =
+                                        *reinterpret_cast<const uint4*>(stage + g * QGRP + px * 16);
                             }
                             __syncwarp();
-                            if (live) {
+                        }
+                        const int nparts_out = (p.nsplit == 2) ? 2 : 1;
+                        for (int part = 0; part < nparts_out; ++part) {
+                            // fp16 (hi), then the rounding remainder (lo)
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __half2float(srow[j * 8]));
+                            for (int jj = 0; jj < STAGE_PX; ++jj) {
+                                const float f = __uint_as_float(v[STAGE_PX * h2 + jj]);
+                                const __half hh = __float2half_rn(f);
+                                srow[jj * 8] = hh;
+                                v[STAGE_PX * h2 + jj] = __float_as_uint(f - __half2float(hh));
+                            }
+                            __syncwarp();
+                            __half* dst = part ? p.out_lo : p.out;
+                            for (int pl2 = 0; pl2 < planes_out; pl2 += 2) {
+                                const int pl = pl2 + psel;
+                                if (pl < planes_out && xok)
+                                    *reinterpret_cast<uint4*>(dst + (((size_t)b * p.c8_out + pl) * p.Hp * p.P + pix) * 8) =
+                                        *reinterpret_cast<const uint4*>(stage + pl * STAGE_PLANE + px * 16);
                             }
                             __syncwarp();
                         }
-                        if (p.nsplit == 3) {   // remainder of the residual: e4m3 plane 2g+1, scaled by 2^11
-                            const uint8_t* rq = reinterpret_cast<const uint8_t*>(p.residual_lo);
-                            for (int g = 0; g < qgroups; ++g) {
-                                uint4 rv = make_uint4(0, 0, 0, 0);
-                                if (xok) rv = *reinterpret_cast<const uint4*>(rq + ((((size_t)b * p.c8_res + 2 * g + 1) * p.Hp + (y + HALO)) * p.P + (x + HALO)) * 16);
-                                *reinterpret_cast<uint4*>(stage + g * QGRP + lane * 16) = rv;
+                        if (p.nsplit == 3) {
+                            // e4m3((x - hi) * 2^11): plane 2g+1 of the q buffer
+                            uint8_t* dq = reinterpret_cast<uint8_t*>(p.out_lo);
+#pragma unroll
+                            for (int jj = 0; jj < STAGE_PX; ++jj) qrow[jj * 16] = to_e4m3(__uint_as_float(v[STAGE_PX * h2 + jj]) * LO_SCALE);
+                            __syncwarp();
+                            for (int g2 = 0; g2 < qgroups; g2 += 2) {
+                                const int g = g2 + psel;
+                                if (g < qgroups && xok)
+                                    *reinterpret_cast<uint4*>(dq + (((size_t)b * p.c8_out + 2 * g + 1) * p.Hp * p.P + pix) * 16) =
+                                        *reinterpret_cast<const uint4*>(stage + g * QGRP + px * 16);
                             }
                             __syncwarp();
-                            if (live) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(from_e4m3(qrow[j * 16]), 1.0f / LO_SCALE, __uint_as_float(v[j])));
-                            }
-                            __syncwarp();
                         }
-                    }
-                    if (p.nsplit == 3) {
-                        // e4m3(x) for the next layer's correction MMA (plane 2g of the q buffer)
-                        uint8_t* dq = reinterpret_cast<uint8_t*>(p.out_lo);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) qrow[j * 16] = to_e4m3(__uint_as_float(v[j]));
-                        __syncwarp();
-                        for (int g = 0; g < qgroups; ++g) {
-                            const uint4 val = *reinterpret_cast<const uint4*>(stage + g * QGRP + lane * 16);
-                            if (xok) *reinterpret_cast<uint4*>(dq + ((((size_t)b * p.c8_out + 2 * g) * p.Hp + (y + HALO)) * p.P + (x + HALO)) * 16) = val;
-                        }
-                        __syncwarp();
-                    }
-                    const int nparts_out = (p.nsplit == 2) ? 2 : 1;
-                    for (int part = 0; part < nparts_out; ++part) {
-                        // fp16 (hi), then the rounding remainder (lo), through the transpose buffer
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const __half h = __float2half_rn(__uint_as_float(v[j]));
-                            srow[j * 8] = h;
-                            v[j] = __float_as_uint(__uint_as_float(v[j]) - __half2float(h));
-                        }
-                        __syncwarp();
-                        __half* dst = part ? p.out_lo : p.out;
-                        for (int pl = 0; pl < planes_out; ++pl) {
-                            const uint4 val = *reinterpret_cast<const uint4*>(stage + pl * STAGE_PLANE + lane * 16);
-                            if (xok) *reinterpret_cast<uint4*>(dst + ((((size_t)b * p.c8_out + pl) * p.Hp + (y + HALO)) * p.P + (x + HALO)) * 8) = val;
-                        }
-                        __syncwarp();
-                    }
-                    if (p.nsplit == 3) {
-                        // e4m3((x - hi) * 2^11): plane 2g+1 of the q buffer
-                        uint8_t* dq = reinterpret_cast<uint8_t*>(p.out_lo);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) qrow[j * 16] = to_e4m3(__uint_as_float(v[j]) * LO_SCALE);
-                        __syncwarp();
-                        for (int g = 0; g < qgroups; ++g) {
-                            const uint4 val = *reinterpret_cast<const uint4*>(stage + g * QGRP + lane * 16);
-                            if (xok) *reinterpret_cast<uint4*>(dq + ((((size_t)b * p.c8_out + 2 * g + 1) * p.Hp + (y + HALO)) * p.P + (x + HALO)) * 16) = val;
-                        }
-                        __syncwarp();
                     }
                 }
             }
@@ -780,18 +811,31 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
     p.wstage_bytes = 2u * (uint32_t)(k + 2 * ZPAD) * 512u;
     // instruction descriptor: D=F32, A=B=F16, both K-major, N = n_tile, M = 128
     p.idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    // shared-memory plan: as many row slots as fit (>= kh+3, ideally 2x for full double buffering)
+    // shared-memory plan.  Rows need >= R slots (ideally 2R: full double buffering across chunk switches).  Weights:
+    // if every stage of a tile (nv*kw of them) fits, they stay RESIDENT for the whole kernel; otherwise as many
+    // stages as fit (<= 12) are kept in flight -- the weight stream is latency-bound with few small stages.
     const size_t kMax = 227 * 1024;
-    const size_t fixed = NUM_EPI_WARPS * (4 * (32 * 16 + 16)) + 1024;
+    const size_t fixed = NUM_EPI_WARPS * (4 * (STAGE_PX * 16 + 16)) + 2048;   // transpose buffers + mbarriers
     const int R = k + ZPAD;
-    int w_stages = 3;
-    size_t avail = kMax - fixed - (size_t)w_stages * p.wstage_bytes;
-    int slots = (int)(avail / (2 * p.rowplane_bytes));
-    if (slots < R) { w_stages = 2; avail = kMax - fixed - (size_t)w_stages * p.wstage_bytes; slots = (int)(avail / (2 * p.rowplane_bytes)); }
-    PCNN_CHECK_ARG(slots >= R, "conv2d_tc: tile does not fit in shared memory (k=%d, n_tile=%d)", k, p.n_tile);
-    if (slots > 2 * R) slots = 2 * R;
-    p.row_slots = slots; p.w_stages = w_stages;
-    const size_t smem = (size_t)slots * 2 * p.rowplane_bytes + (size_t)w_stages * p.wstage_bytes + fixed;
+    const size_t avail = kMax - fixed, rowslot = 2 * (size_t)p.rowplane_bytes, wst = p.wstage_bytes;
+    PCNN_CHECK_ARG((size_t)R * rowslot + 2 * wst <= avail, "conv2d_tc: tile does not fit in shared memory (k=%d, n_tile=%d)", k, p.n_tile);
+    const int total_stages = p.nv * k;
+    int slots, w_stages, resident = 0;
+    if ((size_t)R * rowslot + (size_t)total_stages * wst <= avail && total_stages <= 48) {
+        resident = 1; w_stages = total_stages;
+        slots = (int)std::min<size_t>(2 * R, (avail - (size_t)w_stages * wst) / rowslot);
+    } else {
+        slots = 2 * R;
+        w_stages = 0;
+        while (slots >= R) {
+            if ((size_t)slots * rowslot < avail) w_stages = (int)std::min<size_t>(12, (avail - (size_t)slots * rowslot) / wst);
+            if (w_stages >= 6 || (slots == R && w_stages >= 2)) break;
+            --slots;
+        }
+        PCNN_CHECK_ARG(slots >= R && w_stages >= 2, "conv2d_tc: shared-memory plan failed (k=%d, n_tile=%d)", k, p.n_tile);
+    }
+    p.row_slots = slots; p.w_stages = w_stages; p.w_resident = resident;
+    const size_t smem = (size_t)slots * rowslot + (size_t)w_stages * wst + fixed;
     PCNN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax));
     if (num_sms <= 0) num_sms = 148;
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;

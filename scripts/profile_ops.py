@@ -27,16 +27,31 @@ class Prof:
         def wrapped(*a):
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record(); r = fn(*a); e1.record()
-            records.append((name, e0, e1))
+            records.append((name, e0, e1, a[11:21] if name == "pcnn_conv2d_tc" else None))
             return r
         return wrapped
 ops.lib = Prof(_lib.lib)
 t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
 t0.record(); model(inp); t1.record(); torch.cuda.synchronize()
 agg = collections.defaultdict(lambda: [0, 0.0])
-for name, a, b in records:
+tc = collections.OrderedDict()
+for name, a, b, args in records:
     agg[name][0] += 1; agg[name][1] += a.elapsed_time(b)
+    if args is not None:
+        Bn, cin, cout, _, _, H, W, k, act, ns = args
+        key = (Bn, cin, cout, H, W, k)
+        tc.setdefault(key, [0, 0.0, ns])
+        tc[key][0] += 1; tc[key][1] += a.elapsed_time(b)
 total = t0.elapsed_time(t1); s = sum(v[1] for v in agg.values())
 print("B=%d %s: forward %.2f ms (%.3f ms/sample); sum over ops %.2f ms; torch/other %.2f ms" % (B, prec, total, total / B, s, total - s))
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print("  %-34s n=%4d %8.2f ms %5.1f%%" % (k, n, t, 100 * t / total))
+
+print("conv2d_tc launches by shape (B, Cin_total, Cout, H, W, k): n, total ms, fraction of the MMA floor (128 cyc/MMA @1.9 GHz, 148 SMs)")
+for (Bn, cin, cout, H, W, k), (n, t, ns) in sorted(tc.items(), key=lambda kv: -kv[1][1]):
+    ntile = 256 if W >= 256 else -(-W // 16) * 16
+    tiles = Bn * -(-H // 4) * -(-W // ntile)
+    nv = -(-cin // 16) * {1: 1, 2: 3, 3: 2}[ns]
+    mmas = tiles * nv * k * (k + 3)
+    floor_ms = -(-tiles // 148) * nv * k * (k + 3) * 128 * (ntile / 256.0) / 1.9e6
+    print("  %-32s n=%2d %8.2f ms  floor %.2f ms  -> %.0f%%" % ((Bn, cin, cout, H, W, k), n, t, floor_ms * n, 100 * floor_ms * n / t))
