@@ -136,11 +136,12 @@ __device__ __forceinline__ float tanh_approx(float x) {
     return y;
 }
 // tanh to ~1e-7 absolute without the slow libm path: odd polynomial near 0, 1 - 2/(e^{2x}+1) elsewhere
-__device__ __forceinline__ float tanh_fast(float x) {
-    const float ax = fabsf(x);
-    if (ax < 0.08f) { const float x2 = x * x; return x * fmaf(x2, fmaf(x2, 0.13333334f, -0.33333334f), 1.0f); }
+__device__ __forceinline__ float tanh_fast(float x) {   // branch-free: both forms are a handful of instructions
+    const float ax = fabsf(x), x2 = x * x;
+    const float small = x * fmaf(x2, fmaf(x2, 0.13333334f, -0.33333334f), 1.0f);
     const float e = __expf(2.0f * fminf(ax, 15.0f));
-    return copysignf(1.0f - __fdividef(2.0f, e + 1.0f), x);
+    const float big = copysignf(1.0f - __fdividef(2.0f, e + 1.0f), x);
+    return ax < 0.08f ? small : big;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -221,49 +222,51 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
 
     if (warp == 0) {
         // ================= input-row producer =================
-        if (lane == 0) {
-            uint32_t g = 0;   // running row counter -> ring slot / phase
-            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-                const int tx = t % p.tiles_x;
-                const int ty = (t / p.tiles_x) % p.tiles_y;
-                const int b = t / (p.tiles_x * p.tiles_y);
-                const int x0 = tx * p.n_tile, y0 = ty * ROWS_PER_TILE;
-                const int col0 = x0 + HALO - p.pad;
-                for (int v = 0; v < p.nv; ++v) {
-                    // split precision: per chunk c the passes are (x_hi,W_hi), (x_hi,W_lo), (x_lo,W_hi)
-                    const int c = (p.nsplit == 2) ? v / 3 : (p.nsplit == 3 ? v >> 1 : v);
-                    const __half* inp = ((p.nsplit == 2 && (v % 3) == 2) || (p.nsplit == 3 && (v & 1))) ? p.in_lo : p.in;
-                    for (int rho = 0; rho < R; ++rho, ++g) {
-                        const uint32_t slot = g % p.row_slots, ph = (g / p.row_slots) & 1;
-                        mbar_wait(row_empty + slot, ph ^ 1);
+        // converged warp, one elected lane issues the bulk copies; ring state advances by compare (no div/mod)
+        const bool leader = elect_one();
+        const size_t plane_elems = (size_t)p.Hp * p.P * 8;
+        uint32_t slot = 0, ph = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+            const int tx = t % p.tiles_x;
+            const int ty = (t / p.tiles_x) % p.tiles_y;
+            const int b = t / (p.tiles_x * p.tiles_y);
+            const int x0 = tx * p.n_tile, y0 = ty * ROWS_PER_TILE;
+            const int col0 = x0 + HALO - p.pad, prow0 = y0 + HALO - p.pad;
+            for (int v = 0; v < p.nv; ++v) {
+                // split precision: per chunk c the passes are (x_hi,W_hi), (x_hi,W_lo), (x_lo,W_hi); mode 3: (x_hi,W_hi), (q,Wq)
+                const int c = (p.nsplit == 2) ? v / 3 : (p.nsplit == 3 ? v >> 1 : v);
+                const __half* inp = ((p.nsplit == 2 && (v % 3) == 2) || (p.nsplit == 3 && (v & 1))) ? p.in_lo : p.in;
+                const __half* base = inp + ((size_t)b * p.c8_in + 2 * c) * plane_elems + (size_t)col0 * 8;
+                for (int rho = 0; rho < R; ++rho) {
+                    mbar_wait(row_empty + slot, ph ^ 1);
+                    if (leader) {
                         mbar_expect_tx(row_full + slot, 2 * p.row_copy_bytes);
-                        const int prow = min(y0 + rho + HALO - p.pad, p.Hp - 1);
-                        const uint32_t dst = smem_u32(s_rows + (size_t)slot * row_slot_bytes);
-#pragma unroll
-                        for (int pl = 0; pl < 2; ++pl) {
-                            const __half* src = inp + ((((size_t)b * p.c8_in + (2 * c + pl)) * p.Hp + prow) * p.P + col0) * 8;
-                            bulk_copy_g2s(dst + pl * p.rowplane_bytes, src, p.row_copy_bytes, row_full + slot);
-                        }
+                        const __half* src = base + (size_t)min(prow0 + rho, p.Hp - 1) * p.P * 8;
+                        const uint32_t dst = smem_u32(s_rows) + slot * row_slot_bytes;
+                        bulk_copy_g2s(dst, src, p.row_copy_bytes, row_full + slot);
+                        bulk_copy_g2s(dst + p.rowplane_bytes, src + plane_elems, p.row_copy_bytes, row_full + slot);
                     }
+                    if (++slot == (uint32_t)p.row_slots) { slot = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ================= weight producer =================
-        if (lane == 0) {
-            uint32_t g = 0;
-            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-                if (p.w_resident && t != (int)blockIdx.x) break;    // resident weights: one pass fills every stage
-                for (int v = 0; v < p.nv; ++v) {
-                    const int c = (p.nsplit == 2) ? v / 3 : (p.nsplit == 3 ? v >> 1 : v);
-                    const int wsel = ((p.nsplit == 2 && (v % 3) == 1) || (p.nsplit == 3 && (v & 1))) ? 1 : 0;   // second weight image
-                    for (int dx = 0; dx < p.kw; ++dx, ++g) {
-                        const uint32_t st = g % p.w_stages, ph = (g / p.w_stages) & 1;
-                        mbar_wait(w_empty + st, ph ^ 1);
+        const bool leader = elect_one();
+        uint32_t st = 0, ph = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+            if (p.w_resident && t != (int)blockIdx.x) break;    // resident weights: one pass fills every stage
+            for (int v = 0; v < p.nv; ++v) {
+                const int c = (p.nsplit == 2) ? v / 3 : (p.nsplit == 3 ? v >> 1 : v);
+                const int wsel = ((p.nsplit == 2 && (v % 3) == 1) || (p.nsplit == 3 && (v & 1))) ? 1 : 0;   // second weight image
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) + ((size_t)wsel * p.c16 + c) * p.kw * p.wstage_bytes;
+                for (int dx = 0; dx < p.kw; ++dx, src += p.wstage_bytes) {
+                    mbar_wait(w_empty + st, ph ^ 1);
+                    if (leader) {
                         mbar_expect_tx(w_full + st, p.wstage_bytes);
-                        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) + (((size_t)wsel * p.c16 + c) * p.kw + dx) * p.wstage_bytes;
-                        bulk_copy_g2s(smem_u32(s_w + (size_t)st * p.wstage_bytes), src, p.wstage_bytes, w_full + st);
+                        bulk_copy_g2s(smem_u32(s_w) + st * p.wstage_bytes, src, p.wstage_bytes, w_full + st);
                     }
+                    if (++st == (uint32_t)p.w_stages) { st = 0; ph ^= 1; }
                 }
             }
         }
@@ -394,13 +397,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                             f = fmaxf(f, 0.2f * f);
                             v[j] = __float_as_uint(fmaf(f, mul, add));
                         }
+                    } else if (act == PCNN_ACT_TANH && p.nsplit >= 2) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(tanh_fast(fmaf(__uint_as_float(v[j]), asc, bias)), mul, add));
                     } else if (act == PCNN_ACT_TANH) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float a = fmaf(__uint_as_float(v[j]), asc, bias);
-                            const float f = (p.nsplit >= 2) ? tanh_fast(a) : tanh_approx(a);
-                            v[j] = __float_as_uint(fmaf(f, mul, add));
-                        }
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(tanh_approx(fmaf(__uint_as_float(v[j]), asc, bias)), mul, add));
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(fmaf(__uint_as_float(v[j]), asc, bias), mul, add));
