@@ -31,6 +31,7 @@
 //   alloc), 3..10 = epilogue (TMEM lane quarter = warp % 4, two warps per quarter split the columns).
 //   Two 256-column accumulators in TMEM let the epilogue of tile t overlap the MMAs of tile t+1.
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include <cuda_fp8.h>
 
 #include "pcnn_common.cuh"
@@ -75,6 +76,7 @@ struct Params {
     int tiles_x, tiles_y, num_tiles;
     int row_slots;           // ring of input-row slots (>= kh+3)
     int w_stages;
+    int debug;               // PCNN_TC_DEBUG bit 0: epilogue skips math and stores (timing experiments only)
     int w_resident;          // 1: all nv*kw weight stages fit in shared memory -> loaded once per CTA, reused by every tile
     uint32_t rowplane_bytes; // bytes of one plane of one row window in smem (multiple of 128)
     uint32_t row_copy_bytes; // (n_tile + kw - 1) * 16
@@ -203,7 +205,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int R = p.kh + ZPAD;   // input rows per tile
+    const int R = p.kh + ZPAD;   // input rows per tile (even: odd kernel + 3)
+    const int GR = R / 2;        // rows per barrier group; row_slots is a multiple of GR so a group never wraps
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.row_slots; ++i) { mbar_init(row_full + i, 1); mbar_init(row_empty + i, 1); }
@@ -237,16 +240,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                 const int c = (p.nsplit == 2) ? v / 3 : (p.nsplit == 3 ? v >> 1 : v);
                 const __half* inp = ((p.nsplit == 2 && (v % 3) == 2) || (p.nsplit == 3 && (v & 1))) ? p.in_lo : p.in;
                 const __half* base = inp + ((size_t)b * p.c8_in + 2 * c) * plane_elems + (size_t)col0 * 8;
-                for (int rho = 0; rho < R; ++rho) {
+                // rows travel in two groups per chunk (R is even); one mbarrier pair per group, at the group's first slot
+                for (int grp = 0, rho = 0; grp < 2; ++grp) {
                     mbar_wait(row_empty + slot, ph ^ 1);
                     if (leader) {
-                        mbar_expect_tx(row_full + slot, 2 * p.row_copy_bytes);
-                        const __half* src = base + (size_t)min(prow0 + rho, p.Hp - 1) * p.P * 8;
-                        const uint32_t dst = smem_u32(s_rows) + slot * row_slot_bytes;
-                        bulk_copy_g2s(dst, src, p.row_copy_bytes, row_full + slot);
-                        bulk_copy_g2s(dst + p.rowplane_bytes, src + plane_elems, p.row_copy_bytes, row_full + slot);
+                        mbar_expect_tx(row_full + slot, (uint32_t)GR * 2u * p.row_copy_bytes);
+                        for (int i = 0; i < GR; ++i, ++rho) {
+                            const __half* src = base + (size_t)min(prow0 + rho, p.Hp - 1) * p.P * 8;
+                            const uint32_t dst = smem_u32(s_rows) + (slot + i) * row_slot_bytes;
+                            bulk_copy_g2s(dst, src, p.row_copy_bytes, row_full + slot);
+                            bulk_copy_g2s(dst + p.rowplane_bytes, src + plane_elems, p.row_copy_bytes, row_full + slot);
+                        }
+                    } else {
+                        rho += GR;
                     }
-                    if (++slot == (uint32_t)p.row_slots) { slot = 0; ph ^= 1; }
+                    slot += GR;
+                    if (slot == (uint32_t)p.row_slots) { slot = 0; ph ^= 1; }
                 }
             }
         }
@@ -293,57 +302,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                 const uint32_t d_tmem = tmem_base + acc * 256;
                 uint32_t accum = 0;
                 for (int c = 0; c < p.nv; ++c) {
-                    // rows of this chunk occupy ring slots [slot0, slot0+R) mod nslots: split at the wrap
-                    // point so the inner loops carry no wrap test
-                    const int n1 = min((int)(nslots - slot0), R);
                     const bool f8 = (p.nsplit == 3) && (c & 1);    // correction pass: e4m3 operands, K = 32
+                    // the chunk's rows sit in two groups of GR slots: [slot0, +GR) and the next group (which may wrap to 0)
+                    const uint32_t slotA = slot0, phA = slot0_ph;
+                    uint32_t slotB = slot0 + GR, phB = slot0_ph;
+                    if (slotB == nslots) { slotB = 0; phB ^= 1; }
                     for (int dx = 0; dx < p.kw; ++dx) {
                         mbar_wait(w_full + wst, p.w_resident ? 0u : wph);   // resident stages complete once and stay
                         tc_fence_after();
                         uint32_t a_lo = ((w_base16 + wst * wstage16) & 0x3FFF) | a_lo_lbo;
                         const bool first_dx = (dx == 0), last_dx = (dx == p.kw - 1);
 #pragma unroll 1
-                        for (int seg = 0; seg < 2; ++seg) {
-                            const int nrow = seg ? R - n1 : n1;
-                            uint32_t slot = seg ? 0u : slot0;
-                            const uint32_t ph = seg ? (slot0_ph ^ 1u) : slot0_ph;
-                            uint32_t b_lo = ((rows_base16 + slot * slot16 + dx) & 0x3FFF) | b_lo_lbo;
-                            if (first_dx) {
-                                for (int i = 0; i < nrow; ++i) {
-                                    mbar_wait(row_full + slot, ph);
-                                    tc_fence_after();
-                                    if (leader) {
-                                        if (f8) tc_mma_f8(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, accum);
-                                        else tc_mma_f16(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, accum);
-                                        if (last_dx) tc_commit(row_empty + slot);   // 1x1 kernels: first tap is also the last
+                        for (int grp = 0; grp < 2; ++grp) {
+                            const uint32_t slot = grp ? slotB : slotA;
+                            if (first_dx) { mbar_wait(row_full + slot, grp ? phB : phA); tc_fence_after(); }
+                            if (leader) {
+                                uint32_t b_lo = ((rows_base16 + slot * slot16 + dx) & 0x3FFF) | b_lo_lbo;
+                                if (!f8) {
+#pragma unroll 3
+                                    for (int i = 0; i < GR; ++i) {
+                                        tc_mma_f16(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, accum | (uint32_t)(i | grp | dx));
+                                        a_lo += 32; b_lo += slot16;
                                     }
-                                    accum = 1; a_lo += 32; b_lo += slot16; ++slot;
-                                }
-                            } else if (last_dx) {
-                                for (int i = 0; i < nrow; ++i) {
-                                    if (leader) {
-                                        if (f8) tc_mma_f8(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, 1u);
-                                        else tc_mma_f16(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, 1u);
-                                        tc_commit(row_empty + slot);   // row no longer needed
+                                } else {
+#pragma unroll 3
+                                    for (int i = 0; i < GR; ++i) {
+                                        tc_mma_f8(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, 1u);
+                                        a_lo += 32; b_lo += slot16;
                                     }
-                                    a_lo += 32; b_lo += slot16; ++slot;
                                 }
-                            } else if (leader && !f8) {
-#pragma unroll 4
-                                for (int i = 0; i < nrow; ++i) {
-                                    tc_mma_f16(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, 1u);
-                                    a_lo += 32; b_lo += slot16;
-                                }
-                            } else if (leader) {
-#pragma unroll 4
-                                for (int i = 0; i < nrow; ++i) {
-                                    tc_mma_f8(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, 1u);
-                                    a_lo += 32; b_lo += slot16;
-                                }
+                                if (last_dx) tc_commit(row_empty + slot);   // the whole group is free again
                             } else {
-                                a_lo += 32u * nrow;
+                                a_lo += 32u * GR;
                             }
                         }
+                        accum = 1;
                         if (leader && !p.w_resident) tc_commit(w_empty + wst);
                         if (++wst == nwst) { wst = 0; wph ^= 1; }
                     }
@@ -386,7 +379,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
             for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr0 + c0, v);
-                if (y < p.H) {
+                if (y < p.H && !(p.debug & 1)) {
                     __half* srow = reinterpret_cast<__half*>(stage + (co >> 3) * STAGE_PLANE) + (co & 7);
                     // bias -> activation -> (BN affine * scale).  Padded channels (co >= cout) come out
                     // as exact zeros: zero weights, bias 0, shift 0.
@@ -836,7 +829,9 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
         }
         PCNN_CHECK_ARG(slots >= R && w_stages >= 2, "conv2d_tc: shared-memory plan failed (k=%d, n_tile=%d)", k, p.n_tile);
     }
+    slots = (slots / (R / 2)) * (R / 2);          // barrier groups of R/2 rows must not straddle the ring wrap
     p.row_slots = slots; p.w_stages = w_stages; p.w_resident = resident;
+    { static const int dbg = getenv("PCNN_TC_DEBUG") ? atoi(getenv("PCNN_TC_DEBUG")) : 0; p.debug = dbg; }
     const size_t smem = (size_t)slots * rowslot + (size_t)w_stages * wst + fixed;
     PCNN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax));
     if (num_sms <= 0) num_sms = 148;
