@@ -27,17 +27,24 @@ class Prof:
         def wrapped(*a):
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record(); r = fn(*a); e1.record()
-            records.append((name, e0, e1, a[11:21] if name == "pcnn_conv2d_tc" else None))
+            extra = None
+            if name == "pcnn_conv2d_tc": extra = a[11:21]
+            elif name == "pcnn_conv2d_f32": extra = ("f32",) + tuple(a[8:15])
+            elif name == "pcnn_deconv_same_f32": extra = ("deconv",) + tuple(a[4:14])
+            elif name == "pcnn_avgpool_same_f32": extra = ("pool",) + tuple(a[2:7])
+            records.append((name, e0, e1, extra))
             return r
         return wrapped
 ops.lib = Prof(_lib.lib)
 t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
 t0.record(); model(inp); t1.record(); torch.cuda.synchronize()
 agg = collections.defaultdict(lambda: [0, 0.0])
-tc = collections.OrderedDict()
+tc = collections.OrderedDict(); other = collections.OrderedDict()
 for name, a, b, args in records:
     agg[name][0] += 1; agg[name][1] += a.elapsed_time(b)
-    if args is not None:
+    if args is not None and isinstance(args[0], str):
+        other.setdefault(args, [0, 0.0]); other[args][0] += 1; other[args][1] += a.elapsed_time(b)
+    elif args is not None:
         Bn, cin, cout, _, _, H, W, k, act, ns = args
         key = (Bn, cin, cout, H, W, k)
         tc.setdefault(key, [0, 0.0, ns])
@@ -55,3 +62,7 @@ for (Bn, cin, cout, H, W, k), (n, t, ns) in sorted(tc.items(), key=lambda kv: -k
     mmas = tiles * nv * k * (k + 3)
     floor_ms = -(-tiles // 148) * nv * k * (k + 3) * 128 * (ntile / 256.0) / 1.9e6
     print("  %-32s n=%2d %8.2f ms  floor %.2f ms  -> %.0f%%" % ((Bn, cin, cout, H, W, k), n, t, floor_ms * n, 100 * floor_ms * n / t))
+
+print("other launches by shape:")
+for k, (n, t) in sorted(other.items(), key=lambda kv: -kv[1][1])[:24]:
+    print("  %-60s n=%2d %7.3f ms" % (k, n, t))
