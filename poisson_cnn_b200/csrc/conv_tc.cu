@@ -40,21 +40,23 @@ namespace pcnn {
 namespace tc {
 
 constexpr int HALO = 7;            // materialised halo of the BLK8 layout (kernel sizes up to 15)
-constexpr int ROWS_PER_TILE = 4;   // output rows per tile (M = 4 x 32)
-constexpr int COUT_PAD = 32;
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int STAGE_PX = 16;          // pixels per pass through an epilogue warp's transpose buffer
-constexpr int NUM_THREADS = (3 + NUM_EPI_WARPS) * 32;
-constexpr int ZPAD = ROWS_PER_TILE - 1;   // zero z-rows on each side of the packed weights
+// The M = 128 accumulator rows are RT output rows x CP channel slots, CP = 32, 16 or 8 (smallest >= Cout):
+// narrow layers trade channel padding for more output rows per tile, i.e. fewer MMAs per output row
+// ((kh+RT-1)*kw per RT rows) and an epilogue whose lanes all carry live channels.
+constexpr int M_TILE = 128;
+constexpr int MAX_EPI_WARPS = 8;
+constexpr int CHUNK_PX = 16;                   // accumulator columns per epilogue pass
+constexpr int STAGE_WARP = CHUNK_PX * 128;     // per-warp transpose buffer: 16 pixels x 32 words
+constexpr int NUM_THREADS = (3 + MAX_EPI_WARPS) * 32;
 constexpr float LO_SCALE = 2048.f;        // 2^11: brings the fp16 rounding remainder into e4m3's range (mode 3)
 constexpr unsigned long long SPIN_LIMIT_NS = 4000000000ull;   // a stuck pipeline traps instead of hanging the GPU
 
 struct Params {
     const __half* in;        // BLK8 [B][c8_in][Hp][P][8]  (hi part)
     const __half* in_lo;     // lo part (split precision) or null
-    const __half* wpack;     // [nsplit][C16][kw][2][(kh+6)*32][8]  (hi image, then lo image)
-    const float* bias;       // [32] (zero padded) or null
-    const float* bn_scale;   // [32] or null
+    const __half* wpack;     // [nsplit][C16][kw][2][(kh+2(RT-1))*CP][8]  (hi image, then lo image)
+    const float* bias;       // [Cout] or null
+    const float* bn_scale;   // [Cout] or null
     const float* bn_shift;
     const __half* residual;  // BLK8 like out, or null
     const __half* residual_lo;
@@ -74,13 +76,14 @@ struct Params {
     int act;
     int n_tile;              // MMA N (multiple of 16, <= 256)
     int tiles_x, tiles_y, num_tiles;
-    int row_slots;           // ring of input-row slots (>= kh+3)
+    int row_slots;           // ring of input-row slots (>= kh+RT-1)
     int w_stages;
+    int n_epi;               // active epilogue warps: 8, or 4 when shared memory is needed for operands (large k)
     int debug;               // PCNN_TC_DEBUG bit 0: epilogue skips math and stores (timing experiments only)
     int w_resident;          // 1: all nv*kw weight stages fit in shared memory -> loaded once per CTA, reused by every tile
     uint32_t rowplane_bytes; // bytes of one plane of one row window in smem (multiple of 128)
     uint32_t row_copy_bytes; // (n_tile + kw - 1) * 16
-    uint32_t wstage_bytes;   // 2 * (kh+6) * 512
+    uint32_t wstage_bytes;   // 2 * (kh+2(RT-1)) * CP * 16
     uint32_t idesc;
 };
 
@@ -172,30 +175,39 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes,
     return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+// 16 consecutive accumulator columns of this thread's TMEM lane; completes at tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float2 e4m3x2_to_float2(uint32_t two_bytes) {
+    const __half2_raw h = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)two_bytes, __NV_E4M3);
+    return __half22float2(__half2(h));
+}
+__device__ __forceinline__ uint32_t float2_to_e4m3x2(float lo, float hi) {   // byte 0 = e4m3(lo), byte 1 = e4m3(hi)
+    return (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(lo, hi), __NV_SATFINITE, __NV_E4M3);
+}
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ float2 bits_to_float2(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
 
 // ---------------------------------------------------------------- the kernel
+// CP = channel slots per output row of the M operand (32, 16 or 8); RT = 128 / CP output rows per tile.
+template <int CP>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p) {
+    constexpr int RT = M_TILE / CP;      // output rows per tile
+    constexpr int ZPAD = RT - 1;         // zero z-rows on each side of the packed weights
     extern __shared__ __align__(1024) uint8_t smem[];
-    // carve-up: [row slots][weight stages][epilogue staging 4 x 2176 B][barriers][tmem ptr]
+    // carve-up: [row slots][weight stages][epilogue transpose buffers n_epi x 2 KB][barriers][tmem ptr]
     uint8_t* s_rows = smem;
     const uint32_t row_slot_bytes = 2 * p.rowplane_bytes;
     uint8_t* s_w = s_rows + (size_t)p.row_slots * row_slot_bytes;
     uint8_t* s_stage = s_w + (size_t)p.w_stages * p.wstage_bytes;
-    constexpr int STAGE_PLANE = STAGE_PX * 16 + 16;   // 16 px x 16 B, +16 B so the 4 planes hit different banks
-    constexpr int STAGE_WARP = 4 * STAGE_PLANE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + NUM_EPI_WARPS * STAGE_WARP);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + p.n_epi * STAGE_WARP);
     uint64_t* row_full = bars;
     uint64_t* row_empty = row_full + p.row_slots;
     uint64_t* w_full = row_empty + p.row_slots;
@@ -205,13 +217,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int R = p.kh + ZPAD;   // input rows per tile (even: odd kernel + 3)
+    const int R = p.kh + ZPAD;   // input rows per tile (even: odd kernel + odd ZPAD)
     const int GR = R / 2;        // rows per barrier group; row_slots is a multiple of GR so a group never wraps
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.row_slots; ++i) { mbar_init(row_full + i, 1); mbar_init(row_empty + i, 1); }
         for (int i = 0; i < p.w_stages; ++i) { mbar_init(w_full + i, 1); mbar_init(w_empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, NUM_EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, p.n_epi); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {   // TMEM: 512 columns = two 256-column fp32 accumulators
@@ -233,7 +245,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
             const int tx = t % p.tiles_x;
             const int ty = (t / p.tiles_x) % p.tiles_y;
             const int b = t / (p.tiles_x * p.tiles_y);
-            const int x0 = tx * p.n_tile, y0 = ty * ROWS_PER_TILE;
+            const int x0 = tx * p.n_tile, y0 = ty * RT;
             const int col0 = x0 + HALO - p.pad, prow0 = y0 + HALO - p.pad;
             for (int v = 0; v < p.nv; ++v) {
                 // split precision: per chunk c the passes are (x_hi,W_hi), (x_hi,W_lo), (x_lo,W_hi); mode 3: (x_hi,W_hi), (q,Wq)
@@ -285,7 +297,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
         // registers); one elected lane issues tcgen05.mma / tcgen05.commit.  Everything per MMA is
         // incremental: descriptor low words advance by constants, ring slots wrap by compare.
         {
-            const uint32_t a_lbo = (uint32_t)(p.kh + 2 * ZPAD) * 512u;   // K-half (plane) stride of the packed weights
+            const uint32_t a_lbo = (uint32_t)(p.kh + 2 * ZPAD) * (CP * 16u);   // K-half (plane) stride of the packed weights
             const uint32_t a_hi = (uint32_t)(make_desc(0, a_lbo, 128u) >> 32);
             const uint32_t b_hi = (uint32_t)(make_desc(0, p.rowplane_bytes, 128u) >> 32);
             const uint32_t a_lo_lbo = ((a_lbo >> 4) & 0x3FFF) << 16, b_lo_lbo = ((p.rowplane_bytes >> 4) & 0x3FFF) << 16;
@@ -322,18 +334,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
 #pragma unroll 3
                                     for (int i = 0; i < GR; ++i) {
                                         tc_mma_f16(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, accum | (uint32_t)(i | grp | dx));
-                                        a_lo += 32; b_lo += slot16;
+                                        a_lo += CP; b_lo += slot16;
                                     }
                                 } else {
 #pragma unroll 3
                                     for (int i = 0; i < GR; ++i) {
                                         tc_mma_f8(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, 1u);
-                                        a_lo += 32; b_lo += slot16;
+                                        a_lo += CP; b_lo += slot16;
                                     }
                                 }
                                 if (last_dx) tc_commit(row_empty + slot);   // the whole group is free again
                             } else {
-                                a_lo += 32u * GR;
+                                a_lo += (uint32_t)CP * GR;
                             }
                         }
                         accum = 1;
@@ -347,158 +359,222 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                 __syncwarp();
             }
         }
-    } else {
-        // ================= epilogue (warps 3..10) =================
-        const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int half = (warp - 3) >> 2;       // which half of the tile's columns
-        const int r = (ROWS_PER_TILE - 1) - q;  // output row within the tile (M rows are (3-r)*32 + co)
-        const int co = lane;
-        uint8_t* stage = s_stage + (warp - 3) * STAGE_WARP;
+    } else if (warp - 3 < p.n_epi) {
+        // ================= epilogue (warps 3..3+n_epi) =================
+        // Two thread roles per warp, joined by a 16 px x 32 word transpose buffer (XOR-swizzled 16-byte chunks,
+        // conflict-free both ways):
+        //   "lane side"  : thread = TMEM lane m = 32q + lane = (row slot, channel), 16 consecutive pixels
+        //                  (what tcgen05.ld delivers); does bias / activation / BN / residual add / rounding.
+        //   "pixel side" : thread = (pixel px, octet pair oc): 2 x 8 consecutive M rows of one pixel = the
+        //                  16-byte units of the BLK8 layout; does all global loads (residual) and stores,
+        //                  each warp instruction covering 16 consecutive pixels x 16 B = 256 contiguous bytes.
+        // One 32-bit word per (pixel, M row) carries every output form: [fp16 hi | e4m3(x) | e4m3(lo*2^11)]
+        // (mode 3), [hi | lo] (mode 2) or [hi] (mode 1).
+        const int ew = warp - 3;
+        const int q = warp & 3;                     // TMEM lane quarter this warp may access
+        const int part = ew >> 2, nparts = p.n_epi >> 2;
+        const int m = 32 * q + lane;
+        const int co = m & (CP - 1);
+        uint32_t* stage = reinterpret_cast<uint32_t*>(s_stage + ew * STAGE_WARP);
         const bool live = co < p.cout;
         const float bias = (p.bias && live) ? p.bias[co] : 0.f;
         const float bns = (p.bn_scale && live) ? p.bn_scale[co] : 1.f;
         const float bnt = (p.bn_shift && live) ? p.bn_shift[co] : 0.f;
         const int planes_out = (p.cout + 7) / 8;
-        const int ncols_half = ((p.n_tile / 2 + 31) / 32) * 32;   // columns handled by half 0 (multiple of 32)
-        const int c_begin = half * ncols_half, c_end = half ? p.n_tile : min(ncols_half, p.n_tile);
-        const int act = p.act;
+        const int nchunks = p.n_tile / CHUNK_PX;
+        const int per_part = (nchunks + nparts - 1) / nparts;
+        const int ch_begin = part * per_part, ch_end = min(nchunks, ch_begin + per_part);
+        const int act = p.act, mode = p.nsplit;
         const float asc = p.acc_scale;
+        const bool has_res = p.residual != nullptr;
+        // pixel-side identity
+        const int px = lane & 15, oc = lane >> 4;
+        int o_r[2], o_pl[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int m0 = 8 * (4 * q + 2 * oc + e);
+            o_r[e] = (RT - 1) - m0 / CP;
+            o_pl[e] = (m0 & (CP - 1)) >> 3;
+        }
+        // swizzled word offsets: word (pixel j, M row lane) and the pixel side's four 16-byte chunks
+        const uint32_t lane_word = (uint32_t)(lane & 3);
+        const uint32_t lane_chunk = (uint32_t)(lane >> 2);
+        uint32_t* const px_row = stage + px * 32;
+        const uint32_t px_sw = (uint32_t)(px & 7);
+        const size_t plane_px = (size_t)p.Hp * p.P;
         uint32_t it = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
             const int tx = t % p.tiles_x;
             const int ty = (t / p.tiles_x) % p.tiles_y;
             const int b = t / (p.tiles_x * p.tiles_y);
-            const int x0 = tx * p.n_tile, y = ty * ROWS_PER_TILE + r;
+            const int x0 = tx * p.n_tile;
             const uint32_t acc = it & 1, acc_ph = (it >> 1) & 1;
             // fold the per-(sample,channel) scale into the BN affine: (a*s + t) * o = a*(s*o) + t*o
             const float osc = (p.out_scale && live) ? p.out_scale[(size_t)b * p.cout + co] : 1.f;
             const float mul = bns * osc, add = bnt * osc;
+            // pixel side: per octet, pixel index of (row y, x = x0 + px) within a plane, and validity
+            size_t o_pix[2];
+            bool o_ok[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int y = ty * RT + o_r[e];
+                o_ok[e] = (y < p.H) && (o_pl[e] < planes_out);
+                o_pix[e] = (size_t)(y + HALO) * p.P + (x0 + px + HALO);
+            }
+            uint4 rh[2], rl[2];
+            auto load_residual = [&](int ch) {
+                const int xo = ch * CHUNK_PX;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    rh[e] = make_uint4(0, 0, 0, 0); rl[e] = make_uint4(0, 0, 0, 0);
+                    if (o_ok[e] && x0 + xo + px < p.W) {
+                        const size_t pix = o_pix[e] + xo;
+                        rh[e] = *reinterpret_cast<const uint4*>(p.residual + (((size_t)b * p.c8_res + o_pl[e]) * plane_px + pix) * 8);
+                        if (mode == 2) rl[e] = *reinterpret_cast<const uint4*>(p.residual_lo + (((size_t)b * p.c8_res + o_pl[e]) * plane_px + pix) * 8);
+                        if (mode == 3) {
+                            const uint2 t2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(p.residual_lo) +
+                                (((size_t)b * p.c8_res + (o_pl[e] | 1)) * plane_px + pix) * 16 + 8 * (o_pl[e] & 1));
+                            rl[e].x = t2.x; rl[e].y = t2.y;
+                        }
+                    }
+                }
+            };
+            if (has_res && ch_begin < ch_end) load_residual(ch_begin);   // does not depend on the accumulator
             mbar_wait(acc_full + acc, acc_ph);
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
-            for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld32(taddr0 + c0, v);
-                if (y < p.H && !(p.debug & 1)) {
-                    __half* srow = reinterpret_cast<__half*>(stage + (co >> 3) * STAGE_PLANE) + (co & 7);
-                    // bias -> activation -> (BN affine * scale).  Padded channels (co >= cout) come out
-                    // as exact zeros: zero weights, bias 0, shift 0.
+            for (int ch = ch_begin; ch < ch_end; ++ch) {
+                uint32_t v[16];
+                tmem_ld16_issue(taddr0 + ch * CHUNK_PX, v);
+                float r[16];
+                if (has_res) {
+                    // pixel side: residual -> fp32 -> transpose buffer
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const uint32_t hw[4] = {rh[e].x, rh[e].y, rh[e].z, rh[e].w};
+                        const uint32_t lw[4] = {rl[e].x, rl[e].y, rl[e].z, rl[e].w};
+                        float f[8];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 a = bits_to_float2(hw[i]);
+                            f[2 * i] = a.x; f[2 * i + 1] = a.y;
+                            if (mode == 2) {
+                                const float2 l2 = bits_to_float2(lw[i]);
+                                f[2 * i] += l2.x; f[2 * i + 1] += l2.y;
+                            } else if (mode == 3) {
+                                const float2 l2 = e4m3x2_to_float2((lw[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
+                                f[2 * i] = fmaf(l2.x, 1.0f / LO_SCALE, f[2 * i]);
+                                f[2 * i + 1] = fmaf(l2.y, 1.0f / LO_SCALE, f[2 * i + 1]);
+                            }
+                        }
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const uint32_t c = (uint32_t)(2 * (2 * oc + e) + h) ^ px_sw;
+                            *reinterpret_cast<float4*>(px_row + 4 * c) = make_float4(f[4 * h], f[4 * h + 1], f[4 * h + 2], f[4 * h + 3]);
+                        }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < CHUNK_PX; ++j)
+                        r[j] = __uint_as_float(stage[j * 32 + 4 * (lane_chunk ^ (uint32_t)(j & 7)) + lane_word]);
+                    __syncwarp();
+                    if (ch + 1 < ch_end) load_residual(ch + 1);    // in flight during this chunk's math and stores
+                }
+                tmem_ld_wait();
+                if (!(p.debug & 1)) {
+                    // ---- lane side: bias -> activation -> (BN affine * scale) -> + residual.  Padded channels
+                    //      (co >= cout) come out as exact zeros: zero weights, bias 0, shift 0.
+                    float f[16];
                     if (act == PCNN_ACT_LEAKY_RELU) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float f = fmaf(__uint_as_float(v[j]), asc, bias);
-                            f = fmaxf(f, 0.2f * f);
-                            v[j] = __float_as_uint(fmaf(f, mul, add));
+                        for (int j = 0; j < 16; ++j) {
+                            float a = fmaf(__uint_as_float(v[j]), asc, bias);
+                            a = fmaxf(a, 0.2f * a);
+                            f[j] = fmaf(a, mul, add);
                         }
-                    } else if (act == PCNN_ACT_TANH && p.nsplit >= 2) {
+                    } else if (act == PCNN_ACT_TANH && mode >= 2) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(tanh_fast(fmaf(__uint_as_float(v[j]), asc, bias)), mul, add));
+                        for (int j = 0; j < 16; ++j) f[j] = fmaf(tanh_fast(fmaf(__uint_as_float(v[j]), asc, bias)), mul, add);
                     } else if (act == PCNN_ACT_TANH) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(tanh_approx(fmaf(__uint_as_float(v[j]), asc, bias)), mul, add));
+                        for (int j = 0; j < 16; ++j) f[j] = fmaf(tanh_approx(fmaf(__uint_as_float(v[j]), asc, bias)), mul, add);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(fmaf(__uint_as_float(v[j]), asc, bias), mul, add));
+                        for (int j = 0; j < 16; ++j) f[j] = fmaf(fmaf(__uint_as_float(v[j]), asc, bias), mul, add);
                     }
-                    // ---- residual add (fp32) and stores, 16 pixels per pass through the transpose buffer:
-                    //      thread = (channel, 16 pixels) on the way in; lane = (pixel, plane parity) on the way out
-                    constexpr int QGRP = STAGE_PX * 16 + 16;   // stride of a 16-channel fp8 group in the transpose buffer
-                    const int qgroups = (p.cout + 15) / 16;
-                    uint8_t* qrow = stage + (co >> 4) * QGRP + (co & 15);
-                    const int px = lane & 15, psel = lane >> 4;
+                    if (has_res) {
 #pragma unroll
-                    for (int h2 = 0; h2 < 2; ++h2) {
-                        const int x = x0 + c0 + STAGE_PX * h2 + px;
-                        const bool xok = (x < p.W) && (c0 + STAGE_PX * h2 + px < p.n_tile);
-                        const size_t pix = (size_t)(y + HALO) * p.P + (x + HALO);
-                        if (p.residual) {
-                            const int nparts = (p.nsplit == 2) ? 2 : 1;
-                            for (int part = 0; part < nparts; ++part) {
-                                const __half* rsrc = part ? p.residual_lo : p.residual;
-                                for (int pl2 = 0; pl2 < planes_out; pl2 += 2) {
-                                    const int pl = pl2 + psel;
-                                    if (pl < planes_out) {
-                                        uint4 rv = make_uint4(0, 0, 0, 0);
-                                        if (xok) rv = *reinterpret_cast<const uint4*>(rsrc + (((size_t)b * p.c8_res + pl) * p.Hp * p.P + pix) * 8);
-                                        *reinterpret_cast<uint4*>(stage + pl * STAGE_PLANE + px * 16) = rv;
-                                    }
-                                }
-                                __syncwarp();
-                                if (live) {
+                        for (int j = 0; j < 16; ++j) f[j] += r[j];
+                    }
+                    // ---- rounding: one word per pixel with every output form, into the transpose buffer
 #pragma unroll
-                                    for (int jj = 0; jj < STAGE_PX; ++jj)
-                                        v[STAGE_PX * h2 + jj] = __float_as_uint(__uint_as_float(v[STAGE_PX * h2 + jj]) + __half2float(srow[jj * 8]));
-                                }
-                                __syncwarp();
-                            }
-                            if (p.nsplit == 3) {   // remainder of the residual: e4m3 plane 2g+1, scaled by 2^11
-                                const uint8_t* rq = reinterpret_cast<const uint8_t*>(p.residual_lo);
-                                for (int g2 = 0; g2 < qgroups; g2 += 2) {
-                                    const int g = g2 + psel;
-                                    if (g < qgroups) {
-                                        uint4 rv = make_uint4(0, 0, 0, 0);
-                                        if (xok) rv = *reinterpret_cast<const uint4*>(rq + (((size_t)b * p.c8_res + 2 * g + 1) * p.Hp * p.P + pix) * 16);
-                                        *reinterpret_cast<uint4*>(stage + g * QGRP + px * 16) = rv;
-                                    }
-                                }
-                                __syncwarp();
-                                if (live) {
-#pragma unroll
-                                    for (int jj = 0; jj < STAGE_PX; ++jj)
-                                        v[STAGE_PX * h2 + jj] = __float_as_uint(fmaf(from_e4m3(qrow[jj * 16]), 1.0f / LO_SCALE, __uint_as_float(v[STAGE_PX * h2 + jj])));
-                                }
-                                __syncwarp();
+                    for (int j = 0; j < 16; j += 2) {
+                        const __half2 hh = __floats2half2_rn(f[j], f[j + 1]);
+                        const uint32_t hb = h2_bits(hh);
+                        uint32_t w0, w1;
+                        if (mode == 1) {
+                            w0 = hb & 0xFFFFu; w1 = hb >> 16;
+                        } else {
+                            const float2 back = __half22float2(hh);
+                            const float l0 = f[j] - back.x, l1 = f[j + 1] - back.y;
+                            if (mode == 2) {
+                                const uint32_t lb = h2_bits(__floats2half2_rn(l0, l1));
+                                w0 = __byte_perm(hb, lb, 0x5410); w1 = __byte_perm(hb, lb, 0x7632);
+                            } else {
+                                const uint32_t qq = float2_to_e4m3x2(f[j], f[j + 1]) | (float2_to_e4m3x2(l0 * LO_SCALE, l1 * LO_SCALE) << 16);
+                                w0 = __byte_perm(hb, qq, 0x6410); w1 = __byte_perm(hb, qq, 0x7532);
                             }
                         }
-                        if (p.nsplit == 3) {
-                            // e4m3(x) for the next layer's correction MMA (plane 2g of the q buffer)
-                            uint8_t* dq = reinterpret_cast<uint8_t*>(p.out_lo);
+                        stage[j * 32 + 4 * (lane_chunk ^ (uint32_t)(j & 7)) + lane_word] = w0;
+                        stage[(j + 1) * 32 + 4 * (lane_chunk ^ (uint32_t)((j + 1) & 7)) + lane_word] = w1;
+                    }
+                    __syncwarp();
+                    // ---- pixel side: gather this pixel's two octets and store 16-byte units
+                    const int xo = ch * CHUNK_PX;
+                    const bool xok = x0 + xo + px < p.W;
+                    uint2 q8[2], l8[2];
 #pragma unroll
-                            for (int jj = 0; jj < STAGE_PX; ++jj) qrow[jj * 16] = to_e4m3(__uint_as_float(v[STAGE_PX * h2 + jj]));
-                            __syncwarp();
-                            for (int g2 = 0; g2 < qgroups; g2 += 2) {
-                                const int g = g2 + psel;
-                                if (g < qgroups && xok)
-                                    *reinterpret_cast<uint4*>(dq + (((size_t)b * p.c8_out + 2 * g) * p.Hp * p.P + pix) * 16) =
-                                        *reinterpret_cast<const uint4*>(stage + g * QGRP + px * 16);
-                            }
-                            __syncwarp();
-                        }
-                        const int nparts_out = (p.nsplit == 2) ? 2 : 1;
-                        for (int part = 0; part < nparts_out; ++part) {
-                            // fp16 (hi), then the rounding remainder (lo)
-#pragma unroll
-                            for (int jj = 0; jj < STAGE_PX; ++jj) {
-                                const float f = __uint_as_float(v[STAGE_PX * h2 + jj]);
-                                const __half hh = __float2half_rn(f);
-                                srow[jj * 8] = hh;
-                                v[STAGE_PX * h2 + jj] = __float_as_uint(f - __half2float(hh));
-                            }
-                            __syncwarp();
-                            __half* dst = part ? p.out_lo : p.out;
-                            for (int pl2 = 0; pl2 < planes_out; pl2 += 2) {
-                                const int pl = pl2 + psel;
-                                if (pl < planes_out && xok)
-                                    *reinterpret_cast<uint4*>(dst + (((size_t)b * p.c8_out + pl) * p.Hp * p.P + pix) * 8) =
-                                        *reinterpret_cast<const uint4*>(stage + pl * STAGE_PLANE + px * 16);
-                            }
-                            __syncwarp();
-                        }
-                        if (p.nsplit == 3) {
-                            // e4m3((x - hi) * 2^11): plane 2g+1 of the q buffer
-                            uint8_t* dq = reinterpret_cast<uint8_t*>(p.out_lo);
-#pragma unroll
-                            for (int jj = 0; jj < STAGE_PX; ++jj) qrow[jj * 16] = to_e4m3(__uint_as_float(v[STAGE_PX * h2 + jj]) * LO_SCALE);
-                            __syncwarp();
-                            for (int g2 = 0; g2 < qgroups; g2 += 2) {
-                                const int g = g2 + psel;
-                                if (g < qgroups && xok)
-                                    *reinterpret_cast<uint4*>(dq + (((size_t)b * p.c8_out + 2 * g + 1) * p.Hp * p.P + pix) * 16) =
-                                        *reinterpret_cast<const uint4*>(stage + g * QGRP + px * 16);
-                            }
-                            __syncwarp();
+                    for (int e = 0; e < 2; ++e) {
+                        const uint4 a = *reinterpret_cast<const uint4*>(px_row + 4 * ((uint32_t)(2 * (2 * oc + e)) ^ px_sw));
+                        const uint4 c = *reinterpret_cast<const uint4*>(px_row + 4 * ((uint32_t)(2 * (2 * oc + e) + 1) ^ px_sw));
+                        const uint4 hi = make_uint4(__byte_perm(a.x, a.y, 0x5410), __byte_perm(a.z, a.w, 0x5410),
+                                                    __byte_perm(c.x, c.y, 0x5410), __byte_perm(c.z, c.w, 0x5410));
+                        const bool ok = o_ok[e] && xok;
+                        const size_t pix = o_pix[e] + xo;
+                        if (ok) *reinterpret_cast<uint4*>(p.out + (((size_t)b * p.c8_out + o_pl[e]) * plane_px + pix) * 8) = hi;
+                        if (mode == 2) {
+                            const uint4 lo = make_uint4(__byte_perm(a.x, a.y, 0x7632), __byte_perm(a.z, a.w, 0x7632),
+                                                        __byte_perm(c.x, c.y, 0x7632), __byte_perm(c.z, c.w, 0x7632));
+                            if (ok) *reinterpret_cast<uint4*>(p.out_lo + (((size_t)b * p.c8_out + o_pl[e]) * plane_px + pix) * 8) = lo;
+                        } else if (mode == 3) {
+                            const uint32_t t01 = __byte_perm(a.x, a.y, 0x7362), t23 = __byte_perm(a.z, a.w, 0x7362);
+                            const uint32_t t45 = __byte_perm(c.x, c.y, 0x7362), t67 = __byte_perm(c.z, c.w, 0x7362);
+                            q8[e] = make_uint2(__byte_perm(t01, t23, 0x5410), __byte_perm(t45, t67, 0x5410));
+                            l8[e] = make_uint2(__byte_perm(t01, t23, 0x7632), __byte_perm(t45, t67, 0x7632));
                         }
                     }
+                    if (mode == 3) {
+                        uint8_t* dq = reinterpret_cast<uint8_t*>(p.out_lo);
+                        if (CP >= 16) {
+                            // both octets belong to one row and one 16-channel group: planes (2g, 2g+1) -> 16-byte stores
+                            if (o_ok[0] && xok) {
+                                const size_t base = (((size_t)b * p.c8_out + o_pl[0]) * plane_px + o_pix[0] + xo) * 16;
+                                *reinterpret_cast<uint4*>(dq + base) = make_uint4(q8[0].x, q8[0].y, q8[1].x, q8[1].y);
+                                *reinterpret_cast<uint4*>(dq + base + plane_px * 16) = make_uint4(l8[0].x, l8[0].y, l8[1].x, l8[1].y);
+                            }
+                        } else {
+                            // CP = 8: an octet is a whole row of 8 channels; bytes 8..15 of its pixel are channel padding
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                if (o_ok[e] && xok) {
+                                    const size_t base = (((size_t)b * p.c8_out) * plane_px + o_pix[e] + xo) * 16;
+                                    *reinterpret_cast<uint4*>(dq + base) = make_uint4(q8[e].x, q8[e].y, 0u, 0u);
+                                    *reinterpret_cast<uint4*>(dq + base + plane_px * 16) = make_uint4(l8[e].x, l8[e].y, 0u, 0u);
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
                 }
             }
             tc_fence_before();
@@ -516,20 +592,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
 }
 
 // ---------------------------------------------------------------- layout / packing kernels
-// Keras kernel [kh][kw][Cin][Cout] fp32 -> packed fp16 [C16][kw][2][(kh+6)*32][8]
+// Keras kernel [kh][kw][Cin][Cout] fp32 -> packed fp16 [C16][kw][2][(kh+2(RT-1))*CP][8], RT = 128/CP
 __global__ void pack_weights_kernel(const float* __restrict__ k, __half* __restrict__ out, int kh, int kw,
-                                    int Cin, int Cout, int c16, long long total, int nsplit, float scale) {
-    const int Z = kh + 2 * ZPAD;
+                                    int Cin, int Cout, int c16, long long total, int nsplit, float scale, int cp) {
+    const int zpad = M_TILE / cp - 1;
+    const int Z = kh + 2 * zpad;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int e = idx & 7;
         long long t = idx >> 3;
-        const int co = t % COUT_PAD; t /= COUT_PAD;
+        const int co = t % cp; t /= cp;
         const int z = t % Z; t /= Z;
         const int pl = t & 1; t >>= 1;
         const int dx = t % kw;
         const int c = t / kw;
-        const int ci = c * 16 + pl * 8 + e, dy = z - ZPAD;
+        const int ci = c * 16 + pl * 8 + e, dy = z - zpad;
         float v = 0.f;
         if (dy >= 0 && dy < kh && ci < Cin && co < Cout) v = scale * k[(((long long)dy * kw + dx) * Cin + ci) * Cout + co];
         const __half h = __float2half_rn(v);
@@ -539,11 +616,11 @@ __global__ void pack_weights_kernel(const float* __restrict__ k, __half* __restr
             // fp8 image [c][dx][plane][z][co][16]: plane 0 = e4m3(W_lo) pairs with e4m3(x),
             // plane 1 = e4m3(W * 2^-11) pairs with e4m3(x_lo * 2^11); ci16 = pl*8+e of the fp16 image
             uint8_t* q = reinterpret_cast<uint8_t*>(out + total);
-            const long long stage_elems = 2LL * Z * COUT_PAD * 8;             // fp16 elements per (c,dx) stage == bytes / 2
+            const long long stage_elems = 2LL * Z * cp * 8;                    // fp16 elements per (c,dx) stage == bytes / 2
             const long long base = ((long long)c * kw + dx) * stage_elems * 2; // byte offset of the (c,dx) stage
             const int ci16 = pl * 8 + e;
-            q[base + (((long long)0 * Z + z) * COUT_PAD + co) * 16 + ci16] = to_e4m3(v - __half2float(h));
-            q[base + (((long long)1 * Z + z) * COUT_PAD + co) * 16 + ci16] = to_e4m3(v * (1.0f / LO_SCALE));
+            q[base + (((long long)0 * Z + z) * cp + co) * 16 + ci16] = to_e4m3(v - __half2float(h));
+            q[base + (((long long)1 * Z + z) * cp + co) * 16 + ci16] = to_e4m3(v * (1.0f / LO_SCALE));
         }
     }
 }
@@ -706,8 +783,20 @@ extern "C" size_t pcnn_blk8_bytes(int B, int C, int H, int W) {
     return ((size_t)B * planes * (H + 2 * HALO) * (W + 2 * HALO) * 8 + 8192) * sizeof(__half);
 }
 
-extern "C" size_t pcnn_conv_tc_packed_weight_bytes(int kh, int kw, int Cin, int nsplit) {
-    return (size_t)(nsplit >= 2 ? 2 : 1) * ((Cin + 15) / 16) * kw * 2 * (kh + 2 * ZPAD) * COUT_PAD * 8 * sizeof(__half);
+// channel slots per output row of the M operand for a layer with Cout output channels (PCNN_TC_CP=32 forces the
+// widest layout: A/B experiments only)
+static int choose_cp(int cout) {
+    static const int forced = getenv("PCNN_TC_CP") ? atoi(getenv("PCNN_TC_CP")) : 0;
+    if (forced == 32 || forced == 16 || forced == 8) return forced >= cout ? forced : 32;
+    return cout <= 8 ? 8 : (cout <= 16 ? 16 : 32);
+}
+
+extern "C" int pcnn_conv_tc_channel_slots(int Cout) { return (Cout >= 1 && Cout <= 32) ? choose_cp(Cout) : 0; }
+
+extern "C" size_t pcnn_conv_tc_packed_weight_bytes(int kh, int kw, int Cin, int Cout, int nsplit) {
+    if (Cout < 1 || Cout > 32) return 0;
+    const int cp = choose_cp(Cout);
+    return (size_t)(nsplit >= 2 ? 2 : 1) * ((Cin + 15) / 16) * kw * 2 * (kh + 2 * (M_TILE / cp - 1)) * cp * 8 * sizeof(__half);
 }
 
 extern "C" int pcnn_conv_tc_pack_weights(const float* kernel, void* packed, int kh, int kw, int Cin, int Cout, int nsplit,
@@ -716,10 +805,10 @@ extern "C" int pcnn_conv_tc_pack_weights(const float* kernel, void* packed, int 
     PCNN_CHECK_ARG(nsplit >= 1 && nsplit <= 3, "conv_tc_pack_weights: precision mode must be 1, 2 or 3");
     PCNN_CHECK_ARG(kernel && packed, "conv_tc_pack_weights: null pointer");
     PCNN_CHECK_ARG(kh == kw && (kh & 1) && kh >= 1 && kh <= 2 * HALO + 1, "conv_tc: kernel %dx%d not supported (odd, square, <= 15)", kh, kw);
-    PCNN_CHECK_ARG(Cout >= 1 && Cout <= COUT_PAD && Cin >= 1, "conv_tc: Cout %d not in [1,32]", Cout);
-    const int c16 = (Cin + 15) / 16;
-    const long long total = (long long)c16 * kw * 2 * (kh + 2 * ZPAD) * COUT_PAD * 8;
-    pack_weights_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(kernel, (__half*)packed, kh, kw, Cin, Cout, c16, total, nsplit, scale);
+    PCNN_CHECK_ARG(Cout >= 1 && Cout <= 32 && Cin >= 1, "conv_tc: Cout %d not in [1,32]", Cout);
+    const int c16 = (Cin + 15) / 16, cp = choose_cp(Cout);
+    const long long total = (long long)c16 * kw * 2 * (kh + 2 * (M_TILE / cp - 1)) * cp * 8;
+    pack_weights_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(kernel, (__half*)packed, kh, kw, Cin, Cout, c16, total, nsplit, scale, cp);
     PCNN_CHECK_LAUNCH();
     return PCNN_OK;
 }
@@ -785,7 +874,7 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
     PCNN_CHECK_ARG(nsplit >= 1 && nsplit <= 3, "conv2d_tc: precision mode must be 1, 2 or 3");
     if (nsplit >= 2) PCNN_CHECK_ARG(in_lo && out_lo && (!residual || residual_lo), "conv2d_tc: split precision needs the lo buffers");
     PCNN_CHECK_ARG((k & 1) && k >= 1 && k <= 2 * HALO + 1, "conv2d_tc: kernel size %d not supported (odd, <= 15)", k);
-    PCNN_CHECK_ARG(Cout >= 1 && Cout <= COUT_PAD && Cout <= Cout_total, "conv2d_tc: Cout %d not in [1,32]", Cout);
+    PCNN_CHECK_ARG(Cout >= 1 && Cout <= 32 && Cout <= Cout_total, "conv2d_tc: Cout %d not in [1,32]", Cout);
     PCNN_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cin_total > 0, "conv2d_tc: bad shape");
     PCNN_CHECK_ARG((bn_scale == nullptr) == (bn_shift == nullptr), "conv2d_tc: bn_scale/bn_shift must come together");
     Params p;
@@ -798,20 +887,23 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
     p.nv = p.c16 * (nsplit == 2 ? 3 : (nsplit == 3 ? 2 : 1));
     p.c8_in = p.c16 * 2; p.c8_out = ((Cout_total + 15) / 16) * 2; p.c8_res = ((Cres_total + 15) / 16) * 2;
     p.cout = Cout; p.kh = k; p.kw = k; p.pad = k / 2; p.act = act;
+    const int cp = choose_cp(Cout), rt = M_TILE / cp, zpad = rt - 1;
     p.n_tile = W >= 256 ? 256 : ((W + 15) / 16) * 16;
-    p.tiles_x = ceil_div(W, p.n_tile); p.tiles_y = ceil_div(H, ROWS_PER_TILE);
+    p.tiles_x = ceil_div(W, p.n_tile); p.tiles_y = ceil_div(H, rt);
     p.num_tiles = B * p.tiles_x * p.tiles_y;
     p.row_copy_bytes = (uint32_t)(p.n_tile + k - 1) * 16u;
     p.rowplane_bytes = (p.row_copy_bytes + 127u) & ~127u;
-    p.wstage_bytes = 2u * (uint32_t)(k + 2 * ZPAD) * 512u;
+    p.wstage_bytes = 2u * (uint32_t)(k + 2 * zpad) * (uint32_t)cp * 16u;
     // instruction descriptor: D=F32, A=B=F16, both K-major, N = n_tile, M = 128
     p.idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     // shared-memory plan.  Rows need >= R slots (ideally 2R: full double buffering across chunk switches).  Weights:
     // if every stage of a tile (nv*kw of them) fits, they stay RESIDENT for the whole kernel; otherwise as many
     // stages as fit (<= 12) are kept in flight -- the weight stream is latency-bound with few small stages.
+    // Large kernels are MMA-bound by a wide margin: four epilogue warps suffice and leave their buffers to the operands.
     const size_t kMax = 227 * 1024;
-    const size_t fixed = NUM_EPI_WARPS * (4 * (STAGE_PX * 16 + 16)) + 2048;   // transpose buffers + mbarriers
-    const int R = k + ZPAD;
+    p.n_epi = (k >= 11) ? 4 : MAX_EPI_WARPS;
+    const size_t fixed = (size_t)p.n_epi * STAGE_WARP + 2048;   // transpose buffers + mbarriers
+    const int R = k + zpad;
     const size_t avail = kMax - fixed, rowslot = 2 * (size_t)p.rowplane_bytes, wst = p.wstage_bytes;
     PCNN_CHECK_ARG((size_t)R * rowslot + 2 * wst <= avail, "conv2d_tc: tile does not fit in shared memory (k=%d, n_tile=%d)", k, p.n_tile);
     const int total_stages = p.nv * k;
@@ -830,13 +922,19 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
         PCNN_CHECK_ARG(slots >= R && w_stages >= 2, "conv2d_tc: shared-memory plan failed (k=%d, n_tile=%d)", k, p.n_tile);
     }
     slots = (slots / (R / 2)) * (R / 2);          // barrier groups of R/2 rows must not straddle the ring wrap
+    PCNN_CHECK_ARG(2 * (slots + w_stages) + 5 <= 250, "conv2d_tc: too many pipeline stages for the mbarrier area");
     p.row_slots = slots; p.w_stages = w_stages; p.w_resident = resident;
     { static const int dbg = getenv("PCNN_TC_DEBUG") ? atoi(getenv("PCNN_TC_DEBUG")) : 0; p.debug = dbg; }
     const size_t smem = (size_t)slots * rowslot + (size_t)w_stages * wst + fixed;
-    PCNN_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax));
     if (num_sms <= 0) num_sms = 148;
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-    conv_tc_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(p);
-    PCNN_CHECK_LAUNCH();
-    return PCNN_OK;
+    auto launch = [&](auto kern) -> int {
+        PCNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax));
+        kern<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(p);
+        PCNN_CHECK_LAUNCH();
+        return PCNN_OK;
+    };
+    if (cp == 32) return launch(conv_tc_kernel<32>);
+    if (cp == 16) return launch(conv_tc_kernel<16>);
+    return launch(conv_tc_kernel<8>);
 }

@@ -434,7 +434,7 @@ def _blk8_buffer(key, nbytes, device):
     if pool:
         buf, dirty_halo = pool.pop()
         if dirty_halo:                  # a mirrored halo from the previous user: back to zeros (halo only)
-            _, B, C, H, W = key
+            _, B, C, H, W, _ = key
             check(lib.pcnn_blk8_halo_fill(_p(buf), B, C, H, W, 7, PAD_CONSTANT, _stream()), "blk8_halo_fill")
         return buf
     return torch.zeros(nbytes // 2, dtype=torch.float16, device=device)
@@ -449,7 +449,7 @@ class Blk8:
     halo fill, (mode, -1) when a mirrored halo went stale.  Buffers are recycled through a pool keyed by
     the exact shape, so steady-state inference neither allocates nor re-zeroes them."""
 
-    __slots__ = ("buf", "lo", "mode", "B", "C", "H", "W", "halo", "_key")
+    __slots__ = ("buf", "lo", "mode", "B", "C", "H", "W", "halo", "_key", "_key_lo")
 
     def __init__(self, B, C, H, W, device, split=False):
         nbytes = lib.pcnn_blk8_bytes(B, C, H, W)
@@ -458,9 +458,11 @@ class Blk8:
         self.mode = (2 if split else 1) if isinstance(split, bool) else int(split)
         if self.mode not in (1, 2, 3):
             raise ValueError("Blk8: precision mode must be 1, 2 or 3")
-        self._key = (str(device), B, C, H, W)
+        # hi and lo/q buffers never trade places: bytes one role leaves untouched (channel padding) must stay zero
+        self._key = (str(device), B, C, H, W, "hi")
+        self._key_lo = (str(device), B, C, H, W, "lo%d" % self.mode)
         self.buf = _blk8_buffer(self._key, nbytes, device)
-        self.lo = _blk8_buffer(self._key, nbytes, device) if self.mode >= 2 else None
+        self.lo = _blk8_buffer(self._key_lo, nbytes, device) if self.mode >= 2 else None
         self.B, self.C, self.H, self.W = B, C, H, W
         self.halo = (PAD_CONSTANT, 7)
 
@@ -468,10 +470,9 @@ class Blk8:
         try:
             # a mirrored halo must not leak into the next user: such buffers are re-zeroed on reuse
             dirty = self.halo[0] != PAD_CONSTANT
-            pool = _BLK8_POOL.setdefault(self._key, [])
-            pool.append((self.buf, dirty))
+            _BLK8_POOL.setdefault(self._key, []).append((self.buf, dirty))
             if self.lo is not None:
-                pool.append((self.lo, dirty))
+                _BLK8_POOL.setdefault(self._key_lo, []).append((self.lo, dirty))
         except Exception:
             pass
 
@@ -544,7 +545,7 @@ def pack_conv_weights_tc(kernel, nsplit=1):
     """Keras [k,k,Cin,Cout] fp32 -> packed fp16 operand image (done once per layer); nsplit=2 adds W_lo."""
     _chk(kernel, "kernel")
     kh, kw, Cin, Cout = kernel.shape
-    n = lib.pcnn_conv_tc_packed_weight_bytes(kh, kw, Cin, int(nsplit))
+    n = lib.pcnn_conv_tc_packed_weight_bytes(kh, kw, Cin, Cout, int(nsplit))
     packed = torch.empty(n // 2, dtype=torch.float16, device=kernel.device)
     # power-of-two pre-scale so that max|W| lands near 2^9: W_hi and the remainder W_lo (~2^-12 |W|) both stay in
     # fp16's normal range; the kernel multiplies the accumulator by 1/scale (exact).  One host sync at pack time.

@@ -55,6 +55,11 @@ def test_blk8_roundtrip_and_halo(ops):
     (1, 16, 16, 16, 40, 5, 0),
     (3, 12, 8, 5, 33, 3, 1),
     (1, 32, 32, 4, 16, 1, 0),         # 1x1
+    (2, 15, 15, 37, 300, 5, 1),       # Cout <= 16: 8 output rows x 16 channel slots per tile, ragged both ways
+    (2, 19, 15, 8, 256, 5, 2),
+    (2, 7, 5, 37, 70, 3, 2),          # Cout <= 8: 16 output rows x 8 channel slots
+    (1, 5, 5, 50, 256, 3, 1),
+    (1, 11, 7, 16, 31, 5, 0),
 ])
 def test_conv2d_tc_parity(ops, B, Cin, Cout, H, W, k, act):
     g = torch.Generator().manual_seed(B * 1000 + Cin * 10 + k)
@@ -157,6 +162,9 @@ def test_models_tc_mode_vs_oracle():
     (1, 64, 32, 9, 80, 7, 1),
     (2, 29, 23, 20, 21, 7, 2),
     (3, 12, 8, 5, 33, 3, 0),
+    (2, 15, 15, 37, 300, 5, 1),
+    (2, 7, 5, 37, 70, 3, 2),
+    (1, 11, 7, 16, 31, 5, 1),
 ])
 def test_conv2d_tc3_parity(ops, B, Cin, Cout, H, W, k, act):
     """hi/lo split operands, three MMAs: ~22 operand bits.  Measured floor ~8e-6 on the K=7200 layer with or
@@ -197,6 +205,9 @@ def test_models_tc3_mode_vs_oracle():
     (1, 64, 32, 9, 80, 7, 1),
     (2, 29, 23, 20, 21, 7, 2),
     (3, 12, 8, 5, 33, 3, 0),
+    (2, 15, 15, 37, 300, 5, 1),
+    (2, 7, 5, 37, 70, 3, 2),
+    (1, 11, 7, 16, 31, 5, 1),
 ])
 def test_conv2d_tc2_parity(ops, B, Cin, Cout, H, W, k, act):
     """fp16 main MMA + one e4m3 K=32 MMA carrying both correction terms: ~10x tighter than a single fp16 pass."""
