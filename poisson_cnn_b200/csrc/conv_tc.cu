@@ -783,19 +783,33 @@ extern "C" size_t pcnn_blk8_bytes(int B, int C, int H, int W) {
     return ((size_t)B * planes * (H + 2 * HALO) * (W + 2 * HALO) * 8 + 8192) * sizeof(__half);
 }
 
-// channel slots per output row of the M operand for a layer with Cout output channels (PCNN_TC_CP=32 forces the
-// widest layout: A/B experiments only)
-static int choose_cp(int cout) {
+// shared-memory budget of the kernel
+constexpr size_t SMEM_MAX = 227 * 1024;
+static inline int epi_warps_for(int k) { return (k >= 11) ? 4 : MAX_EPI_WARPS; }   // large kernels are MMA-bound by a wide margin
+static inline size_t smem_fixed_for(int k) { return (size_t)epi_warps_for(k) * STAGE_WARP + 2048; }   // transpose buffers + mbarriers
+
+// Channel slots per output row of the M operand for a k x k layer with Cout output channels: the narrowest of
+// {8, 16, 32} >= Cout whose kh+RT-1 input rows (at the full 256-pixel tile width) plus three weight stages fit in
+// shared memory.  Depends only on (Cout, k), so packing and launching always agree.
+// (PCNN_TC_CP=32 forces the widest layout: A/B experiments only.)
+static int choose_cp(int cout, int k) {
     static const int forced = getenv("PCNN_TC_CP") ? atoi(getenv("PCNN_TC_CP")) : 0;
-    if (forced == 32 || forced == 16 || forced == 8) return forced >= cout ? forced : 32;
-    return cout <= 8 ? 8 : (cout <= 16 ? 16 : 32);
+    if (forced == 32) return 32;
+    for (int cp = 8; cp < 32; cp *= 2) {
+        if (cp < cout) continue;
+        const int zpad = M_TILE / cp - 1, R = k + zpad;
+        const size_t rowslot = 2 * (((size_t)(256 + k - 1) * 16 + 127) & ~(size_t)127);
+        const size_t wst = 2 * (size_t)(k + 2 * zpad) * cp * 16;
+        if ((size_t)R * rowslot + 3 * wst + smem_fixed_for(k) <= SMEM_MAX) return cp;
+    }
+    return 32;
 }
 
-extern "C" int pcnn_conv_tc_channel_slots(int Cout) { return (Cout >= 1 && Cout <= 32) ? choose_cp(Cout) : 0; }
+extern "C" int pcnn_conv_tc_channel_slots(int Cout, int k) { return (Cout >= 1 && Cout <= 32) ? choose_cp(Cout, k) : 0; }
 
 extern "C" size_t pcnn_conv_tc_packed_weight_bytes(int kh, int kw, int Cin, int Cout, int nsplit) {
     if (Cout < 1 || Cout > 32) return 0;
-    const int cp = choose_cp(Cout);
+    const int cp = choose_cp(Cout, kh);
     return (size_t)(nsplit >= 2 ? 2 : 1) * ((Cin + 15) / 16) * kw * 2 * (kh + 2 * (M_TILE / cp - 1)) * cp * 8 * sizeof(__half);
 }
 
@@ -806,7 +820,7 @@ extern "C" int pcnn_conv_tc_pack_weights(const float* kernel, void* packed, int 
     PCNN_CHECK_ARG(kernel && packed, "conv_tc_pack_weights: null pointer");
     PCNN_CHECK_ARG(kh == kw && (kh & 1) && kh >= 1 && kh <= 2 * HALO + 1, "conv_tc: kernel %dx%d not supported (odd, square, <= 15)", kh, kw);
     PCNN_CHECK_ARG(Cout >= 1 && Cout <= 32 && Cin >= 1, "conv_tc: Cout %d not in [1,32]", Cout);
-    const int c16 = (Cin + 15) / 16, cp = choose_cp(Cout);
+    const int c16 = (Cin + 15) / 16, cp = choose_cp(Cout, kh);
     const long long total = (long long)c16 * kw * 2 * (kh + 2 * (M_TILE / cp - 1)) * cp * 8;
     pack_weights_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(kernel, (__half*)packed, kh, kw, Cin, Cout, c16, total, nsplit, scale, cp);
     PCNN_CHECK_LAUNCH();
@@ -887,7 +901,7 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
     p.nv = p.c16 * (nsplit == 2 ? 3 : (nsplit == 3 ? 2 : 1));
     p.c8_in = p.c16 * 2; p.c8_out = ((Cout_total + 15) / 16) * 2; p.c8_res = ((Cres_total + 15) / 16) * 2;
     p.cout = Cout; p.kh = k; p.kw = k; p.pad = k / 2; p.act = act;
-    const int cp = choose_cp(Cout), rt = M_TILE / cp, zpad = rt - 1;
+    const int cp = choose_cp(Cout, k), rt = M_TILE / cp, zpad = rt - 1;
     p.n_tile = W >= 256 ? 256 : ((W + 15) / 16) * 16;
     p.tiles_x = ceil_div(W, p.n_tile); p.tiles_y = ceil_div(H, rt);
     p.num_tiles = B * p.tiles_x * p.tiles_y;
@@ -899,10 +913,9 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
     // shared-memory plan.  Rows need >= R slots (ideally 2R: full double buffering across chunk switches).  Weights:
     // if every stage of a tile (nv*kw of them) fits, they stay RESIDENT for the whole kernel; otherwise as many
     // stages as fit (<= 12) are kept in flight -- the weight stream is latency-bound with few small stages.
-    // Large kernels are MMA-bound by a wide margin: four epilogue warps suffice and leave their buffers to the operands.
-    const size_t kMax = 227 * 1024;
-    p.n_epi = (k >= 11) ? 4 : MAX_EPI_WARPS;
-    const size_t fixed = (size_t)p.n_epi * STAGE_WARP + 2048;   // transpose buffers + mbarriers
+    const size_t kMax = SMEM_MAX;
+    p.n_epi = epi_warps_for(k);
+    const size_t fixed = smem_fixed_for(k);
     const int R = k + zpad;
     const size_t avail = kMax - fixed, rowslot = 2 * (size_t)p.rowplane_bytes, wst = p.wstage_bytes;
     PCNN_CHECK_ARG((size_t)R * rowslot + 2 * wst <= avail, "conv2d_tc: tile does not fit in shared memory (k=%d, n_tile=%d)", k, p.n_tile);

@@ -92,64 +92,80 @@ __global__ void deconv_same_kernel(const float* __restrict__ in, const float* __
 }
 
 // k == stride (every shipped config): non-overlapping transpose conv = one CoutxCin mat-vec per output
-// pixel with a phase-selected matrix.  A CTA owns one OUTPUT row Y (fixed row phase ty) and 32 low-res
-// pixels; the 32 input vectors stay in registers while the s column-phase matrices stream through
-// shared memory; results are staged in shared memory so the read-modify-write of `out` is coalesced.
-// threads: 32 pixels x 8 groups of 4 output channels.
-constexpr int DK_ROWS = 4;   // low-res rows per CTA (amortises the phase-matrix load)
-__global__ void __launch_bounds__(256) deconv_ks_kernel(const float* __restrict__ in, const float* __restrict__ kernel,
-                                                        const float* __restrict__ bias, float* __restrict__ out, int Cin,
-                                                        int Cout, int ih, int iw, int oh, int ow, int s, int pbh, int pbw,
-                                                        int act, float alpha, int accumulate, long long out_bstride) {
-    extern __shared__ float sm[];
-    float* s_w = sm;                    // [s column phases][32 co][32 ci] (zero padded), loaded once per CTA
-    float* s_o = sm + s * 32 * 32;      // [32 co][32*s + 1] output row segment
-    const int pitch = 32 * s + 1;
-    const int b = blockIdx.z;
-    // blockIdx.y = (group of DK_ROWS low-res rows, row phase ty): the s phase matrices are reused for every row
-    const int ty = blockIdx.y % s, ig = blockIdx.y / s;
-    const int j0 = blockIdx.x * 32;
-    const int px = threadIdx.x & 31, cg = threadIdx.x >> 5;
-    const int j = j0 + px;
-    const float* kp = kernel + (long long)ty * s * Cout * Cin;      // [tx][Cout][Cin]
-    for (int e = threadIdx.x; e < s * 32 * 32; e += 256) {
-        const int tx = e >> 10, co = (e >> 5) & 31, ci = e & 31;
-        s_w[e] = (co < Cout && ci < Cin) ? __ldg(kp + ((long long)tx * Cout + co) * Cin + ci) : 0.f;
+// pixel with a phase-selected matrix W[ty][tx].  A CTA owns one low-res row segment of `seg` pixels (the
+// 32 x seg input tile sits in shared memory) and walks the s row phases ty; within a row phase every
+// column phase tx is computed at once by a different thread group, so a pass yields one complete
+// output row segment (seg*s pixels x Cout), staged phase-major in shared memory and then written
+// (read-modify-written when accumulating) with fully coalesced rows.
+// threads: tid -> (tx, cg, pg): 8 output channels x 4 low-res pixels per thread (32 accumulators), weights
+// straight from global/L1 as float4 over ci (the same few KB for the whole CTA), inputs as float4 from smem.
+__global__ void __launch_bounds__(288, 2) deconv_ks_kernel(const float* __restrict__ in, const float* __restrict__ kernel,
+                                                           const float* __restrict__ bias, float* __restrict__ out, int Cin,
+                                                           int Cout, int ih, int iw, int oh, int ow, int s, int pbh, int pbw,
+                                                           int act, float alpha, int accumulate, long long out_bstride,
+                                                           int seg, int phase_stride) {
+    extern __shared__ __align__(16) float sm[];
+    float* s_x = sm;                    // [32 ci][seg]
+    float* s_o = sm + 32 * seg;         // [s tx][phase_stride >= 32 co * seg]; phase_stride % 32 == ceil(32/s): conflict-free gather
+    const int b = blockIdx.z, i = blockIdx.y, j0 = blockIdx.x * seg;
+    const int pgs = seg >> 2, nthr = blockDim.x;
+    for (int e = threadIdx.x; e < 32 * seg; e += nthr) {
+        const int ci = e / seg, px = e - ci * seg;
+        s_x[e] = (ci < Cin && j0 + px < iw) ? __ldg(in + (((long long)b * Cin + ci) * ih + i) * iw + j0 + px) : 0.f;
     }
+    const int tx = threadIdx.x / (4 * pgs);
+    const int rem = threadIdx.x - tx * 4 * pgs;
+    const int cg = rem / pgs, pg = rem - cg * pgs;
+    const bool worker = tx < s;
+    const int ncol = seg * s;           // output pixels of the row segment
     const int X0 = j0 * s - pbw;
-    const int ncol = 32 * s;
-    for (int i = ig * DK_ROWS; i < min((ig + 1) * DK_ROWS, ih); ++i) {
+    __syncthreads();
+    for (int ty = 0; ty < s; ++ty) {
         const int Y = i * s + ty - pbh;
         if (Y < 0 || Y >= oh) continue;     // block-uniform
-        float x[32];
+        float acc[8][4];
 #pragma unroll
-        for (int ci = 0; ci < 32; ++ci)
-            x[ci] = (j < iw && ci < Cin) ? __ldg(in + (((long long)b * Cin + ci) * ih + i) * iw + j) : 0.f;
-        __syncthreads();                    // weights visible / previous row's epilogue finished with s_o
-        for (int tx = 0; tx < s; ++tx) {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < 8; ++c)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const float4* wr = reinterpret_cast<const float4*>(s_w + (tx * 32 + cg * 4 + c) * 32);
+            for (int q = 0; q < 4; ++q) acc[c][q] = 0.f;
+        if (worker) {
+            const float* wp = kernel + ((long long)(ty * s + tx) * Cout + cg * 8) * Cin;
+            const float* xp = s_x + pg * 4;
+#pragma unroll 1
+            for (int ci = 0; ci < Cin; ci += 4) {
+                float4 x4[4];
 #pragma unroll
-                for (int q4 = 0; q4 < 8; ++q4) {
-                    const float4 w = wr[q4];
-                    acc[c] = fmaf(x[4 * q4 + 0], w.x, acc[c]);
-                    acc[c] = fmaf(x[4 * q4 + 1], w.y, acc[c]);
-                    acc[c] = fmaf(x[4 * q4 + 2], w.z, acc[c]);
-                    acc[c] = fmaf(x[4 * q4 + 3], w.w, acc[c]);
+                for (int k = 0; k < 4; ++k) x4[k] = *reinterpret_cast<const float4*>(xp + (ci + k) * seg);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (cg * 8 + c < Cout) w = __ldg(reinterpret_cast<const float4*>(wp + (long long)c * Cin + ci));
+                    acc[c][0] = fmaf(w.x, x4[0].x, acc[c][0]); acc[c][1] = fmaf(w.x, x4[0].y, acc[c][1]);
+                    acc[c][2] = fmaf(w.x, x4[0].z, acc[c][2]); acc[c][3] = fmaf(w.x, x4[0].w, acc[c][3]);
+                    acc[c][0] = fmaf(w.y, x4[1].x, acc[c][0]); acc[c][1] = fmaf(w.y, x4[1].y, acc[c][1]);
+                    acc[c][2] = fmaf(w.y, x4[1].z, acc[c][2]); acc[c][3] = fmaf(w.y, x4[1].w, acc[c][3]);
+                    acc[c][0] = fmaf(w.z, x4[2].x, acc[c][0]); acc[c][1] = fmaf(w.z, x4[2].y, acc[c][1]);
+                    acc[c][2] = fmaf(w.z, x4[2].z, acc[c][2]); acc[c][3] = fmaf(w.z, x4[2].w, acc[c][3]);
+                    acc[c][0] = fmaf(w.w, x4[3].x, acc[c][0]); acc[c][1] = fmaf(w.w, x4[3].y, acc[c][1]);
+                    acc[c][2] = fmaf(w.w, x4[3].z, acc[c][2]); acc[c][3] = fmaf(w.w, x4[3].w, acc[c][3]);
                 }
             }
+        }
+        __syncthreads();                    // previous row phase's write-out finished with s_o
+        if (worker) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) s_o[(cg * 4 + c) * pitch + px * s + tx] = acc[c];
+            for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<float4*>(s_o + tx * phase_stride + (cg * 8 + c) * seg + pg * 4) =
+                    make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
         }
         __syncthreads();
-        // coalesced epilogue: out[b, co, Y, X] (op)= alpha * act(v + bias)
-        for (int e = threadIdx.x; e < Cout * ncol; e += 256) {
+        // coalesced write-out: out[b, co, Y, X] (op)= alpha * act(v + bias); X = px*s + tx - pbw
+        for (int e = threadIdx.x; e < Cout * ncol; e += nthr) {
             const int co = e / ncol, c = e - co * ncol;
+            const int px = c / s, t = c - px * s;
             const int X = X0 + c;
-            if (X < 0 || X >= ow || j0 + c / s >= iw) continue;
-            float v = s_o[co * pitch + c] + (bias ? __ldg(bias + co) : 0.f);
+            if (X < 0 || X >= ow || j0 + px >= iw) continue;
+            float v = s_o[t * phase_stride + co * seg + px] + (bias ? __ldg(bias + co) : 0.f);
             v = apply_act(v, act) * alpha;
             float* o = out + (long long)b * out_bstride + ((long long)co * oh + Y) * ow + X;
             *o = accumulate ? (*o + v) : v;
@@ -459,14 +475,24 @@ extern "C" int pcnn_deconv_same_f32(const float* in, const float* kernel, const 
                    "deconv_same_f32: output_shape (%d,%d) inconsistent with input (%d,%d) at stride %d (TF raises)", oh, ow, ih, iw, stride);
     const int pbh = max((ih - 1) * stride + kh - oh, 0) / 2;
     const int pbw = max((iw - 1) * stride + kw - ow, 0) / 2;
-    if (kh == stride && kw == stride && Cin <= 32 && Cout <= 32 && stride <= 16 && B <= 65535 && ih * stride <= 65535) {
-        const size_t smem = ((size_t)stride * 32 * 32 + 32 * (32 * stride + 1)) * sizeof(float);
-        if (smem > 48 * 1024)
-            PCNN_CHECK_CUDA(cudaFuncSetAttribute(deconv_ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid(ceil_div(iw, 32), ceil_div(ih, DK_ROWS) * stride, B);
-        deconv_ks_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(in, kernel, bias, out, Cin, Cout, ih, iw, oh, ow, stride, pbh, pbw, act, alpha, accumulate, out_bstride);
-        PCNN_CHECK_LAUNCH();
-        return PCNN_OK;
+    if (kh == stride && kw == stride && Cin <= 32 && (Cin % 4) == 0 && Cout <= 32 && stride <= 16 && B <= 65535 && ih <= 65535 &&
+        (reinterpret_cast<uintptr_t>(kernel) % 16) == 0) {
+        // low-res pixels per CTA: seg*stride ~ 256 output pixels, seg a multiple of 4; all `stride` column phases run at once
+        int seg = ((256 / stride + 3) / 4) * 4;
+        seg = std::min(seg, ((iw + 3) / 4) * 4);
+        const int threads = ((seg * stride + 31) / 32) * 32;        // 4 channel groups x seg/4 pixel groups x stride phases
+        int phase_stride = 32 * seg;                                // == 0 mod 32
+        phase_stride += (32 + stride - 1) / stride;                 // phases land ceil(32/s) banks apart
+        phase_stride = (phase_stride + 3) & ~3;                     // float4 staging stores stay aligned
+        const size_t smem = ((size_t)32 * seg + (size_t)stride * phase_stride) * sizeof(float);
+        if (threads <= 288 && smem <= 100 * 1024) {
+            if (smem > 48 * 1024)
+                PCNN_CHECK_CUDA(cudaFuncSetAttribute(deconv_ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dim3 grid(ceil_div(iw, seg), ih, B);
+            deconv_ks_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(in, kernel, bias, out, Cin, Cout, ih, iw, oh, ow, stride, pbh, pbw, act, alpha, accumulate, out_bstride, seg, phase_stride);
+            PCNN_CHECK_LAUNCH();
+            return PCNN_OK;
+        }
     }
     const long long total = (long long)B * Cout * oh * ow;
     deconv_same_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(in, kernel, bias, out, Cin, Cout, ih, iw, oh, ow, kh, kw, stride, pbh, pbw, act, alpha, accumulate, out_bstride, total);

@@ -124,10 +124,10 @@ class Dirichlet_BC_NN_Legacy_2(WeightedModel):
                 u = ops.conv2d_tc(t, w0, b0, self.final_act, PAD_CONSTANT)
                 u = ops.conv2d_tc(u, w1, b1, self.final_act, PAD_CONSTANT, residual=t)
                 t = ops.conv2d_tc(u, w2, b2, self.final_act, PAD_CONSTANT)
-            out = ops.from_blk8(t, C=self.conv("final/%d/conv" % (S - nreg))[0].shape[2])
             for k in range(S - nreg, S):
-                kk, bb = self.conv("final/%d/conv" % k)
-                out = ops.conv2d(out, kk, bb, ACT_TANH, PAD_CONSTANT, 0.0)
+                wp, bb = self.tc_conv("final/%d/conv" % k)
+                t = ops.conv2d_tc(t, wp, bb, ACT_TANH, PAD_CONSTANT)
+            out = ops.from_blk8(t, C=t.C)
             return out, ops.maxabs(out)
         out = ops.dbcnn_expand(h, v, x_res)
         for k in range(S - nreg):

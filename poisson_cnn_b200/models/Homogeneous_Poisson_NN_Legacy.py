@@ -178,18 +178,15 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
 
     def _call_tc(self, rhs, dx):
         """Same graph as the FP32 path with every heavy convolution on tcgen05 (BLK8 fp16 activations).
-        FP32 kernels keep: the 3-channel first conv, pooling / upsampling / merge, the 2..8-pixel
-        multilinear branches, the last two linear convs, Scaling and the boundary ring."""
+        FP32 kernels keep: pooling / upsampling / merge, the 2..8-pixel multilinear branches, Scaling and
+        the boundary ring."""
         B, _, H, Wd = rhs.shape
         F = self.filters
         dev = rhs.device
         x = ops.hpnn_input(rhs) if self.use_positional_embeddings else rhs
-        kk, bb = self.conv("pre_bottleneck/0")
-        x = ops.conv2d(x, kk, bb, self.pre_act, self.pre_pad, self.pre_pad_value,
-                       bn=self.bn("pre_bottleneck/0/bn") if self.use_batchnorm else None)
         split = self.tc_split
         t = ops.to_blk8(x, split=split)
-        for k in range(1, self.n_pre):
+        for k in range(self.n_pre):
             t = self._conv_tc(t, "pre_bottleneck/%d" % k, self.pre_act, self.pre_pad,
                               "pre_bottleneck/%d/bn" % k if self.use_batchnorm else None)
         x0 = t                                   # BLK8, F channels
@@ -227,14 +224,18 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
         for k in range(S - nreg):
             y = self._conv_tc(y, "final/%d/conv" % k, self.final_act, self.final_pad)
             y = self._resnet_tc(y, "final/%d/resnet" % k, self.final_act, PAD_CONSTANT, False)
-        y = ops.from_blk8(y, C=self.conv("final/%d/conv" % (S - nreg))[0].shape[2])
-        return self._tail(y, rhs, dx, S - nreg)
+        for k in range(S - nreg, S):             # the last linear convs: 16 output rows x 8 channel slots per tile
+            y = self._conv_tc(y, "final/%d/conv" % k, ACT_LINEAR, PAD_CONSTANT)
+        cat2 = torch.empty((B, 2, H, Wd), device=dev, dtype=torch.float32) if self.use_scaling and y.C == 1 else None
+        y = ops.from_blk8(y, C=y.C, out=None if cat2 is None else cat2[:, 0:1])
+        return self._tail(y, rhs, dx, S, cat2)
 
-    def _tail(self, y, rhs, dx, first_regular):
-        """The last linear convs, Scaling, boundary ring and post-smoother (FP32 kernels)."""
+    def _tail(self, y, rhs, dx, first_regular, cat2=None):
+        """The last linear convs (strict mode), Scaling, boundary ring and post-smoother (FP32 kernels)."""
         B, _, H, Wd = rhs.shape
         S = self.n_final
-        cat2 = torch.empty((B, 2, H, Wd), device=rhs.device, dtype=torch.float32) if self.use_scaling else None
+        if cat2 is None and self.use_scaling:
+            cat2 = torch.empty((B, 2, H, Wd), device=rhs.device, dtype=torch.float32)
         for k in range(first_regular, S):
             kk, bb = self.conv("final/%d/conv" % k)
             last = (k == S - 1) and self.use_scaling and kk.shape[3] == 1

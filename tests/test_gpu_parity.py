@@ -114,6 +114,23 @@ def test_deconv_same_parity(ops, H, W):
         ops.deconv_same(dev(torch.randn(1, 6, 3, 3)), dev(torch.randn(2, 2, 5, 6)), None, (9, 9), 2)
 
 
+@pytest.mark.parametrize("H,W,Cin,Cout", [(256, 256, 32, 32), (200, 300, 32, 32), (37, 50, 8, 5), (64, 64, 12, 32)])
+def test_deconv_k_equals_stride_fast_path(ops, H, W, Cin, Cout):
+    """k == stride with Cin % 4 == 0 takes the row-segment kernel (all column phases at once)."""
+    g = torch.Generator().manual_seed(H + Cin)
+    for s in (2, 3, 4, 8, 16):
+        ih, iw = -(-H // s), -(-W // s)
+        x = torch.randn(2, Cin, ih, iw, generator=g)
+        kern = torch.randn(s, s, Cout, Cin, generator=g) / Cin ** 0.5
+        bias = torch.randn(Cout, generator=g) * 0.1
+        ref = O.deconv_same(x.double(), kern.double(), bias.double(), "leaky_relu", (H, W), s)
+        got = ops.deconv_same(dev(x), dev(kern), dev(bias), (H, W), s, act=1)
+        assert rel_l2(got, ref) < FP32_TOL, s
+        acc = torch.ones(2, Cout, H, W).cuda()
+        ops.deconv_same(dev(x), dev(kern), dev(bias), (H, W), s, act=1, alpha=0.25, out=acc, accumulate=True)
+        assert rel_l2(acc, 1.0 + 0.25 * ref) < FP32_TOL, s
+
+
 def test_resize_parity(ops):
     from poisson_cnn_b200.config import resize_enum
     g = torch.Generator().manual_seed(3)
