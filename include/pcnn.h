@@ -201,6 +201,20 @@ size_t pcnn_conv_tc_packed_weight_bytes(int kh, int kw, int Cin, int Cout, int n
  * normal range); pass its reciprocal as acc_scale to pcnn_conv2d_tc, which undoes it exactly. */
 int pcnn_conv_tc_pack_weights(const float* kernel, void* packed, int kh, int kw, int Cin, int Cout,
                               int nsplit, float scale, void* stream);
+/* Fused upsample + merge of the HPNN bottleneck branches straight into a BLK8 tensor (csrc/upsample_merge.cu):
+ *   out[:, c_offset : c_offset+C] = alpha * ( sum_d act_d(conv2d_transpose_d(in_d) + bias_d) + sum_r resize_r(in_r) )
+ * i.e. blocks/bottleneck_block.py:57-118 (deconvupscale with k == stride, 'SAME'; Upsample via the per-axis
+ * tables of pcnn_resize_f32) followed by the branch sum of models/Homogeneous_Poisson_NN_Legacy.py:226-233.
+ * The pointer arrays are HOST arrays of n_deconv / n_resize device pointers (<= 8 each); deconv inputs are
+ * [B,C,ih,iw] fp32 with Keras kernels [s,s,C,C]; resize sources are [B,C,ih,iw] fp32 with C*ih*iw <= 8192.
+ * C % 4 == 0, C <= 32; c_offset % 16 == 0; mode = precision mode of the destination (1, 2, 3). */
+int pcnn_upsample_merge_blk8(int n_deconv, const float* const* dc_in, const float* const* dc_kernel,
+                             const float* const* dc_bias, const int* dc_stride, const int* dc_ih,
+                             const int* dc_iw, const int* dc_act, int n_resize, const float* const* rs_in,
+                             const int32_t* const* rs_iy, const float* const* rs_wy,
+                             const int32_t* const* rs_ix, const float* const* rs_wx, const int* rs_taps,
+                             const int* rs_ih, const int* rs_iw, float alpha, void* out, void* out_lo,
+                             int mode, int B, int C, int H, int W, int c_total, int c_offset, void* stream);
 /* Same operator as pcnn_conv2d_f32 (pad + VALID conv + bias + act [+BN] [+residual] [*out_scale]) on
  * tcgen05 tensor cores: FP16 operands, FP32 accumulation in TMEM.  in/out/residual are BLK8 buffers
  * with Cin_total / Cout_total / Cres_total channels; the padding mode is whatever the halo of `in`

@@ -143,19 +143,28 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
         t = ops.conv2d(t, k1, b1, act, pad, pad_value, bn=self.bn(name + "/bn1") if use_bn else None, residual=x)
         return ops.conv2d(t, k2, b2, act, pad, pad_value, out_scale=out_scale)
 
-    def _bottleneck(self, blk, x0, merged, first, alpha):
-        name = "bottleneck_%s/%d" % (blk.kind, blk.index)
-        H, Wd = x0.shape[2], x0.shape[3]
-        h = ops.avgpool_same(x0, blk.downsampling_factor)
-        k, b = self.conv(name + "/conv0")
-        h = ops.conv2d(h, k, b, blk.act, blk.pad, blk.pad_value)
-        for r in range(1, blk.n_convs):
-            h = self._resnet(h, "%s/resnet%d" % (name, r), blk.act, blk.pad, blk.pad_value, blk.use_batchnorm)
+    def _branch_out_hw(self, blk, H, Wd):
         out_hw = (bottleneck_output_size(H, blk.downsampling_factor, blk.upsampling_factor),
                   bottleneck_output_size(Wd, blk.downsampling_factor, blk.upsampling_factor))
         if out_hw != (H, Wd):
             raise ValueError("bottleneck branch ds=%d would produce %s for a %s grid; the merge needs equal shapes"
                              % (blk.downsampling_factor, out_hw, (H, Wd)))
+        return out_hw
+
+    def _bottleneck_lowres(self, blk, x0):
+        """pool -> conv -> resnets of one branch (blocks/bottleneck_block.py:36-50), FP32 kernels."""
+        name = "bottleneck_%s/%d" % (blk.kind, blk.index)
+        h = ops.avgpool_same(x0, blk.downsampling_factor)
+        k, b = self.conv(name + "/conv0")
+        h = ops.conv2d(h, k, b, blk.act, blk.pad, blk.pad_value)
+        for r in range(1, blk.n_convs):
+            h = self._resnet(h, "%s/resnet%d" % (name, r), blk.act, blk.pad, blk.pad_value, blk.use_batchnorm)
+        return h
+
+    def _bottleneck(self, blk, x0, merged, first, alpha):
+        name = "bottleneck_%s/%d" % (blk.kind, blk.index)
+        out_hw = self._branch_out_hw(blk, x0.shape[2], x0.shape[3])
+        h = self._bottleneck_lowres(blk, x0)
         if blk.kind == "deconv":
             dk, db = self.conv(name + "/deconv")
             ops.deconv_same(h, dk, db, out_hw, blk.upsampling_factor, blk.deconv_act, alpha, out=merged, accumulate=not first)
@@ -192,26 +201,41 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
         x0 = t                                   # BLK8, F channels
         x0_f32 = ops.from_blk8(x0)               # pooling pyramid reads NCHW fp32
 
-        merged = torch.empty((B, F, H, Wd), device=dev, dtype=torch.float32)
         blocks = self.bottleneck_deconv_blocks + self.bottleneck_multilinear_blocks
         alpha = 1.0 / float(len(blocks) * F)
-        for i, blk in enumerate(blocks):
+        dc, rs = [], []                          # low-res branch outputs, upsampled and summed by ONE fused kernel
+        for blk in blocks:
+            self._branch_out_hw(blk, H, Wd)
             ph, pw = -(-H // blk.downsampling_factor), -(-Wd // blk.downsampling_factor)
+            name = "bottleneck_%s/%d" % (blk.kind, blk.index)
             if blk.kind == "deconv" and min(ph, pw) >= 16:
-                name = "bottleneck_%s/%d" % (blk.kind, blk.index)
                 h = ops.to_blk8(ops.avgpool_same(x0_f32, blk.downsampling_factor), split=split)
                 h = self._conv_tc(h, name + "/conv0", blk.act, blk.pad)
                 for r in range(1, blk.n_convs):
                     h = self._resnet_tc(h, "%s/resnet%d" % (name, r), blk.act, blk.pad, blk.use_batchnorm)
-                dk, db = self.conv(name + "/deconv")
-                ops.deconv_same(ops.from_blk8(h), dk, db, (H, Wd), blk.upsampling_factor, blk.deconv_act, alpha,
-                                out=merged, accumulate=(i != 0))
+                h = ops.from_blk8(h)
             else:
-                self._bottleneck(blk, x0_f32, merged, i == 0, alpha)
+                h = self._bottleneck_lowres(blk, x0_f32)
+            if blk.kind == "deconv":
+                dk, db = self.conv(name + "/deconv")
+                dc.append((h, dk, db, blk.upsampling_factor, blk.deconv_act))
+            else:
+                rs.append((h, blk.resize_method))
 
         cat = ops.Blk8(B, 2 * F, H, Wd, dev, split=split)
         self._conv_tc(x0, "non_bottleneck_conv", ACT_LEAKY_RELU, PAD_CONSTANT, out=cat)
-        ops.to_blk8(merged, out=cat, c_offset=F)
+        fused = (F % 4 == 0 and len(dc) <= 8 and len(rs) <= 8
+                 and all(tuple(k.shape) == (s_, s_, F, F) and s_ <= 64 for _, k, _, s_, _ in dc)
+                 and all(F * h.shape[2] * h.shape[3] <= 8192 for h, _ in rs))
+        if fused:
+            ops.upsample_merge_blk8(dc, rs, alpha, cat, F, H, Wd)
+        else:                                    # general kernels: fp32 merge buffer, one read-modify-write per branch
+            merged = torch.empty((B, F, H, Wd), device=dev, dtype=torch.float32)
+            for i, (h, dk, db, s_, act_) in enumerate(dc):
+                ops.deconv_same(h, dk, db, (H, Wd), s_, act_, alpha, out=merged, accumulate=(i != 0))
+            for i, (h, method) in enumerate(rs):
+                ops.resize(h, (H, Wd), method, alpha, out=merged, accumulate=(i != 0 or bool(dc)))
+            ops.to_blk8(merged, out=cat, c_offset=F)
         y = self._conv_tc(cat, "post_merge_conv", ACT_LEAKY_RELU, PAD_CONSTANT)
 
         d = ops.dense_input(dx, H, Wd)

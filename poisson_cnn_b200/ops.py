@@ -610,3 +610,49 @@ def dbcnn_expand_blk8(h, modew, x_res, split=False):
     check(lib.pcnn_dbcnn_expand_blk8(_p(h), _p(S), _p(modew), _p(position_table(h.device, x_res)),
                                      _p(position_table(h.device, n)), _p(out.buf), _p(out.lo), out.mode, B, M, x_res, n, _stream()), "dbcnn_expand_blk8")
     return out
+
+
+def upsample_merge_blk8(deconv_branches, resize_branches, alpha, out, c_offset, H, W):
+    """Fused upsample + branch sum written into channels [c_offset, c_offset+C) of the Blk8 tensor `out`.
+    deconv_branches: [(x [B,C,ih,iw] fp32, kernel [s,s,C,C], bias or None, stride, act)];
+    resize_branches: [(x [B,C,ih,iw] fp32, method)]."""
+    import ctypes
+    if not isinstance(out, Blk8) or (out.H, out.W) != (int(H), int(W)):
+        raise ValueError("upsample_merge_blk8: destination must be a Blk8 tensor of the output size")
+    B, C = out.B, None
+    keep = []
+
+    def arr_p(vals):
+        return (ctypes.c_void_p * max(len(vals), 1))(*[v for v in vals])
+
+    def arr_i(vals):
+        return (ctypes.c_int * max(len(vals), 1))(*[int(v) for v in vals])
+    d_in, d_k, d_b, d_s, d_ih, d_iw, d_act = [], [], [], [], [], [], []
+    for x, kern, bias, stride, act in deconv_branches:
+        _chk(x, "x"); _chk(kern, "kernel")
+        x, kern = x.contiguous(), kern.contiguous()
+        C = x.shape[1] if C is None else C
+        if x.shape[0] != B or x.shape[1] != C or tuple(kern.shape) != (stride, stride, C, C):
+            raise ValueError("upsample_merge_blk8: deconv branch needs x [B,C,ih,iw] and a kernel [s,s,C,C] with s == stride")
+        keep += [x, kern]
+        d_in.append(x.data_ptr()); d_k.append(kern.data_ptr()); d_b.append(_p(bias)); d_s.append(stride)
+        d_ih.append(x.shape[2]); d_iw.append(x.shape[3]); d_act.append(act)
+    r_in, r_iy, r_wy, r_ix, r_wx, r_t, r_ih, r_iw = [], [], [], [], [], [], [], []
+    for x, method in resize_branches:
+        _chk(x, "x")
+        x = x.contiguous()
+        C = x.shape[1] if C is None else C
+        if x.shape[0] != B or x.shape[1] != C:
+            raise ValueError("upsample_merge_blk8: resize branch needs x [B,C,ih,iw]")
+        iy, wy = _resize_tables(x.device, x.shape[2], int(H), method)
+        ix, wx = _resize_tables(x.device, x.shape[3], int(W), method)
+        keep += [x]
+        r_in.append(x.data_ptr()); r_iy.append(iy.data_ptr()); r_wy.append(wy.data_ptr()); r_ix.append(ix.data_ptr())
+        r_wx.append(wx.data_ptr()); r_t.append(iy.shape[1]); r_ih.append(x.shape[2]); r_iw.append(x.shape[3])
+    check(lib.pcnn_upsample_merge_blk8(len(d_in), arr_p(d_in), arr_p(d_k), arr_p(d_b), arr_i(d_s), arr_i(d_ih), arr_i(d_iw),
+                                       arr_i(d_act), len(r_in), arr_p(r_in), arr_p(r_iy), arr_p(r_wy), arr_p(r_ix), arr_p(r_wx),
+                                       arr_i(r_t), arr_i(r_ih), arr_i(r_iw), float(alpha), _p(out.buf), _p(out.lo), out.mode,
+                                       B, int(C or 0), int(H), int(W), out.C, int(c_offset), _stream()), "upsample_merge_blk8")
+    if out.halo[0] != PAD_CONSTANT:
+        out.halo = (out.halo[0], -1)
+    return out

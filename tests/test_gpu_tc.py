@@ -117,6 +117,35 @@ def test_conv2d_tc_chain_matches_fp32_path(ops):
     assert rel_l2(ops.from_blk8(t), a) < 2e-3
 
 
+@pytest.mark.parametrize("H,W,C,mode", [(256, 256, 32, 3), (200, 300, 32, 1), (37, 50, 8, 3), (64, 80, 12, 2)])
+def test_upsample_merge_blk8(ops, H, W, C, mode):
+    """Fused deconv (k == stride) + resize branch sum written straight into a BLK8 concat buffer."""
+    from poisson_cnn_b200.config import resize_enum
+    g = torch.Generator().manual_seed(H + C)
+    B = 2
+    dc, rs, ref = [], [], 0.0
+    for s in (16, 8, 4, 3, 2):
+        ih, iw = -(-H // s), -(-W // s)
+        x = torch.randn(B, C, ih, iw, generator=g)
+        kern = torch.randn(s, s, C, C, generator=g) / C ** 0.5
+        bias = torch.randn(C, generator=g) * 0.1
+        dc.append((dev(x), dev(kern), dev(bias), s, 1))
+        ref = ref + O.deconv_same(x.double(), kern.double(), bias.double(), "leaky_relu", (H, W), s)
+    for (ih, iw), m in (((2, 2), "bilinear"), ((4, 5), "bicubic"), ((8, 8), "nearest")):
+        x = torch.randn(B, C, ih, iw, generator=g)
+        rs.append((dev(x), resize_enum(m)))
+        ref = ref + O.resize(x.double(), (H, W), m)
+    alpha = 1.0 / 8
+    ref = ref * alpha
+    out = ops.Blk8(B, 2 * C if C % 16 == 0 else 16 + C, H, W, torch.device("cuda"), split=mode)
+    c_off = C if C % 16 == 0 else 16
+    ops.upsample_merge_blk8(dc, rs, alpha, out, c_off, H, W)
+    got = ops.from_blk8(out, C=C, c_offset=c_off)
+    tol = {1: 6e-4, 2: 2e-6, 3: 4e-5}[mode]          # storage precision of the destination
+    assert rel_l2(got, ref) < tol
+    assert float(ops.from_blk8(out, C=c_off, c_offset=0).abs().max()) == 0.0     # neighbouring channels untouched
+
+
 # ------------------------------------------------------------------ whole models in tensor-core mode
 def _models(hp_cfg, db_cfg, w):
     from poisson_cnn_b200 import convert_tf_object_names, models
