@@ -207,7 +207,7 @@ int pcnn_conv_tc_pack_weights(const float* kernel, void* packed, int kh, int kw,
  * tables of pcnn_resize_f32) followed by the branch sum of models/Homogeneous_Poisson_NN_Legacy.py:226-233.
  * The pointer arrays are HOST arrays of n_deconv / n_resize device pointers (<= 8 each); deconv inputs are
  * [B,C,ih,iw] fp32 with Keras kernels [s,s,C,C]; resize sources are [B,C,ih,iw] fp32 with C*ih*iw <= 8192.
- * C % 4 == 0, C <= 32; c_offset % 16 == 0; mode = precision mode of the destination (1, 2, 3). */
+ * C % 8 == 0, C <= 32; c_offset % 16 == 0; mode = precision mode of the destination (1, 2, 3). */
 int pcnn_upsample_merge_blk8(int n_deconv, const float* const* dc_in, const float* const* dc_kernel,
                              const float* const* dc_bias, const int* dc_stride, const int* dc_ih,
                              const int* dc_iw, const int* dc_act, int n_resize, const float* const* rs_in,

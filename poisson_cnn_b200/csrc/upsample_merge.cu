@@ -1,13 +1,13 @@
 // Fused upsample + merge of the HPNN bottleneck branches (models/Homogeneous_Poisson_NN_Legacy.py:226-233 of the
 // reference sums the upsampled branch outputs; blocks/bottleneck_block.py:57-118 upsample each branch with
 // deconvupscale (k == stride transpose conv, layers/deconvupscale.py:100-109) or tf.image.resize
-// (layers/Upsample.py:57)).  One CTA produces one output row segment of 256 pixels x 32 channels:
-//   * every deconv branch: the low-res row that feeds output row Y sits in shared memory; thread groups
-//     (column phase tx, 8 channels, 4 low-res pixels) compute all column phases at once on the FP32 FMA
-//     pipe (weights as float4 straight from global/L1), stage them phase-major in shared memory, and each
+// (layers/Upsample.py:57)).  Persistent CTAs produce output row segments of 256 pixels x 32 channels, one branch
+// ("stage") at a time, the next stage's operands streaming into shared memory (cp.async) meanwhile:
+//   * every deconv branch: the low-res row that feeds output row Y and the s phase matrices W[ty][*] sit in
+//     shared memory; thread groups (column phase tx, 8 channels, 4 low-res pixels) compute all column phases
+//     at once on the FP32 FMA pipe, stage them phase-major in shared memory, and each
 //     of the first 256 threads -- which owns ONE output pixel, all channels -- gathers its phase
-//     (conflict-free), applies bias + activation and adds it to its running sums (a [32][256] shared array:
-//     registers are left to the 32 accumulators of the compute phase);
+//     (conflict-free), applies bias + activation and adds it to its running sums (32 registers);
 //   * every resize branch: the tiny source map sits in shared memory, each thread interpolates its pixel;
 //   * the sum (x alpha) is written ONCE, straight into the tensor-core operand layout (BLK8 fp16 + remainder /
 //     e4m3 planes) at a channel offset of the concat buffer: the full-resolution fp32 `merged` tensor and its
@@ -39,8 +39,10 @@ struct Params {
     float alpha;
     __half* out; uint8_t* out_lo;
     int mode;                    // precision mode of the destination (1, 2, 3: see pcnn_conv2d_tc)
-    int C, H, W, c8_total, plane0;
-    int sx_floats;               // size of the input-tile region
+    int B, C, H, W, c8_total, plane0;
+    int st_floats;               // staging region (phase-major deconv results / interpolated resize row)
+    int tile_floats;             // offset of the weights inside an operand buffer (= size of the largest input tile)
+    int buf_floats[2];           // operand buffers used by even / odd steps
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
@@ -58,12 +60,15 @@ __device__ __forceinline__ void cp_async4(float* dst, const float* src, bool val
     const int bytes = valid ? 4 : 0;      // src-size 0: the 4 destination bytes are zero-filled
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {     // L2 -> shared, bypassing L1
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
-__device__ __forceinline__ void prefetch_l1(const void* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
 
-// geometry of deconv branch d for this CTA's row segment
+// geometry of deconv branch d for one row segment
 struct DcGeom { int s, ih, iw, i, ty, j_begin, segp, pgs; };
 __device__ __forceinline__ DcGeom dc_geom(const Params& p, int d, int X0, int Y) {
     DcGeom g;
@@ -77,38 +82,48 @@ __device__ __forceinline__ DcGeom dc_geom(const Params& p, int d, int X0, int Y)
     return g;
 }
 
-__global__ void __launch_bounds__(NTHR, 2) upsample_merge_kernel(const Params p) {
+// Persistent CTAs (one per SM) walk (row segment, stage) pairs; stage = one branch.  The operands of the NEXT stage
+// (low-res row tile + the s phase matrices W[ty][0..s), or the tiny resize source) stream into the other
+// shared-memory buffer with cp.async while the current stage computes, also across row boundaries.
+__global__ void __launch_bounds__(NTHR, 1) upsample_merge_kernel(const Params p) {
     extern __shared__ __align__(16) float sm[];
-    float* s_sum = sm;                     // [32 channels][256 pixels] running sums
-    float* s_tile = sm + 32 * SEG_W;       // 2 x sx_floats: deconv [C][segp] low-res row tile / resize [C][ih][iw] source
-    float* s_st = s_tile + 2 * p.sx_floats;   // [s column phases][phase stride] staged deconv results
+    float* s_st = sm;                      // [s column phases][phase stride] staged deconv results / resize row
+    float* s_buf[2] = {s_st + p.st_floats, s_st + p.st_floats + p.buf_floats[0]};   // stage operands: [tile | weights]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int X0 = blockIdx.x * SEG_W, Y = blockIdx.y, b = blockIdx.z;
-    const int X = X0 + tid;
-    const bool owner = tid < SEG_W && X < p.W;
     const int C = p.C;
-    float* my_sum = s_sum + tid;           // owner threads only
-    if (tid < SEG_W) {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) my_sum[c * SEG_W] = 0.f;
-    }
     const int nstages = p.n_dc + p.n_rs;
+    const int segs = (p.W + SEG_W - 1) / SEG_W;
+    const int units = p.B * p.H * segs;
+    const int my_units = (units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total = my_units * nstages;
+    const int wswz = (C == 32) ? 7 : 0;    // 16-byte chunk swizzle of the staged weights (conflict-free across channel groups)
 
-    // asynchronous tile load of stage st (cp.async, one group per stage) + L1 prefetch of this thread's weight rows
-    auto issue_load = [&](int st) {
-        float* dst = s_tile + (st & 1) * p.sx_floats;
+    auto unit_coords = [&](int k, int& b, int& Y, int& X0) {
+        const int u = (int)blockIdx.x + k * (int)gridDim.x;
+        const int seg = u % segs;
+        const int t = u / segs;
+        Y = t % p.H; b = t / p.H; X0 = seg * SEG_W;
+    };
+
+    // asynchronous operand load of step (unit k, stage st): one cp.async group
+    auto issue_load = [&](int step) {
+        const int k = step / nstages, st = step - k * nstages;
+        int b, Y, X0;
+        unit_coords(k, b, Y, X0);
+        float* dst = s_buf[step & 1];
         if (st < p.n_dc) {
             const DcGeom g = dc_geom(p, st, X0, Y);
             const float* inb = p.dc_in[st] + ((long long)b * C * g.ih + g.i) * g.iw + g.j_begin;
             for (int ci = warp; ci < C; ci += NTHR / 32)
                 for (int px = lane; px < g.segp; px += 32)
                     cp_async4(dst + ci * g.segp + px, inb + (long long)ci * g.ih * g.iw + px, g.j_begin + px < g.iw);
-            if (tid < g.s * 4 * g.pgs) {
-                const int tx = tid / (4 * g.pgs);
-                const int cg = (tid - tx * 4 * g.pgs) / g.pgs;
-                const float* wp = p.dc_w[st] + ((long long)(g.ty * g.s + tx) * C + cg * 8) * C;
-                for (int c = 0; c < 8 && cg * 8 + c < C; ++c)
-                    for (int k = 0; k < C; k += 8) prefetch_l1(wp + c * C + k);
+            // phase matrices W[ty][0..s)[co][ci]: s*C*C contiguous floats, 16-byte chunks, swizzled within each row
+            float* wdst = dst + p.tile_floats;
+            const float* wsrc = p.dc_w[st] + (long long)g.ty * g.s * C * C;
+            const int cpr = C >> 2, nchunks = g.s * C * cpr;      // chunks per row, total
+            for (int e = tid; e < nchunks; e += NTHR) {
+                const int row = (C == 32) ? (e >> 3) : e / cpr, ch = e - row * cpr;
+                cp_async16(wdst + row * C + ((ch ^ ((row >> 3) & wswz)) << 2), wsrc + (long long)e * 4);
             }
         } else {
             const int r = st - p.n_dc;
@@ -118,39 +133,53 @@ __global__ void __launch_bounds__(NTHR, 2) upsample_merge_kernel(const Params p)
         }
     };
 
-    issue_load(0);
-    for (int st = 0; st < nstages; ++st) {
+    float sum[32];                         // running sums of this thread's pixel (threads < 256), all channels
+    if (total > 0) issue_load(0);
+#pragma unroll 1
+    for (int step = 0; step < total; ++step) {
         cp_async_commit_wait_all();
-        __syncthreads();                   // tile st landed; everyone is done with the other tile buffer and with s_st
-        if (st + 1 < nstages) issue_load(st + 1);
-        const float* s_x = s_tile + (st & 1) * p.sx_floats;
+        __syncthreads();                   // operands of this step landed; everyone is done with the other buffer and with s_st
+        if (step + 1 < total) issue_load(step + 1);
+        const int k = step / nstages, st = step - k * nstages;
+        int b, Y, X0;
+        unit_coords(k, b, Y, X0);
+        const int X = X0 + tid;
+        const bool owner = tid < SEG_W && X < p.W;
+        if (st == 0) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) sum[c] = 0.f;
+        }
+        const float* s_x = s_buf[step & 1];
         if (st < p.n_dc) {
             // ---------------- transpose-conv branch
             const int d = st;
             const DcGeom g = dc_geom(p, d, X0, Y);
             const int s = g.s, segp = g.segp, pgs = g.pgs, ps = p.dc_ps[d];
+            const float* s_w = s_x + p.tile_floats;
             const int items = s * 4 * pgs;
             for (int it = tid; it < items; it += NTHR) {
                 const int tx = it / (4 * pgs);
                 const int rem = it - tx * 4 * pgs;
                 const int cg = rem / pgs, pg = rem - cg * pgs;
-                if (cg * 8 >= C) continue;
+                if (cg * 8 >= C) continue;          // C is a multiple of 8
                 float acc[8][4];
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) acc[c][q] = 0.f;
-                const float* wp = p.dc_w[d] + ((long long)(g.ty * s + tx) * C + cg * 8) * C;
+                const int row0 = tx * C + cg * 8;
+                const float* wp = s_w + row0 * C;
+                const int sw = (row0 >> 3) & wswz;
                 const float* xp = s_x + pg * 4;
-#pragma unroll 1
+#pragma unroll 2
                 for (int ci = 0; ci < C; ci += 4) {
                     float4 x4[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) x4[k] = *reinterpret_cast<const float4*>(xp + (ci + k) * segp);
+                    for (int kk = 0; kk < 4; ++kk) x4[kk] = *reinterpret_cast<const float4*>(xp + (ci + kk) * segp);
+                    const int co4 = ((ci >> 2) ^ sw) << 2;
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (cg * 8 + c < C) w = __ldg(reinterpret_cast<const float4*>(wp + (long long)c * C + ci));
+                        const float4 w = *reinterpret_cast<const float4*>(wp + c * C + co4);
                         acc[c][0] = fmaf(w.x, x4[0].x, acc[c][0]); acc[c][1] = fmaf(w.x, x4[0].y, acc[c][1]);
                         acc[c][2] = fmaf(w.x, x4[0].z, acc[c][2]); acc[c][3] = fmaf(w.x, x4[0].w, acc[c][3]);
                         acc[c][0] = fmaf(w.y, x4[1].x, acc[c][0]); acc[c][1] = fmaf(w.y, x4[1].y, acc[c][1]);
@@ -172,58 +201,71 @@ __global__ void __launch_bounds__(NTHR, 2) upsample_merge_kernel(const Params p)
                 const int j = jx / s, tx = jx - j * s;
                 const float* gsrc = s_st + tx * ps + (j - g.j_begin);
                 const float* bias = p.dc_b[d];
+                const bool hb = bias != nullptr;
                 const int act = p.dc_act[d];
+                if (act == PCNN_ACT_LEAKY_RELU) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        if (c < C) {
+                            const float v = gsrc[c * segp] + (hb ? __ldg(bias + c) : 0.f);
+                            sum[c] += fmaxf(v, 0.2f * v);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        if (c < C) {
+                            const float v = gsrc[c * segp] + (hb ? __ldg(bias + c) : 0.f);
+                            sum[c] += (act == PCNN_ACT_TANH) ? tanhf(v) : v;
+                        }
+                    }
+                }
+            }
+        } else {
+            // ---------------- resize branch (tiny source in shared memory): the row interpolation is the same for the
+            // whole CTA, so it is done once ([C][iw] values into s_st); each pixel then interpolates along x only
+            const int r = st - p.n_dc;
+            const int ih = p.rs_ih[r], iw = p.rs_iw[r], taps = p.rs_taps[r];
+            for (int e = tid; e < C * iw; e += NTHR) {
+                const int c = e / iw, xs = e - c * iw;
+                const float* src = s_x + c * ih * iw + xs;
+                float acc = 0.f;
+                for (int a = 0; a < taps; ++a)
+                    acc = fmaf(src[__ldg(p.rs_iy[r] + Y * taps + a) * iw], __ldg(p.rs_wy[r] + Y * taps + a), acc);
+                s_st[e] = acc;
+            }
+            __syncthreads();
+            if (owner) {
+                int ix[4];
+                float wx[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const bool on = a < taps;
+                    ix[a] = on ? __ldg(p.rs_ix[r] + X * taps + a) : 0;
+                    wx[a] = on ? __ldg(p.rs_wx[r] + X * taps + a) : 0.f;     // unused taps: weight 0 on element 0
+                }
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
                     if (c < C) {
-                        const float v = gsrc[c * segp] + (bias ? __ldg(bias + c) : 0.f);
-                        my_sum[c * SEG_W] += (act == PCNN_ACT_LEAKY_RELU) ? fmaxf(v, 0.2f * v) : apply_act(v, act);
+                        const float* row = s_st + c * iw;
+                        float acc = row[ix[0]] * wx[0];
+                        acc = fmaf(row[ix[1]], wx[1], acc);
+                        if (taps > 2) { acc = fmaf(row[ix[2]], wx[2], acc); acc = fmaf(row[ix[3]], wx[3], acc); }
+                        sum[c] += acc;
                     }
                 }
-            }
-        } else if (owner) {
-            // ---------------- resize branch (tiny source in shared memory)
-            const int r = st - p.n_dc;
-            const int ih = p.rs_ih[r], iw = p.rs_iw[r], taps = p.rs_taps[r];
-            int iy[4], ix[4];
-            float wy[4], wx[4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const bool on = a < taps;
-                iy[a] = on ? __ldg(p.rs_iy[r] + Y * taps + a) * iw : 0;
-                wy[a] = on ? __ldg(p.rs_wy[r] + Y * taps + a) : 0.f;
-                ix[a] = on ? __ldg(p.rs_ix[r] + X * taps + a) : 0;
-                wx[a] = on ? __ldg(p.rs_wx[r] + X * taps + a) : 0.f;
-            }
-#pragma unroll 2
-            for (int c = 0; c < C; ++c) {
-                const float* src = s_x + c * ih * iw;
-                float acc = 0.f;
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    if (a < taps) {
-                        const float* row = src + iy[a];
-                        float rr = 0.f;   // TF interpolates along x first, then along y
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (q < taps) rr = fmaf(row[ix[q]], wx[q], rr);
-                        acc = fmaf(rr, wy[a], acc);
-                    }
-                }
-                my_sum[c * SEG_W] += acc;
             }
         }
-    }
+        if (st != nstages - 1 || !owner) continue;
 
     // ---------------- write-out: one pixel per thread, 16-byte units of the BLK8 layout
-    if (!owner) return;
     const int Hp = p.H + 2 * HALO, P = p.W + 2 * HALO;
     const size_t plane_px = (size_t)Hp * P;
     const size_t pix = (size_t)(Y + HALO) * P + (X + HALO);
     const int planes = (C + 7) / 8;
-    float sum[32], lo[32];
+    float lo[32];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) sum[c] = my_sum[c * SEG_W] * p.alpha;
+    for (int c = 0; c < 32; ++c) sum[c] = (c < C) ? sum[c] * p.alpha : 0.f;
 #pragma unroll
     for (int pl = 0; pl < 4; ++pl) {
         if (pl < planes) {
@@ -265,6 +307,7 @@ __global__ void __launch_bounds__(NTHR, 2) upsample_merge_kernel(const Params p)
             }
         }
     }
+    }   // step loop
 }
 
 }  // namespace um
@@ -284,28 +327,38 @@ extern "C" int pcnn_upsample_merge_blk8(int n_deconv, const float* const* dc_in,
                    "upsample_merge_blk8: between 1 and %d branches of each kind", MAXB);
     PCNN_CHECK_ARG(out && mode >= 1 && mode <= 3 && (mode == 1 || out_lo), "upsample_merge_blk8: bad destination / precision mode");
     PCNN_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && H <= 65535 && W > 0, "upsample_merge_blk8: bad shape");
-    PCNN_CHECK_ARG(C >= 4 && C <= 32 && (C % 4) == 0, "upsample_merge_blk8: channels %d must be a multiple of 4, <= 32", C);
+    PCNN_CHECK_ARG(C >= 8 && C <= 32 && (C % 8) == 0, "upsample_merge_blk8: channels %d must be a multiple of 8, <= 32", C);
     PCNN_CHECK_ARG((c_offset % 16) == 0 && c_offset + C <= ((c_total + 15) / 16) * 16, "upsample_merge_blk8: channel offset must be a multiple of 16 inside the buffer");
     Params p;
     p.n_dc = n_deconv; p.n_rs = n_resize; p.alpha = alpha;
     p.out = (__half*)out; p.out_lo = (uint8_t*)out_lo; p.mode = mode;
     p.C = C; p.H = H; p.W = W; p.c8_total = ((c_total + 15) / 16) * 2; p.plane0 = c_offset / 8;
-    int sx = 0, st = 0;
-    for (int d = 0; d < n_deconv; ++d) {
+    p.B = B;
+    // stage order: weight blocks (s*C*C floats) alternate large / small so that the two operand buffers are
+    // [largest, 3rd, 5th ...] and [smallest, ...]: the even-step buffer holds the big blocks, the odd one the small
+    int order[MAXB], nd = n_deconv;
+    for (int d = 0; d < nd; ++d) order[d] = d;
+    std::sort(order, order + nd, [&](int a, int b2) { return dc_stride[a] > dc_stride[b2]; });
+    int seq[MAXB];
+    for (int lo = 0, hi = nd - 1, k = 0; lo <= hi; ) { seq[k++] = order[lo++]; if (lo <= hi) seq[k++] = order[hi--]; }
+    int tile = 0, st = 0;
+    size_t need[2] = {0, 0};
+    for (int k = 0; k < nd; ++k) {
+        const int d = seq[k];
         const int s = dc_stride[d], ih = dc_ih[d], iw = dc_iw[d];
-        PCNN_CHECK_ARG(dc_in[d] && dc_kernel[d] && s >= 1 && s <= 64, "upsample_merge_blk8: deconv branch %d: bad argument", d);
+        PCNN_CHECK_ARG(dc_in[d] && dc_kernel[d] && s >= 1 && s <= 32, "upsample_merge_blk8: deconv branch %d: bad argument", d);
         PCNN_CHECK_ARG((reinterpret_cast<uintptr_t>(dc_kernel[d]) % 16) == 0, "upsample_merge_blk8: deconv kernel %d must be 16-byte aligned", d);
         PCNN_CHECK_ARG(ceil_div(H, s) == ih && ceil_div(W, s) == iw,
                        "upsample_merge_blk8: output (%d,%d) inconsistent with input (%d,%d) at stride %d (TF raises)", H, W, ih, iw, s);
-        p.dc_in[d] = dc_in[d]; p.dc_w[d] = dc_kernel[d]; p.dc_b[d] = dc_bias ? dc_bias[d] : nullptr;
-        p.dc_s[d] = s; p.dc_ih[d] = ih; p.dc_iw[d] = iw; p.dc_act[d] = dc_act[d];
-        p.dc_pbh[d] = std::max((ih - 1) * s + s - H, 0) / 2;
-        p.dc_pbw[d] = std::max((iw - 1) * s + s - W, 0) / 2;
+        p.dc_in[k] = dc_in[d]; p.dc_w[k] = dc_kernel[d]; p.dc_b[k] = dc_bias ? dc_bias[d] : nullptr;
+        p.dc_s[k] = s; p.dc_ih[k] = ih; p.dc_iw[k] = iw; p.dc_act[k] = dc_act[d];
+        p.dc_pbh[k] = std::max((ih - 1) * s + s - H, 0) / 2;
+        p.dc_pbw[k] = std::max((iw - 1) * s + s - W, 0) / 2;
         const int segp_max = (((SEG_W - 1) / s + 2) + 3) & ~3;           // low-res pixels touching one 256-pixel segment
         int ps = 32 * segp_max + (32 + s - 1) / s;                        // phases land ~32/s banks apart
         ps = (ps + 3) & ~3;
-        p.dc_ps[d] = ps;
-        sx = std::max(sx, 32 * segp_max);
+        p.dc_ps[k] = ps;
+        tile = std::max(tile, C * segp_max);
         st = std::max(st, s * ps);
     }
     for (int r = 0; r < n_resize; ++r) {
@@ -314,15 +367,29 @@ extern "C" int pcnn_upsample_merge_blk8(int n_deconv, const float* const* dc_in,
         PCNN_CHECK_ARG((long long)C * rs_ih[r] * rs_iw[r] <= 8192, "upsample_merge_blk8: resize source %dx%d too large for the fused kernel", rs_ih[r], rs_iw[r]);
         p.rs_in[r] = rs_in[r]; p.rs_iy[r] = rs_iy[r]; p.rs_wy[r] = rs_wy[r]; p.rs_ix[r] = rs_ix[r]; p.rs_wx[r] = rs_wx[r];
         p.rs_taps[r] = rs_taps[r]; p.rs_ih[r] = rs_ih[r]; p.rs_iw[r] = rs_iw[r];
-        sx = std::max(sx, C * rs_ih[r] * rs_iw[r]);
+        tile = std::max(tile, C * rs_ih[r] * rs_iw[r]);
+        st = std::max(st, C * rs_iw[r]);
     }
-    sx = (sx + 3) & ~3;
-    p.sx_floats = sx;
-    const size_t smem = (size_t)(32 * SEG_W + 2 * sx + st) * sizeof(float);
-    PCNN_CHECK_ARG(smem <= 200 * 1024, "upsample_merge_blk8: shared-memory plan too large (%zu bytes)", smem);
-    if (smem > 48 * 1024)
-        PCNN_CHECK_CUDA(cudaFuncSetAttribute(upsample_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    upsample_merge_kernel<<<dim3(ceil_div(W, SEG_W), H, B), NTHR, smem, (cudaStream_t)stream>>>(p);
+    tile = (tile + 3) & ~3;
+    st = (st + 3) & ~3;
+    const int nstages = n_deconv + n_resize;
+    for (int k = 0; k < nstages; ++k) {
+        const size_t w = k < nd ? (size_t)p.dc_s[k] * C * C : 0;
+        const int par = (nstages % 2 == 0) ? (k & 1) : 0;       // odd stage count: step parity drifts, both buffers get the maximum
+        need[par] = std::max(need[par], (size_t)tile + w);
+    }
+    if (nstages % 2) need[1] = need[0];
+    p.tile_floats = tile; p.st_floats = st; p.buf_floats[0] = (int)need[0]; p.buf_floats[1] = (int)need[1];
+    const size_t smem = ((size_t)st + need[0] + need[1]) * sizeof(float);
+    PCNN_CHECK_ARG(smem <= 227 * 1024, "upsample_merge_blk8: shared-memory plan too large (%zu bytes)", smem);
+    PCNN_CHECK_CUDA(cudaFuncSetAttribute(upsample_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 148;
+    PCNN_CHECK_CUDA(cudaGetDevice(&dev));
+    PCNN_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long units = (long long)B * H * ceil_div(W, SEG_W);
+    PCNN_CHECK_ARG(units < (1ll << 30), "upsample_merge_blk8: too many row segments");
+    const int grid = (int)std::min<long long>(units, sms);
+    upsample_merge_kernel<<<grid, NTHR, smem, (cudaStream_t)stream>>>(p);
     PCNN_CHECK_LAUNCH();
     return PCNN_OK;
 }

@@ -224,7 +224,7 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
 
         cat = ops.Blk8(B, 2 * F, H, Wd, dev, split=split)
         self._conv_tc(x0, "non_bottleneck_conv", ACT_LEAKY_RELU, PAD_CONSTANT, out=cat)
-        fused = (F % 4 == 0 and len(dc) <= 8 and len(rs) <= 8
+        fused = (F % 8 == 0 and len(dc) <= 8 and len(rs) <= 8
                  and all(tuple(k.shape) == (s_, s_, F, F) and s_ <= 64 for _, k, _, s_, _ in dc)
                  and all(F * h.shape[2] * h.shape[3] <= 8192 for h, _ in rs))
         if fused:

@@ -117,7 +117,7 @@ def test_conv2d_tc_chain_matches_fp32_path(ops):
     assert rel_l2(ops.from_blk8(t), a) < 2e-3
 
 
-@pytest.mark.parametrize("H,W,C,mode", [(256, 256, 32, 3), (200, 300, 32, 1), (37, 50, 8, 3), (64, 80, 12, 2)])
+@pytest.mark.parametrize("H,W,C,mode", [(256, 256, 32, 3), (200, 300, 32, 1), (37, 50, 8, 3), (64, 80, 24, 2)])
 def test_upsample_merge_blk8(ops, H, W, C, mode):
     """Fused deconv (k == stride) + resize branch sum written straight into a BLK8 concat buffer."""
     from poisson_cnn_b200.config import resize_enum
