@@ -181,8 +181,9 @@ size_t pcnn_blk8_bytes(int B, int C, int H, int W);
  * holding c_total channels (c_offset multiple of 8: this is how concat is assembled in place). */
 /* mode = precision mode of the tensor (see pcnn_conv2d_tc): 1 fp16 only; 2 second buffer = fp16
  * remainder; 3 second buffer = e4m3 planes (2c: x, 2c+1: remainder * 2^11, 16 channels each). */
+/* halo_mode: as out_halo_mode of pcnn_conv2d_tc (0 = halo untouched, SYMMETRIC = also write the mirrored ring). */
 int pcnn_to_blk8(const float* in, void* out, void* out_lo, int mode, int B, int C, int H, int W, int c_total,
-                 int c_offset, int64_t in_bstride, void* stream);
+                 int c_offset, int64_t in_bstride, int halo_mode, void* stream);
 int pcnn_from_blk8(const void* in, const void* in_lo, int mode, float* out, int B, int C, int H, int W,
                    int c_total, int c_offset, int64_t out_bstride, void* stream);
 /* tf.pad ring of width pad (<= 7) around the interior: mode PCNN_PAD_CONSTANT writes zeros,
@@ -228,12 +229,14 @@ int pcnn_upsample_merge_blk8(int n_deconv, const float* const* dc_in, const floa
  * nsplit = 3: the two correction terms are evaluated by ONE e4m3 MMA of K = 32,
  * [e4m3(x) ; e4m3(x_lo*2^11)] * [e4m3(W_lo) ; e4m3(W*2^-11)], into the same accumulator: 2x the tensor
  * work of a single pass, ~15 significand bits.  The *_lo pointers are then the fp8 "q" buffers
- * (same byte geometry as a BLK8 buffer: 16 B per pixel per plane). */
+ * (same byte geometry as a BLK8 buffer: 16 B per pixel per plane).
+ * out_halo_mode: PCNN_PAD_CONSTANT (0) leaves the halo of `out` alone; PCNN_PAD_SYMMETRIC makes the epilogue
+ * also write the 7-wide mirrored ring (tf.pad SYMMETRIC for the next layer, fused; needs H, W >= 7). */
 int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpack, const float* bias,
                    const float* bn_scale, const float* bn_shift, const void* residual,
                    const void* residual_lo, const float* out_scale, void* out, void* out_lo, int B,
                    int Cin_total, int Cout, int Cout_total, int Cres_total, int H, int W, int k, int act,
-                   int nsplit, float acc_scale, int num_sms, void* stream);
+                   int nsplit, float acc_scale, int out_halo_mode, int num_sms, void* stream);
 
 #ifdef __cplusplus
 }

@@ -41,13 +41,13 @@ SIGNATURES = {
     "pcnn_dst_sine_matrix": (c_int, [P, c_int, P]),
     "pcnn_dst_solve": (c_int, [P] * 10 + [c_int, c_int, c_int, P]),
     "pcnn_blk8_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "pcnn_to_blk8": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, P]),
+    "pcnn_to_blk8": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_int, P]),
     "pcnn_from_blk8": (c_int, [P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, P]),
     "pcnn_blk8_halo_fill": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "pcnn_conv_tc_packed_weight_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "pcnn_conv_tc_channel_slots": (c_int, [c_int, c_int]),
     "pcnn_conv_tc_pack_weights": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_float, P]),
-    "pcnn_conv2d_tc": (c_int, [P] * 11 + [c_int] * 10 + [c_float, c_int, P]),
+    "pcnn_conv2d_tc": (c_int, [P] * 11 + [c_int] * 10 + [c_float, c_int, c_int, P]),
     "pcnn_upsample_merge_blk8": (c_int, [c_int, P, P, P, P, P, P, P, c_int, P, P, P, P, P, P, P, P, c_float, P, P,
                                          c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "pcnn_dbcnn_expand_blk8": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),

@@ -31,6 +31,7 @@
 //   alloc), 3..10 = epilogue (TMEM lane quarter = warp % 4, two warps per quarter split the columns).
 //   Two 256-column accumulators in TMEM let the epilogue of tile t overlap the MMAs of tile t+1.
 #include <cuda_fp16.h>
+#include <climits>
 #include <cstdlib>
 #include <cuda_fp8.h>
 
@@ -78,6 +79,7 @@ struct Params {
     int tiles_x, tiles_y, num_tiles;
     int row_slots;           // ring of input-row slots (>= kh+RT-1)
     int w_stages;
+    int halo_sym;            // 1: the epilogue also writes the SYMMETRIC (edge-repeating mirror) halo ring of width 7 of `out`
     int n_epi;               // active epilogue warps: 8, or 4 when shared memory is needed for operands (large k)
     int debug;               // PCNN_TC_DEBUG bit 0: epilogue skips math and stores (timing experiments only)
     int w_resident;          // 1: all nv*kw weight stages fit in shared memory -> loaded once per CTA, reused by every tile
@@ -415,11 +417,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
             // pixel side: per octet, pixel index of (row y, x = x0 + px) within a plane, and validity
             size_t o_pix[2];
             bool o_ok[2];
+            int o_dy[2][2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int y = ty * RT + o_r[e];
                 o_ok[e] = (y < p.H) && (o_pl[e] < planes_out);
                 o_pix[e] = (size_t)(y + HALO) * p.P + (x0 + px + HALO);
+                o_dy[e][0] = (p.halo_sym && y < HALO) ? -(2 * y + 1) : 0;                       // row displacement of the top mirror
+                o_dy[e][1] = (p.halo_sym && y >= p.H - HALO && y < p.H) ? 2 * (p.H - y) - 1 : 0;  // ... and of the bottom mirror
             }
             uint4 rh[2], rl[2];
             auto load_residual = [&](int ch) {
@@ -531,21 +536,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                     __syncwarp();
                     // ---- pixel side: gather this pixel's two octets and store 16-byte units
                     const int xo = ch * CHUNK_PX;
-                    const bool xok = x0 + xo + px < p.W;
+                    const int x = x0 + xo + px;
+                    const bool xok = x < p.W;
+                    uint4 hi[2], lo[2];
                     uint2 q8[2], l8[2];
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const uint4 a = *reinterpret_cast<const uint4*>(px_row + 4 * ((uint32_t)(2 * (2 * oc + e)) ^ px_sw));
                         const uint4 c = *reinterpret_cast<const uint4*>(px_row + 4 * ((uint32_t)(2 * (2 * oc + e) + 1) ^ px_sw));
-                        const uint4 hi = make_uint4(__byte_perm(a.x, a.y, 0x5410), __byte_perm(a.z, a.w, 0x5410),
-                                                    __byte_perm(c.x, c.y, 0x5410), __byte_perm(c.z, c.w, 0x5410));
-                        const bool ok = o_ok[e] && xok;
-                        const size_t pix = o_pix[e] + xo;
-                        if (ok) *reinterpret_cast<uint4*>(p.out + (((size_t)b * p.c8_out + o_pl[e]) * plane_px + pix) * 8) = hi;
+                        hi[e] = make_uint4(__byte_perm(a.x, a.y, 0x5410), __byte_perm(a.z, a.w, 0x5410),
+                                           __byte_perm(c.x, c.y, 0x5410), __byte_perm(c.z, c.w, 0x5410));
                         if (mode == 2) {
-                            const uint4 lo = make_uint4(__byte_perm(a.x, a.y, 0x7632), __byte_perm(a.z, a.w, 0x7632),
-                                                        __byte_perm(c.x, c.y, 0x7632), __byte_perm(c.z, c.w, 0x7632));
-                            if (ok) *reinterpret_cast<uint4*>(p.out_lo + (((size_t)b * p.c8_out + o_pl[e]) * plane_px + pix) * 8) = lo;
+                            lo[e] = make_uint4(__byte_perm(a.x, a.y, 0x7632), __byte_perm(a.z, a.w, 0x7632),
+                                               __byte_perm(c.x, c.y, 0x7632), __byte_perm(c.z, c.w, 0x7632));
                         } else if (mode == 3) {
                             const uint32_t t01 = __byte_perm(a.x, a.y, 0x7362), t23 = __byte_perm(a.z, a.w, 0x7362);
                             const uint32_t t45 = __byte_perm(c.x, c.y, 0x7362), t67 = __byte_perm(c.z, c.w, 0x7362);
@@ -553,24 +556,54 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                             l8[e] = make_uint2(__byte_perm(t01, t23, 0x7632), __byte_perm(t45, t67, 0x7632));
                         }
                     }
-                    if (mode == 3) {
-                        uint8_t* dq = reinterpret_cast<uint8_t*>(p.out_lo);
-                        if (CP >= 16) {
-                            // both octets belong to one row and one 16-channel group: planes (2g, 2g+1) -> 16-byte stores
-                            if (o_ok[0] && xok) {
-                                const size_t base = (((size_t)b * p.c8_out + o_pl[0]) * plane_px + o_pix[0] + xo) * 16;
-                                *reinterpret_cast<uint4*>(dq + base) = make_uint4(q8[0].x, q8[0].y, q8[1].x, q8[1].y);
-                                *reinterpret_cast<uint4*>(dq + base + plane_px * 16) = make_uint4(l8[0].x, l8[0].y, l8[1].x, l8[1].y);
-                            }
-                        } else {
-                            // CP = 8: an octet is a whole row of 8 channels; bytes 8..15 of its pixel are channel padding
+                    // stores of both octets at a pixel displacement: (0,0) is the pixel itself, the others are its
+                    // SYMMETRIC mirror images in the halo ring (fused tf.pad for the next layer; border pixels only)
+                    auto emit = [&](bool ok0, bool ok1, long long d0, long long d1) {
+                        const bool oks[2] = {ok0, ok1};
+                        const long long ds[2] = {d0, d1};
 #pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                if (o_ok[e] && xok) {
-                                    const size_t base = (((size_t)b * p.c8_out) * plane_px + o_pix[e] + xo) * 16;
-                                    *reinterpret_cast<uint4*>(dq + base) = make_uint4(q8[e].x, q8[e].y, 0u, 0u);
-                                    *reinterpret_cast<uint4*>(dq + base + plane_px * 16) = make_uint4(l8[e].x, l8[e].y, 0u, 0u);
+                        for (int e = 0; e < 2; ++e) {
+                            if (oks[e]) {
+                                const size_t off = (((size_t)b * p.c8_out + o_pl[e]) * plane_px + (size_t)((long long)(o_pix[e] + xo) + ds[e])) * 8;
+                                *reinterpret_cast<uint4*>(p.out + off) = hi[e];
+                                if (mode == 2) *reinterpret_cast<uint4*>(p.out_lo + off) = lo[e];
+                            }
+                        }
+                        if (mode == 3) {
+                            uint8_t* dq = reinterpret_cast<uint8_t*>(p.out_lo);
+                            if (CP >= 16) {
+                                // both octets belong to one row and one 16-channel group: planes (2g, 2g+1) -> 16-byte stores
+                                if (ok0) {
+                                    const size_t base = (((size_t)b * p.c8_out + o_pl[0]) * plane_px + (size_t)((long long)(o_pix[0] + xo) + d0)) * 16;
+                                    *reinterpret_cast<uint4*>(dq + base) = make_uint4(q8[0].x, q8[0].y, q8[1].x, q8[1].y);
+                                    *reinterpret_cast<uint4*>(dq + base + plane_px * 16) = make_uint4(l8[0].x, l8[0].y, l8[1].x, l8[1].y);
                                 }
+                            } else {
+                                // CP = 8: an octet is a whole row of 8 channels; bytes 8..15 of its pixel are channel padding
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    if (oks[e]) {
+                                        const size_t base = (((size_t)b * p.c8_out) * plane_px + (size_t)((long long)(o_pix[e] + xo) + ds[e])) * 16;
+                                        *reinterpret_cast<uint4*>(dq + base) = make_uint4(q8[e].x, q8[e].y, 0u, 0u);
+                                        *reinterpret_cast<uint4*>(dq + base + plane_px * 16) = make_uint4(l8[e].x, l8[e].y, 0u, 0u);
+                                    }
+                                }
+                            }
+                        }
+                    };
+                    emit(o_ok[0] && xok, o_ok[1] && xok, 0, 0);
+                    if (p.halo_sym && xok) {
+                        // mirror displacements: rows -(2y+1) (top ring) / 2(H-y)-1 (bottom ring), columns likewise
+                        const int dxm[3] = {0, (x < HALO) ? -(2 * x + 1) : 0, (x >= p.W - HALO) ? 2 * (p.W - x) - 1 : 0};
+                        const bool any_y = (o_ok[0] && (o_dy[0][0] | o_dy[0][1])) || (o_ok[1] && (o_dy[1][0] | o_dy[1][1]));
+                        if (any_y || dxm[1] || dxm[2]) {
+#pragma unroll 1
+                            for (int t = 1; t < 9; ++t) {
+                                const int ai = t / 3, ci = t - 3 * ai;
+                                if (ci && !dxm[ci]) continue;
+                                const int dy0 = ai ? o_dy[0][ai - 1] : 0, dy1 = ai ? o_dy[1][ai - 1] : 0;
+                                const bool k0 = o_ok[0] && (!ai || dy0), k1 = o_ok[1] && (!ai || dy1);
+                                if (k0 || k1) emit(k0, k1, (long long)dy0 * p.P + dxm[ci], (long long)dy1 * p.P + dxm[ci]);
                             }
                         }
                     }
@@ -625,11 +658,26 @@ __global__ void pack_weights_kernel(const float* __restrict__ k, __half* __restr
     }
 }
 
+// calls fn(pixel index within a padded plane) for interior pixel (y,x) and, with halo_sym, for its SYMMETRIC mirror
+// images in the 7-wide halo ring (only border pixels have any)
+template <class F>
+__device__ __forceinline__ void mirror_targets(int y, int x, int H, int W, int P, int halo_sym, F&& fn) {
+    fn((size_t)(y + HALO) * P + (x + HALO));
+    if (!halo_sym) return;
+    const int ys[3] = {y, (y < HALO) ? -1 - y : INT_MIN, (y >= H - HALO) ? 2 * H - 1 - y : INT_MIN};
+    const int xs[3] = {x, (x < HALO) ? -1 - x : INT_MIN, (x >= W - HALO) ? 2 * W - 1 - x : INT_MIN};
+#pragma unroll 1
+    for (int t = 1; t < 9; ++t) {
+        const int yy = ys[t / 3], xx = xs[t % 3];
+        if (yy != INT_MIN && xx != INT_MIN) fn((size_t)(yy + HALO) * P + (xx + HALO));
+    }
+}
+
 // NCHW fp32 -> BLK8 fp16 interior (planes [plane0, plane0 + ceil(C/8))).  grid (ceil(W/128), H, B*np): no
 // per-element div/mod; each thread reads 8 channel planes (coalesced along x) and writes one 16-byte pixel.
 __global__ void __launch_bounds__(128) to_blk8_kernel(const float* __restrict__ in, __half* __restrict__ out,
                                                       __half* __restrict__ out_lo, int C, int H, int W, int Hp, int P,
-                                                      int c8_total, int plane0, long long in_bstride, int np) {
+                                                      int c8_total, int plane0, long long in_bstride, int np, int halo_sym) {
     const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
     const int b = blockIdx.z / np, pl = blockIdx.z - b * np;
@@ -642,14 +690,17 @@ __global__ void __launch_bounds__(128) to_blk8_kernel(const float* __restrict__ 
         h[e] = __float2half_rn(f);
         l[e] = __float2half_rn(f - __half2float(h[e]));
     }
-    const size_t off = ((((size_t)b * c8_total + plane0 + pl) * Hp + (y + HALO)) * P + (x + HALO)) * 8;
-    *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(h);
-    if (out_lo) *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(l);
+    const size_t plane = ((size_t)b * c8_total + plane0 + pl) * Hp * P;
+    const uint4 hv = *reinterpret_cast<const uint4*>(h), lv = *reinterpret_cast<const uint4*>(l);
+    mirror_targets(y, x, H, W, P, halo_sym, [&](size_t pix) {
+        *reinterpret_cast<uint4*>(out + (plane + pix) * 8) = hv;
+        if (out_lo) *reinterpret_cast<uint4*>(out_lo + (plane + pix) * 8) = lv;
+    });
 }
 
 // mode 3 companion of to_blk8: fp8 planes 2c = e4m3(x), 2c+1 = e4m3((x - fp16(x)) * 2^11), 16 channels each
 __global__ void __launch_bounds__(128) to_q8_kernel(const float* __restrict__ in, uint8_t* __restrict__ outq, int C, int H,
-                                                    int W, int Hp, int P, int c8_total, int plane0, long long in_bstride, int nc) {
+                                                    int W, int Hp, int P, int c8_total, int plane0, long long in_bstride, int nc, int halo_sym) {
     const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
     const int b = blockIdx.z / nc, cc = blockIdx.z - b * nc;
@@ -662,10 +713,12 @@ __global__ void __launch_bounds__(128) to_q8_kernel(const float* __restrict__ in
         a8[e] = to_e4m3(f);
         l8[e] = to_e4m3((f - __half2float(__float2half_rn(f))) * LO_SCALE);
     }
-    const size_t off0 = ((((size_t)b * c8_total + plane0 + 2 * cc) * Hp + (y + HALO)) * P + (x + HALO)) * 16;
-    const size_t off1 = off0 + (size_t)Hp * P * 16;
-    *reinterpret_cast<uint4*>(outq + off0) = *reinterpret_cast<const uint4*>(a8);
-    *reinterpret_cast<uint4*>(outq + off1) = *reinterpret_cast<const uint4*>(l8);
+    const size_t plane = ((size_t)b * c8_total + plane0 + 2 * cc) * Hp * P;
+    const uint4 av = *reinterpret_cast<const uint4*>(a8), lv = *reinterpret_cast<const uint4*>(l8);
+    mirror_targets(y, x, H, W, P, halo_sym, [&](size_t pix) {
+        *reinterpret_cast<uint4*>(outq + (plane + pix) * 16) = av;
+        *reinterpret_cast<uint4*>(outq + (plane + pix + (size_t)Hp * P) * 16) = lv;
+    });
 }
 
 // BLK8 fp16 (+ remainder buffer) -> NCHW fp32.  grid (ceil(W/128), H, B*np): one 16-byte pixel read per thread,
@@ -828,17 +881,20 @@ extern "C" int pcnn_conv_tc_pack_weights(const float* kernel, void* packed, int 
 }
 
 extern "C" int pcnn_to_blk8(const float* in, void* out, void* out_lo, int mode, int B, int C, int H, int W, int c_total, int c_offset,
-                            int64_t in_bstride, void* stream) {
+                            int64_t in_bstride, int halo_mode, void* stream) {
+    PCNN_CHECK_ARG(halo_mode == PCNN_PAD_CONSTANT || (halo_mode == PCNN_PAD_SYMMETRIC && H >= HALO && W >= HALO),
+                   "to_blk8: halo_mode must be 0 (halo untouched) or SYMMETRIC on a map of at least 7x7");
+    const int hsym = halo_mode == PCNN_PAD_SYMMETRIC;
     PCNN_CHECK_ARG(mode >= 1 && mode <= 3 && (mode == 1 || out_lo), "to_blk8: precision mode 2/3 needs the second buffer");
     PCNN_CHECK_ARG(mode != 3 || (c_offset % 16) == 0, "to_blk8: mode 3 needs a channel offset that is a multiple of 16");
     PCNN_CHECK_ARG(in && out && B > 0 && C > 0 && (c_offset % 8) == 0 && c_offset + C <= ((c_total + 15) / 16) * 16, "to_blk8: bad argument");
     const int c8_total = ((c_total + 15) / 16) * 2;
     const int np = (C + 7) / 8, nc = (C + 15) / 16;
     PCNN_CHECK_ARG(H <= 65535 && (long long)B * np <= 65535, "to_blk8: grid too large (H %d, B*planes %lld)", H, (long long)B * np);
-    to_blk8_kernel<<<dim3(ceil_div(W, 128), H, B * np), 128, 0, (cudaStream_t)stream>>>(in, (__half*)out, mode == 2 ? (__half*)out_lo : nullptr, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, in_bstride, np);
+    to_blk8_kernel<<<dim3(ceil_div(W, 128), H, B * np), 128, 0, (cudaStream_t)stream>>>(in, (__half*)out, mode == 2 ? (__half*)out_lo : nullptr, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, in_bstride, np, hsym);
     PCNN_CHECK_LAUNCH();
     if (mode == 3) {
-        to_q8_kernel<<<dim3(ceil_div(W, 128), H, B * nc), 128, 0, (cudaStream_t)stream>>>(in, (uint8_t*)out_lo, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, in_bstride, nc);
+        to_q8_kernel<<<dim3(ceil_div(W, 128), H, B * nc), 128, 0, (cudaStream_t)stream>>>(in, (uint8_t*)out_lo, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, in_bstride, nc, hsym);
         PCNN_CHECK_LAUNCH();
     }
     return PCNN_OK;
@@ -883,7 +939,7 @@ extern "C" int pcnn_dbcnn_expand_blk8(const float* h, const float* sinh_basis, c
 extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpack, const float* bias, const float* bn_scale,
                               const float* bn_shift, const void* residual, const void* residual_lo, const float* out_scale,
                               void* out, void* out_lo, int B, int Cin_total, int Cout, int Cout_total, int Cres_total,
-                              int H, int W, int k, int act, int nsplit, float acc_scale, int num_sms, void* stream) {
+                              int H, int W, int k, int act, int nsplit, float acc_scale, int out_halo_mode, int num_sms, void* stream) {
     PCNN_CHECK_ARG(in && wpack && out, "conv2d_tc: null pointer");
     PCNN_CHECK_ARG(nsplit >= 1 && nsplit <= 3, "conv2d_tc: precision mode must be 1, 2 or 3");
     if (nsplit >= 2) PCNN_CHECK_ARG(in_lo && out_lo && (!residual || residual_lo), "conv2d_tc: split precision needs the lo buffers");
@@ -891,6 +947,8 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
     PCNN_CHECK_ARG(Cout >= 1 && Cout <= 32 && Cout <= Cout_total, "conv2d_tc: Cout %d not in [1,32]", Cout);
     PCNN_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cin_total > 0, "conv2d_tc: bad shape");
     PCNN_CHECK_ARG((bn_scale == nullptr) == (bn_shift == nullptr), "conv2d_tc: bn_scale/bn_shift must come together");
+    PCNN_CHECK_ARG(out_halo_mode == PCNN_PAD_CONSTANT || (out_halo_mode == PCNN_PAD_SYMMETRIC && H >= HALO && W >= HALO),
+                   "conv2d_tc: out_halo_mode must be 0 (halo untouched) or SYMMETRIC on a map of at least 7x7");
     Params p;
     p.in = (const __half*)in; p.in_lo = (const __half*)in_lo; p.wpack = (const __half*)wpack; p.bias = bias;
     p.bn_scale = bn_scale; p.bn_shift = bn_shift;
@@ -900,7 +958,7 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
     p.c16 = (Cin_total + 15) / 16;
     p.nv = p.c16 * (nsplit == 2 ? 3 : (nsplit == 3 ? 2 : 1));
     p.c8_in = p.c16 * 2; p.c8_out = ((Cout_total + 15) / 16) * 2; p.c8_res = ((Cres_total + 15) / 16) * 2;
-    p.cout = Cout; p.kh = k; p.kw = k; p.pad = k / 2; p.act = act;
+    p.cout = Cout; p.kh = k; p.kw = k; p.pad = k / 2; p.act = act; p.halo_sym = (out_halo_mode == PCNN_PAD_SYMMETRIC);
     const int cp = choose_cp(Cout, k), rt = M_TILE / cp, zpad = rt - 1;
     p.n_tile = W >= 256 ? 256 : ((W + 15) / 16) * 16;
     p.tiles_x = ceil_div(W, p.n_tile); p.tiles_y = ceil_div(H, rt);

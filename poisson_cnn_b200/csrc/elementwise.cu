@@ -2,6 +2,7 @@
 // with fused merge accumulation, spatial pyramid pooling, Dense, per-sample max-normalisation and
 // the model glue (input assembly, sinh-mode expansion, boundary ring, oriented 5-way merge).
 // All fp32, NCHW, coalesced along W; reductions use warp shuffles.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cmath>
@@ -37,23 +38,45 @@ __global__ void __launch_bounds__(128) avgpool_thread_kernel(const float* __rest
     out[((long long)blockIdx.z * oh + oy) * ow + ox] = acc / (float)((ye - ys) * (xe - xs));
 }
 
-// Large windows: one warp per output, lanes stride the window columns (coalesced rows).
-// grid (ceil(ow/8), oh, B*C), 8 warps per CTA.
-__global__ void __launch_bounds__(256) avgpool_warp_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
+// Large windows (s >= 8): a CTA owns one (sample, channel) plane and a band of output rows.  Per output row the
+// window rows are first reduced to per-column sums (one column per thread, fully coalesced reads, the row loop
+// unrolled so that several loads are in flight), then each warp reduces whole windows out of shared memory.
+// grid (ceil(oh/rows_per_cta), B*C), 256 threads, W floats of shared memory.
+__global__ void __launch_bounds__(256) avgpool_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
                                                            int H, int W, int oh, int ow, int s, int pt, int pl,
-                                                           long long in_bstride) {
-    const int lane = threadIdx.x & 31;
-    const int ox = blockIdx.x * 8 + (threadIdx.x >> 5), oy = blockIdx.y;
-    if (ox >= ow) return;
-    const int b = blockIdx.z / C, c = blockIdx.z - b * C;
-    const int ys = max(oy * s - pt, 0), ye = min(oy * s - pt + s, H);
-    const int xs = max(ox * s - pl, 0), xe = min(ox * s - pl + s, W);
+                                                           long long in_bstride, int rows_per_cta) {
+    extern __shared__ float colsum[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y / C, c = blockIdx.y - b * C;
     const float* src = in + (long long)b * in_bstride + (long long)c * H * W;
-    float acc = 0.f;
-    for (int y = ys; y < ye; ++y)
-        for (int x = xs + lane; x < xe; x += 32) acc += __ldg(src + (long long)y * W + x);
-    acc = warp_sum(acc);
-    if (lane == 0) out[((long long)blockIdx.z * oh + oy) * ow + ox] = acc / (float)((ye - ys) * (xe - xs));
+    for (int r = 0; r < rows_per_cta; ++r) {
+        const int oy = blockIdx.x * rows_per_cta + r;
+        if (oy >= oh) break;                                  // block-uniform
+        const int ys = max(oy * s - pt, 0), ye = min(oy * s - pt + s, H);
+        for (int x = threadIdx.x; x < W; x += 256) {
+            const float* col = src + (long long)ys * W + x;
+            float acc = 0.f;
+            int y = ys;
+            for (; y + 8 <= ye; y += 8, col += 8ll * W) {
+                float v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = __ldg(col + (long long)k * W);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc += v[k];
+            }
+            for (; y < ye; ++y, col += W) acc += __ldg(col);
+            colsum[x] = acc;
+        }
+        __syncthreads();
+        for (int ox = warp; ox < ow; ox += 8) {
+            const int xs = max(ox * s - pl, 0), xe = min(ox * s - pl + s, W);
+            float acc = 0.f;
+            for (int x = xs + lane; x < xe; x += 32) acc += colsum[x];
+            acc = warp_sum(acc);
+            if (lane == 0) out[((long long)blockIdx.y * oh + oy) * ow + ox] = acc / (float)((ye - ys) * (xe - xs));
+        }
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------ transpose conv (SAME)
@@ -460,7 +483,9 @@ extern "C" int pcnn_avgpool_same_f32(const float* in, float* out, int B, int C, 
     if (s <= 4) {
         avgpool_thread_kernel<<<dim3(ceil_div(ow, 128), oh, B * C), 128, 0, (cudaStream_t)stream>>>(in, out, C, H, W, oh, ow, s, pt, pl, in_bstride);
     } else {
-        avgpool_warp_kernel<<<dim3(ceil_div(ow, 8), oh, B * C), 256, 0, (cudaStream_t)stream>>>(in, out, C, H, W, oh, ow, s, pt, pl, in_bstride);
+        PCNN_CHECK_ARG(W <= 12288, "avgpool_same_f32: rows wider than 12288 are not supported for s > 4");
+        const int rows_per_cta = std::max(1, 32 / s);          // >= 32 input rows per CTA
+        avgpool_rows_kernel<<<dim3(ceil_div(oh, rows_per_cta), B * C), 256, (size_t)W * sizeof(float), (cudaStream_t)stream>>>(in, out, C, H, W, oh, ow, s, pt, pl, in_bstride, rows_per_cta);
     }
     PCNN_CHECK_LAUNCH();
     return PCNN_OK;

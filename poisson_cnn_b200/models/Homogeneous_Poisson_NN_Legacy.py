@@ -172,15 +172,17 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
             ops.resize(h, out_hw, blk.resize_method, alpha, out=merged, accumulate=not first)
 
     # ------------------------------------------------------------------ tensor-core building blocks
-    def _conv_tc(self, x, name, act, pad, bn_name=None, residual=None, out_scale=None, out=None, out_c_offset=0):
+    def _conv_tc(self, x, name, act, pad, bn_name=None, residual=None, out_scale=None, out=None, out_c_offset=0,
+                 next_pad=PAD_CONSTANT):
+        """next_pad: padding mode of the layer that reads the result (a SYMMETRIC ring is written by this conv's epilogue)."""
         wp, bias = self.tc_conv(name)
         return ops.conv2d_tc(x, wp, bias, act, pad, bn=self.bn(bn_name) if bn_name else None, residual=residual,
-                             out_scale=out_scale, out=out, out_c_offset=out_c_offset)
+                             out_scale=out_scale, out=out, out_c_offset=out_c_offset, out_halo=next_pad)
 
-    def _resnet_tc(self, x, name, act, pad, use_bn, out_scale=None):
-        t = self._conv_tc(x, name + "/conv0", act, pad, name + "/bn0" if use_bn else None)
-        t = self._conv_tc(t, name + "/conv1", act, pad, name + "/bn1" if use_bn else None, residual=x)
-        return self._conv_tc(t, name + "/conv2", act, pad, out_scale=out_scale)
+    def _resnet_tc(self, x, name, act, pad, use_bn, out_scale=None, next_pad=PAD_CONSTANT):
+        t = self._conv_tc(x, name + "/conv0", act, pad, name + "/bn0" if use_bn else None, next_pad=pad)
+        t = self._conv_tc(t, name + "/conv1", act, pad, name + "/bn1" if use_bn else None, residual=x, next_pad=pad)
+        return self._conv_tc(t, name + "/conv2", act, pad, out_scale=out_scale, next_pad=next_pad)
 
     def _tc_ok(self, ksize, pad_value=0.0):
         return ksize % 2 == 1 and ksize <= 15 and float(pad_value) == 0.0
@@ -194,10 +196,11 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
         dev = rhs.device
         x = ops.hpnn_input(rhs) if self.use_positional_embeddings else rhs
         split = self.tc_split
-        t = ops.to_blk8(x, split=split)
+        t = ops.to_blk8(x, split=split, halo=self.pre_pad)
         for k in range(self.n_pre):
             t = self._conv_tc(t, "pre_bottleneck/%d" % k, self.pre_act, self.pre_pad,
-                              "pre_bottleneck/%d/bn" % k if self.use_batchnorm else None)
+                              "pre_bottleneck/%d/bn" % k if self.use_batchnorm else None,
+                              next_pad=self.pre_pad if k + 1 < self.n_pre else PAD_CONSTANT)
         x0 = t                                   # BLK8, F channels
         x0_f32 = ops.from_blk8(x0)               # pooling pyramid reads NCHW fp32
 
@@ -209,10 +212,11 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
             ph, pw = -(-H // blk.downsampling_factor), -(-Wd // blk.downsampling_factor)
             name = "bottleneck_%s/%d" % (blk.kind, blk.index)
             if blk.kind == "deconv" and min(ph, pw) >= 16:
-                h = ops.to_blk8(ops.avgpool_same(x0_f32, blk.downsampling_factor), split=split)
-                h = self._conv_tc(h, name + "/conv0", blk.act, blk.pad)
+                h = ops.to_blk8(ops.avgpool_same(x0_f32, blk.downsampling_factor), split=split, halo=blk.pad)
+                h = self._conv_tc(h, name + "/conv0", blk.act, blk.pad, next_pad=blk.pad)
                 for r in range(1, blk.n_convs):
-                    h = self._resnet_tc(h, "%s/resnet%d" % (name, r), blk.act, blk.pad, blk.use_batchnorm)
+                    h = self._resnet_tc(h, "%s/resnet%d" % (name, r), blk.act, blk.pad, blk.use_batchnorm,
+                                        next_pad=blk.pad if r + 1 < blk.n_convs else PAD_CONSTANT)
                 h = ops.from_blk8(h)
             else:
                 h = self._bottleneck_lowres(blk, x0_f32)

@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 from ._lib import lib, check
-from .config import (ACT_LINEAR, PAD_CONSTANT, RESIZE_NEAREST, RESIZE_BILINEAR, RESIZE_BICUBIC)
+from .config import (ACT_LINEAR, PAD_CONSTANT, PAD_SYMMETRIC, RESIZE_NEAREST, RESIZE_BILINEAR, RESIZE_BICUBIC)
 
 POOL_AVG, POOL_MAX = 0, 1
 BC_DIRICHLET, BC_NEUMANN = 0, 1
@@ -430,14 +430,13 @@ _BLK8_POOL = {}     # (device, B, C, H, W) -> [buffer]: recycled buffers keep th
 
 
 def _blk8_buffer(key, nbytes, device):
+    """(buffer, halo state).  Recycled buffers come back with whatever their halo held when they were released
+    (zeros from allocation, or a mirrored ring): the consumer-side check in blk8_halo_fill refreshes it only if
+    the next user needs something else, so steady-state inference neither allocates nor refills."""
     pool = _BLK8_POOL.get(key)
     if pool:
-        buf, dirty_halo = pool.pop()
-        if dirty_halo:                  # a mirrored halo from the previous user: back to zeros (halo only)
-            _, B, C, H, W, _ = key
-            check(lib.pcnn_blk8_halo_fill(_p(buf), B, C, H, W, 7, PAD_CONSTANT, _stream()), "blk8_halo_fill")
-        return buf
-    return torch.zeros(nbytes // 2, dtype=torch.float16, device=device)
+        return pool.pop()
+    return torch.zeros(nbytes // 2, dtype=torch.float16, device=device), (PAD_CONSTANT, 7)
 
 
 class Blk8:
@@ -446,12 +445,13 @@ class Blk8:
     fp16 rounding remainder (x = hi + lo, ~22 bits); 3 a second buffer of e4m3 planes (e4m3(x) and
     e4m3((x-hi)*2^11), 16 channels per plane) feeding the single fp8 correction MMA.
     `halo` records what the halo currently holds: (PAD_CONSTANT, 7) after allocation, (mode, pad) after a
-    halo fill, (mode, -1) when a mirrored halo went stale.  Buffers are recycled through a pool keyed by
-    the exact shape, so steady-state inference neither allocates nor re-zeroes them."""
+    halo fill or a producer that wrote the mirrored ring itself, (mode, -1) when a mirrored halo went stale.
+    Buffers are recycled (with their halo state) through a pool keyed by the exact shape, so steady-state
+    inference neither allocates nor refills them."""
 
     __slots__ = ("buf", "lo", "mode", "B", "C", "H", "W", "halo", "_key", "_key_lo")
 
-    def __init__(self, B, C, H, W, device, split=False):
+    def __init__(self, B, C, H, W, device, split=False, sym=False):
         nbytes = lib.pcnn_blk8_bytes(B, C, H, W)
         if nbytes == 0:
             raise ValueError("Blk8: bad shape")
@@ -459,20 +459,23 @@ class Blk8:
         if self.mode not in (1, 2, 3):
             raise ValueError("Blk8: precision mode must be 1, 2 or 3")
         # hi and lo/q buffers never trade places: bytes one role leaves untouched (channel padding) must stay zero
-        self._key = (str(device), B, C, H, W, "hi")
-        self._key_lo = (str(device), B, C, H, W, "lo%d" % self.mode)
-        self.buf = _blk8_buffer(self._key, nbytes, device)
-        self.lo = _blk8_buffer(self._key_lo, nbytes, device) if self.mode >= 2 else None
+        # ... and tensors whose producer writes a mirrored ring recycle among themselves (no refills in steady state)
+        self._key = (str(device), B, C, H, W, "hi", bool(sym))
+        self._key_lo = (str(device), B, C, H, W, "lo%d" % self.mode, bool(sym))
+        self.buf, st = _blk8_buffer(self._key, nbytes, device)
+        self.lo = None
+        if self.mode >= 2:
+            self.lo, st_lo = _blk8_buffer(self._key_lo, nbytes, device)
+            if st_lo != st:
+                st = (st[0] if st[0] != PAD_CONSTANT else st_lo[0], -1)      # the two buffers disagree: stale
         self.B, self.C, self.H, self.W = B, C, H, W
-        self.halo = (PAD_CONSTANT, 7)
+        self.halo = st
 
     def __del__(self):
         try:
-            # a mirrored halo must not leak into the next user: such buffers are re-zeroed on reuse
-            dirty = self.halo[0] != PAD_CONSTANT
-            _BLK8_POOL.setdefault(self._key, []).append((self.buf, dirty))
+            _BLK8_POOL.setdefault(self._key, []).append((self.buf, self.halo))
             if self.lo is not None:
-                _BLK8_POOL.setdefault(self._key_lo, []).append((self.lo, dirty))
+                _BLK8_POOL.setdefault(self._key_lo, []).append((self.lo, self.halo))
         except Exception:
             pass
 
@@ -501,16 +504,26 @@ def blk8_pool_clear():
     _BLK8_POOL.clear()
 
 
-def to_blk8(x, out=None, c_total=None, c_offset=0, split=False):
-    """NCHW fp32 -> BLK8 (optionally into channels [c_offset, c_offset+C) of a wider buffer)."""
+def _fusable_halo(mode, H, W):
+    """SYMMETRIC rings can be written by the producer itself when the map is at least 7x7."""
+    return int(mode) == PAD_SYMMETRIC and H >= 7 and W >= 7
+
+
+def to_blk8(x, out=None, c_total=None, c_offset=0, split=False, halo=PAD_CONSTANT):
+    """NCHW fp32 -> BLK8 (optionally into channels [c_offset, c_offset+C) of a wider buffer).
+    halo=PAD_SYMMETRIC also writes the mirrored 7-wide ring (the padding of the layer that reads the tensor)."""
     in_bs = _nchw_bstride(x, "x")
     B, C, H, W = x.shape
     if out is None:
-        out = Blk8(B, c_total or C, H, W, x.device, split=split)
+        out = Blk8(B, c_total or C, H, W, x.device, split=split, sym=_fusable_halo(halo, H, W))
     if (out.B, out.H, out.W) != (B, H, W):
         raise ValueError("to_blk8: destination shape mismatch")
-    check(lib.pcnn_to_blk8(_p(x), _p(out.buf), _p(out.lo), out.mode, B, C, H, W, out.C, int(c_offset), in_bs, _stream()), "to_blk8")
-    if out.halo[0] != PAD_CONSTANT:
+    fused = _fusable_halo(halo, H, W) and (out.C + 15) // 16 == (C + 15) // 16 and c_offset == 0
+    check(lib.pcnn_to_blk8(_p(x), _p(out.buf), _p(out.lo), out.mode, B, C, H, W, out.C, int(c_offset), in_bs,
+                           PAD_SYMMETRIC if fused else PAD_CONSTANT, _stream()), "to_blk8")
+    if fused:
+        out.halo = (PAD_SYMMETRIC, 7)
+    elif out.halo[0] != PAD_CONSTANT:
         out.halo = (out.halo[0], -1)
     return out
 
@@ -530,8 +543,8 @@ def blk8_halo_fill(t, pad, mode):
     cur_mode, cur_pad = t.halo
     if mode == PAD_CONSTANT and cur_mode == PAD_CONSTANT:
         return t                      # zero halo is 7 wide from allocation and never written
-    if (cur_mode, cur_pad) == (mode, pad):
-        return t
+    if cur_mode == mode and cur_pad >= pad:
+        return t                      # a wider mirrored ring contains the narrower one
     if mode == PAD_CONSTANT:
         pad = 7
     for b in (t.buf, t.lo):
@@ -565,7 +578,7 @@ def _num_sms(device):
 
 
 def conv2d_tc(x, wp, bias=None, act=ACT_LINEAR, pad_mode=PAD_CONSTANT, bn=None, residual=None, out_scale=None,
-              out=None, out_channels_total=None, out_c_offset=0):
+              out=None, out_channels_total=None, out_c_offset=0, out_halo=PAD_CONSTANT):
     """tcgen05 convolution on BLK8 tensors.  x: Blk8 with >= wp['cin'] channels; returns a Blk8.
     Split precision is selected by the packed weights (wp['nsplit'] == 2 needs split tensors)."""
     if not isinstance(x, Blk8):
@@ -578,12 +591,14 @@ def conv2d_tc(x, wp, bias=None, act=ACT_LINEAR, pad_mode=PAD_CONSTANT, bn=None, 
         raise ValueError("conv2d_tc: weights packed for precision mode %d, input tensor is mode %d" % (nsplit, x.mode))
     blk8_halo_fill(x, k // 2, pad_mode)
     if out is None:
-        out = Blk8(x.B, out_channels_total or cout, x.H, x.W, x.device, split=nsplit)
+        out = Blk8(x.B, out_channels_total or cout, x.H, x.W, x.device, split=nsplit, sym=_fusable_halo(out_halo, x.H, x.W))
     if (out.B, out.H, out.W) != (x.B, x.H, x.W) or out.mode != nsplit:
         raise ValueError("conv2d_tc: destination shape / precision mismatch")
     if residual is not None and ((residual.B, residual.H, residual.W) != (x.B, x.H, x.W) or residual.mode != nsplit):
         raise ValueError("conv2d_tc: residual shape / precision mismatch")
     bn_s, bn_t = (bn if bn is not None else (None, None))
+    # the producer writes the next layer's SYMMETRIC padding itself when it owns every channel of the tensor
+    fused_halo = _fusable_halo(out_halo, x.H, x.W) and out_c_offset == 0 and (out.C + 15) // 16 == (cout + 15) // 16
     timed = KERNEL_TIMER is not None and KERNEL_TIMER.match(wp["cin"], cout, k, k, x.H, x.W)
     if timed:
         KERNEL_TIMER.start()
@@ -592,10 +607,13 @@ def conv2d_tc(x, wp, bias=None, act=ACT_LINEAR, pad_mode=PAD_CONSTANT, bn=None, 
                              None if (residual is None or not split) else _p(residual.lo), _p(out_scale),
                              out.plane_ptr(out_c_offset), out.plane_ptr_lo(out_c_offset) if split else None,
                              x.B, x.C, cout, out.C, 0 if residual is None else residual.C, x.H, x.W, k, int(act),
-                             nsplit, wp["acc_scale"], _num_sms(x.device), _stream()), "conv2d_tc")
+                             nsplit, wp["acc_scale"], PAD_SYMMETRIC if fused_halo else PAD_CONSTANT,
+                             _num_sms(x.device), _stream()), "conv2d_tc")
     if timed:
         KERNEL_TIMER.stop(2.0 * x.B * x.H * x.W * k * k * wp["cin"] * cout)
-    if out.halo[0] != PAD_CONSTANT:
+    if fused_halo:
+        out.halo = (PAD_SYMMETRIC, 7)         # the epilogue wrote the mirrored ring for the next layer
+    elif out.halo[0] != PAD_CONSTANT:
         out.halo = (out.halo[0], -1)          # interior changed: a mirrored halo is stale
     return out
 

@@ -103,6 +103,26 @@ def test_conv2d_tc_symmetric_bn_residual_scale_concat(ops):
     assert rel_l2(ops.from_blk8(again), ref0) < 6e-4
 
 
+@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("B,Cin,Cout,H,W,k", [(2, 32, 32, 18, 50, 11), (1, 16, 12, 40, 270, 5), (2, 8, 5, 33, 9, 3)])
+def test_fused_symmetric_halo_equals_halo_fill(ops, mode, B, Cin, Cout, H, W, k):
+    """A producer asked for out_halo=SYMMETRIC leaves exactly the buffer that pcnn_blk8_halo_fill would make."""
+    g = torch.Generator().manual_seed(H * W + mode)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    kern = torch.randn(k, k, Cin, Cout, generator=g) / (k * Cin ** 0.5)
+    wp = ops.pack_conv_weights_tc(dev(kern), nsplit=mode)
+    xin = ops.to_blk8(dev(x), split=mode, halo=1)
+    assert xin.halo == (1, 7)
+    ref_in = ops.to_blk8(dev(x), split=mode)
+    ops.blk8_halo_fill(ref_in, 7, 1)
+    assert torch.equal(xin.buf, ref_in.buf) and (mode == 1 or torch.equal(xin.lo, ref_in.lo))
+    a = ops.conv2d_tc(xin, wp, None, 1, pad_mode=1, out_halo=1)
+    assert a.halo == (1, 7)
+    b = ops.conv2d_tc(ref_in, wp, None, 1, pad_mode=1)
+    ops.blk8_halo_fill(b, 7, 1)
+    assert torch.equal(a.buf, b.buf) and (mode == 1 or torch.equal(a.lo, b.lo))
+
+
 def test_conv2d_tc_chain_matches_fp32_path(ops):
     """Three chained TC convs stay in BLK8 (no re-layout) and track the strict-FP32 kernels to fp16 accuracy."""
     g = torch.Generator().manual_seed(4)
