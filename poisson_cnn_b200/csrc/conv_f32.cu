@@ -23,6 +23,9 @@ struct ConvF32Params {
     int B, Cin, Cout, H, W, kh, kw, pad_mode, act;
     float pad_value;
     long long in_bstride, out_bstride, res_bstride;
+    // channel / row strides of the tiled kernel (dense NCHW: H*W and W; a batch of 1-D signals run as the rows
+    // of one image: W and the sample stride)
+    long long in_cs, in_rs, out_cs, out_rs, res_cs, res_rs;
     int ci_chunk, pitch, tile_rows, cop;   // cop = padded Cout (multiple of 8)
 };
 
@@ -41,7 +44,6 @@ __global__ void __launch_bounds__(256) conv2d_f32_kernel(const ConvF32Params p) 
     const int pad_t = p.kh / 2, pad_l = p.kw / 2;
     const int tile_cols = TILE_W + p.kw - 1;
     const float* inb = p.in + (long long)b * p.in_bstride;
-    const long long plane = (long long)p.H * p.W;
 
     float acc[PX][CO];
 #pragma unroll
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(256) conv2d_f32_kernel(const ConvF32Params p) 
                 if (inside || p.pad_mode != PCNN_PAD_CONSTANT) {
                     const int sy = pad_src_index(gy, p.H, p.pad_mode);
                     const int sx = pad_src_index(gx, p.W, p.pad_mode);
-                    v = __ldg(inb + (long long)(c0 + ci) * plane + (long long)sy * p.W + sx);
+                    v = __ldg(inb + (long long)(c0 + ci) * p.in_cs + (long long)sy * p.in_rs + sx);
                 } else {
                     v = p.pad_value;
                 }
@@ -126,14 +128,15 @@ __global__ void __launch_bounds__(256) conv2d_f32_kernel(const ConvF32Params p) 
         const float bs = p.bn_scale ? __ldg(p.bn_scale + co) : 1.f;
         const float bt = p.bn_shift ? __ldg(p.bn_shift + co) : 0.f;
         const float os = p.out_scale ? __ldg(p.out_scale + (long long)b * p.Cout + co) : 1.f;
-        const long long base = (long long)co * plane + (long long)gy * p.W;
+        const long long base = (long long)co * p.out_cs + (long long)gy * p.out_rs;
+        const long long rbase = (long long)co * p.res_cs + (long long)gy * p.res_rs;
 #pragma unroll
         for (int i = 0; i < PX; ++i) {
             const int gx = x0 + cx + 8 * i;
             if (gx < p.W) {
                 float v = apply_act(acc[i][j] + bias, p.act);
                 if (p.bn_scale) v = fmaf(v, bs, bt);
-                if (resb) v += __ldg(resb + base + gx);
+                if (resb) v += __ldg(resb + rbase + gx);
                 if (p.out_scale) v *= os;
                 outb[base + gx] = v;
             }
@@ -249,6 +252,16 @@ extern "C" int pcnn_conv2d_f32(const float* in, const float* kernel, const float
             return PCNN_OK;
         }
     }
+    p.in_cs = p.out_cs = p.res_cs = (long long)H * W;
+    p.in_rs = p.out_rs = p.res_rs = W;
+    int gridB = B;
+    if (H == 1 && kh == 1 && B > 1 && !out_scale) {
+        // a batch of 1-D signals (the DBCNN boundary stack): the samples become the rows of ONE image, so the
+        // 8-row tiles are full instead of 1/8 occupied; kh == 1 keeps the rows independent
+        p.H = B; p.B = 1; gridB = 1;
+        p.in_cs = p.out_cs = p.res_cs = W;
+        p.in_rs = in_bstride; p.out_rs = out_bstride; p.res_rs = res_bstride;
+    }
     p.cop = ngroups * CO;
     p.tile_rows = TILE_H + kh - 1;
     int cols = TILE_W + kw - 1;
@@ -268,7 +281,7 @@ extern "C" int pcnn_conv2d_f32(const float* in, const float* kernel, const float
         configured = 200 * 1024;
     }
     dim3 block(64, ngroups, 1);
-    dim3 grid(ceil_div(W, TILE_W), ceil_div(H, TILE_H), B);
+    dim3 grid(ceil_div(W, TILE_W), ceil_div(p.H, TILE_H), gridB);
     PCNN_CHECK_ARG(grid.y <= 65535, "conv2d_f32: H too large");
     conv2d_f32_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(p);
     PCNN_CHECK_LAUNCH();

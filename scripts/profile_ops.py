@@ -59,8 +59,9 @@ for (Bn, cin, cout, H, W, k), (n, t, ns) in sorted(tc.items(), key=lambda kv: -k
     ntile = 256 if W >= 256 else -(-W // 16) * 16
     tiles = Bn * -(-H // 4) * -(-W // ntile)
     nv = -(-cin // 16) * {1: 1, 2: 3, 3: 2}[ns]
-    mmas = tiles * nv * k * (k + 3)
-    floor_ms = -(-tiles // 148) * nv * k * (k + 3) * 128 * (ntile / 256.0) / 1.9e6
+    cp = _lib.lib.pcnn_conv_tc_channel_slots(cout, k); rt = 128 // cp
+    tiles = Bn * (-(-H // rt)) * (-(-W // ntile))
+    floor_ms = -(-tiles // 148) * nv * k * (k + rt - 1) * 128 * (ntile / 256.0) / 1.9e6
     print("  %-32s n=%2d %8.2f ms  floor %.2f ms  -> %.0f%%" % ((Bn, cin, cout, H, W, k), n, t, floor_ms * n, 100 * floor_ms * n / t))
 
 print("other launches by shape:")
