@@ -436,7 +436,15 @@ def _blk8_buffer(key, nbytes, device):
     pool = _BLK8_POOL.get(key)
     if pool:
         return pool.pop()
-    return torch.zeros(nbytes // 2, dtype=torch.float16, device=device), (PAD_CONSTANT, 7)
+    try:
+        buf = torch.zeros(nbytes // 2, dtype=torch.float16, device=device)
+    except torch.OutOfMemoryError:
+        # the pool keeps one set of buffers per tensor shape ever seen; under memory pressure (many grid
+        # shapes in one process) the idle ones are released and the allocation is retried once
+        blk8_pool_clear()
+        torch.cuda.empty_cache()
+        buf = torch.zeros(nbytes // 2, dtype=torch.float16, device=device)
+    return buf, (PAD_CONSTANT, 7)
 
 
 class Blk8:
