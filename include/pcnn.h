@@ -207,8 +207,13 @@ int pcnn_conv_tc_pack_weights(const float* kernel, void* packed, int kh, int kw,
  * i.e. blocks/bottleneck_block.py:57-118 (deconvupscale with k == stride, 'SAME'; Upsample via the per-axis
  * tables of pcnn_resize_f32) followed by the branch sum of models/Homogeneous_Poisson_NN_Legacy.py:226-233.
  * The pointer arrays are HOST arrays of n_deconv / n_resize device pointers (<= 8 each); deconv inputs are
- * [B,C,ih,iw] fp32 with Keras kernels [s,s,C,C]; resize sources are [B,C,ih,iw] fp32 with C*ih*iw <= 8192.
+ * [B,C,ih,iw] fp32 with PACKED kernels (pcnn_upsample_merge_pack_kernel); resize sources are [B,C,ih,iw] fp32,
+ * C*ih*iw <= 8192, sources and tables 16-byte aligned.
  * C % 8 == 0, C <= 32; c_offset % 16 == 0; mode = precision mode of the destination (1, 2, 3). */
+/* dc_kernel[d] of pcnn_upsample_merge_blk8: the Keras deconv kernel [s,s,C,C] re-laid once per layer as
+ * [s][s][C/8][8*C+4] floats (phase, 8-channel group) blocks, so one bulk copy stages a row phase. */
+size_t pcnn_upsample_merge_packed_floats(int stride, int C);
+int pcnn_upsample_merge_pack_kernel(const float* kernel, float* packed, int stride, int C, void* stream);
 int pcnn_upsample_merge_blk8(int n_deconv, const float* const* dc_in, const float* const* dc_kernel,
                              const float* const* dc_bias, const int* dc_stride, const int* dc_ih,
                              const int* dc_iw, const int* dc_act, int n_resize, const float* const* rs_in,

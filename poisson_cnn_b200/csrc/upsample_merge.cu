@@ -18,24 +18,39 @@
 
 #include "pcnn_common.cuh"
 
+#ifdef PCNN_UM_PROFILE
+__device__ unsigned long long g_um_prof[16];
+#define UM_T(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_um_prof[i], (unsigned long long)(t_ - t_prev)); t_prev = t_; } } while (0)
+#else
+#define UM_T(i) do { } while (0)
+#endif
+
 namespace pcnn {
 namespace um {
 
 constexpr int HALO = 7;
 constexpr int MAXB = 8;          // branches of each kind
-constexpr int SEG_W = 256;       // output pixels per CTA
-constexpr int NTHR = 288;        // threads per CTA: 256 pixel owners + one warp so that s = 3 (88 x 3 work items) needs one pass
+constexpr int MAXS = 40;         // stages: (deconv branch, group of <= TXG column phases) or resize branch
+constexpr int TXG = 8;           // column phases per stage: bounds the staged phase matrices to 8 x C x C floats
+constexpr int SEG_W = 128;       // output pixels per row segment
+constexpr int NTHR = 160;        // threads per CTA: 128 pixel owners + one warp (s = 3, 4, 8 have up to 160 work items)
 constexpr float LO_SCALE = 2048.f;
 
 struct Params {
     int n_dc, n_rs;
     const float* dc_in[MAXB];    // [B][Cin][ih][iw]
-    const float* dc_w[MAXB];     // Keras deconv kernel [s][s][Cout][Cin]
+    const float* dc_w[MAXB];     // packed deconv kernel [s][s][C/8][8*C + 4] (pcnn_upsample_merge_pack_kernel)
     const float* dc_b[MAXB];     // [Cout] or null
     int dc_s[MAXB], dc_ih[MAXB], dc_iw[MAXB], dc_pbh[MAXB], dc_pbw[MAXB], dc_act[MAXB], dc_ps[MAXB];
     const float* rs_in[MAXB];    // [B][C][ih][iw]
     const int* rs_iy[MAXB]; const float* rs_wy[MAXB]; const int* rs_ix[MAXB]; const float* rs_wx[MAXB];
     int rs_taps[MAXB], rs_ih[MAXB], rs_iw[MAXB];
+    int rs_off[MAXB], rs_tab[MAXB], rs_st[MAXB];   // offsets: source / interpolation tables in the operand buffer, row buffer in s_st
+    int dc_al16[MAXB];             // deconv input pointer is 16-byte aligned
+    uint32_t dc_magic[MAXB];       // ceil(2^32 / stride)
+    int n_stages;
+    signed char st_branch[MAXS];   // deconv branch index, or -1 - r for resize branch r
+    unsigned char st_tx0[MAXS], st_ntx[MAXS];
     float alpha;
     __half* out; uint8_t* out_lo;
     int mode;                    // precision mode of the destination (1, 2, 3: see pcnn_conv2d_tc)
@@ -64,20 +79,53 @@ __device__ __forceinline__ void cp_async16(float* dst, const float* src) {     /
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async16z(float* dst, const float* src, bool valid) {   // zero-filled when !valid
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    const int bytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16p(float* dst, const float* src, int bytes) {   // first `bytes` copied, rest zero-filled
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(bytes > 0 ? src : nullptr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_copy_g2s(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 // geometry of deconv branch d for one row segment
 struct DcGeom { int s, ih, iw, i, ty, j_begin, segp, pgs; };
+// n / s for 0 <= n < 2^20 and s <= 64 through the branch's precomputed ceil(2^32 / s)
+__device__ __forceinline__ int fast_div(int n, uint32_t magic) { return (int)__umulhi((uint32_t)n, magic); }
 __device__ __forceinline__ DcGeom dc_geom(const Params& p, int d, int X0, int Y) {
     DcGeom g;
     g.s = p.dc_s[d]; g.ih = p.dc_ih[d]; g.iw = p.dc_iw[d];
+    const uint32_t mg = p.dc_magic[d];
     const int jy = Y + p.dc_pbh[d];
-    g.i = jy / g.s; g.ty = jy - g.i * g.s;
+    g.i = fast_div(jy, mg); g.ty = jy - g.i * g.s;
     const int xlast = min(X0 + SEG_W - 1, p.W - 1);
-    g.j_begin = (X0 + p.dc_pbw[d]) / g.s;
-    const int j_end = (xlast + p.dc_pbw[d]) / g.s;
+    g.j_begin = fast_div(X0 + p.dc_pbw[d], mg);
+    const int j_end = fast_div(xlast + p.dc_pbw[d], mg);
     g.segp = ((j_end - g.j_begin + 1) + 3) & ~3; g.pgs = g.segp >> 2;
     return g;
 }
@@ -85,18 +133,25 @@ __device__ __forceinline__ DcGeom dc_geom(const Params& p, int d, int X0, int Y)
 // Persistent CTAs (one per SM) walk (row segment, stage) pairs; stage = one branch.  The operands of the NEXT stage
 // (low-res row tile + the s phase matrices W[ty][0..s), or the tiny resize source) stream into the other
 // shared-memory buffer with cp.async while the current stage computes, also across row boundaries.
-__global__ void __launch_bounds__(NTHR, 1) upsample_merge_kernel(const Params p) {
+__global__ void __launch_bounds__(NTHR, 2) upsample_merge_kernel(const Params p) {
     extern __shared__ __align__(16) float sm[];
-    float* s_st = sm;                      // [s column phases][phase stride] staged deconv results / resize row
-    float* s_buf[2] = {s_st + p.st_floats, s_st + p.st_floats + p.buf_floats[0]};   // stage operands: [tile | weights]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(sm);      // two mbarriers: bulk-copied phase matrices of each operand buffer
+    float* s_st = sm + 4;                  // [s column phases][phase stride] staged deconv results / resize row
+    float* s_buf[2] = {s_st + p.st_floats, s_st + p.st_floats + p.buf_floats[0]};   // stage operands: [tile | weights | bias] or [source | tables]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int C = p.C;
-    const int nstages = p.n_dc + p.n_rs;
+    const int nstages = p.n_stages;
     const int segs = (p.W + SEG_W - 1) / SEG_W;
     const int units = p.B * p.H * segs;
     const int my_units = (units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total = my_units * nstages;
-    const int wswz = (C == 32) ? 7 : 0;    // 16-byte chunk swizzle of the staged weights (conflict-free across channel groups)
+    const int wblk = 8 * C + 4;            // staged phase matrices: (tx, channel group) blocks of 8 rows x C floats, 16 B apart in banks
+    const int ncg = C >> 3;
+    if (tid == 0) {
+        mbar_init(s_bar, 1); mbar_init(s_bar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
     auto unit_coords = [&](int k, int& b, int& Y, int& X0) {
         const int u = (int)blockIdx.x + k * (int)gridDim.x;
@@ -106,43 +161,86 @@ __global__ void __launch_bounds__(NTHR, 1) upsample_merge_kernel(const Params p)
     };
 
     // asynchronous operand load of step (unit k, stage st): one cp.async group
-    auto issue_load = [&](int step) {
-        const int k = step / nstages, st = step - k * nstages;
-        int b, Y, X0;
-        unit_coords(k, b, Y, X0);
+    auto issue_load = [&](int step, int st, int b, int Y, int X0) {
         float* dst = s_buf[step & 1];
-        if (st < p.n_dc) {
-            const DcGeom g = dc_geom(p, st, X0, Y);
-            const float* inb = p.dc_in[st] + ((long long)b * C * g.ih + g.i) * g.iw + g.j_begin;
-            for (int ci = warp; ci < C; ci += NTHR / 32)
-                for (int px = lane; px < g.segp; px += 32)
-                    cp_async4(dst + ci * g.segp + px, inb + (long long)ci * g.ih * g.iw + px, g.j_begin + px < g.iw);
-            // phase matrices W[ty][0..s)[co][ci]: s*C*C contiguous floats, 16-byte chunks, swizzled within each row
-            float* wdst = dst + p.tile_floats;
-            const float* wsrc = p.dc_w[st] + (long long)g.ty * g.s * C * C;
-            const int cpr = C >> 2, nchunks = g.s * C * cpr;      // chunks per row, total
-            for (int e = tid; e < nchunks; e += NTHR) {
-                const int row = (C == 32) ? (e >> 3) : e / cpr, ch = e - row * cpr;
-                cp_async16(wdst + row * C + ((ch ^ ((row >> 3) & wswz)) << 2), wsrc + (long long)e * 4);
+        const int br = p.st_branch[st];
+        if (br >= 0) {
+            const DcGeom g = dc_geom(p, br, X0, Y);
+            const float* inb = p.dc_in[br] + ((long long)b * C * g.ih + g.i) * g.iw + g.j_begin;
+            const long long cstride = (long long)g.ih * g.iw;
+            if (((g.iw | g.j_begin) & 3) == 0 && p.dc_al16[br]) {
+                // rows are 16-byte aligned: whole float4 chunks are either inside the map or beyond its end
+                const int cpr = g.segp >> 2;
+                for (int ci = warp; ci < C; ci += NTHR / 32)
+                    for (int ch = lane; ch < cpr; ch += 32)
+                        cp_async16z(dst + ci * g.segp + 4 * ch, inb + ci * cstride + 4 * ch, g.j_begin + 4 * ch < g.iw);
+            } else {
+                for (int ci = warp; ci < C; ci += NTHR / 32)
+                    for (int px = lane; px < g.segp; px += 32)
+                        cp_async4(dst + ci * g.segp + px, inb + ci * cstride + px, g.j_begin + px < g.iw);
             }
+            // phase matrices W[ty][tx0..tx0+ntx): pre-packed (pcnn_upsample_merge_pack_kernel) as (tx, 8-channel group)
+            // blocks of 8*C + 4 floats, so ONE bulk copy (TMA engine, tracked by the buffer's mbarrier) brings the
+            // whole stage in the bank-staggered layout the FMA loop reads
+            float* wdst = dst + p.tile_floats;
+            const int ntx = p.st_ntx[st], nblk = ntx * ncg;
+            if (tid == 0) {
+                const uint32_t bytes = (uint32_t)(nblk * wblk * 4);
+                mbar_expect_tx(s_bar + (step & 1), bytes);
+                bulk_copy_g2s(wdst, p.dc_w[br] + (long long)(g.ty * g.s + p.st_tx0[st]) * ncg * wblk, bytes, s_bar + (step & 1));
+            }
+            // bias (zeros when the branch has none) behind the phase matrices: the gather reads it from shared memory
+            if (tid < C) cp_async4(wdst + nblk * wblk + tid, p.dc_b[br] ? p.dc_b[br] + tid : p.dc_w[br], p.dc_b[br] != nullptr);
         } else {
-            const int r = st - p.n_dc;
-            const int nsrc = C * p.rs_ih[r] * p.rs_iw[r];
-            const float* src = p.rs_in[r] + (long long)b * nsrc;
-            for (int e = tid; e < nsrc; e += NTHR) cp_async4(dst + e, src + e, true);
+            // all resize branches: the tiny source maps, then this row's / these columns' interpolation tables
+            for (int r = 0; r < p.n_rs; ++r) {
+                const int taps = p.rs_taps[r];
+                const int nsrc = C * p.rs_ih[r] * p.rs_iw[r];
+                const float* src = p.rs_in[r] + (long long)b * nsrc;
+                float* sdst = dst + p.rs_off[r];
+                for (int e = tid; e < (nsrc >> 2); e += NTHR) cp_async16z(sdst + 4 * e, src + 4 * e, true);
+                float* tab = dst + p.rs_tab[r];                      // [iy(4) | wy(4) | ix(SEG_W*4) | wx(SEG_W*4)]
+                if (tid < taps) {
+                    cp_async4(tab + tid, reinterpret_cast<const float*>(p.rs_iy[r] + Y * taps + tid), true);
+                    cp_async4(tab + 4 + tid, p.rs_wy[r] + Y * taps + tid, true);
+                }
+                const int left = (p.W - X0) * taps;                  // valid table entries from X0 on
+                for (int e = tid; e < ((SEG_W * taps) >> 2); e += NTHR) {
+                    const int bytes = min(max((left - 4 * e) * 4, 0), 16);
+                    cp_async16p(tab + 8 + 4 * e, reinterpret_cast<const float*>(p.rs_ix[r] + X0 * taps) + 4 * e, bytes);
+                    cp_async16p(tab + 8 + SEG_W * 4 + 4 * e, p.rs_wx[r] + X0 * taps + 4 * e, bytes);
+                }
+            }
         }
     };
 
+    uint32_t bar_phase[2] = {0u, 0u};
     float sum[32];                         // running sums of this thread's pixel (threads < 256), all channels
-    if (total > 0) issue_load(0);
+    int cb = 0, cY = 0, cX0 = 0, nb = 0, nY = 0, nX0 = 0;     // coordinates of the current and of the next step's unit
+    int st = 0, kk = 0;
+    if (total > 0) { unit_coords(0, cb, cY, cX0); issue_load(0, 0, cb, cY, cX0); }
+#ifdef PCNN_UM_PROFILE
+    long long t_prev = clock64();
+#endif
 #pragma unroll 1
-    for (int step = 0; step < total; ++step) {
+    for (int step = 0; step < total; ++step, st = (st + 1 == nstages) ? 0 : st + 1) {
+        if (step > 0 && st == 0) { ++kk; cb = nb; cY = nY; cX0 = nX0; }
         cp_async_commit_wait_all();
+        UM_T(0);
         __syncthreads();                   // operands of this step landed; everyone is done with the other buffer and with s_st
-        if (step + 1 < total) issue_load(step + 1);
-        const int k = step / nstages, st = step - k * nstages;
-        int b, Y, X0;
-        unit_coords(k, b, Y, X0);
+        UM_T(1);
+        if (p.st_branch[st] >= 0) {       // phase matrices landed (the barrier of a buffer flips once per deconv stage using it)
+            mbar_wait(s_bar + (step & 1), bar_phase[step & 1]);
+            bar_phase[step & 1] ^= 1u;
+        }
+        UM_T(8);
+        const int st_next = (st + 1 == nstages) ? 0 : st + 1;
+        if (step + 1 < total) {
+            if (st_next == 0) unit_coords(kk + 1, nb, nY, nX0); else { nb = cb; nY = cY; nX0 = cX0; }
+            issue_load(step + 1, st_next, nb, nY, nX0);
+        }
+        UM_T(2);
+        const int b = cb, Y = cY, X0 = cX0;
         const int X = X0 + tid;
         const bool owner = tid < SEG_W && X < p.W;
         if (st == 0) {
@@ -150,13 +248,15 @@ __global__ void __launch_bounds__(NTHR, 1) upsample_merge_kernel(const Params p)
             for (int c = 0; c < 32; ++c) sum[c] = 0.f;
         }
         const float* s_x = s_buf[step & 1];
-        if (st < p.n_dc) {
-            // ---------------- transpose-conv branch
-            const int d = st;
+        const int br = p.st_branch[st];
+        if (br >= 0) {
+            // ---------------- transpose-conv branch, column phases [tx0, tx0 + ntx)
+            const int d = br;
             const DcGeom g = dc_geom(p, d, X0, Y);
             const int s = g.s, segp = g.segp, pgs = g.pgs, ps = p.dc_ps[d];
+            const int tx0 = p.st_tx0[st], ntx = p.st_ntx[st];
             const float* s_w = s_x + p.tile_floats;
-            const int items = s * 4 * pgs;
+            const int items = ntx * 4 * pgs;
             for (int it = tid; it < items; it += NTHR) {
                 const int tx = it / (4 * pgs);
                 const int rem = it - tx * 4 * pgs;
@@ -167,19 +267,16 @@ __global__ void __launch_bounds__(NTHR, 1) upsample_merge_kernel(const Params p)
                 for (int c = 0; c < 8; ++c)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) acc[c][q] = 0.f;
-                const int row0 = tx * C + cg * 8;
-                const float* wp = s_w + row0 * C;
-                const int sw = (row0 >> 3) & wswz;
+                const float* wp = s_w + (tx * ncg + cg) * wblk;
                 const float* xp = s_x + pg * 4;
 #pragma unroll 2
                 for (int ci = 0; ci < C; ci += 4) {
                     float4 x4[4];
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) x4[kk] = *reinterpret_cast<const float4*>(xp + (ci + kk) * segp);
-                    const int co4 = ((ci >> 2) ^ sw) << 2;
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const float4 w = *reinterpret_cast<const float4*>(wp + c * C + co4);
+                        const float4 w = *reinterpret_cast<const float4*>(wp + c * C + ci);
                         acc[c][0] = fmaf(w.x, x4[0].x, acc[c][0]); acc[c][1] = fmaf(w.x, x4[0].y, acc[c][1]);
                         acc[c][2] = fmaf(w.x, x4[0].z, acc[c][2]); acc[c][3] = fmaf(w.x, x4[0].w, acc[c][3]);
                         acc[c][0] = fmaf(w.y, x4[1].x, acc[c][0]); acc[c][1] = fmaf(w.y, x4[1].y, acc[c][1]);
@@ -195,67 +292,89 @@ __global__ void __launch_bounds__(NTHR, 1) upsample_merge_kernel(const Params p)
                     *reinterpret_cast<float4*>(s_st + tx * ps + (cg * 8 + c) * segp + pg * 4) =
                         make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
             }
+            UM_T(3);
             __syncthreads();
+            UM_T(4);
             if (owner) {
                 const int jx = X + p.dc_pbw[d];
-                const int j = jx / s, tx = jx - j * s;
+                const int j = fast_div(jx, p.dc_magic[d]), tx = jx - j * s - tx0;
                 const float* gsrc = s_st + tx * ps + (j - g.j_begin);
-                const float* bias = p.dc_b[d];
-                const bool hb = bias != nullptr;
+                const float* bias = s_w + ntx * ncg * wblk;
                 const int act = p.dc_act[d];
-                if (act == PCNN_ACT_LEAKY_RELU) {
+                if (tx < 0 || tx >= ntx) {
+                    // this pixel's column phase belongs to another stage of the branch
+                } else if (act == PCNN_ACT_LEAKY_RELU) {
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         if (c < C) {
-                            const float v = gsrc[c * segp] + (hb ? __ldg(bias + c) : 0.f);
+                            const float v = gsrc[c * segp] + bias[c];
                             sum[c] += fmaxf(v, 0.2f * v);
                         }
+                    }
+                } else if (act == PCNN_ACT_TANH) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        if (c < C) sum[c] += tanhf(gsrc[c * segp] + bias[c]);
                     }
                 } else {
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
-                        if (c < C) {
-                            const float v = gsrc[c * segp] + (hb ? __ldg(bias + c) : 0.f);
-                            sum[c] += (act == PCNN_ACT_TANH) ? tanhf(v) : v;
-                        }
+                        if (c < C) sum[c] += gsrc[c * segp] + bias[c];
                     }
                 }
             }
         } else {
-            // ---------------- resize branch (tiny source in shared memory): the row interpolation is the same for the
-            // whole CTA, so it is done once ([C][iw] values into s_st); each pixel then interpolates along x only
-            const int r = st - p.n_dc;
-            const int ih = p.rs_ih[r], iw = p.rs_iw[r], taps = p.rs_taps[r];
-            for (int e = tid; e < C * iw; e += NTHR) {
-                const int c = e / iw, xs = e - c * iw;
-                const float* src = s_x + c * ih * iw + xs;
-                float acc = 0.f;
-                for (int a = 0; a < taps; ++a)
-                    acc = fmaf(src[__ldg(p.rs_iy[r] + Y * taps + a) * iw], __ldg(p.rs_wy[r] + Y * taps + a), acc);
-                s_st[e] = acc;
+            // ---------------- all resize branches (tiny sources in shared memory): the row interpolation is the same for
+            // the whole CTA, so it is done once per branch ([C][iw] values into s_st); each pixel then interpolates along x
+            for (int r = 0; r < p.n_rs; ++r) {
+                const int ih = p.rs_ih[r], iw = p.rs_iw[r], taps = p.rs_taps[r];
+                const float* tab = s_x + p.rs_tab[r];
+                int iyv[4];
+                float wyv[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {       // unused taps: weight 0 on row 0
+                    const bool on = a < taps;
+                    iyv[a] = on ? __float_as_int(tab[a]) * iw : 0;
+                    wyv[a] = on ? tab[4 + a] : 0.f;
+                }
+                float* rowbuf = s_st + p.rs_st[r];
+                for (int e = tid; e < C * iw; e += NTHR) {
+                    const int c = e / iw, xs = e - c * iw;
+                    const float* src = s_x + p.rs_off[r] + c * ih * iw + xs;
+                    float acc = src[iyv[0]] * wyv[0];
+                    acc = fmaf(src[iyv[1]], wyv[1], acc);
+                    if (taps > 2) { acc = fmaf(src[iyv[2]], wyv[2], acc); acc = fmaf(src[iyv[3]], wyv[3], acc); }
+                    rowbuf[e] = acc;
+                }
             }
             __syncthreads();
             if (owner) {
-                int ix[4];
-                float wx[4];
+                for (int r = 0; r < p.n_rs; ++r) {
+                    const int iw = p.rs_iw[r], taps = p.rs_taps[r];
+                    const float* tab = s_x + p.rs_tab[r];
+                    int ix[4];
+                    float wx[4];
 #pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const bool on = a < taps;
-                    ix[a] = on ? __ldg(p.rs_ix[r] + X * taps + a) : 0;
-                    wx[a] = on ? __ldg(p.rs_wx[r] + X * taps + a) : 0.f;     // unused taps: weight 0 on element 0
-                }
+                    for (int a = 0; a < 4; ++a) {
+                        const bool on = a < taps;
+                        ix[a] = on ? __float_as_int(tab[8 + tid * taps + a]) : 0;
+                        wx[a] = on ? tab[8 + SEG_W * 4 + tid * taps + a] : 0.f;     // unused taps: weight 0 on element 0
+                    }
+                    const float* rowbuf = s_st + p.rs_st[r];
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    if (c < C) {
-                        const float* row = s_st + c * iw;
-                        float acc = row[ix[0]] * wx[0];
-                        acc = fmaf(row[ix[1]], wx[1], acc);
-                        if (taps > 2) { acc = fmaf(row[ix[2]], wx[2], acc); acc = fmaf(row[ix[3]], wx[3], acc); }
-                        sum[c] += acc;
+                    for (int c = 0; c < 32; ++c) {
+                        if (c < C) {
+                            const float* row = rowbuf + c * iw;
+                            float acc = row[ix[0]] * wx[0];
+                            acc = fmaf(row[ix[1]], wx[1], acc);
+                            if (taps > 2) { acc = fmaf(row[ix[2]], wx[2], acc); acc = fmaf(row[ix[3]], wx[3], acc); }
+                            sum[c] += acc;
+                        }
                     }
                 }
             }
         }
+        UM_T(br >= 0 ? 5 : 7);
         if (st != nstages - 1 || !owner) continue;
 
     // ---------------- write-out: one pixel per thread, 16-byte units of the BLK8 layout
@@ -307,7 +426,19 @@ __global__ void __launch_bounds__(NTHR, 1) upsample_merge_kernel(const Params p)
             }
         }
     }
+    UM_T(6);
     }   // step loop
+}
+
+// Keras deconv kernel [s][s][Cout=C][Cin=C] -> [s][s][C/8][8*C + 4]: (phase, 8-output-channel group) blocks of 8 rows x C
+// input channels, each followed by 4 pad floats so consecutive blocks start 16 B apart in the shared-memory banks
+__global__ void pack_kernel(const float* __restrict__ k, float* __restrict__ out, int C, long long nblocks) {
+    const int wblk = 8 * C + 4;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < nblocks * wblk; idx += (long long)gridDim.x * blockDim.x) {
+        const long long blk = idx / wblk;
+        const int e = (int)(idx - blk * wblk);
+        out[idx] = e < 8 * C ? k[blk * 8 * C + e] : 0.f;
+    }
 }
 
 }  // namespace um
@@ -315,6 +446,19 @@ __global__ void __launch_bounds__(NTHR, 1) upsample_merge_kernel(const Params p)
 
 using namespace pcnn;
 using namespace pcnn::um;
+
+extern "C" size_t pcnn_upsample_merge_packed_floats(int stride, int C) {
+    if (stride < 1 || C < 8 || (C % 8)) return 0;
+    return (size_t)stride * stride * (C / 8) * (8 * C + 4);
+}
+
+extern "C" int pcnn_upsample_merge_pack_kernel(const float* kernel, float* packed, int stride, int C, void* stream) {
+    PCNN_CHECK_ARG(kernel && packed && stride >= 1 && stride <= 32 && C >= 8 && C <= 32 && (C % 8) == 0, "upsample_merge_pack_kernel: bad argument");
+    const long long nblocks = (long long)stride * stride * (C / 8);
+    pack_kernel<<<(int)std::min<long long>((nblocks * (8 * C + 4) + 255) / 256, 1184), 256, 0, (cudaStream_t)stream>>>(kernel, packed, C, nblocks);
+    PCNN_CHECK_LAUNCH();
+    return PCNN_OK;
+}
 
 extern "C" int pcnn_upsample_merge_blk8(int n_deconv, const float* const* dc_in, const float* const* dc_kernel,
                                         const float* const* dc_bias, const int* dc_stride, const int* dc_ih, const int* dc_iw,
@@ -341,7 +485,7 @@ extern "C" int pcnn_upsample_merge_blk8(int n_deconv, const float* const* dc_in,
     std::sort(order, order + nd, [&](int a, int b2) { return dc_stride[a] > dc_stride[b2]; });
     int seq[MAXB];
     for (int lo = 0, hi = nd - 1, k = 0; lo <= hi; ) { seq[k++] = order[lo++]; if (lo <= hi) seq[k++] = order[hi--]; }
-    int tile = 0, st = 0;
+    int tile = 0, st = 0, rs_need = 0, rs_st = 0;
     size_t need[2] = {0, 0};
     for (int k = 0; k < nd; ++k) {
         const int d = seq[k];
@@ -350,16 +494,18 @@ extern "C" int pcnn_upsample_merge_blk8(int n_deconv, const float* const* dc_in,
         PCNN_CHECK_ARG((reinterpret_cast<uintptr_t>(dc_kernel[d]) % 16) == 0, "upsample_merge_blk8: deconv kernel %d must be 16-byte aligned", d);
         PCNN_CHECK_ARG(ceil_div(H, s) == ih && ceil_div(W, s) == iw,
                        "upsample_merge_blk8: output (%d,%d) inconsistent with input (%d,%d) at stride %d (TF raises)", H, W, ih, iw, s);
+        p.dc_al16[k] = (reinterpret_cast<uintptr_t>(dc_in[d]) % 16) == 0;
+        p.dc_magic[k] = (uint32_t)((0x100000000ull + (unsigned)s - 1) / (unsigned)s);
         p.dc_in[k] = dc_in[d]; p.dc_w[k] = dc_kernel[d]; p.dc_b[k] = dc_bias ? dc_bias[d] : nullptr;
         p.dc_s[k] = s; p.dc_ih[k] = ih; p.dc_iw[k] = iw; p.dc_act[k] = dc_act[d];
         p.dc_pbh[k] = std::max((ih - 1) * s + s - H, 0) / 2;
         p.dc_pbw[k] = std::max((iw - 1) * s + s - W, 0) / 2;
-        const int segp_max = (((SEG_W - 1) / s + 2) + 3) & ~3;           // low-res pixels touching one 256-pixel segment
+        const int segp_max = (((SEG_W - 1) / s + 2) + 3) & ~3;           // low-res pixels touching one row segment
         int ps = 32 * segp_max + (32 + s - 1) / s;                        // phases land ~32/s banks apart
         ps = (ps + 3) & ~3;
         p.dc_ps[k] = ps;
         tile = std::max(tile, C * segp_max);
-        st = std::max(st, s * ps);
+        st = std::max(st, std::min(s, TXG) * ps);
     }
     for (int r = 0; r < n_resize; ++r) {
         PCNN_CHECK_ARG(rs_in[r] && rs_iy[r] && rs_wy[r] && rs_ix[r] && rs_wx[r] && rs_taps[r] >= 1 && rs_taps[r] <= 4 && rs_ih[r] > 0 && rs_iw[r] > 0,
@@ -367,20 +513,44 @@ extern "C" int pcnn_upsample_merge_blk8(int n_deconv, const float* const* dc_in,
         PCNN_CHECK_ARG((long long)C * rs_ih[r] * rs_iw[r] <= 8192, "upsample_merge_blk8: resize source %dx%d too large for the fused kernel", rs_ih[r], rs_iw[r]);
         p.rs_in[r] = rs_in[r]; p.rs_iy[r] = rs_iy[r]; p.rs_wy[r] = rs_wy[r]; p.rs_ix[r] = rs_ix[r]; p.rs_wx[r] = rs_wx[r];
         p.rs_taps[r] = rs_taps[r]; p.rs_ih[r] = rs_ih[r]; p.rs_iw[r] = rs_iw[r];
-        tile = std::max(tile, C * rs_ih[r] * rs_iw[r]);
-        st = std::max(st, C * rs_iw[r]);
+        PCNN_CHECK_ARG(((reinterpret_cast<uintptr_t>(rs_in[r]) | reinterpret_cast<uintptr_t>(rs_ix[r]) | reinterpret_cast<uintptr_t>(rs_wx[r])) % 16) == 0,
+                       "upsample_merge_blk8: resize branch %d: source and tables must be 16-byte aligned", r);
+        p.rs_off[r] = rs_need;
+        p.rs_tab[r] = rs_need + ((C * rs_ih[r] * rs_iw[r] + 3) & ~3);
+        rs_need = p.rs_tab[r] + 8 + 2 * SEG_W * 4;
+        p.rs_st[r] = rs_st;
+        rs_st += (C * rs_iw[r] + 3) & ~3;
     }
+    st = std::max(st, rs_st);
     tile = (tile + 3) & ~3;
     st = (st + 3) & ~3;
-    const int nstages = n_deconv + n_resize;
+    // stage table: every deconv branch contributes ceil(s / TXG) stages, then the resize branches
+    int nstages = 0;
+    size_t wsize[MAXS];
+    for (int k = 0; k < nd; ++k)
+        for (int tx0 = 0; tx0 < p.dc_s[k]; tx0 += TXG) {
+            PCNN_CHECK_ARG(nstages < MAXS, "upsample_merge_blk8: too many stages");
+            p.st_branch[nstages] = (signed char)k; p.st_tx0[nstages] = (unsigned char)tx0;
+            p.st_ntx[nstages] = (unsigned char)std::min(TXG, p.dc_s[k] - tx0);
+            wsize[nstages] = (size_t)tile + (size_t)p.st_ntx[nstages] * (C / 8) * (8 * C + 4) + 32;
+            ++nstages;
+        }
+    if (n_resize > 0) {
+        PCNN_CHECK_ARG(nstages < MAXS, "upsample_merge_blk8: too many stages");
+        p.st_branch[nstages] = (signed char)-1; p.st_tx0[nstages] = 0; p.st_ntx[nstages] = 0;
+        wsize[nstages] = (size_t)rs_need;
+        ++nstages;
+    }
+    p.n_stages = nstages;
     for (int k = 0; k < nstages; ++k) {
-        const size_t w = k < nd ? (size_t)p.dc_s[k] * C * C : 0;
         const int par = (nstages % 2 == 0) ? (k & 1) : 0;       // odd stage count: step parity drifts, both buffers get the maximum
-        need[par] = std::max(need[par], (size_t)tile + w);
+        need[par] = std::max(need[par], wsize[k]);
     }
     if (nstages % 2) need[1] = need[0];
     p.tile_floats = tile; p.st_floats = st; p.buf_floats[0] = (int)need[0]; p.buf_floats[1] = (int)need[1];
-    const size_t smem = ((size_t)st + need[0] + need[1]) * sizeof(float);
+    need[0] = (need[0] + 3) & ~(size_t)3; need[1] = (need[1] + 3) & ~(size_t)3;
+    p.buf_floats[0] = (int)need[0]; p.buf_floats[1] = (int)need[1];
+    const size_t smem = ((size_t)4 + st + need[0] + need[1]) * sizeof(float);
     PCNN_CHECK_ARG(smem <= 227 * 1024, "upsample_merge_blk8: shared-memory plan too large (%zu bytes)", smem);
     PCNN_CHECK_CUDA(cudaFuncSetAttribute(upsample_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
@@ -388,8 +558,20 @@ extern "C" int pcnn_upsample_merge_blk8(int n_deconv, const float* const* dc_in,
     PCNN_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const long long units = (long long)B * H * ceil_div(W, SEG_W);
     PCNN_CHECK_ARG(units < (1ll << 30), "upsample_merge_blk8: too many row segments");
-    const int grid = (int)std::min<long long>(units, sms);
+    const int ctas_per_sm = std::max(1, std::min(4, (int)((227 * 1024) / (smem + 1024))));
+    const int grid = (int)std::min<long long>(units, (long long)sms * ctas_per_sm);
     upsample_merge_kernel<<<grid, NTHR, smem, (cudaStream_t)stream>>>(p);
     PCNN_CHECK_LAUNCH();
+#ifdef PCNN_UM_PROFILE
+    {
+        unsigned long long h[16];
+        cudaDeviceSynchronize();
+        cudaMemcpyFromSymbol(h, g_um_prof, sizeof(h));
+        const char* names[9] = {"cp.async wait", "barrier (top)", "issue next loads", "compute", "barrier (mid)", "deconv gather", "write-out", "resize stage", "weights mbarrier"};
+        unsigned long long tot = 0; for (int i = 0; i < 9; ++i) tot += h[i];
+        for (int i = 0; i < 9; ++i) fprintf(stderr, "um phase %-18s %12llu cycles %5.1f%%\n", names[i], h[i], 100.0 * h[i] / (tot ? tot : 1));
+        unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_um_prof, z, sizeof(z));
+    }
+#endif
     return PCNN_OK;
 }

@@ -229,10 +229,16 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
         cat = ops.Blk8(B, 2 * F, H, Wd, dev, split=split)
         self._conv_tc(x0, "non_bottleneck_conv", ACT_LEAKY_RELU, PAD_CONSTANT, out=cat)
         fused = (F % 8 == 0 and len(dc) <= 8 and len(rs) <= 8
-                 and all(tuple(k.shape) == (s_, s_, F, F) and s_ <= 64 for _, k, _, s_, _ in dc)
+                 and all(tuple(k.shape) == (s_, s_, F, F) and s_ <= 32 for _, k, _, s_, _ in dc)
                  and all(F * h.shape[2] * h.shape[3] <= 8192 for h, _ in rs))
         if fused:
-            ops.upsample_merge_blk8(dc, rs, alpha, cat, F, H, Wd)
+            packed = []
+            for h, k, bias_, s_, act_ in dc:
+                key = ("deconv_packed", k.data_ptr())
+                if key not in self._tc:          # packed once per layer; the cache dies with the weights (_on_weights_loaded)
+                    self._tc[key] = ops.pack_deconv_kernel(k)
+                packed.append((h, self._tc[key], bias_, s_, act_))
+            ops.upsample_merge_blk8(packed, rs, alpha, cat, F, H, Wd)
         else:                                    # general kernels: fp32 merge buffer, one read-modify-write per branch
             merged = torch.empty((B, F, H, Wd), device=dev, dtype=torch.float32)
             for i, (h, dk, db, s_, act_) in enumerate(dc):

@@ -638,9 +638,22 @@ def dbcnn_expand_blk8(h, modew, x_res, split=False):
     return out
 
 
+def pack_deconv_kernel(kernel):
+    """Keras deconv kernel [s,s,C,C] (k == stride) -> the bank-staggered phase-matrix image the fused
+    upsample-merge kernel bulk-copies ([s][s][C/8][8*C+4] floats); done once per layer."""
+    _chk(kernel, "kernel")
+    s_, s2, C, C2 = kernel.shape
+    n = lib.pcnn_upsample_merge_packed_floats(int(s_), int(C)) if (s_ == s2 and C == C2) else 0
+    if n == 0:
+        raise ValueError("pack_deconv_kernel: needs a [s,s,C,C] kernel with C a multiple of 8")
+    packed = torch.empty(n, dtype=torch.float32, device=kernel.device)
+    check(lib.pcnn_upsample_merge_pack_kernel(_p(kernel.contiguous()), _p(packed), int(s_), int(C), _stream()), "upsample_merge_pack_kernel")
+    return packed
+
+
 def upsample_merge_blk8(deconv_branches, resize_branches, alpha, out, c_offset, H, W):
     """Fused upsample + branch sum written into channels [c_offset, c_offset+C) of the Blk8 tensor `out`.
-    deconv_branches: [(x [B,C,ih,iw] fp32, kernel [s,s,C,C], bias or None, stride, act)];
+    deconv_branches: [(x [B,C,ih,iw] fp32, packed kernel (pack_deconv_kernel), bias or None, stride, act)];
     resize_branches: [(x [B,C,ih,iw] fp32, method)]."""
     import ctypes
     if not isinstance(out, Blk8) or (out.H, out.W) != (int(H), int(W)):
@@ -656,10 +669,10 @@ def upsample_merge_blk8(deconv_branches, resize_branches, alpha, out, c_offset, 
     d_in, d_k, d_b, d_s, d_ih, d_iw, d_act = [], [], [], [], [], [], []
     for x, kern, bias, stride, act in deconv_branches:
         _chk(x, "x"); _chk(kern, "kernel")
-        x, kern = x.contiguous(), kern.contiguous()
+        x = x.contiguous()
         C = x.shape[1] if C is None else C
-        if x.shape[0] != B or x.shape[1] != C or tuple(kern.shape) != (stride, stride, C, C):
-            raise ValueError("upsample_merge_blk8: deconv branch needs x [B,C,ih,iw] and a kernel [s,s,C,C] with s == stride")
+        if x.shape[0] != B or x.shape[1] != C or kern.numel() != lib.pcnn_upsample_merge_packed_floats(int(stride), int(C)):
+            raise ValueError("upsample_merge_blk8: deconv branch needs x [B,C,ih,iw] and pack_deconv_kernel() of a [s,s,C,C] kernel with s == stride")
         keep += [x, kern]
         d_in.append(x.data_ptr()); d_k.append(kern.data_ptr()); d_b.append(_p(bias)); d_s.append(stride)
         d_ih.append(x.shape[2]); d_iw.append(x.shape[3]); d_act.append(act)

@@ -149,7 +149,7 @@ def test_upsample_merge_blk8(ops, H, W, C, mode):
         x = torch.randn(B, C, ih, iw, generator=g)
         kern = torch.randn(s, s, C, C, generator=g) / C ** 0.5
         bias = torch.randn(C, generator=g) * 0.1
-        dc.append((dev(x), dev(kern), dev(bias), s, 1))
+        dc.append((dev(x), ops.pack_deconv_kernel(dev(kern)), dev(bias), s, 1))
         ref = ref + O.deconv_same(x.double(), kern.double(), bias.double(), "leaky_relu", (H, W), s)
     for (ih, iw), m in (((2, 2), "bilinear"), ((4, 5), "bicubic"), ((8, 8), "nearest")):
         x = torch.randn(B, C, ih, iw, generator=g)
