@@ -168,16 +168,23 @@ __global__ void __launch_bounds__(NTHR, 2) upsample_merge_kernel(const Params p)
             const DcGeom g = dc_geom(p, br, X0, Y);
             const float* inb = p.dc_in[br] + ((long long)b * C * g.ih + g.i) * g.iw + g.j_begin;
             const long long cstride = (long long)g.ih * g.iw;
+            constexpr int NW = NTHR / 32;
             if (((g.iw | g.j_begin) & 3) == 0 && p.dc_al16[br]) {
-                // rows are 16-byte aligned: whole float4 chunks are either inside the map or beyond its end
-                const int cpr = g.segp >> 2;
-                for (int ci = warp; ci < C; ci += NTHR / 32)
-                    for (int ch = lane; ch < cpr; ch += 32)
-                        cp_async16z(dst + ci * g.segp + 4 * ch, inb + ci * cstride + 4 * ch, g.j_begin + 4 * ch < g.iw);
+                // rows are 16-byte aligned: whole float4 chunks are either inside the map or beyond its end.
+                // segp <= 132, so a lane owns one chunk column; pointers advance by constants (no per-copy index math)
+                if (4 * lane < g.segp) {
+                    const bool valid = g.j_begin + 4 * lane < g.iw;
+                    const float* sp = inb + warp * cstride + 4 * lane;
+                    float* dp = dst + warp * g.segp + 4 * lane;
+                    for (int ci = warp; ci < C; ci += NW, sp += NW * cstride, dp += NW * g.segp) cp_async16z(dp, sp, valid);
+                }
             } else {
-                for (int ci = warp; ci < C; ci += NTHR / 32)
-                    for (int px = lane; px < g.segp; px += 32)
-                        cp_async4(dst + ci * g.segp + px, inb + ci * cstride + px, g.j_begin + px < g.iw);
+                for (int px = lane; px < g.segp; px += 32) {
+                    const bool valid = g.j_begin + px < g.iw;
+                    const float* sp = inb + warp * cstride + px;
+                    float* dp = dst + warp * g.segp + px;
+                    for (int ci = warp; ci < C; ci += NW, sp += NW * cstride, dp += NW * g.segp) cp_async4(dp, sp, valid);
+                }
             }
             // phase matrices W[ty][tx0..tx0+ntx): pre-packed (pcnn_upsample_merge_pack_kernel) as (tx, 8-channel group)
             // blocks of 8*C + 4 floats, so ONE bulk copy (TMA engine, tracked by the buffer's mbarrier) brings the
