@@ -15,6 +15,8 @@ from ._base import WeightedModel
 
 
 class Dirichlet_BC_NN_Legacy_2(WeightedModel):
+    _MIXED_AS = "tc"       # precision "mixed": this network runs single-pass FP16 (see WeightedModel.set_precision)
+
     def __init__(self, data_format="channels_first", boundary_conv_config=None, spp_config=None,
                  domain_info_mlp_config=None, final_convolutions_config=None, postsmoother_iterations=0,
                  use_batchnorm=False):

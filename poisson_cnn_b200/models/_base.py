@@ -55,8 +55,9 @@ class WeightedModel:
     def _on_weights_loaded(self):
         self._tc = {}
 
-    PRECISIONS = ("fp32", "tc", "tc2", "tc3")
+    PRECISIONS = ("fp32", "tc", "tc2", "tc3", "mixed")
     _TC_MODE = {"tc": 1, "tc3": 2, "tc2": 3}
+    _MIXED_AS = "tc2"      # what 'mixed' means for this network on its own (the DBCNN overrides it with 'tc')
 
     def set_precision(self, precision):
         """'fp32': strict FP32 CUDA-core kernels (rel-L2 <= 1e-5 vs the reference arithmetic);
@@ -64,13 +65,17 @@ class WeightedModel:
         'tc3' : tcgen05 with split FP16 operands (x = hi + lo, W = hi + lo; three MMAs per product term),
                 ~22 significand bits -- the error-compensated mode that holds the 2e-3 budget on any input;
         'tc2' : FP16 main pass + ONE e4m3 K=32 MMA for both correction terms (2x the tensor work of 'tc',
-                ~15 significand bits)."""
+                ~15 significand bits);
+        'mixed': 'tc2' in the HPNN (45 convolutions deep: it carries essentially all of the rounding error of the
+                merged model) and single-pass 'tc' in the DBCNN (shallower, tanh-bounded and max-normalised:
+                measured contribution < 1e-4) -- same accuracy as 'tc2' at ~0.8x its tensor work."""
         if precision not in self.PRECISIONS:
             raise ValueError("precision must be one of %s" % (self.PRECISIONS,))
-        self.precision = precision
-        for sub in ("hpnn", "dbcnn"):
-            if hasattr(self, sub):
-                getattr(self, sub).set_precision(precision)
+        subs = [getattr(self, sub) for sub in ("hpnn", "dbcnn") if hasattr(self, sub)]
+        # a single network resolves 'mixed' to its own mode; the merged model keeps the name and hands it down
+        self.precision = precision if (subs or precision != "mixed") else self._MIXED_AS
+        for sub in subs:
+            sub.set_precision(precision)
         return self
 
     def tc_conv(self, name):

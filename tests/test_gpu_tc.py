@@ -291,3 +291,22 @@ def test_models_tc2_mode_vs_oracle():
     e_hp = rel_l2(model.hpnn([dev(p["rhs"]), dev(p["dx"])]), ref)
     print("tc2-mode rel-L2 vs float64 oracle: pcnn %.3e  hpnn %.3e" % (e_pcnn, e_hp))
     assert e_pcnn < 5e-4 and e_hp < 5e-4      # >= 4x inside the 2e-3 tensor-core budget
+
+
+def test_models_mixed_mode_vs_oracle():
+    """precision='mixed': tc2 in the HPNN, single-pass tc in the DBCNN -- the accuracy of tc2 at ~0.8x the tensor work."""
+    import os
+    from tests.helpers import GOLDEN, pcnn_configs, all_weights
+    from poisson_cnn_b200.synthetic import make_problem
+    hp, db = pcnn_configs()
+    w = all_weights(hp, db)
+    model = _models(hp, db, w).set_precision("mixed")
+    assert (model.precision, model.hpnn.precision, model.dbcnn.precision) == ("mixed", "tc2", "tc")
+    keys = ("rhs", "left", "top", "right", "bottom", "dx")
+    g = np.load(os.path.join(GOLDEN, "pcnn_112x120.npz"))
+    e_pcnn = rel_l2(model([dev(g[k]) for k in keys]), g["out"])
+    p = make_problem(2, 160, 144, seed=53)
+    ref = O.pcnn_forward(hp, db, w, *[p[k].double() for k in keys])
+    e2 = rel_l2(model([dev(p[k]) for k in keys]), ref)
+    print("mixed-mode rel-L2 vs float64 oracle: pcnn golden %.3e  160x144 %.3e" % (e_pcnn, e2))
+    assert e_pcnn < 5e-4 and e2 < 1e-3       # inside the 2e-3 tensor-core budget with margin
