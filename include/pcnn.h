@@ -235,8 +235,11 @@ int pcnn_upsample_merge_blk8(int n_deconv, const float* const* dc_in, const floa
  * [e4m3(x) ; e4m3(x_lo*2^11)] * [e4m3(W_lo) ; e4m3(W*2^-11)], into the same accumulator: 2x the tensor
  * work of a single pass, ~15 significand bits.  The *_lo pointers are then the fp8 "q" buffers
  * (same byte geometry as a BLK8 buffer: 16 B per pixel per plane).
+ * nsplit | PCNN_TC_SKIP_CORRECTION (mode 3 only): the tensors keep their e4m3 planes but THIS layer issues the
+ * fp16 pass only (a layer whose rounding error does not matter pays single-pass cost inside a tc2 network).
  * out_halo_mode: PCNN_PAD_CONSTANT (0) leaves the halo of `out` alone; PCNN_PAD_SYMMETRIC makes the epilogue
  * also write the 7-wide mirrored ring (tf.pad SYMMETRIC for the next layer, fused; needs H, W >= 7). */
+#define PCNN_TC_SKIP_CORRECTION 0x10
 int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpack, const float* bias,
                    const float* bn_scale, const float* bn_shift, const void* residual,
                    const void* residual_lo, const float* out_scale, void* out, void* out_lo, int B,

@@ -68,7 +68,9 @@ struct Params {
     int nsplit;              // precision mode: 1 single FP16 pass; 2 hi/lo fp16 split (3 MMAs per term);
                              // 3 fp16 main pass + ONE e4m3 K=32 MMA for both correction terms (in_lo/out_lo/residual_lo
                              // then point at the fp8 "q" buffers: planes 2c = e4m3(x), 2c+1 = e4m3((x - hi) * 2^11))
-    int nv;                  // virtual K-chunks = c16 * {1, 3, 2}
+    int kpass;               // MMA passes per 16-channel chunk: 1 (fp16 only), 2 (fp16 + e4m3 correction), 3 (hi/lo split).
+                             // kpass = 1 with nsplit = 3 tensors: a layer whose correction pass is skipped
+    int nv;                  // virtual K-chunks = c16 * kpass
     int B, H, W, Hp, P;
     int c8_in, c8_out, c8_res;
     int c16;                 // input-channel chunks of 16
@@ -251,8 +253,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
             const int col0 = x0 + HALO - p.pad, prow0 = y0 + HALO - p.pad;
             for (int v = 0; v < p.nv; ++v) {
                 // split precision: per chunk c the passes are (x_hi,W_hi), (x_hi,W_lo), (x_lo,W_hi); mode 3: (x_hi,W_hi), (q,Wq)
-                const int c = (p.nsplit == 2) ? v / 3 : (p.nsplit == 3 ? v >> 1 : v);
-                const __half* inp = ((p.nsplit == 2 && (v % 3) == 2) || (p.nsplit == 3 && (v & 1))) ? p.in_lo : p.in;
+                const int c = (p.kpass == 3) ? v / 3 : (p.kpass == 2 ? v >> 1 : v);
+                const __half* inp = ((p.kpass == 3 && (v % 3) == 2) || (p.kpass == 2 && (v & 1))) ? p.in_lo : p.in;
                 const __half* base = inp + ((size_t)b * p.c8_in + 2 * c) * plane_elems + (size_t)col0 * 8;
                 // rows travel in two groups per chunk (R is even); one mbarrier pair per group, at the group's first slot
                 for (int grp = 0, rho = 0; grp < 2; ++grp) {
@@ -280,8 +282,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
             if (p.w_resident && t != (int)blockIdx.x) break;    // resident weights: one pass fills every stage
             for (int v = 0; v < p.nv; ++v) {
-                const int c = (p.nsplit == 2) ? v / 3 : (p.nsplit == 3 ? v >> 1 : v);
-                const int wsel = ((p.nsplit == 2 && (v % 3) == 1) || (p.nsplit == 3 && (v & 1))) ? 1 : 0;   // second weight image
+                const int c = (p.kpass == 3) ? v / 3 : (p.kpass == 2 ? v >> 1 : v);
+                const int wsel = ((p.kpass == 3 && (v % 3) == 1) || (p.kpass == 2 && (v & 1))) ? 1 : 0;   // second weight image
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) + ((size_t)wsel * p.c16 + c) * p.kw * p.wstage_bytes;
                 for (int dx = 0; dx < p.kw; ++dx, src += p.wstage_bytes) {
                     mbar_wait(w_empty + st, ph ^ 1);
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                 const uint32_t d_tmem = tmem_base + acc * 256;
                 uint32_t accum = 0;
                 for (int c = 0; c < p.nv; ++c) {
-                    const bool f8 = (p.nsplit == 3) && (c & 1);    // correction pass: e4m3 operands, K = 32
+                    const bool f8 = (p.kpass == 2) && (c & 1);    // correction pass: e4m3 operands, K = 32
                     // the chunk's rows sit in two groups of GR slots: [slot0, +GR) and the next group (which may wrap to 0)
                     const uint32_t slotA = slot0, phA = slot0_ph;
                     uint32_t slotB = slot0 + GR, phB = slot0_ph;
@@ -941,7 +943,10 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
                               void* out, void* out_lo, int B, int Cin_total, int Cout, int Cout_total, int Cres_total,
                               int H, int W, int k, int act, int nsplit, float acc_scale, int out_halo_mode, int num_sms, void* stream) {
     PCNN_CHECK_ARG(in && wpack && out, "conv2d_tc: null pointer");
+    const bool skip_corr = (nsplit & PCNN_TC_SKIP_CORRECTION) != 0;
+    nsplit &= ~PCNN_TC_SKIP_CORRECTION;
     PCNN_CHECK_ARG(nsplit >= 1 && nsplit <= 3, "conv2d_tc: precision mode must be 1, 2 or 3");
+    PCNN_CHECK_ARG(!skip_corr || nsplit == 3, "conv2d_tc: PCNN_TC_SKIP_CORRECTION applies to precision mode 3 only");
     if (nsplit >= 2) PCNN_CHECK_ARG(in_lo && out_lo && (!residual || residual_lo), "conv2d_tc: split precision needs the lo buffers");
     PCNN_CHECK_ARG((k & 1) && k >= 1 && k <= 2 * HALO + 1, "conv2d_tc: kernel size %d not supported (odd, <= 15)", k);
     PCNN_CHECK_ARG(Cout >= 1 && Cout <= 32 && Cout <= Cout_total, "conv2d_tc: Cout %d not in [1,32]", Cout);
@@ -956,7 +961,8 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
     p.out = (__half*)out; p.out_lo = (__half*)out_lo; p.nsplit = nsplit; p.acc_scale = acc_scale;
     p.B = B; p.H = H; p.W = W; p.Hp = H + 2 * HALO; p.P = W + 2 * HALO;
     p.c16 = (Cin_total + 15) / 16;
-    p.nv = p.c16 * (nsplit == 2 ? 3 : (nsplit == 3 ? 2 : 1));
+    p.kpass = skip_corr ? 1 : (nsplit == 2 ? 3 : (nsplit == 3 ? 2 : 1));
+    p.nv = p.c16 * p.kpass;
     p.c8_in = p.c16 * 2; p.c8_out = ((Cout_total + 15) / 16) * 2; p.c8_res = ((Cres_total + 15) / 16) * 2;
     p.cout = Cout; p.kh = k; p.kw = k; p.pad = k / 2; p.act = act; p.halo_sym = (out_halo_mode == PCNN_PAD_SYMMETRIC);
     const int cp = choose_cp(Cout, k), rt = M_TILE / cp, zpad = rt - 1;

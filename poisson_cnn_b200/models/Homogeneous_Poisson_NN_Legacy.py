@@ -130,6 +130,9 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
             if sc.get("kernel_size", 3) % 2 == 0:
                 raise NotImplementedError("Scaling: even kernel sizes with Keras 'same' padding are not built")
 
+    # layer-name prefixes whose tc2 correction pass is skipped (precision experiments / 'mixed' mode)
+    tc_uncorrected = ()
+
     def weight_specs(self, prefix=""):
         return W.hpnn_weight_specs(self._cfg, prefix)
 
@@ -174,10 +177,12 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
     # ------------------------------------------------------------------ tensor-core building blocks
     def _conv_tc(self, x, name, act, pad, bn_name=None, residual=None, out_scale=None, out=None, out_c_offset=0,
                  next_pad=PAD_CONSTANT):
-        """next_pad: padding mode of the layer that reads the result (a SYMMETRIC ring is written by this conv's epilogue)."""
-        wp, bias = self.tc_conv(name)
+        """next_pad: padding mode of the layer that reads the result (a SYMMETRIC ring is written by this conv's epilogue).
+        The precision mode follows the input tensor (bottleneck branches may run single-pass inside a tc2 network)."""
+        wp, bias = self.tc_conv(name, mode=x.mode)
+        corr = not any(name.startswith(pfx) for pfx in self.tc_uncorrected)
         return ops.conv2d_tc(x, wp, bias, act, pad, bn=self.bn(bn_name) if bn_name else None, residual=residual,
-                             out_scale=out_scale, out=out, out_c_offset=out_c_offset, out_halo=next_pad)
+                             out_scale=out_scale, out=out, out_c_offset=out_c_offset, out_halo=next_pad, correction=corr)
 
     def _resnet_tc(self, x, name, act, pad, use_bn, out_scale=None, next_pad=PAD_CONSTANT):
         t = self._conv_tc(x, name + "/conv0", act, pad, name + "/bn0" if use_bn else None, next_pad=pad)
@@ -207,12 +212,15 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
         blocks = self.bottleneck_deconv_blocks + self.bottleneck_multilinear_blocks
         alpha = 1.0 / float(len(blocks) * F)
         dc, rs = [], []                          # low-res branch outputs, upsampled and summed by ONE fused kernel
+        # 'mixed': the branches are averaged with weight 1/(8*F) before they re-enter the trunk -- measured: running
+        # them single-pass changes the merged model's error by < 1e-6 (scripts/layer_sensitivity_probe.py)
+        bsplit = 1 if self.requested_precision == "mixed" else split
         for blk in blocks:
             self._branch_out_hw(blk, H, Wd)
             ph, pw = -(-H // blk.downsampling_factor), -(-Wd // blk.downsampling_factor)
             name = "bottleneck_%s/%d" % (blk.kind, blk.index)
             if blk.kind == "deconv" and min(ph, pw) >= 16:
-                h = ops.to_blk8(ops.avgpool_same(x0_f32, blk.downsampling_factor), split=split, halo=blk.pad)
+                h = ops.to_blk8(ops.avgpool_same(x0_f32, blk.downsampling_factor), split=bsplit, halo=blk.pad)
                 h = self._conv_tc(h, name + "/conv0", blk.act, blk.pad, next_pad=blk.pad)
                 for r in range(1, blk.n_convs):
                     h = self._resnet_tc(h, "%s/resnet%d" % (name, r), blk.act, blk.pad, blk.use_batchnorm,

@@ -21,6 +21,7 @@ class WeightedModel:
         self._tc = {}
         self.device = None
         self.precision = "fp32"
+        self.requested_precision = "fp32"
 
     # -- to be provided by subclasses
     def weight_specs(self, prefix=""):
@@ -74,14 +75,16 @@ class WeightedModel:
         subs = [getattr(self, sub) for sub in ("hpnn", "dbcnn") if hasattr(self, sub)]
         # a single network resolves 'mixed' to its own mode; the merged model keeps the name and hands it down
         self.precision = precision if (subs or precision != "mixed") else self._MIXED_AS
+        self.requested_precision = precision
         for sub in subs:
             sub.set_precision(precision)
         return self
 
-    def tc_conv(self, name):
-        """(packed fp16 operand image, bias) of a conv layer for the tensor-core kernel, packed once."""
+    def tc_conv(self, name, mode=None):
+        """(packed fp16 operand image, bias) of a conv layer for the tensor-core kernel, packed once per
+        precision mode (default: the model's)."""
         from .. import ops
-        nsplit = self._TC_MODE[self.precision]
+        nsplit = mode or self._TC_MODE[self.precision]
         key = (name, nsplit)
         if key not in self._tc:
             self._tc[key] = ops.pack_conv_weights_tc(self._w[name + "/kernel"], nsplit)

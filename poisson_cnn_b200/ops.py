@@ -586,7 +586,7 @@ def _num_sms(device):
 
 
 def conv2d_tc(x, wp, bias=None, act=ACT_LINEAR, pad_mode=PAD_CONSTANT, bn=None, residual=None, out_scale=None,
-              out=None, out_channels_total=None, out_c_offset=0, out_halo=PAD_CONSTANT):
+              out=None, out_channels_total=None, out_c_offset=0, out_halo=PAD_CONSTANT, correction=True):
     """tcgen05 convolution on BLK8 tensors.  x: Blk8 with >= wp['cin'] channels; returns a Blk8.
     Split precision is selected by the packed weights (wp['nsplit'] == 2 needs split tensors)."""
     if not isinstance(x, Blk8):
@@ -615,7 +615,8 @@ def conv2d_tc(x, wp, bias=None, act=ACT_LINEAR, pad_mode=PAD_CONSTANT, bn=None, 
                              None if (residual is None or not split) else _p(residual.lo), _p(out_scale),
                              out.plane_ptr(out_c_offset), out.plane_ptr_lo(out_c_offset) if split else None,
                              x.B, x.C, cout, out.C, 0 if residual is None else residual.C, x.H, x.W, k, int(act),
-                             nsplit, wp["acc_scale"], PAD_SYMMETRIC if fused_halo else PAD_CONSTANT,
+                             nsplit | (0x10 if (nsplit == 3 and not correction) else 0), wp["acc_scale"],
+                             PAD_SYMMETRIC if fused_halo else PAD_CONSTANT,
                              _num_sms(x.device), _stream()), "conv2d_tc")
     if timed:
         KERNEL_TIMER.stop(2.0 * x.B * x.H * x.W * k * k * wp["cin"] * cout)
