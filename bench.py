@@ -240,7 +240,7 @@ def run_ours(args):
         # DRAM bytes per launch of this kernel from the ncu --set full captures (profiles/r01_conv_tc_k15_*_b32_full_raw.csv:
         # dram__bytes_read.sum + dram__bytes_write.sum at 32 samples per launch), scaled to the samples per launch here
         per_sample = {"tc": (151.436032e6 + 94.614272e6) / 32, "tc2": (303.551488e6 + 228.785920e6) / 32}.get(hp_mode)
-        samples_per_launch = min(B, getattr(model, "max_microbatch", B) or B)
+        samples_per_launch = min(B, max(1, int((getattr(model, "max_microbatch", B) or B) * 65536 // (nx * ny))))
         traffic = per_sample * samples_per_launch if (per_sample and args.roofline_kernel == (32, 32, 15) and (nx, ny) == (256, 256)) else None
         roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
                     "frac": ach / peaks["tflops"], "traffic": traffic, "kernel": "conv2d %d->%d k%d (%s)" % (args.roofline_kernel + (hp_mode,)),

@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
             const float osc = (p.out_scale && live) ? p.out_scale[(size_t)b * p.cout + co] : 1.f;
             const float mul = bns * osc, add = bnt * osc;
             // pixel side: per octet, pixel index of (row y, x = x0 + px) within a plane, and validity
-            size_t o_pix[2];
+            size_t o_pix[2], o_off[2], r_off[2];
             bool o_ok[2];
             int o_dy[2][2];
 #pragma unroll
@@ -425,6 +425,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                 const int y = ty * RT + o_r[e];
                 o_ok[e] = (y < p.H) && (o_pl[e] < planes_out);
                 o_pix[e] = (size_t)(y + HALO) * p.P + (x0 + px + HALO);
+                // byte offsets of this thread's 16-byte unit in `out` (and, identically, in the lo / q buffer: every
+                // plane is 16 B per pixel) and in the residual; per chunk only the column advances
+                o_off[e] = (((size_t)b * p.c8_out + o_pl[e]) * plane_px + o_pix[e]) * 16;
+                r_off[e] = (((size_t)b * p.c8_res + o_pl[e]) * plane_px + o_pix[e]) * 16;
                 o_dy[e][0] = (p.halo_sym && y < HALO) ? -(2 * y + 1) : 0;                       // row displacement of the top mirror
                 o_dy[e][1] = (p.halo_sym && y >= p.H - HALO && y < p.H) ? 2 * (p.H - y) - 1 : 0;  // ... and of the bottom mirror
             }
@@ -435,12 +439,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                 for (int e = 0; e < 2; ++e) {
                     rh[e] = make_uint4(0, 0, 0, 0); rl[e] = make_uint4(0, 0, 0, 0);
                     if (o_ok[e] && x0 + xo + px < p.W) {
-                        const size_t pix = o_pix[e] + xo;
-                        rh[e] = *reinterpret_cast<const uint4*>(p.residual + (((size_t)b * p.c8_res + o_pl[e]) * plane_px + pix) * 8);
-                        if (mode == 2) rl[e] = *reinterpret_cast<const uint4*>(p.residual_lo + (((size_t)b * p.c8_res + o_pl[e]) * plane_px + pix) * 8);
+                        const size_t off = r_off[e] + (size_t)xo * 16;
+                        rh[e] = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.residual) + off);
+                        if (mode == 2) rl[e] = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.residual_lo) + off);
                         if (mode == 3) {
-                            const uint2 t2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(p.residual_lo) +
-                                (((size_t)b * p.c8_res + (o_pl[e] | 1)) * plane_px + pix) * 16 + 8 * (o_pl[e] & 1));
+                            // remainder plane 2g+1 of this octet's 16-channel group: one plane up for an even plane, same plane otherwise
+                            const uint2 t2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(p.residual_lo) + off +
+                                ((o_pl[e] & 1) ? (size_t)8 : plane_px * 16));
                             rl[e].x = t2.x; rl[e].y = t2.y;
                         }
                     }
@@ -566,9 +571,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             if (oks[e]) {
-                                const size_t off = (((size_t)b * p.c8_out + o_pl[e]) * plane_px + (size_t)((long long)(o_pix[e] + xo) + ds[e])) * 8;
-                                *reinterpret_cast<uint4*>(p.out + off) = hi[e];
-                                if (mode == 2) *reinterpret_cast<uint4*>(p.out_lo + off) = lo[e];
+                                const size_t off = (size_t)((long long)o_off[e] + ((long long)xo + ds[e]) * 16);
+                                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + off) = hi[e];
+                                if (mode == 2) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out_lo) + off) = lo[e];
                             }
                         }
                         if (mode == 3) {
@@ -576,7 +581,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                             if (CP >= 16) {
                                 // both octets belong to one row and one 16-channel group: planes (2g, 2g+1) -> 16-byte stores
                                 if (ok0) {
-                                    const size_t base = (((size_t)b * p.c8_out + o_pl[0]) * plane_px + (size_t)((long long)(o_pix[0] + xo) + d0)) * 16;
+                                    const size_t base = (size_t)((long long)o_off[0] + ((long long)xo + d0) * 16);
                                     *reinterpret_cast<uint4*>(dq + base) = make_uint4(q8[0].x, q8[0].y, q8[1].x, q8[1].y);
                                     *reinterpret_cast<uint4*>(dq + base + plane_px * 16) = make_uint4(l8[0].x, l8[0].y, l8[1].x, l8[1].y);
                                 }
@@ -585,7 +590,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
 #pragma unroll
                                 for (int e = 0; e < 2; ++e) {
                                     if (oks[e]) {
-                                        const size_t base = (((size_t)b * p.c8_out) * plane_px + (size_t)((long long)(o_pix[e] + xo) + ds[e])) * 16;
+                                        const size_t base = (size_t)((long long)o_off[e] + ((long long)xo + ds[e]) * 16);   // plane 0 (CP = 8)
                                         *reinterpret_cast<uint4*>(dq + base) = make_uint4(q8[e].x, q8[e].y, 0u, 0u);
                                         *reinterpret_cast<uint4*>(dq + base + plane_px * 16) = make_uint4(l8[e].x, l8[e].y, 0u, 0u);
                                     }

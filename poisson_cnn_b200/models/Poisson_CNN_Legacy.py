@@ -13,15 +13,17 @@ from ._base import WeightedModel
 
 
 class Poisson_CNN_Legacy(WeightedModel):
-    def __init__(self, hpnn, dbcnn, jacobi_iterations=0, max_microbatch=64):
+    def __init__(self, hpnn, dbcnn, jacobi_iterations=0, max_microbatch=128):
         super().__init__()
         self.hpnn = hpnn
         self.dbcnn = dbcnn
         self.data_format = hpnn.data_format
         self.jacobi_iterations = jacobi_iterations
-        # samples are independent end to end, so a large batch is processed in slices of this many samples:
-        # bounds activation memory (the DBCNN sees 4x the slice) without changing any result
+        # samples are independent end to end, so a large batch is processed in slices: bounds activation memory
+        # (the DBCNN sees 4x the slice) without changing any result.  The bound is stated in 256x256-grid samples
+        # (128 -> ~63 GB of pooled activations in 'mixed' mode) and scales inversely with the grid size.
         self.max_microbatch = max_microbatch
+        self.microbatch_samples = None
 
     def weight_specs(self, prefix=""):
         hs, hm = self.hpnn.weight_specs(prefix + "hpnn/")
@@ -48,7 +50,9 @@ class Poisson_CNN_Legacy(WeightedModel):
         for t, n, name in ((left, ny, "left"), (right, ny, "right"), (top, nx, "top"), (bottom, nx, "bottom")):
             if tuple(t.shape) != (B, 1, n):
                 raise ValueError("%s boundary must be [batch, 1, %d], got %s" % (name, n, tuple(t.shape)))
-        mb = self.max_microbatch
+        mb = self.microbatch_samples            # explicit slice size, if set
+        if mb is None and self.max_microbatch:
+            mb = max(1, int(self.max_microbatch * 65536 // (nx * ny)))
         if mb and B > mb:
             out = torch.empty((B, 1, nx, ny), device=rhs.device, dtype=torch.float32)
             for lo in range(0, B, mb):

@@ -5,7 +5,7 @@ import torch
 import bench
 from poisson_cnn_b200.synthetic import make_problem
 dev = torch.device("cuda", 0)
-model, _ = bench.build_model(dev, "tc2")
+model, _ = bench.build_model(dev, sys.argv[1] if len(sys.argv) > 1 else "mixed")
 B = 256
 p = make_problem(16, 256, 256, seed=1001)
 inp = [p[k].repeat(B // 16, *([1] * (p[k].dim() - 1))).contiguous().cuda() for k in bench.KEYS]

@@ -64,11 +64,11 @@ def test_micro_batching_is_transparent(model):
     inp = _problem(5, 120, 112, seed=1005)
     model.set_precision("fp32")
     full = model(inp)
-    model.max_microbatch = 2
+    model.microbatch_samples = 2
     try:
         chunked = model(inp)
     finally:
-        model.max_microbatch = 64
+        model.microbatch_samples = None
     assert torch.equal(full, chunked)
 
 
