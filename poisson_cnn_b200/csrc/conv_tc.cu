@@ -201,7 +201,8 @@ __device__ __forceinline__ float2 bits_to_float2(uint32_t u) { return __half22fl
 
 // ---------------------------------------------------------------- the kernel
 // CP = channel slots per output row of the M operand (32, 16 or 8); RT = 128 / CP output rows per tile.
-template <int CP>
+// MODE = precision mode of the tensors (1, 2, 3): compile-time in the epilogue, which is instruction-bound on narrow layers.
+template <int CP, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p) {
     constexpr int RT = M_TILE / CP;      // output rows per tile
     constexpr int ZPAD = RT - 1;         // zero z-rows on each side of the packed weights
@@ -388,7 +389,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
         const int nchunks = p.n_tile / CHUNK_PX;
         const int per_part = (nchunks + nparts - 1) / nparts;
         const int ch_begin = part * per_part, ch_end = min(nchunks, ch_begin + per_part);
-        const int act = p.act, mode = p.nsplit;
+        const int act = p.act;
+        constexpr int mode = MODE;
+        const bool affine = (p.bn_scale != nullptr) || (p.out_scale != nullptr);
         const float asc = p.acc_scale;
         const bool has_res = p.residual != nullptr;
         // pixel-side identity
@@ -497,7 +500,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                     // ---- lane side: bias -> activation -> (BN affine * scale) -> + residual.  Padded channels
                     //      (co >= cout) come out as exact zeros: zero weights, bias 0, shift 0.
                     float f[16];
-                    if (act == PCNN_ACT_LEAKY_RELU) {
+                    if (act == PCNN_ACT_LEAKY_RELU && !affine) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float a = fmaf(__uint_as_float(v[j]), asc, bias);
+                            f[j] = fmaxf(a, 0.2f * a);
+                        }
+                    } else if (act == PCNN_ACT_LEAKY_RELU) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             float a = fmaf(__uint_as_float(v[j]), asc, bias);
@@ -1016,7 +1025,15 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
         PCNN_CHECK_LAUNCH();
         return PCNN_OK;
     };
-    if (cp == 32) return launch(conv_tc_kernel<32>);
-    if (cp == 16) return launch(conv_tc_kernel<16>);
-    return launch(conv_tc_kernel<8>);
+#define PCNN_TC_DISPATCH(CPV)                                         \
+    if (cp == CPV) {                                                  \
+        if (nsplit == 1) return launch(conv_tc_kernel<CPV, 1>);       \
+        if (nsplit == 2) return launch(conv_tc_kernel<CPV, 2>);       \
+        return launch(conv_tc_kernel<CPV, 3>);                        \
+    }
+    PCNN_TC_DISPATCH(32)
+    PCNN_TC_DISPATCH(16)
+    PCNN_TC_DISPATCH(8)
+#undef PCNN_TC_DISPATCH
+    return PCNN_ERR_INVALID_ARGUMENT;
 }
