@@ -72,6 +72,10 @@ class Dirichlet_BC_NN_Legacy_2(WeightedModel):
     def weight_specs(self, prefix=""):
         return W.dbcnn_weight_specs(self._cfg, prefix)
 
+    def keras_key_map(self, prefix=""):
+        from .. import tf_checkpoint as T
+        return T.dbcnn_key_map(self._cfg, "", prefix)
+
     def _resnet1d(self, x, name, act, pad, pad_value, use_bn):
         k0, b0 = self.conv(name + "/conv0")
         k1, b1 = self.conv(name + "/conv1")

@@ -130,6 +130,10 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
             if sc.get("kernel_size", 3) % 2 == 0:
                 raise NotImplementedError("Scaling: even kernel sizes with Keras 'same' padding are not built")
 
+    def keras_key_map(self, prefix=""):
+        from .. import tf_checkpoint as T
+        return T.hpnn_key_map(self._cfg, "", prefix)
+
     # layer-name prefixes whose tc2 correction pass is skipped (precision experiments / 'mixed' mode)
     tc_uncorrected = ()
 

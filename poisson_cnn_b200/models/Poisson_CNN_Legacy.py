@@ -30,10 +30,13 @@ class Poisson_CNN_Legacy(WeightedModel):
         ds, dm = self.dbcnn.weight_specs(prefix + "dbcnn/")
         return {**hs, **ds}, {**hm, **dm}
 
+    def keras_key_map(self, prefix=""):
+        from .. import tf_checkpoint as T
+        return T.pcnn_key_map(self.hpnn._cfg, self.dbcnn._cfg, prefix)
+
     def load_weights(self, source, prefix="", device=None):
-        from .. import weights as W
         if isinstance(source, str):
-            source = W.load_npz(source)
+            source = self._read_weight_file(source, prefix)     # TF checkpoint prefix (reference format) or .npz
         self.hpnn.load_weights(source, prefix + "hpnn/", device)
         self.dbcnn.load_weights(source, prefix + "dbcnn/", device)
         self.device = self.hpnn.device

@@ -12,7 +12,8 @@ class WeightedModel:
 
     The reference creates its variables on the first call and fills them with
     model.load_weights(checkpoint_prefix) (poisson_CNN/train/utils.py:12-15).  Here
-    load_weights() accepts an .npz written by weights.save_npz(), or a {name: array} dict.
+    load_weights() accepts the prefix of such a TF checkpoint (pure-Python reader, tf_checkpoint.py), an .npz
+    written by weights.save_npz(), or a {name: array} dict.
     """
 
     def __init__(self):
@@ -29,7 +30,7 @@ class WeightedModel:
 
     def load_weights(self, source, prefix="", device=None):
         if isinstance(source, str):
-            source = W.load_npz(source)
+            source = self._read_weight_file(source, prefix)
         if device is None:
             device = self.device or torch.device("cuda", torch.cuda.current_device())
         self.device = torch.device(device)
@@ -55,6 +56,20 @@ class WeightedModel:
 
     def _on_weights_loaded(self):
         self._tc = {}
+
+    def keras_key_map(self, prefix=""):
+        """{reference Keras attribute path: variable name} (tf_checkpoint.py); provided by the model classes."""
+        raise NotImplementedError
+
+    def _read_weight_file(self, path, prefix=""):
+        """`path` is either an .npz written by weights.save_npz() or the PREFIX of a TensorFlow checkpoint as
+        written by the reference (model.save_weights / ModelCheckpoint(save_weights_only=True)):
+        <prefix>.index + <prefix>.data-00000-of-00001, read by the pure-Python tensor-bundle reader."""
+        import os
+        if os.path.isfile(path + ".index"):
+            from .. import tf_checkpoint as T
+            return T.load_checkpoint_weights(path, self.keras_key_map(prefix))
+        return W.load_npz(path)
 
     PRECISIONS = ("fp32", "tc", "tc2", "tc3", "mixed")
     _TC_MODE = {"tc": 1, "tc3": 2, "tc2": 3}

@@ -35,9 +35,10 @@ def test_variable_aspect_grids_tc2_tracks_fp32(model, nx, ny, B):
     """BASELINE config 3 shapes (non-square: 2B+2B boundary batches, ragged tiles, two column tiles)."""
     inp = _problem(B, nx, ny, seed=1003)
     ref = model.set_precision("fp32")(inp)
-    out = model.set_precision("tc2")(inp)
-    assert out.shape == (B, 1, nx, ny) and bool(torch.isfinite(out).all())
-    assert rel_l2(out, ref) < 2e-3          # tensor-core budget; typically ~3e-4
+    for mode in ("tc2", "mixed"):
+        out = model.set_precision(mode)(inp)
+        assert out.shape == (B, 1, nx, ny) and bool(torch.isfinite(out).all())
+        assert rel_l2(out, ref) < 2e-3, mode      # tensor-core budget; typically ~3e-4
     # homogeneity: the merged model normalises its inputs per sample and undoes it; with a power-of-two factor
     # every intermediate is bit-identical, so the outputs must scale exactly (a factor like 3 perturbs the
     # normalised inputs by an ulp, which this chaotic seeded network amplifies to ~1e-4 in tensor-core mode)
@@ -104,3 +105,18 @@ def test_hpnn_config1_shape_all_modes():
         assert out.shape == (4, 1, 64, 64)
         assert rel_l2(out, gold) < tol, mode
         assert float(out[:, :, 0].abs().max()) == 0.0 and float(out[:, :, :, -1].abs().max()) == 0.0
+
+
+def test_load_weights_from_tf_checkpoint_prefix(model, tmp_path):
+    """model.load_weights(<TF checkpoint prefix>) -- the reference's weight format (train/utils.py:12-15) -- through
+    the pure-Python tensor-bundle reader gives the same network as the in-memory weights."""
+    from poisson_cnn_b200 import convert_tf_object_names, models, tf_checkpoint as T
+    from tests.helpers import pcnn_configs
+    hp, db = pcnn_configs()
+    prefix = str(tmp_path / "chkpt" / "cp-0001")
+    T.save_checkpoint_weights(prefix, model.get_weights_dict(), model.keras_key_map())
+    other = models.Poisson_CNN_Legacy(models.Homogeneous_Poisson_NN_Legacy(**convert_tf_object_names(hp)),
+                                      models.Dirichlet_BC_NN_Legacy_2(**convert_tf_object_names(db))).load_weights(prefix)
+    inp = _problem(2, 64, 72, seed=1006)
+    model.set_precision("fp32"); other.set_precision("fp32")
+    assert torch.equal(model(inp), other(inp))

@@ -164,3 +164,68 @@ def test_world_size_2_gloo_sharding_and_stats():
         assert r[2]["samples"] == 5
         assert abs(r[2]["rel_l2"] - expect) < 1e-3 * expect
         assert abs(r[2]["max_abs_err"] - 2e-3) < 1e-6
+
+
+# ------------------------------------------------------------------ TF checkpoint (tensor bundle) reader
+def test_crc32c_and_snappy_known_answers():
+    from poisson_cnn_b200 import tf_checkpoint as T
+    assert T.crc32c(b"123456789") == 0xE3069283                       # the CRC-32C check value
+    assert T._mask_crc(T.crc32c(b"")) == 0xa282ead8
+    # snappy: literal "abcd" + copy(offset 4, length 8) -> "abcdabcdabcd"; preamble = uncompressed length
+    stream = bytes([12, (4 - 1) << 2]) + b"abcd" + bytes([((8 - 4) << 2) | 1, 4])
+    assert T._snappy_decompress(stream) == b"abcdabcdabcd"
+
+
+def test_table_roundtrip_prefix_compression_and_blocks(tmp_path):
+    from poisson_cnn_b200 import tf_checkpoint as T
+    items = [(("layer/%03d/kernel" % i).encode(), bytes([i % 251]) * (i % 40)) for i in range(300)] + [(b"", b"header")]
+    path = str(tmp_path / "t.index")
+    T.write_table(path, items, block_size=512)                          # many data blocks, restarts every 16 keys
+    assert T.read_table(path, verify=True) == sorted(items)
+    raw = bytearray(open(path, "rb").read())
+    raw[10] ^= 0xFF                                                     # corrupt a data block: the checksum must notice
+    open(path, "wb").write(bytes(raw))
+    with pytest.raises(ValueError):
+        T.read_table(path, verify=True)
+    with pytest.raises(ValueError):
+        T.read_table(__file__)                                          # not a table at all
+
+
+def test_keras_key_map_is_a_bijection_onto_the_weight_specs():
+    from poisson_cnn_b200 import load_experiment, weights as W, tf_checkpoint as T
+    cfg = load_experiment("pcnn_end_to_end")
+    hp, db = cfg["hpnn_model"], cfg["dbcnn_model"]
+    specs = {**W.hpnn_weight_specs(hp, "hpnn/")[0], **W.dbcnn_weight_specs(db, "dbcnn/")[0]}
+    m = T.pcnn_key_map(hp, db)
+    assert sorted(m.values()) == sorted(specs)                          # every variable has exactly one reference key
+    assert len(set(m)) == len(m)
+    # spot checks against the reference's attribute structure
+    assert m["hpnn/pre_bottleneck_convolutions/0/kernel"] == "hpnn/pre_bottleneck/0/kernel"
+    ds = hp["bottleneck_deconv_config"]["downsampling_factors"]
+    j = sorted(range(len(ds)), key=lambda i: ds[i], reverse=True).index(0)   # the reference sorts blocks by ds, descending
+    assert m["hpnn/bottleneck_deconv_blocks/%d/upsample_layer/kernel" % j] == "hpnn/bottleneck_deconv/0/deconv/kernel"
+    assert m["hpnn/bottleneck_deconv_blocks/%d/conv_layers/1/conv_layers/2/bias" % j] == "hpnn/bottleneck_deconv/0/resnet1/conv2/bias"
+    assert m["hpnn/final_convolutions/1/conv_layers/0/kernel"] == "hpnn/final/0/resnet/conv0/kernel"
+    assert m["dbcnn/domain_info_dense_layers/0/kernel"] == "dbcnn/mlp/0/kernel"
+
+
+def test_tf_checkpoint_roundtrip_through_load_checkpoint_weights(tmp_path):
+    from poisson_cnn_b200 import load_experiment, weights as W, tf_checkpoint as T
+    cfg = load_experiment("pcnn_end_to_end")
+    hp, db = cfg["hpnn_model"], cfg["dbcnn_model"]
+    hs, ds = W.hpnn_weight_specs(hp, "hpnn/"), W.dbcnn_weight_specs(db, "dbcnn/")
+    specs = {k: v for k, v in {**hs[0], **ds[0]}.items() if int(np.prod(v)) <= 4096}     # small tensors: the pure-Python CRC is slow
+    meta = {k: {**hs[1], **ds[1]}[k] for k in specs}
+    w = W.synthetic_weights((specs, meta), seed=3)
+    key_map = {k: v for k, v in T.pcnn_key_map(hp, db).items() if v in specs}
+    prefix = str(tmp_path / "ckpt" / "weights-01")
+    T.save_checkpoint_weights(prefix, w, key_map)
+    assert os.path.isfile(prefix + ".index") and os.path.isfile(prefix + ".data-00000-of-00001")
+    back = T.load_checkpoint_weights(prefix, key_map, verify=True)
+    assert sorted(back) == sorted(w)
+    for k in w:
+        np.testing.assert_array_equal(back[k], w[k])
+    raw = T.read_tensor_bundle(prefix)
+    assert all(k.endswith(T.SUFFIX) for k in raw)
+    with pytest.raises(ValueError):                                     # a variable the model needs but the file lacks
+        T.load_checkpoint_weights(prefix, {**key_map, "hpnn/not_there": "hpnn/not_there"})
