@@ -171,6 +171,18 @@ int pcnn_dst_solve(const float* rhs, const float* left, const float* top, const 
                    const float* bottom, const float* dx, const double* sx, const double* sy,
                    double* work, float* out, int B, int nx, int ny, void* stream);
 
+/* Fused 1-D convolution stack (csrc/boundary_stack.cu): n_layers Conv1D layers (Keras kernels [k][Cin][Cout],
+ * odd k <= 19, <= 28 channels) applied back to back to every signal of in [B][Cin0][n], all activations staying in
+ * shared memory.  Per layer: tf.pad(pad_mode) -> conv -> bias -> act -> BN affine (bn_scale/bn_shift may be NULL per
+ * layer); flags[l] & 1 saves the layer's INPUT, flags[l] & 2 adds the saved tensor after act/BN -- a resnet
+ * (blocks/resnet.py:29-39) is the three layers {1, 2, 0}.  Replaces the boundary_convolution_ops loop of
+ * models/Dirichlet_BC_NN_Legacy.py:136-141 (32 launches).  The pointer arrays are HOST arrays of device pointers. */
+int pcnn_boundary_stack_f32(const float* in, float* out, int B, int n, int Cin0, int n_layers,
+                            const float* const* kernels, const float* const* biases,
+                            const float* const* bn_scale, const float* const* bn_shift, const int* ksize,
+                            const int* cin, const int* cout, const int* flags, int act, int pad_mode,
+                            float pad_value, void* stream);
+
 /* ---- tensor-core path (tcgen05 / TMEM / TMA bulk copies), csrc/conv_tc.cu ---------------------
  * Activations live in the "BLK8" layout: fp16 [B][Cpad/8][H+14][W+14][8] with Cpad = round_up(C,16)
  * and a 7-pixel halo materialised in memory (zero = CONSTANT padding; pcnn_blk8_halo_fill mirrors it

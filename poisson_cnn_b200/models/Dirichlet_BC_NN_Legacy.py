@@ -84,6 +84,22 @@ class Dirichlet_BC_NN_Legacy_2(WeightedModel):
         t = ops.conv1d(t, k1, b1, act, pad, pad_value, bn=self.bn(name + "/bn1") if use_bn else None, residual=x)
         return ops.conv1d(t, k2, b2, act, pad, pad_value)
 
+    def _boundary_layers(self):
+        """Layer program of the boundary stack for ops.boundary_stack (flags: 1 save input, 2 add saved)."""
+        key = ("boundary_stack",)
+        if key not in self._tc:                  # cleared whenever weights are (re)loaded
+            layers = []
+            for k in range(self.n_boundary):
+                kk, bb = self.conv("boundary/%d/conv" % k)
+                layers.append({"kernel": kk, "bias": bb, "bn": self.bn("boundary/%d/bn" % k) if self.use_batchnorm else None, "flags": 0})
+                name = "boundary/%d/resnet" % k
+                for c, fl in enumerate((1, 2, 0)):
+                    kc, bc_ = self.conv("%s/conv%d" % (name, c))
+                    bn = self.bn("%s/bn%d" % (name, c)) if (self.use_batchnorm and c < 2) else None
+                    layers.append({"kernel": kc, "bias": bc_, "bn": bn, "flags": fl})
+            self._tc[key] = layers
+        return self._tc[key]
+
     def _resnet2d(self, x, name, act):
         k0, b0 = self.conv(name + "/conv0")
         k1, b1 = self.conv(name + "/conv1")
@@ -106,12 +122,17 @@ class Dirichlet_BC_NN_Legacy_2(WeightedModel):
         x_res = int(x_res)
         B, _, n = bc.shape
         h = ops.dbcnn_input(bc, x_res)
-        for k in range(self.n_boundary):
-            kk, bb = self.conv("boundary/%d/conv" % k)
-            h = ops.conv1d(h, kk, bb, self.boundary_act, self.boundary_pad, self.boundary_pad_value,
-                           bn=self.bn("boundary/%d/bn" % k) if self.use_batchnorm else None)
-            h = self._resnet1d(h, "boundary/%d/resnet" % k, self.boundary_act, self.boundary_pad,
-                               self.boundary_pad_value, self.use_batchnorm)
+        stack = self._boundary_layers()
+        if ops.boundary_stack_supported(n, stack):
+            # the whole 1-D stack (n_boundary x (conv [+BN] + resnet)) in ONE kernel, activations in shared memory
+            h = ops.boundary_stack(h, stack, self.boundary_act, self.boundary_pad, self.boundary_pad_value)
+        else:
+            for k in range(self.n_boundary):
+                kk, bb = self.conv("boundary/%d/conv" % k)
+                h = ops.conv1d(h, kk, bb, self.boundary_act, self.boundary_pad, self.boundary_pad_value,
+                               bn=self.bn("boundary/%d/bn" % k) if self.use_batchnorm else None)
+                h = self._resnet1d(h, "boundary/%d/resnet" % k, self.boundary_act, self.boundary_pad,
+                                   self.boundary_pad_value, self.use_batchnorm)
         spp = ops.spatial_pyramid_pool(h, self.spp_levels, self.spp_mode, ndims=1)
         v = ops.dense_input(dx, x_res, n, extra=spp, normalize=True)
         for i in range(self.n_mlp):

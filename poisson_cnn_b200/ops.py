@@ -106,6 +106,42 @@ def conv1d(x, kernel, bias=None, act=ACT_LINEAR, pad_mode=PAD_CONSTANT, pad_valu
     return conv2d(x.unsqueeze(2), kernel.unsqueeze(0), bias, act, pad_mode, pad_value, bn, r).squeeze(2)
 
 
+def boundary_stack_supported(n, layers):
+    """The fused 1-D stack keeps three [28, n+18] activation buffers and one layer's weights in shared memory."""
+    if not layers or len(layers) > 48:
+        return False
+    wmax = max(l["kernel"].shape[0] * l["kernel"].shape[1] * 32 for l in layers)
+    ok = all(l["kernel"].shape[0] % 2 == 1 and l["kernel"].shape[0] <= 19 and max(l["kernel"].shape[1:]) <= 28 for l in layers)
+    return ok and (3 * 28 * ((n + 18 + 3) // 4 * 4) + wmax) * 4 <= 220 * 1024
+
+
+def boundary_stack(x, layers, act, pad_mode=PAD_CONSTANT, pad_value=0.0):
+    """Fused Conv1D stack.  x [B,C,n]; layers: [{"kernel": [k,Cin,Cout], "bias": t|None, "bn": (scale, shift)|None,
+    "flags": 0|1 (save input)|2 (add saved)}] -> [B, Cout_last, n]."""
+    import ctypes
+    _chk(x, "x")
+    x = x.contiguous()
+    B, C, n = x.shape
+    L = len(layers)
+    keep = [l["kernel"].contiguous() for l in layers]
+
+    def arr_p(vals):
+        return (ctypes.c_void_p * L)(*vals)
+
+    def arr_i(vals):
+        return (ctypes.c_int * L)(*[int(v) for v in vals])
+    for l, kern in zip(layers, keep):
+        _chk(kern, "kernel")
+    out = torch.empty((B, keep[-1].shape[2], n), device=x.device, dtype=torch.float32)
+    check(lib.pcnn_boundary_stack_f32(
+        _p(x), _p(out), B, n, C, L, arr_p([k.data_ptr() for k in keep]), arr_p([_p(l.get("bias")) for l in layers]),
+        arr_p([None if l.get("bn") is None else l["bn"][0].data_ptr() for l in layers]),
+        arr_p([None if l.get("bn") is None else l["bn"][1].data_ptr() for l in layers]),
+        arr_i([k.shape[0] for k in keep]), arr_i([k.shape[1] for k in keep]), arr_i([k.shape[2] for k in keep]),
+        arr_i([l.get("flags", 0) for l in layers]), int(act), int(pad_mode), float(pad_value), _stream()), "boundary_stack")
+    return out
+
+
 def avgpool_same(x, s):
     in_bs = _nchw_bstride(x, "x")
     B, C, H, W = x.shape

@@ -86,6 +86,35 @@ def test_conv1d_parity(ops):
         assert rel_l2(got, ref) < FP32_TOL
 
 
+@pytest.mark.parametrize("n,pad,act", [(256, "SYMMETRIC", "leaky_relu"), (50, "CONSTANT", "tanh"), (131, "REFLECT", "leaky_relu")])
+def test_boundary_stack_parity(ops, n, pad, act):
+    """Fused Conv1D stack (conv + BN, then a resnet, per stage) vs the oracle's layer-by-layer evaluation."""
+    from poisson_cnn_b200.config import activation_enum, padding_enum
+    g = torch.Generator().manual_seed(n)
+    B, chans, ks = 3, [3, 4, 12, 27], [19, 9, 5]
+    x = torch.randn(B, chans[0], n, generator=g)
+    layers, ref = [], x.double()
+    for cin, cout, k in zip(chans[:-1], chans[1:], ks):
+        specs = [(cin, cout, True, 0), (cout, cout, True, 1), (cout, cout, True, 2), (cout, cout, False, 0)]
+        saved = None
+        for ci, co, has_bn, fl in specs:
+            kern = torch.randn(k, ci, co, generator=g) / (k * ci) ** 0.5
+            bias = torch.randn(co, generator=g) * 0.1
+            bn = (torch.rand(co, generator=g) + 0.5, torch.randn(co, generator=g) * 0.1) if has_bn else None
+            layers.append({"kernel": dev(kern), "bias": dev(bias), "bn": None if bn is None else (dev(bn[0]), dev(bn[1])), "flags": fl})
+            if fl == 1:
+                saved = ref
+            ref = O.conv_nd(ref, kern.double(), bias.double(), act, pad, 0.25)
+            if bn is not None:
+                ref = ref * bn[0].double().view(1, -1, 1) + bn[1].double().view(1, -1, 1)
+            if fl == 2:
+                ref = ref + saved
+    assert ops.boundary_stack_supported(n, layers)
+    got = ops.boundary_stack(dev(x), layers, activation_enum(act), padding_enum(pad), 0.25)
+    assert got.shape == ref.shape
+    assert rel_l2(got, ref) < FP32_TOL
+
+
 @pytest.mark.parametrize("H,W", [(200, 300), (64, 64), (109, 130)])
 def test_avgpool_same_parity(ops, H, W):
     x = torch.randn(2, 5, H, W, generator=torch.Generator().manual_seed(H))
