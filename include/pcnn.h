@@ -183,6 +183,15 @@ int pcnn_boundary_stack_f32(const float* in, float* out, int B, int n, int Cin0,
                             const int* cin, const int* cout, const int* flags, int act, int pad_mode,
                             float pad_value, void* stream);
 
+/* The same fused layer program on tiny 2-D maps, H*W <= 64 (csrc/smallmap_stack.cu): the conv + resnet chain of a
+ * bottleneck branch whose pooled map is 2x2 .. 8x8 (blocks/bottleneck_block.py:36-50 at downsampling 32/64/128).
+ * Keras Conv2D kernels [k][k][Cin][Cout], odd k <= 7, <= 32 channels; in [B][Cin0][H][W] -> out [B][Cout_last][H][W]. */
+int pcnn_smallmap_stack_f32(const float* in, float* out, int B, int H, int W, int Cin0, int n_layers,
+                            const float* const* kernels, const float* const* biases,
+                            const float* const* bn_scale, const float* const* bn_shift, const int* ksize,
+                            const int* cin, const int* cout, const int* flags, int act, int pad_mode,
+                            float pad_value, void* stream);
+
 /* ---- tensor-core path (tcgen05 / TMEM / TMA bulk copies), csrc/conv_tc.cu ---------------------
  * Activations live in the "BLK8" layout: fp16 [B][Cpad/8][H+14][W+14][8] with Cpad = round_up(C,16)
  * and a 7-pixel halo materialised in memory (zero = CONSTANT padding; pcnn_blk8_halo_fill mirrors it

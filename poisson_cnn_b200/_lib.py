@@ -20,6 +20,7 @@ SIGNATURES = {
     "pcnn_conv2d_f32": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_float, c_int, c_int64, c_int64, c_int64, P]),
     "pcnn_boundary_stack_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_int, c_int, c_float, P]),
+    "pcnn_smallmap_stack_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P, P, c_int, c_int, c_float, P]),
     "pcnn_avgpool_same_f32": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_int64, P]),
     "pcnn_deconv_same_f32": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_int, c_int, c_float, c_int, c_int64, P]),

@@ -18,6 +18,19 @@ constexpr int PADMAX = 9;     // kernel sizes up to 19
 constexpr int CMAX = 28;      // channels (4 channel groups x 7)
 constexpr int NTHR = 256;
 
+// asynchronous global -> shared copies (all of a layer's weights in flight at once; the scalar ldg/sts loop this replaces
+// exposed one L2 round trip per element)
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    const int bytes = valid ? 4 : 0;      // src-size 0: zero fill
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+
 struct Params {
     const float* in; float* out;
     const float* kernel[MAXL]; const float* bias[MAXL]; const float* bn_scale[MAXL]; const float* bn_shift[MAXL];
@@ -58,8 +71,9 @@ __global__ void __launch_bounds__(NTHR) boundary_stack_kernel(const Params p) {
         // weights: Keras Conv1D [k][cin][cout] -> smem [k][cin][32]
         for (int e = tid; e < k * cin * 32; e += NTHR) {
             const int co = e & 31, r = e >> 5;
-            s_w[e] = co < cout ? __ldg(p.kernel[l] + (long long)r * cout + co) : 0.f;
+            cp_async4(s_w + e, p.kernel[l] + (long long)r * cout + min(co, cout - 1), co < cout);
         }
+        cp_async_wait_all();
         if (p.flags[l] & 1) saved = cur;
         int dst = 0;
         while (dst == cur || dst == saved) ++dst;

@@ -150,6 +150,21 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
         t = ops.conv2d(t, k1, b1, act, pad, pad_value, bn=self.bn(name + "/bn1") if use_bn else None, residual=x)
         return ops.conv2d(t, k2, b2, act, pad, pad_value, out_scale=out_scale)
 
+    def _branch_layers(self, blk, name):
+        """Layer program of a bottleneck branch for ops.smallmap_stack (flags: 1 save input, 2 add saved)."""
+        key = ("branch_stack", name)
+        if key not in self._tc:                  # cleared whenever weights are (re)loaded
+            k, b = self.conv(name + "/conv0")
+            layers = [{"kernel": k, "bias": b, "bn": None, "flags": 0}]
+            for r in range(1, blk.n_convs):
+                rn = "%s/resnet%d" % (name, r)
+                for c, fl in enumerate((1, 2, 0)):
+                    kc, bc_ = self.conv("%s/conv%d" % (rn, c))
+                    bn = self.bn("%s/bn%d" % (rn, c)) if (blk.use_batchnorm and c < 2) else None
+                    layers.append({"kernel": kc, "bias": bc_, "bn": bn, "flags": fl})
+            self._tc[key] = layers
+        return self._tc[key]
+
     def _branch_out_hw(self, blk, H, Wd):
         out_hw = (bottleneck_output_size(H, blk.downsampling_factor, blk.upsampling_factor),
                   bottleneck_output_size(Wd, blk.downsampling_factor, blk.upsampling_factor))
@@ -162,6 +177,10 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
         """pool -> conv -> resnets of one branch (blocks/bottleneck_block.py:36-50), FP32 kernels."""
         name = "bottleneck_%s/%d" % (blk.kind, blk.index)
         h = ops.avgpool_same(x0, blk.downsampling_factor)
+        stack = self._branch_layers(blk, name)
+        if ops.smallmap_stack_supported(h.shape[2], h.shape[3], stack):
+            # 2x2 .. 8x8 maps: the whole conv + resnet chain in ONE kernel, activations in shared memory
+            return ops.smallmap_stack(h, stack, blk.act, blk.pad, blk.pad_value)
         k, b = self.conv(name + "/conv0")
         h = ops.conv2d(h, k, b, blk.act, blk.pad, blk.pad_value)
         for r in range(1, blk.n_convs):

@@ -142,6 +142,43 @@ def boundary_stack(x, layers, act, pad_mode=PAD_CONSTANT, pad_value=0.0):
     return out
 
 
+def smallmap_stack_supported(H, W, layers):
+    """The fused 2-D small-map stack: maps of <= 64 pixels, odd kernels <= 7, <= 32 channels, everything in shared memory."""
+    if not layers or len(layers) > 24 or H * W > 64:
+        return False
+    ok = all(l["kernel"].shape[0] == l["kernel"].shape[1] and l["kernel"].shape[0] % 2 == 1 and l["kernel"].shape[0] <= 7
+             and max(l["kernel"].shape[2:]) <= 32 for l in layers)
+    if not ok:
+        return False
+    pm = max(l["kernel"].shape[0] // 2 for l in layers)
+    wmax = max(l["kernel"].shape[0] ** 2 * l["kernel"].shape[2] * 32 for l in layers)
+    return (3 * 32 * (H + 2 * pm) * (W + 2 * pm) + wmax) * 4 <= 220 * 1024
+
+
+def smallmap_stack(x, layers, act, pad_mode=PAD_CONSTANT, pad_value=0.0):
+    """Fused Conv2D stack on a tiny map.  x [B,C,H,W] (H*W <= 64); layers as in boundary_stack with Keras Conv2D kernels."""
+    import ctypes
+    _chk(x, "x")
+    x = x.contiguous()
+    B, C, H, W = x.shape
+    L = len(layers)
+    keep = [_chk(l["kernel"], "kernel").contiguous() for l in layers]
+
+    def arr_p(vals):
+        return (ctypes.c_void_p * L)(*vals)
+
+    def arr_i(vals):
+        return (ctypes.c_int * L)(*[int(v) for v in vals])
+    out = torch.empty((B, keep[-1].shape[3], H, W), device=x.device, dtype=torch.float32)
+    check(lib.pcnn_smallmap_stack_f32(
+        _p(x), _p(out), B, H, W, C, L, arr_p([k.data_ptr() for k in keep]), arr_p([_p(l.get("bias")) for l in layers]),
+        arr_p([None if l.get("bn") is None else l["bn"][0].data_ptr() for l in layers]),
+        arr_p([None if l.get("bn") is None else l["bn"][1].data_ptr() for l in layers]),
+        arr_i([k.shape[0] for k in keep]), arr_i([k.shape[2] for k in keep]), arr_i([k.shape[3] for k in keep]),
+        arr_i([l.get("flags", 0) for l in layers]), int(act), int(pad_mode), float(pad_value), _stream()), "smallmap_stack")
+    return out
+
+
 def avgpool_same(x, s):
     in_bs = _nchw_bstride(x, "x")
     B, C, H, W = x.shape

@@ -86,6 +86,32 @@ def test_conv1d_parity(ops):
         assert rel_l2(got, ref) < FP32_TOL
 
 
+@pytest.mark.parametrize("H,W,pad", [(8, 8, "CONSTANT"), (2, 2, "SYMMETRIC"), (4, 7, "SYMMETRIC"), (3, 5, "REFLECT")])
+def test_smallmap_stack_parity(ops, H, W, pad):
+    """Fused Conv2D stack on a tiny map (conv, then two resnets with BN) vs the oracle's layer-by-layer evaluation."""
+    from poisson_cnn_b200.config import padding_enum
+    g = torch.Generator().manual_seed(H * 10 + W)
+    B, C, k = 3, 32, 5
+    x = torch.randn(B, C, H, W, generator=g)
+    layers, ref, saved = [], x.double(), None
+    for has_bn, fl in [(False, 0)] + [(True, 1), (True, 2), (False, 0)] * 2:
+        kern = torch.randn(k, k, C, C, generator=g) / (k * C ** 0.5)
+        bias = torch.randn(C, generator=g) * 0.1
+        bn = (torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1) if has_bn else None
+        layers.append({"kernel": dev(kern), "bias": dev(bias), "bn": None if bn is None else (dev(bn[0]), dev(bn[1])), "flags": fl})
+        if fl == 1:
+            saved = ref
+        ref = O.conv_nd(ref, kern.double(), bias.double(), "leaky_relu", pad, 0.0)
+        if bn is not None:
+            ref = ref * bn[0].double().view(1, -1, 1, 1) + bn[1].double().view(1, -1, 1, 1)
+        if fl == 2:
+            ref = ref + saved
+    assert ops.smallmap_stack_supported(H, W, layers)
+    got = ops.smallmap_stack(dev(x), layers, 1, padding_enum(pad), 0.0)
+    assert got.shape == ref.shape
+    assert rel_l2(got, ref) < FP32_TOL
+
+
 @pytest.mark.parametrize("n,pad,act", [(256, "SYMMETRIC", "leaky_relu"), (50, "CONSTANT", "tanh"), (131, "REFLECT", "leaky_relu")])
 def test_boundary_stack_parity(ops, n, pad, act):
     """Fused Conv1D stack (conv + BN, then a resnet, per stage) vs the oracle's layer-by-layer evaluation."""
