@@ -153,6 +153,9 @@ def run_reference(args):
 
 
 def run_ours(args):
+    # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION) would land there too
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch.distributed as dist
     from poisson_cnn_b200 import ops, _lib
     from poisson_cnn_b200.sharding import init_from_env
