@@ -56,6 +56,18 @@ class Poisson_CNN_Legacy(WeightedModel):
         mb = self.microbatch_samples            # explicit slice size, if set
         if mb is None and self.max_microbatch:
             mb = max(1, int(self.max_microbatch * 65536 // (nx * ny)))
+        try:
+            return self._run(rhs, left, top, right, bottom, dx, mb)
+        except torch.OutOfMemoryError:
+            # the activation-buffer pool keeps one set of buffers per tensor shape ever seen in this process; when a
+            # new grid shape does not fit next to the idle ones, they are released and the call is repeated once
+            from .. import ops
+            ops.blk8_pool_clear()
+            torch.cuda.empty_cache()
+            return self._run(rhs, left, top, right, bottom, dx, mb)
+
+    def _run(self, rhs, left, top, right, bottom, dx, mb):
+        B, _, nx, ny = rhs.shape
         if mb and B > mb:
             out = torch.empty((B, 1, nx, ny), device=rhs.device, dtype=torch.float32)
             for lo in range(0, B, mb):
