@@ -236,7 +236,7 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
         alpha = 1.0 / float(len(blocks) * F)
         dc, rs = [], []                          # low-res branch outputs, upsampled and summed by ONE fused kernel
         # 'mixed': the branches are averaged with weight 1/(8*F) before they re-enter the trunk -- measured: running
-        # them single-pass changes the merged model's error by < 1e-6 (scripts/layer_sensitivity_probe.py)
+        # them single-pass changes the merged model's error by < 1e-6 (tests/probes/layer_sensitivity_probe.py)
         bsplit = 1 if self.requested_precision == "mixed" else split
         for blk in blocks:
             self._branch_out_hw(blk, H, Wd)

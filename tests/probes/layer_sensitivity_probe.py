@@ -1,6 +1,6 @@
 """Error of the merged model (HPNN tc2, DBCNN tc) when groups of HPNN layers skip their correction pass."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import bench
 from oracle import poisson_oracle as O

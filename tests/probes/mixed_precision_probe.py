@@ -1,6 +1,6 @@
 """Error of mixed precision assignments (HPNN mode, DBCNN mode) vs the float64 oracle on bench-like inputs."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import bench
 from oracle import poisson_oracle as O
