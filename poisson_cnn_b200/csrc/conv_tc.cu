@@ -789,46 +789,68 @@ __global__ void __launch_bounds__(128) blk8_halo_fill_kernel(__half* __restrict_
 }
 
 // DBCNN mode expansion straight into BLK8: out[b, m, x, y] = h[b,m,y] * S[m,x] * w[b,m]; channels M, M+1 = pos.
-// grid (ceil(n/128), xres, B*np), thread = one 16-byte pixel of one plane.
+// grid (ceil(n/128), ceil(xres/EXP_ROWS), B): a thread owns one column y, keeps h[b,.,y] in registers and walks
+// EXP_ROWS rows x (S[.,x] and w[b,.] staged in shared memory), writing 16-byte units: h is read once per 16 rows
+// instead of once per row.
+constexpr int EXP_ROWS = 16;
 __global__ void __launch_bounds__(128) dbcnn_expand_blk8_kernel(const float* __restrict__ h, const float* __restrict__ S,
                                                                 const float* __restrict__ mw, const float* __restrict__ posx,
                                                                 const float* __restrict__ posy, __half* __restrict__ out,
                                                                 __half* __restrict__ out_lo, int M, int xres, int n,
                                                                 int c8_total, int np, int mode) {
-    const int y = blockIdx.x * 128 + threadIdx.x, x = blockIdx.y;
+    __shared__ float s_S[EXP_ROWS][32], s_w[32], s_px[EXP_ROWS];
+    const int y = blockIdx.x * 128 + threadIdx.x, x0 = blockIdx.y * EXP_ROWS, b = blockIdx.z;
+    for (int e = threadIdx.x; e < EXP_ROWS * 32; e += 128) {
+        const int r = e >> 5, m = e & 31;
+        s_S[r][m] = (m < M && x0 + r < xres) ? __ldg(S + (long long)m * xres + x0 + r) : 0.f;
+    }
+    if (threadIdx.x < 32) s_w[threadIdx.x] = threadIdx.x < M ? __ldg(mw + (long long)b * M + threadIdx.x) : 0.f;
+    if (threadIdx.x < EXP_ROWS) s_px[threadIdx.x] = x0 + threadIdx.x < xres ? __ldg(posx + x0 + threadIdx.x) : 0.f;
+    __syncthreads();
     if (y >= n) return;
     const int Hp = xres + 2 * HALO, P = n + 2 * HALO;
-    const int b = blockIdx.z / np, pl = blockIdx.z - b * np;
-    __align__(16) __half v[8];
-    __align__(16) __half l[8];
-    float f[8];
+    const float py = __ldg(posy + y);
+    float hv[32];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int m = pl * 8 + e;
-        f[e] = 0.f;
-        if (m < M) f[e] = __ldg(h + ((long long)b * M + m) * n + y) * __ldg(S + (long long)m * xres + x) * __ldg(mw + (long long)b * M + m);
-        else if (m == M) f[e] = __ldg(posx + x);
-        else if (m == M + 1) f[e] = __ldg(posy + y);
-        v[e] = __float2half_rn(f[e]);
-        l[e] = __float2half_rn(f[e] - __half2float(v[e]));
-    }
-    const size_t off = ((((size_t)b * c8_total + pl) * Hp + (x + HALO)) * P + (y + HALO)) * 8;
-    *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(v);
-    if (out_lo && mode == 2) *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(l);
-    if (out_lo && mode == 3) {
-        // fp8 planes 2(pl/2), 2(pl/2)+1, bytes [8*(pl&1), +8): each thread fills its half of the 16-channel group
-        uint8_t* q = reinterpret_cast<uint8_t*>(out_lo);
-        __align__(8) uint8_t a8[8];
-        __align__(8) uint8_t l8[8];
+    for (int m = 0; m < 32; ++m) hv[m] = m < M ? __ldg(h + ((long long)b * M + m) * n + y) : 0.f;
+    const size_t plane_px = (size_t)Hp * P;
+    for (int r = 0; r < EXP_ROWS && x0 + r < xres; ++r) {
+        const size_t pix = (size_t)(x0 + r + HALO) * P + (y + HALO);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            a8[e] = to_e4m3(f[e]);
-            l8[e] = to_e4m3((f[e] - __half2float(v[e])) * LO_SCALE);
+        for (int pl = 0; pl < 4; ++pl) {
+            if (pl < np) {
+                __align__(16) __half v[8];
+                __align__(16) __half l[8];
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int m = pl * 8 + e;
+                    f[e] = hv[m] * s_S[r][m] * s_w[m];           // zero for m >= M
+                    if (m == M) f[e] = s_px[r];
+                    else if (m == M + 1) f[e] = py;
+                    v[e] = __float2half_rn(f[e]);
+                    l[e] = __float2half_rn(f[e] - __half2float(v[e]));
+                }
+                const size_t off = (((size_t)b * c8_total + pl) * plane_px + pix) * 8;
+                *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(v);
+                if (out_lo && mode == 2) *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(l);
+                if (out_lo && mode == 3) {
+                    // fp8 planes 2(pl/2), 2(pl/2)+1, bytes [8*(pl&1), +8): this plane is one half of its 16-channel group
+                    uint8_t* q = reinterpret_cast<uint8_t*>(out_lo);
+                    __align__(8) uint8_t a8[8];
+                    __align__(8) uint8_t l8[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        a8[e] = to_e4m3(f[e]);
+                        l8[e] = to_e4m3((f[e] - __half2float(v[e])) * LO_SCALE);
+                    }
+                    const size_t q0 = (((size_t)b * c8_total + 2 * (pl >> 1)) * plane_px + pix) * 16 + 8 * (pl & 1);
+                    const size_t q1 = q0 + plane_px * 16;
+                    *reinterpret_cast<uint2*>(q + q0) = *reinterpret_cast<const uint2*>(a8);
+                    *reinterpret_cast<uint2*>(q + q1) = *reinterpret_cast<const uint2*>(l8);
+                }
+            }
         }
-        const size_t q0 = ((((size_t)b * c8_total + 2 * (pl >> 1)) * Hp + (x + HALO)) * P + (y + HALO)) * 16 + 8 * (pl & 1);
-        const size_t q1 = q0 + (size_t)Hp * P * 16;
-        *reinterpret_cast<uint2*>(q + q0) = *reinterpret_cast<const uint2*>(a8);
-        *reinterpret_cast<uint2*>(q + q1) = *reinterpret_cast<const uint2*>(l8);
     }
 }
 
@@ -946,8 +968,8 @@ extern "C" int pcnn_dbcnn_expand_blk8(const float* h, const float* sinh_basis, c
     PCNN_CHECK_ARG(h && sinh_basis && modew && posx && posy && out && B > 0 && M > 0, "dbcnn_expand_blk8: bad argument");
     const int c8_total = ((M + 2 + 15) / 16) * 2;
     const int np = (M + 2 + 7) / 8;
-    PCNN_CHECK_ARG(xres <= 65535 && (long long)B * np <= 65535, "dbcnn_expand_blk8: grid too large");
-    dbcnn_expand_blk8_kernel<<<dim3(ceil_div(n, 128), xres, B * np), 128, 0, (cudaStream_t)stream>>>(h, sinh_basis, modew, posx, posy, (__half*)out, (__half*)out_lo, M, xres, n, c8_total, np, mode);
+    PCNN_CHECK_ARG(xres <= 65535 && B <= 65535 && M + 2 <= 32, "dbcnn_expand_blk8: grid too large or more than 30 modes");
+    dbcnn_expand_blk8_kernel<<<dim3(ceil_div(n, 128), ceil_div(xres, EXP_ROWS), B), 128, 0, (cudaStream_t)stream>>>(h, sinh_basis, modew, posx, posy, (__half*)out, (__half*)out_lo, M, xres, n, c8_total, np, mode);
     PCNN_CHECK_LAUNCH();
     return PCNN_OK;
 }
