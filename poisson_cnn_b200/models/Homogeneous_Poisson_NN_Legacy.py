@@ -173,10 +173,28 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
                              % (blk.downsampling_factor, out_hw, (H, Wd)))
         return out_hw
 
-    def _bottleneck_lowres(self, blk, x0):
+    @staticmethod
+    def _pool_pyramid(x0, factors):
+        """{s: AveragePooling2D(s, 'same')(x0)} for every downsampling factor.  Where the windows nest exactly (the
+        grid is divisible by s, so SAME pooling needs no padding at either level) level s is pooled from the largest
+        already computed level that divides it -- means of equally sized blocks compose exactly -- so x0 is read
+        once or twice instead of once per branch."""
+        H, W = x0.shape[2], x0.shape[3]
+        levels = {}
+        for s in sorted(set(factors)):
+            src, f = x0, s
+            if H % s == 0 and W % s == 0:
+                for t in sorted(levels, reverse=True):
+                    if s % t == 0 and H % t == 0 and W % t == 0:
+                        src, f = levels[t], s // t
+                        break
+            levels[s] = ops.avgpool_same(src, f)
+        return levels
+
+    def _bottleneck_lowres(self, blk, x0, pooled=None):
         """pool -> conv -> resnets of one branch (blocks/bottleneck_block.py:36-50), FP32 kernels."""
         name = "bottleneck_%s/%d" % (blk.kind, blk.index)
-        h = ops.avgpool_same(x0, blk.downsampling_factor)
+        h = pooled if pooled is not None else ops.avgpool_same(x0, blk.downsampling_factor)
         stack = self._branch_layers(blk, name)
         if ops.smallmap_stack_supported(h.shape[2], h.shape[3], stack):
             # 2x2 .. 8x8 maps: the whole conv + resnet chain in ONE kernel, activations in shared memory
@@ -238,19 +256,20 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
         # 'mixed': the branches are averaged with weight 1/(8*F) before they re-enter the trunk -- measured: running
         # them single-pass changes the merged model's error by < 1e-6 (tests/probes/layer_sensitivity_probe.py)
         bsplit = 1 if self.requested_precision == "mixed" else split
+        pools = self._pool_pyramid(x0_f32, [blk.downsampling_factor for blk in blocks])
         for blk in blocks:
             self._branch_out_hw(blk, H, Wd)
             ph, pw = -(-H // blk.downsampling_factor), -(-Wd // blk.downsampling_factor)
             name = "bottleneck_%s/%d" % (blk.kind, blk.index)
             if blk.kind == "deconv" and min(ph, pw) >= 16:
-                h = ops.to_blk8(ops.avgpool_same(x0_f32, blk.downsampling_factor), split=bsplit, halo=blk.pad)
+                h = ops.to_blk8(pools[blk.downsampling_factor], split=bsplit, halo=blk.pad)
                 h = self._conv_tc(h, name + "/conv0", blk.act, blk.pad, next_pad=blk.pad)
                 for r in range(1, blk.n_convs):
                     h = self._resnet_tc(h, "%s/resnet%d" % (name, r), blk.act, blk.pad, blk.use_batchnorm,
                                         next_pad=blk.pad if r + 1 < blk.n_convs else PAD_CONSTANT)
                 h = ops.from_blk8(h)
             else:
-                h = self._bottleneck_lowres(blk, x0_f32)
+                h = self._bottleneck_lowres(blk, x0_f32, pools[blk.downsampling_factor])
             if blk.kind == "deconv":
                 dk, db = self.conv(name + "/deconv")
                 dc.append((h, dk, db, blk.upsampling_factor, blk.deconv_act))
