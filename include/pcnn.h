@@ -216,7 +216,8 @@ int pcnn_dbcnn_expand_blk8(const float* h, const float* sinh_basis, const float*
                            int n, void* stream);
 /* Keras kernel [k,k,Cin,Cout] fp32 -> fp16 operand image of the row-group GEMM:
  * [ceil(Cin/16)][k][2][(k+2(RT-1))*CP][8] with CP = pcnn_conv_tc_channel_slots(Cout, k) channel slots per
- * output row and RT = 128/CP output rows per tile (see conv_tc.cu).  Done once per layer at load time. */
+ * output row (8, 16, 24 or 32) and RT = 128/CP (5 for CP = 24) output rows per tile (see conv_tc.cu).
+ * Done once per layer at load time. */
 int pcnn_conv_tc_channel_slots(int Cout, int k);
 size_t pcnn_conv_tc_packed_weight_bytes(int kh, int kw, int Cin, int Cout, int nsplit);
 /* scale: a power of two applied to the weights before rounding (keeps W_hi and W_lo in fp16's

@@ -45,6 +45,11 @@ constexpr int HALO = 7;            // materialised halo of the BLK8 layout (kern
 // narrow layers trade channel padding for more output rows per tile, i.e. fewer MMAs per output row
 // ((kh+RT-1)*kw per RT rows) and an epilogue whose lanes all carry live channels.
 constexpr int M_TILE = 128;
+// output rows per tile for CP channel slots: 128/CP, and 5 (120 of the 128 accumulator rows) for CP = 24
+__host__ __device__ constexpr int rows_per_tile(int cp) { return cp == 24 ? 5 : M_TILE / cp; }
+// z-rows of the packed weights per (chunk, tap, K-half): kh taps + RT-1 zero rows on each side; CP = 24 gets one more
+// so that the 128-row window of the last input row (8 rows past 5 x 24) stays inside the stage
+__host__ __device__ constexpr int packed_zrows(int kh, int cp) { return kh + 2 * (rows_per_tile(cp) - 1) + (cp == 24 ? 1 : 0); }
 constexpr int MAX_EPI_WARPS = 8;
 constexpr int CHUNK_PX = 16;                   // accumulator columns per epilogue pass
 constexpr int STAGE_WARP = CHUNK_PX * 128;     // per-warp transpose buffer: 16 pixels x 32 words
@@ -200,11 +205,11 @@ __device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cas
 __device__ __forceinline__ float2 bits_to_float2(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
 
 // ---------------------------------------------------------------- the kernel
-// CP = channel slots per output row of the M operand (32, 16 or 8); RT = 128 / CP output rows per tile.
+// CP = channel slots per output row of the M operand (32, 24, 16 or 8); RT = rows_per_tile(CP) output rows per tile.
 // MODE = precision mode of the tensors (1, 2, 3): compile-time in the epilogue, which is instruction-bound on narrow layers.
 template <int CP, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p) {
-    constexpr int RT = M_TILE / CP;      // output rows per tile
+    constexpr int RT = rows_per_tile(CP);      // output rows per tile
     constexpr int ZPAD = RT - 1;         // zero z-rows on each side of the packed weights
     extern __shared__ __align__(1024) uint8_t smem[];
     // carve-up: [row slots][weight stages][epilogue transpose buffers n_epi x 2 KB][barriers][tmem ptr]
@@ -222,8 +227,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int R = p.kh + ZPAD;   // input rows per tile (even: odd kernel + odd ZPAD)
-    const int GR = R / 2;        // rows per barrier group; row_slots is a multiple of GR so a group never wraps
+    const int R = p.kh + ZPAD;   // input rows per tile
+    // rows travel in two barrier groups per chunk: R/2 each when R is even (row_slots is then a multiple of R/2 and a
+    // group never wraps), (R+1)/2 and R/2 when it is odd (CP = 24; row_slots is then a multiple of R)
+    const int GR0 = (R + 1) / 2, GR1 = R / 2;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.row_slots; ++i) { mbar_init(row_full + i, 1); mbar_init(row_empty + i, 1); }
@@ -259,6 +266,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                 const __half* base = inp + ((size_t)b * p.c8_in + 2 * c) * plane_elems + (size_t)col0 * 8;
                 // rows travel in two groups per chunk (R is even); one mbarrier pair per group, at the group's first slot
                 for (int grp = 0, rho = 0; grp < 2; ++grp) {
+                    const int GR = grp ? GR1 : GR0;
                     mbar_wait(row_empty + slot, ph ^ 1);
                     if (leader) {
                         mbar_expect_tx(row_full + slot, (uint32_t)GR * 2u * p.row_copy_bytes);
@@ -302,7 +310,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
         // registers); one elected lane issues tcgen05.mma / tcgen05.commit.  Everything per MMA is
         // incremental: descriptor low words advance by constants, ring slots wrap by compare.
         {
-            const uint32_t a_lbo = (uint32_t)(p.kh + 2 * ZPAD) * (CP * 16u);   // K-half (plane) stride of the packed weights
+            const uint32_t a_lbo = (uint32_t)packed_zrows(p.kh, CP) * (CP * 16u);   // K-half (plane) stride of the packed weights
             const uint32_t a_hi = (uint32_t)(make_desc(0, a_lbo, 128u) >> 32);
             const uint32_t b_hi = (uint32_t)(make_desc(0, p.rowplane_bytes, 128u) >> 32);
             const uint32_t a_lo_lbo = ((a_lbo >> 4) & 0x3FFF) << 16, b_lo_lbo = ((p.rowplane_bytes >> 4) & 0x3FFF) << 16;
@@ -322,7 +330,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                     const bool f8 = (p.kpass == 2) && (c & 1);    // correction pass: e4m3 operands, K = 32
                     // the chunk's rows sit in two groups of GR slots: [slot0, +GR) and the next group (which may wrap to 0)
                     const uint32_t slotA = slot0, phA = slot0_ph;
-                    uint32_t slotB = slot0 + GR, phB = slot0_ph;
+                    uint32_t slotB = slot0 + GR0, phB = slot0_ph;
                     if (slotB == nslots) { slotB = 0; phB ^= 1; }
                     for (int dx = 0; dx < p.kw; ++dx) {
                         mbar_wait(w_full + wst, p.w_resident ? 0u : wph);   // resident stages complete once and stay
@@ -332,6 +340,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
 #pragma unroll 1
                         for (int grp = 0; grp < 2; ++grp) {
                             const uint32_t slot = grp ? slotB : slotA;
+                            const int GR = grp ? GR1 : GR0;
                             if (first_dx) { mbar_wait(row_full + slot, grp ? phB : phA); tc_fence_after(); }
                             if (leader) {
                                 uint32_t b_lo = ((rows_base16 + slot * slot16 + dx) & 0x3FFF) | b_lo_lbo;
@@ -379,9 +388,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
         const int q = warp & 3;                     // TMEM lane quarter this warp may access
         const int part = ew >> 2, nparts = p.n_epi >> 2;
         const int m = 32 * q + lane;
-        const int co = m & (CP - 1);
+        const int co = m % CP;                      // CP = 24: rows 120..127 are never stored
         uint32_t* stage = reinterpret_cast<uint32_t*>(s_stage + ew * STAGE_WARP);
-        const bool live = co < p.cout;
+        const bool live = co < p.cout && m < RT * CP;
         const float bias = (p.bias && live) ? p.bias[co] : 0.f;
         const float bns = (p.bn_scale && live) ? p.bn_scale[co] : 1.f;
         const float bnt = (p.bn_shift && live) ? p.bn_shift[co] : 0.f;
@@ -401,7 +410,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
         for (int e = 0; e < 2; ++e) {
             const int m0 = 8 * (4 * q + 2 * oc + e);
             o_r[e] = (RT - 1) - m0 / CP;
-            o_pl[e] = (m0 & (CP - 1)) >> 3;
+            o_pl[e] = (m0 % CP) >> 3;
+            if (m0 >= RT * CP) o_pl[e] = 1 << 20;    // CP = 24: the last octet (rows 120..127) belongs to no output row
         }
         // swizzled word offsets: word (pixel j, M row lane) and the pixel side's four 16-byte chunks
         const uint32_t lane_word = (uint32_t)(lane & 3);
@@ -587,7 +597,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                         }
                         if (mode == 3) {
                             uint8_t* dq = reinterpret_cast<uint8_t*>(p.out_lo);
-                            if (CP >= 16) {
+                            if (CP == 32 || CP == 16) {
                                 // both octets belong to one row and one 16-channel group: planes (2g, 2g+1) -> 16-byte stores
                                 if (ok0) {
                                     const size_t base = (size_t)((long long)o_off[0] + ((long long)xo + d0) * 16);
@@ -595,13 +605,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                                     *reinterpret_cast<uint4*>(dq + base + plane_px * 16) = make_uint4(l8[0].x, l8[0].y, l8[1].x, l8[1].y);
                                 }
                             } else {
-                                // CP = 8: an octet is a whole row of 8 channels; bytes 8..15 of its pixel are channel padding
+                                // CP = 8 / 24: an octet's neighbour in its 16-channel group is channel padding (CP = 8, and plane 2
+                                // of CP = 24: written as zeros) or lives in another thread (planes 0 / 1 of CP = 24: 8-byte stores)
 #pragma unroll
                                 for (int e = 0; e < 2; ++e) {
                                     if (oks[e]) {
-                                        const size_t base = (size_t)((long long)o_off[e] + ((long long)xo + ds[e]) * 16);   // plane 0 (CP = 8)
-                                        *reinterpret_cast<uint4*>(dq + base) = make_uint4(q8[e].x, q8[e].y, 0u, 0u);
-                                        *reinterpret_cast<uint4*>(dq + base + plane_px * 16) = make_uint4(l8[e].x, l8[e].y, 0u, 0u);
+                                        const size_t base = (size_t)((long long)o_off[e] + ((long long)xo + ds[e]) * 16);   // hi plane o_pl
+                                        if (CP == 8 || o_pl[e] == 2) {       // even plane, alone in its group: q plane = o_pl, remainder plane = o_pl + 1
+                                            *reinterpret_cast<uint4*>(dq + base) = make_uint4(q8[e].x, q8[e].y, 0u, 0u);
+                                            *reinterpret_cast<uint4*>(dq + base + plane_px * 16) = make_uint4(l8[e].x, l8[e].y, 0u, 0u);
+                                        } else if (o_pl[e] == 0) {           // group 0, bytes 0..7
+                                            *reinterpret_cast<uint2*>(dq + base) = q8[e];
+                                            *reinterpret_cast<uint2*>(dq + base + plane_px * 16) = l8[e];
+                                        } else {                             // plane 1: group 0, bytes 8..15 of planes 0 (x) and 1 (remainder)
+                                            *reinterpret_cast<uint2*>(dq + base - plane_px * 16 + 8) = q8[e];
+                                            *reinterpret_cast<uint2*>(dq + base + 8) = l8[e];
+                                        }
                                     }
                                 }
                             }
@@ -644,8 +663,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
 // Keras kernel [kh][kw][Cin][Cout] fp32 -> packed fp16 [C16][kw][2][(kh+2(RT-1))*CP][8], RT = 128/CP
 __global__ void pack_weights_kernel(const float* __restrict__ k, __half* __restrict__ out, int kh, int kw,
                                     int Cin, int Cout, int c16, long long total, int nsplit, float scale, int cp) {
-    const int zpad = M_TILE / cp - 1;
-    const int Z = kh + 2 * zpad;
+    const int zpad = rows_per_tile(cp) - 1;
+    const int Z = packed_zrows(kh, cp);
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int e = idx & 7;
@@ -886,11 +905,12 @@ static inline size_t smem_fixed_for(int k) { return (size_t)epi_warps_for(k) * S
 static int choose_cp(int cout, int k) {
     static const int forced = getenv("PCNN_TC_CP") ? atoi(getenv("PCNN_TC_CP")) : 0;
     if (forced == 32) return 32;
-    for (int cp = 8; cp < 32; cp *= 2) {
-        if (cp < cout) continue;
-        const int zpad = M_TILE / cp - 1, R = k + zpad;
+    static const int no24 = getenv("PCNN_TC_NO_CP24") ? atoi(getenv("PCNN_TC_NO_CP24")) : 0;
+    for (int cp = 8; cp < 32; cp += 8) {
+        if (cp < cout || (cp == 24 && no24)) continue;
+        const int zpad = rows_per_tile(cp) - 1, R = k + zpad;
         const size_t rowslot = 2 * (((size_t)(256 + k - 1) * 16 + 127) & ~(size_t)127);
-        const size_t wst = 2 * (size_t)(k + 2 * zpad) * cp * 16;
+        const size_t wst = 2 * (size_t)packed_zrows(k, cp) * cp * 16;
         if ((size_t)R * rowslot + 3 * wst + smem_fixed_for(k) <= SMEM_MAX) return cp;
     }
     return 32;
@@ -901,7 +921,7 @@ extern "C" int pcnn_conv_tc_channel_slots(int Cout, int k) { return (Cout >= 1 &
 extern "C" size_t pcnn_conv_tc_packed_weight_bytes(int kh, int kw, int Cin, int Cout, int nsplit) {
     if (Cout < 1 || Cout > 32) return 0;
     const int cp = choose_cp(Cout, kh);
-    return (size_t)(nsplit >= 2 ? 2 : 1) * ((Cin + 15) / 16) * kw * 2 * (kh + 2 * (M_TILE / cp - 1)) * cp * 8 * sizeof(__half);
+    return (size_t)(nsplit >= 2 ? 2 : 1) * ((Cin + 15) / 16) * kw * 2 * packed_zrows(kh, cp) * cp * 8 * sizeof(__half);
 }
 
 extern "C" int pcnn_conv_tc_pack_weights(const float* kernel, void* packed, int kh, int kw, int Cin, int Cout, int nsplit,
@@ -912,7 +932,7 @@ extern "C" int pcnn_conv_tc_pack_weights(const float* kernel, void* packed, int 
     PCNN_CHECK_ARG(kh == kw && (kh & 1) && kh >= 1 && kh <= 2 * HALO + 1, "conv_tc: kernel %dx%d not supported (odd, square, <= 15)", kh, kw);
     PCNN_CHECK_ARG(Cout >= 1 && Cout <= 32 && Cin >= 1, "conv_tc: Cout %d not in [1,32]", Cout);
     const int c16 = (Cin + 15) / 16, cp = choose_cp(Cout, kh);
-    const long long total = (long long)c16 * kw * 2 * (kh + 2 * (M_TILE / cp - 1)) * cp * 8;
+    const long long total = (long long)c16 * kw * 2 * packed_zrows(kh, cp) * cp * 8;
     pack_weights_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(kernel, (__half*)packed, kh, kw, Cin, Cout, c16, total, nsplit, scale, cp);
     PCNN_CHECK_LAUNCH();
     return PCNN_OK;
@@ -1001,13 +1021,13 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
     p.nv = p.c16 * p.kpass;
     p.c8_in = p.c16 * 2; p.c8_out = ((Cout_total + 15) / 16) * 2; p.c8_res = ((Cres_total + 15) / 16) * 2;
     p.cout = Cout; p.kh = k; p.kw = k; p.pad = k / 2; p.act = act; p.halo_sym = (out_halo_mode == PCNN_PAD_SYMMETRIC);
-    const int cp = choose_cp(Cout, k), rt = M_TILE / cp, zpad = rt - 1;
+    const int cp = choose_cp(Cout, k), rt = rows_per_tile(cp), zpad = rt - 1;
     p.n_tile = W >= 256 ? 256 : ((W + 15) / 16) * 16;
     p.tiles_x = ceil_div(W, p.n_tile); p.tiles_y = ceil_div(H, rt);
     p.num_tiles = B * p.tiles_x * p.tiles_y;
     p.row_copy_bytes = (uint32_t)(p.n_tile + k - 1) * 16u;
     p.rowplane_bytes = (p.row_copy_bytes + 127u) & ~127u;
-    p.wstage_bytes = 2u * (uint32_t)(k + 2 * zpad) * (uint32_t)cp * 16u;
+    p.wstage_bytes = 2u * (uint32_t)packed_zrows(k, cp) * (uint32_t)cp * 16u;
     // instruction descriptor: D=F32, A=B=F16, both K-major, N = n_tile, M = 128
     p.idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     // shared-memory plan.  Rows need >= R slots (ideally 2R: full double buffering across chunk switches).  Weights:
@@ -1034,7 +1054,8 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
         }
         PCNN_CHECK_ARG(slots >= R && w_stages >= 2, "conv2d_tc: shared-memory plan failed (k=%d, n_tile=%d)", k, p.n_tile);
     }
-    slots = (slots / (R / 2)) * (R / 2);          // barrier groups of R/2 rows must not straddle the ring wrap
+    if (R & 1) slots = (slots / R) * R;           // odd R: groups of (R+1)/2 and R/2 rows, the ring wraps between chunks only
+    else slots = (slots / (R / 2)) * (R / 2);     // barrier groups of R/2 rows must not straddle the ring wrap
     PCNN_CHECK_ARG(2 * (slots + w_stages) + 5 <= 250, "conv2d_tc: too many pipeline stages for the mbarrier area");
     p.row_slots = slots; p.w_stages = w_stages; p.w_resident = resident;
     { static const int dbg = getenv("PCNN_TC_DEBUG") ? atoi(getenv("PCNN_TC_DEBUG")) : 0; p.debug = dbg; }
@@ -1054,6 +1075,7 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
         return launch(conv_tc_kernel<CPV, 3>);                        \
     }
     PCNN_TC_DISPATCH(32)
+    PCNN_TC_DISPATCH(24)
     PCNN_TC_DISPATCH(16)
     PCNN_TC_DISPATCH(8)
 #undef PCNN_TC_DISPATCH

@@ -55,6 +55,9 @@ def test_blk8_roundtrip_and_halo(ops):
     (1, 16, 16, 16, 40, 5, 0),
     (3, 12, 8, 5, 33, 3, 1),
     (1, 32, 32, 4, 16, 1, 0),         # 1x1
+    (2, 29, 23, 33, 300, 7, 1),       # 17 <= Cout <= 24: 5 output rows x 24 channel slots (120 of 128 accumulator rows), odd row count
+    (1, 24, 24, 12, 256, 9, 1),
+    (2, 23, 19, 9, 40, 7, 2),
     (2, 15, 15, 37, 300, 5, 1),       # Cout <= 16: 8 output rows x 16 channel slots per tile, ragged both ways
     (2, 19, 15, 8, 256, 5, 2),
     (2, 7, 5, 37, 70, 3, 2),          # Cout <= 8: 16 output rows x 8 channel slots
@@ -104,7 +107,7 @@ def test_conv2d_tc_symmetric_bn_residual_scale_concat(ops):
 
 
 @pytest.mark.parametrize("mode", [1, 2, 3])
-@pytest.mark.parametrize("B,Cin,Cout,H,W,k", [(2, 32, 32, 18, 50, 11), (1, 16, 12, 40, 270, 5), (2, 8, 5, 33, 9, 3)])
+@pytest.mark.parametrize("B,Cin,Cout,H,W,k", [(2, 32, 32, 18, 50, 11), (1, 16, 12, 40, 270, 5), (2, 8, 5, 33, 9, 3), (1, 24, 20, 23, 60, 7)])
 def test_fused_symmetric_halo_equals_halo_fill(ops, mode, B, Cin, Cout, H, W, k):
     """A producer asked for out_halo=SYMMETRIC leaves exactly the buffer that pcnn_blk8_halo_fill would make."""
     g = torch.Generator().manual_seed(H * W + mode)
@@ -214,6 +217,8 @@ def test_models_tc_mode_vs_oracle():
     (2, 15, 15, 37, 300, 5, 1),
     (2, 7, 5, 37, 70, 3, 2),
     (1, 11, 7, 16, 31, 5, 1),
+    (2, 28, 24, 33, 300, 9, 1),
+    (2, 24, 20, 9, 40, 7, 2),
 ])
 def test_conv2d_tc3_parity(ops, B, Cin, Cout, H, W, k, act):
     """hi/lo split operands, three MMAs: ~22 operand bits.  Measured floor ~8e-6 on the K=7200 layer with or
@@ -257,6 +262,8 @@ def test_models_tc3_mode_vs_oracle():
     (2, 15, 15, 37, 300, 5, 1),
     (2, 7, 5, 37, 70, 3, 2),
     (1, 11, 7, 16, 31, 5, 1),
+    (2, 28, 24, 33, 300, 9, 1),
+    (2, 24, 20, 9, 40, 7, 2),
 ])
 def test_conv2d_tc2_parity(ops, B, Cin, Cout, H, W, k, act):
     """fp16 main MMA + one e4m3 K=32 MMA carrying both correction terms: ~10x tighter than a single fp16 pass."""
