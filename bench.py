@@ -240,9 +240,12 @@ def run_ours(args):
         kk = args.roofline_kernel[2]
         hp_mode = {"mixed": "tc2"}.get(args.precision, args.precision)      # precision mode of the HPNN, which owns the timed kernel
         issue_factor = {"tc": 1.0, "tc3": 3.0, "tc2": 2.0}.get(hp_mode, 0.0) * (kk + 3.0) / kk   # MMAs issued per algorithmic MAC
-        # DRAM bytes per launch of this kernel from the ncu --set full captures (profiles/r01_conv_tc_k15_*_b32_full_raw.csv:
-        # dram__bytes_read.sum + dram__bytes_write.sum at 32 samples per launch), scaled to the samples per launch here
-        per_sample = {"tc": (151.436032e6 + 94.614272e6) / 32, "tc2": (303.551488e6 + 228.785920e6) / 32}.get(hp_mode)
+        # DRAM bytes per launch of this kernel from the ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum
+        # at 32 samples per launch), scaled to the samples per launch here.  tc2: three of the four 32->32 k15 launches of a
+        # forward have no residual input (profiles/r01_conv_tc_k15_tc2_b32_full_raw.csv: 303.6 + 228.8 MB), one has
+        # (profiles/r01b_conv_tc_k15_tc2_res_b32_full_raw.csv: 512.1 + 237.5 MB)
+        per_sample = {"tc": (151.436032e6 + 94.614272e6) / 32,
+                      "tc2": (3 * (303.551488e6 + 228.785920e6) + (512.086272e6 + 237.487872e6)) / 4 / 32}.get(hp_mode)
         samples_per_launch = min(B, max(1, int((getattr(model, "max_microbatch", B) or B) * 65536 // (nx * ny))))
         traffic = per_sample * samples_per_launch if (per_sample and args.roofline_kernel == (32, 32, 15) and (nx, ny) == (256, 256)) else None
         roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
