@@ -32,8 +32,10 @@ constexpr int HALO = 7;
 constexpr int MAXB = 8;          // branches of each kind
 constexpr int MAXS = 40;         // stages: (deconv branch, group of <= TXG column phases) or resize branch
 constexpr int TXG = 8;           // column phases per stage: bounds the staged phase matrices to 8 x C x C floats
-constexpr int SEG_W = 128;       // output pixels per row segment
-constexpr int NTHR = 160;        // threads per CTA: 128 pixel owners + one warp (s = 3, 4, 8 have up to 160 work items)
+constexpr int SEG_W = 256;       // output pixels per row segment
+constexpr int NTHR = 288;        // threads per CTA: 256 pixel owners + one warp (s = 3 has 264 work items).  Measured: 256-pixel
+                                 // segments with one CTA per SM (4.05 ms per 64 samples) beat 128-pixel segments with two (4.4 ms):
+                                 // the per-stage fixed cost is paid half as often
 constexpr float LO_SCALE = 2048.f;
 
 struct Params {
@@ -130,10 +132,10 @@ __device__ __forceinline__ DcGeom dc_geom(const Params& p, int d, int X0, int Y)
     return g;
 }
 
-// Persistent CTAs (one per SM) walk (row segment, stage) pairs; stage = one branch.  The operands of the NEXT stage
+// Persistent CTAs walk (row segment, stage) pairs; stage = one branch.  The operands of the NEXT stage
 // (low-res row tile + the s phase matrices W[ty][0..s), or the tiny resize source) stream into the other
 // shared-memory buffer with cp.async while the current stage computes, also across row boundaries.
-__global__ void __launch_bounds__(NTHR, 2) upsample_merge_kernel(const Params p) {
+__global__ void __launch_bounds__(NTHR, 1) upsample_merge_kernel(const Params p) {
     extern __shared__ __align__(16) float sm[];
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(sm);      // two mbarriers: bulk-copied phase matrices of each operand buffer
     float* s_st = sm + 4;                  // [s column phases][phase stride] staged deconv results / resize row
