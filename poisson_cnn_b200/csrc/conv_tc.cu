@@ -242,6 +242,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
+    // the weight stages start as zeros: the producer only ever copies the live z-rows into them
+    for (uint32_t i = threadIdx.x; i < (uint32_t)p.w_stages * (p.wstage_bytes >> 4); i += NUM_THREADS)
+        reinterpret_cast<uint4*>(s_w)[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core's reads
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -287,6 +291,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
     } else if (warp == 1) {
         // ================= weight producer =================
         const bool leader = elect_one();
+        const uint32_t w_plane = p.wstage_bytes >> 1, w_zoff = (uint32_t)ZPAD * CP * 16u, w_live = (uint32_t)p.kh * CP * 16u;
         uint32_t st = 0, ph = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
             if (p.w_resident && t != (int)blockIdx.x) break;    // resident weights: one pass fills every stage
@@ -297,8 +302,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                 for (int dx = 0; dx < p.kw; ++dx, src += p.wstage_bytes) {
                     mbar_wait(w_empty + st, ph ^ 1);
                     if (leader) {
-                        mbar_expect_tx(w_full + st, p.wstage_bytes);
-                        bulk_copy_g2s(smem_u32(s_w) + st * p.wstage_bytes, src, p.wstage_bytes, w_full + st);
+                        // only the kh live z-rows of each K-half travel: the zero rows around them were written once at
+                        // kernel start and no copy ever touches them (44..71 % of a stage's bytes)
+                        mbar_expect_tx(w_full + st, 2u * w_live);
+                        const uint32_t dst = smem_u32(s_w) + st * p.wstage_bytes + w_zoff;
+                        bulk_copy_g2s(dst, src + w_zoff, w_live, w_full + st);
+                        bulk_copy_g2s(dst + w_plane, src + w_plane + w_zoff, w_live, w_full + st);
                     }
                     if (++st == (uint32_t)p.w_stages) { st = 0; ph ^= 1; }
                 }
