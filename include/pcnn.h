@@ -217,6 +217,8 @@ int pcnn_dbcnn_expand_blk8(const float* h, const float* sinh_basis, const float*
 /* Keras kernel [k,k,Cin,Cout] fp32 -> fp16 operand image of the row-group GEMM:
  * [ceil(Cin/16)][k][2][(k+2(RT-1))*CP][8] with CP = pcnn_conv_tc_channel_slots(Cout, k) channel slots per
  * output row (8, 16, 24 or 32) and RT = 128/CP (5 for CP = 24) output rows per tile (see conv_tc.cu).
+ * When ceil(Cin/8) is odd (and k >= 3) the last chunk holds one live 8-channel plane and its stages pair two
+ * column taps in the two K halves instead ((k+1)/2 stages used): 21 % fewer MMAs on 17..24-channel layers.
  * Done once per layer at load time. */
 int pcnn_conv_tc_channel_slots(int Cout, int k);
 size_t pcnn_conv_tc_packed_weight_bytes(int kh, int kw, int Cin, int Cout, int nsplit);
@@ -245,7 +247,8 @@ int pcnn_upsample_merge_blk8(int n_deconv, const float* const* dc_in, const floa
                              int mode, int B, int C, int H, int W, int c_total, int c_offset, void* stream);
 /* Same operator as pcnn_conv2d_f32 (pad + VALID conv + bias + act [+BN] [+residual] [*out_scale]) on
  * tcgen05 tensor cores: FP16 operands, FP32 accumulation in TMEM.  in/out/residual are BLK8 buffers
- * with Cin_total / Cout_total / Cres_total channels; the padding mode is whatever the halo of `in`
+ * with Cin_total / Cout_total / Cres_total channels (Cin_total = the Cin the weights were packed with: the
+ * tensor holds round_up(Cin,16) channel slots); the padding mode is whatever the halo of `in`
  * holds.  Odd k <= 15, Cout <= 32.  num_sms: CTAs of the persistent grid (<= 0: 148).
  *
  * Split precision (nsplit = 2): every BLK8 tensor is a pair of buffers x = hi + lo (lo = the fp16

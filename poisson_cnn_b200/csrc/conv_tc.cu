@@ -89,7 +89,10 @@ struct Params {
     int halo_sym;            // 1: the epilogue also writes the SYMMETRIC (edge-repeating mirror) halo ring of width 7 of `out`
     int n_epi;               // active epilogue warps: 8, or 4 when shared memory is needed for operands (large k)
     int debug;               // PCNN_TC_DEBUG bit 0: epilogue skips math and stores (timing experiments only)
-    int w_resident;          // 1: all nv*kw weight stages fit in shared memory -> loaded once per CTA, reused by every tile
+    int w_resident;          // 1: all weight stages of a tile fit in shared memory -> loaded once per CTA, reused by every tile
+    int pair_tail;           // 1: the last 16-channel chunk holds ONE live 8-channel plane (ceil(Cin/8) odd): its fp16 passes put two
+                             // adjacent column taps into the two K halves (B: K-half stride = one pixel) -> (kw+1)/2 MMAs per row, not kw
+    int npairs;              // (kw+1)/2 weight stages of a paired chunk
     uint32_t rowplane_bytes; // bytes of one plane of one row window in smem (multiple of 128)
     uint32_t row_copy_bytes; // (n_tile + kw - 1) * 16
     uint32_t wstage_bytes;   // 2 * (kh+2(RT-1)) * CP * 16
@@ -268,17 +271,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                 const int c = (p.kpass == 3) ? v / 3 : (p.kpass == 2 ? v >> 1 : v);
                 const __half* inp = ((p.kpass == 3 && (v % 3) == 2) || (p.kpass == 2 && (v & 1))) ? p.in_lo : p.in;
                 const __half* base = inp + ((size_t)b * p.c8_in + 2 * c) * plane_elems + (size_t)col0 * 8;
+                const bool paired = p.pair_tail && c == p.c16 - 1 && !(p.kpass == 2 && (v & 1));   // only plane 2c travels
                 // rows travel in two groups per chunk (R is even); one mbarrier pair per group, at the group's first slot
                 for (int grp = 0, rho = 0; grp < 2; ++grp) {
                     const int GR = grp ? GR1 : GR0;
                     mbar_wait(row_empty + slot, ph ^ 1);
                     if (leader) {
-                        mbar_expect_tx(row_full + slot, (uint32_t)GR * 2u * p.row_copy_bytes);
+                        mbar_expect_tx(row_full + slot, (uint32_t)GR * (paired ? 1u : 2u) * p.row_copy_bytes);
                         for (int i = 0; i < GR; ++i, ++rho) {
                             const __half* src = base + (size_t)min(prow0 + rho, p.Hp - 1) * p.P * 8;
                             const uint32_t dst = smem_u32(s_rows) + (slot + i) * row_slot_bytes;
                             bulk_copy_g2s(dst, src, p.row_copy_bytes, row_full + slot);
-                            bulk_copy_g2s(dst + p.rowplane_bytes, src + plane_elems, p.row_copy_bytes, row_full + slot);
+                            if (!paired) bulk_copy_g2s(dst + p.rowplane_bytes, src + plane_elems, p.row_copy_bytes, row_full + slot);
                         }
                     } else {
                         rho += GR;
@@ -299,7 +303,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                 const int c = (p.kpass == 3) ? v / 3 : (p.kpass == 2 ? v >> 1 : v);
                 const int wsel = ((p.kpass == 3 && (v % 3) == 1) || (p.kpass == 2 && (v & 1))) ? 1 : 0;   // second weight image
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) + ((size_t)wsel * p.c16 + c) * p.kw * p.wstage_bytes;
-                for (int dx = 0; dx < p.kw; ++dx, src += p.wstage_bytes) {
+                // a paired chunk has (kw+1)/2 stages: K-half 0 / 1 = column taps (2s, 2s+1)
+                const int nst = (p.pair_tail && c == p.c16 - 1 && !(p.kpass == 2 && (v & 1))) ? p.npairs : p.kw;
+                for (int dx = 0; dx < nst; ++dx, src += p.wstage_bytes) {
                     mbar_wait(w_empty + st, ph ^ 1);
                     if (leader) {
                         // only the kh live z-rows of each K-half travel: the zero rows around them were written once at
@@ -337,26 +343,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                 uint32_t accum = 0;
                 for (int c = 0; c < p.nv; ++c) {
                     const bool f8 = (p.kpass == 2) && (c & 1);    // correction pass: e4m3 operands, K = 32
+                    // paired chunk (one live 8-channel plane): the K halves are column taps (dx, dx+1) of that plane, i.e. the
+                    // B descriptor's K-half stride is one pixel (16 B); the last stage is taps (kw-2, kw-1) with a zero first half
+                    const bool paired = p.pair_tail && !f8 && ((p.kpass == 3) ? c / 3 : (p.kpass == 2 ? c >> 1 : c)) == p.c16 - 1;
+                    const int nst = paired ? p.npairs : p.kw;
+                    const uint32_t b_lbo = paired ? (1u << 16) : b_lo_lbo;
                     // the chunk's rows sit in two groups of GR slots: [slot0, +GR) and the next group (which may wrap to 0)
                     const uint32_t slotA = slot0, phA = slot0_ph;
                     uint32_t slotB = slot0 + GR0, phB = slot0_ph;
                     if (slotB == nslots) { slotB = 0; phB ^= 1; }
-                    for (int dx = 0; dx < p.kw; ++dx) {
+                    for (int st = 0; st < nst; ++st) {
+                        const int dx = paired ? min(2 * st, p.kw - 2) : st;   // first column tap of the stage
                         mbar_wait(w_full + wst, p.w_resident ? 0u : wph);   // resident stages complete once and stay
                         tc_fence_after();
                         uint32_t a_lo = ((w_base16 + wst * wstage16) & 0x3FFF) | a_lo_lbo;
-                        const bool first_dx = (dx == 0), last_dx = (dx == p.kw - 1);
+                        const bool first_dx = (st == 0), last_dx = (st == nst - 1);
 #pragma unroll 1
                         for (int grp = 0; grp < 2; ++grp) {
                             const uint32_t slot = grp ? slotB : slotA;
                             const int GR = grp ? GR1 : GR0;
                             if (first_dx) { mbar_wait(row_full + slot, grp ? phB : phA); tc_fence_after(); }
                             if (leader) {
-                                uint32_t b_lo = ((rows_base16 + slot * slot16 + dx) & 0x3FFF) | b_lo_lbo;
+                                uint32_t b_lo = ((rows_base16 + slot * slot16 + dx) & 0x3FFF) | b_lbo;
                                 if (!f8) {
 #pragma unroll 3
                                     for (int i = 0; i < GR; ++i) {
-                                        tc_mma_f16(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, accum | (uint32_t)(i | grp | dx));
+                                        tc_mma_f16(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, p.idesc, accum | (uint32_t)(i | grp | st));
                                         a_lo += CP; b_lo += slot16;
                                     }
                                 } else {
@@ -669,11 +681,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
 }
 
 // ---------------------------------------------------------------- layout / packing kernels
-// Keras kernel [kh][kw][Cin][Cout] fp32 -> packed fp16 [C16][kw][2][(kh+2(RT-1))*CP][8], RT = 128/CP
+// One 8-channel plane in the last 16-channel chunk (ceil(Cin/8) odd) and k >= 3: that chunk's fp16 passes pair column
+// taps in the K dimension.  Packing and launching must agree, so both ask this function.  (PCNN_TC_NO_PAIR=1: A/B only.)
+static inline bool pair_tail_for(int Cin, int k) {
+    static const int off = getenv("PCNN_TC_NO_PAIR") ? atoi(getenv("PCNN_TC_NO_PAIR")) : 0;
+    return !off && k >= 3 && (((Cin + 7) / 8) & 1);
+}
+
+// Keras kernel [kh][kw][Cin][Cout] fp32 -> packed fp16 [C16][kw][2][(kh+2(RT-1))*CP][8], RT = 128/CP.
+// pair_tail: in the last chunk, stage s < (kw+1)/2 holds channels [16c, 16c+8) of column taps (2s, 2s+1) in its two K
+// halves (last stage: a zero half and tap kw-1, read at column offset kw-2); the remaining stages of that chunk are unused.
 __global__ void pack_weights_kernel(const float* __restrict__ k, __half* __restrict__ out, int kh, int kw,
-                                    int Cin, int Cout, int c16, long long total, int nsplit, float scale, int cp) {
+                                    int Cin, int Cout, int c16, long long total, int nsplit, float scale, int cp, int pair_tail) {
     const int zpad = rows_per_tile(cp) - 1;
     const int Z = packed_zrows(kh, cp);
+    const int npairs = (kw + 1) / 2;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int e = idx & 7;
@@ -683,20 +705,30 @@ __global__ void pack_weights_kernel(const float* __restrict__ k, __half* __restr
         const int pl = t & 1; t >>= 1;
         const int dx = t % kw;
         const int c = t / kw;
-        const int ci = c * 16 + pl * 8 + e, dy = z - zpad;
-        float v = 0.f;
-        if (dy >= 0 && dy < kh && ci < Cin && co < Cout) v = scale * k[(((long long)dy * kw + dx) * Cin + ci) * Cout + co];
-        const __half h = __float2half_rn(v);
+        const int dy = z - zpad;
+        const bool rowok = dy >= 0 && dy < kh && co < Cout;
+        auto w_at = [&](int tap, int ci) -> float {
+            return (rowok && tap >= 0 && tap < kw && ci < Cin) ? scale * k[(((long long)dy * kw + tap) * Cin + ci) * Cout + co] : 0.f;
+        };
+        const float v = w_at(dx, c * 16 + pl * 8 + e);        // unpaired image: K half = channel half
+        float vh = v;                                         // what the fp16 image holds
+        if (pair_tail && c == c16 - 1) {
+            int tap = -1;
+            if (dx < npairs - 1) tap = 2 * dx + pl;
+            else if (dx == npairs - 1 && pl == 1) tap = kw - 1;
+            vh = w_at(tap, c * 16 + e);
+        }
+        const __half h = __float2half_rn(vh);
         out[idx] = h;
-        if (nsplit == 2) out[total + idx] = __float2half_rn(v - __half2float(h));
+        if (nsplit == 2) out[total + idx] = __float2half_rn(vh - __half2float(h));
         if (nsplit == 3) {
             // fp8 image [c][dx][plane][z][co][16]: plane 0 = e4m3(W_lo) pairs with e4m3(x),
-            // plane 1 = e4m3(W * 2^-11) pairs with e4m3(x_lo * 2^11); ci16 = pl*8+e of the fp16 image
+            // plane 1 = e4m3(W * 2^-11) pairs with e4m3(x_lo * 2^11); ci16 = pl*8+e of the (unpaired) fp16 image
             uint8_t* q = reinterpret_cast<uint8_t*>(out + total);
             const long long stage_elems = 2LL * Z * cp * 8;                    // fp16 elements per (c,dx) stage == bytes / 2
             const long long base = ((long long)c * kw + dx) * stage_elems * 2; // byte offset of the (c,dx) stage
             const int ci16 = pl * 8 + e;
-            q[base + (((long long)0 * Z + z) * cp + co) * 16 + ci16] = to_e4m3(v - __half2float(h));
+            q[base + (((long long)0 * Z + z) * cp + co) * 16 + ci16] = to_e4m3(v - __half2float(__float2half_rn(v)));
             q[base + (((long long)1 * Z + z) * cp + co) * 16 + ci16] = to_e4m3(v * (1.0f / LO_SCALE));
         }
     }
@@ -942,7 +974,8 @@ extern "C" int pcnn_conv_tc_pack_weights(const float* kernel, void* packed, int 
     PCNN_CHECK_ARG(Cout >= 1 && Cout <= 32 && Cin >= 1, "conv_tc: Cout %d not in [1,32]", Cout);
     const int c16 = (Cin + 15) / 16, cp = choose_cp(Cout, kh);
     const long long total = (long long)c16 * kw * 2 * packed_zrows(kh, cp) * cp * 8;
-    pack_weights_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(kernel, (__half*)packed, kh, kw, Cin, Cout, c16, total, nsplit, scale, cp);
+    pack_weights_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(kernel, (__half*)packed, kh, kw, Cin, Cout, c16, total, nsplit, scale, cp,
+                                                                           pair_tail_for(Cin, kh) ? 1 : 0);
     PCNN_CHECK_LAUNCH();
     return PCNN_OK;
 }
@@ -1028,6 +1061,8 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
     p.c16 = (Cin_total + 15) / 16;
     p.kpass = skip_corr ? 1 : (nsplit == 2 ? 3 : (nsplit == 3 ? 2 : 1));
     p.nv = p.c16 * p.kpass;
+    p.pair_tail = pair_tail_for(Cin_total, k) ? 1 : 0;
+    p.npairs = (k + 1) / 2;
     p.c8_in = p.c16 * 2; p.c8_out = ((Cout_total + 15) / 16) * 2; p.c8_res = ((Cres_total + 15) / 16) * 2;
     p.cout = Cout; p.kh = k; p.kw = k; p.pad = k / 2; p.act = act; p.halo_sym = (out_halo_mode == PCNN_PAD_SYMMETRIC);
     const int cp = choose_cp(Cout, k), rt = rows_per_tile(cp), zpad = rt - 1;
@@ -1048,7 +1083,8 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
     const int R = k + zpad;
     const size_t avail = kMax - fixed, rowslot = 2 * (size_t)p.rowplane_bytes, wst = p.wstage_bytes;
     PCNN_CHECK_ARG((size_t)R * rowslot + 2 * wst <= avail, "conv2d_tc: tile does not fit in shared memory (k=%d, n_tile=%d)", k, p.n_tile);
-    const int total_stages = p.nv * k;
+    // weight stages per tile: kw per pass, (kw+1)/2 for the fp16 passes of a paired last chunk
+    const int total_stages = p.nv * k - (p.pair_tail ? (p.kpass == 2 ? 1 : p.kpass) * (k - p.npairs) : 0);
     int slots, w_stages, resident = 0;
     if ((size_t)R * rowslot + (size_t)total_stages * wst <= avail && total_stages <= 48) {
         resident = 1; w_stages = total_stages;

@@ -687,7 +687,7 @@ def conv2d_tc(x, wp, bias=None, act=ACT_LINEAR, pad_mode=PAD_CONSTANT, bn=None, 
                              None if residual is None else _p(residual.buf),
                              None if (residual is None or not split) else _p(residual.lo), _p(out_scale),
                              out.plane_ptr(out_c_offset), out.plane_ptr_lo(out_c_offset) if split else None,
-                             x.B, x.C, cout, out.C, 0 if residual is None else residual.C, x.H, x.W, k, int(act),
+                             x.B, wp["cin"], cout, out.C, 0 if residual is None else residual.C, x.H, x.W, k, int(act),
                              nsplit | (0x10 if (nsplit == 3 and not correction) else 0), wp["acc_scale"],
                              PAD_SYMMETRIC if fused_halo else PAD_CONSTANT,
                              _num_sms(x.device), _stream()), "conv2d_tc")
