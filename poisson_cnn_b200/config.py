@@ -14,6 +14,7 @@ import os
 ACT_LINEAR, ACT_LEAKY_RELU, ACT_TANH = 0, 1, 2
 PAD_CONSTANT, PAD_SYMMETRIC, PAD_REFLECT = 0, 1, 2
 RESIZE_NEAREST, RESIZE_BILINEAR, RESIZE_BICUBIC = 0, 1, 2
+RESIZE_BICUBIC_LEGACY_AC = 3   # tf.compat.v1 resize_images(BICUBIC, align_corners=True): the dataset generators' resize
 
 _ACTS = {
     "tf.nn.leaky_relu": ACT_LEAKY_RELU, "leaky_relu": ACT_LEAKY_RELU,

@@ -93,6 +93,7 @@ struct Params {
     int pair_tail;           // 1: the last 16-channel chunk holds ONE live 8-channel plane (ceil(Cin/8) odd): its fp16 passes put two
                              // adjacent column taps into the two K halves (B: K-half stride = one pixel) -> (kw+1)/2 MMAs per row, not kw
     int npairs;              // (kw+1)/2 weight stages of a paired chunk
+    int res_tail_pl;         // mode 3: plane of the residual tensor holding a lone live octet (ceil(Cres/8) odd), else -1
     uint32_t rowplane_bytes; // bytes of one plane of one row window in smem (multiple of 128)
     uint32_t row_copy_bytes; // (n_tile + kw - 1) * 16
     uint32_t wstage_bytes;   // 2 * (kh+2(RT-1)) * CP * 16
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                 const int c = (p.kpass == 3) ? v / 3 : (p.kpass == 2 ? v >> 1 : v);
                 const __half* inp = ((p.kpass == 3 && (v % 3) == 2) || (p.kpass == 2 && (v & 1))) ? p.in_lo : p.in;
                 const __half* base = inp + ((size_t)b * p.c8_in + 2 * c) * plane_elems + (size_t)col0 * 8;
-                const bool paired = p.pair_tail && c == p.c16 - 1 && !(p.kpass == 2 && (v & 1));   // only plane 2c travels
+                const bool paired = p.pair_tail && c == p.c16 - 1;   // only plane 2c travels (fp16 and e4m3 passes alike)
                 // rows travel in two groups per chunk (R is even); one mbarrier pair per group, at the group's first slot
                 for (int grp = 0, rho = 0; grp < 2; ++grp) {
                     const int GR = grp ? GR1 : GR0;
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                 const int wsel = ((p.kpass == 3 && (v % 3) == 1) || (p.kpass == 2 && (v & 1))) ? 1 : 0;   // second weight image
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) + ((size_t)wsel * p.c16 + c) * p.kw * p.wstage_bytes;
                 // a paired chunk has (kw+1)/2 stages: K-half 0 / 1 = column taps (2s, 2s+1)
-                const int nst = (p.pair_tail && c == p.c16 - 1 && !(p.kpass == 2 && (v & 1))) ? p.npairs : p.kw;
+                const int nst = (p.pair_tail && c == p.c16 - 1) ? p.npairs : p.kw;
                 for (int dx = 0; dx < nst; ++dx, src += p.wstage_bytes) {
                     mbar_wait(w_empty + st, ph ^ 1);
                     if (leader) {
@@ -345,7 +346,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                     const bool f8 = (p.kpass == 2) && (c & 1);    // correction pass: e4m3 operands, K = 32
                     // paired chunk (one live 8-channel plane): the K halves are column taps (dx, dx+1) of that plane, i.e. the
                     // B descriptor's K-half stride is one pixel (16 B); the last stage is taps (kw-2, kw-1) with a zero first half
-                    const bool paired = p.pair_tail && !f8 && ((p.kpass == 3) ? c / 3 : (p.kpass == 2 ? c >> 1 : c)) == p.c16 - 1;
+                    // (e4m3 pass: the lone q plane carries [e4m3(x) | e4m3(x_lo)] of its 8 channels per pixel, so the same pairing holds)
+                    const bool paired = p.pair_tail && ((p.kpass == 3) ? c / 3 : (p.kpass == 2 ? c >> 1 : c)) == p.c16 - 1;
                     const int nst = paired ? p.npairs : p.kw;
                     const uint32_t b_lbo = paired ? (1u << 16) : b_lo_lbo;
                     // the chunk's rows sit in two groups of GR slots: [slot0, +GR) and the next group (which may wrap to 0)
@@ -416,6 +418,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
         const float bns = (p.bn_scale && live) ? p.bn_scale[co] : 1.f;
         const float bnt = (p.bn_shift && live) ? p.bn_shift[co] : 0.f;
         const int planes_out = (p.cout + 7) / 8;
+        // mode 3 "tail" plane: with an odd number of live 8-channel planes the last one is alone in its 16-channel group; its
+        // q plane then holds [e4m3(x) x 8 | e4m3(x_lo * 2^11) x 8] per pixel (one plane instead of two half-empty ones), which
+        // is what lets the consumer pair column taps in the e4m3 pass as well
+        const int tail_pl = (planes_out & 1) ? planes_out - 1 : -1;
         const int nchunks = p.n_tile / CHUNK_PX;
         const int per_part = (nchunks + nparts - 1) / nparts;
         const int ch_begin = part * per_part, ch_end = min(nchunks, ch_begin + per_part);
@@ -478,8 +484,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                         if (mode == 2) rl[e] = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.residual_lo) + off);
                         if (mode == 3) {
                             // remainder plane 2g+1 of this octet's 16-channel group: one plane up for an even plane, same plane otherwise
+                            // (tail plane: bytes 8..15 of the same plane)
                             const uint2 t2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(p.residual_lo) + off +
-                                ((o_pl[e] & 1) ? (size_t)8 : plane_px * 16));
+                                (((o_pl[e] & 1) || o_pl[e] == p.res_tail_pl) ? (size_t)8 : plane_px * 16));
                             rl[e].x = t2.x; rl[e].y = t2.y;
                         }
                     }
@@ -622,19 +629,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                                 // both octets belong to one row and one 16-channel group: planes (2g, 2g+1) -> 16-byte stores
                                 if (ok0) {
                                     const size_t base = (size_t)((long long)o_off[0] + ((long long)xo + d0) * 16);
-                                    *reinterpret_cast<uint4*>(dq + base) = make_uint4(q8[0].x, q8[0].y, q8[1].x, q8[1].y);
-                                    *reinterpret_cast<uint4*>(dq + base + plane_px * 16) = make_uint4(l8[0].x, l8[0].y, l8[1].x, l8[1].y);
+                                    if (o_pl[0] == tail_pl) {
+                                        *reinterpret_cast<uint4*>(dq + base) = make_uint4(q8[0].x, q8[0].y, l8[0].x, l8[0].y);
+                                    } else {
+                                        *reinterpret_cast<uint4*>(dq + base) = make_uint4(q8[0].x, q8[0].y, q8[1].x, q8[1].y);
+                                        *reinterpret_cast<uint4*>(dq + base + plane_px * 16) = make_uint4(l8[0].x, l8[0].y, l8[1].x, l8[1].y);
+                                    }
                                 }
                             } else {
-                                // CP = 8 / 24: an octet's neighbour in its 16-channel group is channel padding (CP = 8, and plane 2
-                                // of CP = 24: written as zeros) or lives in another thread (planes 0 / 1 of CP = 24: 8-byte stores)
+                                // CP = 8 / 24: an octet is alone in its 16-channel group (the tail plane) or its neighbour lives in
+                                // another thread (planes 0 / 1 of CP = 24: 8-byte stores)
 #pragma unroll
                                 for (int e = 0; e < 2; ++e) {
                                     if (oks[e]) {
                                         const size_t base = (size_t)((long long)o_off[e] + ((long long)xo + ds[e]) * 16);   // hi plane o_pl
-                                        if (CP == 8 || o_pl[e] == 2) {       // even plane, alone in its group: q plane = o_pl, remainder plane = o_pl + 1
-                                            *reinterpret_cast<uint4*>(dq + base) = make_uint4(q8[e].x, q8[e].y, 0u, 0u);
-                                            *reinterpret_cast<uint4*>(dq + base + plane_px * 16) = make_uint4(l8[e].x, l8[e].y, 0u, 0u);
+                                        if (o_pl[e] == tail_pl) {            // alone in its group: [x | remainder] in its own q plane
+                                            *reinterpret_cast<uint4*>(dq + base) = make_uint4(q8[e].x, q8[e].y, l8[e].x, l8[e].y);
                                         } else if (o_pl[e] == 0) {           // group 0, bytes 0..7
                                             *reinterpret_cast<uint2*>(dq + base) = q8[e];
                                             *reinterpret_cast<uint2*>(dq + base + plane_px * 16) = l8[e];
@@ -723,13 +733,21 @@ __global__ void pack_weights_kernel(const float* __restrict__ k, __half* __restr
         if (nsplit == 2) out[total + idx] = __float2half_rn(vh - __half2float(h));
         if (nsplit == 3) {
             // fp8 image [c][dx][plane][z][co][16]: plane 0 = e4m3(W_lo) pairs with e4m3(x),
-            // plane 1 = e4m3(W * 2^-11) pairs with e4m3(x_lo * 2^11); ci16 = pl*8+e of the (unpaired) fp16 image
+            // plane 1 = e4m3(W * 2^-11) pairs with e4m3(x_lo * 2^11); ci16 = pl*8+e of the fp16 image
             uint8_t* q = reinterpret_cast<uint8_t*>(out + total);
             const long long stage_elems = 2LL * Z * cp * 8;                    // fp16 elements per (c,dx) stage == bytes / 2
             const long long base = ((long long)c * kw + dx) * stage_elems * 2; // byte offset of the (c,dx) stage
-            const int ci16 = pl * 8 + e;
-            q[base + (((long long)0 * Z + z) * cp + co) * 16 + ci16] = to_e4m3(v - __half2float(__float2half_rn(v)));
-            q[base + (((long long)1 * Z + z) * cp + co) * 16 + ci16] = to_e4m3(v * (1.0f / LO_SCALE));
+            if (pair_tail && c == c16 - 1) {
+                // paired tail chunk: K half pl = column tap (as in the fp16 image); its 16 bytes are [W_lo x 8 | W * 2^-11 x 8],
+                // facing [e4m3(x) x 8 | e4m3(x_lo * 2^11) x 8] of the lone q plane
+                const long long o = base + (((long long)pl * Z + z) * cp + co) * 16 + e;
+                q[o] = to_e4m3(vh - __half2float(h));
+                q[o + 8] = to_e4m3(vh * (1.0f / LO_SCALE));
+            } else {
+                const int ci16 = pl * 8 + e;
+                q[base + (((long long)0 * Z + z) * cp + co) * 16 + ci16] = to_e4m3(v - __half2float(__float2half_rn(v)));
+                q[base + (((long long)1 * Z + z) * cp + co) * 16 + ci16] = to_e4m3(v * (1.0f / LO_SCALE));
+            }
         }
     }
 }
@@ -775,8 +793,11 @@ __global__ void __launch_bounds__(128) to_blk8_kernel(const float* __restrict__ 
 }
 
 // mode 3 companion of to_blk8: fp8 planes 2c = e4m3(x), 2c+1 = e4m3((x - fp16(x)) * 2^11), 16 channels each
+// tail_pl: plane of the tensor that is alone in its 16-channel group (odd live-plane count), or -1: that plane holds
+// [e4m3(x) x 8 | e4m3(remainder) x 8] per pixel and its partner plane stays zero
 __global__ void __launch_bounds__(128) to_q8_kernel(const float* __restrict__ in, uint8_t* __restrict__ outq, int C, int H,
-                                                    int W, int Hp, int P, int c8_total, int plane0, long long in_bstride, int nc, int halo_sym) {
+                                                    int W, int Hp, int P, int c8_total, int plane0, long long in_bstride, int nc, int halo_sym,
+                                                    int tail_pl) {
     const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
     const int b = blockIdx.z / nc, cc = blockIdx.z - b * nc;
@@ -791,9 +812,14 @@ __global__ void __launch_bounds__(128) to_q8_kernel(const float* __restrict__ in
     }
     const size_t plane = ((size_t)b * c8_total + plane0 + 2 * cc) * Hp * P;
     const uint4 av = *reinterpret_cast<const uint4*>(a8), lv = *reinterpret_cast<const uint4*>(l8);
+    const bool tail = (plane0 + 2 * cc == tail_pl);
     mirror_targets(y, x, H, W, P, halo_sym, [&](size_t pix) {
-        *reinterpret_cast<uint4*>(outq + (plane + pix) * 16) = av;
-        *reinterpret_cast<uint4*>(outq + (plane + pix + (size_t)Hp * P) * 16) = lv;
+        if (tail) {
+            *reinterpret_cast<uint4*>(outq + (plane + pix) * 16) = make_uint4(av.x, av.y, lv.x, lv.y);
+        } else {
+            *reinterpret_cast<uint4*>(outq + (plane + pix) * 16) = av;
+            *reinterpret_cast<uint4*>(outq + (plane + pix + (size_t)Hp * P) * 16) = lv;
+        }
     });
 }
 
@@ -801,7 +827,7 @@ __global__ void __launch_bounds__(128) to_q8_kernel(const float* __restrict__ in
 // eight coalesced channel-plane writes.
 __global__ void __launch_bounds__(128) from_blk8_kernel(const __half* __restrict__ in, const __half* __restrict__ in_lo,
                                                         float* __restrict__ out, int C, int H, int W, int Hp, int P,
-                                                        int c8_total, int plane0, long long out_bstride, int np, int mode) {
+                                                        int c8_total, int plane0, long long out_bstride, int np, int mode, int tail_pl) {
     const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
     const int b = blockIdx.z / np, pl = blockIdx.z - b * np;
@@ -819,7 +845,10 @@ __global__ void __launch_bounds__(128) from_blk8_kernel(const __half* __restrict
     }
     if (in_lo && mode == 3) {
         // channel c lives in fp8 plane 2*(c/16)+1 at byte c%16: this 8-channel plane is half of one 16-byte pixel
-        const size_t qoff = ((((size_t)b * c8_total + plane0 + 2 * (pl >> 1) + 1) * Hp + (y + HALO)) * P + (x + HALO)) * 16 + 8 * (pl & 1);
+        // (the tail plane keeps its remainders in its own bytes 8..15)
+        const int pa = plane0 + pl;
+        const int qpl = (pa == tail_pl) ? pa : (pa | 1);
+        const size_t qoff = ((((size_t)b * c8_total + qpl) * Hp + (y + HALO)) * P + (x + HALO)) * 16 + ((pa == tail_pl) ? 8 : 8 * (pa & 1));
         const uint2 qv = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(in_lo) + qoff);
         const uint8_t* q = reinterpret_cast<const uint8_t*>(&qv);
 #pragma unroll
@@ -904,8 +933,10 @@ __global__ void __launch_bounds__(128) dbcnn_expand_blk8_kernel(const float* __r
                         a8[e] = to_e4m3(f[e]);
                         l8[e] = to_e4m3((f[e] - __half2float(v[e])) * LO_SCALE);
                     }
+                    // (a lone last plane keeps [x | remainder] in its own q plane)
+                    const bool tail = (np & 1) && pl == np - 1;
                     const size_t q0 = (((size_t)b * c8_total + 2 * (pl >> 1)) * plane_px + pix) * 16 + 8 * (pl & 1);
-                    const size_t q1 = q0 + plane_px * 16;
+                    const size_t q1 = tail ? q0 + 8 : q0 + plane_px * 16;
                     *reinterpret_cast<uint2*>(q + q0) = *reinterpret_cast<const uint2*>(a8);
                     *reinterpret_cast<uint2*>(q + q1) = *reinterpret_cast<const uint2*>(l8);
                 }
@@ -926,6 +957,10 @@ static inline int grid_for(long long total, int block = 256, int cap = 148 * 16)
 
 using namespace pcnn;
 using namespace pcnn::tc;
+
+// Mode-3 tensors with an odd number of live 8-channel planes: index of the last one (alone in its 16-channel group), else -1.
+// Its q plane holds [e4m3(x) x 8 | e4m3((x - hi) * 2^11) x 8] per pixel and the partner plane stays zero.
+static inline int tail_plane(int C) { const int np = (C + 7) / 8; return (np & 1) ? np - 1 : -1; }
 
 extern "C" size_t pcnn_blk8_bytes(int B, int C, int H, int W) {
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
@@ -988,13 +1023,14 @@ extern "C" int pcnn_to_blk8(const float* in, void* out, void* out_lo, int mode, 
     PCNN_CHECK_ARG(mode >= 1 && mode <= 3 && (mode == 1 || out_lo), "to_blk8: precision mode 2/3 needs the second buffer");
     PCNN_CHECK_ARG(mode != 3 || (c_offset % 16) == 0, "to_blk8: mode 3 needs a channel offset that is a multiple of 16");
     PCNN_CHECK_ARG(in && out && B > 0 && C > 0 && (c_offset % 8) == 0 && c_offset + C <= ((c_total + 15) / 16) * 16, "to_blk8: bad argument");
+    const int tail_pl = tail_plane(c_total);
     const int c8_total = ((c_total + 15) / 16) * 2;
     const int np = (C + 7) / 8, nc = (C + 15) / 16;
     PCNN_CHECK_ARG(H <= 65535 && (long long)B * np <= 65535, "to_blk8: grid too large (H %d, B*planes %lld)", H, (long long)B * np);
     to_blk8_kernel<<<dim3(ceil_div(W, 128), H, B * np), 128, 0, (cudaStream_t)stream>>>(in, (__half*)out, mode == 2 ? (__half*)out_lo : nullptr, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, in_bstride, np, hsym);
     PCNN_CHECK_LAUNCH();
     if (mode == 3) {
-        to_q8_kernel<<<dim3(ceil_div(W, 128), H, B * nc), 128, 0, (cudaStream_t)stream>>>(in, (uint8_t*)out_lo, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, in_bstride, nc, hsym);
+        to_q8_kernel<<<dim3(ceil_div(W, 128), H, B * nc), 128, 0, (cudaStream_t)stream>>>(in, (uint8_t*)out_lo, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, in_bstride, nc, hsym, tail_pl);
         PCNN_CHECK_LAUNCH();
     }
     return PCNN_OK;
@@ -1008,7 +1044,7 @@ extern "C" int pcnn_from_blk8(const void* in, const void* in_lo, int mode, float
     const int c8_total = ((c_total + 15) / 16) * 2;
     const int np = (C + 7) / 8;
     PCNN_CHECK_ARG(H <= 65535 && (long long)B * np <= 65535, "from_blk8: grid too large");
-    from_blk8_kernel<<<dim3(ceil_div(W, 128), H, B * np), 128, 0, (cudaStream_t)stream>>>((const __half*)in, mode >= 2 ? (const __half*)in_lo : nullptr, out, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, out_bstride, np, mode);
+    from_blk8_kernel<<<dim3(ceil_div(W, 128), H, B * np), 128, 0, (cudaStream_t)stream>>>((const __half*)in, mode >= 2 ? (const __half*)in_lo : nullptr, out, C, H, W, H + 2 * HALO, W + 2 * HALO, c8_total, c_offset / 8, out_bstride, np, mode, tail_plane(c_total));
     PCNN_CHECK_LAUNCH();
     return PCNN_OK;
 }
@@ -1063,6 +1099,13 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
     p.nv = p.c16 * p.kpass;
     p.pair_tail = pair_tail_for(Cin_total, k) ? 1 : 0;
     p.npairs = (k + 1) / 2;
+    p.res_tail_pl = (nsplit == 3 && residual) ? tail_plane(Cres_total) : -1;
+    // mode 3: a lone last plane of the output uses the tail q layout, which belongs to the TENSOR: a convolution with an odd
+    // plane count must own the tensor's last plane (and then the tensor has as many live planes as the convolution writes)
+    PCNN_CHECK_ARG(nsplit != 3 || (((Cout + 7) / 8) & 1) == 0 || (Cout_total + 7) / 8 == (Cout + 7) / 8,
+                   "conv2d_tc: precision mode 3 cannot write %d channels into a %d-channel tensor (odd plane count)", Cout, Cout_total);
+    PCNN_CHECK_ARG(nsplit != 3 || (((Cout + 7) / 8) & 1) || tail_plane(Cout_total) < 0 || (Cout + 7) / 8 <= tail_plane(Cout_total),
+                   "conv2d_tc: precision mode 3: %d channels overlap the tail plane of a %d-channel tensor", Cout, Cout_total);
     p.c8_in = p.c16 * 2; p.c8_out = ((Cout_total + 15) / 16) * 2; p.c8_res = ((Cres_total + 15) / 16) * 2;
     p.cout = Cout; p.kh = k; p.kw = k; p.pad = k / 2; p.act = act; p.halo_sym = (out_halo_mode == PCNN_PAD_SYMMETRIC);
     const int cp = choose_cp(Cout, k), rt = rows_per_tile(cp), zpad = rt - 1;
@@ -1083,8 +1126,8 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
     const int R = k + zpad;
     const size_t avail = kMax - fixed, rowslot = 2 * (size_t)p.rowplane_bytes, wst = p.wstage_bytes;
     PCNN_CHECK_ARG((size_t)R * rowslot + 2 * wst <= avail, "conv2d_tc: tile does not fit in shared memory (k=%d, n_tile=%d)", k, p.n_tile);
-    // weight stages per tile: kw per pass, (kw+1)/2 for the fp16 passes of a paired last chunk
-    const int total_stages = p.nv * k - (p.pair_tail ? (p.kpass == 2 ? 1 : p.kpass) * (k - p.npairs) : 0);
+    // weight stages per tile: kw per pass, (kw+1)/2 for the passes of a paired last chunk
+    const int total_stages = p.nv * k - (p.pair_tail ? p.kpass * (k - p.npairs) : 0);
     int slots, w_stages, resident = 0;
     if ((size_t)R * rowslot + (size_t)total_stages * wst <= avail && total_stages <= 48) {
         resident = 1; w_stages = total_stages;

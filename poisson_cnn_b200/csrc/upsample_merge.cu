@@ -57,6 +57,7 @@ struct Params {
     __half* out; uint8_t* out_lo;
     int mode;                    // precision mode of the destination (1, 2, 3: see pcnn_conv2d_tc)
     int B, C, H, W, c8_total, plane0;
+    int tail_pl;             // mode 3: plane of the tensor that is alone in its 16-channel group (odd live-plane count), or -1
     int st_floats;               // staging region (phase-major deconv results / interpolated resize row)
     int tile_floats;             // offset of the weights inside an operand buffer (= size of the largest input tile)
     int buf_floats[2];           // operand buffers used by even / odd steps
@@ -430,8 +431,12 @@ __global__ void __launch_bounds__(NTHR, 1) upsample_merge_kernel(const Params p)
                                             e4m3x4(l[8] * LO_SCALE, l[9] * LO_SCALE, l[10] * LO_SCALE, l[11] * LO_SCALE),
                                             e4m3x4(l[12] * LO_SCALE, l[13] * LO_SCALE, l[14] * LO_SCALE, l[15] * LO_SCALE));
                 uint8_t* q = p.out_lo + (((size_t)b * p.c8_total + p.plane0 + 2 * g) * plane_px + pix) * 16;
-                *reinterpret_cast<uint4*>(q) = qv;
-                *reinterpret_cast<uint4*>(q + plane_px * 16) = lv;
+                if (p.plane0 + 2 * g == p.tail_pl) {      // lone plane: [x x 8 | remainder x 8] in its own q plane
+                    *reinterpret_cast<uint4*>(q) = make_uint4(qv.x, qv.y, lv.x, lv.y);
+                } else {
+                    *reinterpret_cast<uint4*>(q) = qv;
+                    *reinterpret_cast<uint4*>(q + plane_px * 16) = lv;
+                }
             }
         }
     }
@@ -482,10 +487,14 @@ extern "C" int pcnn_upsample_merge_blk8(int n_deconv, const float* const* dc_in,
     PCNN_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && H <= 65535 && W > 0, "upsample_merge_blk8: bad shape");
     PCNN_CHECK_ARG(C >= 8 && C <= 32 && (C % 8) == 0, "upsample_merge_blk8: channels %d must be a multiple of 8, <= 32", C);
     PCNN_CHECK_ARG((c_offset % 16) == 0 && c_offset + C <= ((c_total + 15) / 16) * 16, "upsample_merge_blk8: channel offset must be a multiple of 16 inside the buffer");
+    const int np_total = (c_total + 7) / 8;
+    const int tail_pl = (mode == 3 && (np_total & 1)) ? np_total - 1 : -1;
+    PCNN_CHECK_ARG(mode != 3 || (C % 16) == 0 || c_offset / 8 + C / 8 - 1 == tail_pl,
+                   "upsample_merge_blk8: precision mode 3 writes whole 16-channel groups or ends on the tensor's lone last plane (C %d at %d of %d)", C, c_offset, c_total);
     Params p;
     p.n_dc = n_deconv; p.n_rs = n_resize; p.alpha = alpha;
     p.out = (__half*)out; p.out_lo = (uint8_t*)out_lo; p.mode = mode;
-    p.C = C; p.H = H; p.W = W; p.c8_total = ((c_total + 15) / 16) * 2; p.plane0 = c_offset / 8;
+    p.C = C; p.H = H; p.W = W; p.c8_total = ((c_total + 15) / 16) * 2; p.plane0 = c_offset / 8; p.tail_pl = tail_pl;
     p.B = B;
     // stage order: weight blocks (s*C*C floats) alternate large / small so that the two operand buffers are
     // [largest, 3rd, 5th ...] and [smallest, ...]: the even-step buffer holds the big blocks, the odd one the small

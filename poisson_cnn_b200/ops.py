@@ -10,7 +10,8 @@ import torch
 
 from . import _lib
 from ._lib import lib, check
-from .config import (ACT_LINEAR, PAD_CONSTANT, PAD_SYMMETRIC, RESIZE_NEAREST, RESIZE_BILINEAR, RESIZE_BICUBIC)
+from .config import (ACT_LINEAR, PAD_CONSTANT, PAD_SYMMETRIC, RESIZE_NEAREST, RESIZE_BILINEAR, RESIZE_BICUBIC,
+                     RESIZE_BICUBIC_LEGACY_AC)
 
 POOL_AVG, POOL_MAX = 0, 1
 BC_DIRICHLET, BC_NEUMANN = 0, 1
@@ -215,10 +216,11 @@ def _cached(key, build):
     return _cache[key]
 
 
-def _bicubic_table():
-    # TF resize_bicubic CPU kernel: 1024-step Keys (a=-0.5) table in float32
+def _bicubic_table(a=-0.5):
+    # TF resize_bicubic CPU kernel: 1024-step cubic-convolution table in float32 (a = -0.5 Keys with half-pixel
+    # centres, a = -0.75 for the legacy align_corners path)
     n = 1024
-    a = np.float32(-0.5)
+    a = np.float32(a)
     x = np.arange(n + 1, dtype=np.float32) / np.float32(n)
     t0 = ((a + np.float32(2)) * x - (a + np.float32(3))) * x * x + np.float32(1)
     x1 = x + np.float32(1)
@@ -229,9 +231,22 @@ def _bicubic_table():
 
 
 def resize_axis_table(n_in, n_out, method):
-    """Per-axis gather indices / weights of tf.image.resize (half-pixel centres, antialias=False)."""
-    scale = np.float32(n_in) / np.float32(n_out)
+    """Per-axis gather indices / weights of tf.image.resize (half-pixel centres, antialias=False), or of the
+    legacy tf.compat.v1 resize_images(BICUBIC, align_corners=True) used by dataset/utils/image_resize.py:20."""
     o = np.arange(n_out, dtype=np.float32)
+    if method == RESIZE_BICUBIC_LEGACY_AC:
+        # scale = (in-1)/(out-1), src = dst*scale, a = -0.75, out-of-range taps CLAMP to the edge (no renormalisation)
+        scale = np.float32(n_in - 1) / np.float32(n_out - 1) if n_out > 1 else np.float32(n_in) / np.float32(n_out)
+        src = o * scale
+        fl = np.floor(src)
+        tab = _cached("bicubic_tab_legacy", lambda: _bicubic_table(-0.75))
+        n = 1024
+        loc = fl.astype(np.int64)
+        off = np.rint((src - fl) * np.float32(n)).astype(np.int64)
+        w = np.stack([tab[off * 2 + 1], tab[off * 2], tab[(n - off) * 2], tab[(n - off) * 2 + 1]], 1).astype(np.float32)
+        idx = np.clip(np.stack([loc - 1, loc, loc + 1, loc + 2], 1), 0, n_in - 1)
+        return idx.astype(np.int32), w
+    scale = np.float32(n_in) / np.float32(n_out)
     if method == RESIZE_NEAREST:
         idx = np.clip(np.floor((o + np.float32(0.5)) * scale).astype(np.int64), 0, n_in - 1)
         return idx[:, None].astype(np.int32), np.ones((n_out, 1), np.float32)
@@ -670,6 +685,9 @@ def conv2d_tc(x, wp, bias=None, act=ACT_LINEAR, pad_mode=PAD_CONSTANT, bn=None, 
     split = nsplit >= 2
     if x.mode != nsplit:
         raise ValueError("conv2d_tc: weights packed for precision mode %d, input tensor is mode %d" % (nsplit, x.mode))
+    if nsplit == 3 and -(-wp["cin"] // 8) != -(-x.C // 8) and (-(-wp["cin"] // 8) % 2 or -(-x.C // 8) % 2):
+        # a lone last 8-channel plane changes the e4m3 plane layout of the tensor and the packing of the kernel
+        raise ValueError("conv2d_tc: mode-3 tensor with %d channels does not match a kernel packed for %d" % (x.C, wp["cin"]))
     blk8_halo_fill(x, k // 2, pad_mode)
     if out is None:
         out = Blk8(x.B, out_channels_total or cout, x.H, x.W, x.device, split=nsplit, sym=_fusable_halo(out_halo, x.H, x.W))

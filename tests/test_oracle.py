@@ -183,3 +183,32 @@ def test_oracle_reproduces_golden(name):
             hp, db = pcnn_configs()
             out = O.pcnn_forward(hp, db, all_weights(hp, db), *(t(k, dt) for k in ("rhs", "left", "top", "right", "bottom", "dx")))
         assert rel_l2(out, g["out"]) < tol
+
+
+def test_legacy_bicubic_image_resize_cross_checked_against_torch():
+    """dataset/utils/image_resize.py:20 (tf.compat.v1 resize_images BICUBIC, align_corners=True).  TF itself cannot
+    run here (parity unpinned); the restatement is cross-checked against torch's independent implementation of the
+    same filter (cubic convolution a = -0.75, align_corners, clamped taps), which differs only by TF's 1024-step
+    coefficient table (|dw| <= ~1e-3), and on the exact properties: control points are reproduced, constants stay
+    constant."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(5)
+    x = 2 * torch.rand(3, 1, 6, 9, generator=g, dtype=torch.float64) - 1
+    got = O.image_resize(x, (41, 73))
+    ref = F.interpolate(x, size=(41, 73), mode="bicubic", align_corners=True)
+    assert float((got - ref).abs().max()) < 3e-3
+    # align_corners: output point i*(out-1)/(in-1) sits on control point i
+    same = O.image_resize(x, (11, 17))       # (6-1)*2+1, (9-1)*2+1
+    np.testing.assert_allclose(same[:, :, ::2, ::2].numpy(), x.numpy(), atol=1e-12)
+    const = O.image_resize(torch.full((1, 1, 5, 5), 0.7, dtype=torch.float64), (20, 33))
+    np.testing.assert_allclose(const.numpy(), 0.7, atol=1e-6)      # table rows sum to 1 within float32 rounding
+
+
+def test_legacy_bicubic_host_tables_match_oracle():
+    from poisson_cnn_b200 import ops
+    from poisson_cnn_b200.config import RESIZE_BICUBIC_LEGACY_AC
+    for n_in, n_out in [(5, 64), (8, 256), (3, 7), (1, 1), (12, 300), (20, 2048)]:
+        idx, w = ops.resize_axis_table(n_in, n_out, RESIZE_BICUBIC_LEGACY_AC)
+        oi, ow = O.legacy_bicubic_axis_weights(n_in, n_out)
+        np.testing.assert_array_equal(idx, oi)
+        np.testing.assert_array_equal(w.astype(np.float64), ow)
