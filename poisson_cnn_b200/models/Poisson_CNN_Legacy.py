@@ -24,6 +24,7 @@ class Poisson_CNN_Legacy(WeightedModel):
         # (128 -> ~63 GB of pooled activations in 'mixed' mode) and scales inversely with the grid size.
         self.max_microbatch = max_microbatch
         self.microbatch_samples = None
+        self._io_streams = None     # (host->device, device->host) copy streams of the host-buffer call path
 
     def weight_specs(self, prefix=""):
         hs, hm = self.hpnn.weight_specs(prefix + "hpnn/")
@@ -45,7 +46,12 @@ class Poisson_CNN_Legacy(WeightedModel):
     def get_weights_dict(self, prefix=""):
         return {**self.hpnn.get_weights_dict(prefix + "hpnn/"), **self.dbcnn.get_weights_dict(prefix + "dbcnn/")}
 
-    def __call__(self, inp):
+    def __call__(self, inp, out=None):
+        """inp = [rhs, left, top, right, bottom, dx].  CUDA tensors -> CUDA result on the current stream (no sync).
+        HOST tensors (what a Keras user passes) -> the batch is streamed through the device in slices, the
+        host->device copy of slice i+1 and the device->host copy of slice i-1 overlapping the kernels of slice i on two
+        copy streams; returns a pinned host tensor (`out` if given: pass a pinned [B,1,nx,ny] float32 buffer to avoid the
+        page-locking cost per call).  The result is complete once the current stream has drained."""
         rhs, left, top, right, bottom, dx = inp
         if rhs.dim() != 4 or rhs.shape[1] != 1:
             raise ValueError("rhs must be [batch, 1, nx, ny] (channels_first)")
@@ -56,6 +62,10 @@ class Poisson_CNN_Legacy(WeightedModel):
         mb = self.microbatch_samples            # explicit slice size, if set
         if mb is None and self.max_microbatch:
             mb = max(1, int(self.max_microbatch * 65536 // (nx * ny)))
+        if not rhs.is_cuda:
+            return self._run_host(list(inp), mb, out)
+        if out is not None:
+            raise ValueError("out= applies to host inputs only")
         try:
             return self._run(rhs, left, top, right, bottom, dx, mb)
         except torch.OutOfMemoryError:
@@ -65,6 +75,53 @@ class Poisson_CNN_Legacy(WeightedModel):
             ops.blk8_pool_clear()
             torch.cuda.empty_cache()
             return self._run(rhs, left, top, right, bottom, dx, mb)
+
+    def _run_host(self, host, mb, out):
+        if self.device is None:
+            raise ValueError("load_weights() first: the model does not know its device yet")
+        dev = self.device
+        if any(t.is_cuda for t in host):
+            raise ValueError("inputs must be all on the host or all on the device")
+        host = [t.contiguous().float() for t in host]
+        host = [t if t.is_pinned() else t.pin_memory() for t in host]
+        B, _, nx, ny = host[0].shape
+        if out is None:
+            out = torch.empty((B, 1, nx, ny), dtype=torch.float32).pin_memory()
+        elif tuple(out.shape) != (B, 1, nx, ny) or out.dtype != torch.float32 or out.is_cuda or not out.is_contiguous():
+            raise ValueError("out must be a contiguous host float32 tensor of shape [batch, 1, nx, ny]")
+        mb = mb or B
+        # only the first slice's host->device copy and the last slice's device->host copy are exposed
+        with torch.cuda.device(dev):
+            if self._io_streams is None:
+                self._io_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            s_in, s_out = self._io_streams
+            cur = torch.cuda.current_stream(dev)
+            slices = [(lo, min(lo + mb, B)) for lo in range(0, B, mb)]
+            bufs = [[torch.empty((hi - lo,) + tuple(t.shape[1:]), device=dev, dtype=torch.float32) for t in host] for lo, hi in slices]
+            alloc = torch.cuda.Event(); alloc.record(cur)
+            s_in.wait_event(alloc)              # recycled blocks may still be read by kernels queued earlier
+            ready = []
+            with torch.cuda.stream(s_in):
+                for (lo, hi), bs in zip(slices, bufs):
+                    for b, t in zip(bs, host):
+                        b.copy_(t[lo:hi], non_blocking=True)
+                    ev = torch.cuda.Event(); ev.record(s_in); ready.append(ev)
+            for (lo, hi), bs, ev in zip(slices, bufs, ready):
+                cur.wait_event(ev)
+                try:
+                    o = self._forward(bs)
+                except torch.OutOfMemoryError:
+                    ops.blk8_pool_clear()
+                    torch.cuda.empty_cache()
+                    o = self._forward(bs)
+                done = torch.cuda.Event(); done.record(cur)
+                s_out.wait_event(done)
+                with torch.cuda.stream(s_out):
+                    out[lo:hi].copy_(o, non_blocking=True)
+                o.record_stream(s_out)
+            fin = torch.cuda.Event(); fin.record(s_out)
+            cur.wait_event(fin)                 # the caller's stream order covers the last device->host copy
+        return out
 
     def _run(self, rhs, left, top, right, bottom, dx, mb):
         B, _, nx, ny = rhs.shape

@@ -142,3 +142,28 @@ def test_random_grid_shapes_tensor_core_modes_track_fp32(model):
             out = model.set_precision(mode)(inp)
             assert bool(torch.isfinite(out).all()) and rel_l2(out, ref) < 2e-3, (nx, ny, B, mode)
         checked += 1
+
+
+def test_host_buffer_call_matches_device_call(model):
+    """model(host tensors) streams slices of the batch through the device on separate copy streams: same bits as the
+    device-resident call, pinned or pageable inputs, caller-provided output buffer."""
+    from poisson_cnn_b200.synthetic import make_problem
+    p = make_problem(5, 112, 120, seed=1010)
+    host = [p[k] for k in KEYS]
+    model.set_precision("mixed")
+    model.microbatch_samples = 2                 # 3 slices: 2 + 2 + 1
+    try:
+        ref = model([t.cuda() for t in host])
+        got = model(host)
+        torch.cuda.synchronize()
+        assert not got.is_cuda and got.is_pinned() and bool(torch.isfinite(got).all()) and torch.equal(got, ref.cpu())
+        out = torch.empty(5, 1, 112, 120).pin_memory()
+        got2 = model([t.pin_memory() for t in host], out=out)
+        torch.cuda.synchronize()
+        assert got2 is out and torch.equal(out, ref.cpu())
+        with pytest.raises(ValueError):
+            model(host, out=torch.empty(4, 1, 112, 120))
+        with pytest.raises(ValueError):
+            model([host[0].cuda()] + host[1:])
+    finally:
+        model.microbatch_samples = None
