@@ -50,10 +50,9 @@ __host__ __device__ constexpr int rows_per_tile(int cp) { return cp == 24 ? 5 : 
 // z-rows of the packed weights per (chunk, tap, K-half): kh taps + RT-1 zero rows on each side; CP = 24 gets one more
 // so that the 128-row window of the last input row (8 rows past 5 x 24) stays inside the stage
 __host__ __device__ constexpr int packed_zrows(int kh, int cp) { return kh + 2 * (rows_per_tile(cp) - 1) + (cp == 24 ? 1 : 0); }
-constexpr int MAX_EPI_WARPS = 8;
+constexpr int MAX_EPI_WARPS = 8;               // 12 for k <= 5 (second kernel build): those epilogues are latency-bound
 constexpr int CHUNK_PX = 16;                   // accumulator columns per epilogue pass
 constexpr int STAGE_WARP = CHUNK_PX * 128;     // per-warp transpose buffer: 16 pixels x 32 words
-constexpr int NUM_THREADS = (3 + MAX_EPI_WARPS) * 32;
 constexpr float LO_SCALE = 2048.f;        // 2^11: brings the fp16 rounding remainder into e4m3's range (mode 3)
 constexpr unsigned long long SPIN_LIMIT_NS = 4000000000ull;   // a stuck pipeline traps instead of hanging the GPU
 
@@ -211,8 +210,9 @@ __device__ __forceinline__ float2 bits_to_float2(uint32_t u) { return __half22fl
 // ---------------------------------------------------------------- the kernel
 // CP = channel slots per output row of the M operand (32, 24, 16 or 8); RT = rows_per_tile(CP) output rows per tile.
 // MODE = precision mode of the tensors (1, 2, 3): compile-time in the epilogue, which is instruction-bound on narrow layers.
-template <int CP, int MODE>
-__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p) {
+// NEPI = epilogue warps the build allows (8 or 12: the register budget per thread follows from it).
+template <int CP, int MODE, int NEPI>
+__global__ void __launch_bounds__((3 + NEPI) * 32, 1) conv_tc_kernel(const Params p) {
     constexpr int RT = rows_per_tile(CP);      // output rows per tile
     constexpr int ZPAD = RT - 1;         // zero z-rows on each side of the packed weights
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     // the weight stages start as zeros: the producer only ever copies the live z-rows into them
-    for (uint32_t i = threadIdx.x; i < (uint32_t)p.w_stages * (p.wstage_bytes >> 4); i += NUM_THREADS)
+    for (uint32_t i = threadIdx.x; i < (uint32_t)p.w_stages * (p.wstage_bytes >> 4); i += blockDim.x)
         reinterpret_cast<uint4*>(s_w)[i] = make_uint4(0u, 0u, 0u, 0u);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core's reads
     tc_fence_before();
@@ -423,8 +423,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
         // is what lets the consumer pair column taps in the e4m3 pass as well
         const int tail_pl = (planes_out & 1) ? planes_out - 1 : -1;
         const int nchunks = p.n_tile / CHUNK_PX;
-        const int per_part = (nchunks + nparts - 1) / nparts;
-        const int ch_begin = part * per_part, ch_end = min(nchunks, ch_begin + per_part);
+        const int ch_begin = (part * nchunks) / nparts, ch_end = ((part + 1) * nchunks) / nparts;   // balanced column split
         const int act = p.act;
         constexpr int mode = MODE;
         const bool affine = (p.bn_scale != nullptr) || (p.out_scale != nullptr);
@@ -496,9 +495,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
             mbar_wait(acc_full + acc, acc_ph);
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
+            // the accumulator columns of chunk ch+1 are requested as soon as chunk ch has arrived, so the TMEM read latency
+            // hides behind the math and stores of chunk ch (it was the critical path of the narrow, small-k layers)
+            uint32_t vn[16];
+            if (ch_begin < ch_end) tmem_ld16_issue(taddr0 + ch_begin * CHUNK_PX, vn);
             for (int ch = ch_begin; ch < ch_end; ++ch) {
                 uint32_t v[16];
-                tmem_ld16_issue(taddr0 + ch * CHUNK_PX, v);
                 float r[16];
                 if (has_res) {
                     // pixel side: residual -> fp32 -> transpose buffer
@@ -534,6 +536,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const Params p)
                     if (ch + 1 < ch_end) load_residual(ch + 1);    // in flight during this chunk's math and stores
                 }
                 tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = vn[j];
+                if (ch + 1 < ch_end) tmem_ld16_issue(taddr0 + (ch + 1) * CHUNK_PX, vn);
                 if (!(p.debug & 1)) {
                     // ---- lane side: bias -> activation -> (BN affine * scale) -> + residual.  Padded channels
                     //      (co >= cout) come out as exact zeros: zero weights, bias 0, shift 0.
@@ -971,7 +976,12 @@ extern "C" size_t pcnn_blk8_bytes(int B, int C, int H, int W) {
 
 // shared-memory budget of the kernel
 constexpr size_t SMEM_MAX = 227 * 1024;
-static inline int epi_warps_for(int k) { return (k >= 11) ? 4 : MAX_EPI_WARPS; }   // large kernels are MMA-bound by a wide margin
+// large kernels are MMA-bound by a wide margin (4 epilogue warps leave shared memory for operands); k <= 5 layers are bound
+// by the latency chain of their epilogue with two warps per scheduler, so they get three (PCNN_TC_EPI12=0: A/B only)
+static inline int epi_warps_for(int k) {
+    static const int epi12 = getenv("PCNN_TC_EPI12") ? atoi(getenv("PCNN_TC_EPI12")) : 1;
+    return (k >= 11) ? 4 : ((k <= 5 && epi12) ? 12 : MAX_EPI_WARPS);
+}
 static inline size_t smem_fixed_for(int k) { return (size_t)epi_warps_for(k) * STAGE_WARP + 2048; }   // transpose buffers + mbarriers
 
 // Channel slots per output row of the M operand for a k x k layer with Cout output channels: the narrowest of
@@ -1152,15 +1162,20 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
     auto launch = [&](auto kern) -> int {
         PCNN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax));
-        kern<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(p);
+        kern<<<grid, (3 + (p.n_epi > 8 ? 12 : 8)) * 32, smem, (cudaStream_t)stream>>>(p);
         PCNN_CHECK_LAUNCH();
         return PCNN_OK;
     };
-#define PCNN_TC_DISPATCH(CPV)                                         \
-    if (cp == CPV) {                                                  \
-        if (nsplit == 1) return launch(conv_tc_kernel<CPV, 1>);       \
-        if (nsplit == 2) return launch(conv_tc_kernel<CPV, 2>);       \
-        return launch(conv_tc_kernel<CPV, 3>);                        \
+#define PCNN_TC_DISPATCH(CPV)                                                                                   \
+    if (cp == CPV && p.n_epi <= 8) {                                                                            \
+        if (nsplit == 1) return launch(conv_tc_kernel<CPV, 1, 8>);                                              \
+        if (nsplit == 2) return launch(conv_tc_kernel<CPV, 2, 8>);                                              \
+        return launch(conv_tc_kernel<CPV, 3, 8>);                                                               \
+    }                                                                                                           \
+    if (cp == CPV) {                                                                                            \
+        if (nsplit == 1) return launch(conv_tc_kernel<CPV, 1, 12>);                                             \
+        if (nsplit == 2) return launch(conv_tc_kernel<CPV, 2, 12>);                                             \
+        return launch(conv_tc_kernel<CPV, 3, 12>);                                                              \
     }
     PCNN_TC_DISPATCH(32)
     PCNN_TC_DISPATCH(24)
