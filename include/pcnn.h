@@ -201,7 +201,11 @@ size_t pcnn_blk8_bytes(int B, int C, int H, int W);
 /* NCHW fp32 [B,C,H,W] (batch stride in_bstride) -> channels [c_offset, c_offset+C) of a BLK8 buffer
  * holding c_total channels (c_offset multiple of 8: this is how concat is assembled in place). */
 /* mode = precision mode of the tensor (see pcnn_conv2d_tc): 1 fp16 only; 2 second buffer = fp16
- * remainder; 3 second buffer = e4m3 planes (2c: x, 2c+1: remainder * 2^11, 16 channels each). */
+ * remainder; 3 second buffer = e4m3 planes (2c: x, 2c+1: remainder * 2^11, 16 channels each).
+ * Mode 3, tensors with an odd number of live 8-channel planes (c_total in 1..8, 17..24, ...): the lone last plane p
+ * keeps [e4m3(x) x 8 | e4m3(remainder * 2^11) x 8] per pixel in q plane p and leaves q plane p+1 zero.  All
+ * producers here (to_blk8, conv2d_tc, dbcnn_expand_blk8, upsample_merge_blk8) write and all consumers (conv2d_tc,
+ * from_blk8) read that form; it belongs to the TENSOR (c_total), not to the channel range of one call. */
 /* halo_mode: as out_halo_mode of pcnn_conv2d_tc (0 = halo untouched, SYMMETRIC = also write the mirrored ring). */
 int pcnn_to_blk8(const float* in, void* out, void* out_lo, int mode, int B, int C, int H, int W, int c_total,
                  int c_offset, int64_t in_bstride, int halo_mode, void* stream);
