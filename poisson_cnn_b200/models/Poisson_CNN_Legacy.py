@@ -76,6 +76,20 @@ class Poisson_CNN_Legacy(WeightedModel):
             torch.cuda.empty_cache()
             return self._run(rhs, left, top, right, bottom, dx, mb)
 
+    def capture(self, example_inputs):
+        """CUDA-graph the forward pass for the (batch, grid) shape of `example_inputs` (CUDA tensors, batch no larger
+        than one micro-batch): returns a callable with the same [rhs, left, top, right, bottom, dx] signature whose
+        cost on the host is one graph launch instead of ~165 kernel launches.  See poisson_cnn_b200/graph.py."""
+        from ..graph import GraphedCall
+        rhs = example_inputs[0]
+        B, _, nx, ny = rhs.shape
+        mb = self.microbatch_samples
+        if mb is None and self.max_microbatch:
+            mb = max(1, int(self.max_microbatch * 65536 // (nx * ny)))
+        if mb and B > mb:
+            raise ValueError("capture: batch %d exceeds one micro-batch (%d); graphs are for small batches" % (B, mb))
+        return GraphedCall(self._forward, list(example_inputs))
+
     def _run_host(self, host, mb, out):
         if self.device is None:
             raise ValueError("load_weights() first: the model does not know its device yet")

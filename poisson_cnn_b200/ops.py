@@ -545,7 +545,7 @@ class Blk8:
     Buffers are recycled (with their halo state) through a pool keyed by the exact shape, so steady-state
     inference neither allocates nor refills them."""
 
-    __slots__ = ("buf", "lo", "mode", "B", "C", "H", "W", "halo", "_key", "_key_lo")
+    __slots__ = ("buf", "lo", "mode", "B", "C", "H", "W", "halo", "_key", "_key_lo", "_pool")
 
     def __init__(self, B, C, H, W, device, split=False, sym=False):
         nbytes = lib.pcnn_blk8_bytes(B, C, H, W)
@@ -558,6 +558,7 @@ class Blk8:
         # ... and tensors whose producer writes a mirrored ring recycle among themselves (no refills in steady state)
         self._key = (str(device), B, C, H, W, "hi", bool(sym))
         self._key_lo = (str(device), B, C, H, W, "lo%d" % self.mode, bool(sym))
+        self._pool = _BLK8_POOL          # buffers go back to the pool they came from (a CUDA graph owns a private one)
         self.buf, st = _blk8_buffer(self._key, nbytes, device)
         self.lo = None
         if self.mode >= 2:
@@ -569,9 +570,9 @@ class Blk8:
 
     def __del__(self):
         try:
-            _BLK8_POOL.setdefault(self._key, []).append((self.buf, self.halo))
+            self._pool.setdefault(self._key, []).append((self.buf, self.halo))
             if self.lo is not None:
-                _BLK8_POOL.setdefault(self._key_lo, []).append((self.lo, self.halo))
+                self._pool.setdefault(self._key_lo, []).append((self.lo, self.halo))
         except Exception:
             pass
 
@@ -598,6 +599,40 @@ class Blk8:
 
 def blk8_pool_clear():
     _BLK8_POOL.clear()
+
+
+class blk8_pool_scope:
+    """Context manager: BLK8 buffers are drawn from (and return to) `pool` instead of the process-wide one.
+    graph.GraphedCall gives every captured CUDA graph its own pool: the buffers a graph was captured with, and the
+    halo contents it leaves in them, must never be seen by eager calls or by other graphs."""
+
+    def __init__(self, pool):
+        self.pool = pool
+
+    def __enter__(self):
+        global _BLK8_POOL
+        self._saved = _BLK8_POOL
+        _BLK8_POOL = self.pool
+        return self.pool
+
+    def __exit__(self, *exc):
+        global _BLK8_POOL
+        _BLK8_POOL = self._saved
+        return False
+
+
+def blk8_pool_canonicalize(pool=None):
+    """Sort every free list by buffer address: the next pass then hands the same buffer to the same tensor as the
+    previous canonicalised pass did, whatever order the buffers came back in."""
+    pool = _BLK8_POOL if pool is None else pool
+    for v in pool.values():
+        v.sort(key=lambda e: e[0].data_ptr())
+
+
+def blk8_pool_snapshot(pool=None):
+    """{key: [(address, halo state), ...]}: what the next pass will find (used to detect the steady state)."""
+    pool = _BLK8_POOL if pool is None else pool
+    return {k: [(b.data_ptr(), st) for b, st in v] for k, v in pool.items() if v}
 
 
 def _fusable_halo(mode, H, W):

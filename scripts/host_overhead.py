@@ -15,4 +15,12 @@ for B in [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "1,16,64").spli
     t0 = time.perf_counter(); e0.record()
     for _ in range(5): model(inp)
     e1.record(); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
-    print("B=%d: enqueue %.1f ms/forward, GPU %.1f ms/forward, wall %.1f ms/forward" % (B, (t1 - t0) * 200, e0.elapsed_time(e1) / 5, (t2 - t0) * 200))
+    print("B=%d eager: enqueue %.2f ms/forward, GPU %.2f ms/forward, wall %.2f ms/forward" % (B, (t1 - t0) * 200, e0.elapsed_time(e1) / 5, (t2 - t0) * 200))
+    if B <= 128:
+        g = model.capture(inp)
+        for _ in range(2): g(inp)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); e0.record()
+        for _ in range(5): g(inp)
+        e1.record(); t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+        print("B=%d graph: enqueue %.2f ms/forward, GPU %.2f ms/forward, wall %.2f ms/forward" % (B, (t1 - t0) * 200, e0.elapsed_time(e1) / 5, (t2 - t0) * 200))

@@ -167,3 +167,25 @@ def test_host_buffer_call_matches_device_call(model):
             model([host[0].cuda()] + host[1:])
     finally:
         model.microbatch_samples = None
+
+
+def test_cuda_graph_replay_matches_eager(model):
+    """model.capture(): the replayed CUDA graph (private buffer pool, steady-state halo contents) returns the same
+    bits as the eager call, for several different inputs and interleaved with eager calls of other shapes."""
+    from poisson_cnn_b200.synthetic import make_problem
+    model.set_precision("mixed")
+    ex = [t.cuda() for t in (make_problem(2, 112, 120, seed=1)[k] for k in KEYS)]
+    g = model.capture(ex)
+    for seed in (2, 3, 4):
+        inp = [make_problem(2, 112, 120, seed=seed)[k].cuda() for k in KEYS]
+        ref = model(inp)
+        other = model(_problem(1, 128, 128, seed=9))          # eager traffic through the process-wide pool in between
+        got = g(inp).clone()
+        assert bool(torch.isfinite(ref).all()) and torch.equal(got, ref)
+        assert bool(torch.isfinite(other).all())
+    model.set_precision("fp32")
+    g32 = model.capture(ex)
+    inp = [make_problem(2, 112, 120, seed=5)[k].cuda() for k in KEYS]
+    assert torch.equal(g32(inp), model(inp))
+    with pytest.raises(ValueError):
+        g32([t[:1] for t in inp])
