@@ -1131,8 +1131,9 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
     // if every stage of a tile (nv*kw of them) fits, they stay RESIDENT for the whole kernel; otherwise as many
     // stages as fit (<= 12) are kept in flight -- the weight stream is latency-bound with few small stages.
     const size_t kMax = SMEM_MAX;
-    p.n_epi = epi_warps_for(k);
-    const size_t fixed = smem_fixed_for(k);
+    // (12 warps only for single-pass tensors: with 128 registers the mode-2/3 epilogues of the 480-thread build are no faster)
+    p.n_epi = (epi_warps_for(k) == 12 && nsplit != 1) ? MAX_EPI_WARPS : epi_warps_for(k);
+    const size_t fixed = smem_fixed_for(k);       // shared-memory plan as for the widest epilogue: choose_cp() must not depend on the mode
     const int R = k + zpad;
     const size_t avail = kMax - fixed, rowslot = 2 * (size_t)p.rowplane_bytes, wst = p.wstage_bytes;
     PCNN_CHECK_ARG((size_t)R * rowslot + 2 * wst <= avail, "conv2d_tc: tile does not fit in shared memory (k=%d, n_tile=%d)", k, p.n_tile);
