@@ -249,6 +249,20 @@ int pcnn_upsample_merge_blk8(int n_deconv, const float* const* dc_in, const floa
                              const int32_t* const* rs_ix, const float* const* rs_wx, const int* rs_taps,
                              const int* rs_ih, const int* rs_iw, float alpha, void* out, void* out_lo,
                              int mode, int B, int C, int H, int W, int c_total, int c_offset, void* stream);
+/* pcnn_upsample_merge_blk8 with the transpose convolutions on the tensor cores (csrc/upsample_merge_tc.cu; mma.sync
+ * m16n8k16, fp16 operands, fp32 accumulation): dc_in[d] are BLK8 fp16 tensors [B][4][ih+14][iw+14][8] (C = 32 channels, the
+ * hi buffer of a branch output: no fp32 copy of the branch is made), dc_wpack[d] the Keras deconv kernel [s,s,32,32]
+ * re-laid once per layer as fp16 [s][s][32][36] (pcnn_upsample_merge_tc_pack_kernel); resize branches as in
+ * pcnn_upsample_merge_blk8.  Same destination conventions (mode 3 needs an even number of 8-channel planes). */
+size_t pcnn_upsample_merge_tc_packed_bytes(int stride);
+int pcnn_upsample_merge_tc_pack_kernel(const float* kernel, void* packed, int stride, void* stream);
+int pcnn_upsample_merge_tc_blk8(int n_deconv, const void* const* dc_in, const void* const* dc_wpack,
+                                const float* const* dc_bias, const int* dc_stride, const int* dc_ih,
+                                const int* dc_iw, const int* dc_act, int n_resize, const float* const* rs_in,
+                                const int32_t* const* rs_iy, const float* const* rs_wy,
+                                const int32_t* const* rs_ix, const float* const* rs_wx, const int* rs_taps,
+                                const int* rs_ih, const int* rs_iw, float alpha, void* out, void* out_lo,
+                                int mode, int B, int H, int W, int c_total, int c_offset, void* stream);
 /* Same operator as pcnn_conv2d_f32 (pad + VALID conv + bias + act [+BN] [+residual] [*out_scale]) on
  * tcgen05 tensor cores: FP16 operands, FP32 accumulation in TMEM.  in/out/residual are BLK8 buffers
  * with Cin_total / Cout_total / Cres_total channels (Cin_total = the Cin the weights were packed with: the

@@ -52,6 +52,10 @@ SIGNATURES = {
     "pcnn_conv2d_tc": (c_int, [P] * 11 + [c_int] * 10 + [c_float, c_int, c_int, P]),
     "pcnn_upsample_merge_blk8": (c_int, [c_int, P, P, P, P, P, P, P, c_int, P, P, P, P, P, P, P, P, c_float, P, P,
                                          c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "pcnn_upsample_merge_tc_blk8": (c_int, [c_int, P, P, P, P, P, P, P, c_int, P, P, P, P, P, P, P, P, c_float, P, P,
+                                            c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "pcnn_upsample_merge_tc_packed_bytes": (c_size_t, [c_int]),
+    "pcnn_upsample_merge_tc_pack_kernel": (c_int, [P, P, c_int, P]),
     "pcnn_upsample_merge_packed_floats": (c_size_t, [c_int, c_int]),
     "pcnn_upsample_merge_pack_kernel": (c_int, [P, P, c_int, c_int, P]),
     "pcnn_dbcnn_expand_blk8": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),

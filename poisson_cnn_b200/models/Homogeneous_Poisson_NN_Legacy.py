@@ -6,6 +6,8 @@ libpcnn.so.  model([rhs, dx]) -> [B,1,H,W] on the device/stream of the inputs, n
 """
 import copy
 
+import os
+
 import torch
 
 from .. import ops
@@ -257,6 +259,10 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
         # them single-pass changes the merged model's error by < 1e-6 (tests/probes/layer_sensitivity_probe.py)
         bsplit = 1 if self.requested_precision == "mixed" else split
         pools = self._pool_pyramid(x0_f32, [blk.downsampling_factor for blk in blocks])
+        # single-pass branches with 32 filters feed the tensor-core upsample-merge kernel as BLK8 fp16 (no fp32 copy)
+        um_tc = (bsplit == 1 and F == 32 and os.environ.get("PCNN_UM_TC", "1") != "0"
+                 and any(b_.kind == "deconv" for b_ in blocks) and len(blocks) <= 16
+                 and all(b_.upsampling_factor <= 32 for b_ in blocks if b_.kind == "deconv"))
         for blk in blocks:
             self._branch_out_hw(blk, H, Wd)
             ph, pw = -(-H // blk.downsampling_factor), -(-Wd // blk.downsampling_factor)
@@ -267,9 +273,12 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
                 for r in range(1, blk.n_convs):
                     h = self._resnet_tc(h, "%s/resnet%d" % (name, r), blk.act, blk.pad, blk.use_batchnorm,
                                         next_pad=blk.pad if r + 1 < blk.n_convs else PAD_CONSTANT)
-                h = ops.from_blk8(h)
+                if not um_tc:
+                    h = ops.from_blk8(h)
             else:
                 h = self._bottleneck_lowres(blk, x0_f32, pools[blk.downsampling_factor])
+                if um_tc and blk.kind == "deconv":
+                    h = ops.to_blk8(h)           # tiny map (< 16 pixels a side) computed by the FP32 stack kernel
             if blk.kind == "deconv":
                 dk, db = self.conv(name + "/deconv")
                 dc.append((h, dk, db, blk.upsampling_factor, blk.deconv_act))
@@ -281,7 +290,16 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
         fused = (F % 8 == 0 and len(dc) <= 8 and len(rs) <= 8
                  and all(tuple(k.shape) == (s_, s_, F, F) and s_ <= 32 for _, k, _, s_, _ in dc)
                  and all(F * h.shape[2] * h.shape[3] <= 8192 for h, _ in rs))
-        if fused:
+        if um_tc and fused:
+            packed = []
+            for h, k, bias_, s_, act_ in dc:
+                key = ("deconv_packed_tc", k.data_ptr())
+                if key not in self._tc:
+                    self._tc[key] = ops.pack_deconv_kernel_tc(k)
+                packed.append((h, self._tc[key], bias_, s_, act_))
+            ops.upsample_merge_tc_blk8(packed, rs, alpha, cat, F, H, Wd)
+        elif fused:
+            dc = [(ops.from_blk8(h) if isinstance(h, ops.Blk8) else h, k, b_, s_, a_) for h, k, b_, s_, a_ in dc]
             packed = []
             for h, k, bias_, s_, act_ in dc:
                 key = ("deconv_packed", k.data_ptr())
@@ -292,6 +310,7 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
         else:                                    # general kernels: fp32 merge buffer, one read-modify-write per branch
             merged = torch.empty((B, F, H, Wd), device=dev, dtype=torch.float32)
             for i, (h, dk, db, s_, act_) in enumerate(dc):
+                h = ops.from_blk8(h) if isinstance(h, ops.Blk8) else h
                 ops.deconv_same(h, dk, db, (H, Wd), s_, act_, alpha, out=merged, accumulate=(i != 0))
             for i, (h, method) in enumerate(rs):
                 ops.resize(h, (H, Wd), method, alpha, out=merged, accumulate=(i != 0 or bool(dc)))

@@ -822,3 +822,58 @@ def upsample_merge_blk8(deconv_branches, resize_branches, alpha, out, c_offset, 
     if out.halo[0] != PAD_CONSTANT:
         out.halo = (out.halo[0], -1)
     return out
+
+
+def pack_deconv_kernel_tc(kernel):
+    """Keras deconv kernel [s,s,32,32] (k == stride) -> fp16 phase matrices [s][s][32][36] for upsample_merge_tc_blk8."""
+    _chk(kernel, "kernel")
+    s_, s2, C, C2 = kernel.shape
+    if s_ != s2 or C != 32 or C2 != 32 or lib.pcnn_upsample_merge_tc_packed_bytes(int(s_)) == 0:
+        raise ValueError("pack_deconv_kernel_tc: needs a [s,s,32,32] kernel with s <= 32")
+    packed = torch.empty(lib.pcnn_upsample_merge_tc_packed_bytes(int(s_)) // 2, dtype=torch.float16, device=kernel.device)
+    check(lib.pcnn_upsample_merge_tc_pack_kernel(_p(kernel.contiguous()), _p(packed), int(s_), _stream()), "upsample_merge_tc_pack_kernel")
+    return packed
+
+
+def upsample_merge_tc_blk8(deconv_branches, resize_branches, alpha, out, c_offset, H, W):
+    """upsample_merge_blk8 with the transpose convolutions on the tensor cores, reading the branch outputs as BLK8 fp16.
+    deconv_branches: [(Blk8 x with 32 channels [ih,iw], packed kernel (pack_deconv_kernel_tc), bias or None, stride, act)];
+    resize_branches: [(x [B,32,ih,iw] fp32, method)]."""
+    import ctypes
+    if not isinstance(out, Blk8) or (out.H, out.W) != (int(H), int(W)):
+        raise ValueError("upsample_merge_tc_blk8: destination must be a Blk8 tensor of the output size")
+    B = out.B
+    keep = []
+
+    def arr_p(vals):
+        return (ctypes.c_void_p * max(len(vals), 1))(*[v for v in vals])
+
+    def arr_i(vals):
+        return (ctypes.c_int * max(len(vals), 1))(*[int(v) for v in vals])
+    d_in, d_k, d_b, d_s, d_ih, d_iw, d_act = [], [], [], [], [], [], []
+    for x, kern, bias, stride, act in deconv_branches:
+        if not isinstance(x, Blk8) or x.C != 32 or x.B != B:
+            raise ValueError("upsample_merge_tc_blk8: deconv branch inputs are 32-channel Blk8 tensors of the same batch")
+        if kern.dtype != torch.float16 or kern.numel() * 2 != lib.pcnn_upsample_merge_tc_packed_bytes(int(stride)):
+            raise ValueError("upsample_merge_tc_blk8: kernel must come from pack_deconv_kernel_tc() with s == stride")
+        keep += [x, kern]
+        d_in.append(x.buf.data_ptr()); d_k.append(kern.data_ptr()); d_b.append(_p(bias)); d_s.append(stride)
+        d_ih.append(x.H); d_iw.append(x.W); d_act.append(act)
+    r_in, r_iy, r_wy, r_ix, r_wx, r_t, r_ih, r_iw = [], [], [], [], [], [], [], []
+    for x, method in resize_branches:
+        _chk(x, "x")
+        x = x.contiguous()
+        if x.shape[0] != B or x.shape[1] != 32:
+            raise ValueError("upsample_merge_tc_blk8: resize branch needs x [B,32,ih,iw]")
+        iy, wy = _resize_tables(x.device, x.shape[2], int(H), method)
+        ix, wx = _resize_tables(x.device, x.shape[3], int(W), method)
+        keep += [x]
+        r_in.append(x.data_ptr()); r_iy.append(iy.data_ptr()); r_wy.append(wy.data_ptr()); r_ix.append(ix.data_ptr())
+        r_wx.append(wx.data_ptr()); r_t.append(iy.shape[1]); r_ih.append(x.shape[2]); r_iw.append(x.shape[3])
+    check(lib.pcnn_upsample_merge_tc_blk8(len(d_in), arr_p(d_in), arr_p(d_k), arr_p(d_b), arr_i(d_s), arr_i(d_ih), arr_i(d_iw),
+                                          arr_i(d_act), len(r_in), arr_p(r_in), arr_p(r_iy), arr_p(r_wy), arr_p(r_ix), arr_p(r_wx),
+                                          arr_i(r_t), arr_i(r_ih), arr_i(r_iw), float(alpha), _p(out.buf), _p(out.lo), out.mode,
+                                          B, int(H), int(W), out.C, int(c_offset), _stream()), "upsample_merge_tc_blk8")
+    if out.halo[0] != PAD_CONSTANT:
+        out.halo = (out.halo[0], -1)
+    return out

@@ -169,6 +169,41 @@ def test_upsample_merge_blk8(ops, H, W, C, mode):
     assert float(ops.from_blk8(out, C=c_off, c_offset=0).abs().max()) == 0.0     # neighbouring channels untouched
 
 
+@pytest.mark.parametrize("H,W,mode,B", [(256, 256, 3, 2), (200, 300, 1, 3), (37, 50, 3, 2), (64, 80, 2, 9), (112, 120, 3, 17)])
+def test_upsample_merge_tc_blk8(ops, H, W, mode, B):
+    """Tensor-core version: the transpose convolutions run as mma.sync products from BLK8 fp16 branch outputs.  Same
+    operator as test_upsample_merge_blk8; the reference sees the fp16-rounded inputs and kernels the tensor cores see."""
+    from poisson_cnn_b200.config import resize_enum
+    g = torch.Generator().manual_seed(H + W + B)
+    C = 32
+    dc, rs, ref, parts = [], [], 0.0, []
+    for s, act in ((16, 1), (8, 1), (4, 2), (3, 0), (2, 1)):
+        ih, iw = -(-H // s), -(-W // s)
+        x = torch.randn(B, C, ih, iw, generator=g)
+        kern = torch.randn(s, s, C, C, generator=g) / C ** 0.5
+        bias = torch.randn(C, generator=g) * 0.1
+        dc.append((ops.to_blk8(dev(x)), ops.pack_deconv_kernel_tc(dev(kern)), dev(bias) if s != 3 else None, s, act))
+        parts.append(O.deconv_same(h16(x), h16(kern), bias.double() if s != 3 else torch.zeros(C, dtype=torch.float64), ACTS[act], (H, W), s))
+        ref = ref + parts[-1]
+    for (ih, iw), m in (((2, 2), "bilinear"), ((4, 5), "bicubic"), ((8, 8), "nearest")):
+        x = torch.randn(B, C, ih, iw, generator=g)
+        rs.append((dev(x), resize_enum(m)))
+        ref = ref + O.resize(x.double(), (H, W), m)
+    alpha = 1.0 / 8
+    ref = ref * alpha
+    out = ops.Blk8(B, 2 * C, H, W, torch.device("cuda"), split=mode)
+    ops.upsample_merge_tc_blk8(dc, rs, alpha, out, C, H, W)
+    got = ops.from_blk8(out, C=C, c_offset=C)
+    assert bool(torch.isfinite(got).all())
+    tol = {1: 6e-4, 2: 3e-6, 3: 4e-5}[mode]          # storage precision of the destination
+    assert rel_l2(got, ref) < tol
+    assert float(ops.from_blk8(out, C=C, c_offset=0).abs().max()) == 0.0     # neighbouring channels untouched
+    if mode == 1:                                     # two branches, no resize branches, whole tensor
+        out2 = ops.Blk8(B, C, H, W, torch.device("cuda"))
+        ops.upsample_merge_tc_blk8(dc[:2], [], 1.0, out2, 0, H, W)
+        assert rel_l2(ops.from_blk8(out2), parts[0] + parts[1]) < tol
+
+
 # ------------------------------------------------------------------ whole models in tensor-core mode
 def _models(hp_cfg, db_cfg, w):
     from poisson_cnn_b200 import convert_tf_object_names, models
