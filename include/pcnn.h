@@ -254,6 +254,8 @@ int pcnn_upsample_merge_blk8(int n_deconv, const float* const* dc_in, const floa
  * hi buffer of a branch output: no fp32 copy of the branch is made), dc_wpack[d] the Keras deconv kernel [s,s,32,32]
  * re-laid once per layer as fp16 [s][s][32][36] (pcnn_upsample_merge_tc_pack_kernel); resize branches as in
  * pcnn_upsample_merge_blk8.  Same destination conventions (mode 3 needs an even number of 8-channel planes). */
+/* shared memory the tensor-core kernel needs for these branches (0: unsupported); beyond 227 KB use pcnn_upsample_merge_blk8 */
+size_t pcnn_upsample_merge_tc_smem_bytes(int n_deconv, const int* dc_stride, int n_resize, const int* rs_ih, const int* rs_iw);
 size_t pcnn_upsample_merge_tc_packed_bytes(int stride);
 int pcnn_upsample_merge_tc_pack_kernel(const float* kernel, void* packed, int stride, void* stream);
 int pcnn_upsample_merge_tc_blk8(int n_deconv, const void* const* dc_in, const void* const* dc_wpack,

@@ -419,6 +419,26 @@ extern "C" int pcnn_upsample_merge_tc_pack_kernel(const float* kernel, void* pac
     return PCNN_OK;
 }
 
+// Shared memory the kernel needs for these branches (0 = unsupported arguments); callers fall back to
+// pcnn_upsample_merge_blk8 when it exceeds 227 KB (large resize sources: grids beyond ~400 pixels a side).
+extern "C" size_t pcnn_upsample_merge_tc_smem_bytes(int n_deconv, const int* dc_stride, int n_resize, const int* rs_ih, const int* rs_iw) {
+    if (n_deconv < 1 || n_deconv > MAXB || n_resize < 0 || n_resize > MAXB || !dc_stride || (n_resize && (!rs_ih || !rs_iw))) return 0;
+    size_t a = 0, w = 0, r = 0, row = 0;
+    for (int d = 0; d < n_deconv; ++d) {
+        const int s = dc_stride[d];
+        if (s < 1 || s > 32) return 0;
+        a += (size_t)4 * ((((SEG_W - 1) / s + 2) + 3) & ~3) * 16;
+        w += (size_t)s * WMAT * 2;
+    }
+    for (int q = 0; q < n_resize; ++q) {
+        if (rs_ih[q] < 1 || rs_iw[q] < 1) return 0;
+        r += (size_t)C * rs_ih[q] * rs_iw[q] * 4;
+        row += (size_t)((C * rs_iw[q] + 3) & ~3);
+    }
+    row = (row + 31) & ~(size_t)31;
+    return w + 2 * a + 2 * r + (size_t)NWARP * 32 * C * 4 + (size_t)NWARP * row * 4 + 64;
+}
+
 extern "C" int pcnn_upsample_merge_tc_blk8(int n_deconv, const void* const* dc_in, const void* const* dc_wpack,
                                            const float* const* dc_bias, const int* dc_stride, const int* dc_ih, const int* dc_iw,
                                            const int* dc_act, int n_resize, const float* const* rs_in,

@@ -263,6 +263,10 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
         um_tc = (bsplit == 1 and F == 32 and os.environ.get("PCNN_UM_TC", "1") != "0"
                  and any(b_.kind == "deconv" for b_ in blocks) and len(blocks) <= 16
                  and all(b_.upsampling_factor <= 32 for b_ in blocks if b_.kind == "deconv"))
+        if um_tc:                                # ... and only if its operands fit in shared memory (grids up to ~400 pixels a side)
+            um_tc = ops.upsample_merge_tc_fits(
+                [b_.upsampling_factor for b_ in blocks if b_.kind == "deconv"],
+                [(-(-H // b_.downsampling_factor), -(-Wd // b_.downsampling_factor)) for b_ in blocks if b_.kind != "deconv"])
         for blk in blocks:
             self._branch_out_hw(blk, H, Wd)
             ph, pw = -(-H // blk.downsampling_factor), -(-Wd // blk.downsampling_factor)

@@ -835,6 +835,16 @@ def pack_deconv_kernel_tc(kernel):
     return packed
 
 
+def upsample_merge_tc_fits(strides, resize_hw):
+    """True if the tensor-core upsample-merge kernel can stage these branches in shared memory."""
+    import ctypes
+    st = (ctypes.c_int * max(len(strides), 1))(*[int(v) for v in strides])
+    ih = (ctypes.c_int * max(len(resize_hw), 1))(*[int(h) for h, _ in resize_hw])
+    iw = (ctypes.c_int * max(len(resize_hw), 1))(*[int(w) for _, w in resize_hw])
+    n = lib.pcnn_upsample_merge_tc_smem_bytes(len(strides), st, len(resize_hw), ih, iw)
+    return 0 < n <= 227 * 1024
+
+
 def upsample_merge_tc_blk8(deconv_branches, resize_branches, alpha, out, c_offset, H, W):
     """upsample_merge_blk8 with the transpose convolutions on the tensor cores, reading the branch outputs as BLK8 fp16.
     deconv_branches: [(Blk8 x with 32 channels [ih,iw], packed kernel (pack_deconv_kernel_tc), bias or None, stride, act)];

@@ -1,5 +1,5 @@
 """Warm, in-pipeline time per C-ABI entry point: wraps every libpcnn call in CUDA events (same stream) and sums
-the elapsed time per function over one forward pass.  usage: profile_ops.py [B] [precision]"""
+the elapsed time per function over one forward pass.  usage: profile_ops.py [B] [precision] [nx] [ny]"""
 import sys, os, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -11,7 +11,9 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 prec = sys.argv[2] if len(sys.argv) > 2 else "tc2"
 dev = torch.device("cuda", 0)
 model, _ = bench.build_model(dev, prec)
-p = make_problem(min(B, 16), 256, 256, seed=1001)
+NX = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+NY = int(sys.argv[4]) if len(sys.argv) > 4 else NX
+p = make_problem(min(B, 16), NX, NY, seed=1001)
 inp = [p[k].repeat(-(-B // p[k].shape[0]), *([1] * (p[k].dim() - 1)))[:B].contiguous().cuda() for k in bench.KEYS]
 for _ in range(2):
     model(inp)

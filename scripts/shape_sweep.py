@@ -9,7 +9,9 @@ model, _ = bench.build_model(dev, "mixed")
 for nx, ny, B in ((384, 128, 128), (512, 256, 128), (200, 300, 128), (1024, 1024, 16), (2048, 2048, 16)):
     p = make_problem(2, nx, ny, seed=1003)
     inp = [p[k].repeat(B // 2, *([1] * (p[k].dim() - 1))).contiguous().cuda() for k in bench.KEYS]
-    out = model.set_precision("mixed")(inp)
+    model.set_precision("mixed")
+    for _ in range(2):                      # the first pass of a new shape allocates the activation pool
+        out = model(inp)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); out = model(inp); e1.record(); torch.cuda.synchronize()

@@ -30,7 +30,7 @@ def _problem(B, nx, ny, seed):
     return [p[k].cuda() for k in KEYS]
 
 
-@pytest.mark.parametrize("nx,ny,B", [(384, 128, 2), (512, 256, 2), (200, 300, 3), (256, 256, 2)])
+@pytest.mark.parametrize("nx,ny,B", [(384, 128, 2), (512, 256, 2), (200, 300, 3), (256, 256, 2), (512, 512, 1)])
 def test_variable_aspect_grids_tc2_tracks_fp32(model, nx, ny, B):
     """BASELINE config 3 shapes (non-square: 2B+2B boundary batches, ragged tiles, two column tiles)."""
     inp = _problem(B, nx, ny, seed=1003)
