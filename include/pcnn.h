@@ -291,6 +291,21 @@ int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpack, const f
                    int Cin_total, int Cout, int Cout_total, int Cres_total, int H, int W, int k, int act,
                    int nsplit, float acc_scale, int out_halo_mode, int num_sms, void* stream);
 
+/* Convolution of a SEPARABLE input on the row-group kernel ("row weights").  The DBCNN's first 2-D convolution
+ * (models/Dirichlet_BC_NN_Legacy.py:155-160 of the reference) sees in[b,m,x,y] = h[b,m,y] * S[m,x] (the mode expansion of
+ * :137-153; the two position channels are rank-1 too), so its row taps fold into per-row weights
+ *     A_x[b_tap, m, co] = sum_a W[a, b_tap, m, co] * S[m, x + a - k/2]     (S zero outside [0,H): CONSTANT zero padding)
+ * and out[b,co,x,y] = sum_{b_tap,m} A_x[b_tap,m,co] * h[b,m,y + b_tap - k/2]: ceil(Cin/16)*k MMAs per tile instead of
+ * ceil(Cin/16)*k*(k+RT-1), and the [B,Cin,H,W] expansion is never written.
+ * in_row: BLK8 fp16 tensor of the signals, [B][2*ceil(Cin/16)][1+14][W+14][8] (H = 1).  wrow: fp16
+ * [ceil(Cin/16)][k][2][T][CP][8] with T = pcnn_conv_tc_rowweight_slots(Cout,k,H), CP = pcnn_conv_tc_channel_slots(Cout,k),
+ * RT = 128/CP (5 for 24): slot t holds output row (t/RT)*RT + RT-1 - t%RT (zeros beyond H), K half = channels
+ * 16c + 8*half + [0,8).  Single FP16 pass only; bias + activation in the epilogue; out as for pcnn_conv2d_tc. */
+int pcnn_conv_tc_rowweight_slots(int Cout, int k, int H);
+int pcnn_conv2d_tc_rowweights(const void* in_row, const void* wrow, const float* bias, void* out, int B, int Cin,
+                              int Cout, int Cout_total, int H, int W, int k, int act, float acc_scale, int num_sms,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

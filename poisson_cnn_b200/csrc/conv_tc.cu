@@ -93,6 +93,10 @@ struct Params {
                              // adjacent column taps into the two K halves (B: K-half stride = one pixel) -> (kw+1)/2 MMAs per row, not kw
     int npairs;              // (kw+1)/2 weight stages of a paired chunk
     int res_tail_pl;         // mode 3: plane of the residual tensor holding a lone live octet (ceil(Cres/8) odd), else -1
+    int rw;                  // 1: "row weights" (pcnn_conv2d_tc_rowweights): the input is ONE row (a 1-D signal, H = 1) and every output
+                             // row has its own kw x Cin x Cout weights: wpack = [c16][kw][2][T slots][CP][8], slot t = tile*RT + (RT-1-r);
+                             // per tile one input row and c16*kw MMAs (no row taps, no zero z-rows)
+    int rw_tslots;           // T
     uint32_t rowplane_bytes; // bytes of one plane of one row window in smem (multiple of 128)
     uint32_t row_copy_bytes; // (n_tile + kw - 1) * 16
     uint32_t wstage_bytes;   // 2 * (kh+2(RT-1)) * CP * 16
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__((3 + NEPI) * 32, 1) conv_tc_kernel(const Param
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int R = p.kh + ZPAD;   // input rows per tile
+    const int R = p.rw ? 1 : p.kh + ZPAD;   // input rows per tile
     // rows travel in two barrier groups per chunk: R/2 each when R is even (row_slots is then a multiple of R/2 and a
     // group never wraps), (R+1)/2 and R/2 when it is odd (CP = 24; row_slots is then a multiple of R)
     const int GR0 = (R + 1) / 2, GR1 = R / 2;
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__((3 + NEPI) * 32, 1) conv_tc_kernel(const Param
         // ================= input-row producer =================
         // converged warp, one elected lane issues the bulk copies; ring state advances by compare (no div/mod)
         const bool leader = elect_one();
-        const size_t plane_elems = (size_t)p.Hp * p.P * 8;
+        const size_t plane_elems = (size_t)(p.rw ? 1 + 2 * HALO : p.Hp) * p.P * 8;    // row-weights mode: the input tensor has H = 1
         uint32_t slot = 0, ph = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
             const int tx = t % p.tiles_x;
@@ -276,11 +280,12 @@ __global__ void __launch_bounds__((3 + NEPI) * 32, 1) conv_tc_kernel(const Param
                 // rows travel in two groups per chunk (R is even); one mbarrier pair per group, at the group's first slot
                 for (int grp = 0, rho = 0; grp < 2; ++grp) {
                     const int GR = grp ? GR1 : GR0;
+                    if (GR == 0) continue;                 // row-weights mode: a single input row, one group
                     mbar_wait(row_empty + slot, ph ^ 1);
                     if (leader) {
                         mbar_expect_tx(row_full + slot, (uint32_t)GR * (paired ? 1u : 2u) * p.row_copy_bytes);
                         for (int i = 0; i < GR; ++i, ++rho) {
-                            const __half* src = base + (size_t)min(prow0 + rho, p.Hp - 1) * p.P * 8;
+                            const __half* src = base + (size_t)(p.rw ? HALO : min(prow0 + rho, p.Hp - 1)) * p.P * 8;
                             const uint32_t dst = smem_u32(s_rows) + (slot + i) * row_slot_bytes;
                             bulk_copy_g2s(dst, src, p.row_copy_bytes, row_full + slot);
                             if (!paired) bulk_copy_g2s(dst + p.rowplane_bytes, src + plane_elems, p.row_copy_bytes, row_full + slot);
@@ -300,6 +305,23 @@ __global__ void __launch_bounds__((3 + NEPI) * 32, 1) conv_tc_kernel(const Param
         uint32_t st = 0, ph = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
             if (p.w_resident && t != (int)blockIdx.x) break;    // resident weights: one pass fills every stage
+            if (p.rw) {
+                // row weights: per (chunk, column tap) the 128 M rows of THIS tile: slots [ty*RT, ...) of each K half
+                const int ty = (t / p.tiles_x) % p.tiles_y;
+                const uint32_t khalf_g = (uint32_t)p.rw_tslots * CP * 16u;       // K-half stride in global memory
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)ty * RT * CP * 16u;
+                for (int s2 = 0; s2 < p.c16 * p.kw; ++s2, src += 2u * khalf_g) {
+                    mbar_wait(w_empty + st, ph ^ 1);
+                    if (leader) {
+                        mbar_expect_tx(w_full + st, 4096u);
+                        const uint32_t dst = smem_u32(s_w) + st * p.wstage_bytes;
+                        bulk_copy_g2s(dst, src, 2048u, w_full + st);
+                        bulk_copy_g2s(dst + 2048u, src + khalf_g, 2048u, w_full + st);
+                    }
+                    if (++st == (uint32_t)p.w_stages) { st = 0; ph ^= 1; }
+                }
+                continue;
+            }
             for (int v = 0; v < p.nv; ++v) {
                 const int c = (p.kpass == 3) ? v / 3 : (p.kpass == 2 ? v >> 1 : v);
                 const int wsel = ((p.kpass == 3 && (v % 3) == 1) || (p.kpass == 2 && (v & 1))) ? 1 : 0;   // second weight image
@@ -326,7 +348,7 @@ __global__ void __launch_bounds__((3 + NEPI) * 32, 1) conv_tc_kernel(const Param
         // registers); one elected lane issues tcgen05.mma / tcgen05.commit.  Everything per MMA is
         // incremental: descriptor low words advance by constants, ring slots wrap by compare.
         {
-            const uint32_t a_lbo = (uint32_t)packed_zrows(p.kh, CP) * (CP * 16u);   // K-half (plane) stride of the packed weights
+            const uint32_t a_lbo = p.rw ? 2048u : (uint32_t)packed_zrows(p.kh, CP) * (CP * 16u);   // K-half (plane) stride of the packed weights
             const uint32_t a_hi = (uint32_t)(make_desc(0, a_lbo, 128u) >> 32);
             const uint32_t b_hi = (uint32_t)(make_desc(0, p.rowplane_bytes, 128u) >> 32);
             const uint32_t a_lo_lbo = ((a_lbo >> 4) & 0x3FFF) << 16, b_lo_lbo = ((p.rowplane_bytes >> 4) & 0x3FFF) << 16;
@@ -364,6 +386,7 @@ __global__ void __launch_bounds__((3 + NEPI) * 32, 1) conv_tc_kernel(const Param
                         for (int grp = 0; grp < 2; ++grp) {
                             const uint32_t slot = grp ? slotB : slotA;
                             const int GR = grp ? GR1 : GR0;
+                            if (GR == 0) continue;
                             if (first_dx) { mbar_wait(row_full + slot, grp ? phB : phA); tc_fence_after(); }
                             if (leader) {
                                 uint32_t b_lo = ((rows_base16 + slot * slot16 + dx) & 0x3FFF) | b_lbo;
@@ -1082,10 +1105,11 @@ extern "C" int pcnn_dbcnn_expand_blk8(const float* h, const float* sinh_basis, c
     return PCNN_OK;
 }
 
-extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpack, const float* bias, const float* bn_scale,
-                              const float* bn_shift, const void* residual, const void* residual_lo, const float* out_scale,
-                              void* out, void* out_lo, int B, int Cin_total, int Cout, int Cout_total, int Cres_total,
-                              int H, int W, int k, int act, int nsplit, float acc_scale, int out_halo_mode, int num_sms, void* stream) {
+static int conv2d_tc_impl(const void* in, const void* in_lo, const void* wpack, const float* bias, const float* bn_scale,
+                          const float* bn_shift, const void* residual, const void* residual_lo, const float* out_scale,
+                          void* out, void* out_lo, int B, int Cin_total, int Cout, int Cout_total, int Cres_total,
+                          int H, int W, int k, int act, int nsplit, float acc_scale, int out_halo_mode, int num_sms, void* stream,
+                          int rw, int rw_tslots) {
     PCNN_CHECK_ARG(in && wpack && out, "conv2d_tc: null pointer");
     const bool skip_corr = (nsplit & PCNN_TC_SKIP_CORRECTION) != 0;
     nsplit &= ~PCNN_TC_SKIP_CORRECTION;
@@ -1107,8 +1131,9 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
     p.c16 = (Cin_total + 15) / 16;
     p.kpass = skip_corr ? 1 : (nsplit == 2 ? 3 : (nsplit == 3 ? 2 : 1));
     p.nv = p.c16 * p.kpass;
-    p.pair_tail = pair_tail_for(Cin_total, k) ? 1 : 0;
+    p.pair_tail = (!rw && pair_tail_for(Cin_total, k)) ? 1 : 0;
     p.npairs = (k + 1) / 2;
+    p.rw = rw; p.rw_tslots = rw_tslots;
     p.res_tail_pl = (nsplit == 3 && residual) ? tail_plane(Cres_total) : -1;
     // mode 3: a lone last plane of the output uses the tail q layout, which belongs to the TENSOR: a convolution with an odd
     // plane count must own the tensor's last plane (and then the tensor has as many live planes as the convolution writes)
@@ -1124,7 +1149,7 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
     p.num_tiles = B * p.tiles_x * p.tiles_y;
     p.row_copy_bytes = (uint32_t)(p.n_tile + k - 1) * 16u;
     p.rowplane_bytes = (p.row_copy_bytes + 127u) & ~127u;
-    p.wstage_bytes = 2u * (uint32_t)packed_zrows(k, cp) * (uint32_t)cp * 16u;
+    p.wstage_bytes = rw ? 4096u : 2u * (uint32_t)packed_zrows(k, cp) * (uint32_t)cp * 16u;
     // instruction descriptor: D=F32, A=B=F16, both K-major, N = n_tile, M = 128
     p.idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     // shared-memory plan.  Rows need >= R slots (ideally 2R: full double buffering across chunk switches).  Weights:
@@ -1133,14 +1158,18 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
     const size_t kMax = SMEM_MAX;
     // (12 warps only for single-pass tensors: with 128 registers the mode-2/3 epilogues of the 480-thread build are no faster)
     p.n_epi = (epi_warps_for(k) == 12 && nsplit != 1) ? MAX_EPI_WARPS : epi_warps_for(k);
-    const size_t fixed = smem_fixed_for(k);       // shared-memory plan as for the widest epilogue: choose_cp() must not depend on the mode
-    const int R = k + zpad;
+    if (rw) p.n_epi = 12;                         // 14 MMAs per tile: this layer is all epilogue
+    const size_t fixed = rw ? (size_t)12 * STAGE_WARP + 2048      // shared-memory plan as for the widest epilogue: choose_cp() must not
+                            : smem_fixed_for(k);                  // depend on the mode
+    const int R = rw ? 1 : k + zpad;
     const size_t avail = kMax - fixed, rowslot = 2 * (size_t)p.rowplane_bytes, wst = p.wstage_bytes;
     PCNN_CHECK_ARG((size_t)R * rowslot + 2 * wst <= avail, "conv2d_tc: tile does not fit in shared memory (k=%d, n_tile=%d)", k, p.n_tile);
     // weight stages per tile: kw per pass, (kw+1)/2 for the passes of a paired last chunk
     const int total_stages = p.nv * k - (p.pair_tail ? p.kpass * (k - p.npairs) : 0);
     int slots, w_stages, resident = 0;
-    if ((size_t)R * rowslot + (size_t)total_stages * wst <= avail && total_stages <= 48) {
+    if (rw) {
+        slots = 4; w_stages = 12;                 // four tiles' signal rows and twelve 4 KB weight stages in flight
+    } else if ((size_t)R * rowslot + (size_t)total_stages * wst <= avail && total_stages <= 48) {
         resident = 1; w_stages = total_stages;
         slots = (int)std::min<size_t>(2 * R, (avail - (size_t)w_stages * wst) / rowslot);
     } else {
@@ -1184,4 +1213,26 @@ extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpa
     PCNN_TC_DISPATCH(8)
 #undef PCNN_TC_DISPATCH
     return PCNN_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpack, const float* bias, const float* bn_scale,
+                              const float* bn_shift, const void* residual, const void* residual_lo, const float* out_scale,
+                              void* out, void* out_lo, int B, int Cin_total, int Cout, int Cout_total, int Cres_total,
+                              int H, int W, int k, int act, int nsplit, float acc_scale, int out_halo_mode, int num_sms, void* stream) {
+    return conv2d_tc_impl(in, in_lo, wpack, bias, bn_scale, bn_shift, residual, residual_lo, out_scale, out, out_lo, B, Cin_total, Cout,
+                          Cout_total, Cres_total, H, W, k, act, nsplit, acc_scale, out_halo_mode, num_sms, stream, 0, 0);
+}
+
+// Slots of the row-weight array for an H-row output: tiles*RT + 2 (the 128-row window of the last tile stays inside).
+extern "C" int pcnn_conv_tc_rowweight_slots(int Cout, int k, int H) {
+    if (Cout < 1 || Cout > 32 || H < 1) return 0;
+    const int rt = rows_per_tile(choose_cp(Cout, k));
+    return ceil_div(H, rt) * rt + 2;
+}
+
+extern "C" int pcnn_conv2d_tc_rowweights(const void* in_row, const void* wrow, const float* bias, void* out, int B, int Cin, int Cout,
+                                         int Cout_total, int H, int W, int k, int act, float acc_scale, int num_sms, void* stream) {
+    PCNN_CHECK_ARG(in_row && wrow && out, "conv2d_tc_rowweights: null pointer");
+    return conv2d_tc_impl(in_row, nullptr, wrow, bias, nullptr, nullptr, nullptr, nullptr, nullptr, out, nullptr, B, Cin, Cout, Cout_total, 0,
+                          H, W, k, act, 1, acc_scale, PCNN_PAD_CONSTANT, num_sms, stream, 1, pcnn_conv_tc_rowweight_slots(Cout, k, H));
 }

@@ -6,6 +6,8 @@ model([bc, dx, x_output_resolution]) with bc [B,1,n], dx [B,1] -> [B,1,x_res,n].
 import copy
 import warnings
 
+import os
+
 import torch
 
 from .. import ops
@@ -141,11 +143,29 @@ class Dirichlet_BC_NN_Legacy_2(WeightedModel):
         if self.precision in ("tc", "tc2", "tc3"):
             if not self._tc_supported():
                 raise NotImplementedError("precision='tc' covers odd kernels <= 15, <= 32 filters, zero CONSTANT padding")
-            # the [B,29,x_res,n] mode expansion is produced directly in the tensor-core operand layout
-            t = ops.dbcnn_expand_blk8(h, v, x_res, split=self.tc_split)
+            # Single-pass mode: the first 2-D convolution sees a SEPARABLE input (every channel of the mode expansion is
+            # h[b,m,y] * S[m,x]; the position channels are 1 * posx[x] and posy[y] * 1), so its row taps fold into per-row
+            # weights and the [B,29,x_res,n] expansion is never written (ops.pack_rowweights_tc): 14 MMAs per tile, not 121.
+            sep = (self.tc_split == 1 and S - nreg >= 1 and os.environ.get("PCNN_DBCNN_SEPARABLE", "1") != "0")
+            if sep:
+                M = h.shape[1]
+                key = ("rowweights", x_res)
+                if key not in self._tc:
+                    basis = torch.cat([ops.sinh_basis_table(h.device, M, x_res), ops.position_table(h.device, x_res)[None],
+                                       torch.ones((1, x_res), device=h.device)], 0)
+                    self._tc[key] = ops.pack_rowweights_tc(self._w["final/0/conv/kernel"], basis)
+                sig = torch.cat([h * v[:, :, None], torch.ones((B, 1, n), device=h.device),
+                                 ops.position_table(h.device, n).expand(B, 1, n)], 1)
+                t = ops.to_blk8(sig.view(B, M + 2, 1, n).contiguous())
+            else:
+                # the [B,29,x_res,n] mode expansion is produced directly in the tensor-core operand layout
+                t = ops.dbcnn_expand_blk8(h, v, x_res, split=self.tc_split)
             for k in range(S - nreg):
-                wp, bb = self.tc_conv("final/%d/conv" % k)
-                t = ops.conv2d_tc(t, wp, bb, self.final_act, PAD_CONSTANT)
+                if sep and k == 0:
+                    t = ops.conv2d_tc_rowweights(t, self._tc[("rowweights", x_res)], self._w.get("final/0/conv/bias"), self.final_act)
+                else:
+                    wp, bb = self.tc_conv("final/%d/conv" % k)
+                    t = ops.conv2d_tc(t, wp, bb, self.final_act, PAD_CONSTANT)
                 name = "final/%d/resnet" % k
                 (w0, b0), (w1, b1), (w2, b2) = (self.tc_conv(name + "/conv%d" % i) for i in range(3))
                 u = ops.conv2d_tc(t, w0, b0, self.final_act, PAD_CONSTANT)

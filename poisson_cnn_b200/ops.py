@@ -887,3 +887,51 @@ def upsample_merge_tc_blk8(deconv_branches, resize_branches, alpha, out, c_offse
     if out.halo[0] != PAD_CONSTANT:
         out.halo = (out.halo[0], -1)
     return out
+
+
+def pack_rowweights_tc(kernel, row_basis):
+    """Row weights of a convolution whose input is separable, in[b,m,x,y] = h[b,m,y] * row_basis[m,x] (zero padding):
+    A_x[b,m,co] = sum_a kernel[a,b,m,co] * row_basis[m, x+a-k/2], packed for pcnn_conv2d_tc_rowweights.  Done once per
+    (layer, grid height); a weight transformation like pack_conv_weights_tc (torch einsum, then the slot re-ordering)."""
+    _chk(kernel, "kernel"); _chk(row_basis, "row_basis")
+    k, k2, Cin, Cout = kernel.shape
+    if k != k2 or k % 2 == 0 or row_basis.shape[0] != Cin:
+        raise ValueError("pack_rowweights_tc: needs an odd square kernel and a [Cin, H] row basis")
+    H = row_basis.shape[1]
+    cp = lib.pcnn_conv_tc_channel_slots(int(Cout), int(k))
+    T = lib.pcnn_conv_tc_rowweight_slots(int(Cout), int(k), int(H))
+    if cp == 0 or T == 0:
+        raise ValueError("pack_rowweights_tc: unsupported layer (Cout <= 32, odd k <= 15)")
+    rt = 5 if cp == 24 else 128 // cp
+    pad = k // 2
+    sp = torch.nn.functional.pad(row_basis, (pad, pad))                       # [Cin, H + 2 pad], zero-extended
+    U = sp.unfold(1, k, 1)                                                    # [Cin, H, k]: U[m,x,a] = S[m, x+a-pad]
+    A = torch.einsum("mxa,abmc->xbmc", U.double(), kernel.double()).float()   # [H, k, Cin, Cout]
+    amax = float(A.abs().max())
+    scale = 2.0 ** max(-24, min(24, math.floor(math.log2(512.0 / amax)))) if amax > 0 and math.isfinite(amax) else 1.0
+    c16 = -(-Cin // 16)
+    Ap = torch.zeros((H + 1, k, c16 * 16, cp), device=kernel.device, dtype=torch.float32)     # row H = zeros (slots beyond H)
+    Ap[:H, :, :Cin, :Cout] = A * scale
+    t = torch.arange(T, device=kernel.device)
+    x_of_t = (t // rt) * rt + (rt - 1 - t % rt)
+    x_of_t = torch.where(x_of_t < H, x_of_t, torch.full_like(x_of_t, H))
+    P = Ap[x_of_t]                                                            # [T, k, c16*16, cp]
+    P = P.reshape(T, k, c16, 2, 8, cp).permute(2, 1, 3, 0, 5, 4).contiguous() # [c16, k, 2, T, cp, 8]
+    return {"packed": P.half().contiguous(), "k": int(k), "cin": int(Cin), "cout": int(Cout), "H": int(H), "acc_scale": 1.0 / scale}
+
+
+def conv2d_tc_rowweights(x_row, wp, bias=None, act=ACT_LINEAR):
+    """out[b,co,x,y] = act(sum A_x[b_tap,m,co] * x_row[b,m,y+b_tap-k/2] + bias): x_row is a Blk8 tensor with H = 1 (the 1-D
+    signals), wp comes from pack_rowweights_tc.  Returns a Blk8 [B, Cout, wp['H'], W] (single fp16 pass)."""
+    if not isinstance(x_row, Blk8) or x_row.H != 1 or x_row.mode != 1:
+        raise ValueError("conv2d_tc_rowweights: x_row must be a single-pass Blk8 tensor with H = 1")
+    if -(-wp["cin"] // 16) != -(-x_row.C // 16):
+        raise ValueError("conv2d_tc_rowweights: weights expect %d input channels, tensor holds %d" % (wp["cin"], x_row.C))
+    blk8_halo_fill(x_row, wp["k"] // 2, PAD_CONSTANT)
+    out = Blk8(x_row.B, wp["cout"], wp["H"], x_row.W, x_row.device, split=1)
+    check(lib.pcnn_conv2d_tc_rowweights(_p(x_row.buf), _p(wp["packed"]), _p(bias), _p(out.buf), x_row.B, wp["cin"], wp["cout"],
+                                        out.C, wp["H"], x_row.W, wp["k"], int(act), wp["acc_scale"], _num_sms(x_row.device),
+                                        _stream()), "conv2d_tc_rowweights")
+    if out.halo[0] != PAD_CONSTANT:
+        out.halo = (out.halo[0], -1)
+    return out

@@ -169,6 +169,27 @@ def test_upsample_merge_blk8(ops, H, W, C, mode):
     assert float(ops.from_blk8(out, C=c_off, c_offset=0).abs().max()) == 0.0     # neighbouring channels untouched
 
 
+@pytest.mark.parametrize("B,Cin,Cout,H,W,k,act", [(3, 29, 23, 37, 300, 7, 2), (2, 29, 23, 256, 256, 7, 1), (2, 16, 12, 19, 40, 5, 0),
+                                                  (1, 32, 32, 8, 64, 3, 1), (2, 5, 4, 33, 20, 3, 2)])
+def test_conv2d_tc_rowweights_separable_input(ops, B, Cin, Cout, H, W, k, act):
+    """A convolution whose input is h[b,m,y] * S[m,x] with the row taps folded into per-row weights
+    (pcnn_conv2d_tc_rowweights): equals the full convolution of the expanded tensor (zero padding)."""
+    g = torch.Generator().manual_seed(B * 100 + Cin + H)
+    sig = torch.randn(B, Cin, W, generator=g)
+    basis = torch.randn(Cin, H, generator=g)
+    x = sig[:, :, None, :] * basis[None, :, :, None]
+    kern = torch.randn(k, k, Cin, Cout, generator=g) / (k * Cin ** 0.5)
+    bias = torch.randn(Cout, generator=g) * 0.1
+    wp = ops.pack_rowweights_tc(dev(kern), dev(basis))
+    xr = ops.to_blk8(dev(sig.view(B, Cin, 1, W).contiguous()))
+    got = ops.from_blk8(ops.conv2d_tc_rowweights(xr, wp, dev(bias), act))
+    assert got.shape == (B, Cout, H, W)
+    ref = O.conv_nd(x.double(), kern.double(), bias.double(), ACTS[act], "CONSTANT", 0.0)
+    assert rel_l2(got, ref) < 1.5e-3          # fp16 operands (row weights and signals), fp16 output
+    full = ops.from_blk8(ops.conv2d_tc(ops.to_blk8(dev(x)), ops.pack_conv_weights_tc(dev(kern)), dev(bias), act))
+    assert rel_l2(got, full) < 2e-3           # the k x k convolution of the expanded tensor on the same kernel family
+
+
 @pytest.mark.parametrize("H,W,mode,B", [(256, 256, 3, 2), (200, 300, 1, 3), (37, 50, 3, 2), (64, 80, 2, 9), (112, 120, 3, 17)])
 def test_upsample_merge_tc_blk8(ops, H, W, mode, B):
     """Tensor-core version: the transpose convolutions run as mma.sync products from BLK8 fp16 branch outputs.  Same

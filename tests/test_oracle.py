@@ -212,3 +212,21 @@ def test_legacy_bicubic_host_tables_match_oracle():
         oi, ow = O.legacy_bicubic_axis_weights(n_in, n_out)
         np.testing.assert_array_equal(idx, oi)
         np.testing.assert_array_equal(w.astype(np.float64), ow)
+
+
+def test_separable_input_convolution_identity():
+    """The algebra behind pcnn_conv2d_tc_rowweights (the DBCNN's first 2-D convolution, Dirichlet_BC_NN_Legacy.py:137-160):
+    for in[m,x,y] = h[m,y] * S[m,x] and zero padding, conv(in)[co,x,y] = sum_{b,m} A_x[b,m,co] * h[m, y+b-p] with
+    A_x[b,m,co] = sum_a W[a,b,m,co] * S[m, x+a-p]."""
+    g = torch.Generator().manual_seed(3)
+    Cin, Cout, H, W, k = 6, 5, 9, 11, 5
+    p = k // 2
+    h = torch.randn(1, Cin, W, generator=g, dtype=torch.float64)
+    S = torch.randn(Cin, H, generator=g, dtype=torch.float64)
+    kern = torch.randn(k, k, Cin, Cout, generator=g, dtype=torch.float64)
+    full = O.conv_nd(h[:, :, None, :] * S[None, :, :, None], kern, None, "linear", "CONSTANT", 0.0)
+    Sp = torch.nn.functional.pad(S, (p, p))
+    A = torch.einsum("mxa,abmc->xbmc", Sp.unfold(1, k, 1), kern)                       # [H, k, Cin, Cout]
+    hp = torch.nn.functional.pad(h[0], (p, p)).unfold(1, k, 1)                          # [Cin, W, k]: h[m, y+b-p]
+    folded = torch.einsum("xbmc,myb->cxy", A, hp)
+    np.testing.assert_allclose(folded.numpy(), full[0].numpy(), atol=1e-12)
