@@ -301,6 +301,9 @@ int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpack, const f
  * [ceil(Cin/16)][k][2][T][CP][8] with T = pcnn_conv_tc_rowweight_slots(Cout,k,H), CP = pcnn_conv_tc_channel_slots(Cout,k),
  * RT = 128/CP (5 for 24): slot t holds output row (t/RT)*RT + RT-1 - t%RT (zeros beyond H), K half = channels
  * 16c + 8*half + [0,8).  Single FP16 pass only; bias + activation in the epilogue; out as for pcnn_conv2d_tc. */
+/* the signals of the DBCNN's separable layer as a BLK8 tensor with H = 1 (zero-initialised, pcnn_blk8_bytes(B, M+2, 1, n)):
+ * channel m < M = h[b,m,y] * modew[b,m], channel M = 1, channel M+1 = posy[y] */
+int pcnn_dbcnn_signal_blk8(const float* h, const float* modew, const float* posy, void* out, int B, int M, int n, void* stream);
 int pcnn_conv_tc_rowweight_slots(int Cout, int k, int H);
 int pcnn_conv2d_tc_rowweights(const void* in_row, const void* wrow, const float* bias, void* out, int B, int Cin,
                               int Cout, int Cout_total, int H, int W, int k, int act, float acc_scale, int num_sms,

@@ -51,6 +51,7 @@ SIGNATURES = {
     "pcnn_conv_tc_pack_weights": (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, c_float, P]),
     "pcnn_conv2d_tc": (c_int, [P] * 11 + [c_int] * 10 + [c_float, c_int, c_int, P]),
     "pcnn_conv_tc_rowweight_slots": (c_int, [c_int, c_int, c_int]),
+    "pcnn_dbcnn_signal_blk8": (c_int, [P, P, P, P, c_int, c_int, c_int, P]),
     "pcnn_conv2d_tc_rowweights": (c_int, [P, P, P, P] + [c_int] * 8 + [c_float, c_int, P]),
     "pcnn_upsample_merge_blk8": (c_int, [c_int, P, P, P, P, P, P, P, c_int, P, P, P, P, P, P, P, P, c_float, P, P,
                                          c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),

@@ -973,6 +973,32 @@ __global__ void __launch_bounds__(128) dbcnn_expand_blk8_kernel(const float* __r
     }
 }
 
+// The DBCNN's separable first layer (pcnn_conv2d_tc_rowweights) reads the boundary features as ONE row: BLK8 tensor
+// [B][np][1+14][n+14][8], row HALO: channel m < M = h[b,m,y] * w[b,m]; channel M = 1 (pairs with posx[x] in the row weights),
+// channel M+1 = posy[y].  One thread per (b, y) writes the np 16-byte units.
+__global__ void __launch_bounds__(128) dbcnn_signal_blk8_kernel(const float* __restrict__ h, const float* __restrict__ mw,
+                                                                const float* __restrict__ posy, __half* __restrict__ out,
+                                                                int M, int n, int np) {
+    const int y = blockIdx.x * 128 + threadIdx.x, b = blockIdx.y;
+    if (y >= n) return;
+    const int P = n + 2 * HALO;
+    const size_t plane_px = (size_t)(1 + 2 * HALO) * P;
+    const size_t pix = (size_t)HALO * P + (y + HALO);
+    for (int pl = 0; pl < np; ++pl) {
+        __align__(16) __half v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int m = pl * 8 + e;
+            float f = 0.f;
+            if (m < M) f = __ldg(h + ((long long)b * M + m) * n + y) * __ldg(mw + (long long)b * M + m);
+            else if (m == M) f = 1.f;
+            else if (m == M + 1) f = __ldg(posy + y);
+            v[e] = __float2half_rn(f);
+        }
+        *reinterpret_cast<uint4*>(out + (((size_t)b * (2 * ((np + 1) / 2)) + pl) * plane_px + pix) * 8) = *reinterpret_cast<const uint4*>(v);
+    }
+}
+
 static inline int grid_for(long long total, int block = 256, int cap = 148 * 16) {
     long long g = (total + block - 1) / block;
     if (g > cap) g = cap;
@@ -1213,6 +1239,13 @@ static int conv2d_tc_impl(const void* in, const void* in_lo, const void* wpack, 
     PCNN_TC_DISPATCH(8)
 #undef PCNN_TC_DISPATCH
     return PCNN_ERR_INVALID_ARGUMENT;
+}
+
+extern "C" int pcnn_dbcnn_signal_blk8(const float* h, const float* modew, const float* posy, void* out, int B, int M, int n, void* stream) {
+    PCNN_CHECK_ARG(h && modew && posy && out && B > 0 && B <= 65535 && M > 0 && M + 2 <= 32 && n > 0, "dbcnn_signal_blk8: bad argument");
+    dbcnn_signal_blk8_kernel<<<dim3(ceil_div(n, 128), B), 128, 0, (cudaStream_t)stream>>>(h, modew, posy, (__half*)out, M, n, (M + 2 + 7) / 8);
+    PCNN_CHECK_LAUNCH();
+    return PCNN_OK;
 }
 
 extern "C" int pcnn_conv2d_tc(const void* in, const void* in_lo, const void* wpack, const float* bias, const float* bn_scale,

@@ -154,9 +154,7 @@ class Dirichlet_BC_NN_Legacy_2(WeightedModel):
                     basis = torch.cat([ops.sinh_basis_table(h.device, M, x_res), ops.position_table(h.device, x_res)[None],
                                        torch.ones((1, x_res), device=h.device)], 0)
                     self._tc[key] = ops.pack_rowweights_tc(self._w["final/0/conv/kernel"], basis)
-                sig = torch.cat([h * v[:, :, None], torch.ones((B, 1, n), device=h.device),
-                                 ops.position_table(h.device, n).expand(B, 1, n)], 1)
-                t = ops.to_blk8(sig.view(B, M + 2, 1, n).contiguous())
+                t = ops.dbcnn_signal_blk8(h, v)
             else:
                 # the [B,29,x_res,n] mode expansion is produced directly in the tensor-core operand layout
                 t = ops.dbcnn_expand_blk8(h, v, x_res, split=self.tc_split)

@@ -935,3 +935,14 @@ def conv2d_tc_rowweights(x_row, wp, bias=None, act=ACT_LINEAR):
     if out.halo[0] != PAD_CONSTANT:
         out.halo = (out.halo[0], -1)
     return out
+
+
+def dbcnn_signal_blk8(h, modew):
+    """The DBCNN boundary features as the one-row operand of the separable first 2-D convolution: Blk8 [B, M+2, 1, n] with
+    channel m < M = h[b,m,y] * modew[b,m], channel M = 1, channel M+1 = posy[y]."""
+    _chk(h, "h"); _chk(modew, "modew")
+    h, modew = h.contiguous(), modew.contiguous()
+    B, M, n = h.shape
+    out = Blk8(B, M + 2, 1, n, h.device, split=1)
+    check(lib.pcnn_dbcnn_signal_blk8(_p(h), _p(modew), _p(position_table(h.device, n)), _p(out.buf), B, M, n, _stream()), "dbcnn_signal_blk8")
+    return out

@@ -229,3 +229,15 @@ def test_tf_checkpoint_roundtrip_through_load_checkpoint_weights(tmp_path):
     assert all(k.endswith(T.SUFFIX) for k in raw)
     with pytest.raises(ValueError):                                     # a variable the model needs but the file lacks
         T.load_checkpoint_weights(prefix, {**key_map, "hpnn/not_there": "hpnn/not_there"})
+
+
+def test_upsample_merge_tc_shared_memory_plan():
+    """The tensor-core upsample-merge kernel stages every branch operand in shared memory; the host asks the library whether
+    a configuration fits (grids beyond ~400 pixels a side fall back to the FP32-FMA kernel)."""
+    from poisson_cnn_b200 import ops
+    strides = [2, 3, 4, 8, 16]
+    assert ops.upsample_merge_tc_fits(strides, [(8, 8), (4, 4), (2, 2)])            # 256 x 256
+    assert ops.upsample_merge_tc_fits(strides, [(16, 8), (8, 4), (4, 2)])           # 512 x 256
+    assert not ops.upsample_merge_tc_fits(strides, [(16, 16), (8, 8), (4, 4)])      # 512 x 512
+    assert not ops.upsample_merge_tc_fits([], [(2, 2)])                              # needs a transpose-conv branch
+    assert not ops.upsample_merge_tc_fits([64], [])                                  # stride beyond 32
