@@ -167,12 +167,11 @@ __global__ void __launch_bounds__(NTHR, 1) upsample_merge_tc_kernel(const Params
                     mbar_wait(in_empty + buf, ((unit >> 1) & 1) ^ 1);
                     mbar_expect_tx(in_full + buf, (uint32_t)(p.a_bytes + p.r_bytes));
                     for (int d = 0; d < p.n_dc; ++d) {
-                        const int s = p.dc_s[d], Hp = p.dc_ih[d] + 2 * HALO, P = p.dc_iw[d] + 2 * HALO;
+                        const int Hp = p.dc_ih[d] + 2 * HALO, P = p.dc_iw[d] + 2 * HALO;
                         const int i = fast_div(Y + p.dc_pbh[d], p.dc_magic[d]);
                         const int jb = fast_div(X0 + p.dc_pbw[d], p.dc_magic[d]);
                         const uint32_t bytes = (uint32_t)p.dc_segp[d] * 16u;
                         const __half* src = p.dc_in[d] + (((size_t)b * 4 * Hp + (i + HALO)) * P + (jb + HALO)) * 8;
-                        (void)s;
                         for (int pl = 0; pl < 4; ++pl)
                             bulk_copy_g2s(s_a[buf] + p.dc_aoff[d] + pl * bytes, src + (size_t)pl * Hp * P * 8, bytes, in_full + buf);
                     }
