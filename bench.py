@@ -242,7 +242,8 @@ def run_ours(args):
         # DRAM bytes per launch of this kernel from the ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum
         # at 32 samples per launch), scaled to the samples per launch here.  tc2: three of the four 32->32 k15 launches of a
         # forward have no residual input (profiles/r01_conv_tc_k15_tc2_b32_full_raw.csv: 303.6 + 228.8 MB), one has
-        # (profiles/r01b_conv_tc_k15_tc2_res_b32_full_raw.csv: 512.1 + 237.5 MB)
+        # (profiles/r01b_conv_tc_k15_tc2_res_b32_full_raw.csv: 512.1 + 237.5 MB; unchanged in the final build,
+        # profiles/r01c_k15_tc2_full_raw.csv: 512.5 + 237.3 MB)
         per_sample = {"tc": (151.436032e6 + 94.614272e6) / 32,
                       "tc2": (3 * (303.551488e6 + 228.785920e6) + (512.086272e6 + 237.487872e6)) / 4 / 32}.get(hp_mode)
         samples_per_launch = min(B, max(1, int((getattr(model, "max_microbatch", B) or B) * 65536 // (nx * ny))))
