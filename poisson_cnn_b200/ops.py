@@ -889,20 +889,12 @@ def upsample_merge_tc_blk8(deconv_branches, resize_branches, alpha, out, c_offse
     return out
 
 
-def pack_rowweights_tc(kernel, row_basis):
-    """Row weights of a convolution whose input is separable, in[b,m,x,y] = h[b,m,y] * row_basis[m,x] (zero padding):
-    A_x[b,m,co] = sum_a kernel[a,b,m,co] * row_basis[m, x+a-k/2], packed for pcnn_conv2d_tc_rowweights.  Done once per
-    (layer, grid height); a weight transformation like pack_conv_weights_tc (torch einsum, then the slot re-ordering)."""
-    _chk(kernel, "kernel"); _chk(row_basis, "row_basis")
-    k, k2, Cin, Cout = kernel.shape
-    if k != k2 or k % 2 == 0 or row_basis.shape[0] != Cin:
-        raise ValueError("pack_rowweights_tc: needs an odd square kernel and a [Cin, H] row basis")
+def rowweights_image(kernel, row_basis, cp, rt, T):
+    """The fp16 operand image of pcnn_conv2d_tc_rowweights (layout in include/pcnn.h) and the power-of-two pre-scale:
+    [ceil(Cin/16)][k][2][T][cp][8], slot t = output row (t//rt)*rt + rt-1 - t%rt (zeros beyond H), K half = channels
+    16c + 8*half + [0,8).  Pure tensor algebra (any device): A_x[b,m,co] = sum_a kernel[a,b,m,co] * row_basis[m, x+a-k/2]."""
+    k, _, Cin, Cout = kernel.shape
     H = row_basis.shape[1]
-    cp = lib.pcnn_conv_tc_channel_slots(int(Cout), int(k))
-    T = lib.pcnn_conv_tc_rowweight_slots(int(Cout), int(k), int(H))
-    if cp == 0 or T == 0:
-        raise ValueError("pack_rowweights_tc: unsupported layer (Cout <= 32, odd k <= 15)")
-    rt = 5 if cp == 24 else 128 // cp
     pad = k // 2
     sp = torch.nn.functional.pad(row_basis, (pad, pad))                       # [Cin, H + 2 pad], zero-extended
     U = sp.unfold(1, k, 1)                                                    # [Cin, H, k]: U[m,x,a] = S[m, x+a-pad]
@@ -917,7 +909,25 @@ def pack_rowweights_tc(kernel, row_basis):
     x_of_t = torch.where(x_of_t < H, x_of_t, torch.full_like(x_of_t, H))
     P = Ap[x_of_t]                                                            # [T, k, c16*16, cp]
     P = P.reshape(T, k, c16, 2, 8, cp).permute(2, 1, 3, 0, 5, 4).contiguous() # [c16, k, 2, T, cp, 8]
-    return {"packed": P.half().contiguous(), "k": int(k), "cin": int(Cin), "cout": int(Cout), "H": int(H), "acc_scale": 1.0 / scale}
+    return P.half().contiguous(), scale
+
+
+def pack_rowweights_tc(kernel, row_basis):
+    """Row weights of a convolution whose input is separable, in[b,m,x,y] = h[b,m,y] * row_basis[m,x] (zero padding):
+    A_x[b,m,co] = sum_a kernel[a,b,m,co] * row_basis[m, x+a-k/2], packed for pcnn_conv2d_tc_rowweights.  Done once per
+    (layer, grid height); a weight transformation like pack_conv_weights_tc (torch einsum, then the slot re-ordering)."""
+    _chk(kernel, "kernel"); _chk(row_basis, "row_basis")
+    k, k2, Cin, Cout = kernel.shape
+    if k != k2 or k % 2 == 0 or row_basis.shape[0] != Cin:
+        raise ValueError("pack_rowweights_tc: needs an odd square kernel and a [Cin, H] row basis")
+    H = row_basis.shape[1]
+    cp = lib.pcnn_conv_tc_channel_slots(int(Cout), int(k))
+    T = lib.pcnn_conv_tc_rowweight_slots(int(Cout), int(k), int(H))
+    if cp == 0 or T == 0:
+        raise ValueError("pack_rowweights_tc: unsupported layer (Cout <= 32, odd k <= 15)")
+    rt = 5 if cp == 24 else 128 // cp
+    packed, scale = rowweights_image(kernel, row_basis, cp, rt, T)
+    return {"packed": packed, "k": int(k), "cin": int(Cin), "cout": int(Cout), "H": int(H), "acc_scale": 1.0 / scale}
 
 
 def conv2d_tc_rowweights(x_row, wp, bias=None, act=ACT_LINEAR):

@@ -241,3 +241,32 @@ def test_upsample_merge_tc_shared_memory_plan():
     assert not ops.upsample_merge_tc_fits(strides, [(16, 16), (8, 8), (4, 4)])      # 512 x 512
     assert not ops.upsample_merge_tc_fits([], [(2, 2)])                              # needs a transpose-conv branch
     assert not ops.upsample_merge_tc_fits([64], [])                                  # stride beyond 32
+
+
+def test_rowweights_image_layout():
+    """include/pcnn.h, pcnn_conv2d_tc_rowweights: slot order, K halves, channel padding and pre-scale of the per-row weights
+    (an explicit loop over the documented layout against the vectorised packing)."""
+    from poisson_cnn_b200 import ops
+    from poisson_cnn_b200._lib import lib
+    g = torch.Generator().manual_seed(4)
+    k, Cin, Cout, H = 3, 19, 7, 11
+    kern = torch.randn(k, k, Cin, Cout, generator=g)
+    basis = torch.randn(Cin, H, generator=g)
+    cp = lib.pcnn_conv_tc_channel_slots(Cout, k)
+    rt = 5 if cp == 24 else 128 // cp
+    T = lib.pcnn_conv_tc_rowweight_slots(Cout, k, H)
+    assert cp == 8 and rt == 16 and T == -(-H // rt) * rt + 2
+    img, scale = ops.rowweights_image(kern, basis, cp, rt, T)
+    assert img.shape == (2, k, 2, T, cp, 8) and img.dtype == torch.float16
+    assert scale == 2.0 ** np.floor(np.log2(scale)) and scale > 0
+    p = k // 2
+    for t in (0, 3, rt - 1, rt, T - 1):
+        x = (t // rt) * rt + (rt - 1 - t % rt)
+        for b in range(k):
+            for ci in (0, 7, 8, 18, 19, 31):
+                for co in (0, 6, 7):
+                    want = 0.0
+                    if x < H and ci < Cin and co < Cout:
+                        want = scale * sum(float(kern[a, b, ci, co]) * float(basis[ci, x + a - p]) for a in range(k) if 0 <= x + a - p < H)
+                    got = float(img[ci // 16, b, (ci % 16) // 8, t, co, ci % 8])
+                    assert abs(got - want) <= 1e-3 * max(1.0, abs(want)), (t, x, b, ci, co, got, want)
