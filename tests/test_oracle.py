@@ -230,3 +230,19 @@ def test_separable_input_convolution_identity():
     hp = torch.nn.functional.pad(h[0], (p, p)).unfold(1, k, 1)                          # [Cin, W, k]: h[m, y+b-p]
     folded = torch.einsum("xbmc,myb->cxy", A, hp)
     np.testing.assert_allclose(folded.numpy(), full[0].numpy(), atol=1e-12)
+
+
+def test_tf2_resize_cross_checked_against_pillow():
+    """layers/Upsample.py:56-59 -> tf.image.resize(method, antialias=False) with half-pixel centres.  TF cannot run here
+    (parity unpinned); for UP-sampling, Pillow's resize implements the same filters independently: bilinear = triangle
+    filter, bicubic = Keys a = -0.5, taps outside the image dropped and the rest renormalised.  The oracle must agree with
+    it up to TF's 1024-step coefficient table (bicubic) / float32 rounding (bilinear)."""
+    Image = pytest.importorskip("PIL.Image")
+    g = torch.Generator().manual_seed(8)
+    for (ih, iw), (oh, ow) in (((2, 2), (64, 80)), ((4, 5), (64, 80)), ((8, 8), (256, 256)), ((3, 7), (29, 100))):
+        x = torch.randn(ih, iw, generator=g)
+        img = Image.fromarray(x.numpy().astype(np.float32), mode="F")
+        for method, pil, tol in (("bilinear", Image.BILINEAR, 2e-6), ("bicubic", Image.BICUBIC, 2e-3)):
+            ref = np.asarray(img.resize((ow, oh), resample=pil), dtype=np.float64)
+            got = O.resize(x.double()[None, None], (oh, ow), method)[0, 0].numpy()
+            assert np.abs(got - ref).max() < tol * max(1.0, np.abs(ref).max()), (method, ih, iw, np.abs(got - ref).max())
