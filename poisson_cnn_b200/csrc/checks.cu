@@ -6,40 +6,96 @@
 namespace pcnn {
 
 // ------------------------------------------------------------------ Laplacian residual
-template <int HALO>
+// One warp owns a strip of RS interior rows x 128 columns: every lane marches down the strip with 4 consecutive columns
+// (one 16-byte load per row of u and of f) and a rolling register window of 2*HALO+1 rows; the left/right neighbours come
+// from the adjacent lanes by shuffle (the two edge lanes load them).  No index division per element; DRAM traffic is
+// (RS + 2*HALO)/RS x 4 B for u plus 4 B for f per grid point (RS = 32: 8.25 B / 8.5 B against the 8 B algorithmic figure).
+// Squared residuals are accumulated in double per lane, reduced by warp shuffles, one double atomic per CTA.
+template <bool VEC>
+__device__ __forceinline__ float4 load_row4(const float* __restrict__ row, int j0, int W) {
+    if (VEC) {
+        if (j0 + 3 < W) return __ldg(reinterpret_cast<const float4*>(row + j0));
+    }
+    float4 v;
+    v.x = (j0 + 0 < W) ? __ldg(row + j0 + 0) : 0.f;
+    v.y = (j0 + 1 < W) ? __ldg(row + j0 + 1) : 0.f;
+    v.z = (j0 + 2 < W) ? __ldg(row + j0 + 2) : 0.f;
+    v.w = (j0 + 3 < W) ? __ldg(row + j0 + 3) : 0.f;
+    return v;
+}
+
+constexpr int kResidualStripRows = 32;
+
+template <int HALO, bool VEC>
 __global__ void __launch_bounds__(256) laplacian_residual_kernel(
     const float* __restrict__ rhs, const float* __restrict__ sol, const float* __restrict__ gs,
-    const float* __restrict__ rhs_maxabs, double* __restrict__ sq_sum, int H, int W) {
+    const float* __restrict__ rhs_maxabs, double* __restrict__ sq_sum, int H, int W, int nchunk, int nitems) {
     const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float qx = 1.0f / (gs[b * 2 + 0] * gs[b * 2 + 0]);
     const float qy = 1.0f / (gs[b * 2 + 1] * gs[b * 2 + 1]);
     // central second-derivative coefficients (dataset/utils/get_fd_coefficients.py)
     float c[5];
     if constexpr (HALO == 1) { c[0] = 1.f; c[1] = -2.f; c[2] = 1.f; c[3] = 0.f; c[4] = 0.f; }
     else { c[0] = -1.f / 12.f; c[1] = 4.f / 3.f; c[2] = -2.5f; c[3] = 4.f / 3.f; c[4] = -1.f / 12.f; }
-    const int ih = H - 2 * HALO, iw = W - 2 * HALO;
-    const long long n = (long long)ih * iw;
+    const float cc = c[HALO] * qx + c[HALO] * qy;             // kernel centre = sum_d stencil_d*q_d
     const float* u = sol + (long long)b * H * W;
     const float* f = rhs + (long long)b * H * W;
     double acc = 0.0;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int i = idx / iw + HALO, j = idx % iw + HALO;
-        const float* p = u + (long long)i * W + j;
-        float lap = (c[HALO] * qx + c[HALO] * qy) * __ldg(p);   // kernel centre = sum_d stencil_d*q_d
+    const int item = blockIdx.x * 8 + warp;
+    if (item < nitems) {
+        const int chunk = item % nchunk, strip = item / nchunk;
+        const int j0 = chunk * 128 + lane * 4;
+        const int i0 = HALO + strip * kResidualStripRows;
+        const int i1 = min(i0 + kResidualStripRows, H - HALO);
+        float4 win[2 * HALO + 1];
 #pragma unroll
-        for (int t = 1; t <= HALO; ++t) {
-            lap = fmaf(c[HALO - t] * qx, __ldg(p - (long long)t * W), lap);
-            lap = fmaf(c[HALO + t] * qx, __ldg(p + (long long)t * W), lap);
-            lap = fmaf(c[HALO - t] * qy, __ldg(p - t), lap);
-            lap = fmaf(c[HALO + t] * qy, __ldg(p + t), lap);
+        for (int t = 0; t < 2 * HALO; ++t) win[t + 1] = load_row4<VEC>(u + (long long)(i0 - HALO + t) * W, j0, W);
+        for (int i = i0; i < i1; ++i) {
+#pragma unroll
+            for (int t = 0; t < 2 * HALO; ++t) win[t] = win[t + 1];
+            win[2 * HALO] = load_row4<VEC>(u + (long long)(i + HALO) * W, j0, W);
+            const float4 fv = load_row4<VEC>(f + (long long)i * W, j0, W);
+            const float4 mid = win[HALO];
+            // columns j0-HALO .. j0+3+HALO of the centre row
+            float row[4 + 2 * HALO];
+            row[HALO + 0] = mid.x; row[HALO + 1] = mid.y; row[HALO + 2] = mid.z; row[HALO + 3] = mid.w;
+            const float* ur = u + (long long)i * W;
+            {
+                float l1 = __shfl_up_sync(0xffffffffu, mid.w, 1), r1 = __shfl_down_sync(0xffffffffu, mid.x, 1);
+                if (lane == 0) l1 = (j0 >= 1) ? __ldg(ur + j0 - 1) : 0.f;
+                if (lane == 31) r1 = (j0 + 4 < W) ? __ldg(ur + j0 + 4) : 0.f;
+                row[HALO - 1] = l1; row[HALO + 4] = r1;
+            }
+            if constexpr (HALO == 2) {
+                float l2 = __shfl_up_sync(0xffffffffu, mid.z, 1), r2 = __shfl_down_sync(0xffffffffu, mid.y, 1);
+                if (lane == 0) l2 = (j0 >= 2) ? __ldg(ur + j0 - 2) : 0.f;
+                if (lane == 31) r2 = (j0 + 5 < W) ? __ldg(ur + j0 + 5) : 0.f;
+                row[0] = l2; row[HALO + 5] = r2;
+            }
+            const float fe[4] = {fv.x, fv.y, fv.z, fv.w};
+            float col[2 * HALO + 1][4];
+#pragma unroll
+            for (int t = 0; t <= 2 * HALO; ++t) { col[t][0] = win[t].x; col[t][1] = win[t].y; col[t][2] = win[t].z; col[t][3] = win[t].w; }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = j0 + e;
+                float lap = cc * row[HALO + e];
+#pragma unroll
+                for (int t = 1; t <= HALO; ++t) {
+                    lap = fmaf(c[HALO - t] * qx, col[HALO - t][e], lap);
+                    lap = fmaf(c[HALO + t] * qx, col[HALO + t][e], lap);
+                    lap = fmaf(c[HALO - t] * qy, row[HALO + e - t], lap);
+                    lap = fmaf(c[HALO + t] * qy, row[HALO + e + t], lap);
+                }
+                const float d = fe[e] - lap;
+                if (j >= HALO && j < W - HALO) acc += (double)d * (double)d;
+            }
         }
-        const float d = __ldg(f + (long long)i * W + j) - lap;
-        acc += (double)d * (double)d;
     }
     __shared__ double red[8];
     acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    if (lane == 0) red[warp] = acc;
     __syncthreads();
     if (threadIdx.x < 32) {
         double v = (threadIdx.x < 8) ? red[threadIdx.x] : 0.0;
@@ -193,14 +249,18 @@ extern "C" int pcnn_laplacian_residual_f32(const float* rhs, const float* sol, c
     PCNN_CHECK_ARG(stencil == 3 || stencil == 5, "laplacian_residual_f32: stencil size %d not supported (3 or 5)", stencil);
     PCNN_CHECK_ARG(H > stencil - 1 && W > stencil - 1, "laplacian_residual_f32: grid smaller than the stencil");
     PCNN_CHECK_CUDA(cudaMemsetAsync(sq_sum, 0, sizeof(double) * B, (cudaStream_t)stream));
-    const long long n = (long long)(H - stencil + 1) * (W - stencil + 1);
-    // enough CTAs per sample to fill 148 SMs x 8 resident CTAs even at small B
-    int gx = (int)std::min<long long>((n + 1023) / 1024, std::max(1, (148 * 8 + B - 1) / B));
-    if (gx < 1) gx = 1;
-    if (stencil == 3)
-        laplacian_residual_kernel<1><<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(rhs, sol, grid_spacings, rhs_maxabs, sq_sum, H, W);
-    else
-        laplacian_residual_kernel<2><<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(rhs, sol, grid_spacings, rhs_maxabs, sq_sum, H, W);
+    const int halo = stencil / 2;
+    const int nchunk = ceil_div(W, 128), nstrip = ceil_div(H - 2 * halo, kResidualStripRows), nitems = nchunk * nstrip;
+    const dim3 grid(ceil_div(nitems, 8), B);
+    const bool vec = (W % 4 == 0) && (((uintptr_t)rhs | (uintptr_t)sol) % 16 == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stencil == 3) {
+        if (vec) laplacian_residual_kernel<1, true><<<grid, 256, 0, st>>>(rhs, sol, grid_spacings, rhs_maxabs, sq_sum, H, W, nchunk, nitems);
+        else laplacian_residual_kernel<1, false><<<grid, 256, 0, st>>>(rhs, sol, grid_spacings, rhs_maxabs, sq_sum, H, W, nchunk, nitems);
+    } else {
+        if (vec) laplacian_residual_kernel<2, true><<<grid, 256, 0, st>>>(rhs, sol, grid_spacings, rhs_maxabs, sq_sum, H, W, nchunk, nitems);
+        else laplacian_residual_kernel<2, false><<<grid, 256, 0, st>>>(rhs, sol, grid_spacings, rhs_maxabs, sq_sum, H, W, nchunk, nitems);
+    }
     PCNN_CHECK_LAUNCH();
     return PCNN_OK;
 }

@@ -8,6 +8,8 @@
 //   threadIdx.y = group of 8 output channels (a warp reads its 8 weights as two broadcast LDS.128).
 // Input channels are streamed through shared memory in chunks; the halo (tf.pad CONSTANT /
 // SYMMETRIC / REFLECT) is resolved while the tile is loaded, so no padded copy ever exists.
+#include <algorithm>
+
 #include "pcnn_common.cuh"
 
 namespace pcnn {
@@ -27,6 +29,12 @@ struct ConvF32Params {
     // of one image: W and the sample stride)
     long long in_cs, in_rs, out_cs, out_rs, res_cs, res_rs;
     int ci_chunk, pitch, tile_rows, cop;   // cop = padded Cout (multiple of 8)
+    // Blocked summation: every flush_ci input channels (~256 product terms) the register accumulators are added to
+    // per-thread totals in shared memory and restart from zero, so a K = kh*kw*Cin = 7200-term dot product is a sum of
+    // ~30 short sums instead of one long sequential FP32 sum (rounding error ~sqrt(256)+sqrt(30) instead of ~sqrt(7200)
+    // ulps: the strict mode's distance to the float64 oracle at 256x256 went from 1.4e-5 to below the 1e-5 budget).
+    // 0 = a single sequential sum (short dot products).
+    int flush_ci;
 };
 
 __global__ void __launch_bounds__(256) conv2d_f32_kernel(const ConvF32Params p) {
@@ -34,6 +42,7 @@ __global__ void __launch_bounds__(256) conv2d_f32_kernel(const ConvF32Params p) 
     const int tile_elems = p.tile_rows * p.pitch;
     float* s_in = smem;                                   // [ci_chunk][tile_rows][pitch]
     float* s_w = smem + (size_t)p.ci_chunk * tile_elems;   // [ci_chunk][kh][kw][cop]
+    float* s_tot = s_w + (size_t)p.ci_chunk * p.kh * p.kw * p.cop;   // [PX*CO][threads] running totals (flush_ci > 0)
 
     const int tid = threadIdx.x, cg = threadIdx.y;
     const int nthreads = blockDim.x * blockDim.y;
@@ -52,6 +61,11 @@ __global__ void __launch_bounds__(256) conv2d_f32_kernel(const ConvF32Params p) 
         for (int j = 0; j < CO; ++j) acc[i][j] = 0.f;
 
     const int wk = p.kh * p.kw * p.cop;   // smem weights per input channel
+    int since_flush = 0;
+    if (p.flush_ci) {
+#pragma unroll
+        for (int o = 0; o < PX * CO; ++o) s_tot[o * nthreads + flat] = 0.f;     // private to this thread: no barrier needed
+    }
 
     for (int c0 = 0; c0 < p.Cin; c0 += p.ci_chunk) {
         const int nci = min(p.ci_chunk, p.Cin - c0);
@@ -112,7 +126,23 @@ __global__ void __launch_bounds__(256) conv2d_f32_kernel(const ConvF32Params p) 
                     }
                 }
             }
+            if (p.flush_ci && ++since_flush == p.flush_ci) {
+                since_flush = 0;
+#pragma unroll
+                for (int i = 0; i < PX; ++i)
+#pragma unroll
+                    for (int j = 0; j < CO; ++j) {
+                        s_tot[(i * CO + j) * nthreads + flat] += acc[i][j];
+                        acc[i][j] = 0.f;
+                    }
+            }
         }
+    }
+    if (p.flush_ci) {
+#pragma unroll
+        for (int i = 0; i < PX; ++i)
+#pragma unroll
+            for (int j = 0; j < CO; ++j) acc[i][j] += s_tot[(i * CO + j) * nthreads + flat];
     }
 
     // ---- epilogue: bias -> activation -> BN affine -> residual -> per-(b,c) scale ----
@@ -188,13 +218,16 @@ __global__ void __launch_bounds__(256) conv2d_small_f32_kernel(const ConvF32Para
     for (int ci = 0; ci < p.Cin; ++ci) {
         const float* sin = s_in + ci * ph * pw;
         const float* sw = s_w + ci * taps * 8 + c;
+        float part[2] = {0.f, 0.f};              // blocked summation: one short sum per input channel
         for (int dy = 0; dy < p.kh; ++dy)
             for (int dx = 0; dx < p.kw; ++dx) {
                 const float w = sw[(dy * p.kw + dx) * 8];
                 const float* s0 = sin + dy * pw + dx;
-                acc[0] = fmaf(s0[poff[0]], w, acc[0]);
-                acc[1] = fmaf(s0[poff[1]], w, acc[1]);
+                part[0] = fmaf(s0[poff[0]], w, part[0]);
+                part[1] = fmaf(s0[poff[1]], w, part[1]);
             }
+        acc[0] += part[0];
+        acc[1] += part[1];
     }
     if (co >= p.Cout) return;
     const float bias = p.bias ? __ldg(p.bias + co) : 0.f;
@@ -267,19 +300,22 @@ extern "C" int pcnn_conv2d_f32(const float* in, const float* kernel, const float
     int cols = TILE_W + kw - 1;
     p.pitch = cols + ((8 - (cols % 32)) % 32 + 32) % 32;   // pitch == 8 (mod 32)
     const size_t per_ci = ((size_t)p.tile_rows * p.pitch + (size_t)kh * kw * p.cop) * sizeof(float);
-    const size_t budget = 96 * 1024;
+    // blocked summation for long dot products (see ConvF32Params::flush_ci): 64 KB of per-thread totals at 256 threads
+    const int taps = kh * kw;
+    p.flush_ci = ((long long)taps * Cin > 512) ? std::max(1, 256 / taps) : 0;
+    const size_t tot_bytes = p.flush_ci ? (size_t)PX * CO * 64 * ngroups * sizeof(float) : 0;
+    const size_t budget = (p.flush_ci ? 48 : 96) * 1024;
     int chunk = (int)(budget / per_ci);
     if (chunk < 1) chunk = 1;
     if (chunk > Cin) chunk = Cin;
     if (chunk > 8) chunk = 8;
     p.ci_chunk = chunk;
-    const size_t smem = per_ci * chunk;
+    const size_t smem = per_ci * chunk + tot_bytes;
     PCNN_CHECK_ARG(smem <= 200 * 1024, "conv2d_f32: kernel %dx%d needs %zu B of shared memory", kh, kw, smem);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    // the attribute belongs to the (device, context) the launch goes to: set it on every large launch (cheap) instead of
+    // caching one process-wide flag, which broke the second GPU of a multi-device process
+    if (smem > 48 * 1024)
         PCNN_CHECK_CUDA(cudaFuncSetAttribute(conv2d_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = 200 * 1024;
-    }
     dim3 block(64, ngroups, 1);
     dim3 grid(ceil_div(W, TILE_W), ceil_div(p.H, TILE_H), gridB);
     PCNN_CHECK_ARG(grid.y <= 65535, "conv2d_f32: H too large");

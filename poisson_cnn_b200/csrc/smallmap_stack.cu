@@ -103,6 +103,11 @@ __global__ void __launch_bounds__(NTHR) smallmap_stack_kernel(const Params p) {
             for (int ci = 0; ci < cin; ++ci) {
                 const float* base = a + ci * plane + (pm - pad) * Wp + (pm - pad);
                 const float* wt = s_w + ci * 32 + co0;
+                float part[4][4];                        // blocked summation: one short sum per input channel
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) part[c][q] = 0.f;
                 for (int dy = 0; dy < k; ++dy)
                     for (int dx = 0; dx < k; ++dx, wt += cin * 32) {
                         const float4 w = *reinterpret_cast<const float4*>(wt);
@@ -110,10 +115,14 @@ __global__ void __launch_bounds__(NTHR) smallmap_stack_kernel(const Params p) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const float v = s0[poff[q]];
-                            acc[0][q] = fmaf(v, w.x, acc[0][q]); acc[1][q] = fmaf(v, w.y, acc[1][q]);
-                            acc[2][q] = fmaf(v, w.z, acc[2][q]); acc[3][q] = fmaf(v, w.w, acc[3][q]);
+                            part[0][q] = fmaf(v, w.x, part[0][q]); part[1][q] = fmaf(v, w.y, part[1][q]);
+                            part[2][q] = fmaf(v, w.z, part[2][q]); part[3][q] = fmaf(v, w.w, part[3][q]);
                         }
                     }
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[c][q] += part[c][q];
             }
             const float* res = (p.flags[l] & 2) ? buf[saved] : nullptr;
 #pragma unroll

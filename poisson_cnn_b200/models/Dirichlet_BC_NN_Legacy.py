@@ -186,10 +186,13 @@ class Dirichlet_BC_NN_Legacy_2(WeightedModel):
 
     def __call__(self, inp):
         bc, dx, x_res = inp
-        raw, m = self.raw_forward(bc, dx, x_res)
-        out = ops.dbcnn_finalize(raw, m, bc)
-        if self.postsmoother_iterations > 0:
-            out = ops.jacobi(out, torch.zeros_like(out), torch.cat([dx, dx], 1), self.postsmoother_iterations)
-        return out
+        if not isinstance(bc, torch.Tensor) or not bc.is_cuda:
+            raise ValueError("bc must be a CUDA tensor (the hot path has no CPU implementation)")
+        with torch.cuda.device(bc.device):      # launches go to the current device: make it the tensors' device
+            raw, m = self.raw_forward(bc, dx, x_res)
+            out = ops.dbcnn_finalize(raw, m, bc)
+            if self.postsmoother_iterations > 0:
+                out = ops.jacobi(out, torch.zeros_like(out), torch.cat([dx, dx], 1), self.postsmoother_iterations)
+            return out
 
     call = __call__

@@ -51,6 +51,9 @@ class _Bottleneck:
 
 
 class Homogeneous_Poisson_NN_Legacy(WeightedModel):
+    # the single-pass 'tc' mode misses the 2e-3 budget on this 45-convolution-deep network (measured 4.4e-3 at 256x256)
+    COMPLIANT_PRECISIONS = ("fp32", "tc2", "tc3", "mixed")
+
     def __init__(self, data_format="channels_first", final_convolutions_config=None,
                  pre_bottleneck_convolutions_config=None, bottleneck_deconv_config=None,
                  bottleneck_multilinear_config=None, input_normalization=None, output_scaling=None,
@@ -382,6 +385,12 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
             raise ValueError("rhs must be [batch, 1, nx, ny] (channels_first)")
         if dx.dim() != 2 or dx.shape[1] != 1 or dx.shape[0] != rhs.shape[0]:
             raise ValueError("dx must be [batch, 1]")
+        if not rhs.is_cuda:
+            raise ValueError("rhs must be a CUDA tensor (the hot path has no CPU implementation)")
+        with torch.cuda.device(rhs.device):     # launches go to the current device: make it the tensors' device
+            return self._forward(rhs, dx)
+
+    def _forward(self, rhs, dx):
         B, _, H, Wd = rhs.shape
         F = self.filters
         if self.precision in ("tc", "tc2", "tc3"):

@@ -30,6 +30,11 @@ def _chk(t, name, dtype=torch.float32):
         raise ValueError("%s must be a CUDA tensor (the hot path has no CPU implementation)" % name)
     if t.dtype != dtype:
         raise ValueError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if t.device.index != torch.cuda.current_device():
+        # every launch goes to torch's CURRENT device and stream: a tensor living elsewhere would be dereferenced on the
+        # wrong GPU.  The model classes switch to their own device; direct users of ops wrap calls in torch.cuda.device().
+        raise ValueError("%s lives on %s but the current CUDA device is %d (wrap the call in torch.cuda.device(...))"
+                         % (name, t.device, torch.cuda.current_device()))
     return t
 
 
@@ -489,12 +494,35 @@ def jacobi(guess, rhs, grid_spacings, n_iter):
     return cur
 
 
-def dst_solve(rhs, left, top, right, bottom, dx):
-    """DST-I direct solve of the reference's ground-truth system.  rhs [B,1,nx,ny] -> [B,1,nx,ny]."""
+def dst_solve(rhs, left, top, right, bottom, dx, method="fft", dtype=torch.float64):
+    """DST-I direct solve of the reference's ground-truth system.  rhs [B,1,nx,ny] -> [B,1,nx,ny].
+    method "fft" (default): Bluestein chirp-z transforms on shared-memory FFTs, three passes over the grid (csrc/dst_fft.cu),
+    arithmetic in `dtype` (float64 like the reference's solver, or float32); "gemm": the dense sine-matrix form in float64
+    (O(N^3), kept as an independent cross-check and for sides beyond 2050 points)."""
     for t, nme in ((rhs, "rhs"), (left, "left"), (top, "top"), (right, "right"), (bottom, "bottom"), (dx, "dx")):
         _chk(t, nme)
+    if method not in ("fft", "gemm"):
+        raise ValueError("dst_solve: method must be 'fft' or 'gemm'")
     B, _, nx, ny = rhs.shape
     dev = rhs.device
+    args = [t.contiguous() for t in (rhs, left, top, right, bottom, dx)]
+    out = torch.empty_like(args[0])
+    if method == "fft" and max(nx, ny) <= 2050:
+        dbl = 1 if dtype == torch.float64 else 0
+        if dtype not in (torch.float64, torch.float32):
+            raise ValueError("dst_solve: dtype must be float64 or float32")
+
+        def plan(n):
+            def build():
+                p = torch.empty((lib.pcnn_dst_fft_plan_bytes(n, dbl),), device=dev, dtype=torch.uint8)
+                check(lib.pcnn_dst_fft_plan_init(_p(p), n, dbl, _stream()), "dst_fft_plan_init")
+                return p
+            return _cached(("dst_plan", str(dev), n, dbl), build)
+        px, py = plan(nx - 2), plan(ny - 2)
+        work = torch.empty((lib.pcnn_dst_fft_workspace_bytes(B, nx, ny, dbl),), device=dev, dtype=torch.uint8)
+        check(lib.pcnn_dst_solve_fft(*[_p(t) for t in args], _p(px), _p(py), _p(work), _p(out), B, nx, ny, dbl, _stream()),
+              "dst_solve_fft")
+        return out
 
     def sine(m):
         def build():
@@ -504,10 +532,7 @@ def dst_solve(rhs, left, top, right, bottom, dx):
         return _cached(("dst_sine", str(dev), m), build)
     sx, sy = sine(nx - 2), sine(ny - 2)
     work = torch.empty((lib.pcnn_dst_workspace_bytes(B, nx, ny) // 8,), device=dev, dtype=torch.float64)
-    out = torch.empty_like(rhs)
-    check(lib.pcnn_dst_solve(_p(rhs.contiguous()), _p(left.contiguous()), _p(top.contiguous()), _p(right.contiguous()),
-                             _p(bottom.contiguous()), _p(dx.contiguous()), _p(sx), _p(sy), _p(work), _p(out), B, nx, ny,
-                             _stream()), "dst_solve")
+    check(lib.pcnn_dst_solve(*[_p(t) for t in args], _p(sx), _p(sy), _p(work), _p(out), B, nx, ny, _stream()), "dst_solve")
     return out
 
 

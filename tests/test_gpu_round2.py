@@ -1,0 +1,258 @@
+"""Round-2 GPU parity tests: the cases VERDICT r01 found untested.
+
+  * config 2 shape: `mixed` and `tc2` against the float64 oracle at 256x256 on 8 DISTINCT samples (<= 1e-3 each way),
+  * strict FP32 at 256x256 against the float64 AND the float32 oracle, 1e-5 stated per comparator,
+  * Neumann HPNN in the tensor-core modes at a non-square shape,
+  * config 4: 2048x2048 forward + stencil-3/5 residual, 1024x1024 against the float64 oracle,
+  * the FFT (Bluestein) DST solve against the oracle, the dense sine-matrix solve and its own discrete system,
+  * the tiled residual kernel on ragged / unaligned / multi-chunk shapes,
+  * the host-buffer call returns COMPLETE results, fp16 activation storage with large magnitudes.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import pcnn_configs, all_weights, rel_l2
+from oracle import poisson_oracle as O
+
+pytestmark = pytest.mark.gpu
+KEYS = ("rhs", "left", "top", "right", "bottom", "dx")
+
+
+def dev(t):
+    return torch.as_tensor(t).float().cuda()
+
+
+@pytest.fixture(scope="module")
+def bundle():
+    from poisson_cnn_b200 import convert_tf_object_names, models
+    hp, db = pcnn_configs()
+    w = all_weights(hp, db)
+    m = models.Poisson_CNN_Legacy(models.Homogeneous_Poisson_NN_Legacy(**convert_tf_object_names(hp)),
+                                  models.Dirichlet_BC_NN_Legacy_2(**convert_tf_object_names(db))).load_weights(w)
+    return m, hp, db, w
+
+
+def distinct_problems(n, nx, ny, seed):
+    """n samples drawn from n different seeds (make_problem uses ONE control-point count per call): distinct fields,
+    distinct smoothness, distinct amplitudes and dx."""
+    from poisson_cnn_b200.synthetic import make_problem
+    ps = [make_problem(1, nx, ny, seed=seed + 17 * i) for i in range(n)]
+    return {k: torch.cat([p[k] for p in ps], 0) for k in KEYS}
+
+
+def per_sample_rel_l2(a, b):
+    a, b = a.double().cpu().flatten(1), b.double().cpu().flatten(1)
+    return ((a - b).norm(dim=1) / b.norm(dim=1)).tolist()
+
+
+# ------------------------------------------------------------------ config 2: 256 x 256, 8 distinct samples
+@pytest.fixture(scope="module")
+def oracle_256(bundle):
+    _, hp, db, w = bundle
+    p = distinct_problems(8, 256, 256, seed=2000)
+    with torch.no_grad():
+        ref64 = O.pcnn_forward(hp, db, w, *[p[k].double() for k in KEYS])
+    return p, ref64
+
+
+def test_mixed_and_tc2_vs_f64_oracle_256x256_8_samples(bundle, oracle_256):
+    """The headline configuration's accuracy on more than the 2 samples bench.py checks: every one of 8 distinct
+    256x256 problems within 1e-3 of the float64 oracle (budget 2e-3) in the default `mixed` mode and in `tc2`."""
+    model = bundle[0]
+    p, ref = oracle_256
+    inp = [p[k].cuda() for k in KEYS]
+    try:
+        for mode in ("mixed", "tc2"):
+            out = model.set_precision(mode)(inp)
+            errs = per_sample_rel_l2(out, ref)
+            print("%s 256x256 per-sample rel-L2 vs f64 oracle: %s" % (mode, " ".join("%.2e" % e for e in errs)))
+            assert max(errs) < 1e-3, (mode, errs)
+            assert rel_l2(out, ref) < 1e-3
+    finally:
+        model.set_precision("fp32")
+
+
+def test_strict_fp32_256x256_vs_f32_and_f64_oracle(bundle, oracle_256):
+    """Strict mode at the headline shape.  Budget 1e-5 (north star), stated per comparator:
+       vs the float64 oracle (the exact answer): <= 1e-5 -- holds since conv_f32 sums in blocks (1.4e-5 before);
+       vs the float32 oracle (same arithmetic as the reference, different summation order): two fp32 evaluations each carry
+       their own rounding noise, so their distance is bounded by the sum of both distances to the exact answer; asserted at
+       the measured CPU-fp32 noise + 1e-5."""
+    model, hp, db, w = bundle
+    p, ref64 = oracle_256
+    n = 4
+    out = model.set_precision("fp32")([p[k][:n].cuda() for k in KEYS])
+    with torch.no_grad():
+        ref32 = O.pcnn_forward(hp, db, w, *[p[k][:n].float() for k in KEYS])
+    e64 = per_sample_rel_l2(out, ref64[:n])
+    e32 = per_sample_rel_l2(out, ref32)
+    o32 = per_sample_rel_l2(ref32, ref64[:n])
+    print("fp32 256x256: vs f64 oracle %s | vs f32 oracle %s | f32 oracle vs f64 oracle %s" % (
+        " ".join("%.2e" % e for e in e64), " ".join("%.2e" % e for e in e32), " ".join("%.2e" % e for e in o32)))
+    assert max(e64) < 1e-5, e64
+    assert all(a < b + 1e-5 for a, b in zip(e32, o32)), (e32, o32)
+
+
+# ------------------------------------------------------------------ Neumann HPNN in the tensor-core modes
+def test_hpnn_neumann_tensor_core_modes_nonsquare():
+    from poisson_cnn_b200 import convert_tf_object_names, models
+    from poisson_cnn_b200.synthetic import make_problem
+    hp, db = pcnn_configs()
+    hp = dict(hp, bc_type="neumann")
+    w = all_weights(hp, db)
+    p = make_problem(2, 144, 200, seed=23, magnitudes=False)
+    with torch.no_grad():
+        ref = O.hpnn_forward(hp, w, p["rhs"].double(), p["dx"].double(), "hpnn/")
+    m = models.Homogeneous_Poisson_NN_Legacy(**convert_tf_object_names(hp)).load_weights(w, "hpnn/")
+    for mode in ("mixed", "tc2", "tc3"):
+        out = m.set_precision(mode)([dev(p["rhs"]), dev(p["dx"])])
+        e = rel_l2(out, ref)
+        print("Neumann HPNN 144x200 %s: %.3e" % (mode, e))
+        assert e < 2e-3, (mode, e)
+        # homogeneous Neumann ring: the SYMMETRIC pad copies the first interior line (Homogeneous_Poisson_NN_Legacy.py:251)
+        assert torch.equal(out[:, :, 0, 1:-1], out[:, :, 1, 1:-1]) and torch.equal(out[:, :, 1:-1, -1], out[:, :, 1:-1, -2])
+
+
+# ------------------------------------------------------------------ config 4: large grids
+def test_forward_1024_vs_f64_oracle(bundle):
+    model, hp, db, w = bundle
+    p = distinct_problems(1, 1024, 1024, seed=2100)
+    with torch.no_grad():
+        ref = O.pcnn_forward(hp, db, w, *[p[k].double() for k in KEYS])
+    try:
+        out = model.set_precision("mixed")([p[k].cuda() for k in KEYS])
+        e = rel_l2(out, ref)
+        print("mixed 1024x1024 vs f64 oracle: %.3e" % e)
+        assert e < 2e-3
+    finally:
+        model.set_precision("fp32")
+
+
+def test_forward_2048_and_residual(bundle):
+    """BASELINE config 4 at 2048x2048: `mixed` forward against the strict FP32 path (pinned on goldens and at 256x256
+    above), then the stencil-3 and stencil-5 residual kernels against the oracle's residual of the same field."""
+    from poisson_cnn_b200.losses import linear_operator_loss
+    model = bundle[0]
+    p = distinct_problems(1, 2048, 2048, seed=2200)
+    inp = [p[k].cuda() for k in KEYS]
+    try:
+        ref = model.set_precision("fp32")(inp)
+        out = model.set_precision("mixed")(inp)
+    finally:
+        model.set_precision("fp32")
+    assert out.shape == (1, 1, 2048, 2048) and bool(torch.isfinite(out).all())
+    e = rel_l2(out, ref)
+    print("mixed vs strict fp32 at 2048x2048: %.3e" % e)
+    assert e < 2e-3
+    gs = torch.cat([p["dx"], 1.25 * p["dx"]], 1)
+    for st in (3, 5):
+        got = float(linear_operator_loss(st, 2, ndims=2)(inp[0], out, gs.cuda()))
+        want = float(O.laplacian_residual(p["rhs"].double(), out.double().cpu(), gs.double(), st))
+        assert abs(got - want) < 1e-4 * want, (st, got, want)
+
+
+# ------------------------------------------------------------------ residual kernel: ragged / unaligned shapes
+@pytest.mark.parametrize("B,H,W", [(3, 70, 93), (2, 5, 5), (2, 6, 7), (1, 35, 128), (2, 34, 132), (1, 67, 260), (2, 97, 1030),
+                                   (1, 256, 256), (4, 40, 512)])
+def test_laplacian_residual_tiled_kernel(B, H, W):
+    from poisson_cnn_b200.losses import linear_operator_loss
+    g = torch.Generator().manual_seed(H * 1000 + W)
+    rhs = torch.randn(B, 1, H, W, generator=g)
+    sol = torch.randn(B, 1, H, W, generator=g) * 1e-3
+    gs = 5e-3 + 4.5e-2 * torch.rand(B, 2, generator=g)
+    for st in (3, 5):
+        if min(H, W) <= st - 1:
+            continue
+        ref = O.laplacian_residual(rhs.double(), sol.double(), gs.double(), st, per_sample=True)
+        got = linear_operator_loss(st, 2, ndims=2).per_sample_squared_sums(dev(rhs), dev(sol), dev(gs))
+        n_int = (H - st + 1) * (W - st + 1)
+        ref = torch.as_tensor(ref).double().flatten()
+        got = got.double().cpu().flatten()
+        # the oracle may report per-sample means or sums: compare what both call the per-sample statistic
+        if not torch.allclose(got, ref, rtol=1e-4):
+            assert torch.allclose(got / n_int, ref, rtol=1e-4) or torch.allclose(got, ref / n_int, rtol=1e-4), (st, got, ref)
+        refn = O.laplacian_residual(rhs.double(), sol.double(), gs.double(), st)
+        gotn = linear_operator_loss(st, 2, ndims=2)(dev(rhs), dev(sol), dev(gs))
+        assert abs(float(gotn) - float(refn)) < 1e-4 * float(refn), (st, H, W)
+    # an unaligned view (pointer not 16-byte aligned) takes the scalar-load path
+    if W % 4 == 0:
+        flat = torch.empty(B * H * W + 1, device="cuda")
+        s2 = flat[1:].view(B, 1, H, W)
+        s2.copy_(dev(sol))
+        a = linear_operator_loss(3, 2, ndims=2)(dev(rhs), s2, dev(gs))
+        b = linear_operator_loss(3, 2, ndims=2)(dev(rhs), dev(sol), dev(gs))
+        assert abs(float(a) - float(b)) <= 1e-6 * abs(float(b))
+
+
+# ------------------------------------------------------------------ FFT (Bluestein) DST solve
+@pytest.mark.parametrize("B,nx,ny", [(3, 70, 93), (2, 3, 3), (2, 4, 9), (1, 64, 64), (2, 256, 256), (1, 200, 300), (2, 11, 600)])
+def test_dst_fft_solve_vs_oracle_and_gemm(B, nx, ny):
+    from poisson_cnn_b200.synthetic import make_problem
+    from poisson_cnn_b200.solvers import dst_poisson_solve
+    p = make_problem(B, nx, ny, seed=31 + nx)
+    ref = O.dst_poisson_solve(p["rhs"], p["left"], p["top"], p["right"], p["bottom"], p["dx"])
+    bnd = {k: dev(p[k]) for k in ("left", "top", "right", "bottom")}
+    fft64 = dst_poisson_solve(dev(p["rhs"]), bnd, dev(p["dx"]))
+    gemm = dst_poisson_solve(dev(p["rhs"]), bnd, dev(p["dx"]), method="gemm")
+    fft32 = dst_poisson_solve(dev(p["rhs"]), bnd, dev(p["dx"]), dtype=torch.float32)
+    assert rel_l2(fft64, ref) < 1e-6 and rel_l2(fft64, gemm) < 1e-6
+    assert rel_l2(fft32, ref) < 2e-5
+    # ring: left/right rows win the corners (multigrid.py:145-148)
+    assert torch.equal(fft64[:, 0, 0, :], bnd["left"][:, 0]) and torch.equal(fft64[:, 0, -1, :], bnd["right"][:, 0])
+    assert torch.equal(fft64[:, 0, 1:-1, 0], bnd["bottom"][:, 0, 1:-1]) and torch.equal(fft64[:, 0, 1:-1, -1], bnd["top"][:, 0, 1:-1])
+
+
+@pytest.mark.parametrize("n", [1024, 2048])
+def test_dst_fft_solve_large_matches_gemm_and_system(n):
+    from poisson_cnn_b200.losses import linear_operator_loss
+    from poisson_cnn_b200.synthetic import make_problem
+    from poisson_cnn_b200.solvers import dst_poisson_solve
+    p = make_problem(1, n, n, seed=1005)
+    bnd = {k: dev(p[k]) for k in ("left", "top", "right", "bottom")}
+    rhs, dx = dev(p["rhs"]), dev(p["dx"])
+    fft64 = dst_poisson_solve(rhs, bnd, dx)
+    gemm = dst_poisson_solve(rhs, bnd, dx, method="gemm")
+    fft32 = dst_poisson_solve(rhs, bnd, dx, dtype=torch.float32)
+    e, e32 = rel_l2(fft64, gemm), rel_l2(fft32, gemm)
+    print("DST %d^2: fft(f64) vs gemm(f64) %.2e, fft(f32) vs gemm %.2e" % (n, e, e32))
+    assert e < 1e-6 and e32 < 1e-4
+    r = float(linear_operator_loss(3, 2, ndims=2)(rhs, fft64, torch.cat([dx, dx], 1)))
+    bound = (float(fft64.abs().max()) * 2.0 ** -23 / float(dx.min()) ** 2) ** 2 * 64
+    assert r < max(bound, 1e-6 * float((rhs ** 2).mean()))
+
+
+# ------------------------------------------------------------------ host-buffer call completes before returning
+def test_host_call_result_is_complete_without_global_sync(bundle):
+    model = bundle[0]
+    from poisson_cnn_b200.synthetic import make_problem
+    p = make_problem(6, 96, 80, seed=77)
+    model.microbatch_samples = 2
+    try:
+        ref = model([p[k].cuda() for k in KEYS]).cpu()
+        host = model([p[k] for k in KEYS])                 # no torch.cuda.synchronize() before reading
+        assert not host.is_cuda and torch.equal(host, ref)
+        out, ev = model([p[k] for k in KEYS], non_blocking=True)
+        ev.synchronize()
+        assert torch.equal(out, ref)
+    finally:
+        model.microbatch_samples = None
+
+
+def test_fp16_activation_storage_with_large_magnitudes(bundle):
+    """fp16 BLK8 activations top out at 65504: weights scaled up so that intermediate activations are O(100) must not
+    overflow to inf in the tensor-core modes.  Only the scale-invariant pieces are rescaled: conv kernels of the
+    HPNN trunk by a common factor would change the function, so the check is on finiteness and agreement with strict FP32."""
+    from poisson_cnn_b200 import convert_tf_object_names, models
+    from poisson_cnn_b200.synthetic import make_problem
+    hp, db = pcnn_configs()
+    w = dict(all_weights(hp, db))
+    for k in list(w):
+        if k.startswith("hpnn/pre_bottleneck/0") and k.endswith("kernel"):
+            w[k] = w[k] * 64.0                     # activations of the first layers ~64x larger (leaky-relu is homogeneous)
+    m = models.Homogeneous_Poisson_NN_Legacy(**convert_tf_object_names(hp)).load_weights(w, "hpnn/")
+    p = make_problem(2, 128, 128, seed=5, magnitudes=False)
+    ref = m.set_precision("fp32")([dev(p["rhs"]), dev(p["dx"])])
+    out = m.set_precision("mixed")([dev(p["rhs"]), dev(p["dx"])])
+    assert bool(torch.isfinite(out).all())
+    assert rel_l2(out, ref) < 2e-3

@@ -261,7 +261,13 @@ def test_models_tc_mode_vs_oracle():
     e_hp = rel_l2(model.hpnn([dev(p["rhs"]), dev(p["dx"])]), ref)
     print("tc-mode rel-L2 vs float64 oracle: pcnn %.3e  dbcnn %.3e  hpnn %.3e" % (e_pcnn, e_db, e_hp))
     assert e_pcnn < TC_TOL and e_db < TC_TOL
-    assert e_hp < 2 * TC_TOL     # HPNN alone is deeper (45 convs) than the merged average; see DESIGN.md precision budget
+    # The single-pass mode is NOT a compliant mode for the 45-convolution-deep HPNN (4.4e-3 at 256x256 against the 2e-3
+    # budget): the class says so (COMPLIANT_PRECISIONS) and selecting it warns.  What is asserted here
+    # is only that the kernels work (sane error); compliance is carried by tc2 / tc3 / mixed (tests below, test_gpu_round2).
+    assert "tc" not in model.hpnn.COMPLIANT_PRECISIONS and "tc" in model.dbcnn.COMPLIANT_PRECISIONS
+    assert e_hp < 1e-2
+    with pytest.warns(UserWarning, match="outside the 2e-3"):
+        model.hpnn.set_precision("tc")
 
 
 # ------------------------------------------------------------------ split precision (tc3)
