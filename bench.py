@@ -1,12 +1,14 @@
 #!/usr/bin/env python
-"""Headline benchmark: 256x256 Poisson solutions/s of the full Poisson_CNN_Legacy forward
-(BASELINE.json configs[1]: homogeneous + Dirichlet-BC networks merged, batch 256 per GPU).
+"""Benchmarks of the poisson_CNN inference hot path on B200 (one process per GPU).
 
-  python bench.py --gpus N --steps K --warmup W                 # this repo (CUDA kernels via the C ABI)
-  python bench.py --impl reference --gpus N --steps K --warmup W  # CPU restatement of the reference path
-  torchrun --nproc-per-node N bench.py --gpus N ...             # one rank per GPU, weak scaling
+  python bench.py --gpus N --steps K --warmup W                   # BASELINE configs[1] (default): 256x256, batch 256 per GPU
+  python bench.py --config {1,2,3,4,5} ...                        # the other BASELINE.json configs (see CONFIGS below)
+  python bench.py --impl reference --gpus N --steps K --warmup W  # CPU restatement of the reference path (the reference is TensorFlow)
+  python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...   # one rank per GPU
 
-Prints ONE JSON line (rank 0).  A step = one forward pass over one batch of synthetic problems.
+Prints ONE JSON line (rank 0).  A step = one pass of the hot path over one batch of synthetic problems.
+Config 2 shards by replication of the per-GPU batch (weak scaling, the headline); configs 3, 4 and 5 split a FIXED batch
+over the ranks (strong scaling).  No data-path collective anywhere: samples are independent end to end.
 """
 import argparse
 import json
@@ -23,20 +25,43 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 FLOP_PER_SOLUTION_256 = 441.43e9      # conv/transpose-conv MACs x2 at true channel counts
+FLOP_HPNN_PER_PIXEL = 2 * 2451520.0   # HPNN alone
 METRIC = "256x256 Poisson solutions/sec (full Poisson_CNN forward)"
+KEYS = ("rhs", "left", "top", "right", "bottom", "dx")
+CONFIGS = {
+    1: "Homogeneous_Poisson_NN forward, batch 4, 64x64, zero Dirichlet ring (small-domain scaling block)",
+    2: "full Poisson_CNN, batch 256 per GPU, 256x256 (weak scaling)",
+    3: "variable-aspect grids 384x128 / 512x256 / 200x300, Dirichlet Poisson_CNN + homogeneous-Neumann HPNN, batch 128 per shape split over the GPUs",
+    4: "large grids 1024x1024 and 2048x2048, batch 16 split over the GPUs, forward + 5-point Laplacian residual",
+    5: "DST ground-truth solve vs CNN surrogate sweep 64^2..2048^2, batch split over the GPUs",
+}
 
 
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
         d = json.load(open(path))
-        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
-    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback"}
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "tflops_burst": d["bf16_tflops"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1700.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 def pcnn_flops(nx, ny):
     """Analytic conv FLOPs per solution (scaled from the 256x256 count; weak shape dependence ignored)."""
     return FLOP_PER_SOLUTION_256 * (nx * ny) / 65536.0
+
+
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch of the dominant kernel from the latest committed `ncu --set full` capture, as summarised in
+    profiles/roofline_traffic.json by scripts/summarize_ncu.py ({key: {"bytes_per_sample": ..., "source": file}}).
+    None when no capture is recorded for this kernel (the value is never a constant baked into this file)."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.isfile(path):
+        return None
+    try:
+        return json.load(open(path)).get(kernel_key)
+    except Exception:
+        return None
 
 
 class ClockSampler(threading.Thread):
@@ -82,39 +107,43 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def build_model(device, precision):
-    from poisson_cnn_b200 import convert_tf_object_names, load_experiment, models, weights as W
-    cfg = load_experiment("pcnn_end_to_end")
-    hp_cfg, db_cfg = cfg["hpnn_model"], cfg["dbcnn_model"]
+def model_weights(experiment="pcnn_end_to_end"):
+    from poisson_cnn_b200 import load_experiment, weights as W
+    cfg = load_experiment(experiment)
+    if "hpnn_model" in cfg:
+        hp_cfg, db_cfg = cfg["hpnn_model"], cfg["dbcnn_model"]
+    else:
+        hp_cfg, db_cfg = cfg["model"], load_experiment("pcnn_end_to_end")["dbcnn_model"]
     hs, ds = W.hpnn_weight_specs(hp_cfg, "hpnn/"), W.dbcnn_weight_specs(db_cfg, "dbcnn/")
     w = W.synthetic_weights(({**hs[0], **ds[0]}, {**hs[1], **ds[1]}), seed=0)
+    return hp_cfg, db_cfg, w
+
+
+def build_model(device, precision):
+    from poisson_cnn_b200 import convert_tf_object_names, models
+    hp_cfg, db_cfg, w = model_weights()
     hp = models.Homogeneous_Poisson_NN_Legacy(**convert_tf_object_names(hp_cfg))
     db = models.Dirichlet_BC_NN_Legacy_2(**convert_tf_object_names(db_cfg))
     model = models.Poisson_CNN_Legacy(hp, db).load_weights(w, device=device)
-    if hasattr(model, "set_precision"):
-        model.set_precision(precision)
-    elif precision != "fp32":
-        raise SystemExit("precision %s not built" % precision)
+    model.set_precision(precision)
     return model, (hp_cfg, db_cfg, w)
 
 
-KEYS = ("rhs", "left", "top", "right", "bottom", "dx")
+def build_hpnn(device, precision, hp_cfg, w):
+    from poisson_cnn_b200 import convert_tf_object_names, models
+    m = models.Homogeneous_Poisson_NN_Legacy(**convert_tf_object_names(hp_cfg)).load_weights(w, "hpnn/", device=device)
+    return m.set_precision(precision)
 
 
-def oracle_throughput(hp_cfg, db_cfg, w, nx, ny, budget_s, steps=None, warmup=0):
-    """Times the CPU restatement (oracle, torch-CPU fp32, all host threads) on single-sample forwards of
-    the same workload; returns (solutions/s, samples timed, threads)."""
-    from oracle import poisson_oracle as O
-    from poisson_cnn_b200.synthetic import make_problem
+def oracle_throughput(fn, budget_s, steps=None, warmup=0):
+    """Times a CPU-oracle call (torch-CPU fp32, all host threads); returns (calls/s, calls timed, threads)."""
     threads = torch.get_num_threads()
-    p = make_problem(1, nx, ny, seed=1001)
-    args = [p[k] for k in KEYS]
     with torch.no_grad():
         for _ in range(warmup):
-            O.pcnn_forward(hp_cfg, db_cfg, w, *args)
+            fn()
         n, t0 = 0, time.perf_counter()
         while True:
-            O.pcnn_forward(hp_cfg, db_cfg, w, *args)
+            fn()
             n += 1
             el = time.perf_counter() - t0
             if (steps is not None and n >= steps) or (steps is None and el >= budget_s):
@@ -122,50 +151,167 @@ def oracle_throughput(hp_cfg, db_cfg, w, nx, ny, budget_s, steps=None, warmup=0)
     return n / el, n, threads
 
 
-def run_reference(args):
-    """--impl reference: the reference's own implementation is TensorFlow (not installable here, see
-    DESIGN.md); the stand-in is the oracle restatement on the host cores, bounded to one sample per step."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def use_all_host_threads():
     # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can
     try:
         torch.set_num_threads(len(os.sched_getaffinity(0)))
     except Exception:
         torch.set_num_threads(os.cpu_count() or 1)
-    from poisson_cnn_b200 import load_experiment, weights as W
-    cfg = load_experiment("pcnn_end_to_end")
-    hp_cfg, db_cfg = cfg["hpnn_model"], cfg["dbcnn_model"]
-    hs, ds = W.hpnn_weight_specs(hp_cfg, "hpnn/"), W.dbcnn_weight_specs(db_cfg, "dbcnn/")
-    w = W.synthetic_weights(({**hs[0], **ds[0]}, {**hs[1], **ds[1]}), seed=0)
+
+
+def reference_workload(args):
+    """(callable for one bounded CPU step, solutions per call, workload text, metric) of the selected config."""
+    from oracle import poisson_oracle as O
+    from poisson_cnn_b200.synthetic import make_problem
+    if args.config == 1:
+        hp_cfg, db_cfg, w = model_weights("hpnn_smalldomain")
+        p = make_problem(4, 64, 64, seed=1001, magnitudes=False)
+        return (lambda: O.hpnn_forward(hp_cfg, w, p["rhs"], p["dx"], "hpnn/")), 4, \
+            "Homogeneous_Poisson_NN_Legacy forward, batch 4, 64x64 (config 1 exactly)", "64x64 HPNN solutions/sec"
+    hp_cfg, db_cfg, w = model_weights()
+    nx, ny = {2: (args.grid, args.grid), 3: (384, 128), 4: (1024, 1024), 5: (256, 256)}[args.config]
+    p = make_problem(1, nx, ny, seed=1001)
+    a = [p[k] for k in KEYS]
+    return (lambda: O.pcnn_forward(hp_cfg, db_cfg, w, *a)), 1, \
+        "Poisson_CNN_Legacy forward, %dx%d grids, pcnn_end_to_end architecture, 1 sample per step (bounded CPU sample of config %d)" % (nx, ny, args.config), \
+        (METRIC if args.config == 2 else "%dx%d Poisson solutions/sec (full Poisson_CNN forward)" % (nx, ny))
+
+
+def run_reference(args):
+    """--impl reference: the reference's own implementation is TensorFlow (not installable here); the
+    stand-in is the oracle restatement on the host cores, bounded to one small sample of the workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    use_all_host_threads()
+    fn, per_call, workload, metric = reference_workload(args)
     steps = max(1, min(args.steps, 8))
-    val, n, threads = oracle_throughput(hp_cfg, db_cfg, w, args.grid, args.grid, None, steps=steps, warmup=1 if args.warmup else 0)
+    val, n, threads = oracle_throughput(fn, None, steps=steps, warmup=1 if args.warmup else 0)
+    val *= per_call
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "solutions/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": 1 if args.warmup else 0, "ms_per_step": 1000.0 / val, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Poisson_CNN_Legacy forward, %dx%d grids, pcnn_end_to_end architecture, 1 sample per step (bounded CPU sample of the batch-256 workload)" % (args.grid, args.grid)},
+        "impl": "reference", "metric": metric, "value": val, "unit": "solutions/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": 1 if args.warmup else 0, "ms_per_step": 1000.0 * per_call / val, "higher_is_better": True,
+        "scaling": "weak" if args.config in (1, 2) else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "baseline_config": args.config},
         "cpu_baseline": {"value": val, "unit": "solutions/s", "cores": threads, "kind": "port",
-                         "sample": "%d single-sample forwards, torch-CPU fp32 oracle (reference is TensorFlow: not installable offline)" % n},
+                         "sample": "%d forwards of %d sample(s), torch-CPU fp32 oracle (reference is TensorFlow: not installable offline)" % (n, per_call)},
         "e2e": {"value": val, "unit": "solutions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def run_ours(args):
-    # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION) would land there too
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
-    import torch.distributed as dist
-    from poisson_cnn_b200 import ops, _lib
-    from poisson_cnn_b200.sharding import init_from_env
-    from poisson_cnn_b200.synthetic import make_problem
+# ======================================================================================================================
+class Harness:
+    """Process-group plumbing + CUDA-event timing shared by all configs."""
 
-    rank, world, local = init_from_env()
-    if world != args.gpus and world > 1:
-        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
+    def __init__(self, args):
+        # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION) would land there too
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        import torch.distributed as dist
+        from poisson_cnn_b200.sharding import init_from_env
+        self.dist = dist
+        self.rank, self.world, self.local = init_from_env()
+        if self.world != args.gpus and self.world > 1:
+            raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, self.world))
+        torch.cuda.set_device(self.local)
+        self.device = torch.device("cuda", self.local)
+        self.args = args
+        self.peaks = measured_peaks()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms):
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.device, dtype=torch.float64)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            return float(t)
+        return ms
+
+    def sum_over_ranks(self, v):
+        if self.world > 1:
+            t = torch.tensor([v], device=self.device, dtype=torch.float64)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+            return float(t)
+        return v
+
+    def time_steps(self, fn, steps, warmup):
+        """W untimed calls, then exactly K calls between barrier+synchronize, CUDA events, max over ranks -> total ms."""
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1))
+
+    def finish(self, line):
+        if self.world > 1:
+            self.dist.barrier()
+        if self.rank == 0:
+            print(json.dumps(line), flush=True)
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def hbm_kernel_rooflines(h, B2048=16, iters=10):
+    """CUDA-event timing of the two memory-bound check kernels against their 8 B/grid-point algorithmic figure
+    (SURVEY 8(d)): the 5-point Laplacian residual (read u, read f) and the DST direct solve (read f, write u)."""
+    from poisson_cnn_b200 import ops, _lib
+    from poisson_cnn_b200.losses import linear_operator_loss
+    dev, peak = h.device, h.peaks["hbm_gbs"]
+    res, dst = {}, {}
+    for (B, n) in ((256, 256), (B2048, 2048)):
+        g = torch.Generator(device=dev).manual_seed(7)
+        u = torch.randn((B, 1, n, n), device=dev, generator=g)
+        f = torch.randn((B, 1, n, n), device=dev, generator=g)
+        dx = 5e-3 + 4.5e-2 * torch.rand((B, 1), device=dev, generator=g)
+        gs = torch.cat([dx, dx], 1)
+        bc = [torch.randn((B, 1, n), device=dev, generator=g) for _ in range(4)]
+        tag = "%dx%dx%d" % (B, n, n)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for st in (3, 5):
+            ops.laplacian_residual(f, u, gs, st)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(iters):
+                ops.laplacian_residual(f, u, gs, st)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            gbs = B * n * n * 8 / ms / 1e6
+            res["stencil%d_%s" % (st, tag)] = {"ms": ms, "gbs": gbs, "frac_of_hbm_peak": gbs / peak, "grids_per_s": B / ms * 1e3}
+        for name, kw in (("fft_f64", {}), ("fft_f32", {"dtype": torch.float32})):
+            ops.dst_solve(f, bc[0], bc[1], bc[2], bc[3], dx, **kw)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(max(1, iters // 3)):
+                ops.dst_solve(f, bc[0], bc[1], bc[2], bc[3], dx, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / max(1, iters // 3)
+            gbs = B * n * n * 8 / ms / 1e6
+            tb = 8 if name == "fft_f64" else 4
+            dst["%s_%s" % (name, tag)] = {"ms": ms, "solutions_per_s": B / ms * 1e3, "gbs_at_8B_per_pt": gbs, "frac_of_hbm_peak": gbs / peak,
+                                          "passes": int(_lib.lib.pcnn_dst_fft_passes()), "actual_bytes_per_pt": 8 + 4 * tb}
+        del u, f, bc
+    res["peak_gbs"] = dst["peak_gbs"] = peak
+    res["algorithmic_bytes_per_pt"] = dst["algorithmic_bytes_per_pt"] = 8
+    return res, dst
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_config2(args):
+    from poisson_cnn_b200 import ops, _lib
+    from poisson_cnn_b200.synthetic import make_problem
+    h = Harness(args)
+    rank, world, device = h.rank, h.world, h.device
     B, nx, ny = args.batch, args.grid, args.grid
     model, (hp_cfg, db_cfg, w) = build_model(device, args.precision)
 
@@ -179,59 +325,37 @@ def run_ours(args):
     h2d = sum(host[k].numel() * 4 for k in KEYS)
     out_host = torch.empty((B, 1, nx, ny), dtype=torch.float32).pin_memory()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world > 1:
-            t = torch.tensor([ms], device=device, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t)
-        return ms
-
     # ---------------- device-resident timing ("value") ----------------
+    state = {}
+
+    def step():
+        state["out"] = model(dev_in)
     for _ in range(args.warmup):
-        out = model(dev_in)
-    barrier()
-    sampler = ClockSampler(local); sampler.start()
+        step()
+    h.barrier()
+    sampler = ClockSampler(h.local); sampler.start()
     timer = ops.KernelTimer(*args.roofline_kernel)
     ops.KERNEL_TIMER = timer
     launches0 = _lib.lib.pcnn_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    t_host0 = time.perf_counter()
-    for _ in range(args.steps):
-        out = model(dev_in)
-    host_enqueue_ms = (time.perf_counter() - t_host0) * 1000.0 / args.steps   # CPU time to enqueue one step (no sync inside)
-    e1.record()
-    barrier()
+    ms_total = h.time_steps(step, args.steps, 0)
     ops.KERNEL_TIMER = None
     launches = _lib.lib.pcnn_launch_count() - launches0
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
     sampler.stop_flag = True; sampler.join(2)
+    out = state["out"]
     ms_per_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total / 1000.0)
 
     # ---------------- end to end through the public API with host buffers ("e2e") ----------------
     def e2e_step():
-        # the public call with HOST buffers: slices of the batch are copied in, solved and copied out on three streams
+        # the public call with HOST buffers: slices of the batch are copied in, solved and copied out on three streams;
+        # the call returns once the result is complete in `out_host`
         model([host[k] for k in KEYS], out=out_host)
     e2e_steps = max(1, min(args.steps, 3)) if ms_per_step > 2000 else args.steps
-    e2e_step()
-    barrier()
-    e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_ms = h.time_steps(e2e_step, e2e_steps, 1)
     e2e_value = world * B * e2e_steps / (e2e_ms / 1000.0)
 
     # ---------------- roofline of the dominant kernel (live CUDA-event timing inside the timed region)
-    peaks = measured_peaks()
+    peaks = h.peaks
     ks = timer.summary()
     roofline = None
     if ks:
@@ -239,45 +363,53 @@ def run_ours(args):
         kk = args.roofline_kernel[2]
         hp_mode = {"mixed": "tc2"}.get(args.precision, args.precision)      # precision mode of the HPNN, which owns the timed kernel
         issue_factor = {"tc": 1.0, "tc3": 3.0, "tc2": 2.0}.get(hp_mode, 0.0) * (kk + 3.0) / kk   # MMAs issued per algorithmic MAC
-        # DRAM bytes per launch of this kernel from the ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum
-        # at 32 samples per launch), scaled to the samples per launch here.  tc2: three of the four 32->32 k15 launches of a
-        # forward have no residual input (profiles/r01_conv_tc_k15_tc2_b32_full_raw.csv: 303.6 + 228.8 MB), one has
-        # (profiles/r01b_conv_tc_k15_tc2_res_b32_full_raw.csv: 512.1 + 237.5 MB; unchanged in the final build,
-        # profiles/r01c_k15_tc2_full_raw.csv: 512.5 + 237.3 MB)
-        per_sample = {"tc": (151.436032e6 + 94.614272e6) / 32,
-                      "tc2": (3 * (303.551488e6 + 228.785920e6) + (512.086272e6 + 237.487872e6)) / 4 / 32}.get(hp_mode)
         samples_per_launch = min(B, max(1, int((getattr(model, "max_microbatch", B) or B) * 65536 // (nx * ny))))
-        traffic = per_sample * samples_per_launch if (per_sample and args.roofline_kernel == (32, 32, 15) and (nx, ny) == (256, 256)) else None
+        rec = ncu_traffic("conv2d_%d_%d_k%d_%s" % (args.roofline_kernel + (hp_mode,))) if (nx, ny) == (256, 256) else None
+        traffic = rec["bytes_per_sample"] * samples_per_launch if rec else None
         roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["tflops"], "traffic": traffic, "kernel": "conv2d %d->%d k%d (%s)" % (args.roofline_kernel + (hp_mode,)),
+                    "frac": ach / peaks["tflops"], "traffic": traffic, "traffic_source": rec["source"] if rec else None,
+                    "kernel": "conv2d %d->%d k%d (%s)" % (args.roofline_kernel + (hp_mode,)),
                     "launches_timed": ks["launches"], "avg_launch_ms": ks["avg_ms"], "peak_source": peaks["source"] + " bf16 sustained",
                     "algorithmic_flops_per_launch": ks["flops_per_launch"],
                     "mma_issued_tflops": ach * issue_factor if issue_factor else None,
                     "mma_issued_frac": ach * issue_factor / peaks["tflops"] if issue_factor else None,
-                    "note": "achieved/frac count ALGORITHMIC conv FLOPs once; the kernel issues (k+3)/k x that in MMAs (row-group zero padding) and 3x in tc3 (hi/lo operand split)"}
+                    "note": "achieved/frac count ALGORITHMIC conv FLOPs once; the kernel issues (k+3)/k x that in MMAs (row-group zero padding), 2x in tc2 (e4m3 correction pass), 3x in tc3"}
 
     # ---------------- accuracy + residual of what was timed (outside the timed region) ----------------
-    acc = None
-    cpu_baseline = None
+    acc = cpu_baseline = residual = dst = None
     if rank == 0:
         from oracle import poisson_oracle as O
         from poisson_cnn_b200.losses import linear_operator_loss
         nchk = min(B, args.check_samples)
-        ref = O.pcnn_forward(hp_cfg, db_cfg, w, *[host[k][:nchk].double() for k in KEYS])
+        with torch.no_grad():
+            ref = O.pcnn_forward(hp_cfg, db_cfg, w, *[host[k][:nchk].double() for k in KEYS])
         got = out[:nchk].double().cpu()
         gs = torch.cat([dev_in[5], dev_in[5]], 1)
         res = float(linear_operator_loss(3, 2, ndims=2)(dev_in[0], out, gs))
-        acc = {"rel_l2_vs_oracle_f64": float((got - ref).norm() / ref.norm()), "samples_checked": nchk, "laplacian_residual_mse": res}
+        per = ((got - ref).flatten(1).norm(dim=1) / ref.flatten(1).norm(dim=1)).tolist()
+        acc = {"rel_l2_vs_oracle_f64": float((got - ref).norm() / ref.norm()), "samples_checked": nchk,
+               "max_per_sample_rel_l2": max(per), "laplacian_residual_mse": res}
         if world == 1 and not args.no_cpu_baseline:
-            val, n, threads = oracle_throughput(hp_cfg, db_cfg, w, nx, ny, args.cpu_budget_s)
+            a = [host[k][:1] for k in KEYS]
+            val, n, threads = oracle_throughput(lambda: O.pcnn_forward(hp_cfg, db_cfg, w, *a), args.cpu_budget_s)
             cpu_baseline = {"value": val, "unit": "solutions/s", "cores": threads, "kind": "port",
                             "sample": "%d single-sample %dx%d Poisson_CNN forwards, torch-CPU fp32 oracle (TensorFlow reference not installable offline)" % (n, nx, ny)}
+    if world == 1 and not args.no_hbm_kernels:
+        del out
+        state.clear()
+        ops.blk8_pool_clear()
+        torch.cuda.empty_cache()
+        residual, dst = hbm_kernel_rooflines(h)
 
     # ---------------- the other precision modes, briefly (N=1 only; informational) ----------------
     other = {}
     if world == 1 and args.other_modes:
+        import warnings
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for mode in [m for m in args.other_modes.split(",") if m and m != args.precision]:
-            model.set_precision(mode)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                model.set_precision(mode)
             nst = 1 if mode == "fp32" else 2
             o = model(dev_in)
             torch.cuda.synchronize()
@@ -289,35 +421,251 @@ def run_ours(args):
             ms = e0.elapsed_time(e1) / nst
             nchk = min(B, args.check_samples)
             err = float((o[:nchk].double().cpu() - ref).norm() / ref.norm())
-            other[mode] = {"value": B / (ms / 1000.0), "ms_per_step": ms, "rel_l2_vs_oracle_f64": err, "steps": nst}
+            other[mode] = {"value": B / (ms / 1000.0), "ms_per_step": ms, "rel_l2_vs_oracle_f64": err, "steps": nst,
+                           "compliant": mode in model.COMPLIANT_PRECISIONS}
         model.set_precision(args.precision)
 
-    if world > 1:
-        dist.barrier()
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": "solutions/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"fp32": "f32", "tc": "f16", "tc3": "f16 hi+lo split (3 MMAs), f32 accumulate", "tc2": "f16 + e4m3 correction MMA (K=32), f32 accumulate",
-                                     "mixed": "f16 + e4m3 correction MMA (K=32) in the HPNN, single-pass f16 in the DBCNN, f32 accumulate"}.get(args.precision, args.precision), "data": "synthetic",
-            "config": {"workload": "Poisson_CNN_Legacy forward (HPNN + 4x DBCNN merged), batch %d per GPU, %dx%d grids, pcnn_end_to_end architecture, precision mode %s" % (B, nx, ny, args.precision),
-                       "per_gpu_batch": B, "global_batch": B * world, "grid": [nx, ny], "parallelism": "batch-sharded x%d" % world,
-                       "l2": "inputs+activations per step (%.1f GB) exceed the 126 MB L2" % (B * nx * ny * 4 * 32 / 1e9),
-                       "flop_per_solution": pcnn_flops(nx, ny)},
-            "e2e": {"value": e2e_value, "unit": "solutions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_host.numel() * 4, "steps": e2e_steps},
-            "gpu_launches": int(launches),
-            "host_enqueue_ms_per_step": host_enqueue_ms,
-            "clocks": sampler.result(),
-            "roofline": roofline,
-            "cpu_baseline": cpu_baseline,
-            "accuracy": acc,
-            "other_modes": other,
-            "model_tflops": value / world * pcnn_flops(nx, ny) / 1e12,
-            "frac_of_bf16_sustained_peak": value / world * pcnn_flops(nx, ny) / 1e12 / peaks["tflops"],
-        }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    line = {
+        "metric": METRIC, "value": value, "unit": "solutions/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": {"fp32": "f32", "tc": "f16", "tc3": "f16 hi+lo split (3 MMAs), f32 accumulate", "tc2": "f16 + e4m3 correction MMA (K=32), f32 accumulate",
+                                 "mixed": "f16 + e4m3 correction MMA (K=32) in the HPNN, single-pass f16 in the DBCNN, f32 accumulate"}.get(args.precision, args.precision), "data": "synthetic",
+        "config": {"workload": "Poisson_CNN_Legacy forward (HPNN + 4x DBCNN merged), batch %d per GPU, %dx%d grids, pcnn_end_to_end architecture, precision mode %s" % (B, nx, ny, args.precision),
+                   "baseline_config": 2, "per_gpu_batch": B, "global_batch": B * world, "grid": [nx, ny], "parallelism": "batch-sharded x%d" % world,
+                   "l2": "inputs+activations per step (%.1f GB) exceed the 126 MB L2" % (B * nx * ny * 4 * 32 / 1e9),
+                   "flop_per_solution": pcnn_flops(nx, ny)},
+        "e2e": {"value": e2e_value, "unit": "solutions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_host.numel() * 4, "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": sampler.result(),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "accuracy": acc,
+        "residual": residual,
+        "dst": dst,
+        "other_modes": other,
+        "model_tflops": value / world * pcnn_flops(nx, ny) / 1e12,
+        "frac_of_bf16_sustained_peak": value / world * pcnn_flops(nx, ny) / 1e12 / peaks["tflops"],
+    }
+    h.finish(line)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_config1(args):
+    """BASELINE configs[0]: the reference's own CPU-runnable case on the GPU, next to the CPU oracle on the same inputs."""
+    from poisson_cnn_b200 import _lib
+    from poisson_cnn_b200.synthetic import make_problem
+    from oracle import poisson_oracle as O
+    h = Harness(args)
+    hp_cfg, db_cfg, w = model_weights("hpnn_smalldomain")
+    m = build_hpnn(h.device, args.precision, hp_cfg, w)
+    p = make_problem(4, 64, 64, seed=1001, magnitudes=False)
+    rhs, dx = p["rhs"].cuda(), p["dx"].cuda()
+    state = {}
+
+    def step():
+        state["out"] = m([rhs, dx])
+    sampler = ClockSampler(h.local); sampler.start()
+    l0 = _lib.lib.pcnn_launch_count()
+    ms = h.time_steps(step, args.steps, args.warmup)
+    launches = _lib.lib.pcnn_launch_count() - l0
+    sampler.stop_flag = True; sampler.join(2)
+    hr, hd = p["rhs"].pin_memory(), p["dx"].pin_memory()
+
+    def e2e():
+        o = m([hr.to(h.device, non_blocking=True), hd.to(h.device, non_blocking=True)])
+        state["host"] = o.cpu()
+    e2e_ms = h.time_steps(e2e, args.steps, 1)
+    with torch.no_grad():
+        ref = O.hpnn_forward(hp_cfg, w, p["rhs"].double(), p["dx"].double(), "hpnn/")
+    err = float((state["out"].double().cpu() - ref).norm() / ref.norm())
+    use_all_host_threads()
+    val, n, threads = oracle_throughput(lambda: O.hpnn_forward(hp_cfg, w, p["rhs"], p["dx"], "hpnn/"), min(args.cpu_budget_s, 10.0))
+    value = 4 * h.world * args.steps / (ms / 1e3)
+    line = {"metric": "64x64 HPNN solutions/sec (Homogeneous_Poisson_NN_Legacy forward)", "value": value, "unit": "solutions/s",
+            "n_gpus": h.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": CONFIGS[1] + ", precision mode " + args.precision, "baseline_config": 1, "l2": "latency-bound: 4 samples, ~170 dependent launches"},
+            "e2e": {"value": 4 * h.world * args.steps / (e2e_ms / 1e3), "unit": "solutions/s", "h2d_bytes_per_step": 4 * 64 * 64 * 4 + 16, "d2h_bytes_per_step": 4 * 64 * 64 * 4},
+            "gpu_launches": int(launches), "clocks": sampler.result(),
+            "roofline": {"bound": "tensor", "achieved": value / h.world * 64 * 64 * FLOP_HPNN_PER_PIXEL / 1e12, "peak": h.peaks["tflops"], "unit": "TFLOP/s",
+                         "frac": value / h.world * 64 * 64 * FLOP_HPNN_PER_PIXEL / 1e12 / h.peaks["tflops"], "traffic": None,
+                         "note": "whole-model algorithmic FLOPs; at batch 4 the pass is launch-latency-bound, not tensor-bound"},
+            "cpu_baseline": {"value": val * 4, "unit": "solutions/s", "cores": threads, "kind": "port", "sample": "%d forwards of the same 4x64x64 batch, torch-CPU fp32 oracle" % n},
+            "accuracy": {"rel_l2_vs_oracle_f64": err, "samples_checked": 4}}
+    h.finish(line)
+
+
+def _timed_forward_set(h, jobs, steps, warmup):
+    """jobs: list of (name, callable, solutions_per_call).  Times the whole set per step and each job on its own."""
+    def step():
+        for _, fn, _ in jobs:
+            fn()
+    ms = h.time_steps(step, steps, warmup)
+    per = {}
+    for name, fn, n in jobs:
+        t = h.time_steps(fn, max(1, steps // 2), 0)
+        per[name] = {"ms": t / max(1, steps // 2), "solutions_local": n}
+    return ms, per
+
+
+def run_config3(args):
+    """Variable-aspect grids, Dirichlet PCNN + homogeneous-Neumann HPNN, B per shape split over the ranks (strong scaling)."""
+    from poisson_cnn_b200 import _lib
+    from poisson_cnn_b200.sharding import shard_bounds, bucket_by_shape
+    from poisson_cnn_b200.synthetic import make_problem
+    h = Harness(args)
+    model, (hp_cfg, db_cfg, w) = build_model(h.device, args.precision)
+    hp_n = dict(hp_cfg, bc_type="neumann")
+    neumann = build_hpnn(h.device, {"mixed": "tc2"}.get(args.precision, args.precision), hp_n, w)
+    B = args.batch if args.batch != 256 else 128
+    shapes = [(384, 128)] * B + [(512, 256)] * B + [(200, 300)] * B
+    jobs, total, flops = [], 0, 0.0
+    for (nx, ny), idx in bucket_by_shape(shapes).items():
+        lo, hi = shard_bounds(len(idx), h.world, h.rank)
+        nloc = hi - lo
+        total += len(idx) * 2
+        flops += len(idx) * (pcnn_flops(nx, ny) + nx * ny * FLOP_HPNN_PER_PIXEL)
+        if nloc == 0:
+            continue
+        base = make_problem(min(nloc, 8), nx, ny, seed=3000 + nx + h.rank)
+        reps = -(-nloc // base["rhs"].shape[0])
+        inp = [base[k].repeat(reps, *([1] * (base[k].dim() - 1)))[:nloc].contiguous().to(h.device) for k in KEYS]
+        jobs.append(("dirichlet_pcnn_%dx%d" % (nx, ny), (lambda inp=inp: model(inp)), nloc))
+        jobs.append(("neumann_hpnn_%dx%d" % (nx, ny), (lambda inp=inp: neumann([inp[0], inp[5]])), nloc))
+    sampler = ClockSampler(h.local); sampler.start()
+    l0 = _lib.lib.pcnn_launch_count()
+    ms, per = _timed_forward_set(h, jobs, args.steps, args.warmup)
+    launches = _lib.lib.pcnn_launch_count() - l0
+    sampler.stop_flag = True; sampler.join(2)
+    value = total * args.steps / (ms / 1e3)
+    for name, d in per.items():
+        d["solutions_per_s_this_rank"] = d["solutions_local"] / d["ms"] * 1e3
+    line = {"metric": "variable-aspect Poisson solutions/sec (384x128, 512x256, 200x300; Dirichlet Poisson_CNN + Neumann HPNN)", "value": value,
+            "unit": "solutions/s", "n_gpus": h.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": CONFIGS[3] + ", precision mode " + args.precision, "baseline_config": 3, "batch_per_shape": B,
+                       "solutions_per_step": total, "parallelism": "each shape bucket split over %d ranks" % h.world,
+                       "l2": "activations per step far exceed the 126 MB L2"},
+            "gpu_launches": int(launches), "clocks": sampler.result(), "per_job_rank0": per,
+            "roofline": {"bound": "tensor", "achieved": flops * args.steps / (ms / 1e3) / 1e12 / h.world, "peak": h.peaks["tflops"], "unit": "TFLOP/s",
+                         "frac": flops * args.steps / (ms / 1e3) / 1e12 / h.world / h.peaks["tflops"], "traffic": None,
+                         "note": "whole-workload algorithmic conv FLOPs per GPU (not a single kernel)"}}
+    h.finish(line)
+
+
+def run_config4(args):
+    """1024^2 and 2048^2, batch 16 split over the ranks, forward + 5-point residual (strong scaling)."""
+    from poisson_cnn_b200 import _lib
+    from poisson_cnn_b200.losses import linear_operator_loss
+    from poisson_cnn_b200.sharding import shard_bounds
+    from poisson_cnn_b200.synthetic import make_problem
+    h = Harness(args)
+    model, _ = build_model(h.device, args.precision)
+    loss = linear_operator_loss(3, 2, ndims=2)
+    B = args.batch if args.batch != 256 else 16
+    jobs, state, flops = [], {}, 0.0
+    grids = [int(g) for g in args.grids.split(",")] if args.grids else [1024, 2048]
+    for n in grids:
+        lo, hi = shard_bounds(B, h.world, h.rank)
+        nloc = hi - lo
+        flops += B * pcnn_flops(n, n)
+        if nloc == 0:
+            continue
+        base = make_problem(1, n, n, seed=4000 + n + h.rank)
+        inp = [base[k].repeat(nloc, *([1] * (base[k].dim() - 1))).contiguous().to(h.device) for k in KEYS]
+        gs = torch.cat([inp[5], inp[5]], 1)
+
+        def fn(inp=inp, gs=gs, n=n):
+            out = model(inp)
+            state[n] = loss.per_sample_squared_sums(inp[0], out, gs)
+        jobs.append(("forward+residual_%dx%d" % (n, n), fn, nloc))
+    sampler = ClockSampler(h.local); sampler.start()
+    l0 = _lib.lib.pcnn_launch_count()
+    ms, per = _timed_forward_set(h, jobs, args.steps, args.warmup)
+    launches = _lib.lib.pcnn_launch_count() - l0
+    sampler.stop_flag = True; sampler.join(2)
+    for name, d in per.items():
+        d["solutions_per_s_this_rank"] = d["solutions_local"] / d["ms"] * 1e3
+    total = B * len(grids)
+    res = {str(n): float(v.sum().sqrt()) for n, v in state.items()}
+    line = {"metric": "large-grid Poisson solutions/sec (%s, forward + 5-point residual)" % " and ".join("%dx%d" % (n, n) for n in grids),
+            "value": total * args.steps / (ms / 1e3), "unit": "solutions/s", "n_gpus": h.world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.precision,
+            "data": "synthetic",
+            "config": {"workload": CONFIGS[4] + ", precision mode " + args.precision, "baseline_config": 4, "batch": B, "grids": grids,
+                       "parallelism": "batch of %d split over %d ranks (%d per rank)" % (B, h.world, -(-B // h.world)), "l2": "one 32-channel 2048^2 activation is 1.1 GB"},
+            "gpu_launches": int(launches), "clocks": sampler.result(), "per_job_rank0": per, "residual_l2_rank0": res,
+            "roofline": {"bound": "tensor", "achieved": flops * args.steps / (ms / 1e3) / 1e12 / h.world, "peak": h.peaks["tflops"], "unit": "TFLOP/s",
+                         "frac": flops * args.steps / (ms / 1e3) / 1e12 / h.world / h.peaks["tflops"], "traffic": None,
+                         "note": "whole-workload algorithmic conv FLOPs per GPU (not a single kernel)"}}
+    h.finish(line)
+
+
+def run_config5(args):
+    """DST ground-truth solve vs CNN surrogate, 64^2 .. 2048^2: throughput of both and the DST's own discrete residual."""
+    from poisson_cnn_b200 import dataset, _lib
+    from poisson_cnn_b200.losses import linear_operator_loss
+    from poisson_cnn_b200.sharding import shard_bounds
+    from poisson_cnn_b200.solvers import dst_poisson_solve
+    h = Harness(args)
+    dev = h.device
+    model, _ = build_model(dev, args.precision)
+    loss = linear_operator_loss(3, 2, ndims=2)
+    rows, tot_solutions, tot_ms = [], 0, 0.0
+    sampler = ClockSampler(h.local); sampler.start()
+    l0 = _lib.lib.pcnn_launch_count()
+    for n, B in ((64, 256), (128, 256), (256, 256), (512, 64), (1024, 16), (2048, 16)):
+        lo, hi = shard_bounds(B, h.world, h.rank)
+        nloc = max(hi - lo, 1)
+        gen = torch.Generator(device=dev).manual_seed(1005 + h.rank)
+        rhs = dataset.generate_random_RHS(nloc, [n, n], smoothness=6, max_magnitude=1.0, device=dev, generator=gen)
+        bnd = dataset.generate_random_boundaries([n, n], batch_size=nloc, smoothness=5, max_magnitude={k: 1.0 for k in ("left", "top", "right", "bottom")},
+                                                 return_with_expanded_dims=True, device=dev, generator=gen)
+        dx = 5e-3 + (5e-2 - 5e-3) * torch.rand((nloc, 1), device=dev, generator=gen)
+        inp = [rhs, bnd["left"], bnd["top"], bnd["right"], bnd["bottom"], dx]
+        row = {"grid": n, "batch": B, "batch_this_rank": nloc}
+        st = {}
+        for name, kw in (("dst_fft_f64", {}), ("dst_fft_f32", {"dtype": torch.float32}), ("dst_gemm_f64", {"method": "gemm"})):
+            if name == "dst_gemm_f64" and n > 1024:
+                continue
+
+            def fn(kw=kw):
+                st["u"] = dst_poisson_solve(rhs, bnd, dx, **kw)
+            ms = h.time_steps(fn, args.steps, 1) / args.steps
+            gs = torch.cat([dx, dx], 1)
+            r = float(loss(rhs, st["u"], gs)) ** 0.5 / float((rhs[..., 1:-1, 1:-1] ** 2).mean()) ** 0.5
+            row[name] = {"ms": ms, "solutions_per_s": B / ms * 1e3, "gbs_at_8B_per_pt": B * n * n * 8 / ms / 1e6 / h.world,
+                         "frac_of_hbm_peak": B * n * n * 8 / ms / 1e6 / h.world / h.peaks["hbm_gbs"], "discrete_residual_rel": r}
+            if name == "dst_fft_f64":
+                u64 = st["u"]
+            elif name == "dst_fft_f32":
+                row[name]["rel_l2_vs_f64"] = float((st["u"].double() - u64.double()).norm() / u64.double().norm())
+        try:
+            def fwd():
+                st["cnn"] = model(inp)
+            ms = h.time_steps(fwd, args.steps, 1) / args.steps
+            row["cnn"] = {"ms": ms, "solutions_per_s": B / ms * 1e3,
+                          "rel_l2_vs_dst": float((st["cnn"].double() - u64.double()).norm() / u64.double().norm()),
+                          "note": "seeded synthetic weights (no trained weights ship with the reference): the distance to the DST solution exercises the harness, not the method"}
+            tot_solutions += B
+            tot_ms += ms
+        except Exception as e:      # 64^2: the shipped Scaling config has empty SPP bins on tiny maps (NaN in the reference too)
+            row["cnn"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:100])}
+        rows.append(row)
+        del rhs, bnd, inp, st
+        torch.cuda.empty_cache()
+    launches = _lib.lib.pcnn_launch_count() - l0
+    sampler.stop_flag = True; sampler.join(2)
+    big = rows[-1]["dst_fft_f64"]
+    line = {"metric": "2048x2048 DST ground-truth solutions/sec (config 5 sweep; CNN throughput per grid in `sweep`)", "value": big["solutions_per_s"],
+            "unit": "solutions/s", "n_gpus": h.world, "steps": args.steps, "warmup": 1, "ms_per_step": big["ms"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64 (DST), %s (CNN)" % args.precision, "data": "synthetic (generated on the GPU)",
+            "config": {"workload": CONFIGS[5], "baseline_config": 5, "l2": "grids above 512^2 exceed L2 per batch"},
+            "gpu_launches": int(launches), "clocks": sampler.result(), "sweep": rows,
+            "roofline": {"bound": "hbm", "achieved": big["gbs_at_8B_per_pt"], "peak": h.peaks["hbm_gbs"], "unit": "GB/s", "frac": big["frac_of_hbm_peak"],
+                         "traffic": None, "passes": int(_lib.lib.pcnn_dst_fft_passes()),
+                         "note": "algorithmic 8 B per grid point (read f, write u); the solve makes 3 passes with a float64 intermediate: 40 B per point"}}
+    h.finish(line)
 
 
 def main():
@@ -326,21 +674,24 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="samples per GPU per step (BASELINE configs[1]: 256)")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs[i-1]: " + "; ".join("%d = %s" % kv for kv in CONFIGS.items()))
+    ap.add_argument("--batch", type=int, default=256, help="config 2: samples per GPU per step (256); configs 3/4: total batch per shape (default 128 / 16)")
     ap.add_argument("--grid", type=int, default=256)
+    ap.add_argument("--grids", default="", help="config 4: comma list of square grid sizes (default 1024,2048)")
     ap.add_argument("--precision", default=os.environ.get("PCNN_PRECISION", "mixed"), choices=["fp32", "tc", "tc2", "tc3", "mixed"],
-                    help="mixed (default): tc2 in the HPNN + single-pass tc in the DBCNN, holds the 2e-3 budget with a 6x margin; tc2: fp16 main MMA + one e4m3 correction MMA everywhere; tc3: hi/lo fp16 split; tc: single FP16 pass; fp32: strict CUDA-core path")
+                    help="mixed (default): tc2 in the HPNN + single-pass tc in the DBCNN, holds the 2e-3 budget with a 6x margin; tc2: fp16 main MMA + one e4m3 correction MMA everywhere; tc3: hi/lo fp16 split; tc: single FP16 pass (NOT compliant: 4.4e-3); fp32: strict CUDA-core path")
     ap.add_argument("--other-modes", default="tc2,tc,tc3,fp32", help="comma list of extra precision modes timed briefly at N=1 (reported under other_modes)")
     ap.add_argument("--check-samples", type=int, default=2)
     ap.add_argument("--cpu-budget-s", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hbm-kernels", action="store_true", help="skip the residual / DST roofline measurements of the config-2 line")
     ap.add_argument("--roofline-kernel", type=lambda s: tuple(int(v) for v in s.split(",")), default=(32, 32, 15),
                     help="Cin,Cout,k of the conv whose launches are timed for the roofline (dominant: 32->32 k15)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_ours(args)
+        {1: run_config1, 2: run_config2, 3: run_config3, 4: run_config4, 5: run_config5}[args.config](args)
 
 
 if __name__ == "__main__":
