@@ -74,7 +74,7 @@ template <> __device__ __forceinline__ double2 ldgc<double2>(const double2* p) {
 template <typename C, int LR>
 __device__ __forceinline__ void fft_stage(C* s, int tid, int q, int lp, const C* __restrict__ tw) {
     constexpr int R = 1 << LR, NB = 8 / R;
-    const int NT = 1 << (q - 3), Tn = 1 << (q - LR), p = 1 << lp, lstep = q - lp - LR;
+    const int NT = 1 << (q - 3), Tn = 1 << (q - LR), p = 1 << lp;
     C v[8];
     int jout[NB];
 #pragma unroll
@@ -86,8 +86,11 @@ __device__ __forceinline__ void fft_stage(C* s, int tid, int q, int lp, const C*
 #pragma unroll
         for (int t = 0; t < R; ++t) u[t] = s[spos(i + t * Tn)];
         if (lp > 0) {
+            // per-stage table [t-1][k] (k < p) at offset p - 8: lanes with consecutive k read consecutive entries (a gather
+            // from one exp(-2 pi i j/L) table touched up to 32 cache lines per warp load and ran the FFT at L1-tag rate)
+            const C* tws = tw + (p - 8) + k;
 #pragma unroll
-            for (int t = 1; t < R; ++t) u[t] = cmul(u[t], ldgc(tw + ((t * k) << lstep)));
+            for (int t = 1; t < R; ++t) u[t] = cmul(u[t], ldgc(tws + ((t - 1) << lp)));
         }
         dftR<C, R>(u);
 #pragma unroll
@@ -113,7 +116,7 @@ __device__ __forceinline__ void fft_fwd(C* s, int tid, int q, const C* __restric
 
 template <typename T>
 struct DstPlan {                  // device tables of one transform length n (built by dst_plan_kernel)
-    const typename Cx<T>::t* tw;  // [L]   exp(-2 pi i k / L)
+    const typename Cx<T>::t* tw;  // [L]   per-stage twiddle tables (dst_twiddle_kernel)
     const typename Cx<T>::t* bh;  // [L]   FFT(conj chirp, wrapped) / L
     const typename Cx<T>::t* ch;  // [n+1] chirp c_m = exp(i pi m^2 / (2(n+1)))
     const double* lam;            // [n]   2 - 2 cos(k pi / (n+1)), k = 1..n
@@ -179,15 +182,24 @@ __global__ void dst_plan_kernel(const typename Cx<T>::t* __restrict__ tw, typena
     }
 }
 
-// the twiddle table, in its own launch: the FFT of the plan kernel reads it through the read-only data path, which is only
-// coherent across kernel boundaries
+// The twiddle tables, in their own launch (the FFT of the plan kernel reads them through the read-only data path, which is
+// only coherent across kernel boundaries).  Stage with p = 2^lp sub-transforms already merged (lp = 3, 6, ...) and radix R
+// (8, or 2 / 4 for the last stage) owns entries [p - 8, p - 8 + (R-1) p): tw[p - 8 + (t-1) p + k] = exp(-2 pi i t k / (p R)).
+// Total <= L entries.
 template <typename T>
-__global__ void dst_twiddle_kernel(typename Cx<T>::t* tw, int L) {
+__global__ void dst_twiddle_kernel(typename Cx<T>::t* tw, int q) {
     using C = typename Cx<T>::t;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < L; k += gridDim.x * blockDim.x) {
-        double sn, cs;
-        sincospi(-2.0 * (double)k / (double)L, &sn, &cs);
-        tw[k] = cmk<C>((T)cs, (T)sn);
+    const int a = q / 3, r = q - 3 * a;
+    for (int lp = 3; lp <= 3 * a; lp += 3) {
+        const int LR = (lp < 3 * a) ? 3 : r;
+        if (LR == 0) break;
+        const int p = 1 << lp, R = 1 << LR;
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < (R - 1) * p; e += gridDim.x * blockDim.x) {
+            const int t = e / p + 1, k = e - (t - 1) * p;
+            double sn, cs;
+            sincospi(-2.0 * (double)((long long)t * k) / (double)((long long)p * R), &sn, &cs);
+            tw[p - 8 + e] = cmk<C>((T)cs, (T)sn);
+        }
     }
 }
 
@@ -343,7 +355,7 @@ static int plan_init(void* plan, int n, cudaStream_t st) {
     DstPlan<T> p = plan_view<T>(plan, n);
     const int L = 1 << p.q, NT = L / 8;
     const size_t smem = (size_t)(L + L / 8) * sizeof(C);
-    dst_twiddle_kernel<T><<<ceil_div(L, 256), 256, 0, st>>>(const_cast<C*>(p.tw), L);
+    dst_twiddle_kernel<T><<<ceil_div(L, 256), 256, 0, st>>>(const_cast<C*>(p.tw), p.q);
     PCNN_CHECK_LAUNCH();
     PCNN_CHECK_CUDA(cudaFuncSetAttribute(dst_plan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dst_plan_kernel<T><<<1, NT, smem, st>>>(p.tw, const_cast<C*>(p.bh), const_cast<C*>(p.ch),

@@ -266,7 +266,7 @@ def test_models_tc_mode_vs_oracle():
     # is only that the kernels work (sane error); compliance is carried by tc2 / tc3 / mixed (tests below, test_gpu_round2).
     assert "tc" not in model.hpnn.COMPLIANT_PRECISIONS and "tc" in model.dbcnn.COMPLIANT_PRECISIONS
     assert e_hp < 1e-2
-    with pytest.warns(UserWarning, match="outside the 2e-3"):
+    with pytest.warns(UserWarning, match="(?i)outside the 2e-3"):
         model.hpnn.set_precision("tc")
 
 
