@@ -297,9 +297,8 @@ def hbm_kernel_rooflines(h, B2048=16, iters=10):
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / max(1, iters // 3)
             gbs = B * n * n * 8 / ms / 1e6
-            tb = 8 if name == "fft_f64" else 4
             dst["%s_%s" % (name, tag)] = {"ms": ms, "solutions_per_s": B / ms * 1e3, "gbs_at_8B_per_pt": gbs, "frac_of_hbm_peak": gbs / peak,
-                                          "passes": int(_lib.lib.pcnn_dst_fft_passes()), "actual_bytes_per_pt": 8 + 4 * tb}
+                                          "passes": int(_lib.lib.pcnn_dst_fft_passes()), "actual_bytes_per_pt": 56}
         del u, f, bc
     res["peak_gbs"] = dst["peak_gbs"] = peak
     res["algorithmic_bytes_per_pt"] = dst["algorithmic_bytes_per_pt"] = 8
@@ -664,7 +663,7 @@ def run_config5(args):
             "gpu_launches": int(launches), "clocks": sampler.result(), "sweep": rows,
             "roofline": {"bound": "hbm", "achieved": big["gbs_at_8B_per_pt"], "peak": h.peaks["hbm_gbs"], "unit": "GB/s", "frac": big["frac_of_hbm_peak"],
                          "traffic": None, "passes": int(_lib.lib.pcnn_dst_fft_passes()),
-                         "note": "algorithmic 8 B per grid point (read f, write u); the solve makes 3 passes with a float64 intermediate: 40 B per point"}}
+                         "note": "algorithmic 8 B per grid point (read f, write u); the solve makes 3 passes (DST rows, tridiagonal columns, DST rows) with a float64 intermediate: 56 B per point"}}
     h.finish(line)
 
 

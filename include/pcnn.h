@@ -171,21 +171,22 @@ int pcnn_dst_solve(const float* rhs, const float* left, const float* top, const 
                    const float* bottom, const float* dx, const double* sx, const double* sy,
                    double* work, float* out, int B, int nx, int ny, void* stream);
 
-/* The same solve with every 1-D DST-I done as a Bluestein chirp-z transform on power-of-two FFTs in shared memory
- * (csrc/dst_fft.cu): O(N^2 log N) work and three passes over the grid (rows, columns in place, rows) instead of four
- * dense O(N^3) sine-matrix products -- HBM-bound like an FFT, for ANY grid size (N-1 = 255, 1023, 2047 are not FFT-friendly).
- * A plan holds the device tables of one interior length n = N-2 (FFT twiddles, spectrum of the conjugate chirp, chirp,
- * eigenvalues): pcnn_dst_fft_plan_bytes bytes, filled once by pcnn_dst_fft_plan_init; plan_x is for n = nx-2, plan_y for
- * n = ny-2 (the same buffer may be passed twice when nx == ny).  use_double selects the arithmetic and the type of the
- * intermediate grid `work` (pcnn_dst_fft_workspace_bytes): 1 = float64 like the reference's solver, 0 = float32.
- * 3 <= nx, ny <= 2050.  pcnn_dst_fft_passes() = full-grid passes made (3), reported by bench.py next to the 8 B/point figure. */
+/* The same solve in O(N^2 log N): DST-I along y for every row (Bluestein chirp-z transform on power-of-two FFTs in shared
+ * memory, so ANY grid size works: N-1 = 255, 1023, 2047 are not FFT-friendly), then -- the system having decoupled per y-mode
+ * into constant-coefficient tridiagonal systems along x -- one float64 Thomas solve per (sample, mode), then the inverse DST
+ * along y (csrc/dst_fft.cu).  Three full-grid passes (4 launches) instead of four dense O(N^3) sine-matrix products.
+ * A plan holds the device tables of the interior row length n = ny-2 (FFT twiddles, spectrum of the conjugate chirp, chirp,
+ * eigenvalues): pcnn_dst_fft_plan_bytes bytes, filled once by pcnn_dst_fft_plan_init.  use_double selects the FFT arithmetic
+ * (1 = float64 like the reference's solver, 0 = float32); the intermediate grid and the tridiagonal solves are always
+ * float64.  work: pcnn_dst_fft_workspace_bytes.  nx >= 3, 3 <= ny <= 2050.  pcnn_dst_fft_passes() = full-grid passes made
+ * (3), reported by bench.py next to the 8 B/point figure. */
 size_t pcnn_dst_fft_plan_bytes(int n, int use_double);
 int pcnn_dst_fft_plan_init(void* plan, int n, int use_double, void* stream);
-size_t pcnn_dst_fft_workspace_bytes(int B, int nx, int ny, int use_double);
+size_t pcnn_dst_fft_workspace_bytes(int B, int nx, int ny);
 int pcnn_dst_fft_passes(void);
 int pcnn_dst_solve_fft(const float* rhs, const float* left, const float* top, const float* right,
-                       const float* bottom, const float* dx, void* plan_x, void* plan_y, void* work,
-                       float* out, int B, int nx, int ny, int use_double, void* stream);
+                       const float* bottom, const float* dx, void* plan_y, void* work, float* out, int B,
+                       int nx, int ny, int use_double, void* stream);
 
 /* Fused 1-D convolution stack (csrc/boundary_stack.cu): n_layers Conv1D layers (Keras kernels [k][Cin][Cout],
  * odd k <= 19, <= 28 channels) applied back to back to every signal of in [B][Cin0][n], all activations staying in

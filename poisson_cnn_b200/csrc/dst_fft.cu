@@ -13,12 +13,16 @@
 // with 8 points in registers per thread, in place (all reads, barrier, all writes), index padding idx + idx/8 makes both the
 // strided reads and the scattered writes bank-conflict-free for 8- and 16-byte elements.
 //
-// Three passes over the grid (the O(N^3) sine-matrix GEMM form in checks.cu made 4 passes of dense GEMMs):
-//   P1 rows   : b = -dx^2 f + adjacent Dirichlet values (built on the fly), DST along y      f (4 B) -> T
-//   P2 columns: DST along x, multiply by norm/(lam_x+lam_y), DST along x, in place            T -> T
-//   P3 rows   : DST along y, write u (fp32) and the Dirichlet ring                             T -> u (4 B)
-// T is double (default: the reference solves in float64) or float.  Algorithmic bytes: 8 B per grid point; actual traffic
-// 8 + 4*sizeof(T) = 40 B (double) or 24 B (float) per point.
+// Passes over the grid (the O(N^3) sine-matrix GEMM form in checks.cu made 4 passes of dense GEMMs):
+//   P1 rows   : b = -dx^2 f + adjacent Dirichlet values (built on the fly), DST along y        f (4 B) -> T (8 B)
+//   P2 columns: after the y-transform the system decouples per y-mode k into constant-coefficient tridiagonal systems
+//               -u[i-1] + (2 + lam_k) u[i] - u[i+1] = T[i][k] along x: Thomas algorithm, one thread per (sample, k),
+//               coalesced across k, float64 (condition ~1e6 for the lowest modes) -- "Fourier analysis + tridiagonal
+//               solve" (FACR(0)); two sweeps over T in place instead of two more DSTs per column       T -> T (2 x 16 B)
+//   P3 rows   : DST along y, write u (fp32) and the Dirichlet ring                               T (8 B) -> u (4 B)
+// The FFT arithmetic is double (default: the reference solves in float64) or float; T and the tridiagonal solve are always
+// double.  Algorithmic bytes: 8 B per grid point; actual traffic 8 + 16 + 32 = 56 B per point plus the L2-resident table
+// of elimination coefficients, in 4 kernel launches ("passes": 3 full-grid transform/solve passes).
 #include "pcnn_common.cuh"
 
 namespace pcnn {
@@ -208,10 +212,10 @@ __global__ void dst_twiddle_kernel(typename Cx<T>::t* tw, int q) {
 // MODE 1: x_j = T[b][i-1][j-1] -> out[b][i][k] = S_k (fp32) and the Dirichlet ring (write order of multigrid.py:145-148:
 //         top/bottom first, then left/right, i.e. the corners hold left/right values)
 template <typename T, int MODE>
-__global__ void __launch_bounds__(512) dst_rows_kernel(const float* __restrict__ rhs, const float* __restrict__ left,
+__global__ void __launch_bounds__(512, 2) dst_rows_kernel(const float* __restrict__ rhs, const float* __restrict__ left,
                                                        const float* __restrict__ top, const float* __restrict__ right,
                                                        const float* __restrict__ bottom, const float* __restrict__ dx,
-                                                       T* __restrict__ tbuf, float* __restrict__ out, int B, int nx, int ny,
+                                                       double* __restrict__ tbuf, float* __restrict__ out, int B, int nx, int ny,
                                                        DstPlan<T> pl) {
     using C = typename Cx<T>::t;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(512) dst_rows_kernel(const float* __restrict__
                 if (i == 1) v += (T)left[(long long)b * ny + j];
                 if (i == mx) v += (T)right[(long long)b * ny + j];
             } else {
-                v = tbuf[((long long)b * mx + (i - 1)) * my + (j - 1)];
+                v = (T)tbuf[((long long)b * mx + (i - 1)) * my + (j - 1)];
             }
             const C c = ldgc(pl.ch + j);
             a = cmk<C>(v * c.x, v * c.y);
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(512) dst_rows_kernel(const float* __restrict__
         const int k = tid + m * NT;
         if (k >= 1 && k <= my) {
             const T v = dst_value<T>(s, k, pl);
-            if (MODE == 0) tbuf[((long long)b * mx + (i - 1)) * my + (k - 1)] = v;
+            if (MODE == 0) tbuf[((long long)b * mx + (i - 1)) * my + (k - 1)] = (double)v;
             else out[((long long)b * nx + i) * ny + k] = (float)v;
         }
     }
@@ -267,54 +271,62 @@ __global__ void __launch_bounds__(512) dst_rows_kernel(const float* __restrict__
     }
 }
 
-// ---- P2: lines along x (stride my), F adjacent columns per CTA, forward DST, eigenvalue division, inverse DST, in place
-template <typename T>
-__global__ void __launch_bounds__(512) dst_cols_kernel(T* __restrict__ tbuf, int mx, int my, DstPlan<T> plx,
-                                                       const double* __restrict__ lamy, double norm) {
-    using C = typename Cx<T>::t;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int q = plx.q, L = 1 << q, NT = L >> 3, Lp = L + (L >> 3);
-    const int lf = 0 + (31 - __clz((int)blockDim.x)) - (q - 3);      // log2 F
-    const int F = 1 << lf;
-    const int f = threadIdx.x >> (q - 3), tid = threadIdx.x & (NT - 1);
-    C* sall = reinterpret_cast<C*>(smem_raw);
-    C* s = sall + (size_t)f * Lp;
-    const int k0 = blockIdx.x * F;
-    T* base = tbuf + (long long)blockIdx.y * mx * my;
-    // zero what the loader below does not write: idx = 0 and idx > mx (and whole transforms of columns beyond my)
-    const bool col_live = (k0 + f) < my;
+// ---- P2: tridiagonal solves along x, one thread per (sample, y-mode k); consecutive threads own consecutive k, so every
+// row access is one coalesced segment.  System per column: -u[i-1] + d u[i] - u[i+1] = r[i], d = 2 + lam_y[k]
+// (from (lam_x + lam_y) u^ = b^ with the x-direction left in physical space).  Thomas:
+//   forward   inv_i = 1 / (d + c_{i-1}),  c_i = -inv_i,  r'_i = (r_i + r'_{i-1}) inv_i          (c_0 = r'_0 = 0)
+//   backward  u_n = r'_n,  u_i = r'_i - c_i u_{i+1}
+// The elimination coefficients c_i depend on (i, k) only: the threads of sample 0 store them once per call ([mx][my]
+// doubles, L2-resident for the backward sweep of every sample).  `scale` = the inverse-DST normalisation 2/(my+1) of P3.
+constexpr int kThomasUnroll = 16;      // independent row loads in flight per thread
+
+__global__ void __launch_bounds__(128) dst_thomas_forward_kernel(double* __restrict__ tbuf, double* __restrict__ ctab,
+                                                                const double* __restrict__ lamy, int mx, int my) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= my) return;
+    const int b = blockIdx.y;
+    double* col = tbuf + (long long)b * mx * my + k;
+    const double d = 2.0 + lamy[k];
+    double c = 0.0, rp = 0.0;
+    for (int i0 = 0; i0 < mx; i0 += kThomasUnroll) {
+        double v[kThomasUnroll];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const int idx = tid + m * NT;
-        if (idx == 0 || idx > mx || !col_live) s[spos(idx)] = cmk<C>((T)0, (T)0);
-    }
-    for (int e = threadIdx.x; e < (mx << lf); e += blockDim.x) {
-        const int i = e >> lf, ff = e & (F - 1);
-        if (k0 + ff < my) {
-            const T v = base[(long long)i * my + k0 + ff];
-            const C c = ldgc(plx.ch + i + 1);
-            sall[(size_t)ff * Lp + spos(i + 1)] = cmk<C>(v * c.x, v * c.y);
+        for (int u = 0; u < kThomasUnroll; ++u) v[u] = (i0 + u < mx) ? col[(long long)(i0 + u) * my] : 0.0;
+#pragma unroll
+        for (int u = 0; u < kThomasUnroll; ++u) {
+            if (i0 + u < mx) {
+                const double inv = 1.0 / (d + c);
+                rp = (v[u] + rp) * inv;
+                c = -inv;
+                col[(long long)(i0 + u) * my] = rp;
+                if (b == 0) ctab[(long long)(i0 + u) * my + k] = c;
+            }
         }
     }
-    __syncthreads();
-    dst_core<T>(s, tid, plx);
-    const double ly = col_live ? lamy[k0 + f] : 1.0;
+}
+
+__global__ void __launch_bounds__(128) dst_thomas_backward_kernel(double* __restrict__ tbuf, const double* __restrict__ ctab,
+                                                                 int mx, int my, double scale) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= my) return;
+    double* col = tbuf + (long long)blockIdx.y * mx * my + k;
+    const double* cc = ctab + k;
+    double un = 0.0;                    // u_{i+1}; the last row has no successor (c_n multiplies nothing)
+    for (int i0 = mx - 1; i0 >= 0; i0 -= kThomasUnroll) {
+        double v[kThomasUnroll], cv[kThomasUnroll];
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const int p = tid + m * NT;
-        C a = cmk<C>((T)0, (T)0);
-        if (p >= 1 && p <= mx && col_live) {
-            const T v = (T)((double)dst_value<T>(s, p, plx) * (norm / (plx.lam[p - 1] + ly)));
-            const C c = ldgc(plx.ch + p);
-            a = cmk<C>(v * c.x, v * c.y);
+        for (int u = 0; u < kThomasUnroll; ++u) {
+            const bool ok = i0 - u >= 0;
+            v[u] = ok ? col[(long long)(i0 - u) * my] : 0.0;
+            cv[u] = ok ? __ldg(cc + (long long)(i0 - u) * my) : 0.0;
         }
-        s[spos(p)] = a;          // same thread reads and overwrites its own entry: no hazard
-    }
-    __syncthreads();
-    dst_core<T>(s, tid, plx);
-    for (int e = threadIdx.x; e < (mx << lf); e += blockDim.x) {
-        const int i = e >> lf, ff = e & (F - 1);
-        if (k0 + ff < my) base[(long long)i * my + k0 + ff] = dst_value<T>(sall + (size_t)ff * Lp, i + 1, plx);
+#pragma unroll
+        for (int u = 0; u < kThomasUnroll; ++u) {
+            if (i0 - u >= 0) {
+                un = (i0 - u == mx - 1) ? v[u] : v[u] - cv[u] * un;
+                col[(long long)(i0 - u) * my] = un * scale;
+            }
+        }
     }
 }
 
@@ -366,33 +378,28 @@ static int plan_init(void* plan, int n, cudaStream_t st) {
 
 template <typename T>
 static int solve(const float* rhs, const float* left, const float* top, const float* right, const float* bottom,
-                 const float* dx, void* plan_x, void* plan_y, void* work, float* out, int B, int nx, int ny, cudaStream_t st) {
+                 const float* dx, void* plan_y, void* work, float* out, int B, int nx, int ny, cudaStream_t st) {
     using C = typename Cx<T>::t;
     const int mx = nx - 2, my = ny - 2;
-    DstPlan<T> px = plan_view<T>(plan_x, mx), py = plan_view<T>(plan_y, my);
-    T* tbuf = reinterpret_cast<T*>(work);
-    const double norm = (2.0 / (mx + 1)) * (2.0 / (my + 1));
-    {   // rows
-        const int NT = 1 << (py.q - 3);
-        const int threads = NT > 256 ? NT : 256, F = threads / NT;
-        const size_t smem = (size_t)threads * 9 * sizeof(C);
-        const long long nlines = (long long)B * mx;
-        const unsigned grid = (unsigned)((nlines + F - 1) / F);
-        PCNN_CHECK_CUDA(cudaFuncSetAttribute(dst_rows_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PCNN_CHECK_CUDA(cudaFuncSetAttribute(dst_rows_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dst_rows_kernel<T, 0><<<grid, threads, smem, st>>>(rhs, left, top, right, bottom, dx, tbuf, out, B, nx, ny, py);
-        PCNN_CHECK_LAUNCH();
-        {   // columns
-            const int NTx = 1 << (px.q - 3);
-            const int thx = NTx > 256 ? NTx : 256, Fx = thx / NTx;
-            const size_t smx = (size_t)thx * 9 * sizeof(C);
-            PCNN_CHECK_CUDA(cudaFuncSetAttribute(dst_cols_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smx));
-            dst_cols_kernel<T><<<dim3((unsigned)ceil_div(my, Fx), (unsigned)B), thx, smx, st>>>(tbuf, mx, my, px, py.lam, norm);
-            PCNN_CHECK_LAUNCH();
-        }
-        dst_rows_kernel<T, 1><<<grid, threads, smem, st>>>(rhs, left, top, right, bottom, dx, tbuf, out, B, nx, ny, py);
-        PCNN_CHECK_LAUNCH();
-    }
+    DstPlan<T> py = plan_view<T>(plan_y, my);
+    double* tbuf = reinterpret_cast<double*>(work);
+    double* ctab = tbuf + (size_t)B * mx * my;
+    const int NT = 1 << (py.q - 3);
+    const int threads = NT > 256 ? NT : 256, F = threads / NT;
+    const size_t smem = (size_t)threads * 9 * sizeof(C);
+    const long long nlines = (long long)B * mx;
+    const unsigned grid = (unsigned)((nlines + F - 1) / F);
+    PCNN_CHECK_CUDA(cudaFuncSetAttribute(dst_rows_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PCNN_CHECK_CUDA(cudaFuncSetAttribute(dst_rows_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dst_rows_kernel<T, 0><<<grid, threads, smem, st>>>(rhs, left, top, right, bottom, dx, tbuf, out, B, nx, ny, py);
+    PCNN_CHECK_LAUNCH();
+    const dim3 tg((unsigned)ceil_div(my, 128), (unsigned)B);
+    dst_thomas_forward_kernel<<<tg, 128, 0, st>>>(tbuf, ctab, py.lam, mx, my);
+    PCNN_CHECK_LAUNCH();
+    dst_thomas_backward_kernel<<<tg, 128, 0, st>>>(tbuf, ctab, mx, my, 2.0 / (my + 1));
+    PCNN_CHECK_LAUNCH();
+    dst_rows_kernel<T, 1><<<grid, threads, smem, st>>>(rhs, left, top, right, bottom, dx, tbuf, out, B, nx, ny, py);
+    PCNN_CHECK_LAUNCH();
     return PCNN_OK;
 }
 
@@ -410,19 +417,19 @@ extern "C" int pcnn_dst_fft_plan_init(void* plan, int n, int use_double, void* s
     return use_double ? plan_init<double>(plan, n, (cudaStream_t)stream) : plan_init<float>(plan, n, (cudaStream_t)stream);
 }
 
-extern "C" size_t pcnn_dst_fft_workspace_bytes(int B, int nx, int ny, int use_double) {
+extern "C" size_t pcnn_dst_fft_workspace_bytes(int B, int nx, int ny) {
     if (B <= 0 || nx < 3 || ny < 3) return 0;
-    return (size_t)B * (nx - 2) * (ny - 2) * (use_double ? sizeof(double) : sizeof(float));
+    return ((size_t)B + 1) * (nx - 2) * (ny - 2) * sizeof(double);      // T for every sample + one table of elimination coefficients
 }
 
 extern "C" int pcnn_dst_fft_passes(void) { return 3; }
 
 extern "C" int pcnn_dst_solve_fft(const float* rhs, const float* left, const float* top, const float* right,
-                                  const float* bottom, const float* dx, void* plan_x, void* plan_y, void* work,
-                                  float* out, int B, int nx, int ny, int use_double, void* stream) {
-    PCNN_CHECK_ARG(rhs && left && top && right && bottom && dx && plan_x && plan_y && work && out, "dst_solve_fft: null pointer");
-    PCNN_CHECK_ARG(B > 0 && B <= 65535 && nx >= 3 && ny >= 3 && nx <= 2050 && ny <= 2050, "dst_solve_fft: needs 3 <= nx, ny <= 2050 and B <= 65535");
+                                  const float* bottom, const float* dx, void* plan_y, void* work, float* out, int B,
+                                  int nx, int ny, int use_double, void* stream) {
+    PCNN_CHECK_ARG(rhs && left && top && right && bottom && dx && plan_y && work && out, "dst_solve_fft: null pointer");
+    PCNN_CHECK_ARG(B > 0 && B <= 65535 && nx >= 3 && ny >= 3 && ny <= 2050, "dst_solve_fft: needs nx >= 3, 3 <= ny <= 2050 and B <= 65535");
     if (use_double)
-        return solve<double>(rhs, left, top, right, bottom, dx, plan_x, plan_y, work, out, B, nx, ny, (cudaStream_t)stream);
-    return solve<float>(rhs, left, top, right, bottom, dx, plan_x, plan_y, work, out, B, nx, ny, (cudaStream_t)stream);
+        return solve<double>(rhs, left, top, right, bottom, dx, plan_y, work, out, B, nx, ny, (cudaStream_t)stream);
+    return solve<float>(rhs, left, top, right, bottom, dx, plan_y, work, out, B, nx, ny, (cudaStream_t)stream);
 }

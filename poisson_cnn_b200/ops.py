@@ -496,9 +496,10 @@ def jacobi(guess, rhs, grid_spacings, n_iter):
 
 def dst_solve(rhs, left, top, right, bottom, dx, method="fft", dtype=torch.float64):
     """DST-I direct solve of the reference's ground-truth system.  rhs [B,1,nx,ny] -> [B,1,nx,ny].
-    method "fft" (default): Bluestein chirp-z transforms on shared-memory FFTs, three passes over the grid (csrc/dst_fft.cu),
-    arithmetic in `dtype` (float64 like the reference's solver, or float32); "gemm": the dense sine-matrix form in float64
-    (O(N^3), kept as an independent cross-check and for sides beyond 2050 points)."""
+    method "fft" (default): DST-I along y (Bluestein chirp-z transforms on shared-memory FFTs, arithmetic in `dtype`: float64
+    like the reference's solver, or float32), float64 tridiagonal solves along x, inverse DST along y: three passes over the
+    grid (csrc/dst_fft.cu); "gemm": the dense sine-matrix form in float64 (O(N^3), kept as an independent cross-check and
+    for rows beyond 2050 points)."""
     for t, nme in ((rhs, "rhs"), (left, "left"), (top, "top"), (right, "right"), (bottom, "bottom"), (dx, "dx")):
         _chk(t, nme)
     if method not in ("fft", "gemm"):
@@ -507,20 +508,18 @@ def dst_solve(rhs, left, top, right, bottom, dx, method="fft", dtype=torch.float
     dev = rhs.device
     args = [t.contiguous() for t in (rhs, left, top, right, bottom, dx)]
     out = torch.empty_like(args[0])
-    if method == "fft" and max(nx, ny) <= 2050:
+    if method == "fft" and ny <= 2050:
         dbl = 1 if dtype == torch.float64 else 0
         if dtype not in (torch.float64, torch.float32):
             raise ValueError("dst_solve: dtype must be float64 or float32")
 
-        def plan(n):
-            def build():
-                p = torch.empty((lib.pcnn_dst_fft_plan_bytes(n, dbl),), device=dev, dtype=torch.uint8)
-                check(lib.pcnn_dst_fft_plan_init(_p(p), n, dbl, _stream()), "dst_fft_plan_init")
-                return p
-            return _cached(("dst_plan", str(dev), n, dbl), build)
-        px, py = plan(nx - 2), plan(ny - 2)
-        work = torch.empty((lib.pcnn_dst_fft_workspace_bytes(B, nx, ny, dbl),), device=dev, dtype=torch.uint8)
-        check(lib.pcnn_dst_solve_fft(*[_p(t) for t in args], _p(px), _p(py), _p(work), _p(out), B, nx, ny, dbl, _stream()),
+        def build():
+            p = torch.empty((lib.pcnn_dst_fft_plan_bytes(ny - 2, dbl),), device=dev, dtype=torch.uint8)
+            check(lib.pcnn_dst_fft_plan_init(_p(p), ny - 2, dbl, _stream()), "dst_fft_plan_init")
+            return p
+        py = _cached(("dst_plan", str(dev), ny - 2, dbl), build)
+        work = torch.empty((lib.pcnn_dst_fft_workspace_bytes(B, nx, ny),), device=dev, dtype=torch.uint8)
+        check(lib.pcnn_dst_solve_fft(*[_p(t) for t in args], _p(py), _p(work), _p(out), B, nx, ny, dbl, _stream()),
               "dst_solve_fft")
         return out
 
