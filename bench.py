@@ -333,8 +333,14 @@ def run_config2(args):
         step()
     h.barrier()
     sampler = ClockSampler(h.local); sampler.start()
-    timer = ops.KernelTimer(*args.roofline_kernel)
-    ops.KERNEL_TIMER = timer
+    # CUDA events around every launch of the dominant conv shape, recorded by the engine on the launching stream
+    use_engine = getattr(model, "use_engine", False)
+    timer = None
+    if use_engine:
+        model.engine().profile_conv_begin(*args.roofline_kernel, max_launches=64 * args.steps)
+    else:
+        timer = ops.KernelTimer(*args.roofline_kernel)
+        ops.KERNEL_TIMER = timer
     launches0 = _lib.lib.pcnn_launch_count()
     ms_total = h.time_steps(step, args.steps, 0)
     ops.KERNEL_TIMER = None
@@ -355,7 +361,7 @@ def run_config2(args):
 
     # ---------------- roofline of the dominant kernel (live CUDA-event timing inside the timed region)
     peaks = h.peaks
-    ks = timer.summary()
+    ks = model.engine().profile_conv_end() if use_engine else timer.summary()
     roofline = None
     if ks:
         ach = ks["flops_per_launch"] / (ks["avg_ms"] * 1e-3) / 1e12
@@ -432,7 +438,9 @@ def run_config2(args):
         "config": {"workload": "Poisson_CNN_Legacy forward (HPNN + 4x DBCNN merged), batch %d per GPU, %dx%d grids, pcnn_end_to_end architecture, precision mode %s" % (B, nx, ny, args.precision),
                    "baseline_config": 2, "per_gpu_batch": B, "global_batch": B * world, "grid": [nx, ny], "parallelism": "batch-sharded x%d" % world,
                    "l2": "inputs+activations per step (%.1f GB) exceed the 126 MB L2" % (B * nx * ny * 4 * 32 / 1e9),
-                   "flop_per_solution": pcnn_flops(nx, ny)},
+                   "flop_per_solution": pcnn_flops(nx, ny),
+                   "host": "model-level C ABI (pcnn_forward: layer program in libpcnn.so)" if use_engine else "op-by-op Python program",
+                   "workspace_bytes": model.engine().workspace_bytes("pcnn", B, nx, ny) if use_engine else None},
         "e2e": {"value": e2e_value, "unit": "solutions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_host.numel() * 4, "steps": e2e_steps},
         "gpu_launches": int(launches),
         "clocks": sampler.result(),

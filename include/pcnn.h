@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PCNN_VERSION 100
+#define PCNN_VERSION 200
 
 typedef enum {
     PCNN_OK = 0,
@@ -325,6 +325,56 @@ int pcnn_conv_tc_rowweight_slots(int Cout, int k, int H);
 int pcnn_conv2d_tc_rowweights(const void* in_row, const void* wrow, const float* bias, void* out, int B, int Cin,
                               int Cout, int Cout_total, int H, int W, int k, int act, float acc_scale, int num_sms,
                               void* stream);
+
+/* ==== model-level API ==========================================================================================
+ * The reference's unit of work is one Keras call: model([rhs, left, top, right, bottom, dx]) of Poisson_CNN_Legacy
+ * (models/Poisson_CNN_Legacy.py:15-51), model([rhs, dx]) of Homogeneous_Poisson_NN_Legacy (:182-257) and
+ * model([bc, dx, x_output_resolution]) of Dirichlet_BC_NN_Legacy_2 (models/Dirichlet_BC_NN_Legacy.py:124-166).  A handle
+ * holds the parsed config, the name-addressed weights and their packed operand images; a forward call runs the whole layer
+ * program (csrc/engine.cu) on the caller's stream inside ONE caller-provided workspace.
+ *
+ *   pcnn_create            config_json = {"hpnn_model": {...}, "dbcnn_model": {...}[, "jacobi_iterations": n]}: the sections
+ *                          of the reference's experiment JSONs (experiments/pcnn_end_to_end.json; activations may stay the
+ *                          "tf.nn.leaky_relu" strings).  "model" is accepted for "hpnn_model".  Either section alone gives a
+ *                          single-network handle.  Config errors return PCNN_ERR_INVALID_ARGUMENT with the reference's
+ *                          ValueError texts in pcnn_last_error().  One handle per (process, device); not thread-safe.
+ *   pcnn_set_weight        one variable, Keras layout, from HOST memory (dtype 0 = float32, 1 = float64); names as in
+ *                          poisson_cnn_b200/weights.py: "hpnn/pre_bottleneck/0/kernel", "dbcnn/boundary/3/resnet/conv1/bias",
+ *                          "hpnn/final/2/resnet/bn0/gamma", ...  Allocates device memory (setup phase).
+ *   pcnn_finalize_weights  checks that every variable of the config is present with the right shape, folds BatchNorm, packs
+ *                          the tensor-core operand images.  precision: 0 strict FP32, 1 tc (single fp16 pass; NOT within the
+ *                          2e-3 budget for the HPNN), 2 tc3, 3 tc2, 4 mixed (tc2 in the HPNN trunk, single pass in the DBCNN and
+ *                          the HPNN's bottleneck branches: the default of the Python host).  May be called again.
+ *   pcnn_*workspace_bytes  bytes a forward call of this shape needs (a dry run of the layer program with liveness-based
+ *                          buffer reuse; batches larger than the micro-batch are processed in slices inside the same arena).
+ *   pcnn_*forward          device pointers, fp32, dense: rhs/out [B,1,H,W]; left,right [B,1,W]; top,bottom [B,1,H]; dx [B,1];
+ *                          bc [B,1,n] -> out [B,1,x_res,n].  The library allocates nothing and never synchronises here.  The
+ *                          FIRST call for a (workspace pointer, shape) pair zero-fills the workspace and uploads the small
+ *                          host-built tables (a host-blocking copy from pageable memory); later calls only launch kernels,
+ *                          so a call is CUDA-graph capturable after one warm-up.  The workspace contents belong to the
+ *                          handle between calls of the same shape (halo rings, tables).
+ *   pcnn_set_microbatch    samples per slice (0 = automatic: 128 * 65536 / (H*W), the Python host's rule).
+ *   pcnn_profile_conv_*    CUDA-event timing of every tensor-core conv launch with this (Cin, Cout, k) inside forward calls
+ *                          (bench.py's live roofline measurement); _end synchronises on the recorded events. */
+typedef struct pcnn_model* pcnn_handle;
+enum { PCNN_PREC_FP32 = 0, PCNN_PREC_TC = 1, PCNN_PREC_TC3 = 2, PCNN_PREC_TC2 = 3, PCNN_PREC_MIXED = 4 };
+int pcnn_create(const char* config_json, int device, pcnn_handle* out);
+int pcnn_destroy(pcnn_handle handle);
+int pcnn_set_weight(pcnn_handle handle, const char* name, const void* host_ptr, const int64_t* shape, int ndim, int dtype);
+int pcnn_finalize_weights(pcnn_handle handle, int precision);
+int pcnn_set_microbatch(pcnn_handle handle, int samples);
+int pcnn_workspace_bytes(pcnn_handle handle, int B, int H, int W, size_t* bytes);
+int pcnn_hpnn_workspace_bytes(pcnn_handle handle, int B, int H, int W, size_t* bytes);
+int pcnn_dbcnn_workspace_bytes(pcnn_handle handle, int B, int n, int x_res, size_t* bytes);
+int pcnn_hpnn_forward(pcnn_handle handle, const float* rhs, const float* dx, float* out, int B, int H, int W,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int pcnn_dbcnn_forward(pcnn_handle handle, const float* bc, const float* dx, float* out, int B, int n, int x_res,
+                       void* workspace, size_t workspace_bytes, void* stream);
+int pcnn_forward(pcnn_handle handle, const float* rhs, const float* left, const float* top, const float* right,
+                 const float* bottom, const float* dx, float* out, int B, int H, int W, void* workspace,
+                 size_t workspace_bytes, void* stream);
+int pcnn_profile_conv_begin(pcnn_handle handle, int cin, int cout, int k, int max_launches);
+int pcnn_profile_conv_end(pcnn_handle handle, int* launches, double* avg_ms, double* flops_per_launch);
 
 #ifdef __cplusplus
 }

@@ -68,6 +68,20 @@ SIGNATURES = {
     "pcnn_upsample_merge_packed_floats": (c_size_t, [c_int, c_int]),
     "pcnn_upsample_merge_pack_kernel": (c_int, [P, P, c_int, c_int, P]),
     "pcnn_dbcnn_expand_blk8": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    # model-level API (csrc/engine.cu); a pcnn_handle crosses the ABI as a plain address
+    "pcnn_create": (c_int, [c_char_p, c_int, ctypes.POINTER(c_void_p)]),
+    "pcnn_destroy": (c_int, [P]),
+    "pcnn_set_weight": (c_int, [P, c_char_p, P, ctypes.POINTER(c_int64), c_int, c_int]),
+    "pcnn_finalize_weights": (c_int, [P, c_int]),
+    "pcnn_set_microbatch": (c_int, [P, c_int]),
+    "pcnn_workspace_bytes": (c_int, [P, c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
+    "pcnn_hpnn_workspace_bytes": (c_int, [P, c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
+    "pcnn_dbcnn_workspace_bytes": (c_int, [P, c_int, c_int, c_int, ctypes.POINTER(c_size_t)]),
+    "pcnn_hpnn_forward": (c_int, [P, P, P, P, c_int, c_int, c_int, P, c_size_t, P]),
+    "pcnn_dbcnn_forward": (c_int, [P, P, P, P, c_int, c_int, c_int, P, c_size_t, P]),
+    "pcnn_forward": (c_int, [P] * 8 + [c_int, c_int, c_int, P, c_size_t, P]),
+    "pcnn_profile_conv_begin": (c_int, [P, c_int, c_int, c_int, c_int]),
+    "pcnn_profile_conv_end": (c_int, [P, ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
 }
 
 
@@ -85,7 +99,7 @@ def _load():
         fn = getattr(lib, name)  # AttributeError if the .so is stale
         fn.restype = res
         fn.argtypes = args
-    if lib.pcnn_version() < 100:
+    if lib.pcnn_version() < 200:
         raise ImportError("libpcnn.so is older than the Python host side; rebuild")
     return lib
 

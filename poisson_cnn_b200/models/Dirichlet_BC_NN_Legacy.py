@@ -43,7 +43,8 @@ class Dirichlet_BC_NN_Legacy_2(WeightedModel):
 
         self._cfg = copy.deepcopy({
             "use_batchnorm": use_batchnorm, "boundary_conv_config": boundary_conv_config, "spp_config": spp_config,
-            "domain_info_mlp_config": domain_info_mlp_config, "final_convolutions_config": final_convolutions_config})
+            "domain_info_mlp_config": domain_info_mlp_config, "final_convolutions_config": final_convolutions_config,
+            "postsmoother_iterations": postsmoother_iterations, "data_format": data_format})
 
         bcfg = copy.deepcopy(boundary_conv_config)
         self.boundary_pad = padding_enum(bcfg.pop("padding_mode", "CONSTANT"))
@@ -77,6 +78,12 @@ class Dirichlet_BC_NN_Legacy_2(WeightedModel):
     def keras_key_map(self, prefix=""):
         from .. import tf_checkpoint as T
         return T.dbcnn_key_map(self._cfg, "", prefix)
+
+    def _engine_config(self):
+        return {"dbcnn_model": self._cfg}
+
+    def _engine_weights(self):
+        return self.get_weights_dict("dbcnn/")
 
     def _resnet1d(self, x, name, act, pad, pad_value, use_bn):
         k0, b0 = self.conv(name + "/conv0")
@@ -189,6 +196,12 @@ class Dirichlet_BC_NN_Legacy_2(WeightedModel):
         if not isinstance(bc, torch.Tensor) or not bc.is_cuda:
             raise ValueError("bc must be a CUDA tensor (the hot path has no CPU implementation)")
         with torch.cuda.device(bc.device):      # launches go to the current device: make it the tensors' device
+            if self.use_engine:
+                if bc.dim() != 3 or bc.shape[1] != 1:
+                    raise ValueError("bc must be [batch, 1, n] (channels_first)")
+                if dx.dim() != 2 or dx.shape[1] != 1 or dx.shape[0] != bc.shape[0]:
+                    raise ValueError("dx must be [batch, 1]")
+                return self.engine().dbcnn_forward(bc, dx, x_res)
             raw, m = self.raw_forward(bc, dx, x_res)
             out = ops.dbcnn_finalize(raw, m, bc)
             if self.postsmoother_iterations > 0:

@@ -90,7 +90,8 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
             "pre_bottleneck_convolutions_config": pre_bottleneck_convolutions_config,
             "bottleneck_deconv_config": bottleneck_deconv_config,
             "bottleneck_multilinear_config": bottleneck_multilinear_config,
-            "final_convolutions_config": final_convolutions_config, "scaling_config": scaling_config})
+            "final_convolutions_config": final_convolutions_config, "scaling_config": scaling_config,
+            "postsmoother_iterations": postsmoother_iterations, "bc_type": bc_type.lower(), "data_format": data_format})
 
         pre = copy.deepcopy(pre_bottleneck_convolutions_config)
         self.pre_pad = padding_enum(pre.pop("padding_mode", "CONSTANT"))
@@ -390,7 +391,15 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
         with torch.cuda.device(rhs.device):     # launches go to the current device: make it the tensors' device
             return self._forward(rhs, dx)
 
+    def _engine_config(self):
+        return {"hpnn_model": self._cfg}
+
+    def _engine_weights(self):
+        return self.get_weights_dict("hpnn/")
+
     def _forward(self, rhs, dx):
+        if self.use_engine and not self.tc_uncorrected:
+            return self.engine().hpnn_forward(rhs, dx)
         B, _, H, Wd = rhs.shape
         F = self.filters
         if self.precision in ("tc", "tc2", "tc3"):

@@ -43,6 +43,7 @@ class Poisson_CNN_Legacy(WeightedModel):
         self.hpnn.load_weights(source, prefix + "hpnn/", device)
         self.dbcnn.load_weights(source, prefix + "dbcnn/", device)
         self.device = self.hpnn.device
+        self._on_weights_loaded()
         return self
 
     def get_weights_dict(self, prefix=""):
@@ -146,8 +147,24 @@ class Poisson_CNN_Legacy(WeightedModel):
         fin.synchronize()                       # stream order does not order the HOST: wait for the last copy
         return out
 
+    def _engine_config(self):
+        return {"hpnn_model": self.hpnn._cfg, "dbcnn_model": self.dbcnn._cfg, "jacobi_iterations": int(self.jacobi_iterations)}
+
+    def _engine_weights(self):
+        return self.get_weights_dict()
+
+    def _engine_microbatch(self, nx, ny):
+        """Explicit slice size for the engine, or 0 for its automatic rule (128 * 65536 / (nx*ny): this class's default)."""
+        if self.microbatch_samples:
+            return int(self.microbatch_samples)
+        if self.max_microbatch and self.max_microbatch != 128:
+            return max(1, int(self.max_microbatch * 65536 // (nx * ny)))
+        return 0 if self.max_microbatch else 65535 // 4
+
     def _run(self, rhs, left, top, right, bottom, dx, mb):
         B, _, nx, ny = rhs.shape
+        if self.use_engine:                     # the engine slices the batch itself, inside one workspace
+            return self._forward([rhs, left, top, right, bottom, dx])
         if mb and B > mb:
             out = torch.empty((B, 1, nx, ny), device=rhs.device, dtype=torch.float32)
             for lo in range(0, B, mb):
@@ -158,6 +175,10 @@ class Poisson_CNN_Legacy(WeightedModel):
     def _forward(self, inp):
         rhs, left, top, right, bottom, dx = inp
         B, _, nx, ny = rhs.shape
+        if self.use_engine:
+            e = self.engine()
+            e.set_microbatch(self._engine_microbatch(nx, ny))
+            return e.forward(rhs, left, top, right, bottom, dx)
 
         # per-sample max-normalisation of the five inputs (set_max_magnitude_in_batch_and_return_scaling_factors)
         mrhs = ops.maxabs(rhs)

@@ -1,4 +1,6 @@
 """Shared weight handling of the hot-path models."""
+import os
+
 import numpy as np
 import torch
 
@@ -23,6 +25,10 @@ class WeightedModel:
         self.device = None
         self.precision = "fp32"
         self.requested_precision = "fp32"
+        # The forward pass runs inside libpcnn.so (model-level C ABI, csrc/engine.cu).  PCNN_PY_PROGRAM=1 (or
+        # use_engine = False) drives the same kernels op by op from Python instead: the development / probing path.
+        self.use_engine = os.environ.get("PCNN_PY_PROGRAM", "0") != "1"
+        self._engine = None
 
     # -- to be provided by subclasses
     def weight_specs(self, prefix=""):
@@ -56,6 +62,29 @@ class WeightedModel:
 
     def _on_weights_loaded(self):
         self._tc = {}
+        if self._engine is not None:
+            self._engine.close()
+        self._engine = None
+
+    # -- model-level C ABI
+    def _engine_config(self):
+        """The JSON handed to pcnn_create (sections of the reference's experiment files)."""
+        raise NotImplementedError
+
+    def _engine_weights(self):
+        """{name: numpy array} with the 'hpnn/' / 'dbcnn/' prefixes the engine expects."""
+        raise NotImplementedError
+
+    def engine(self):
+        """The pcnn_handle of this model (created on first use, re-finalised when the precision mode changes)."""
+        from ..engine import Engine
+        if self.device is None:
+            raise RuntimeError("model has no weights: call load_weights() or init_synthetic_weights() first")
+        if self._engine is None:
+            self._engine = Engine(self._engine_config(), self.device).set_weights(self._engine_weights())
+        if self._engine.precision != self.requested_precision:
+            self._engine.finalize(self.requested_precision)
+        return self._engine
 
     def keras_key_map(self, prefix=""):
         """{reference Keras attribute path: variable name} (tf_checkpoint.py); provided by the model classes."""

@@ -23,7 +23,7 @@ def test_cabi_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     from poisson_cnn_b200 import _lib
     assert set(_lib.SIGNATURES) == declared
-    assert _lib.lib.pcnn_version() == 100
+    assert _lib.lib.pcnn_version() == 200
 
 
 def test_cabi_rejects_bad_arguments_without_gpu():
@@ -270,3 +270,55 @@ def test_rowweights_image_layout():
                         want = scale * sum(float(kern[a, b, ci, co]) * float(basis[ci, x + a - p]) for a in range(k) if 0 <= x + a - p < H)
                     got = float(img[ci // 16, b, (ci % 16) // 8, t, co, ci % 8])
                     assert abs(got - want) <= 1e-3 * max(1.0, abs(want)), (t, x, b, ci, co, got, want)
+
+
+# ------------------------------------------------------------------ model-level C ABI (csrc/engine.cu), host-only parts
+def _create(cfg):
+    import ctypes, json
+    from poisson_cnn_b200 import _lib
+    h = ctypes.c_void_p()
+    st = _lib.lib.pcnn_create(json.dumps(cfg).encode(), 0, ctypes.byref(h))
+    return st, h, _lib.lib.pcnn_last_error().decode()
+
+
+def test_engine_create_parses_reference_configs_without_gpu():
+    from poisson_cnn_b200 import _lib, load_experiment
+    cfg = load_experiment("pcnn_end_to_end")
+    st, h, msg = _create({"hpnn_model": cfg["hpnn_model"], "dbcnn_model": cfg["dbcnn_model"]})
+    assert st == 0, msg
+    # a forward / workspace query before finalize_weights is an argument error, not a crash
+    import ctypes
+    n = ctypes.c_size_t(0)
+    assert _lib.lib.pcnn_workspace_bytes(h, 4, 64, 64, ctypes.byref(n)) == -1
+    assert b"finalize" in _lib.lib.pcnn_last_error()
+    assert _lib.lib.pcnn_destroy(h) == 0
+    for name in ("hpnn_neumann", "hpnn_smalldomain"):
+        st, h, msg = _create({"model": load_experiment(name)["model"]})
+        assert st == 0, msg
+        _lib.lib.pcnn_destroy(h)
+
+
+def test_engine_create_reports_the_reference_config_errors():
+    import copy
+    from poisson_cnn_b200 import load_experiment
+    cfg = load_experiment("pcnn_end_to_end")
+    hp, db = cfg["hpnn_model"], cfg["dbcnn_model"]
+    cases = [
+        ({k: v for k, v in hp.items() if k != "pre_bottleneck_convolutions_config"}, "hpnn_model", "Provide a config for pre bottleneck convolutions"),
+        ({k: v for k, v in hp.items() if k != "bottleneck_multilinear_config"}, "hpnn_model", "Provide a config for bottleneck blocks"),
+        ({k: v for k, v in hp.items() if k != "final_convolutions_config"}, "hpnn_model", "Provide a config for final convolutions"),
+        (dict(hp, bc_type="robin"), "hpnn_model", "bc_type can only be neumann or dirichlet."),
+        ({k: v for k, v in db.items() if k != "spp_config"}, "dbcnn_model", "Provide a config for the Spatial Pyramid Pooling."),
+        ({k: v for k, v in db.items() if k != "domain_info_mlp_config"}, "dbcnn_model", "Provide a config for the domain info MLP."),
+    ]
+    for sub, key, text in cases:
+        st, h, msg = _create({key: sub})
+        assert st == -1 and text in msg, (key, msg)
+    bad = copy.deepcopy(hp)
+    bad["pre_bottleneck_convolutions_config"]["activation"] = "tf.nn.softmax"
+    st, h, msg = _create({"hpnn_model": bad})
+    assert st == -1 and "unsupported activation" in msg
+    from poisson_cnn_b200 import _lib
+    import ctypes
+    assert _lib.lib.pcnn_create(b"{not json", 0, ctypes.byref(ctypes.c_void_p())) == -1
+    assert _lib.lib.pcnn_create(b"{}", 0, ctypes.byref(ctypes.c_void_p())) == -1
