@@ -373,6 +373,15 @@ int pcnn_dbcnn_forward(pcnn_handle handle, const float* bc, const float* dx, flo
 int pcnn_forward(pcnn_handle handle, const float* rhs, const float* left, const float* top, const float* right,
                  const float* bottom, const float* dx, float* out, int B, int H, int W, void* workspace,
                  size_t workspace_bytes, void* stream);
+/* Host-side table builders of the engine (no GPU involved), exported so that they can be pinned by CPU tests against the
+ * Python host's tables: "pos" (a = n): cos(pi*linspace(0,1,n)); "sinh" (a = modes, b = x_res): the sinh basis of
+ * models/Dirichlet_BC_NN_Legacy.py:106-112; "resize_idx" / "resize_w" (a = n_in, b = n_out, c = 0 nearest | 1 bilinear | 2
+ * bicubic): the per-axis gather tables of tf.image.resize.  Return the number of elements written (or a negative status).
+ * pcnn_host_rowweights: the fp16 operand image of pcnn_conv2d_tc_rowweights and its accumulator scale for a Keras kernel
+ * [k,k,Cin,Cout] whose input channels are (Cin-2 sinh modes, posx, 1) on a grid of height x_res. */
+long long pcnn_host_table(const char* what, int a, int b, int c, void* out, size_t out_bytes);
+long long pcnn_host_rowweights(const float* kernel, int k, int Cin, int Cout, int x_res, void* out_img, size_t out_bytes,
+                               float* acc_scale);
 int pcnn_profile_conv_begin(pcnn_handle handle, int cin, int cout, int k, int max_launches);
 int pcnn_profile_conv_end(pcnn_handle handle, int* launches, double* avg_ms, double* flops_per_launch);
 

@@ -80,6 +80,8 @@ SIGNATURES = {
     "pcnn_hpnn_forward": (c_int, [P, P, P, P, c_int, c_int, c_int, P, c_size_t, P]),
     "pcnn_dbcnn_forward": (c_int, [P, P, P, P, c_int, c_int, c_int, P, c_size_t, P]),
     "pcnn_forward": (c_int, [P] * 8 + [c_int, c_int, c_int, P, c_size_t, P]),
+    "pcnn_host_table": (ctypes.c_longlong, [c_char_p, c_int, c_int, c_int, P, c_size_t]),
+    "pcnn_host_rowweights": (ctypes.c_longlong, [P, c_int, c_int, c_int, c_int, P, c_size_t, ctypes.POINTER(c_float)]),
     "pcnn_profile_conv_begin": (c_int, [P, c_int, c_int, c_int, c_int]),
     "pcnn_profile_conv_end": (c_int, [P, ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
 }

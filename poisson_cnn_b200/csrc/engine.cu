@@ -11,6 +11,7 @@
 // tables (a host-blocking copy, once), every later call only launches kernels -- CUDA-graph capturable after one warm-up.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -469,12 +470,20 @@ struct Ctx {
 
     B8 b8(int Bcap, int B, int C, int H, int W, int mode, bool sym) {
         B8 t;
+        // Slots are shared by BYTE GEOMETRY (Cpad = round_up(C, 16) channel slots), not by the exact channel count: every
+        // producer rewrites all ceil(C/8) live planes as whole 16-byte pixels (padding channels of the last live plane come
+        // out as exact zeros) and no consumer reads a plane beyond ceil(Cin/8) (tap pairing reads the lone last plane
+        // only), so stale data of a previous tenant is either overwritten or never touched.  The halo ring is what must
+        // match, hence the `sym` bit in the key.  32/28/24/20-channel tensors of the trunk share three slots instead of
+        // twelve (59.6 GB -> see tests/test_gpu_engine.py for the planned workspace at the headline shape).
         const size_t bytes = pcnn_blk8_bytes(Bcap, C, H, W);
-        t.s_hi = alloc(SlotKey{1, Bcap, C, H, W, 0, sym ? 1 : 0}, bytes);
+        static const bool exact = std::getenv("PCNN_ENGINE_EXACT_SLOTS") != nullptr;      // debugging aid: one class per C
+        const int cpad8 = exact ? 1000 + C : (C + 15) / 16 * 2;
+        t.s_hi = alloc(SlotKey{1, Bcap, cpad8, H, W, 0, sym ? 1 : 0}, bytes);
         t.hi = ptr(t.s_hi);
         t.halo = prep->slots[t.s_hi].halo;
         if (mode >= 2) {
-            t.s_lo = alloc(SlotKey{2, Bcap, C, H, W, mode, sym ? 1 : 0}, bytes);
+            t.s_lo = alloc(SlotKey{2, Bcap, cpad8, H, W, mode, sym ? 1 : 0}, bytes);
             t.lo = ptr(t.s_lo);
             const Halo hl = prep->slots[t.s_lo].halo;
             if (hl != t.halo) { t.halo.mode = t.halo.mode != PCNN_PAD_CONSTANT ? t.halo.mode : hl.mode; t.halo.pad = -1; }
@@ -1660,32 +1669,41 @@ static int pcnn_run(Ctx& c, const float* rhs, const float* left, const float* to
     TRY(hpnn_run(c, rhs_n, dx, hp, B, Bcap, nx, ny));
     const size_t plane = (size_t)nx * ny;
     const float *L, *T, *R, *Bt;
+    // The DBCNN's weights are shared by the four boundaries, so their problems can be batched.  Small batches are batched
+    // (4B, or 2B + 2B on non-square grids: fills the GPU at batch 1); large ones run one boundary per call, which keeps the
+    // DBCNN's activations at the size of the HPNN's instead of four times that (the kernels have thousands of tiles either way).
+    const bool batch_sides = (long long)4 * Bcap * plane <= 64LL * 65536;
+    float* dxr = c.vec((size_t)4 * Bcap);
+    for (int i = 0; i < 4; ++i)
+        if (!c.dry) PCNN_CHECK_CUDA(cudaMemcpyAsync(dxr + (size_t)i * B, dx, (size_t)B * 4, cudaMemcpyDeviceToDevice, c.st));
     if (nx == ny) {
         float* bcs = c.vec((size_t)4 * Bcap * ny);
-        float* dx4 = c.vec((size_t)4 * Bcap);
         float* res = c.vec((size_t)4 * Bcap * plane);
         const float* src[4] = {left, top, right, bottom};
         const float* mm[4] = {ml, mt, mr, mb};
-        for (int i = 0; i < 4; ++i) {
-            RUN(c, pcnn_scale_inv_f32(src[i], mm[i], bcs + (size_t)i * B * ny, B, ny, c.st));
-            if (!c.dry) PCNN_CHECK_CUDA(cudaMemcpyAsync(dx4 + (size_t)i * B, dx, (size_t)B * 4, cudaMemcpyDeviceToDevice, c.st));
+        for (int i = 0; i < 4; ++i) RUN(c, pcnn_scale_inv_f32(src[i], mm[i], bcs + (size_t)i * B * ny, B, ny, c.st));
+        if (batch_sides) {
+            TRY(dbcnn_run(c, bcs, dxr, res, 4 * B, 4 * Bcap, ny, nx));
+        } else {
+            for (int i = 0; i < 4; ++i) TRY(dbcnn_run(c, bcs + (size_t)i * B * ny, dx, res + (size_t)i * B * plane, B, Bcap, ny, nx));
         }
-        TRY(dbcnn_run(c, bcs, dx4, res, 4 * B, 4 * Bcap, ny, nx));
         L = res; T = res + (size_t)B * plane; R = res + (size_t)2 * B * plane; Bt = res + (size_t)3 * B * plane;
     } else {
         float* lr = c.vec((size_t)2 * Bcap * ny);
         float* tb = c.vec((size_t)2 * Bcap * nx);
-        float* dx2 = c.vec((size_t)2 * Bcap);
         float* res_lr = c.vec((size_t)2 * Bcap * plane);
         float* res_tb = c.vec((size_t)2 * Bcap * plane);
         RUN(c, pcnn_scale_inv_f32(left, ml, lr, B, ny, c.st));
         RUN(c, pcnn_scale_inv_f32(right, mr, lr + (size_t)B * ny, B, ny, c.st));
         RUN(c, pcnn_scale_inv_f32(top, mt, tb, B, nx, c.st));
         RUN(c, pcnn_scale_inv_f32(bottom, mb, tb + (size_t)B * nx, B, nx, c.st));
-        for (int i = 0; i < 2; ++i)
-            if (!c.dry) PCNN_CHECK_CUDA(cudaMemcpyAsync(dx2 + (size_t)i * B, dx, (size_t)B * 4, cudaMemcpyDeviceToDevice, c.st));
-        TRY(dbcnn_run(c, lr, dx2, res_lr, 2 * B, 2 * Bcap, ny, nx));
-        TRY(dbcnn_run(c, tb, dx2, res_tb, 2 * B, 2 * Bcap, nx, ny));
+        if (batch_sides) {
+            TRY(dbcnn_run(c, lr, dxr, res_lr, 2 * B, 2 * Bcap, ny, nx));
+            TRY(dbcnn_run(c, tb, dxr, res_tb, 2 * B, 2 * Bcap, nx, ny));
+        } else {
+            for (int i = 0; i < 2; ++i) TRY(dbcnn_run(c, lr + (size_t)i * B * ny, dx, res_lr + (size_t)i * B * plane, B, Bcap, ny, nx));
+            for (int i = 0; i < 2; ++i) TRY(dbcnn_run(c, tb + (size_t)i * B * nx, dx, res_tb + (size_t)i * B * plane, B, Bcap, nx, ny));
+        }
         L = res_lr; R = res_lr + (size_t)B * plane; T = res_tb; Bt = res_tb + (size_t)B * plane;
     }
     if (jacobi_iters > 0) {
@@ -1969,4 +1987,46 @@ extern "C" int pcnn_profile_conv_end(pcnn_handle handle, int* launches, double* 
     m.prof_k = m.prof_cin = m.prof_cout = 0;
     m.prof_used = 0;
     return PCNN_OK;
+}
+
+// ---- host-side table builders, exported so that the CPU test-suite can pin them against the Python host's tables
+// (tests/test_host.py); no GPU involved.  what: "pos" (a = n) -> float[n]; "sinh" (a = modes, b = x_res) -> float[a*b];
+// "resize_idx" / "resize_w" (a = n_in, b = n_out, c = method 0 nearest / 1 bilinear / 2 bicubic) -> int32 / float [b*taps];
+// "spp1" (a = n; levels = the shipped DBCNN levels are passed as `levels`, n_levels) -> int32[bins*4].
+// Returns the number of elements written, or a negative status.
+extern "C" long long pcnn_host_table(const char* what, int a, int b, int c, void* out, size_t out_bytes) {
+    PCNN_CHECK_ARG(what && out, "pcnn_host_table: null argument");
+    ENG_GUARD_BEGIN
+    const std::string w(what);
+    auto emit = [&](const void* src, size_t bytes, size_t count) -> long long {
+        if (bytes > out_bytes) { set_error("pcnn_host_table: output buffer too small (%zu > %zu)", bytes, out_bytes); return PCNN_ERR_INVALID_ARGUMENT; }
+        std::memcpy(out, src, bytes);
+        return (long long)count;
+    };
+    if (w == "pos") { const auto v = eng::position_table(a); return emit(v.data(), v.size() * 4, v.size()); }
+    if (w == "sinh") { const auto v = eng::sinh_basis(a, b); return emit(v.data(), v.size() * 4, v.size()); }
+    if (w == "resize_idx") { const auto t = eng::resize_axis_table(a, b, c); return emit(t.idx.data(), t.idx.size() * 4, t.idx.size()); }
+    if (w == "resize_w") { const auto t = eng::resize_axis_table(a, b, c); return emit(t.w.data(), t.w.size() * 4, t.w.size()); }
+    set_error("pcnn_host_table: unknown table '%s'", what);
+    return PCNN_ERR_INVALID_ARGUMENT;
+    ENG_GUARD_END
+}
+
+// The separable DBCNN layer's row weights exactly as the engine uploads them: kernel [k,k,Cin,Cout] (host, fp32), M = Cin - 2
+// sinh modes, grid height x_res -> fp16 image (pcnn_conv2d_tc_rowweights layout) + its power-of-two accumulator scale.
+extern "C" long long pcnn_host_rowweights(const float* kernel, int k, int Cin, int Cout, int x_res, void* out_img, size_t out_bytes,
+                                          float* acc_scale) {
+    PCNN_CHECK_ARG(kernel && out_img && acc_scale && k >= 1 && Cin >= 3 && Cout >= 1, "pcnn_host_rowweights: bad argument");
+    ENG_GUARD_BEGIN
+    const int cp = pcnn_conv_tc_channel_slots(Cout, k), T = pcnn_conv_tc_rowweight_slots(Cout, k, x_res);
+    PCNN_CHECK_ARG(cp > 0 && T > 0, "pcnn_host_rowweights: unsupported layer (Cout <= 32, odd k <= 15)");
+    eng::Weight w;
+    w.shape = {k, k, Cin, Cout};
+    w.host.assign(kernel, kernel + (size_t)k * k * Cin * Cout);
+    const eng::RowWeights r = eng::build_rowweights(w, Cin - 2, x_res, cp, cp == 24 ? 5 : 128 / cp, T);
+    if (r.img.size() * 2 > out_bytes) { set_error("pcnn_host_rowweights: output buffer too small"); return PCNN_ERR_INVALID_ARGUMENT; }
+    std::memcpy(out_img, r.img.data(), r.img.size() * 2);
+    *acc_scale = r.acc_scale;
+    return (long long)r.img.size();
+    ENG_GUARD_END
 }

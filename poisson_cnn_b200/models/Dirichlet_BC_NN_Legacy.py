@@ -157,10 +157,8 @@ class Dirichlet_BC_NN_Legacy_2(WeightedModel):
             if sep:
                 M = h.shape[1]
                 key = ("rowweights", x_res)
-                if key not in self._tc:
-                    basis = torch.cat([ops.sinh_basis_table(h.device, M, x_res), ops.position_table(h.device, x_res)[None],
-                                       torch.ones((1, x_res), device=h.device)], 0)
-                    self._tc[key] = ops.pack_rowweights_tc(self._w["final/0/conv/kernel"], basis)
+                if key not in self._tc:      # row basis = (M sinh modes, posx, 1): built by the library's host-side packer
+                    self._tc[key] = ops.pack_rowweights_tc(self._w["final/0/conv/kernel"], x_res=x_res)
                 t = ops.dbcnn_signal_blk8(h, v)
             else:
                 # the [B,29,x_res,n] mode expansion is produced directly in the tensor-core operand layout

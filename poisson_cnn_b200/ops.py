@@ -383,22 +383,25 @@ def tf_linspace01(n):
     return v
 
 
+def host_table(what, count, a, b=0, c=0, dtype=np.float32):
+    """A host-built table from the library's own builders (csrc/engine.cu: the model-level C ABI uploads the same bytes)."""
+    import ctypes
+    out = np.zeros(int(count), dtype=dtype)
+    n = lib.pcnn_host_table(what.encode(), int(a), int(b), int(c), out.ctypes.data_as(ctypes.c_void_p), out.nbytes)
+    if n != count:
+        check(int(n) if n < 0 else -1, "pcnn_host_table(%s)" % what)
+    return out
+
+
 def position_table(device, n):
     """cos(pi * linspace(0,1,n)), float32 (generate_position_embeddings)."""
-    return _cached(("pos", str(device), n),
-                   lambda: torch.from_numpy(np.cos(np.float32(math.pi) * tf_linspace01(n)).astype(np.float32)).to(device))
+    return _cached(("pos", str(device), n), lambda: torch.from_numpy(host_table("pos", n, n)).to(device))
 
 
 def sinh_basis_table(device, n_modes, x_res):
     """build_series_x_dir_components (poisson_CNN/models/Dirichlet_BC_NN_Legacy.py:106-112), float32."""
-    def build():
-        xbar = tf_linspace01(x_res)
-        modes = np.arange(1, n_modes + 1, dtype=np.float32)
-        arg = modes[:, None] * (np.float32(math.pi) * (xbar - np.float32(1)))[None, :]
-        s = np.sinh(arg.astype(np.float32)).astype(np.float32)
-        s = s * (np.float32(1.0) / np.abs(s).max(1, keepdims=True))
-        return torch.from_numpy(np.ascontiguousarray(s.astype(np.float32))).to(device)
-    return _cached(("sinh", str(device), n_modes, x_res), build)
+    return _cached(("sinh", str(device), n_modes, x_res),
+                   lambda: torch.from_numpy(host_table("sinh", n_modes * x_res, n_modes, x_res).reshape(n_modes, x_res)).to(device))
 
 
 def hpnn_input(rhs):
@@ -936,20 +939,36 @@ def rowweights_image(kernel, row_basis, cp, rt, T):
     return P.half().contiguous(), scale
 
 
-def pack_rowweights_tc(kernel, row_basis):
+def pack_rowweights_tc(kernel, row_basis=None, x_res=None):
     """Row weights of a convolution whose input is separable, in[b,m,x,y] = h[b,m,y] * row_basis[m,x] (zero padding):
     A_x[b,m,co] = sum_a kernel[a,b,m,co] * row_basis[m, x+a-k/2], packed for pcnn_conv2d_tc_rowweights.  Done once per
-    (layer, grid height); a weight transformation like pack_conv_weights_tc (torch einsum, then the slot re-ordering)."""
-    _chk(kernel, "kernel"); _chk(row_basis, "row_basis")
+    (layer, grid height).  With x_res (the DBCNN's case: Cin-2 sinh modes, posx, 1) the image comes from the library's
+    host-side builder pcnn_host_rowweights -- the bytes the model-level C ABI uploads; with an explicit row_basis it is
+    computed by rowweights_image (torch einsum, then the slot re-ordering)."""
+    import ctypes
+    _chk(kernel, "kernel")
     k, k2, Cin, Cout = kernel.shape
-    if k != k2 or k % 2 == 0 or row_basis.shape[0] != Cin:
-        raise ValueError("pack_rowweights_tc: needs an odd square kernel and a [Cin, H] row basis")
-    H = row_basis.shape[1]
+    if k != k2 or k % 2 == 0:
+        raise ValueError("pack_rowweights_tc: needs an odd square kernel")
+    H = int(x_res) if row_basis is None else row_basis.shape[1]
     cp = lib.pcnn_conv_tc_channel_slots(int(Cout), int(k))
     T = lib.pcnn_conv_tc_rowweight_slots(int(Cout), int(k), int(H))
     if cp == 0 or T == 0:
         raise ValueError("pack_rowweights_tc: unsupported layer (Cout <= 32, odd k <= 15)")
     rt = 5 if cp == 24 else 128 // cp
+    if row_basis is None:
+        kk = np.ascontiguousarray(kernel.detach().cpu().numpy(), dtype=np.float32)
+        img = np.zeros(-(-Cin // 16) * k * 2 * T * cp * 8, dtype=np.float16)
+        sc = ctypes.c_float(0.0)
+        n = lib.pcnn_host_rowweights(kk.ctypes.data_as(ctypes.c_void_p), int(k), int(Cin), int(Cout), H,
+                                     img.ctypes.data_as(ctypes.c_void_p), img.nbytes, ctypes.byref(sc))
+        if n != img.size:
+            check(int(n) if n < 0 else -1, "pcnn_host_rowweights")
+        return {"packed": torch.from_numpy(img).to(kernel.device), "k": int(k), "cin": int(Cin), "cout": int(Cout), "H": H,
+                "acc_scale": float(sc.value)}
+    _chk(row_basis, "row_basis")
+    if row_basis.shape[0] != Cin:
+        raise ValueError("pack_rowweights_tc: needs a [Cin, H] row basis")
     packed, scale = rowweights_image(kernel, row_basis, cp, rt, T)
     return {"packed": packed, "k": int(k), "cin": int(Cin), "cout": int(Cout), "H": int(H), "acc_scale": 1.0 / scale}
 

@@ -79,20 +79,22 @@ def _model(hp, db, w):
 
 @pytest.mark.parametrize("nx,ny,B", [(112, 120, 3), (128, 128, 2), (200, 300, 2)])
 def test_engine_matches_python_program(setup, nx, ny, B):
-    """Same kernels, same order: the C++ layer program reproduces the Python op-by-op program (bit-exact up to the
-    host-built float tables, hence the tiny tolerance), in strict FP32, mixed and tc2; micro-batch with a remainder slice."""
+    """Same kernels, same order, same host tables (both sides take them from the library's builders): the C++ layer program
+    reproduces the Python op-by-op program BIT FOR BIT in strict FP32, mixed and tc2; micro-batch with a remainder slice.
+    (Bit-exactness is the only meaningful bar here: with the seeded synthetic weights the network is chaotic -- a 1-ulp change
+    of the input moves the single-pass output by 2.7e-3, scripts/engine_diag2.py.)"""
     from poisson_cnn_b200.synthetic import make_problem
     hp, db, w = setup
     p = make_problem(B, nx, ny, seed=500 + nx)
     inp = [p[k].cuda() for k in KEYS]
     m_eng, m_py = _model(hp, db, w), _model(hp, db, w)
     m_py.use_engine = m_py.hpnn.use_engine = m_py.dbcnn.use_engine = False
-    for mode, tol in (("fp32", 2e-6), ("mixed", 2e-5), ("tc2", 2e-5)):
+    for mode in ("fp32", "mixed", "tc2"):
         a = m_eng.set_precision(mode)(inp)
         b = m_py.set_precision(mode)(inp)
         e = rel_l2(a, b)
         print("%s %dx%d engine vs python program: %.2e" % (mode, nx, ny, e))
-        assert e < tol, (mode, e)
+        assert torch.equal(a, b), (mode, e)
         a2 = m_eng(inp)                          # steady state (tables cached, halo rings carried over): identical bits
         assert torch.equal(a, a2)
     m_eng.set_precision("mixed")

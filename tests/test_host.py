@@ -322,3 +322,54 @@ def test_engine_create_reports_the_reference_config_errors():
     import ctypes
     assert _lib.lib.pcnn_create(b"{not json", 0, ctypes.byref(ctypes.c_void_p())) == -1
     assert _lib.lib.pcnn_create(b"{}", 0, ctypes.byref(ctypes.c_void_p())) == -1
+
+
+def test_engine_host_tables_match_the_python_tables():
+    """The C++ engine builds its tables on the host (csrc/engine.cu); they must agree with the numpy restatements of the
+    Python host (ops.resize_axis_table: bit-exact; cos / sinh bases: within one float32 ulp of numpy's own libm)."""
+    import math
+    from poisson_cnn_b200 import ops
+    for n in (1, 2, 7, 256, 300):
+        ref = np.cos(np.float32(math.pi) * ops.tf_linspace01(n)).astype(np.float32)
+        got = ops.host_table("pos", n, n)
+        assert np.abs(got - ref).max() <= 6e-8 * 1.01
+    M, xres = 27, 112
+    xbar = ops.tf_linspace01(xres)
+    arg = np.arange(1, M + 1, dtype=np.float32)[:, None] * (np.float32(math.pi) * (xbar - np.float32(1)))[None, :]
+    s = np.sinh(arg.astype(np.float32)).astype(np.float32)
+    s = s * (np.float32(1.0) / np.abs(s).max(1, keepdims=True))
+    got = ops.host_table("sinh", M * xres, M, xres).reshape(M, xres)
+    np.testing.assert_allclose(got, s, rtol=3e-7, atol=1e-37)
+    for (a, b) in ((2, 256), (4, 300), (8, 109), (7, 64), (1, 5)):
+        for m in (0, 1, 2):
+            idx, w = ops.resize_axis_table(a, b, m)
+            taps = idx.shape[1]
+            np.testing.assert_array_equal(ops.host_table("resize_idx", b * taps, a, b, m, np.int32).reshape(b, taps), idx)
+            np.testing.assert_array_equal(ops.host_table("resize_w", b * taps, a, b, m).reshape(b, taps), w)
+
+
+def test_engine_host_rowweights_match_the_torch_packer():
+    """pcnn_host_rowweights (what the engine uploads) against ops.rowweights_image (torch einsum): same layout, same
+    power-of-two scale; values equal up to one fp16 ulp on a handful of elements (float summation order)."""
+    import ctypes, math
+    from poisson_cnn_b200 import ops, _lib
+    g = torch.Generator().manual_seed(0)
+    k, Cin, Cout, H = 7, 29, 23, 112
+    kern = torch.randn(k, k, Cin, Cout, generator=g) / 30
+    M = Cin - 2
+    S = torch.from_numpy(ops.host_table("sinh", M * H, M, H).reshape(M, H))
+    pos = torch.from_numpy(ops.host_table("pos", H, H))
+    basis = torch.cat([S, pos[None], torch.ones(1, H)], 0)
+    cp = _lib.lib.pcnn_conv_tc_channel_slots(Cout, k)
+    T = _lib.lib.pcnn_conv_tc_rowweight_slots(Cout, k, H)
+    rt = 5 if cp == 24 else 128 // cp
+    ref, scale = ops.rowweights_image(kern, basis, cp, rt, T)
+    img = np.zeros(ref.numel(), dtype=np.float16)
+    sc = ctypes.c_float(0)
+    kk = np.ascontiguousarray(kern.numpy())
+    n = _lib.lib.pcnn_host_rowweights(kk.ctypes.data_as(ctypes.c_void_p), k, Cin, Cout, H, img.ctypes.data_as(ctypes.c_void_p), img.nbytes, ctypes.byref(sc))
+    assert n == ref.numel() and abs(sc.value - 1.0 / scale) == 0.0
+    r = ref.numpy().ravel().astype(np.float32)
+    d = np.abs(img.astype(np.float32) - r)
+    assert (d > 0).sum() < 1e-3 * d.size
+    assert np.all(d <= np.maximum(np.abs(r), 2.0 ** -14) * 2.0 ** -10 * 1.01)
