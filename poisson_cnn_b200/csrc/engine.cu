@@ -1672,7 +1672,8 @@ static int pcnn_run(Ctx& c, const float* rhs, const float* left, const float* to
     // The DBCNN's weights are shared by the four boundaries, so their problems can be batched.  Small batches are batched
     // (4B, or 2B + 2B on non-square grids: fills the GPU at batch 1); large ones run one boundary per call, which keeps the
     // DBCNN's activations at the size of the HPNN's instead of four times that (the kernels have thousands of tiles either way).
-    const bool batch_sides = (long long)4 * Bcap * plane <= 64LL * 65536;
+    static const long long side_px = std::getenv("PCNN_ENGINE_BATCH_SIDES_PX") ? std::atoll(std::getenv("PCNN_ENGINE_BATCH_SIDES_PX")) : 64LL * 65536;
+    const bool batch_sides = (long long)4 * Bcap * plane <= side_px;
     float* dxr = c.vec((size_t)4 * Bcap);
     for (int i = 0; i < 4; ++i)
         if (!c.dry) PCNN_CHECK_CUDA(cudaMemcpyAsync(dxr + (size_t)i * B, dx, (size_t)B * 4, cudaMemcpyDeviceToDevice, c.st));
