@@ -188,6 +188,22 @@ int pcnn_dst_solve_fft(const float* rhs, const float* left, const float* top, co
                        const float* bottom, const float* dx, void* plan_y, void* work, float* out, int B,
                        int nx, int ny, int use_double, void* stream);
 
+/* ---- the caller after the path: pressure-Poisson solve of the reference's Navier-Stokes projection solver -------------
+ * (Navier_Stokes_2D/solvers.py:153-186 operator, :204-334 solve).  A = minus the cell-centred 5-point
+ * Laplacian with homogeneous Neumann boundaries, (A v)[i,j] = (deg v[i,j] - sum of existing neighbours) / dx^2, on [B,H,W]
+ * fields with per-sample dx [B].  pcnn_neumann_cg_solve runs batched conjugate gradients for  A p = -rhs - mean(-rhs)
+ * (the reference's zero-integral Lagrange row with uniform Riemann weights) and returns the zero-mean p:
+ *   x            in: initial guess (e.g. the Neumann HPNN's prediction), multiplied by guess_scale[b] when given (the
+ *                reference's ((dx (n-1))^2 / sf) rescale of the network output, solvers.py:250); out: solution
+ *   max_iter     CG iterations enqueued (3 kernels each; per-sample step lengths live on the device, a sample whose
+ *                residual is below rel_tol * |b| freezes); no host synchronisation inside
+ *   residual_history  [max_iter][B] doubles or NULL: |r_k| / |b| after every iteration
+ *   workspace    pcnn_neumann_cg_workspace_bytes(B,H,W), 8-byte aligned */
+size_t pcnn_neumann_cg_workspace_bytes(int B, int H, int W);
+int pcnn_neumann_laplacian_apply_f32(const float* v, const float* dx, float* out, int B, int H, int W, void* stream);
+int pcnn_neumann_cg_solve(const float* rhs, const float* dx, const float* guess_scale, float* x, int B, int H, int W,
+                          int max_iter, double rel_tol, double* residual_history, void* workspace, void* stream);
+
 /* Fused 1-D convolution stack (csrc/boundary_stack.cu): n_layers Conv1D layers (Keras kernels [k][Cin][Cout],
  * odd k <= 19, <= 28 channels) applied back to back to every signal of in [B][Cin0][n], all activations staying in
  * shared memory.  Per layer: tf.pad(pad_mode) -> conv -> bias -> act -> BN affine (bn_scale/bn_shift may be NULL per

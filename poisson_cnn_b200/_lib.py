@@ -47,6 +47,9 @@ SIGNATURES = {
     "pcnn_dst_fft_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pcnn_dst_fft_passes": (c_int, []),
     "pcnn_dst_solve_fft": (c_int, [P] * 9 + [c_int, c_int, c_int, c_int, P]),
+    "pcnn_neumann_cg_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pcnn_neumann_laplacian_apply_f32": (c_int, [P, P, P, c_int, c_int, c_int, P]),
+    "pcnn_neumann_cg_solve": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, ctypes.c_double, P, P, P]),
     "pcnn_blk8_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "pcnn_to_blk8": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, c_int, P]),
     "pcnn_from_blk8": (c_int, [P, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, P]),

@@ -1669,11 +1669,12 @@ static int pcnn_run(Ctx& c, const float* rhs, const float* left, const float* to
     TRY(hpnn_run(c, rhs_n, dx, hp, B, Bcap, nx, ny));
     const size_t plane = (size_t)nx * ny;
     const float *L, *T, *R, *Bt;
-    // The DBCNN's weights are shared by the four boundaries, so their problems can be batched.  Small batches are batched
-    // (4B, or 2B + 2B on non-square grids: fills the GPU at batch 1); large ones run one boundary per call, which keeps the
-    // DBCNN's activations at the size of the HPNN's instead of four times that (the kernels have thousands of tiles either way).
-    static const long long side_px = std::getenv("PCNN_ENGINE_BATCH_SIDES_PX") ? std::atoll(std::getenv("PCNN_ENGINE_BATCH_SIDES_PX")) : 64LL * 65536;
-    const bool batch_sides = (long long)4 * Bcap * plane <= side_px;
+    // The DBCNN's weights are shared by the four boundaries, so their problems can be batched: all four in one call for
+    // small batches (fills the GPU at batch 1), two per call in between, one per call for large ones.  Fewer, larger calls
+    // save the fixed cost of ~25 launches per call (measured at the headline shape: 4B 1176, B 1144 solutions/s) but the
+    // DBCNN's activations then are 4x / 2x the HPNN's: the middle tier keeps the planned workspace at ~15 GB.
+    static const long long side_px = std::getenv("PCNN_ENGINE_BATCH_SIDES_PX") ? std::atoll(std::getenv("PCNN_ENGINE_BATCH_SIDES_PX")) : 256LL * 65536;
+    const int group = ((long long)4 * Bcap * plane <= side_px) ? 4 : (((long long)2 * Bcap * plane <= side_px) ? 2 : 1);
     float* dxr = c.vec((size_t)4 * Bcap);
     for (int i = 0; i < 4; ++i)
         if (!c.dry) PCNN_CHECK_CUDA(cudaMemcpyAsync(dxr + (size_t)i * B, dx, (size_t)B * 4, cudaMemcpyDeviceToDevice, c.st));
@@ -1683,11 +1684,8 @@ static int pcnn_run(Ctx& c, const float* rhs, const float* left, const float* to
         const float* src[4] = {left, top, right, bottom};
         const float* mm[4] = {ml, mt, mr, mb};
         for (int i = 0; i < 4; ++i) RUN(c, pcnn_scale_inv_f32(src[i], mm[i], bcs + (size_t)i * B * ny, B, ny, c.st));
-        if (batch_sides) {
-            TRY(dbcnn_run(c, bcs, dxr, res, 4 * B, 4 * Bcap, ny, nx));
-        } else {
-            for (int i = 0; i < 4; ++i) TRY(dbcnn_run(c, bcs + (size_t)i * B * ny, dx, res + (size_t)i * B * plane, B, Bcap, ny, nx));
-        }
+        for (int i = 0; i < 4; i += group)
+            TRY(dbcnn_run(c, bcs + (size_t)i * B * ny, dxr, res + (size_t)i * B * plane, group * B, group * Bcap, ny, nx));
         L = res; T = res + (size_t)B * plane; R = res + (size_t)2 * B * plane; Bt = res + (size_t)3 * B * plane;
     } else {
         float* lr = c.vec((size_t)2 * Bcap * ny);
@@ -1698,13 +1696,9 @@ static int pcnn_run(Ctx& c, const float* rhs, const float* left, const float* to
         RUN(c, pcnn_scale_inv_f32(right, mr, lr + (size_t)B * ny, B, ny, c.st));
         RUN(c, pcnn_scale_inv_f32(top, mt, tb, B, nx, c.st));
         RUN(c, pcnn_scale_inv_f32(bottom, mb, tb + (size_t)B * nx, B, nx, c.st));
-        if (batch_sides) {
-            TRY(dbcnn_run(c, lr, dxr, res_lr, 2 * B, 2 * Bcap, ny, nx));
-            TRY(dbcnn_run(c, tb, dxr, res_tb, 2 * B, 2 * Bcap, nx, ny));
-        } else {
-            for (int i = 0; i < 2; ++i) TRY(dbcnn_run(c, lr + (size_t)i * B * ny, dx, res_lr + (size_t)i * B * plane, B, Bcap, ny, nx));
-            for (int i = 0; i < 2; ++i) TRY(dbcnn_run(c, tb + (size_t)i * B * nx, dx, res_tb + (size_t)i * B * plane, B, Bcap, nx, ny));
-        }
+        const int g2 = group >= 2 ? 2 : 1;
+        for (int i = 0; i < 2; i += g2) TRY(dbcnn_run(c, lr + (size_t)i * B * ny, dxr, res_lr + (size_t)i * B * plane, g2 * B, g2 * Bcap, ny, nx));
+        for (int i = 0; i < 2; i += g2) TRY(dbcnn_run(c, tb + (size_t)i * B * nx, dxr, res_tb + (size_t)i * B * plane, g2 * B, g2 * Bcap, nx, ny));
         L = res_lr; R = res_lr + (size_t)B * plane; T = res_tb; Bt = res_tb + (size_t)B * plane;
     }
     if (jacobi_iters > 0) {

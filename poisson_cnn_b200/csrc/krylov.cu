@@ -1,0 +1,222 @@
+// The step AFTER the hot path: the pressure-Poisson solve of the reference's Navier-Stokes projection
+// solver, which takes the Neumann HPNN's prediction as the initial guess of a Krylov iteration
+// (Navier_Stokes_2D/solvers.py:29-33 builds the model, :153-186 the operator, :204-334 the solve).
+//
+// Operator (Poisson_pressure_matrix, solvers.py:164-173): A = kron(I, T) + kron(T, I), T = tridiag(-1, [1,2,...,2,1], -1)/dh^2,
+// i.e. minus the cell-centred 5-point Laplacian with homogeneous Neumann boundaries (the diagonal counts the neighbours
+// that exist).  A is symmetric positive semi-definite with the constants as null space; the reference pins the constant
+// with a zero-integral Lagrange row (uniform Riemann weights), which is equivalent to projecting the right-hand side onto
+// zero mean, solving A p = b - mean(b), and returning the zero-mean solution.  The reference runs scipy BiCGStab with an
+// ILU preconditioner on the CPU; here it is batched conjugate gradients on the GPU: three HBM-bound kernels per iteration,
+// per-sample step lengths computed on the device (no host synchronisation inside the loop), dot products by warp shuffles
+// + one double atomic per CTA, convergence per sample (a converged sample freezes: alpha = beta = 0).
+#include <algorithm>
+
+#include "pcnn_common.cuh"
+
+namespace pcnn {
+
+constexpr int KR_THREADS = 256;
+
+__device__ __forceinline__ void block_atomic_add(double v, double* dst) {
+    __shared__ double red[KR_THREADS / 32];
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = threadIdx.x < KR_THREADS / 32 ? red[threadIdx.x] : 0.0;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) atomicAdd(dst, t);
+    }
+    __syncthreads();
+}
+
+// (A v)[i,j] = (deg * v[i,j] - sum of existing neighbours) / dh^2
+__device__ __forceinline__ float neumann_apply_at(const float* __restrict__ v, int i, int j, int H, int W, float q) {
+    const float c = v[(long long)i * W + j];
+    float acc = 0.f;
+    int deg = 0;
+    if (i > 0) { acc += v[(long long)(i - 1) * W + j]; ++deg; }
+    if (i < H - 1) { acc += v[(long long)(i + 1) * W + j]; ++deg; }
+    if (j > 0) { acc += v[(long long)i * W + j - 1]; ++deg; }
+    if (j < W - 1) { acc += v[(long long)i * W + j + 1]; ++deg; }
+    return ((float)deg * c - acc) * q;
+}
+
+// sums[b] += sum x[b,:]   (grid (blocks, B))
+__global__ void __launch_bounds__(KR_THREADS) kr_sum_kernel(const float* __restrict__ x, double* __restrict__ sums, long long n) {
+    const int b = blockIdx.y;
+    const float* xb = x + (long long)b * n;
+    double acc = 0.0;
+    for (long long i = blockIdx.x * (long long)KR_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * KR_THREADS) acc += (double)xb[i];
+    block_atomic_add(acc, sums + b);
+}
+
+// r = (-rhs - mean(-rhs)) - A x0,  p = r,  x = guess_scale[b] * x0 (in place),  rr += r.r,  bb += |b|^2
+__global__ void __launch_bounds__(KR_THREADS) kr_init_kernel(const float* __restrict__ rhs, const float* __restrict__ dx,
+                                                            const float* __restrict__ guess_scale, float* __restrict__ x,
+                                                            float* __restrict__ r, float* __restrict__ p,
+                                                            const double* __restrict__ rhs_sum, double* __restrict__ rr,
+                                                            double* __restrict__ bb, int H, int W) {
+    const int b = blockIdx.y;
+    const long long n = (long long)H * W;
+    const float q = 1.0f / (dx[b] * dx[b]);
+    const float mean_b = (float)(-rhs_sum[b] / (double)n);
+    const float gs = guess_scale ? guess_scale[b] : 1.0f;
+    float* xb = x + b * n;
+    const float* fb = rhs + b * n;
+    double a_rr = 0.0, a_bb = 0.0;
+    for (long long idx = blockIdx.x * (long long)KR_THREADS + threadIdx.x; idx < n; idx += (long long)gridDim.x * KR_THREADS) {
+        const int i = (int)(idx / W), j = (int)(idx - (long long)i * W);
+        const float bv = -fb[idx] - mean_b;
+        const float rv = bv - gs * neumann_apply_at(xb, i, j, H, W, q);
+        r[b * n + idx] = rv;
+        p[b * n + idx] = rv;
+        a_rr += (double)rv * rv;
+        a_bb += (double)bv * bv;
+    }
+    block_atomic_add(a_rr, rr + b);
+    block_atomic_add(a_bb, bb + b);
+}
+
+__global__ void kr_scale_kernel(float* __restrict__ x, const float* __restrict__ scale, long long n, long long total) {
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+        x[idx] *= scale[idx / n];
+}
+
+// q = A p ; pq[b] += p.q ; zeroes the accumulator the NEXT kernel will add into
+__global__ void __launch_bounds__(KR_THREADS) kr_apply_kernel(const float* __restrict__ p, const float* __restrict__ dx,
+                                                             float* __restrict__ qv, double* __restrict__ pq,
+                                                             double* __restrict__ rr_next, int H, int W) {
+    const int b = blockIdx.y;
+    const long long n = (long long)H * W;
+    if (blockIdx.x == 0 && threadIdx.x == 0) rr_next[b] = 0.0;
+    const float q = 1.0f / (dx[b] * dx[b]);
+    const float* pb = p + b * n;
+    double acc = 0.0;
+    for (long long idx = blockIdx.x * (long long)KR_THREADS + threadIdx.x; idx < n; idx += (long long)gridDim.x * KR_THREADS) {
+        const int i = (int)(idx / W), j = (int)(idx - (long long)i * W);
+        const float v = neumann_apply_at(pb, i, j, H, W, q);
+        qv[b * n + idx] = v;
+        acc += (double)pb[idx] * v;
+    }
+    block_atomic_add(acc, pq + b);
+}
+
+// alpha = rr/pq (0 once converged) ; x += alpha p ; r -= alpha q ; rr_next += r.r
+__global__ void __launch_bounds__(KR_THREADS) kr_update_kernel(float* __restrict__ x, float* __restrict__ r,
+                                                              const float* __restrict__ p, const float* __restrict__ qv,
+                                                              const double* __restrict__ rr, const double* __restrict__ pq,
+                                                              const double* __restrict__ bb, double* __restrict__ rr_next,
+                                                              double tol2, long long n) {
+    const int b = blockIdx.y;
+    const bool active = rr[b] > tol2 * bb[b] && pq[b] > 0.0;
+    const float alpha = active ? (float)(rr[b] / pq[b]) : 0.f;
+    double acc = 0.0;
+    for (long long idx = blockIdx.x * (long long)KR_THREADS + threadIdx.x; idx < n; idx += (long long)gridDim.x * KR_THREADS) {
+        const long long g = b * n + idx;
+        x[g] = fmaf(alpha, p[g], x[g]);
+        const float rv = fmaf(-alpha, qv[g], r[g]);
+        r[g] = rv;
+        acc += (double)rv * rv;
+    }
+    block_atomic_add(acc, rr_next + b);
+}
+
+// beta = rr_next/rr (0 once converged) ; p = r + beta p ; records rr_next ; zeroes pq for the next iteration
+__global__ void __launch_bounds__(KR_THREADS) kr_direction_kernel(float* __restrict__ p, const float* __restrict__ r,
+                                                                 const double* __restrict__ rr, const double* __restrict__ rr_next,
+                                                                 const double* __restrict__ bb, double* __restrict__ pq,
+                                                                 double* __restrict__ history, double tol2, long long n) {
+    const int b = blockIdx.y;
+    const bool active = rr[b] > tol2 * bb[b];
+    const float beta = active ? (float)(rr_next[b] / rr[b]) : 0.f;
+    for (long long idx = blockIdx.x * (long long)KR_THREADS + threadIdx.x; idx < n; idx += (long long)gridDim.x * KR_THREADS) {
+        const long long g = b * n + idx;
+        p[g] = fmaf(beta, p[g], r[g]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (history) history[b] = bb[b] > 0.0 ? sqrt(rr_next[b] / bb[b]) : 0.0;
+        pq[b] = 0.0;      // no block of this kernel reads pq (kr_update did); the next kr_apply accumulates into it
+    }
+}
+
+// out = A v (the operator alone: tests, residual checks)
+__global__ void __launch_bounds__(KR_THREADS) kr_apply_only_kernel(const float* __restrict__ p, const float* __restrict__ dx,
+                                                                  float* __restrict__ q, int H, int W) {
+    const int b = blockIdx.y;
+    const long long n = (long long)H * W;
+    const float qq = 1.0f / (dx[b] * dx[b]);
+    for (long long idx = blockIdx.x * (long long)KR_THREADS + threadIdx.x; idx < n; idx += (long long)gridDim.x * KR_THREADS) {
+        const int i = (int)(idx / W), j = (int)(idx - (long long)i * W);
+        q[b * n + idx] = neumann_apply_at(p + b * n, i, j, H, W, qq);
+    }
+}
+
+// x -= mean(x)
+__global__ void kr_center_kernel(float* __restrict__ x, const double* __restrict__ sums, long long n, long long total) {
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+        x[idx] -= (float)(sums[idx / n] / (double)n);
+}
+
+}  // namespace pcnn
+
+using namespace pcnn;
+
+extern "C" size_t pcnn_neumann_cg_workspace_bytes(int B, int H, int W) {
+    if (B <= 0 || H < 2 || W < 2) return 0;
+    // r, p, q (float, B*H*W each) + 6 double accumulators per sample
+    return (size_t)3 * B * H * W * sizeof(float) + (size_t)8 * B * sizeof(double);
+}
+
+extern "C" int pcnn_neumann_laplacian_apply_f32(const float* v, const float* dx, float* out, int B, int H, int W, void* stream) {
+    PCNN_CHECK_ARG(v && dx && out && v != out && B > 0 && B <= 65535 && H >= 2 && W >= 2, "neumann_laplacian_apply_f32: bad argument");
+    const long long n = (long long)H * W;
+    const int gx = (int)std::min<long long>((n + KR_THREADS * 4 - 1) / (KR_THREADS * 4), 2048);
+    kr_apply_only_kernel<<<dim3(gx, B), KR_THREADS, 0, (cudaStream_t)stream>>>(v, dx, out, H, W);
+    PCNN_CHECK_LAUNCH();
+    return PCNN_OK;
+}
+
+extern "C" int pcnn_neumann_cg_solve(const float* rhs, const float* dx, const float* guess_scale, float* x, int B, int H, int W,
+                                     int max_iter, double rel_tol, double* residual_history, void* workspace, void* stream) {
+    PCNN_CHECK_ARG(rhs && dx && x && workspace, "neumann_cg_solve: null pointer");
+    PCNN_CHECK_ARG(B > 0 && B <= 65535 && H >= 2 && W >= 2 && max_iter >= 0 && rel_tol >= 0.0, "neumann_cg_solve: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)H * W, total = n * B;
+    float* r = reinterpret_cast<float*>(workspace);
+    float* p = r + total;
+    float* q = p + total;
+    double* acc = reinterpret_cast<double*>(q + total);      // [rhs_sum | bb | pq | rr0 | rr1 | xsum] x B
+    PCNN_CHECK_ARG(((uintptr_t)acc & 7) == 0, "neumann_cg_solve: workspace must be 8-byte aligned");
+    double *rhs_sum = acc, *bb = acc + B, *pq = acc + 2 * B, *rr0 = acc + 3 * B, *rr1 = acc + 4 * B, *xsum = acc + 5 * B;
+    PCNN_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 8 * B, st));
+    const int gx = (int)std::min<long long>((n + KR_THREADS * 4 - 1) / (KR_THREADS * 4), 1024);
+    const dim3 grid(gx, B);
+    const double tol2 = rel_tol * rel_tol;
+    kr_sum_kernel<<<grid, KR_THREADS, 0, st>>>(rhs, rhs_sum, n);
+    PCNN_CHECK_LAUNCH();
+    kr_init_kernel<<<grid, KR_THREADS, 0, st>>>(rhs, dx, guess_scale, x, r, p, rhs_sum, rr0, bb, H, W);
+    PCNN_CHECK_LAUNCH();
+    if (guess_scale) {
+        const int gs = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+        kr_scale_kernel<<<gs, 256, 0, st>>>(x, guess_scale, n, total);
+        PCNN_CHECK_LAUNCH();
+    }
+    for (int it = 0; it < max_iter; ++it) {
+        double* rr = (it & 1) ? rr1 : rr0;
+        double* rr_next = (it & 1) ? rr0 : rr1;
+        kr_apply_kernel<<<grid, KR_THREADS, 0, st>>>(p, dx, q, pq, rr_next, H, W);
+        PCNN_CHECK_LAUNCH();
+        kr_update_kernel<<<grid, KR_THREADS, 0, st>>>(x, r, p, q, rr, pq, bb, rr_next, tol2, n);
+        PCNN_CHECK_LAUNCH();
+        kr_direction_kernel<<<grid, KR_THREADS, 0, st>>>(p, r, rr, rr_next, bb, pq, residual_history ? residual_history + (size_t)it * B : nullptr, tol2, n);
+        PCNN_CHECK_LAUNCH();
+    }
+    kr_sum_kernel<<<grid, KR_THREADS, 0, st>>>(x, xsum, n);
+    PCNN_CHECK_LAUNCH();
+    const int gs = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    kr_center_kernel<<<gs, 256, 0, st>>>(x, xsum, n, total);
+    PCNN_CHECK_LAUNCH();
+    return PCNN_OK;
+}

@@ -1,0 +1,67 @@
+"""GPU tests of the caller after the hot path: the pressure-Poisson solve of the reference's
+Navier-Stokes projection solver (Navier_Stokes_2D/solvers.py:153-334) as batched conjugate gradients seeded by the Neumann
+HPNN, against the oracle's direct solve of the reference's augmented system and its float64 CG restatement."""
+import pytest
+import torch
+
+from tests.helpers import rel_l2
+from oracle import poisson_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _rhs(B, m, n, seed):
+    from poisson_cnn_b200.synthetic import make_problem
+    p = make_problem(B, m, n, seed=seed)
+    return p["rhs"], p["dx"]
+
+
+def test_neumann_operator_matches_reference_matrix():
+    from poisson_cnn_b200.solvers import neumann_laplacian_apply
+    g = torch.Generator().manual_seed(3)
+    v = torch.randn(2, 1, 9, 12, generator=g)
+    dx = torch.tensor([[0.03], [0.011]])
+    got = neumann_laplacian_apply(v.cuda(), dx.cuda()).cpu().double()
+    for b in range(2):
+        A = O.pressure_poisson_matrix(9, 12, float(dx[b]))
+        ref = torch.from_numpy(A[:-1, :-1] @ v[b, 0].double().reshape(-1).numpy()).reshape(9, 12)
+        assert rel_l2(got[b, 0], ref) < 1e-5
+
+
+@pytest.mark.parametrize("B,m,n", [(2, 48, 40), (3, 64, 64), (1, 33, 130)])
+def test_pressure_solve_converges_to_the_reference_system(B, m, n):
+    from poisson_cnn_b200.solvers import pressure_poisson_solve
+    rhs, dx = _rhs(B, m, n, seed=60 + m)
+    ref = O.pressure_poisson_reference(rhs, dx)
+    p, hist = pressure_poisson_solve(rhs.cuda(), dx.cuda(), max_iter=600, rel_tol=1e-6, return_history=True)
+    assert p.shape == (B, 1, m, n)
+    assert rel_l2(p, ref) < 2e-4                       # fp32 vectors, condition number ~ (n/pi)^2
+    assert float(p.mean(dim=(1, 2, 3)).abs().max()) < 1e-6 * float(p.abs().max()) + 1e-9
+    assert float(hist[-1].max()) <= 1.01e-6            # every sample reached the tolerance and froze there
+    # the first iterations follow the float64 CG restatement
+    _, h64 = O.neumann_cg(rhs, dx, torch.zeros_like(rhs), 10)
+    assert torch.allclose(hist[:10].cpu(), h64, rtol=1e-3)
+
+
+def test_pressure_solve_seeded_by_the_neumann_hpnn():
+    """The reference's use of the network (solvers.py:246-262): the Neumann HPNN's prediction, rescaled by (dx (n-1))^2 / sf,
+    as x0.  The weights are seeded noise (no trained weights ship), so the guess cannot help; what is checked is that the
+    path runs end to end on the GPU, starts from the residual of THAT guess, and converges to the same solution."""
+    from poisson_cnn_b200 import convert_tf_object_names, load_experiment, models, weights as W
+    from poisson_cnn_b200.solvers import pressure_poisson_solve, hpnn_initial_guess, neumann_laplacian_apply
+    cfg = load_experiment("hpnn_neumann")["model"]
+    w = W.synthetic_weights(W.hpnn_weight_specs(cfg, "hpnn/"), seed=0)
+    model = models.Homogeneous_Poisson_NN_Legacy(**convert_tf_object_names(cfg)).load_weights(w, "hpnn/").set_precision("mixed")
+    rhs, dx = _rhs(2, 112, 120, seed=71)
+    rhs, dx = rhs.cuda(), dx.cuda()
+    ref = pressure_poisson_solve(rhs, dx, max_iter=900, rel_tol=1e-6)
+    p, hist = pressure_poisson_solve(rhs, dx, model=model, max_iter=900, rel_tol=1e-6, return_history=True)
+    assert bool(torch.isfinite(p).all()) and rel_l2(p, ref) < 5e-4
+    pred, scale = hpnn_initial_guess(model, rhs, dx)
+    x0 = pred * scale.view(-1, 1, 1, 1)
+    b = -rhs - (-rhs).mean(dim=(1, 2, 3), keepdim=True)
+    r0 = b - neumann_laplacian_apply(x0, dx)
+    # residual after the first iteration is below the initial one computed independently here (CG is monotone in the A-norm,
+    # and the history starts from this very residual)
+    rel0 = (r0.flatten(1).norm(dim=1) / b.flatten(1).norm(dim=1)).double()
+    assert bool((hist[0] <= rel0 * 1.5).all())

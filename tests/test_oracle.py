@@ -246,3 +246,23 @@ def test_tf2_resize_cross_checked_against_pillow():
             ref = np.asarray(img.resize((ow, oh), resample=pil), dtype=np.float64)
             got = O.resize(x.double()[None, None], (oh, ow), method)[0, 0].numpy()
             assert np.abs(got - ref).max() < tol * max(1.0, np.abs(ref).max()), (method, ih, iw, np.abs(got - ref).max())
+
+
+def test_pressure_projection_oracle_is_consistent():
+    """f4 (Navier_Stokes_2D/solvers.py:153-334): the replicate-padded stencil of the CG restatement IS the reference's
+    kron-built Neumann matrix, and CG on the mean-projected system converges to the direct solve of the augmented
+    (zero-integral Lagrange) system."""
+    g = torch.Generator().manual_seed(5)
+    m, n, dh = 9, 12, 0.03
+    A = O.pressure_poisson_matrix(m, n, dh)
+    v = torch.randn(1, 1, m, n, generator=g, dtype=torch.float64)
+    got = (A[:-1, :-1] @ v.reshape(-1).numpy()).reshape(m, n)
+    vp = torch.nn.functional.pad(v, (1, 1, 1, 1), mode="replicate")[0, 0]
+    ref = (4 * v[0, 0] - vp[:-2, 1:-1] - vp[2:, 1:-1] - vp[1:-1, :-2] - vp[1:-1, 2:]) / dh ** 2
+    np.testing.assert_allclose(got, ref.numpy(), rtol=1e-12, atol=1e-9)
+    rhs = torch.randn(2, 1, m, n, generator=g, dtype=torch.float64)
+    dx = torch.tensor([[0.03], [0.011]], dtype=torch.float64)
+    direct = O.pressure_poisson_reference(rhs, dx)
+    cg, hist = O.neumann_cg(rhs, dx, torch.zeros_like(rhs), 150)
+    assert float((cg - direct).norm() / direct.norm()) < 1e-6
+    assert float(hist[-1].max()) < 1e-9 and abs(float(direct.mean())) < 1e-12
