@@ -1670,10 +1670,12 @@ static int pcnn_run(Ctx& c, const float* rhs, const float* left, const float* to
     const size_t plane = (size_t)nx * ny;
     const float *L, *T, *R, *Bt;
     // The DBCNN's weights are shared by the four boundaries, so their problems can be batched: all four in one call for
-    // small batches (fills the GPU at batch 1), two per call in between, one per call for large ones.  Fewer, larger calls
-    // save the fixed cost of ~25 launches per call (measured at the headline shape: 4B 1176, B 1144 solutions/s) but the
-    // DBCNN's activations then are 4x / 2x the HPNN's: the middle tier keeps the planned workspace at ~15 GB.
-    static const long long side_px = std::getenv("PCNN_ENGINE_BATCH_SIDES_PX") ? std::atoll(std::getenv("PCNN_ENGINE_BATCH_SIDES_PX")) : 256LL * 65536;
+    // small batches (fills the GPU at batch 1), two per call in between, one per call once a single boundary already is
+    // >= 64 problems of 256x256 (thousands of tiles per launch).  Larger calls save the fixed cost of ~25 launches each, but
+    // the DBCNN's activations then are 4x / 2x the HPNN's.  Measured at the headline shape (B = 256 in 128-sample slices,
+    // back-to-back runs on one box, power-capped): 4B 1176, 2B 1142, B 1144 solutions/s -- inside the run-to-run spread, so
+    // the smaller workspace wins (12.2 GB instead of 17.6 / ~20 GB).
+    static const long long side_px = std::getenv("PCNN_ENGINE_BATCH_SIDES_PX") ? std::atoll(std::getenv("PCNN_ENGINE_BATCH_SIDES_PX")) : 64LL * 65536;
     const int group = ((long long)4 * Bcap * plane <= side_px) ? 4 : (((long long)2 * Bcap * plane <= side_px) ? 2 : 1);
     float* dxr = c.vec((size_t)4 * Bcap);
     for (int i = 0; i < 4; ++i)
