@@ -90,11 +90,24 @@ __device__ __forceinline__ void fft_stage(C* s, int tid, int q, int lp, const C*
 #pragma unroll
         for (int t = 0; t < R; ++t) u[t] = s[spos(i + t * Tn)];
         if (lp > 0) {
-            // per-stage table [t-1][k] (k < p) at offset p - 8: lanes with consecutive k read consecutive entries (a gather
-            // from one exp(-2 pi i j/L) table touched up to 32 cache lines per warp load and ran the FFT at L1-tag rate)
-            const C* tws = tw + (p - 8) + k;
-#pragma unroll
-            for (int t = 1; t < R; ++t) u[t] = cmul(u[t], ldgc(tws + ((t - 1) << lp)));
+            // w = exp(-2 pi i k / (p R)) from the per-stage table (entry [0][k] at offset p - 8: lanes with consecutive k read
+            // consecutive entries), its powers by multiplication: one table load per butterfly instead of R-1.  With all
+            // R-1 loaded, twiddles + chirp + spectrum tables (160 KB at L = 4096, double) overflowed what two resident
+            // CTAs leave of the L1 and the kernel sat in long-scoreboard stalls (ncu: profiles/r02_checks_full_raw.csv).
+            const C w1 = ldgc(tw + (p - 8) + k);
+            u[1] = cmul(u[1], w1);
+            if constexpr (R >= 4) {
+                const C w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+                u[2] = cmul(u[2], w2);
+                u[3] = cmul(u[3], w3);
+                if constexpr (R == 8) {
+                    const C w4 = cmul(w2, w2), w5 = cmul(w4, w1), w6 = cmul(w3, w3), w7 = cmul(w4, w3);
+                    u[4] = cmul(u[4], w4);
+                    u[5] = cmul(u[5], w5);
+                    u[6] = cmul(u[6], w6);
+                    u[7] = cmul(u[7], w7);
+                }
+            }
         }
         dftR<C, R>(u);
 #pragma unroll

@@ -12,7 +12,7 @@ PROF = os.path.join(ROOT, "profiles")
 # key -> [(capture file, samples per captured launch, weight = how many launches of a forward pass look like this one)]
 MANIFEST = {
     # 32->32 k15 tc2: of the four launches per forward, three have no residual input and one has
-    "conv2d_32_32_k15_tc2": [("r01_conv_tc_k15_tc2_b32_full_raw.csv", 32, 3), ("r01c_k15_tc2_full_raw.csv", 32, 1)],
+    "conv2d_32_32_k15_tc2": [("r01_conv_tc_k15_tc2_b32_full_raw.csv", 32, 3), ("r02_k15_tc2_res_b32_full_raw.csv", 32, 1)],
     "conv2d_32_32_k15_tc": [("r01_conv_tc_k15_tc1_b32_full_raw.csv", 32, 1)],
 }
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
