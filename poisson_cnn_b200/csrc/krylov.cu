@@ -17,6 +17,7 @@
 namespace pcnn {
 
 constexpr int KR_THREADS = 256;
+constexpr int kResidualReplacement = 50;     // iterations between recomputations of the true residual
 
 __device__ __forceinline__ void block_atomic_add(double v, double* dst) {
     __shared__ double red[KR_THREADS / 32];
@@ -52,7 +53,8 @@ __global__ void __launch_bounds__(KR_THREADS) kr_sum_kernel(const float* __restr
     block_atomic_add(acc, sums + b);
 }
 
-// r = (-rhs - mean(-rhs)) - A x0,  p = r,  x = guess_scale[b] * x0 (in place),  rr += r.r,  bb += |b|^2
+// r = (-rhs - mean(-rhs)) - gs A x,  p = r (if p),  rr += r.r,  bb += |b|^2 (if bb).  Also the residual-replacement step
+// of the iteration (p = bb = null, gs = 1): the recursively updated r is replaced by the true residual of the current x.
 __global__ void __launch_bounds__(KR_THREADS) kr_init_kernel(const float* __restrict__ rhs, const float* __restrict__ dx,
                                                             const float* __restrict__ guess_scale, float* __restrict__ x,
                                                             float* __restrict__ r, float* __restrict__ p,
@@ -71,12 +73,12 @@ __global__ void __launch_bounds__(KR_THREADS) kr_init_kernel(const float* __rest
         const float bv = -fb[idx] - mean_b;
         const float rv = bv - gs * neumann_apply_at(xb, i, j, H, W, q);
         r[b * n + idx] = rv;
-        p[b * n + idx] = rv;
+        if (p) p[b * n + idx] = rv;
         a_rr += (double)rv * rv;
         a_bb += (double)bv * bv;
     }
     block_atomic_add(a_rr, rr + b);
-    block_atomic_add(a_bb, bb + b);
+    if (bb) block_atomic_add(a_bb, bb + b);
 }
 
 __global__ void kr_scale_kernel(float* __restrict__ x, const float* __restrict__ scale, long long n, long long total) {
@@ -206,6 +208,13 @@ extern "C" int pcnn_neumann_cg_solve(const float* rhs, const float* dx, const fl
     for (int it = 0; it < max_iter; ++it) {
         double* rr = (it & 1) ? rr1 : rr0;
         double* rr_next = (it & 1) ? rr0 : rr1;
+        if (it > 0 && it % kResidualReplacement == 0) {
+            // residual replacement: in fp32 the recursively updated r drifts from b - A x (by ~eps * cond * max|x_k|, which is
+            // large when the initial guess is far off); the search direction is kept, so convergence is not restarted
+            PCNN_CHECK_CUDA(cudaMemsetAsync(rr, 0, sizeof(double) * B, st));
+            kr_init_kernel<<<grid, KR_THREADS, 0, st>>>(rhs, dx, nullptr, x, r, nullptr, rhs_sum, rr, nullptr, H, W);
+            PCNN_CHECK_LAUNCH();
+        }
         kr_apply_kernel<<<grid, KR_THREADS, 0, st>>>(p, dx, q, pq, rr_next, H, W);
         PCNN_CHECK_LAUNCH();
         kr_update_kernel<<<grid, KR_THREADS, 0, st>>>(x, r, p, q, rr, pq, bb, rr_next, tol2, n);
