@@ -205,9 +205,11 @@ class Harness:
     """Process-group plumbing + CUDA-event timing shared by all configs."""
 
     def __init__(self, args):
-        # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION) would land there too
+        # stdout carries exactly one JSON line: NCCL writes its version banner (NCCL_DEBUG=VERSION / WARN) and its log to
+        # stdout by default, so its output is sent to stderr and the banner-only level is switched off
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+            os.environ["NCCL_DEBUG"] = "NONE"
         import torch.distributed as dist
         from poisson_cnn_b200.sharding import init_from_env
         self.dist = dist
