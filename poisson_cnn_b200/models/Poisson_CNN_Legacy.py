@@ -5,6 +5,10 @@ with rhs [B,1,nx,ny], left/right [B,1,ny], top/bottom [B,1,nx], dx [B,1] -> [B,1
 The DBCNN weights are shared by the four boundaries, so the four calls are batched (4B when
 nx == ny, otherwise 2B + 2B); the rot90/flip of flip_and_rotate_tensor and the 1/scaling-factor
 rescales are folded into the final merge kernel.
+
+Like the reference, every input is divided by its per-sample max|.| (set_max_magnitude_in_batch_and_return_scaling_factors,
+Poisson_CNN_Legacy.py:23-28): an all-zero right-hand side or boundary (a homogeneous problem) gives 1/0 = inf and a NaN
+prediction for that sample -- the reference's behaviour, kept deliberately; pass the homogeneous part to the HPNN alone.
 """
 import torch
 

@@ -434,6 +434,17 @@ def load_checkpoint_weights(ckpt_prefix, key_map, verify=False):
     if missing:
         have = [k for k in raw if k.endswith(SUFFIX)][:5]
         raise ValueError("TF checkpoint %s lacks %d variables, e.g. %s (it has e.g. %s)" % (ckpt_prefix, len(missing), missing[:3], have))
+    # model variables the checkpoint holds but the key map does not name: a silent naming drift would hide here
+    used = {ref + SUFFIX for ref in key_map}
+    extra = [k for k in raw if k.endswith(SUFFIX) and k not in used and "optimizer" not in k and "save_counter" not in k
+             and not k.startswith("_CHECKPOINTABLE_OBJECT_GRAPH")]
+    import warnings
+    if extra:
+        warnings.warn("TF checkpoint %s holds %d model variables this model does not use, e.g. %s" % (ckpt_prefix, len(extra), extra[:3]))
+    if not os.path.isfile(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "tf_ckpt", "pcnn.index")):
+        warnings.warn("the TensorFlow tensor-bundle reader and the Keras key map have not been verified against a TensorFlow-written "
+                      "checkpoint yet (no TensorFlow in the build environment; tests/golden/make_tf_fixtures.py generates the "
+                      "fixture): a naming mismatch would surface as a 'lacks N variables' error above", stacklevel=2)
     return out
 
 

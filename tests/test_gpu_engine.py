@@ -187,3 +187,59 @@ def test_host_launch_overhead_is_small(setup):
     torch.cuda.synchronize()
     print("host time per engine forward (B=1, 256x256, mixed): median %.3f ms, min %.3f ms" % (1e3 * sorted(ts)[5], 1e3 * min(ts)))
     assert sorted(ts)[5] < 2.5e-3
+
+
+def _variant(name):
+    """Config variants that steer the layer program into its less-travelled branches."""
+    import copy
+    hp, db = pcnn_configs()
+    hp, db = copy.deepcopy(hp), copy.deepcopy(db)
+    if name == "filters16":               # F != 32: no tensor-core upsample-merge, fused fp32-input merge kernel
+        for k in ("bottleneck_deconv_config", "bottleneck_multilinear_config"):
+            hp[k]["filters"] = 16
+        hp["pre_bottleneck_convolutions_config"]["filters"] = [4, 8, 16]
+    elif name == "no_scaling_smoother":   # no Scaling block, post-smoother and merged-model Jacobi sweeps on
+        hp["use_scaling"] = False
+        hp["postsmoother_iterations"] = 2
+        db["postsmoother_iterations"] = 1
+    elif name == "few_branches":          # other branch lists (ds = 2, 5 deconv; 16 bilinear), no BatchNorm, no position channels
+        hp["bottleneck_deconv_config"].update(downsampling_factors=[2, 4], upsampling_factors=[2, 4], deconv_kernel_sizes=[2, 4],
+                                              conv_kernel_sizes=[7, 5], n_convs=[2, 3])
+        hp["bottleneck_multilinear_config"].update(downsampling_factors=[16], upsampling_factors=[16], conv_kernel_sizes=[3],
+                                                   n_convs=[2], resize_methods=["bilinear"])
+        hp["use_batchnorm"] = False
+        hp["use_positional_embeddings"] = False
+        db["use_batchnorm"] = False
+    elif name == "constant_pad":          # CONSTANT padding everywhere, reflect in the 1-D stack's place is not TC-relevant
+        hp["pre_bottleneck_convolutions_config"]["padding_mode"] = "CONSTANT"
+        hp["bottleneck_deconv_config"]["padding_mode"] = "CONSTANT"
+        db["boundary_conv_config"]["padding_mode"] = "CONSTANT"
+    return hp, db
+
+
+@pytest.mark.parametrize("variant,nx,ny", [("filters16", 96, 128), ("no_scaling_smoother", 112, 120), ("few_branches", 64, 80),
+                                            ("constant_pad", 128, 112), ("base", 48, 704), ("base", 256, 40)])
+def test_engine_matches_python_program_on_variants(variant, nx, ny):
+    """The C++ layer program against the op-by-op Python program, bit for bit, on configs and shapes that take the
+    fallback branches: general (unfused) merge, fused fp32-input merge, FP32 small-map chain without the stack kernel,
+    1-D stack too long for shared memory (n = 704), maps smaller than the halo, post-smoothers."""
+    from poisson_cnn_b200 import convert_tf_object_names, models, weights as W
+    from poisson_cnn_b200.synthetic import make_problem
+    hp, db = pcnn_configs() if variant == "base" else _variant(variant)
+    hs, ds = W.hpnn_weight_specs(hp, "hpnn/"), W.dbcnn_weight_specs(db, "dbcnn/")
+    w = W.synthetic_weights(({**hs[0], **ds[0]}, {**hs[1], **ds[1]}), seed=3)
+
+    def build(py):
+        m = models.Poisson_CNN_Legacy(models.Homogeneous_Poisson_NN_Legacy(**convert_tf_object_names(hp)),
+                                      models.Dirichlet_BC_NN_Legacy_2(**convert_tf_object_names(db)),
+                                      jacobi_iterations=1 if variant == "no_scaling_smoother" else 0).load_weights(w)
+        if py:
+            m.use_engine = m.hpnn.use_engine = m.dbcnn.use_engine = False
+        return m
+    p = make_problem(2, nx, ny, seed=900 + nx)
+    inp = [p[k].cuda() for k in KEYS]
+    me, mp = build(False), build(True)
+    for mode in ("fp32", "mixed", "tc2", "tc3"):
+        a, b = me.set_precision(mode)(inp), mp.set_precision(mode)(inp)
+        same = torch.equal(a, b) or (bool(torch.isnan(a).any()) and torch.equal(torch.nan_to_num(a, nan=7.0), torch.nan_to_num(b, nan=7.0)))
+        assert same, (variant, mode, rel_l2(a, b))
