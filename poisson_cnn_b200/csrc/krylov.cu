@@ -17,7 +17,6 @@
 namespace pcnn {
 
 constexpr int KR_THREADS = 256;
-constexpr int kResidualReplacement = 50;     // iterations between recomputations of the true residual
 
 __device__ __forceinline__ void block_atomic_add(double v, double* dst) {
     __shared__ double red[KR_THREADS / 32];
@@ -53,8 +52,7 @@ __global__ void __launch_bounds__(KR_THREADS) kr_sum_kernel(const float* __restr
     block_atomic_add(acc, sums + b);
 }
 
-// r = (-rhs - mean(-rhs)) - gs A x,  p = r (if p),  rr += r.r,  bb += |b|^2 (if bb).  Also the residual-replacement step
-// of the iteration (p = bb = null, gs = 1): the recursively updated r is replaced by the true residual of the current x.
+// r = (-rhs - mean(-rhs)) - gs A x0,  p = r,  rr += r.r,  bb += |b|^2  (x is scaled by gs afterwards)
 __global__ void __launch_bounds__(KR_THREADS) kr_init_kernel(const float* __restrict__ rhs, const float* __restrict__ dx,
                                                             const float* __restrict__ guess_scale, float* __restrict__ x,
                                                             float* __restrict__ r, float* __restrict__ p,
@@ -208,13 +206,6 @@ extern "C" int pcnn_neumann_cg_solve(const float* rhs, const float* dx, const fl
     for (int it = 0; it < max_iter; ++it) {
         double* rr = (it & 1) ? rr1 : rr0;
         double* rr_next = (it & 1) ? rr0 : rr1;
-        if (it > 0 && it % kResidualReplacement == 0) {
-            // residual replacement: in fp32 the recursively updated r drifts from b - A x (by ~eps * cond * max|x_k|, which is
-            // large when the initial guess is far off); the search direction is kept, so convergence is not restarted
-            PCNN_CHECK_CUDA(cudaMemsetAsync(rr, 0, sizeof(double) * B, st));
-            kr_init_kernel<<<grid, KR_THREADS, 0, st>>>(rhs, dx, nullptr, x, r, nullptr, rhs_sum, rr, nullptr, H, W);
-            PCNN_CHECK_LAUNCH();
-        }
         kr_apply_kernel<<<grid, KR_THREADS, 0, st>>>(p, dx, q, pq, rr_next, H, W);
         PCNN_CHECK_LAUNCH();
         kr_update_kernel<<<grid, KR_THREADS, 0, st>>>(x, r, p, q, rr, pq, bb, rr_next, tol2, n);
