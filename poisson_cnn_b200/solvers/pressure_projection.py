@@ -36,11 +36,12 @@ def hpnn_initial_guess(model, rhs, dx):
     return pred, scale.contiguous()
 
 
-def pressure_poisson_solve(rhs, dx, model=None, max_iter=200, rel_tol=1e-6, return_history=False):
+def pressure_poisson_solve(rhs, dx, model=None, x0=None, max_iter=200, rel_tol=1e-6, return_history=False):
     """Solve  laplace(p) = rhs  with homogeneous Neumann boundaries and zero mean (Poisson_pressure_solver, solvers.py:204-334).
-    rhs [B,1,m,n] (CUDA), dx [B,1]; model: a Neumann Homogeneous_Poisson_NN_Legacy whose prediction seeds the iteration
-    (None: zero initial guess, the reference's current default).  Returns p [B,1,m,n] (and the [max_iter,B] history of
-    relative residuals |r_k|/|b| when return_history).  No host synchronisation."""
+    rhs [B,1,m,n] (CUDA), dx [B,1]; model: a Neumann Homogeneous_Poisson_NN_Legacy whose prediction seeds the iteration, or
+    x0: an explicit initial guess [B,1,m,n] (neither: zero initial guess, the reference's current default).  Returns p
+    [B,1,m,n] (and the [max_iter,B] history of relative residuals |r_k|/|b| when return_history).  No host synchronisation.
+    Vectors are fp32: the iteration reaches ~eps * cond * max(|x0|, |p|), so a guess far larger than the solution costs digits."""
     ops._chk(rhs, "rhs")
     ops._chk(dx, "dx")
     if rhs.dim() != 4 or rhs.shape[1] != 1:
@@ -48,9 +49,16 @@ def pressure_poisson_solve(rhs, dx, model=None, max_iter=200, rel_tol=1e-6, retu
     B, _, H, W = rhs.shape
     rhs = rhs.contiguous()
     dxv = dx.reshape(B).contiguous()
+    if model is not None and x0 is not None:
+        raise ValueError("pass either model= or x0=, not both")
     if model is not None:
         x, scale = hpnn_initial_guess(model, rhs, dx.reshape(B, 1).contiguous())
         x = x.contiguous()
+    elif x0 is not None:
+        ops._chk(x0, "x0")
+        if tuple(x0.shape) != tuple(rhs.shape):
+            raise ValueError("x0 must have the shape of rhs")
+        x, scale = x0.clone().contiguous(), None
     else:
         x, scale = torch.zeros_like(rhs), None
     work = torch.empty((lib.pcnn_neumann_cg_workspace_bytes(B, H, W) + 7) // 8, device=rhs.device, dtype=torch.float64)
