@@ -10,6 +10,10 @@
 // ILU preconditioner on the CPU; here it is batched conjugate gradients on the GPU: three HBM-bound kernels per iteration,
 // per-sample step lengths computed on the device (no host synchronisation inside the loop), dot products by warp shuffles
 // + one double atomic per CTA, convergence per sample (a converged sample freezes: alpha = beta = 0).
+// A is singular: rounding leaves a constant component in r that A can never reduce (p.Ap does not see it, r.r does), so
+// alpha = r.r / p.Ap explodes once |r| approaches it (fp32: ~sqrt(n) eps |b| = 6e-6 |b| at 100 x 100, above a 1e-6 tolerance).
+// Every use of r is therefore projected onto zero mean: sum(r) is accumulated next to r.r, p = (r - mean r) + beta p, and
+// the norms are |r|^2 - (sum r)^2 / n.
 #include <algorithm>
 
 #include "pcnn_common.cuh"
@@ -52,31 +56,34 @@ __global__ void __launch_bounds__(KR_THREADS) kr_sum_kernel(const float* __restr
     block_atomic_add(acc, sums + b);
 }
 
-// r = (-rhs - mean(-rhs)) - gs A x0,  p = r,  rr += r.r,  bb += |b|^2  (x is scaled by gs afterwards)
+// r = (-rhs - mean(-rhs)) - gs A x0,  p = 0 (the first direction kernel makes it r - mean r),  rr += r.r,  rs += sum r,
+// bb += |b|^2   (x is scaled by gs afterwards)
 __global__ void __launch_bounds__(KR_THREADS) kr_init_kernel(const float* __restrict__ rhs, const float* __restrict__ dx,
-                                                            const float* __restrict__ guess_scale, float* __restrict__ x,
+                                                            const float* __restrict__ guess_scale, const float* __restrict__ x,
                                                             float* __restrict__ r, float* __restrict__ p,
                                                             const double* __restrict__ rhs_sum, double* __restrict__ rr,
-                                                            double* __restrict__ bb, int H, int W) {
+                                                            double* __restrict__ rs, double* __restrict__ bb, int H, int W) {
     const int b = blockIdx.y;
     const long long n = (long long)H * W;
     const float q = 1.0f / (dx[b] * dx[b]);
     const float mean_b = (float)(-rhs_sum[b] / (double)n);
     const float gs = guess_scale ? guess_scale[b] : 1.0f;
-    float* xb = x + b * n;
+    const float* xb = x + b * n;
     const float* fb = rhs + b * n;
-    double a_rr = 0.0, a_bb = 0.0;
+    double a_rr = 0.0, a_rs = 0.0, a_bb = 0.0;
     for (long long idx = blockIdx.x * (long long)KR_THREADS + threadIdx.x; idx < n; idx += (long long)gridDim.x * KR_THREADS) {
         const int i = (int)(idx / W), j = (int)(idx - (long long)i * W);
         const float bv = -fb[idx] - mean_b;
         const float rv = bv - gs * neumann_apply_at(xb, i, j, H, W, q);
         r[b * n + idx] = rv;
-        if (p) p[b * n + idx] = rv;
+        p[b * n + idx] = 0.f;
         a_rr += (double)rv * rv;
+        a_rs += (double)rv;
         a_bb += (double)bv * bv;
     }
     block_atomic_add(a_rr, rr + b);
-    if (bb) block_atomic_add(a_bb, bb + b);
+    block_atomic_add(a_rs, rs + b);
+    block_atomic_add(a_bb, bb + b);
 }
 
 __global__ void kr_scale_kernel(float* __restrict__ x, const float* __restrict__ scale, long long n, long long total) {
@@ -84,13 +91,13 @@ __global__ void kr_scale_kernel(float* __restrict__ x, const float* __restrict__
         x[idx] *= scale[idx / n];
 }
 
-// q = A p ; pq[b] += p.q ; zeroes the accumulator the NEXT kernel will add into
+// q = A p ; pq[b] += p.q ; zeroes the accumulators the NEXT kernel will add into
 __global__ void __launch_bounds__(KR_THREADS) kr_apply_kernel(const float* __restrict__ p, const float* __restrict__ dx,
                                                              float* __restrict__ qv, double* __restrict__ pq,
-                                                             double* __restrict__ rr_next, int H, int W) {
+                                                             double* __restrict__ rr_next, double* __restrict__ rs_next, int H, int W) {
     const int b = blockIdx.y;
     const long long n = (long long)H * W;
-    if (blockIdx.x == 0 && threadIdx.x == 0) rr_next[b] = 0.0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { rr_next[b] = 0.0; rs_next[b] = 0.0; }
     const float q = 1.0f / (dx[b] * dx[b]);
     const float* pb = p + b * n;
     double acc = 0.0;
@@ -103,40 +110,49 @@ __global__ void __launch_bounds__(KR_THREADS) kr_apply_kernel(const float* __res
     block_atomic_add(acc, pq + b);
 }
 
-// alpha = rr/pq (0 once converged) ; x += alpha p ; r -= alpha q ; rr_next += r.r
+// alpha = |r - mean r|^2 / p.q (0 once converged) ; x += alpha p ; r -= alpha q ; rr_next += r.r ; rs_next += sum r
 __global__ void __launch_bounds__(KR_THREADS) kr_update_kernel(float* __restrict__ x, float* __restrict__ r,
                                                               const float* __restrict__ p, const float* __restrict__ qv,
-                                                              const double* __restrict__ rr, const double* __restrict__ pq,
-                                                              const double* __restrict__ bb, double* __restrict__ rr_next,
+                                                              const double* __restrict__ rr, const double* __restrict__ rs,
+                                                              const double* __restrict__ pq, const double* __restrict__ bb,
+                                                              double* __restrict__ rr_next, double* __restrict__ rs_next,
                                                               double tol2, long long n) {
     const int b = blockIdx.y;
-    const bool active = rr[b] > tol2 * bb[b] && pq[b] > 0.0;
-    const float alpha = active ? (float)(rr[b] / pq[b]) : 0.f;
-    double acc = 0.0;
+    const double rrp = fmax(rr[b] - rs[b] * rs[b] / (double)n, 0.0);
+    const bool active = rrp > tol2 * bb[b] && pq[b] > 0.0;
+    const float alpha = active ? (float)(rrp / pq[b]) : 0.f;
+    double acc = 0.0, accs = 0.0;
     for (long long idx = blockIdx.x * (long long)KR_THREADS + threadIdx.x; idx < n; idx += (long long)gridDim.x * KR_THREADS) {
         const long long g = b * n + idx;
         x[g] = fmaf(alpha, p[g], x[g]);
         const float rv = fmaf(-alpha, qv[g], r[g]);
         r[g] = rv;
         acc += (double)rv * rv;
+        accs += (double)rv;
     }
     block_atomic_add(acc, rr_next + b);
+    block_atomic_add(accs, rs_next + b);
 }
 
-// beta = rr_next/rr (0 once converged) ; p = r + beta p ; records rr_next ; zeroes pq for the next iteration
+// beta = |r_next|^2 / |r|^2 (projected norms; 0 once converged and for the very first direction) ; p = (r - mean r) + beta p ;
+// records the relative residual ; zeroes pq for the next iteration
 __global__ void __launch_bounds__(KR_THREADS) kr_direction_kernel(float* __restrict__ p, const float* __restrict__ r,
-                                                                 const double* __restrict__ rr, const double* __restrict__ rr_next,
+                                                                 const double* __restrict__ rr, const double* __restrict__ rs,
+                                                                 const double* __restrict__ rr_next, const double* __restrict__ rs_next,
                                                                  const double* __restrict__ bb, double* __restrict__ pq,
-                                                                 double* __restrict__ history, double tol2, long long n) {
+                                                                 double* __restrict__ history, double tol2, long long n, int first) {
     const int b = blockIdx.y;
-    const bool active = rr[b] > tol2 * bb[b];
-    const float beta = active ? (float)(rr_next[b] / rr[b]) : 0.f;
+    const double rrp = fmax(rr[b] - rs[b] * rs[b] / (double)n, 0.0);
+    const double rrp_next = fmax(rr_next[b] - rs_next[b] * rs_next[b] / (double)n, 0.0);
+    const bool active = !first && rrp > tol2 * bb[b];
+    const float beta = active ? (float)(rrp_next / rrp) : 0.f;
+    const float mean = (float)(rs_next[b] / (double)n);
     for (long long idx = blockIdx.x * (long long)KR_THREADS + threadIdx.x; idx < n; idx += (long long)gridDim.x * KR_THREADS) {
         const long long g = b * n + idx;
-        p[g] = fmaf(beta, p[g], r[g]);
+        p[g] = fmaf(beta, p[g], r[g] - mean);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        if (history) history[b] = bb[b] > 0.0 ? sqrt(rr_next[b] / bb[b]) : 0.0;
+        if (history) history[b] = bb[b] > 0.0 ? sqrt(rrp_next / bb[b]) : 0.0;
         pq[b] = 0.0;      // no block of this kernel reads pq (kr_update did); the next kr_apply accumulates into it
     }
 }
@@ -187,30 +203,34 @@ extern "C" int pcnn_neumann_cg_solve(const float* rhs, const float* dx, const fl
     float* r = reinterpret_cast<float*>(workspace);
     float* p = r + total;
     float* q = p + total;
-    double* acc = reinterpret_cast<double*>(q + total);      // [rhs_sum | bb | pq | rr0 | rr1 | xsum] x B
+    double* acc = reinterpret_cast<double*>(q + total);      // [rhs_sum | bb | pq | rr0 | rr1 | xsum | rs0 | rs1] x B
     PCNN_CHECK_ARG(((uintptr_t)acc & 7) == 0, "neumann_cg_solve: workspace must be 8-byte aligned");
     double *rhs_sum = acc, *bb = acc + B, *pq = acc + 2 * B, *rr0 = acc + 3 * B, *rr1 = acc + 4 * B, *xsum = acc + 5 * B;
+    double *rs0 = acc + 6 * B, *rs1 = acc + 7 * B;
     PCNN_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 8 * B, st));
     const int gx = (int)std::min<long long>((n + KR_THREADS * 4 - 1) / (KR_THREADS * 4), 1024);
     const dim3 grid(gx, B);
     const double tol2 = rel_tol * rel_tol;
     kr_sum_kernel<<<grid, KR_THREADS, 0, st>>>(rhs, rhs_sum, n);
     PCNN_CHECK_LAUNCH();
-    kr_init_kernel<<<grid, KR_THREADS, 0, st>>>(rhs, dx, guess_scale, x, r, p, rhs_sum, rr0, bb, H, W);
+    kr_init_kernel<<<grid, KR_THREADS, 0, st>>>(rhs, dx, guess_scale, x, r, p, rhs_sum, rr0, rs0, bb, H, W);
     PCNN_CHECK_LAUNCH();
     if (guess_scale) {
         const int gs = (int)std::min<long long>((total + 255) / 256, 148 * 16);
         kr_scale_kernel<<<gs, 256, 0, st>>>(x, guess_scale, n, total);
         PCNN_CHECK_LAUNCH();
     }
+    kr_direction_kernel<<<grid, KR_THREADS, 0, st>>>(p, r, rr0, rs0, rr0, rs0, bb, pq, nullptr, tol2, n, 1);     // p = r - mean(r)
+    PCNN_CHECK_LAUNCH();
     for (int it = 0; it < max_iter; ++it) {
-        double* rr = (it & 1) ? rr1 : rr0;
-        double* rr_next = (it & 1) ? rr0 : rr1;
-        kr_apply_kernel<<<grid, KR_THREADS, 0, st>>>(p, dx, q, pq, rr_next, H, W);
+        double *rr = (it & 1) ? rr1 : rr0, *rs = (it & 1) ? rs1 : rs0;
+        double *rr_next = (it & 1) ? rr0 : rr1, *rs_next = (it & 1) ? rs0 : rs1;
+        kr_apply_kernel<<<grid, KR_THREADS, 0, st>>>(p, dx, q, pq, rr_next, rs_next, H, W);
         PCNN_CHECK_LAUNCH();
-        kr_update_kernel<<<grid, KR_THREADS, 0, st>>>(x, r, p, q, rr, pq, bb, rr_next, tol2, n);
+        kr_update_kernel<<<grid, KR_THREADS, 0, st>>>(x, r, p, q, rr, rs, pq, bb, rr_next, rs_next, tol2, n);
         PCNN_CHECK_LAUNCH();
-        kr_direction_kernel<<<grid, KR_THREADS, 0, st>>>(p, r, rr, rr_next, bb, pq, residual_history ? residual_history + (size_t)it * B : nullptr, tol2, n);
+        kr_direction_kernel<<<grid, KR_THREADS, 0, st>>>(p, r, rr, rs, rr_next, rs_next, bb, pq,
+                                                         residual_history ? residual_history + (size_t)it * B : nullptr, tol2, n, 0);
         PCNN_CHECK_LAUNCH();
     }
     kr_sum_kernel<<<grid, KR_THREADS, 0, st>>>(x, xsum, n);
