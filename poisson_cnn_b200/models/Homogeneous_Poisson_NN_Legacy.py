@@ -239,23 +239,10 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
     def _tc_ok(self, ksize, pad_value=0.0):
         return ksize % 2 == 1 and ksize <= 15 and float(pad_value) == 0.0
 
-    def _call_tc(self, rhs, dx):
-        """Same graph as the FP32 path with every heavy convolution on tcgen05 (BLK8 fp16 activations).
-        FP32 kernels keep: pooling / upsampling / merge, the 2..8-pixel multilinear branches, Scaling and
-        the boundary ring."""
-        B, _, H, Wd = rhs.shape
+    def _branches_tc(self, x0_f32, H, Wd, split):
+        """pool -> conv -> resnets of every bottleneck branch from the full-resolution NCHW fp32 features (the pooling pyramid
+        reads them); returns the low-res branch outputs for _merge_tc."""
         F = self.filters
-        dev = rhs.device
-        x = ops.hpnn_input(rhs) if self.use_positional_embeddings else rhs
-        split = self.tc_split
-        t = ops.to_blk8(x, split=split, halo=self.pre_pad)
-        for k in range(self.n_pre):
-            t = self._conv_tc(t, "pre_bottleneck/%d" % k, self.pre_act, self.pre_pad,
-                              "pre_bottleneck/%d/bn" % k if self.use_batchnorm else None,
-                              next_pad=self.pre_pad if k + 1 < self.n_pre else PAD_CONSTANT)
-        x0 = t                                   # BLK8, F channels
-        x0_f32 = ops.from_blk8(x0)               # pooling pyramid reads NCHW fp32
-
         blocks = self.bottleneck_deconv_blocks + self.bottleneck_multilinear_blocks
         alpha = 1.0 / float(len(blocks) * F)
         dc, rs = [], []                          # low-res branch outputs, upsampled and summed by ONE fused kernel
@@ -293,8 +280,12 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
             else:
                 rs.append((h, blk.resize_method))
 
-        cat = ops.Blk8(B, 2 * F, H, Wd, dev, split=split)
-        self._conv_tc(x0, "non_bottleneck_conv", ACT_LEAKY_RELU, PAD_CONSTANT, out=cat)
+        return dc, rs, um_tc, alpha
+
+    def _merge_tc(self, branches, cat, B, H, Wd, dev):
+        """All upsamplings + the branch sum written into channels [F, 2F) of the BLK8 tensor `cat` (one fused kernel)."""
+        dc, rs, um_tc, alpha = branches
+        F = self.filters
         fused = (F % 8 == 0 and len(dc) <= 8 and len(rs) <= 8
                  and all(tuple(k.shape) == (s_, s_, F, F) and s_ <= 32 for _, k, _, s_, _ in dc)
                  and all(F * h.shape[2] * h.shape[3] <= 8192 for h, _ in rs))
@@ -323,6 +314,28 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
             for i, (h, method) in enumerate(rs):
                 ops.resize(h, (H, Wd), method, alpha, out=merged, accumulate=(i != 0 or bool(dc)))
             ops.to_blk8(merged, out=cat, c_offset=F)
+
+    def _call_tc(self, rhs, dx):
+        """Same graph as the FP32 path with every heavy convolution on tcgen05 (BLK8 fp16 activations).
+        FP32 kernels keep: pooling / upsampling / merge, the 2..8-pixel multilinear branches, Scaling and
+        the boundary ring."""
+        B, _, H, Wd = rhs.shape
+        F = self.filters
+        dev = rhs.device
+        x = ops.hpnn_input(rhs) if self.use_positional_embeddings else rhs
+        split = self.tc_split
+        t = ops.to_blk8(x, split=split, halo=self.pre_pad)
+        for k in range(self.n_pre):
+            t = self._conv_tc(t, "pre_bottleneck/%d" % k, self.pre_act, self.pre_pad,
+                              "pre_bottleneck/%d/bn" % k if self.use_batchnorm else None,
+                              next_pad=self.pre_pad if k + 1 < self.n_pre else PAD_CONSTANT)
+        x0 = t                                   # BLK8, F channels
+        x0_f32 = ops.from_blk8(x0)               # pooling pyramid reads NCHW fp32
+
+        branches = self._branches_tc(x0_f32, H, Wd, split)
+        cat = ops.Blk8(B, 2 * F, H, Wd, dev, split=split)
+        self._conv_tc(x0, "non_bottleneck_conv", ACT_LEAKY_RELU, PAD_CONSTANT, out=cat)
+        self._merge_tc(branches, cat, B, H, Wd, dev)
         y = self._conv_tc(cat, "post_merge_conv", ACT_LEAKY_RELU, PAD_CONSTANT)
 
         d = ops.dense_input(dx, H, Wd)
