@@ -62,6 +62,22 @@ class SpatialHPNN:
             self.local = list(range(self.world))       # emulation: every band lives in this process
         self.pools = {i: {} for i in self.local}        # private BLK8 pools: band buffers carry neighbour rows in their halos
         self.full_pool = {}
+        self.profile = None                             # set to {} to collect CUDA-event times per phase (ms, last call)
+
+    def _tick(self, name):
+        if self.profile is None:
+            return
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self._marks.append((name, e))
+
+    def _report(self):
+        if self.profile is None:
+            return
+        torch.cuda.synchronize()
+        self.profile.clear()
+        for (n0, e0), (n1, e1) in zip(self._marks[:-1], self._marks[1:]):
+            self.profile[n1] = self.profile.get(n1, 0.0) + e0.elapsed_time(e1)
 
     # ------------------------------------------------------------------ exchange
     def _exchange(self, ts):
@@ -150,6 +166,8 @@ class SpatialHPNN:
         split = m.tc_split
         rhs = rhs.contiguous()
         with torch.cuda.device(dev):
+            self._marks = []
+            self._tick("start")
             posx, posy = ops.position_table(dev, H), ops.position_table(dev, Wd)
 
             def first(i):
@@ -167,13 +185,17 @@ class SpatialHPNN:
                 t = self._conv(t, "pre_bottleneck/%d" % k, m.pre_act, m.pre_pad, "pre_bottleneck/%d/bn" % k if m.use_batchnorm else None,
                                next_pad=m.pre_pad if k + 1 < m.n_pre else PAD_CONSTANT)
             x0 = t
+            self._tick("pre_bottleneck (banded)")
             # the bottleneck branches need the whole map: gather the band features, run the low-resolution branches and the
             # fused upsample-merge replicated, keep this rank's rows of the merged map
             x0_full = self._gather_rows(self._each(lambda i: ops.from_blk8(x0[i])))
+            self._tick("gather x0")
             with ops.blk8_pool_scope(self.full_pool):
                 branches = m._branches_tc(x0_full, H, Wd, split)
+                self._tick("branches (replicated)")
                 cat_full = ops.Blk8(B, 2 * F, H, Wd, dev, split=split)
                 m._merge_tc(branches, cat_full, B, H, Wd, dev)
+                self._tick("upsample-merge (replicated)")
             cat = self._each(lambda i: ops.Blk8(B, 2 * F, h, Wd, dev, split=split))
             self._conv(x0, "non_bottleneck_conv", ACT_LEAKY_RELU, PAD_CONSTANT, out=cat)
             p0 = (F // 16) * 2                       # first plane of channels [F, 2F)
@@ -185,6 +207,7 @@ class SpatialHPNN:
                     _view(cat[i], which)[:, p0:, HALO:HALO + h].copy_(vf[:, p0:, HALO + i * h:HALO + (i + 1) * h])
             self._exchange(cat)
             del cat_full, branches
+            self._tick("non_bottleneck_conv + band copy")
             y = self._conv(cat, "post_merge_conv", ACT_LEAKY_RELU, PAD_CONSTANT)
             d = ops.dense_input(dx, H, Wd)
             d = ops.dense(d, *m.conv("dx_dense/0"), ACT_LEAKY_RELU)
@@ -197,6 +220,10 @@ class SpatialHPNN:
                 y = self._resnet(y, "final/%d/resnet" % k, m.final_act, PAD_CONSTANT, False)
             for k in range(S - nreg, S):
                 y = self._conv(y, "final/%d/conv" % k, ACT_LINEAR, PAD_CONSTANT)
+            self._tick("trunk after the merge (banded)")
             # Scaling, boundary ring, post-smoother need the whole (single-channel) map: gather, replicated tail
             y_full = self._gather_rows(self._each(lambda i: ops.from_blk8(y[i], C=y[i].C)))
-            return m._tail(y_full, rhs, dx, S, None)
+            out = m._tail(y_full, rhs, dx, S, None)
+            self._tick("gather + tail (replicated)")
+            self._report()
+            return out

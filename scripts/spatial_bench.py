@@ -50,6 +50,10 @@ t_sp, out = timed(lambda: sp([rhs, dx]))
 res["spatial_ms"] = t_sp
 res["speedup_vs_engine_1gpu"] = t_eng / t_sp
 res["bit_identical"] = bool(torch.equal(out, ref))
+sp.profile = {}
+sp([rhs, dx])
+res["phases_ms_rank0"] = {k: round(v, 2) for k, v in sp.profile.items()}
+sp.profile = None
 if world == 1:
     m.use_engine = False
     t_py, _ = timed(lambda: m([rhs, dx]))
