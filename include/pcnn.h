@@ -298,6 +298,16 @@ int pcnn_upsample_merge_tc_blk8(int n_deconv, const void* const* dc_in, const vo
                                 const int32_t* const* rs_ix, const float* const* rs_wx, const int* rs_taps,
                                 const int* rs_ih, const int* rs_iw, float alpha, void* out, void* out_lo,
                                 int mode, int B, int H, int W, int c_total, int c_offset, void* stream);
+/* In place: channels [c_offset, c_offset+C) of the BLK8 tensor `buf` += alpha * sum_r resize_r(rs_in[r]) -- the Upsample branches
+ * of the merge (layers/Upsample.py:56-59, models/Homogeneous_Poisson_NN_Legacy.py:226-233) as a second pass after
+ * pcnn_upsample_merge_tc_blk8 ran with the transpose-conv branches only: used when the low-resolution resize sources are too large
+ * for that kernel's shared-memory staging (grids beyond ~400 pixels a side; before, such grids fell back to eight fp32
+ * read-modify-write passes: 12.8 of 51.7 ms of a 2048^2 forward).  Branch arguments as in pcnn_upsample_merge_blk8; C % 8 == 0
+ * (mode 3: C % 16 == 0 and no tail plane in the destination). */
+int pcnn_resize_add_blk8(int n_resize, const float* const* rs_in, const int32_t* const* rs_iy, const float* const* rs_wy,
+                         const int32_t* const* rs_ix, const float* const* rs_wx, const int* rs_taps, const int* rs_ih,
+                         const int* rs_iw, float alpha, void* buf, void* buf_lo, int mode, int B, int C, int H, int W,
+                         int c_total, int c_offset, void* stream);
 /* Same operator as pcnn_conv2d_f32 (pad + VALID conv + bias + act [+BN] [+residual] [*out_scale]) on
  * tcgen05 tensor cores: FP16 operands, FP32 accumulation in TMEM.  in/out/residual are BLK8 buffers
  * with Cin_total / Cout_total / Cres_total channels (Cin_total = the Cin the weights were packed with: the

@@ -65,6 +65,7 @@ SIGNATURES = {
                                          c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "pcnn_upsample_merge_tc_blk8": (c_int, [c_int, P, P, P, P, P, P, P, c_int, P, P, P, P, P, P, P, P, c_float, P, P,
                                             c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    "pcnn_resize_add_blk8": (c_int, [c_int, P, P, P, P, P, P, P, P, c_float, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
     "pcnn_upsample_merge_tc_packed_bytes": (c_size_t, [c_int]),
     "pcnn_upsample_merge_tc_smem_bytes": (c_size_t, [c_int, P, c_int, P, P]),
     "pcnn_upsample_merge_tc_pack_kernel": (c_int, [P, P, c_int, P]),

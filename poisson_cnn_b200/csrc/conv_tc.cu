@@ -1006,6 +1006,82 @@ static inline int grid_for(long long total, int block = 256, int cap = 148 * 16)
     return (int)g;
 }
 
+// In-place  x += alpha * sum_r resize_r(src_r)  on channels [plane0*8, plane0*8 + 8*np) of a BLK8 tensor (all precision
+// modes): the Upsample branches of the HPNN merge (layers/Upsample.py:56-59) for grids whose low-resolution sources are too
+// large for the shared-memory staging of the fused upsample-merge kernel (2048^2: 64 x 64 x 32 floats per sample).
+// One thread per (pixel, 8-channel plane): decode (as from_blk8), gather <= 16 taps x 8 channels per branch from the
+// L2-resident sources, encode (as to_blk8 / to_q8).  No tail plane: the destination has an even number of planes.
+constexpr int RA_MAX = 8;
+struct ResizeAddParams {
+    const float* src[RA_MAX];
+    const int32_t* iy[RA_MAX]; const float* wy[RA_MAX];
+    const int32_t* ix[RA_MAX]; const float* wx[RA_MAX];
+    int taps[RA_MAX], ih[RA_MAX], iw[RA_MAX];
+    int n, C;
+    float alpha;
+};
+__global__ void __launch_bounds__(128) resize_add_blk8_kernel(const ResizeAddParams p, __half* __restrict__ buf, uint8_t* __restrict__ lo,
+                                                              int mode, int H, int W, int Hp, int P, int c8_total, int plane0, int np) {
+    const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const int b = blockIdx.z / np, pl = blockIdx.z - b * np;
+    const int pa = plane0 + pl;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < p.n; ++r) {
+        const int taps = p.taps[r], ih = p.ih[r], iw = p.iw[r];
+        const float* src = p.src[r] + ((long long)b * p.C + pl * 8) * ih * iw;
+        for (int a = 0; a < taps; ++a) {
+            const int sy = __ldg(p.iy[r] + y * taps + a);
+            const float fy = __ldg(p.wy[r] + y * taps + a);
+            for (int c = 0; c < taps; ++c) {
+                const float w = fy * __ldg(p.wx[r] + x * taps + c);
+                const float* s0 = src + (long long)sy * iw + __ldg(p.ix[r] + x * taps + c);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, __ldg(s0 + (long long)e * ih * iw), acc[e]);
+            }
+        }
+    }
+    const size_t pix = (size_t)(y + HALO) * P + (x + HALO);
+    const size_t off = (((size_t)b * c8_total + pa) * Hp * P + pix) * 8;
+    const uint4 hv = *reinterpret_cast<const uint4*>(buf + off);
+    const __half* h = reinterpret_cast<const __half*>(&hv);
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = __half2float(h[e]);
+    const size_t q0 = (((size_t)b * c8_total + (pa & ~1)) * Hp * P + pix) * 16 + 8 * (pa & 1);      // e4m3(x) bytes of this plane
+    const size_t q1 = q0 + (size_t)Hp * P * 16;                                                     // remainder bytes
+    if (mode == 2) {
+        const uint4 lv = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(lo) + off);
+        const __half* l = reinterpret_cast<const __half*>(&lv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] += __half2float(l[e]);
+    } else if (mode == 3) {
+        const uint2 qv = *reinterpret_cast<const uint2*>(lo + q1);
+        const uint8_t* q = reinterpret_cast<const uint8_t*>(&qv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] += from_e4m3(q[e]) * (1.0f / LO_SCALE);
+    }
+    __align__(16) __half ho[8];
+    __align__(16) __half lo16[8];
+    __align__(8) uint8_t a8[8];
+    __align__(8) uint8_t l8[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float v = fmaf(p.alpha, acc[e], f[e]);
+        ho[e] = __float2half_rn(v);
+        const float rem = v - __half2float(ho[e]);
+        lo16[e] = __float2half_rn(rem);
+        a8[e] = to_e4m3(v);
+        l8[e] = to_e4m3(rem * LO_SCALE);
+    }
+    *reinterpret_cast<uint4*>(buf + off) = *reinterpret_cast<const uint4*>(ho);
+    if (mode == 2) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(lo) + off) = *reinterpret_cast<const uint4*>(lo16);
+    if (mode == 3) {
+        *reinterpret_cast<uint2*>(lo + q0) = *reinterpret_cast<const uint2*>(a8);
+        *reinterpret_cast<uint2*>(lo + q1) = *reinterpret_cast<const uint2*>(l8);
+    }
+}
+
 }  // namespace tc
 }  // namespace pcnn
 
@@ -1268,4 +1344,30 @@ extern "C" int pcnn_conv2d_tc_rowweights(const void* in_row, const void* wrow, c
     PCNN_CHECK_ARG(in_row && wrow && out, "conv2d_tc_rowweights: null pointer");
     return conv2d_tc_impl(in_row, nullptr, wrow, bias, nullptr, nullptr, nullptr, nullptr, nullptr, out, nullptr, B, Cin, Cout, Cout_total, 0,
                           H, W, k, act, 1, acc_scale, PCNN_PAD_CONSTANT, num_sms, stream, 1, pcnn_conv_tc_rowweight_slots(Cout, k, H));
+}
+
+extern "C" int pcnn_resize_add_blk8(int n_resize, const float* const* rs_in, const int32_t* const* rs_iy, const float* const* rs_wy,
+                                    const int32_t* const* rs_ix, const float* const* rs_wx, const int* rs_taps, const int* rs_ih,
+                                    const int* rs_iw, float alpha, void* buf, void* buf_lo, int mode, int B, int C, int H, int W,
+                                    int c_total, int c_offset, void* stream) {
+    PCNN_CHECK_ARG(n_resize >= 1 && n_resize <= RA_MAX && rs_in && rs_iy && rs_wy && rs_ix && rs_wx && rs_taps && rs_ih && rs_iw,
+                   "resize_add_blk8: between 1 and %d resize branches", RA_MAX);
+    PCNN_CHECK_ARG(buf && mode >= 1 && mode <= 3 && (mode == 1 || buf_lo), "resize_add_blk8: bad destination / precision mode");
+    PCNN_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && (c_offset % 16) == 0 && c_offset + C <= ((c_total + 15) / 16) * 16,
+                   "resize_add_blk8: C must be a multiple of 8, the channel offset a multiple of 16 inside the buffer");
+    PCNN_CHECK_ARG(mode != 3 || ((((c_total + 7) / 8) & 1) == 0 && (C % 16) == 0), "resize_add_blk8: precision mode 3 needs whole 16-channel groups and no tail plane");
+    ResizeAddParams p;
+    p.n = n_resize; p.C = C; p.alpha = alpha;
+    for (int r = 0; r < n_resize; ++r) {
+        PCNN_CHECK_ARG(rs_in[r] && rs_iy[r] && rs_wy[r] && rs_ix[r] && rs_wx[r] && rs_taps[r] >= 1 && rs_taps[r] <= 4 && rs_ih[r] > 0 && rs_iw[r] > 0,
+                       "resize_add_blk8: branch %d: bad argument", r);
+        p.src[r] = rs_in[r]; p.iy[r] = rs_iy[r]; p.wy[r] = rs_wy[r]; p.ix[r] = rs_ix[r]; p.wx[r] = rs_wx[r];
+        p.taps[r] = rs_taps[r]; p.ih[r] = rs_ih[r]; p.iw[r] = rs_iw[r];
+    }
+    const int np = C / 8;
+    PCNN_CHECK_ARG(H <= 65535 && (long long)B * np <= 65535, "resize_add_blk8: grid too large");
+    resize_add_blk8_kernel<<<dim3(ceil_div(W, 128), H, B * np), 128, 0, (cudaStream_t)stream>>>(
+        p, (__half*)buf, (uint8_t*)buf_lo, mode, H, W, H + 2 * HALO, W + 2 * HALO, ((c_total + 15) / 16) * 2, c_offset / 8, np);
+    PCNN_CHECK_LAUNCH();
+    return PCNN_OK;
 }

@@ -1270,10 +1270,16 @@ static int hpnn_tc(Ctx& c, const float* rhs, const float* dx, float* out, int B,
         if (b.deconv) { ++ndeconv; strides_ok = strides_ok && b.us <= 32; um_strides.push_back(b.us); }
         else { um_ih.push_back(cdiv(H, b.ds)); um_iw.push_back(cdiv(W, b.ds)); }
     }
-    bool um_tc = bsplit == 1 && F == 32 && ndeconv > 0 && h.blocks.size() <= 16 && strides_ok;
+    // um_tc 1: every branch in the fused tensor-core upsample-merge (its resize sources are staged whole in shared memory:
+    // grids up to ~400 pixels a side); 2: larger grids -- transpose-conv branches fused, resize branches added by a second
+    // pass (pcnn_resize_add_blk8); 0: general kernels
+    int um_tc = (bsplit == 1 && F == 32 && ndeconv > 0 && h.blocks.size() <= 16 && strides_ok) ? 1 : 0;
     if (um_tc) {
-        const size_t n = pcnn_upsample_merge_tc_smem_bytes((int)um_strides.size(), um_strides.data(), (int)um_ih.size(), um_ih.data(), um_iw.data());
-        um_tc = n > 0 && n <= 227 * 1024;
+        auto fits = [&](int nrs) {
+            const size_t n = pcnn_upsample_merge_tc_smem_bytes((int)um_strides.size(), um_strides.data(), nrs, um_ih.data(), um_iw.data());
+            return n > 0 && n <= 227 * 1024;
+        };
+        um_tc = fits((int)um_ih.size()) ? 1 : ((!um_ih.empty() && fits(0)) ? 2 : 0);
     }
     struct Branch { const BlockCfg* cfg; bool is_b8; B8 b8; F32 f32; };
     std::vector<Branch> br;
@@ -1315,9 +1321,14 @@ static int hpnn_tc(Ctx& c, const float* rhs, const float* dx, float* out, int B,
         TRY(conv_tc(c, x0, "hpnn/non_bottleneck_conv", a, Bcap, &dummy));
         c.free(x0);
     }
-    bool fused = F % 8 == 0 && ndeconv <= 8 && (int)h.blocks.size() - ndeconv <= 8 && strides_ok;
+    const bool fused_dc = F % 8 == 0 && ndeconv <= 8 && (int)h.blocks.size() - ndeconv <= 8 && strides_ok;
+    bool fused = fused_dc;
     for (const Branch& r : br)
         if (!r.cfg->deconv) fused = fused && (size_t)F * r.f32.H * r.f32.W <= 8192;
+    const bool two_pass = um_tc == 2 && fused_dc;
+    if (um_tc == 1 && !fused) um_tc = 0;          // (sources between the two limits: general kernels, as before)
+    if (um_tc == 2 && !fused_dc) um_tc = 0;
+    if (two_pass) fused = true;
     {
         // operand lists of the fused kernels (host arrays of device pointers)
         std::vector<const void*> d_in, d_k;
@@ -1347,11 +1358,15 @@ static int hpnn_tc(Ctx& c, const float* rhs, const float* dx, float* out, int B,
             }
             const void* nullp = nullptr; const float* nullf = nullptr; const int32_t* nulli = nullptr; int zero = 0;
             auto P = [&](auto& v, auto& dflt) { return v.empty() ? &dflt : v.data(); };
-            if (um_tc)
+            if (um_tc) {
+                const int nrs = two_pass ? 0 : (int)r_in.size();
                 RUN(c, pcnn_upsample_merge_tc_blk8((int)d_in.size(), P(d_in, nullp), P(d_k, nullp), P(d_b, nullf), P(d_s, zero), P(d_ih, zero), P(d_iw, zero),
-                                                   P(d_act, zero), (int)r_in.size(), P(r_in, nullf), P(r_iy, nulli), P(r_wy, nullf), P(r_ix, nulli),
+                                                   P(d_act, zero), nrs, P(r_in, nullf), P(r_iy, nulli), P(r_wy, nullf), P(r_ix, nulli),
                                                    P(r_wx, nullf), P(r_t, zero), P(r_ih, zero), P(r_iw, zero), alpha, cat.hi, cat.lo, cat.mode, B, H, W, cat.C, F, c.st));
-            else
+                if (two_pass)
+                    RUN(c, pcnn_resize_add_blk8((int)r_in.size(), r_in.data(), r_iy.data(), r_wy.data(), r_ix.data(), r_wx.data(), r_t.data(),
+                                                r_ih.data(), r_iw.data(), alpha, cat.hi, cat.lo, cat.mode, B, F, H, W, cat.C, F, c.st));
+            } else
                 RUN(c, pcnn_upsample_merge_blk8((int)d_in.size(), reinterpret_cast<const float* const*>(P(d_in, nullp)),
                                                 reinterpret_cast<const float* const*>(P(d_k, nullp)), P(d_b, nullf), P(d_s, zero), P(d_ih, zero),
                                                 P(d_iw, zero), P(d_act, zero), (int)r_in.size(), P(r_in, nullf), P(r_iy, nulli), P(r_wy, nullf),

@@ -254,10 +254,13 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
         um_tc = (bsplit == 1 and F == 32 and os.environ.get("PCNN_UM_TC", "1") != "0"
                  and any(b_.kind == "deconv" for b_ in blocks) and len(blocks) <= 16
                  and all(b_.upsampling_factor <= 32 for b_ in blocks if b_.kind == "deconv"))
-        if um_tc:                                # ... and only if its operands fit in shared memory (grids up to ~400 pixels a side)
-            um_tc = ops.upsample_merge_tc_fits(
-                [b_.upsampling_factor for b_ in blocks if b_.kind == "deconv"],
-                [(-(-H // b_.downsampling_factor), -(-Wd // b_.downsampling_factor)) for b_ in blocks if b_.kind != "deconv"])
+        if um_tc:
+            # 1: everything in the fused kernel (its resize sources are staged whole in shared memory: grids up to ~400 pixels a
+            # side); 2: larger grids -- the transpose-conv branches in the fused kernel, the resize branches added by a second
+            # pass (ops.resize_add_blk8); 0: general kernels
+            strides = [b_.upsampling_factor for b_ in blocks if b_.kind == "deconv"]
+            rs_hw = [(-(-H // b_.downsampling_factor), -(-Wd // b_.downsampling_factor)) for b_ in blocks if b_.kind != "deconv"]
+            um_tc = 1 if ops.upsample_merge_tc_fits(strides, rs_hw) else (2 if (rs_hw and ops.upsample_merge_tc_fits(strides, [])) else 0)
         for blk in blocks:
             self._branch_out_hw(blk, H, Wd)
             ph, pw = -(-H // blk.downsampling_factor), -(-Wd // blk.downsampling_factor)
@@ -286,17 +289,19 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
         """All upsamplings + the branch sum written into channels [F, 2F) of the BLK8 tensor `cat` (one fused kernel)."""
         dc, rs, um_tc, alpha = branches
         F = self.filters
-        fused = (F % 8 == 0 and len(dc) <= 8 and len(rs) <= 8
-                 and all(tuple(k.shape) == (s_, s_, F, F) and s_ <= 32 for _, k, _, s_, _ in dc)
-                 and all(F * h.shape[2] * h.shape[3] <= 8192 for h, _ in rs))
-        if um_tc and fused:
+        fused_dc = (F % 8 == 0 and len(dc) <= 8 and len(rs) <= 8
+                    and all(tuple(k.shape) == (s_, s_, F, F) and s_ <= 32 for _, k, _, s_, _ in dc))
+        fused = fused_dc and all(F * h.shape[2] * h.shape[3] <= 8192 for h, _ in rs)
+        if (um_tc == 1 and fused) or (um_tc == 2 and fused_dc):
             packed = []
             for h, k, bias_, s_, act_ in dc:
                 key = ("deconv_packed_tc", k.data_ptr())
                 if key not in self._tc:
                     self._tc[key] = ops.pack_deconv_kernel_tc(k)
                 packed.append((h, self._tc[key], bias_, s_, act_))
-            ops.upsample_merge_tc_blk8(packed, rs, alpha, cat, F, H, Wd)
+            ops.upsample_merge_tc_blk8(packed, rs if um_tc == 1 else [], alpha, cat, F, H, Wd)
+            if um_tc == 2:
+                ops.resize_add_blk8(rs, alpha, cat, F, H, Wd)
         elif fused:
             dc = [(ops.from_blk8(h) if isinstance(h, ops.Blk8) else h, k, b_, s_, a_) for h, k, b_, s_, a_ in dc]
             packed = []

@@ -916,6 +916,38 @@ def upsample_merge_tc_blk8(deconv_branches, resize_branches, alpha, out, c_offse
     return out
 
 
+def resize_add_blk8(resize_branches, alpha, out, c_offset, H, W):
+    """In place: channels [c_offset, c_offset+C) of the Blk8 tensor `out` += alpha * sum_r resize_r(x_r).
+    resize_branches: [(x [B,C,ih,iw] fp32, method)].  The second pass of the merge on grids whose resize sources do not
+    fit the fused kernel's shared memory (see pcnn.h)."""
+    import ctypes
+    if not isinstance(out, Blk8) or (out.H, out.W) != (int(H), int(W)) or not resize_branches:
+        raise ValueError("resize_add_blk8: destination must be a Blk8 tensor of the output size and at least one branch")
+    B, C, keep = out.B, None, []
+
+    def arr_p(vals):
+        return (ctypes.c_void_p * len(vals))(*vals)
+
+    def arr_i(vals):
+        return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+    r_in, r_iy, r_wy, r_ix, r_wx, r_t, r_ih, r_iw = [], [], [], [], [], [], [], []
+    for x, method in resize_branches:
+        _chk(x, "x")
+        x = x.contiguous()
+        C = x.shape[1] if C is None else C
+        if x.shape[0] != B or x.shape[1] != C:
+            raise ValueError("resize_add_blk8: resize branches need x [B,C,ih,iw] with one C")
+        iy, wy = _resize_tables(x.device, x.shape[2], int(H), method)
+        ix, wx = _resize_tables(x.device, x.shape[3], int(W), method)
+        keep += [x]
+        r_in.append(x.data_ptr()); r_iy.append(iy.data_ptr()); r_wy.append(wy.data_ptr()); r_ix.append(ix.data_ptr())
+        r_wx.append(wx.data_ptr()); r_t.append(iy.shape[1]); r_ih.append(x.shape[2]); r_iw.append(x.shape[3])
+    check(lib.pcnn_resize_add_blk8(len(r_in), arr_p(r_in), arr_p(r_iy), arr_p(r_wy), arr_p(r_ix), arr_p(r_wx), arr_i(r_t), arr_i(r_ih),
+                                   arr_i(r_iw), float(alpha), _p(out.buf), _p(out.lo), out.mode, B, int(C), int(H), int(W), out.C,
+                                   int(c_offset), _stream()), "resize_add_blk8")
+    return out
+
+
 def rowweights_image(kernel, row_basis, cp, rt, T):
     """The fp16 operand image of pcnn_conv2d_tc_rowweights (layout in include/pcnn.h) and the power-of-two pre-scale:
     [ceil(Cin/16)][k][2][T][cp][8], slot t = output row (t//rt)*rt + rt-1 - t%rt (zeros beyond H), K half = channels

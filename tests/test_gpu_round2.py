@@ -259,3 +259,49 @@ def test_fp16_activation_storage_with_large_magnitudes(bundle):
     out = m.set_precision("mixed")([dev(p["rhs"]), dev(p["dx"])])
     assert bool(torch.isfinite(out).all())
     assert rel_l2(out, ref) < 2e-3
+
+
+# ------------------------------------------------------------------ two-pass merge for large grids
+@pytest.mark.parametrize("mode,tol", [(1, 1e-3), (2, 2e-6), (3, 2e-4)])
+def test_resize_add_blk8_matches_oracle(mode, tol):
+    """pcnn_resize_add_blk8: channels [32,64) of a 64-channel BLK8 tensor += alpha * (bicubic + bilinear + nearest up-sampling)."""
+    from poisson_cnn_b200 import ops
+    from poisson_cnn_b200.config import RESIZE_NEAREST, RESIZE_BILINEAR, RESIZE_BICUBIC
+    g = torch.Generator().manual_seed(11)
+    B, H, W = 2, 37, 150
+    x = torch.randn(B, 64, H, W, generator=g)
+    srcs = [(torch.randn(B, 32, 5, 9, generator=g), RESIZE_BICUBIC, "bicubic"), (torch.randn(B, 32, 3, 4, generator=g), RESIZE_BILINEAR, "bilinear"),
+            (torch.randn(B, 32, 2, 2, generator=g), RESIZE_NEAREST, "nearest")]
+    t = ops.to_blk8(dev(x), split=mode)
+    ops.resize_add_blk8([(dev(s), m) for s, m, _ in srcs], 0.25, t, 32, H, W)
+    got = ops.from_blk8(t)
+    ref = x.double().clone()
+    for s, _, name in srcs:
+        ref[:, 32:] += 0.25 * O.resize(s.double(), (H, W), name)
+    assert rel_l2(got[:, 32:], ref[:, 32:]) < tol
+    base = ops.from_blk8(ops.to_blk8(dev(x), split=mode))
+    assert torch.equal(got[:, :32], base[:, :32])          # the other channels are untouched
+
+
+def test_large_grid_merge_takes_the_two_pass_path(bundle):
+    """Grids beyond ~400 pixels a side: the fused upsample-merge runs the transpose-conv branches, the resize branches are
+    added by pcnn_resize_add_blk8 (before: eight fp32 read-modify-write passes).  Engine and Python program agree bit for
+    bit, and the result tracks the strict FP32 path."""
+    from poisson_cnn_b200 import ops
+    model = bundle[0]
+    blocks = model.hpnn.bottleneck_deconv_blocks + model.hpnn.bottleneck_multilinear_blocks
+    strides = [b.upsampling_factor for b in blocks if b.kind == "deconv"]
+    rs_hw = [(-(-448 // b.downsampling_factor), -(-512 // b.downsampling_factor)) for b in blocks if b.kind != "deconv"]
+    assert not ops.upsample_merge_tc_fits(strides, rs_hw) and ops.upsample_merge_tc_fits(strides, [])
+    p = distinct_problems(1, 448, 512, seed=2300)
+    inp = [p[k].cuda() for k in KEYS]
+    try:
+        ref = model.set_precision("fp32")(inp)
+        a = model.set_precision("mixed")(inp)
+        model.use_engine = model.hpnn.use_engine = model.dbcnn.use_engine = False
+        b = model(inp)
+    finally:
+        model.use_engine = model.hpnn.use_engine = model.dbcnn.use_engine = True
+        model.set_precision("fp32")
+    assert torch.equal(a, b)
+    assert rel_l2(a, ref) < 2e-3
