@@ -872,10 +872,12 @@ def upsample_merge_tc_fits(strides, resize_hw):
     return 0 < n <= 227 * 1024
 
 
-def upsample_merge_tc_blk8(deconv_branches, resize_branches, alpha, out, c_offset, H, W):
+def upsample_merge_tc_blk8(deconv_branches, resize_branches, alpha, out, c_offset, H, W, row_offset=0, full_H=None):
     """upsample_merge_blk8 with the transpose convolutions on the tensor cores, reading the branch outputs as BLK8 fp16.
     deconv_branches: [(Blk8 x with 32 channels [ih,iw], packed kernel (pack_deconv_kernel_tc), bias or None, stride, act)];
-    resize_branches: [(x [B,32,ih,iw] fp32, method)]."""
+    resize_branches: [(x [B,32,ih,iw] fp32, method)].
+    row_offset / full_H: `out` is a band of rows [row_offset, row_offset + H) of a full_H-row map (spatial decomposition):
+    the resize tables are those of the full map, entered at row_offset; the deconv inputs are the band's own low-res rows."""
     import ctypes
     if not isinstance(out, Blk8) or (out.H, out.W) != (int(H), int(W)):
         raise ValueError("upsample_merge_tc_blk8: destination must be a Blk8 tensor of the output size")
@@ -902,9 +904,10 @@ def upsample_merge_tc_blk8(deconv_branches, resize_branches, alpha, out, c_offse
         x = x.contiguous()
         if x.shape[0] != B or x.shape[1] != 32:
             raise ValueError("upsample_merge_tc_blk8: resize branch needs x [B,32,ih,iw]")
-        iy, wy = _resize_tables(x.device, x.shape[2], int(H), method)
+        iy, wy = _resize_tables(x.device, x.shape[2], int(full_H or H), method)
         ix, wx = _resize_tables(x.device, x.shape[3], int(W), method)
         keep += [x]
+        iy, wy = iy[int(row_offset):], wy[int(row_offset):]
         r_in.append(x.data_ptr()); r_iy.append(iy.data_ptr()); r_wy.append(wy.data_ptr()); r_ix.append(ix.data_ptr())
         r_wx.append(wx.data_ptr()); r_t.append(iy.shape[1]); r_ih.append(x.shape[2]); r_iw.append(x.shape[3])
     check(lib.pcnn_upsample_merge_tc_blk8(len(d_in), arr_p(d_in), arr_p(d_k), arr_p(d_b), arr_i(d_s), arr_i(d_ih), arr_i(d_iw),
@@ -916,7 +919,7 @@ def upsample_merge_tc_blk8(deconv_branches, resize_branches, alpha, out, c_offse
     return out
 
 
-def resize_add_blk8(resize_branches, alpha, out, c_offset, H, W):
+def resize_add_blk8(resize_branches, alpha, out, c_offset, H, W, row_offset=0, full_H=None):
     """In place: channels [c_offset, c_offset+C) of the Blk8 tensor `out` += alpha * sum_r resize_r(x_r).
     resize_branches: [(x [B,C,ih,iw] fp32, method)].  The second pass of the merge on grids whose resize sources do not
     fit the fused kernel's shared memory (see pcnn.h)."""
@@ -937,9 +940,10 @@ def resize_add_blk8(resize_branches, alpha, out, c_offset, H, W):
         C = x.shape[1] if C is None else C
         if x.shape[0] != B or x.shape[1] != C:
             raise ValueError("resize_add_blk8: resize branches need x [B,C,ih,iw] with one C")
-        iy, wy = _resize_tables(x.device, x.shape[2], int(H), method)
+        iy, wy = _resize_tables(x.device, x.shape[2], int(full_H or H), method)      # row_offset / full_H: as in upsample_merge_tc_blk8
         ix, wx = _resize_tables(x.device, x.shape[3], int(W), method)
         keep += [x]
+        iy, wy = iy[int(row_offset):], wy[int(row_offset):]
         r_in.append(x.data_ptr()); r_iy.append(iy.data_ptr()); r_wy.append(wy.data_ptr()); r_ix.append(ix.data_ptr())
         r_wx.append(wx.data_ptr()); r_t.append(iy.shape[1]); r_ih.append(x.shape[2]); r_iw.append(x.shape[3])
     check(lib.pcnn_resize_add_blk8(len(r_in), arr_p(r_in), arr_p(r_iy), arr_p(r_wy), arr_p(r_ix), arr_p(r_wx), arr_i(r_t), arr_i(r_ih),

@@ -9,14 +9,17 @@ GPU (torch.distributed over NCCL), and every full-resolution convolution of the 
     halo rows are simply filled with the neighbour's edge rows -- the kernels run unchanged and compute, bit for bit, what
     the monolithic convolution computes for those rows.  One exchange of <= 7 rows x 2 neighbours per layer (peer copies of
     (W+14) x 16 B x planes per row; 1.8 MB per direction at 2048^2 in `tc2`).
-  * Global couplings: the pooled pyramids of the bottleneck branches need the whole map -> the band features are
-    all-gathered once (32 channels) and the low-resolution branches (9 % of the FLOPs) plus the fused upsample-merge run
-    REPLICATED on every rank; each rank keeps its band of the merged map.  The Scaling block and the boundary ring need the
-    whole 1-channel output -> all-gather, replicated tail.  The dx MLP is replicated.  No other exchange.
+  * Bottleneck branches whose pooling windows and transpose-conv phases align with the bands (down-sampling factor divides
+    the band height, >= 16 low-resolution rows per band: ds = 2, 4, 8, 16 at 2048^2 on 8 GPUs) are split the same way: pooled
+    per band, convolved per band with their own halo exchange, up-sampled into the band of the merged map by the fused
+    merge kernel with band-local inputs.  The others (ds = 3: 2048 is not a multiple of 3; the 2x2 .. 64x64 maps of the
+    multilinear branches) run REPLICATED from one all-gather of the 32-channel features; the merge takes their rows /
+    the full-map interpolation tables entered at the band's first row.
+  * The Scaling block and the boundary ring need the whole 1-channel output -> all-gather, replicated tail.  The dx MLP is
+    replicated.  No other exchange.
 
 The result is bit-identical to the single-GPU tensor-core program (tests/test_gpu_spatial.py), because every kernel sees
-exactly the operands it sees there.  Expected speed-up = 1 / (0.86 / P + 0.14) minus the exchanges (the replicated branches
-and merge are ~14 % of a forward at 2048^2).
+exactly the operands it sees there (including the hierarchical pooling chain, which follows the full map's divisibility).
 
 `world=P, comm=None` emulates the P bands inside ONE process on one GPU (the exchange is a device copy): the test of the
 decomposition logic; `comm=torch.distributed group` runs one band per rank.
@@ -148,6 +151,127 @@ class SpatialHPNN:
         t = self._conv(t, name + "/conv1", act, pad, name + "/bn1" if use_bn else None, residual=xs, next_pad=pad)
         return self._conv(t, name + "/conv2", act, pad, out_scale=out_scale, next_pad=next_pad)
 
+    # ------------------------------------------------------------------ bottleneck branches
+    def _pool_chain(self, H, Wd, factors):
+        """{s: (source level t or 0 for the features, factor)} exactly as Homogeneous_Poisson_NN_Legacy._pool_pyramid decides
+        for the FULL map (means of means differ from direct means in the last bit: the bands must follow the same chain)."""
+        chain, done = {}, []
+        for s in sorted(set(factors)):
+            src, f = 0, s
+            if H % s == 0 and Wd % s == 0:
+                for t in sorted(done, reverse=True):
+                    if s % t == 0 and H % t == 0 and Wd % t == 0:
+                        src, f = t, s // t
+                        break
+            chain[s] = (src, f)
+            done.append(s)
+        return chain
+
+    def _branches(self, x0, H, Wd, h, split):
+        """Low-resolution branch outputs for the banded merge: {'dc': [(per-band Blk8 dict, kernel, bias, stride, act)],
+        'rs': [(full fp32 source, method)], 'um': 1|2} or None when the banded merge does not apply (then everything runs
+        replicated through the model's own _branches_tc / _merge_tc)."""
+        m = self.m
+        F = m.filters
+        blocks = m.bottleneck_deconv_blocks + m.bottleneck_multilinear_blocks
+        bsplit = 1 if m.requested_precision == "mixed" else split
+        deconv = [b for b in blocks if b.kind == "deconv"]
+        strides = [b.upsampling_factor for b in deconv]
+        rs_hw = [(-(-H // b.downsampling_factor), -(-Wd // b.downsampling_factor)) for b in blocks if b.kind != "deconv"]
+        ok = (bsplit == 1 and F == 32 and deconv and len(blocks) <= 16 and all(s <= 32 for s in strides) and len(deconv) <= 8
+              and len(rs_hw) <= 8 and all(b.upsampling_factor == b.downsampling_factor and h % b.upsampling_factor == 0 for b in deconv))
+        if not ok:
+            return None
+        um = 1 if ops.upsample_merge_tc_fits(strides, rs_hw) else (2 if (rs_hw and ops.upsample_merge_tc_fits(strides, [])) else 0)
+        if um == 0 or (um == 1 and any(F * a * b > 8192 for a, b in rs_hw)):
+            return None
+        for b in blocks:
+            m._branch_out_hw(b, H, Wd)
+        chain = self._pool_chain(H, Wd, [b.downsampling_factor for b in blocks])
+        banded = {b.downsampling_factor for b in deconv
+                  if h % b.downsampling_factor == 0 and h // b.downsampling_factor >= 16 and -(-Wd // b.downsampling_factor) >= 16}
+        self._tick("branch setup")
+        # replicated levels: from the gathered features, through the model's own pyramid (same chain by construction)
+        rep = [b for b in blocks if b.downsampling_factor not in banded]
+        rep_out = {}
+        if rep:
+            x0_full = self._gather_rows(self._each(lambda i: ops.from_blk8(x0[i])))
+            with ops.blk8_pool_scope(self.full_pool):
+                pools = m._pool_pyramid(x0_full, [b.downsampling_factor for b in blocks])
+                for b in rep:
+                    ph, pw = -(-H // b.downsampling_factor), -(-Wd // b.downsampling_factor)
+                    name = "bottleneck_%s/%d" % (b.kind, b.index)
+                    if b.kind == "deconv" and min(ph, pw) >= 16:
+                        t = ops.to_blk8(pools[b.downsampling_factor], split=bsplit, halo=b.pad)
+                        t = m._conv_tc(t, name + "/conv0", b.act, b.pad, next_pad=b.pad)
+                        for r in range(1, b.n_convs):
+                            t = m._resnet_tc(t, "%s/resnet%d" % (name, r), b.act, b.pad, b.use_batchnorm,
+                                             next_pad=b.pad if r + 1 < b.n_convs else PAD_CONSTANT)
+                    else:
+                        t = m._bottleneck_lowres(b, x0_full, pools[b.downsampling_factor])
+                        if b.kind == "deconv":
+                            t = ops.to_blk8(t)
+                    rep_out[(b.kind, b.index)] = t
+                del pools
+            del x0_full
+        self._tick("branches (replicated)")
+        # banded levels: pooled per band along the full map's chain, convolved per band with halo exchange
+        band_pool = {}
+        x0f = self._each(lambda i: ops.from_blk8(x0[i])) if banded else None
+        needed = set(banded)                      # banded levels and, transitively, the levels they are pooled from
+        grew = True
+        while grew:
+            grew = False
+            for q in list(needed):
+                if chain[q][0] and chain[q][0] not in needed:
+                    needed.add(chain[q][0])
+                    grew = True
+        for s_ in sorted(needed):
+            src, f = chain[s_]
+            band_pool[s_] = self._each(lambda i: ops.avgpool_same(x0f[i] if src == 0 else band_pool[src][i], f))
+        dc, rs = [], []
+        for b in blocks:
+            name = "bottleneck_%s/%d" % (b.kind, b.index)
+            if b.kind != "deconv":
+                rs.append((rep_out[(b.kind, b.index)], b.resize_method))
+                continue
+            s_ = b.downsampling_factor
+            if s_ in banded:
+                t = self._each(lambda i: ops.to_blk8(band_pool[s_][i], split=bsplit, halo=b.pad))
+                self._exchange(t)
+                t = self._conv(t, name + "/conv0", b.act, b.pad, next_pad=b.pad)
+                for r in range(1, b.n_convs):
+                    t = self._resnet(t, "%s/resnet%d" % (name, r), b.act, b.pad, b.use_batchnorm,
+                                     next_pad=b.pad if r + 1 < b.n_convs else PAD_CONSTANT)
+            else:                                   # this band's rows of the replicated low-resolution output
+                full = rep_out[(b.kind, b.index)]
+                hl = h // s_
+                vf = _view(full)
+
+                def rows(i):
+                    t_ = ops.Blk8(full.B, full.C, hl, full.W, full.device, split=1)
+                    _view(t_)[:, :, HALO:HALO + hl].copy_(vf[:, :, HALO + i * hl:HALO + (i + 1) * hl])
+                    return t_
+                t = self._each(rows)
+            dk, db = m.conv(name + "/deconv")
+            key = ("deconv_packed_tc", dk.data_ptr())
+            if key not in m._tc:
+                m._tc[key] = ops.pack_deconv_kernel_tc(dk)
+            dc.append((t, m._tc[key], db, b.upsampling_factor, b.deconv_act))
+        self._tick("branches (banded)")
+        return {"dc": dc, "rs": rs, "um": um, "alpha": 1.0 / float(len(blocks) * F)}
+
+    def _merge_banded(self, br, cat, H, Wd, h):
+        F = self.m.filters
+
+        def one(i):
+            packed = [(t[i], k, b_, s_, a_) for t, k, b_, s_, a_ in br["dc"]]
+            ops.upsample_merge_tc_blk8(packed, br["rs"] if br["um"] == 1 else [], br["alpha"], cat[i], F, h, Wd, row_offset=i * h, full_H=H)
+            if br["um"] == 2:
+                ops.resize_add_blk8(br["rs"], br["alpha"], cat[i], F, h, Wd, row_offset=i * h, full_H=H)
+            return None
+        self._each(one)
+
     # ------------------------------------------------------------------ forward
     def __call__(self, inp):
         rhs, dx = inp
@@ -186,28 +310,30 @@ class SpatialHPNN:
                                next_pad=m.pre_pad if k + 1 < m.n_pre else PAD_CONSTANT)
             x0 = t
             self._tick("pre_bottleneck (banded)")
-            # the bottleneck branches need the whole map: gather the band features, run the low-resolution branches and the
-            # fused upsample-merge replicated, keep this rank's rows of the merged map
-            x0_full = self._gather_rows(self._each(lambda i: ops.from_blk8(x0[i])))
-            self._tick("gather x0")
-            with ops.blk8_pool_scope(self.full_pool):
-                branches = m._branches_tc(x0_full, H, Wd, split)
-                self._tick("branches (replicated)")
-                cat_full = ops.Blk8(B, 2 * F, H, Wd, dev, split=split)
-                m._merge_tc(branches, cat_full, B, H, Wd, dev)
-                self._tick("upsample-merge (replicated)")
+            br = self._branches(x0, H, Wd, h, split)
             cat = self._each(lambda i: ops.Blk8(B, 2 * F, h, Wd, dev, split=split))
             self._conv(x0, "non_bottleneck_conv", ACT_LEAKY_RELU, PAD_CONSTANT, out=cat)
-            p0 = (F // 16) * 2                       # first plane of channels [F, 2F)
-            for which in ("buf", "lo"):
-                if getattr(cat_full, which) is None:
-                    continue
-                vf = _view(cat_full, which)
-                for i in self.local:
-                    _view(cat[i], which)[:, p0:, HALO:HALO + h].copy_(vf[:, p0:, HALO + i * h:HALO + (i + 1) * h])
+            if br is not None:
+                self._merge_banded(br, cat, H, Wd, h)
+                self._tick("upsample-merge (banded)")
+            else:
+                # general merge kernels (no fused tensor-core merge for this config / shape): everything replicated from the
+                # gathered features, each rank keeps its rows of the merged map
+                x0_full = self._gather_rows(self._each(lambda i: ops.from_blk8(x0[i])))
+                with ops.blk8_pool_scope(self.full_pool):
+                    branches = m._branches_tc(x0_full, H, Wd, split)
+                    cat_full = ops.Blk8(B, 2 * F, H, Wd, dev, split=split)
+                    m._merge_tc(branches, cat_full, B, H, Wd, dev)
+                p0 = (F // 16) * 2                       # first plane of channels [F, 2F)
+                for which in ("buf", "lo"):
+                    if getattr(cat_full, which) is None:
+                        continue
+                    vf = _view(cat_full, which)
+                    for i in self.local:
+                        _view(cat[i], which)[:, p0:, HALO:HALO + h].copy_(vf[:, p0:, HALO + i * h:HALO + (i + 1) * h])
+                del cat_full, branches, x0_full
+                self._tick("branches + merge (replicated)")
             self._exchange(cat)
-            del cat_full, branches
-            self._tick("non_bottleneck_conv + band copy")
             y = self._conv(cat, "post_merge_conv", ACT_LEAKY_RELU, PAD_CONSTANT)
             d = ops.dense_input(dx, H, Wd)
             d = ops.dense(d, *m.conv("dx_dense/0"), ACT_LEAKY_RELU)

@@ -20,7 +20,7 @@ def _hpnn(bc_type="dirichlet", device=None):
     return models.Homogeneous_Poisson_NN_Legacy(**convert_tf_object_names(hp)).load_weights(all_weights(hp, db), "hpnn/", device=device)
 
 
-@pytest.mark.parametrize("P,H,W,mode", [(2, 128, 112, "mixed"), (4, 128, 112, "tc2"), (2, 160, 128, "tc3"), (3, 144, 120, "mixed")])
+@pytest.mark.parametrize("P,H,W,mode", [(2, 128, 112, "mixed"), (4, 128, 112, "tc2"), (2, 160, 128, "tc3"), (3, 144, 120, "mixed"), (2, 512, 448, "mixed"), (4, 256, 256, "mixed")])
 def test_band_emulation_is_bit_identical(P, H, W, mode):
     from poisson_cnn_b200.spatial import SpatialHPNN
     from poisson_cnn_b200.synthetic import make_problem
