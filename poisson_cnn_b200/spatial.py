@@ -46,8 +46,8 @@ def _view(t, which="buf"):
 class SpatialHPNN:
     """model([rhs, dx]) of a Homogeneous_Poisson_NN_Legacy with the grid split into row bands.
 
-    rhs [B,1,H,W] and dx [B,1] are given in full on every rank and the full result is returned on every rank; H must be a
-    multiple of the number of bands and every band at least 16 rows.  Tensor-core precisions only ('mixed', 'tc2', 'tc3',
+    rhs [B,1,H,W] and dx [B,1] are given in full on every rank and the full result is returned on every rank; every band has
+    at least 16 rows.  Tensor-core precisions only ('mixed', 'tc2', 'tc3',
     'tc'): the strict FP32 kernels resolve padding while loading tiles and have no materialised halo to exchange."""
 
     def __init__(self, hpnn, world=None, group=None):
@@ -122,13 +122,16 @@ class SpatialHPNN:
         return r if self.group is None else self.dist.get_global_rank(self.group, r)
 
     def _gather_rows(self, parts):
-        """{band: [B,C,h,W] fp32} -> [B,C,H,W] on every rank."""
+        """{band: [B,C,h_i,W] fp32} -> [B,C,H,W] on every rank (bands may differ in height)."""
         if self.dist is None:
             return torch.cat([parts[i] for i in self.local], 2)
-        x = parts[self.rank].contiguous()
-        out = torch.empty((self.world,) + tuple(x.shape), device=x.device, dtype=x.dtype)
-        self.dist.all_gather_into_tensor(out, x, group=self.group)
-        return out.permute(1, 2, 0, 3, 4).reshape(x.shape[0], x.shape[1], self.world * x.shape[2], x.shape[3]).contiguous()
+        x = parts[self.rank]
+        hmax = max(self.bounds[i + 1] - self.bounds[i] for i in range(self.world))
+        pad = torch.zeros((x.shape[0], x.shape[1], hmax, x.shape[3]), device=x.device, dtype=x.dtype)
+        pad[:, :, :x.shape[2]].copy_(x)
+        out = torch.empty((self.world,) + tuple(pad.shape), device=x.device, dtype=x.dtype)
+        self.dist.all_gather_into_tensor(out, pad, group=self.group)
+        return torch.cat([out[i, :, :, :self.bounds[i + 1] - self.bounds[i]] for i in range(self.world)], 2)
 
     # ------------------------------------------------------------------ band-wise layers
     def _each(self, fn):
@@ -167,7 +170,7 @@ class SpatialHPNN:
             done.append(s)
         return chain
 
-    def _branches(self, x0, H, Wd, h, split):
+    def _branches(self, x0, H, Wd, split):
         """Low-resolution branch outputs for the banded merge: {'dc': [(per-band Blk8 dict, kernel, bias, stride, act)],
         'rs': [(full fp32 source, method)], 'um': 1|2} or None when the banded merge does not apply (then everything runs
         replicated through the model's own _branches_tc / _merge_tc)."""
@@ -178,8 +181,13 @@ class SpatialHPNN:
         deconv = [b for b in blocks if b.kind == "deconv"]
         strides = [b.upsampling_factor for b in deconv]
         rs_hw = [(-(-H // b.downsampling_factor), -(-Wd // b.downsampling_factor)) for b in blocks if b.kind != "deconv"]
-        ok = (bsplit == 1 and F == 32 and deconv and len(blocks) <= 16 and all(s <= 32 for s in strides) and len(deconv) <= 8
-              and len(rs_hw) <= 8 and all(b.upsampling_factor == b.downsampling_factor and h % b.upsampling_factor == 0 for b in deconv))
+        bnd = self.bounds
+        hs = [bnd[i + 1] - bnd[i] for i in range(self.world)]
+        # band boundaries are multiples of every transpose-conv stride (self.align), so every branch's low-resolution rows and
+        # up-sampling phases split cleanly; SAME pooling must not start before row 0 (pad_before = 0)
+        ok = (bsplit == 1 and F == 32 and bool(deconv) and len(blocks) <= 16 and all(s <= 32 for s in strides) and len(deconv) <= 8
+              and len(rs_hw) <= 8 and all(b.upsampling_factor == b.downsampling_factor and all(r % b.upsampling_factor == 0 for r in bnd[:-1])
+                                          and (-(-H // b.downsampling_factor) * b.downsampling_factor - H) // 2 == 0 for b in deconv))
         if not ok:
             return None
         um = 1 if ops.upsample_merge_tc_fits(strides, rs_hw) else (2 if (rs_hw and ops.upsample_merge_tc_fits(strides, [])) else 0)
@@ -189,7 +197,7 @@ class SpatialHPNN:
             m._branch_out_hw(b, H, Wd)
         chain = self._pool_chain(H, Wd, [b.downsampling_factor for b in blocks])
         banded = {b.downsampling_factor for b in deconv
-                  if h % b.downsampling_factor == 0 and h // b.downsampling_factor >= 16 and -(-Wd // b.downsampling_factor) >= 16}
+                  if min(hs) // b.downsampling_factor >= 16 and -(-Wd // b.downsampling_factor) >= 16}
         self._tick("branch setup")
         # replicated levels: from the gathered features, through the model's own pyramid (same chain by construction)
         rep = [b for b in blocks if b.downsampling_factor not in banded]
@@ -245,12 +253,12 @@ class SpatialHPNN:
                                      next_pad=b.pad if r + 1 < b.n_convs else PAD_CONSTANT)
             else:                                   # this band's rows of the replicated low-resolution output
                 full = rep_out[(b.kind, b.index)]
-                hl = h // s_
                 vf = _view(full)
 
                 def rows(i):
+                    lo_, hl = bnd[i] // s_, -(-hs[i] // s_)
                     t_ = ops.Blk8(full.B, full.C, hl, full.W, full.device, split=1)
-                    _view(t_)[:, :, HALO:HALO + hl].copy_(vf[:, :, HALO + i * hl:HALO + (i + 1) * hl])
+                    _view(t_)[:, :, HALO:HALO + hl].copy_(vf[:, :, HALO + lo_:HALO + lo_ + hl])
                     return t_
                 t = self._each(rows)
             dk, db = m.conv(name + "/deconv")
@@ -261,14 +269,15 @@ class SpatialHPNN:
         self._tick("branches (banded)")
         return {"dc": dc, "rs": rs, "um": um, "alpha": 1.0 / float(len(blocks) * F)}
 
-    def _merge_banded(self, br, cat, H, Wd, h):
+    def _merge_banded(self, br, cat, H, Wd):
         F = self.m.filters
 
         def one(i):
+            r0, hb = self.bounds[i], self.bounds[i + 1] - self.bounds[i]
             packed = [(t[i], k, b_, s_, a_) for t, k, b_, s_, a_ in br["dc"]]
-            ops.upsample_merge_tc_blk8(packed, br["rs"] if br["um"] == 1 else [], br["alpha"], cat[i], F, h, Wd, row_offset=i * h, full_H=H)
+            ops.upsample_merge_tc_blk8(packed, br["rs"] if br["um"] == 1 else [], br["alpha"], cat[i], F, hb, Wd, row_offset=r0, full_H=H)
             if br["um"] == 2:
-                ops.resize_add_blk8(br["rs"], br["alpha"], cat[i], F, h, Wd, row_offset=i * h, full_H=H)
+                ops.resize_add_blk8(br["rs"], br["alpha"], cat[i], F, hb, Wd, row_offset=r0, full_H=H)
             return None
         self._each(one)
 
@@ -282,9 +291,17 @@ class SpatialHPNN:
             raise NotImplementedError("config not supported by the tensor-core program")
         B, _, H, Wd = rhs.shape
         P = self.world
-        if H % P or H // P < 16:
-            raise ValueError("the grid height (%d) must be a multiple of the %d bands and every band at least 16 rows" % (H, P))
-        h = H // P
+        # band boundaries: as even as possible on multiples of the lcm of the transpose-conv strides (48 for the shipped
+        # config), so that every deconv branch's low-resolution rows and up-sampling phases split with the bands
+        L = 1
+        for b_ in m.bottleneck_deconv_blocks:
+            L = L * b_.upsampling_factor // __import__("math").gcd(L, b_.upsampling_factor)
+        bnd = [0] + [int(round(i * H / P / L)) * L for i in range(1, P)] + [H]
+        if any(bnd[i + 1] - bnd[i] < 16 for i in range(P)):
+            bnd = [(i * H) // P for i in range(P + 1)]              # grid too small for aligned bands: plain equal split
+        if any(bnd[i + 1] - bnd[i] < 16 for i in range(P)):
+            raise ValueError("every band of the grid height (%d) over %d bands must have at least 16 rows" % (H, P))
+        self.bounds = bnd
         F = m.filters
         dev = rhs.device
         split = m.tc_split
@@ -295,10 +312,11 @@ class SpatialHPNN:
             posx, posy = ops.position_table(dev, H), ops.position_table(dev, Wd)
 
             def first(i):
-                band = rhs[:, :, i * h:(i + 1) * h].contiguous()
+                r0, h = bnd[i], bnd[i + 1] - bnd[i]
+                band = rhs[:, :, r0:r0 + h].contiguous()
                 if m.use_positional_embeddings:
                     x = torch.empty((B, 3, h, Wd), device=dev, dtype=torch.float32)
-                    ops.check(ops.lib.pcnn_hpnn_input_f32(band.data_ptr(), posx[i * h:].data_ptr(), posy.data_ptr(), x.data_ptr(), B, h, Wd,
+                    ops.check(ops.lib.pcnn_hpnn_input_f32(band.data_ptr(), posx[r0:].data_ptr(), posy.data_ptr(), x.data_ptr(), B, h, Wd,
                                                           ops._stream()), "hpnn_input")
                 else:
                     x = band
@@ -310,11 +328,11 @@ class SpatialHPNN:
                                next_pad=m.pre_pad if k + 1 < m.n_pre else PAD_CONSTANT)
             x0 = t
             self._tick("pre_bottleneck (banded)")
-            br = self._branches(x0, H, Wd, h, split)
-            cat = self._each(lambda i: ops.Blk8(B, 2 * F, h, Wd, dev, split=split))
+            br = self._branches(x0, H, Wd, split)
+            cat = self._each(lambda i: ops.Blk8(B, 2 * F, bnd[i + 1] - bnd[i], Wd, dev, split=split))
             self._conv(x0, "non_bottleneck_conv", ACT_LEAKY_RELU, PAD_CONSTANT, out=cat)
             if br is not None:
-                self._merge_banded(br, cat, H, Wd, h)
+                self._merge_banded(br, cat, H, Wd)
                 self._tick("upsample-merge (banded)")
             else:
                 # general merge kernels (no fused tensor-core merge for this config / shape): everything replicated from the
@@ -330,7 +348,7 @@ class SpatialHPNN:
                         continue
                     vf = _view(cat_full, which)
                     for i in self.local:
-                        _view(cat[i], which)[:, p0:, HALO:HALO + h].copy_(vf[:, p0:, HALO + i * h:HALO + (i + 1) * h])
+                        _view(cat[i], which)[:, p0:, HALO:HALO + bnd[i + 1] - bnd[i]].copy_(vf[:, p0:, HALO + bnd[i]:HALO + bnd[i + 1]])
                 del cat_full, branches, x0_full
                 self._tick("branches + merge (replicated)")
             self._exchange(cat)
