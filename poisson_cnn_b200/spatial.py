@@ -85,36 +85,36 @@ class SpatialHPNN:
     # ------------------------------------------------------------------ exchange
     def _exchange(self, ts):
         """Fill the halo rows at interior band edges with the neighbour's edge rows.  ts: {band: Blk8}."""
-        for which in ("buf", "lo"):
-            if any(getattr(t, which) is None for t in ts.values()):
-                continue
-            if self.dist is None:
+        whiches = [w for w in ("buf", "lo") if all(getattr(t, w) is not None for t in ts.values())]
+        if self.dist is None:
+            for which in whiches:
                 for i in self.local[:-1]:
                     up, dn = _view(ts[i], which), _view(ts[i + 1], which)
                     Hp = up.shape[2]
                     dn[:, :, 0:HALO].copy_(up[:, :, Hp - 2 * HALO:Hp - HALO])        # my bottom rows -> lower band's top halo
                     up[:, :, Hp - HALO:Hp].copy_(dn[:, :, HALO:2 * HALO])            # lower band's top rows -> my bottom halo
-            else:
+        else:
+            reqs, fills = [], []
+            for which in whiches:                      # one NCCL group for both buffers and both neighbours
                 v = _view(ts[self.rank], which)
                 Hp = v.shape[2]
-                reqs, recv = [], {}
                 if self.rank > 0:
                     send_up = v[:, :, HALO:2 * HALO].contiguous()
-                    recv["top"] = torch.empty_like(send_up)
+                    got = torch.empty_like(send_up)
                     reqs += [self.dist.P2POp(self.dist.isend, send_up, self._peer(self.rank - 1), self.group),
-                             self.dist.P2POp(self.dist.irecv, recv["top"], self._peer(self.rank - 1), self.group)]
+                             self.dist.P2POp(self.dist.irecv, got, self._peer(self.rank - 1), self.group)]
+                    fills.append((v[:, :, 0:HALO], got))
                 if self.rank < self.world - 1:
                     send_dn = v[:, :, Hp - 2 * HALO:Hp - HALO].contiguous()
-                    recv["bottom"] = torch.empty_like(send_dn)
+                    got = torch.empty_like(send_dn)
                     reqs += [self.dist.P2POp(self.dist.isend, send_dn, self._peer(self.rank + 1), self.group),
-                             self.dist.P2POp(self.dist.irecv, recv["bottom"], self._peer(self.rank + 1), self.group)]
-                if reqs:
-                    for r in self.dist.batch_isend_irecv(reqs):
-                        r.wait()
-                if "top" in recv:
-                    v[:, :, 0:HALO].copy_(recv["top"])
-                if "bottom" in recv:
-                    v[:, :, Hp - HALO:Hp].copy_(recv["bottom"])
+                             self.dist.P2POp(self.dist.irecv, got, self._peer(self.rank + 1), self.group)]
+                    fills.append((v[:, :, Hp - HALO:Hp], got))
+            if reqs:
+                for r in self.dist.batch_isend_irecv(reqs):
+                    r.wait()
+            for dst, got in fills:
+                dst.copy_(got)
         for t in ts.values():
             t.halo = (t.halo[0], HALO)        # the halo now holds what the next layer must see: no refill
 
@@ -199,34 +199,22 @@ class SpatialHPNN:
         banded = {b.downsampling_factor for b in deconv
                   if min(hs) // b.downsampling_factor >= 16 and -(-Wd // b.downsampling_factor) >= 16}
         self._tick("branch setup")
-        # replicated levels: from the gathered features, through the model's own pyramid (same chain by construction)
+
+        def aligned(t):       # level t can be pooled per band exactly as the full map pools it
+            return all(r % t == 0 for r in bnd[:-1]) and (-(-H // t) * t - H) // 2 == 0 and min(hs) >= t
         rep = [b for b in blocks if b.downsampling_factor not in banded]
-        rep_out = {}
-        if rep:
-            x0_full = self._gather_rows(self._each(lambda i: ops.from_blk8(x0[i])))
-            with ops.blk8_pool_scope(self.full_pool):
-                pools = m._pool_pyramid(x0_full, [b.downsampling_factor for b in blocks])
-                for b in rep:
-                    ph, pw = -(-H // b.downsampling_factor), -(-Wd // b.downsampling_factor)
-                    name = "bottleneck_%s/%d" % (b.kind, b.index)
-                    if b.kind == "deconv" and min(ph, pw) >= 16:
-                        t = ops.to_blk8(pools[b.downsampling_factor], split=bsplit, halo=b.pad)
-                        t = m._conv_tc(t, name + "/conv0", b.act, b.pad, next_pad=b.pad)
-                        for r in range(1, b.n_convs):
-                            t = m._resnet_tc(t, "%s/resnet%d" % (name, r), b.act, b.pad, b.use_batchnorm,
-                                             next_pad=b.pad if r + 1 < b.n_convs else PAD_CONSTANT)
-                    else:
-                        t = m._bottleneck_lowres(b, x0_full, pools[b.downsampling_factor])
-                        if b.kind == "deconv":
-                            t = ops.to_blk8(t)
-                    rep_out[(b.kind, b.index)] = t
-                del pools
-            del x0_full
-        self._tick("branches (replicated)")
-        # banded levels: pooled per band along the full map's chain, convolved per band with halo exchange
-        band_pool = {}
-        x0f = self._each(lambda i: ops.from_blk8(x0[i])) if banded else None
-        needed = set(banded)                      # banded levels and, transitively, the levels they are pooled from
+        # every replicated level is derived, along the full map's chain, from the SMALLEST map that can be pooled per band and
+        # gathered (level 16 for the 32/64/128 branches at 2048^2: 2 MB instead of the 537 MB of the features themselves)
+        gather_levels, need_x0 = set(), False
+        for b in rep:
+            t = b.downsampling_factor
+            while t and not aligned(t):
+                t = chain[t][0]
+            if t:
+                gather_levels.add(t)
+            else:
+                need_x0 = True
+        needed = set(banded) | gather_levels      # per-band levels and, transitively, the levels they are pooled from
         grew = True
         while grew:
             grew = False
@@ -234,9 +222,38 @@ class SpatialHPNN:
                 if chain[q][0] and chain[q][0] not in needed:
                     needed.add(chain[q][0])
                     grew = True
+        band_pool = {}
+        x0f = self._each(lambda i: ops.from_blk8(x0[i])) if (needed or need_x0) else None
         for s_ in sorted(needed):
             src, f = chain[s_]
             band_pool[s_] = self._each(lambda i: ops.avgpool_same(x0f[i] if src == 0 else band_pool[src][i], f))
+        full = {0: self._gather_rows(x0f)} if need_x0 else {}
+        for t in sorted(gather_levels):
+            full[t] = self._gather_rows(band_pool[t])
+        rep_out = {}
+        with ops.blk8_pool_scope(self.full_pool):
+            def full_level(t):
+                if t not in full:
+                    src, f = chain[t]
+                    full[t] = ops.avgpool_same(full_level(src), f)
+                return full[t]
+            for b in rep:
+                ph, pw = -(-H // b.downsampling_factor), -(-Wd // b.downsampling_factor)
+                name = "bottleneck_%s/%d" % (b.kind, b.index)
+                pooled = full_level(b.downsampling_factor)
+                if b.kind == "deconv" and min(ph, pw) >= 16:
+                    t = ops.to_blk8(pooled, split=bsplit, halo=b.pad)
+                    t = m._conv_tc(t, name + "/conv0", b.act, b.pad, next_pad=b.pad)
+                    for r in range(1, b.n_convs):
+                        t = m._resnet_tc(t, "%s/resnet%d" % (name, r), b.act, b.pad, b.use_batchnorm,
+                                         next_pad=b.pad if r + 1 < b.n_convs else PAD_CONSTANT)
+                else:
+                    t = m._bottleneck_lowres(b, None, pooled)
+                    if b.kind == "deconv":
+                        t = ops.to_blk8(t)
+                rep_out[(b.kind, b.index)] = t
+        del full
+        self._tick("branches (replicated)")
         dc, rs = [], []
         for b in blocks:
             name = "bottleneck_%s/%d" % (b.kind, b.index)
