@@ -121,17 +121,19 @@ class SpatialHPNN:
     def _peer(self, r):
         return r if self.group is None else self.dist.get_global_rank(self.group, r)
 
-    def _gather_rows(self, parts):
-        """{band: [B,C,h_i,W] fp32} -> [B,C,H,W] on every rank (bands may differ in height)."""
+    def _gather_rows(self, parts, div=1):
+        """{band: [B,C,h_i/div,W'] fp32} -> the full map on every rank (bands may differ in height; div: the pooling level
+        of the parts, whose band i holds ceil(h_i / div) rows)."""
         if self.dist is None:
             return torch.cat([parts[i] for i in self.local], 2)
         x = parts[self.rank]
-        hmax = max(self.bounds[i + 1] - self.bounds[i] for i in range(self.world))
-        pad = torch.zeros((x.shape[0], x.shape[1], hmax, x.shape[3]), device=x.device, dtype=x.dtype)
+        rows = [-(-(self.bounds[i + 1] - self.bounds[i]) // div) for i in range(self.world)]
+        assert x.shape[2] == rows[self.rank]
+        pad = torch.zeros((x.shape[0], x.shape[1], max(rows), x.shape[3]), device=x.device, dtype=x.dtype)
         pad[:, :, :x.shape[2]].copy_(x)
         out = torch.empty((self.world,) + tuple(pad.shape), device=x.device, dtype=x.dtype)
         self.dist.all_gather_into_tensor(out, pad, group=self.group)
-        return torch.cat([out[i, :, :, :self.bounds[i + 1] - self.bounds[i]] for i in range(self.world)], 2)
+        return torch.cat([out[i, :, :, :rows[i]] for i in range(self.world)], 2)
 
     # ------------------------------------------------------------------ band-wise layers
     def _each(self, fn):
@@ -229,7 +231,7 @@ class SpatialHPNN:
             band_pool[s_] = self._each(lambda i: ops.avgpool_same(x0f[i] if src == 0 else band_pool[src][i], f))
         full = {0: self._gather_rows(x0f)} if need_x0 else {}
         for t in sorted(gather_levels):
-            full[t] = self._gather_rows(band_pool[t])
+            full[t] = self._gather_rows(band_pool[t], div=t)
         rep_out = {}
         with ops.blk8_pool_scope(self.full_pool):
             def full_level(t):
