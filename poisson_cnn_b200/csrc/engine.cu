@@ -724,7 +724,7 @@ static int finalize(Model& m, int precision, cudaStream_t st) {
             const int nm = m.hp_mode, bm = m.branch_single ? 1 : nm;
             for (size_t k = 0; k < h.pre.filters.size(); ++k) TRY(tc_pack(m, "hpnn/pre_bottleneck/" + std::to_string(k), nm, st));
             for (const BlockCfg& b : h.blocks) {
-                if (!b.deconv) continue;
+                if (!tc_kernel_ok(b.ksize, b.pad_value) || b.pad > PCNN_PAD_SYMMETRIC) continue;      // FP32 kernels only
                 TRY(tc_pack(m, "hpnn/" + b.name + "/conv0", bm, st));
                 for (int r = 1; r < b.n_convs; ++r)
                     for (int i = 0; i < 3; ++i) TRY(tc_pack(m, "hpnn/" + b.name + "/resnet" + std::to_string(r) + "/conv" + std::to_string(i), bm, st));
@@ -1287,7 +1287,8 @@ static int hpnn_tc(Ctx& c, const float* rhs, const float* dx, float* out, int B,
         const int ph = cdiv(H, b.ds), pw = cdiv(W, b.ds);
         const std::string name = "hpnn/" + b.name;
         Branch r{&b, false, B8(), F32()};
-        if (b.deconv && std::min(ph, pw) >= 16) {
+        // tensor cores for every branch whose pooled map is at least 16 pixels a side (Python: _branch_on_tc)
+        if (std::min(ph, pw) >= 16 && tc_kernel_ok(b.ksize, b.pad_value) && b.pad <= PCNN_PAD_SYMMETRIC) {
             B8 hb;
             TRY(to_blk8(c, pools[b.ds], Bcap, bsplit, b.pad, nullptr, 0, &hb));
             TcArgs a; a.act = b.act; a.pad = b.pad; a.next_pad = b.pad;
@@ -1300,8 +1301,8 @@ static int hpnn_tc(Ctx& c, const float* rhs, const float* dx, float* out, int B,
                               rr + 1 < b.n_convs ? b.pad : PCNN_PAD_CONSTANT, Bcap, &y));
                 hb = y;
             }
-            if (um_tc) { r.is_b8 = true; r.b8 = hb; }
-            else { TRY(from_blk8(c, hb, hb.C, Bcap, nullptr, &r.f32)); c.free(hb); }
+            if (um_tc && b.deconv) { r.is_b8 = true; r.b8 = hb; }
+            else { TRY(from_blk8(c, hb, hb.C, Bcap, nullptr, &r.f32)); c.free(hb); }      // resize branches read NCHW fp32
         } else {
             TRY(branch_lowres_f32(c, b, pools[b.ds], Bcap, &r.f32));
             if (um_tc && b.deconv) {      // tiny map (< 16 pixels a side) computed by the FP32 stack kernel

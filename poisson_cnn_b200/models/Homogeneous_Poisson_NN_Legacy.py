@@ -239,6 +239,12 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
     def _tc_ok(self, ksize, pad_value=0.0):
         return ksize % 2 == 1 and ksize <= 15 and float(pad_value) == 0.0
 
+    def _branch_on_tc(self, blk, ph, pw):
+        """A branch's conv + resnet chain runs on the tensor cores when its pooled map is at least 16 pixels a side (the
+        transpose-conv branches at every shipped size; the multilinear ones from ~512-pixel grids on: 64x64 ... 16x16 maps at
+        2048^2, which the FP32 kernels ran at 8 CTAs per launch); smaller maps take the fused FP32 stack kernels."""
+        return min(ph, pw) >= 16 and self._tc_ok(blk.ksize, blk.pad_value) and blk.pad in (PAD_CONSTANT, 1)
+
     def _branches_tc(self, x0_f32, H, Wd, split):
         """pool -> conv -> resnets of every bottleneck branch from the full-resolution NCHW fp32 features (the pooling pyramid
         reads them); returns the low-res branch outputs for _merge_tc."""
@@ -265,14 +271,14 @@ class Homogeneous_Poisson_NN_Legacy(WeightedModel):
             self._branch_out_hw(blk, H, Wd)
             ph, pw = -(-H // blk.downsampling_factor), -(-Wd // blk.downsampling_factor)
             name = "bottleneck_%s/%d" % (blk.kind, blk.index)
-            if blk.kind == "deconv" and min(ph, pw) >= 16:
+            if self._branch_on_tc(blk, ph, pw):
                 h = ops.to_blk8(pools[blk.downsampling_factor], split=bsplit, halo=blk.pad)
                 h = self._conv_tc(h, name + "/conv0", blk.act, blk.pad, next_pad=blk.pad)
                 for r in range(1, blk.n_convs):
                     h = self._resnet_tc(h, "%s/resnet%d" % (name, r), blk.act, blk.pad, blk.use_batchnorm,
                                         next_pad=blk.pad if r + 1 < blk.n_convs else PAD_CONSTANT)
-                if not um_tc:
-                    h = ops.from_blk8(h)
+                if not um_tc or blk.kind != "deconv":
+                    h = ops.from_blk8(h)         # the resize branches and the non-tensor-core merges read NCHW fp32
             else:
                 h = self._bottleneck_lowres(blk, x0_f32, pools[blk.downsampling_factor])
                 if um_tc and blk.kind == "deconv":

@@ -243,12 +243,14 @@ class SpatialHPNN:
                 ph, pw = -(-H // b.downsampling_factor), -(-Wd // b.downsampling_factor)
                 name = "bottleneck_%s/%d" % (b.kind, b.index)
                 pooled = full_level(b.downsampling_factor)
-                if b.kind == "deconv" and min(ph, pw) >= 16:
+                if m._branch_on_tc(b, ph, pw):
                     t = ops.to_blk8(pooled, split=bsplit, halo=b.pad)
                     t = m._conv_tc(t, name + "/conv0", b.act, b.pad, next_pad=b.pad)
                     for r in range(1, b.n_convs):
                         t = m._resnet_tc(t, "%s/resnet%d" % (name, r), b.act, b.pad, b.use_batchnorm,
                                          next_pad=b.pad if r + 1 < b.n_convs else PAD_CONSTANT)
+                    if b.kind != "deconv":
+                        t = ops.from_blk8(t)
                 else:
                     t = m._bottleneck_lowres(b, None, pooled)
                     if b.kind == "deconv":
