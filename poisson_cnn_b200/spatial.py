@@ -66,6 +66,7 @@ class SpatialHPNN:
         self.pools = {i: {} for i in self.local}        # private BLK8 pools: band buffers carry neighbour rows in their halos
         self.full_pool = {}
         self.profile = None                             # set to {} to collect CUDA-event times per phase (ms, last call)
+        self.min_band_pixels = 128 * 1024               # low-resolution pixels per band below which a branch runs replicated
 
     def _tick(self, name):
         if self.profile is None:
@@ -198,8 +199,12 @@ class SpatialHPNN:
         for b in blocks:
             m._branch_out_hw(b, H, Wd)
         chain = self._pool_chain(H, Wd, [b.downsampling_factor for b in blocks])
+        # a branch is split with the bands when a band of its low-resolution map is large enough for the convolution time
+        # saved to exceed the ~80 us an exchange costs per layer (measured: splitting every branch at N = 2 took 5.6 ms where
+        # the replicated branches take 3); smaller maps run replicated
         banded = {b.downsampling_factor for b in deconv
-                  if min(hs) // b.downsampling_factor >= 16 and -(-Wd // b.downsampling_factor) >= 16}
+                  if min(hs) // b.downsampling_factor >= 16 and -(-Wd // b.downsampling_factor) >= 16
+                  and (min(hs) // b.downsampling_factor) * (-(-Wd // b.downsampling_factor)) >= self.min_band_pixels}
         self._tick("branch setup")
 
         def aligned(t):       # level t can be pooled per band exactly as the full map pools it
