@@ -43,6 +43,22 @@ def _view(t, which="buf"):
     return buf[:n].view(t.B, planes, t.H + 2 * HALO, t.W + 2 * HALO, 8)
 
 
+def band_bounds(H, P, strides):
+    """Row boundaries [r_0 = 0, ..., r_P = H] of P bands: as even as possible on multiples of lcm(strides), so that the
+    low-resolution rows and the up-sampling phases of every transpose-conv branch split with the bands; a plain equal
+    split when the grid is too small for aligned bands of >= 16 rows."""
+    import math
+    L = 1
+    for s_ in strides:
+        L = L * int(s_) // math.gcd(L, int(s_))
+    bnd = [0] + [int(round(i * H / P / L)) * L for i in range(1, P)] + [H]
+    if any(bnd[i + 1] - bnd[i] < 16 for i in range(P)):
+        bnd = [(i * H) // P for i in range(P + 1)]
+    if any(bnd[i + 1] - bnd[i] < 16 for i in range(P)):
+        raise ValueError("every band of the grid height (%d) over %d bands must have at least 16 rows" % (H, P))
+    return bnd
+
+
 class SpatialHPNN:
     """model([rhs, dx]) of a Homogeneous_Poisson_NN_Legacy with the grid split into row bands.
 
@@ -317,16 +333,7 @@ class SpatialHPNN:
             raise NotImplementedError("config not supported by the tensor-core program")
         B, _, H, Wd = rhs.shape
         P = self.world
-        # band boundaries: as even as possible on multiples of the lcm of the transpose-conv strides (48 for the shipped
-        # config), so that every deconv branch's low-resolution rows and up-sampling phases split with the bands
-        L = 1
-        for b_ in m.bottleneck_deconv_blocks:
-            L = L * b_.upsampling_factor // __import__("math").gcd(L, b_.upsampling_factor)
-        bnd = [0] + [int(round(i * H / P / L)) * L for i in range(1, P)] + [H]
-        if any(bnd[i + 1] - bnd[i] < 16 for i in range(P)):
-            bnd = [(i * H) // P for i in range(P + 1)]              # grid too small for aligned bands: plain equal split
-        if any(bnd[i + 1] - bnd[i] < 16 for i in range(P)):
-            raise ValueError("every band of the grid height (%d) over %d bands must have at least 16 rows" % (H, P))
+        bnd = band_bounds(H, P, [b_.upsampling_factor for b_ in m.bottleneck_deconv_blocks])
         self.bounds = bnd
         F = m.filters
         dev = rhs.device

@@ -373,3 +373,15 @@ def test_engine_host_rowweights_match_the_torch_packer():
     d = np.abs(img.astype(np.float32) - r)
     assert (d > 0).sum() < 1e-3 * d.size
     assert np.all(d <= np.maximum(np.abs(r), 2.0 ** -14) * 2.0 ** -10 * 1.01)
+
+
+def test_spatial_band_bounds():
+    """Band boundaries of the single-grid decomposition: multiples of the lcm of the transpose-conv strides, near-even."""
+    from poisson_cnn_b200.spatial import band_bounds
+    assert band_bounds(2048, 2, [16, 8, 4, 3, 2]) == [0, 1008, 2048]
+    b = band_bounds(2048, 8, [16, 8, 4, 3, 2])
+    assert b[0] == 0 and b[-1] == 2048 and all(r % 48 == 0 for r in b[:-1]) and min(b[i + 1] - b[i] for i in range(8)) >= 240
+    assert band_bounds(128, 4, [16, 8, 4, 3, 2]) == [0, 32, 64, 96, 128]          # too small for aligned bands: equal split
+    assert band_bounds(256, 4, [16, 8, 4, 3, 2]) == [0, 48, 144, 192, 256]
+    with pytest.raises(ValueError):
+        band_bounds(48, 4, [2])
