@@ -315,6 +315,8 @@ def run_config2(args):
     rank, world, device = h.rank, h.world, h.device
     B, nx, ny = args.batch, args.grid, args.grid
     model, (hp_cfg, db_cfg, w) = build_model(device, args.precision)
+    if args.microbatch:
+        model.microbatch_samples = args.microbatch
 
     # synthetic problems: a small pool of distinct smooth fields tiled to the batch (host generation of
     # 256 bicubic fields per rank is slow and irrelevant to the measurement); dx differs per sample
@@ -370,7 +372,7 @@ def run_config2(args):
         kk = args.roofline_kernel[2]
         hp_mode = {"mixed": "tc2"}.get(args.precision, args.precision)      # precision mode of the HPNN, which owns the timed kernel
         issue_factor = {"tc": 1.0, "tc3": 3.0, "tc2": 2.0}.get(hp_mode, 0.0) * (kk + 3.0) / kk   # MMAs issued per algorithmic MAC
-        samples_per_launch = min(B, max(1, int((getattr(model, "max_microbatch", B) or B) * 65536 // (nx * ny))))
+        samples_per_launch = min(B, args.microbatch or max(1, int((getattr(model, "max_microbatch", B) or B) * 65536 // (nx * ny))))
         rec = ncu_traffic("conv2d_%d_%d_k%d_%s" % (args.roofline_kernel + (hp_mode,))) if (nx, ny) == (256, 256) else None
         traffic = rec["bytes_per_sample"] * samples_per_launch if rec else None
         roofline = {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
@@ -686,6 +688,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs[i-1]: " + "; ".join("%d = %s" % kv for kv in CONFIGS.items()))
     ap.add_argument("--batch", type=int, default=256, help="config 2: samples per GPU per step (256); configs 3/4: total batch per shape (default 128 / 16)")
     ap.add_argument("--grid", type=int, default=256)
+    ap.add_argument("--microbatch", type=int, default=0, help="config 2: samples per slice of the forward pass (0: the model's default, 128 at 256x256)")
     ap.add_argument("--grids", default="", help="config 4: comma list of square grid sizes (default 1024,2048)")
     ap.add_argument("--precision", default=os.environ.get("PCNN_PRECISION", "mixed"), choices=["fp32", "tc", "tc2", "tc3", "mixed"],
                     help="mixed (default): tc2 in the HPNN + single-pass tc in the DBCNN, holds the 2e-3 budget with a 6x margin; tc2: fp16 main MMA + one e4m3 correction MMA everywhere; tc3: hi/lo fp16 split; tc: single FP16 pass (NOT compliant: 4.4e-3); fp32: strict CUDA-core path")
