@@ -315,8 +315,8 @@ def run_config2(args):
     rank, world, device = h.rank, h.world, h.device
     B, nx, ny = args.batch, args.grid, args.grid
     model, (hp_cfg, db_cfg, w) = build_model(device, args.precision)
-    if args.microbatch:
-        model.microbatch_samples = args.microbatch
+    args.microbatch = args.microbatch or max(1, 256 * 65536 // (nx * ny))
+    model.microbatch_samples = args.microbatch
 
     # synthetic problems: a small pool of distinct smooth fields tiled to the batch (host generation of
     # 256 bicubic fields per rank is slow and irrelevant to the measurement); dx differs per sample
@@ -444,7 +444,8 @@ def run_config2(args):
                    "l2": "inputs+activations per step (%.1f GB) exceed the 126 MB L2" % (B * nx * ny * 4 * 32 / 1e9),
                    "flop_per_solution": pcnn_flops(nx, ny),
                    "host": "model-level C ABI (pcnn_forward: layer program in libpcnn.so)" if use_engine else "op-by-op Python program",
-                   "workspace_bytes": model.engine().workspace_bytes("pcnn", B, nx, ny) if use_engine else None},
+                   "workspace_bytes": model.engine().workspace_bytes("pcnn", B, nx, ny) if use_engine else None,
+                   "samples_per_slice": samples_per_launch if ks else None},
         "e2e": {"value": e2e_value, "unit": "solutions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_host.numel() * 4, "steps": e2e_steps},
         "gpu_launches": int(launches),
         "clocks": sampler.result(),
@@ -688,7 +689,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs[i-1]: " + "; ".join("%d = %s" % kv for kv in CONFIGS.items()))
     ap.add_argument("--batch", type=int, default=256, help="config 2: samples per GPU per step (256); configs 3/4: total batch per shape (default 128 / 16)")
     ap.add_argument("--grid", type=int, default=256)
-    ap.add_argument("--microbatch", type=int, default=0, help="config 2: samples per slice of the forward pass (0: the model's default, 128 at 256x256)")
+    ap.add_argument("--microbatch", type=int, default=0, help="config 2: samples per slice of the forward pass (0: 256 * 65536 / (grid*grid) -- the whole 256-problem batch in one slice at 256x256, a 24.4 GB workspace, +2 %% over the library default of 128 (12.2 GB) in alternating runs)")
     ap.add_argument("--grids", default="", help="config 4: comma list of square grid sizes (default 1024,2048)")
     ap.add_argument("--precision", default=os.environ.get("PCNN_PRECISION", "mixed"), choices=["fp32", "tc", "tc2", "tc3", "mixed"],
                     help="mixed (default): tc2 in the HPNN + single-pass tc in the DBCNN, holds the 2e-3 budget with a 6x margin; tc2: fp16 main MMA + one e4m3 correction MMA everywhere; tc3: hi/lo fp16 split; tc: single FP16 pass (NOT compliant: 4.4e-3); fp32: strict CUDA-core path")
