@@ -6,7 +6,9 @@ SRC := $(wildcard poisson_cnn_b200/csrc/*.cu)
 OBJ := $(patsubst poisson_cnn_b200/csrc/%.cu,build/%.o,$(SRC))
 LIB := poisson_cnn_b200/libpcnn.so
 
-all: $(LIB)
+CHOST := build/pcnn_host
+
+all: $(LIB) $(CHOST)
 
 build/%.o: poisson_cnn_b200/csrc/%.cu poisson_cnn_b200/csrc/pcnn_common.cuh include/pcnn.h
 	@mkdir -p build
@@ -16,6 +18,11 @@ build/engine.o: poisson_cnn_b200/csrc/engine_json.h
 
 $(LIB): $(OBJ)
 	$(NVCC) -shared $(ARCH) -o $@ $(OBJ) -lcudart
+
+# a host in plain C for the model-level ABI (gcc + libcudart only): examples/c_host/pcnn_host.c
+$(CHOST): examples/c_host/pcnn_host.c include/pcnn.h $(LIB)
+	gcc -O2 -Wall -Iinclude -I/usr/local/cuda/include $< -o $@ -Lpoisson_cnn_b200 -lpcnn -L/usr/local/cuda/lib64 -lcudart \
+	    -Wl,-rpath,'$$ORIGIN/../poisson_cnn_b200' -Wl,-rpath,/usr/local/cuda/lib64
 
 clean:
 	rm -rf build $(LIB)
