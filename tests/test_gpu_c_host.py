@@ -48,4 +48,4 @@ def test_plain_c_host_runs_the_forward_pass(tmp_path, precision, tol):
     bad = str(tmp_path / "bad.json")
     open(bad, "w").write('{"hpnn_model": {"bc_type": "robin"}}')
     res = subprocess.run([HOST, bad, wpath, ipath, str(B), str(H), str(W), "0", opath], capture_output=True, text=True, timeout=60)
-    assert res.returncode != 0 and "Provide a config for pre bottleneck convolutions" in res.stderr
+    assert res.returncode != 0 and "bc_type can only be neumann or dirichlet." in res.stderr
