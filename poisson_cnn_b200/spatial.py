@@ -83,6 +83,7 @@ class SpatialHPNN:
         self.full_pool = {}
         self.profile = None                             # set to {} to collect CUDA-event times per phase (ms, last call)
         self.min_band_pixels = 128 * 1024               # low-resolution pixels per band below which a branch runs replicated
+        self._stage = {}                                # send / receive staging buffers of the halo exchange
 
     def _tick(self, name):
         if self.profile is None:
@@ -115,18 +116,20 @@ class SpatialHPNN:
             for which in whiches:                      # one NCCL group for both buffers and both neighbours
                 v = _view(ts[self.rank], which)
                 Hp = v.shape[2]
-                if self.rank > 0:
-                    send_up = v[:, :, HALO:2 * HALO].contiguous()
-                    got = torch.empty_like(send_up)
-                    reqs += [self.dist.P2POp(self.dist.isend, send_up, self._peer(self.rank - 1), self.group),
-                             self.dist.P2POp(self.dist.irecv, got, self._peer(self.rank - 1), self.group)]
-                    fills.append((v[:, :, 0:HALO], got))
-                if self.rank < self.world - 1:
-                    send_dn = v[:, :, Hp - 2 * HALO:Hp - HALO].contiguous()
-                    got = torch.empty_like(send_dn)
-                    reqs += [self.dist.P2POp(self.dist.isend, send_dn, self._peer(self.rank + 1), self.group),
-                             self.dist.P2POp(self.dist.irecv, got, self._peer(self.rank + 1), self.group)]
-                    fills.append((v[:, :, Hp - HALO:Hp], got))
+                for side, peer, rows_out, rows_in in (("up", self.rank - 1, slice(HALO, 2 * HALO), slice(0, HALO)),
+                                                      ("dn", self.rank + 1, slice(Hp - 2 * HALO, Hp - HALO), slice(Hp - HALO, Hp))):
+                    if peer < 0 or peer >= self.world:
+                        continue
+                    # staging buffers are kept per (buffer, side, geometry): no allocation in the steady state
+                    key = (which, side, tuple(v.shape), v.dtype)
+                    if key not in self._stage:
+                        shp = (v.shape[0], v.shape[1], HALO, v.shape[3], v.shape[4])
+                        self._stage[key] = (torch.empty(shp, device=v.device, dtype=v.dtype), torch.empty(shp, device=v.device, dtype=v.dtype))
+                    send, got = self._stage[key]
+                    send.copy_(v[:, :, rows_out])
+                    reqs += [self.dist.P2POp(self.dist.isend, send, self._peer(peer), self.group),
+                             self.dist.P2POp(self.dist.irecv, got, self._peer(peer), self.group)]
+                    fills.append((v[:, :, rows_in], got))
             if reqs:
                 for r in self.dist.batch_isend_irecv(reqs):
                     r.wait()
