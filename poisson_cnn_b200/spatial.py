@@ -152,7 +152,10 @@ class SpatialHPNN:
         pad = torch.zeros((x.shape[0], x.shape[1], max(rows), x.shape[3]), device=x.device, dtype=x.dtype)
         pad[:, :, :x.shape[2]].copy_(x)
         out = torch.empty((self.world,) + tuple(pad.shape), device=x.device, dtype=x.dtype)
-        self.dist.all_gather_into_tensor(out, pad, group=self.group)
+        if x.is_cuda:
+            self.dist.all_gather_into_tensor(out, pad, group=self.group)
+        else:                      # gloo (the CPU test of this logic) takes the per-rank list form
+            self.dist.all_gather(list(out.unbind(0)), pad, group=self.group)
         return torch.cat([out[i, :, :, :rows[i]] for i in range(self.world)], 2)
 
     # ------------------------------------------------------------------ band-wise layers

@@ -166,6 +166,68 @@ def test_world_size_2_gloo_sharding_and_stats():
         assert abs(r[2]["max_abs_err"] - 2e-3) < 1e-6
 
 
+def _gloo_spatial_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import types
+    import torch.distributed as dist
+    from poisson_cnn_b200.sharding import init_from_env
+    from poisson_cnn_b200.spatial import SpatialHPNN, band_bounds, _view, HALO
+    init_from_env("gloo")
+    B, C, H, W = 2, 32, 96, 20
+    bnd = band_bounds(H, world, [2, 3, 4])                     # lcm 12: 36 + 24 + 36 rows on 3 ranks
+    h = bnd[rank + 1] - bnd[rank]
+    planes = (C + 15) // 16 * 2
+    g = torch.Generator().manual_seed(5)
+    full = torch.randn((B, planes, H + 2 * HALO, W + 2 * HALO, 8), generator=g).to(torch.float16)     # same on every rank
+    full_lo = (full.float() * 3).to(torch.float16)
+
+    def band_of(src):
+        t = torch.zeros((B, planes, h + 2 * HALO, W + 2 * HALO, 8), dtype=torch.float16)
+        t[:, :, HALO:HALO + h] = src[:, :, HALO + bnd[rank]:HALO + bnd[rank + 1]]
+        return t
+    blk = types.SimpleNamespace(B=B, C=C, H=h, W=W, halo=(0, 0), buf=band_of(full).reshape(-1), lo=band_of(full_lo).reshape(-1))
+    sp = SpatialHPNN(None)                                     # the default group: one band per rank
+    sp.bounds = bnd
+    sp._exchange({rank: blk})
+    sp._exchange({rank: blk})                                  # the staging buffers are reused: a second exchange must not corrupt
+    ok = True
+    for which, src in (("buf", full), ("lo", full_lo)):
+        v = _view(blk, which)
+        lo_row = HALO if rank == 0 else 0                      # physical edges keep their (zero) halo rows
+        hi_row = h + HALO if rank == world - 1 else h + 2 * HALO
+        want = src[:, :, bnd[rank] + lo_row:bnd[rank] + hi_row]
+        ok = ok and torch.equal(v[:, :, lo_row:hi_row], want)
+        if rank == 0:
+            ok = ok and float(v[:, :, :HALO].abs().max()) == 0.0
+    # ragged gather of a pooled level (div = 5 does not divide the 24-row band: ceil)
+    div = 5
+    rows = [-(-(bnd[i + 1] - bnd[i]) // div) for i in range(world)]
+    part = torch.full((B, 3, rows[rank], 4), float(rank + 1))
+    got = sp._gather_rows({rank: part}, div=div)
+    want = torch.cat([torch.full((B, 3, rows[i], 4), float(i + 1)) for i in range(world)], 2)
+    q.put((rank, bool(ok), bool(torch.equal(got, want)), blk.halo, bnd))
+    dist.destroy_process_group()
+
+
+def test_world_size_3_gloo_halo_exchange_and_row_gather():
+    """The N > 1 host logic of the spatial decomposition (poisson_cnn_b200/spatial.py) on CPU tensors: after the exchange
+    the halo rows of a band hold the neighbour's edge rows of BOTH operand buffers, physical edges are untouched, and the
+    gather of uneven pooled bands reassembles the map."""
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_spatial_worker, args=(r, 3, port, q)) for r in range(3)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=180) for _ in range(3))
+    [p.join(60) for p in procs]
+    assert [r[0] for r in res] == [0, 1, 2]
+    for r in res:
+        assert r[1], "halo rows of rank %d differ from the neighbour's edge rows" % r[0]
+        assert r[2], "row gather on rank %d" % r[0]
+        assert r[3][1] == 7 and r[4] == [0, 36, 60, 96]
+
+
 # ------------------------------------------------------------------ TF checkpoint (tensor bundle) reader
 def test_crc32c_and_snappy_known_answers():
     from poisson_cnn_b200 import tf_checkpoint as T
