@@ -154,6 +154,28 @@ def test_forward_2048_and_residual(bundle):
         assert abs(got - want) < 1e-4 * want, (st, got, want)
 
 
+def test_2048_slice_of_4_equals_single_problems(bundle):
+    """`bench.py --config 4` runs 4 problems of 2048x2048 per engine slice: the 64-channel BLK8 buffers of such a slice pass
+    2^31 BYTES (4 x 64 x 2062^2 fp16 = 2.18e9), the FP32 feature maps 2^31 bytes too.  Every sample of the slice must be
+    bit-identical to the same problem run alone (all reductions are per sample), which a 32-bit offset anywhere would break."""
+    model = bundle[0]
+    p = distinct_problems(4, 2048, 2048, seed=2300)
+    inp = [p[k].cuda() for k in KEYS]
+    try:
+        model.set_precision("mixed")
+        model.microbatch_samples = 4          # bench.py --config 4: the whole 4-problem batch in ONE engine slice
+        together = model(inp)
+        model.microbatch_samples = None
+        for i in (0, 3):
+            alone = model([t[i:i + 1].contiguous() for t in inp])
+            assert torch.equal(together[i:i + 1], alone), "sample %d of the 4-problem slice differs from the single run" % i
+        assert bool(torch.isfinite(together).all())
+    finally:
+        model.microbatch_samples = None
+        model.set_precision("fp32")
+        torch.cuda.empty_cache()
+
+
 # ------------------------------------------------------------------ residual kernel: ragged / unaligned shapes
 @pytest.mark.parametrize("B,H,W", [(3, 70, 93), (2, 5, 5), (2, 6, 7), (1, 35, 128), (2, 34, 132), (1, 67, 260), (2, 97, 1030),
                                    (1, 256, 256), (4, 40, 512)])
