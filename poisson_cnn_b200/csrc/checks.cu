@@ -126,6 +126,34 @@ __global__ void jacobi_sweep_kernel(const float* __restrict__ cur, const float* 
     }
 }
 
+// float4 variant (W % 4 == 0, 16-byte aligned maps): one thread per 4 consecutive points of a row, one 32-bit division per 4
+// points; the arithmetic per point is the scalar kernel's.
+__global__ void __launch_bounds__(256) jacobi_sweep_vec4_kernel(const float* __restrict__ cur, const float* __restrict__ rhs,
+                                                               const float* __restrict__ gs, float* __restrict__ next, int H, int W4) {
+    const int b = blockIdx.y;
+    const unsigned n4 = (unsigned)H * (unsigned)W4;
+    const long long base = (long long)b * n4 * 4;
+    const float* cb = cur + base;
+    const float4* c4 = reinterpret_cast<const float4*>(cb);
+    const float4* f4 = reinterpret_cast<const float4*>(rhs + base);
+    float4* o4 = reinterpret_cast<float4*>(next + base);
+    const float px = 1.0f / (gs[b * 2] * gs[b * 2]), py = 1.0f / (gs[b * 2 + 1] * gs[b * 2 + 1]);
+    const float dinv = 1.0f / (-2.0f * px - 2.0f * py);
+    for (unsigned v = blockIdx.x * 256u + threadIdx.x; v < n4; v += gridDim.x * 256u) {
+        const unsigned i = v / (unsigned)W4, j4 = v - i * (unsigned)W4;
+        const float4 c = __ldg(c4 + v);
+        float4 o = c;
+        if (i > 0 && i < (unsigned)H - 1) {
+            const float4 up = __ldg(c4 + v - W4), dn = __ldg(c4 + v + W4), f = __ldg(f4 + v);
+            if (j4 > 0) o.x = dinv * (f.x - (px * (up.x + dn.x) + py * (__ldg(cb + (long long)v * 4 - 1) + c.y)));
+            o.y = dinv * (f.y - (px * (up.y + dn.y) + py * (c.x + c.z)));
+            o.z = dinv * (f.z - (px * (up.z + dn.z) + py * (c.y + c.w)));
+            if (j4 < (unsigned)W4 - 1) o.w = dinv * (f.w - (px * (up.w + dn.w) + py * (c.z + __ldg(cb + (long long)v * 4 + 4))));
+        }
+        o4[v] = o;
+    }
+}
+
 // ------------------------------------------------------------------ DST-I direct solve (double)
 __global__ void dst_sine_kernel(double* s, int m) {
     const long long total = (long long)m * m;
@@ -269,7 +297,13 @@ extern "C" int pcnn_jacobi_sweep_f32(const float* cur, const float* rhs, const f
                                      float* next, int B, int H, int W, void* stream) {
     PCNN_CHECK_ARG(cur && rhs && grid_spacings && next && cur != next && B > 0 && H >= 3 && W >= 3, "jacobi_sweep_f32: bad argument");
     const long long total = (long long)B * H * W;
-    jacobi_sweep_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(cur, rhs, grid_spacings, next, H, W, total);
+    const long long n4 = (long long)H * (W / 4);
+    if (W % 4 == 0 && B <= 65535 && n4 < (1ll << 31) && (((uintptr_t)cur | (uintptr_t)rhs | (uintptr_t)next) & 15) == 0) {
+        const int gx = (int)std::min<long long>((n4 + 255) / 256, 148 * 16);
+        jacobi_sweep_vec4_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(cur, rhs, grid_spacings, next, H, W / 4);
+    } else {
+        jacobi_sweep_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(cur, rhs, grid_spacings, next, H, W, total);
+    }
     PCNN_CHECK_LAUNCH();
     return PCNN_OK;
 }

@@ -305,11 +305,12 @@ def test_laplacian_residual_and_dst(ops):
     assert float(r) < 1e-3 * float((p["rhs"] ** 2).mean())
 
 
-def test_jacobi_parity(ops):
+@pytest.mark.parametrize("W", [37, 36, 4])          # scalar kernel / float4 kernel / float4 with one vector per row
+def test_jacobi_parity(ops, W):
     from poisson_cnn_b200.synthetic import make_problem
-    p = make_problem(2, 40, 37, seed=41)
-    gs = torch.cat([p["dx"], p["dx"]], 1)
-    guess = torch.randn(2, 1, 40, 37, generator=torch.Generator().manual_seed(2)) * 1e-2
+    p = make_problem(2, 40, W, seed=41)
+    gs = torch.cat([p["dx"], 1.5 * p["dx"]], 1)
+    guess = torch.randn(2, 1, 40, W, generator=torch.Generator().manual_seed(2)) * 1e-2
     ref = O.jacobi_iterations(guess.double(), p["rhs"].double(), gs.double(), 3)
     got = ops.jacobi(dev(guess), dev(p["rhs"]), dev(gs), 3)
     assert rel_l2(got, ref) < FP32_TOL
