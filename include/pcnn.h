@@ -195,7 +195,7 @@ int pcnn_dst_solve_fft(const float* rhs, const float* left, const float* top, co
  * (the reference's zero-integral Lagrange row with uniform Riemann weights) and returns the zero-mean p:
  *   x            in: initial guess (e.g. the Neumann HPNN's prediction), multiplied by guess_scale[b] when given (the
  *                reference's ((dx (n-1))^2 / sf) rescale of the network output, solvers.py:250); out: solution
- *   max_iter     CG iterations enqueued (3 kernels each; per-sample step lengths live on the device, a sample whose
+ *   max_iter     CG iterations enqueued (2 kernels each; per-sample step lengths live on the device, a sample whose
  *                residual is below rel_tol * |b| freezes); no host synchronisation inside
  *   residual_history  [max_iter][B] doubles or NULL: |r_k| / |b| after every iteration
  *   workspace    pcnn_neumann_cg_workspace_bytes(B,H,W), 8-byte aligned */

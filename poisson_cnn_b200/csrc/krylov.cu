@@ -7,7 +7,7 @@
 // that exist).  A is symmetric positive semi-definite with the constants as null space; the reference pins the constant
 // with a zero-integral Lagrange row (uniform Riemann weights), which is equivalent to projecting the right-hand side onto
 // zero mean, solving A p = b - mean(b), and returning the zero-mean solution.  The reference runs scipy BiCGStab with an
-// ILU preconditioner on the CPU; here it is batched conjugate gradients on the GPU: three HBM-bound kernels per iteration,
+// ILU preconditioner on the CPU; here it is batched conjugate gradients on the GPU: two HBM-bound kernels per iteration,
 // per-sample step lengths computed on the device (no host synchronisation inside the loop), dot products by warp shuffles
 // + one double atomic per CTA, convergence per sample (a converged sample freezes: alpha = beta = 0).
 // A is singular: rounding leaves a constant component in r that A can never reduce (p.Ap does not see it, r.r does), so
@@ -91,177 +91,157 @@ __global__ void kr_scale_kernel(float* __restrict__ x, const float* __restrict__
         x[idx] *= scale[idx / n];
 }
 
-// q = A p ; pq[b] += p.q ; zeroes the accumulators the NEXT kernel will add into
-__global__ void __launch_bounds__(KR_THREADS) kr_apply_kernel(const float* __restrict__ p, const float* __restrict__ dx,
-                                                             float* __restrict__ qv, double* __restrict__ pq,
-                                                             double* __restrict__ rr_next, double* __restrict__ rs_next, int H, int W) {
-    const int b = blockIdx.y;
-    const long long n = (long long)H * W;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { rr_next[b] = 0.0; rs_next[b] = 0.0; }
-    const float q = 1.0f / (dx[b] * dx[b]);
-    const float* pb = p + b * n;
-    double acc = 0.0;
-    for (long long idx = blockIdx.x * (long long)KR_THREADS + threadIdx.x; idx < n; idx += (long long)gridDim.x * KR_THREADS) {
-        const int i = (int)(idx / W), j = (int)(idx - (long long)i * W);
-        const float v = neumann_apply_at(pb, i, j, H, W, q);
-        qv[b * n + idx] = v;
-        acc += (double)pb[idx] * v;
-    }
-    block_atomic_add(acc, pq + b);
+// ---- one CG iteration = TWO kernels, 36 B of fp32 vectors per grid point:
+//   kr_direction_apply:  p_k = (r_k - mean r_k) + beta p_{k-1}   (written to the OTHER p buffer: neighbours still need p_{k-1}),
+//                        x  += alpha_{k-1} p_{k-1}               (the previous iteration's update of x, deferred to here
+//                                                                 because p_{k-1} is being read anyway),
+//                        q   = A p_k  (p_k of the four neighbours is recomputed from their r and p_{k-1}),  pq_k += p_k.q
+//                        reads r p x (+ halo from L1/L2), writes p x q: 24 B
+//   kr_residual:         r  -= alpha_k q ;  rr_{k+1} += r.r ;  rs_{k+1} += sum r        reads r q, writes r: 12 B
+// alpha_k = |r_k - mean|^2 / pq_k and beta = |r_k - mean|^2 / |r_{k-1} - mean|^2 are recomputed by every block from the
+// per-sample double accumulators, which rotate (3 generations of rr / rs, 2 of pq) so that a kernel never zeroes or
+// accumulates into a slot another block of the same kernel reads.  Frozen (converged) samples get alpha = beta = 0.
+// V4: one thread per 4 consecutive points of a row (W % 4 == 0, 16-byte aligned vectors), else one thread per point.
+
+__device__ __forceinline__ double projected_norm2(const double* rr, const double* rs, int b, long long n) {
+    return fmax(rr[b] - rs[b] * rs[b] / (double)n, 0.0);
 }
 
-// alpha = |r - mean r|^2 / p.q (0 once converged) ; x += alpha p ; r -= alpha q ; rr_next += r.r ; rs_next += sum r
-__global__ void __launch_bounds__(KR_THREADS) kr_update_kernel(float* __restrict__ x, float* __restrict__ r,
-                                                              const float* __restrict__ p, const float* __restrict__ qv,
-                                                              const double* __restrict__ rr, const double* __restrict__ rs,
-                                                              const double* __restrict__ pq, const double* __restrict__ bb,
-                                                              double* __restrict__ rr_next, double* __restrict__ rs_next,
-                                                              double tol2, long long n) {
+template <bool V4>
+__global__ void __launch_bounds__(KR_THREADS) kr_direction_apply_kernel(
+        const float* __restrict__ r, const float* __restrict__ p_old, float* __restrict__ p_new, float* __restrict__ x,
+        float* __restrict__ qv, const float* __restrict__ dx, const double* __restrict__ bb,
+        const double* __restrict__ rr_prev, const double* __restrict__ rs_prev, const double* __restrict__ pq_prev,
+        const double* __restrict__ rr_cur, const double* __restrict__ rs_cur, double* __restrict__ pq_cur,
+        double* __restrict__ rr_zero, double* __restrict__ rs_zero, double* __restrict__ history, double tol2,
+        int H, int Wv, int first) {
     const int b = blockIdx.y;
-    const double rrp = fmax(rr[b] - rs[b] * rs[b] / (double)n, 0.0);
-    const bool active = rrp > tol2 * bb[b] && pq[b] > 0.0;
-    const float alpha = active ? (float)(rrp / pq[b]) : 0.f;
+    const unsigned nv = (unsigned)H * (unsigned)Wv;
+    const long long n = (long long)nv * (V4 ? 4 : 1);
+    const double rrp_cur = projected_norm2(rr_cur, rs_cur, b, n);
+    float alpha_prev = 0.f, beta = 0.f;
+    if (!first) {
+        const double rrp_prev = projected_norm2(rr_prev, rs_prev, b, n);
+        const bool active = rrp_prev > tol2 * bb[b];
+        if (active) beta = (float)(rrp_cur / rrp_prev);
+        if (active && pq_prev[b] > 0.0) alpha_prev = (float)(rrp_prev / pq_prev[b]);
+    }
+    const float mean = (float)(rs_cur[b] / (double)n);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        rr_zero[b] = 0.0;
+        rs_zero[b] = 0.0;
+        if (history) history[b] = bb[b] > 0.0 ? sqrt(rrp_cur / bb[b]) : 0.0;
+    }
+    const float q = 1.0f / (dx[b] * dx[b]);
+    const float* rb = r + b * n;
+    const float* pb = p_old + b * n;
+    double acc = 0.0;
+    for (unsigned v = blockIdx.x * KR_THREADS + threadIdx.x; v < nv; v += gridDim.x * KR_THREADS) {
+        const unsigned i = v / (unsigned)Wv, j = v - i * (unsigned)Wv;
+        const bool has_up = i > 0, has_dn = i < (unsigned)H - 1, has_l = j > 0, has_r = j < (unsigned)Wv - 1;
+        const int dv = (int)has_up + (int)has_dn;
+        if constexpr (V4) {
+            const float4* r4 = reinterpret_cast<const float4*>(rb);
+            const float4* p4 = reinterpret_cast<const float4*>(pb);
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 cr = r4[v], cp = p4[v];
+            const float4 ur = has_up ? r4[v - Wv] : z, upo = has_up ? p4[v - Wv] : z;
+            const float4 dr = has_dn ? r4[v + Wv] : z, dpo = has_dn ? p4[v + Wv] : z;
+            float4 c, up = z, dn = z;
+            c.x = fmaf(beta, cp.x, cr.x - mean); c.y = fmaf(beta, cp.y, cr.y - mean);
+            c.z = fmaf(beta, cp.z, cr.z - mean); c.w = fmaf(beta, cp.w, cr.w - mean);
+            if (has_up) {
+                up.x = fmaf(beta, upo.x, ur.x - mean); up.y = fmaf(beta, upo.y, ur.y - mean);
+                up.z = fmaf(beta, upo.z, ur.z - mean); up.w = fmaf(beta, upo.w, ur.w - mean);
+            }
+            if (has_dn) {
+                dn.x = fmaf(beta, dpo.x, dr.x - mean); dn.y = fmaf(beta, dpo.y, dr.y - mean);
+                dn.z = fmaf(beta, dpo.z, dr.z - mean); dn.w = fmaf(beta, dpo.w, dr.w - mean);
+            }
+            const long long e = (long long)v * 4;
+            const float left = has_l ? fmaf(beta, pb[e - 1], rb[e - 1] - mean) : 0.f;
+            const float right = has_r ? fmaf(beta, pb[e + 4], rb[e + 4] - mean) : 0.f;
+            float4 o;      // the scalar operator's order: ((up + down) + left) + right
+            o.x = ((float)(dv + 1 + (int)has_l) * c.x - (((up.x + dn.x) + left) + c.y)) * q;
+            o.y = ((float)(dv + 2) * c.y - (((up.y + dn.y) + c.x) + c.z)) * q;
+            o.z = ((float)(dv + 2) * c.z - (((up.z + dn.z) + c.y) + c.w)) * q;
+            o.w = ((float)(dv + 1 + (int)has_r) * c.w - (((up.w + dn.w) + c.z) + right)) * q;
+            float4* x4 = reinterpret_cast<float4*>(x + b * n);
+            float4 xv = x4[v];
+            xv.x = fmaf(alpha_prev, cp.x, xv.x); xv.y = fmaf(alpha_prev, cp.y, xv.y);
+            xv.z = fmaf(alpha_prev, cp.z, xv.z); xv.w = fmaf(alpha_prev, cp.w, xv.w);
+            x4[v] = xv;
+            reinterpret_cast<float4*>(p_new + b * n)[v] = c;
+            reinterpret_cast<float4*>(qv + b * n)[v] = o;
+            acc += (double)c.x * o.x; acc += (double)c.y * o.y; acc += (double)c.z * o.z; acc += (double)c.w * o.w;
+        } else {
+            const float cp = pb[v];
+            const float c = fmaf(beta, cp, rb[v] - mean);
+            float nb = 0.f;
+            if (has_up) nb += fmaf(beta, pb[v - Wv], rb[v - Wv] - mean);
+            if (has_dn) nb += fmaf(beta, pb[v + Wv], rb[v + Wv] - mean);
+            if (has_l) nb += fmaf(beta, pb[v - 1], rb[v - 1] - mean);
+            if (has_r) nb += fmaf(beta, pb[v + 1], rb[v + 1] - mean);
+            const float o = ((float)(dv + (int)has_l + (int)has_r) * c - nb) * q;
+            x[b * n + v] = fmaf(alpha_prev, cp, x[b * n + v]);
+            p_new[b * n + v] = c;
+            qv[b * n + v] = o;
+            acc += (double)c * o;
+        }
+    }
+    block_atomic_add(acc, pq_cur + b);
+}
+
+template <bool V4>
+__global__ void __launch_bounds__(KR_THREADS) kr_residual_kernel(float* __restrict__ r, const float* __restrict__ qv,
+                                                                const double* __restrict__ rr_cur, const double* __restrict__ rs_cur,
+                                                                const double* __restrict__ pq_cur, const double* __restrict__ bb,
+                                                                double* __restrict__ rr_next, double* __restrict__ rs_next,
+                                                                double* __restrict__ pq_zero, double tol2, long long n) {
+    const int b = blockIdx.y;
+    const double rrp = projected_norm2(rr_cur, rs_cur, b, n);
+    const bool active = rrp > tol2 * bb[b] && pq_cur[b] > 0.0;
+    const float alpha = active ? (float)(rrp / pq_cur[b]) : 0.f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) pq_zero[b] = 0.0;
     double acc = 0.0, accs = 0.0;
-    for (long long idx = blockIdx.x * (long long)KR_THREADS + threadIdx.x; idx < n; idx += (long long)gridDim.x * KR_THREADS) {
-        const long long g = b * n + idx;
-        x[g] = fmaf(alpha, p[g], x[g]);
-        const float rv = fmaf(-alpha, qv[g], r[g]);
-        r[g] = rv;
-        acc += (double)rv * rv;
-        accs += (double)rv;
+    if constexpr (V4) {
+        const unsigned n4 = (unsigned)(n >> 2);
+        float4* r4 = reinterpret_cast<float4*>(r + b * n);
+        const float4* q4 = reinterpret_cast<const float4*>(qv + b * n);
+        for (unsigned v = blockIdx.x * KR_THREADS + threadIdx.x; v < n4; v += gridDim.x * KR_THREADS) {
+            float4 rv = r4[v];
+            const float4 qq = q4[v];
+            rv.x = fmaf(-alpha, qq.x, rv.x); rv.y = fmaf(-alpha, qq.y, rv.y); rv.z = fmaf(-alpha, qq.z, rv.z); rv.w = fmaf(-alpha, qq.w, rv.w);
+            r4[v] = rv;
+            acc += (double)rv.x * rv.x; acc += (double)rv.y * rv.y; acc += (double)rv.z * rv.z; acc += (double)rv.w * rv.w;
+            accs += (double)rv.x; accs += (double)rv.y; accs += (double)rv.z; accs += (double)rv.w;
+        }
+    } else {
+        for (long long idx = blockIdx.x * (long long)KR_THREADS + threadIdx.x; idx < n; idx += (long long)gridDim.x * KR_THREADS) {
+            const float rv = fmaf(-alpha, qv[b * n + idx], r[b * n + idx]);
+            r[b * n + idx] = rv;
+            acc += (double)rv * rv;
+            accs += (double)rv;
+        }
     }
     block_atomic_add(acc, rr_next + b);
     block_atomic_add(accs, rs_next + b);
 }
 
-// beta = |r_next|^2 / |r|^2 (projected norms; 0 once converged and for the very first direction) ; p = (r - mean r) + beta p ;
-// records the relative residual ; zeroes pq for the next iteration
-__global__ void __launch_bounds__(KR_THREADS) kr_direction_kernel(float* __restrict__ p, const float* __restrict__ r,
-                                                                 const double* __restrict__ rr, const double* __restrict__ rs,
-                                                                 const double* __restrict__ rr_next, const double* __restrict__ rs_next,
-                                                                 const double* __restrict__ bb, double* __restrict__ pq,
-                                                                 double* __restrict__ history, double tol2, long long n, int first) {
+// after the last iteration: the deferred x += alpha_last p_last, and the last row of the residual history
+__global__ void __launch_bounds__(KR_THREADS) kr_final_kernel(float* __restrict__ x, const float* __restrict__ p_last,
+                                                             const double* __restrict__ rr_last, const double* __restrict__ rs_last,
+                                                             const double* __restrict__ pq_last, const double* __restrict__ rr_end,
+                                                             const double* __restrict__ rs_end, const double* __restrict__ bb,
+                                                             double* __restrict__ history, double tol2, long long n) {
     const int b = blockIdx.y;
-    const double rrp = fmax(rr[b] - rs[b] * rs[b] / (double)n, 0.0);
-    const double rrp_next = fmax(rr_next[b] - rs_next[b] * rs_next[b] / (double)n, 0.0);
-    const bool active = !first && rrp > tol2 * bb[b];
-    const float beta = active ? (float)(rrp_next / rrp) : 0.f;
-    const float mean = (float)(rs_next[b] / (double)n);
-    for (long long idx = blockIdx.x * (long long)KR_THREADS + threadIdx.x; idx < n; idx += (long long)gridDim.x * KR_THREADS) {
-        const long long g = b * n + idx;
-        p[g] = fmaf(beta, p[g], r[g] - mean);
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        if (history) history[b] = bb[b] > 0.0 ? sqrt(rrp_next / bb[b]) : 0.0;
-        pq[b] = 0.0;      // no block of this kernel reads pq (kr_update did); the next kr_apply accumulates into it
-    }
-}
-
-// ---- float4 variants of the three per-iteration kernels (W % 4 == 0, 16-byte aligned vectors): one 16-byte access per
-// vector and thread instead of four 4-byte ones, one 32-bit division per 4 points instead of a 64-bit one per point.
-// The arithmetic per point follows the scalar kernels (same order of the neighbour sum).
-
-// 4 points (i, 4*j4 .. 4*j4+3) of A v.  v4: the sample's map as float4 rows of W4 = W/4
-__device__ __forceinline__ float4 neumann_apply_vec4(const float4* __restrict__ v4, const float* __restrict__ v, int i, int j4, int H, int W4,
-                                                     float q, float4& centre) {
-    const long long row = (long long)i * W4;
-    const float4 c = v4[row + j4];
-    centre = c;
-    const bool has_up = i > 0, has_dn = i < H - 1, has_l = j4 > 0, has_r = j4 < W4 - 1;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 up = has_up ? v4[row - W4 + j4] : z;
-    const float4 dn = has_dn ? v4[row + W4 + j4] : z;
-    const float left = has_l ? v[(row + j4) * 4 - 1] : 0.f;
-    const float right = has_r ? v[(row + j4) * 4 + 4] : 0.f;
-    const int dv = (int)has_up + (int)has_dn;
-    float4 o;
-    // scalar order: ((up + down) + left) + right, skipping the neighbours that do not exist (adding 0.f changes nothing)
-    o.x = ((float)(dv + 1 + (int)has_l) * c.x - (((up.x + dn.x) + left) + c.y)) * q;
-    o.y = ((float)(dv + 2) * c.y - (((up.y + dn.y) + c.x) + c.z)) * q;
-    o.z = ((float)(dv + 2) * c.z - (((up.z + dn.z) + c.y) + c.w)) * q;
-    o.w = ((float)(dv + 1 + (int)has_r) * c.w - (((up.w + dn.w) + c.z) + right)) * q;
-    return o;
-}
-
-__global__ void __launch_bounds__(KR_THREADS) kr_apply_vec4_kernel(const float* __restrict__ p, const float* __restrict__ dx,
-                                                                  float* __restrict__ qv, double* __restrict__ pq,
-                                                                  double* __restrict__ rr_next, double* __restrict__ rs_next, int H, int W4) {
-    const int b = blockIdx.y;
-    const unsigned n4 = (unsigned)H * (unsigned)W4;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { rr_next[b] = 0.0; rs_next[b] = 0.0; }
-    const float q = 1.0f / (dx[b] * dx[b]);
-    const float* pb = p + (long long)b * n4 * 4;
-    const float4* pb4 = reinterpret_cast<const float4*>(pb);
-    float4* qb4 = reinterpret_cast<float4*>(qv + (long long)b * n4 * 4);
-    double acc = 0.0;
-    for (unsigned v = blockIdx.x * KR_THREADS + threadIdx.x; v < n4; v += gridDim.x * KR_THREADS) {
-        const unsigned i = v / (unsigned)W4, j4 = v - i * (unsigned)W4;
-        float4 c;
-        const float4 o = neumann_apply_vec4(pb4, pb, (int)i, (int)j4, H, W4, q, c);
-        qb4[v] = o;
-        acc += (double)c.x * o.x;
-        acc += (double)c.y * o.y;
-        acc += (double)c.z * o.z;
-        acc += (double)c.w * o.w;
-    }
-    block_atomic_add(acc, pq + b);
-}
-
-__global__ void __launch_bounds__(KR_THREADS) kr_update_vec4_kernel(float* __restrict__ x, float* __restrict__ r,
-                                                                   const float* __restrict__ p, const float* __restrict__ qv,
-                                                                   const double* __restrict__ rr, const double* __restrict__ rs,
-                                                                   const double* __restrict__ pq, const double* __restrict__ bb,
-                                                                   double* __restrict__ rr_next, double* __restrict__ rs_next,
-                                                                   double tol2, long long n) {
-    const int b = blockIdx.y;
-    const double rrp = fmax(rr[b] - rs[b] * rs[b] / (double)n, 0.0);
-    const bool active = rrp > tol2 * bb[b] && pq[b] > 0.0;
-    const float alpha = active ? (float)(rrp / pq[b]) : 0.f;
-    const unsigned n4 = (unsigned)(n >> 2);
-    float4* x4 = reinterpret_cast<float4*>(x + b * n);
-    float4* r4 = reinterpret_cast<float4*>(r + b * n);
-    const float4* p4 = reinterpret_cast<const float4*>(p + b * n);
-    const float4* q4 = reinterpret_cast<const float4*>(qv + b * n);
-    double acc = 0.0, accs = 0.0;
-    for (unsigned v = blockIdx.x * KR_THREADS + threadIdx.x; v < n4; v += gridDim.x * KR_THREADS) {
-        float4 xv = x4[v], rv = r4[v];
-        const float4 pv = p4[v], qq = q4[v];
-        xv.x = fmaf(alpha, pv.x, xv.x); xv.y = fmaf(alpha, pv.y, xv.y); xv.z = fmaf(alpha, pv.z, xv.z); xv.w = fmaf(alpha, pv.w, xv.w);
-        rv.x = fmaf(-alpha, qq.x, rv.x); rv.y = fmaf(-alpha, qq.y, rv.y); rv.z = fmaf(-alpha, qq.z, rv.z); rv.w = fmaf(-alpha, qq.w, rv.w);
-        x4[v] = xv;
-        r4[v] = rv;
-        acc += (double)rv.x * rv.x; acc += (double)rv.y * rv.y; acc += (double)rv.z * rv.z; acc += (double)rv.w * rv.w;
-        accs += (double)rv.x; accs += (double)rv.y; accs += (double)rv.z; accs += (double)rv.w;
-    }
-    block_atomic_add(acc, rr_next + b);
-    block_atomic_add(accs, rs_next + b);
-}
-
-__global__ void __launch_bounds__(KR_THREADS) kr_direction_vec4_kernel(float* __restrict__ p, const float* __restrict__ r,
-                                                                      const double* __restrict__ rr, const double* __restrict__ rs,
-                                                                      const double* __restrict__ rr_next, const double* __restrict__ rs_next,
-                                                                      const double* __restrict__ bb, double* __restrict__ pq,
-                                                                      double* __restrict__ history, double tol2, long long n, int first) {
-    const int b = blockIdx.y;
-    const double rrp = fmax(rr[b] - rs[b] * rs[b] / (double)n, 0.0);
-    const double rrp_next = fmax(rr_next[b] - rs_next[b] * rs_next[b] / (double)n, 0.0);
-    const bool active = !first && rrp > tol2 * bb[b];
-    const float beta = active ? (float)(rrp_next / rrp) : 0.f;
-    const float mean = (float)(rs_next[b] / (double)n);
-    const unsigned n4 = (unsigned)(n >> 2);
-    float4* p4 = reinterpret_cast<float4*>(p + b * n);
-    const float4* r4 = reinterpret_cast<const float4*>(r + b * n);
-    for (unsigned v = blockIdx.x * KR_THREADS + threadIdx.x; v < n4; v += gridDim.x * KR_THREADS) {
-        float4 pv = p4[v];
-        const float4 rv = r4[v];
-        pv.x = fmaf(beta, pv.x, rv.x - mean); pv.y = fmaf(beta, pv.y, rv.y - mean);
-        pv.z = fmaf(beta, pv.z, rv.z - mean); pv.w = fmaf(beta, pv.w, rv.w - mean);
-        p4[v] = pv;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        if (history) history[b] = bb[b] > 0.0 ? sqrt(rrp_next / bb[b]) : 0.0;
-        pq[b] = 0.0;
-    }
+    const double rrp = projected_norm2(rr_last, rs_last, b, n);
+    const bool active = rrp > tol2 * bb[b] && pq_last[b] > 0.0;
+    const float alpha = active ? (float)(rrp / pq_last[b]) : 0.f;
+    if (history && blockIdx.x == 0 && threadIdx.x == 0)
+        history[b] = bb[b] > 0.0 ? sqrt(projected_norm2(rr_end, rs_end, b, n) / bb[b]) : 0.0;
+    for (long long idx = blockIdx.x * (long long)KR_THREADS + threadIdx.x; idx < n; idx += (long long)gridDim.x * KR_THREADS)
+        x[b * n + idx] = fmaf(alpha, p_last[b * n + idx], x[b * n + idx]);
 }
 
 // out = A v (the operator alone: tests, residual checks)
@@ -288,8 +268,8 @@ using namespace pcnn;
 
 extern "C" size_t pcnn_neumann_cg_workspace_bytes(int B, int H, int W) {
     if (B <= 0 || H < 2 || W < 2) return 0;
-    // r, p, q (float, B*H*W each) + 6 double accumulators per sample
-    return (size_t)3 * B * H * W * sizeof(float) + (size_t)8 * B * sizeof(double);
+    // r, two p buffers, q (float, B*H*W each) + 12 double accumulators per sample
+    return (size_t)4 * B * H * W * sizeof(float) + (size_t)12 * B * sizeof(double);
 }
 
 extern "C" int pcnn_neumann_laplacian_apply_f32(const float* v, const float* dx, float* out, int B, int H, int W, void* stream) {
@@ -301,56 +281,65 @@ extern "C" int pcnn_neumann_laplacian_apply_f32(const float* v, const float* dx,
     return PCNN_OK;
 }
 
+template <bool V4>
+static int cg_iterations(float* x, float* r, float* pbuf0, float* pbuf1, float* q, const float* dx, const double* bb, double* const* rr,
+                         double* const* rs, double* const* pq, int B, int H, int W, int max_iter, double tol2, double* residual_history,
+                         dim3 grid, cudaStream_t st) {
+    const long long n = (long long)H * W;
+    float* pbuf[2] = {pbuf0, pbuf1};
+    for (int k = 0; k < max_iter; ++k) {
+        const int c3 = k % 3, p3 = (k + 2) % 3, n3 = (k + 1) % 3, c2 = k & 1, o2 = (k + 1) & 1;
+        kr_direction_apply_kernel<V4><<<grid, KR_THREADS, 0, st>>>(r, pbuf[c2], pbuf[o2], x, q, dx, bb, rr[p3], rs[p3], pq[o2], rr[c3], rs[c3], pq[c2],
+                                                                   rr[n3], rs[n3], (residual_history && k > 0) ? residual_history + (size_t)(k - 1) * B : nullptr,
+                                                                   tol2, H, V4 ? W / 4 : W, k == 0);
+        PCNN_CHECK_LAUNCH();
+        kr_residual_kernel<V4><<<grid, KR_THREADS, 0, st>>>(r, q, rr[c3], rs[c3], pq[c2], bb, rr[n3], rs[n3], pq[o2], tol2, n);
+        PCNN_CHECK_LAUNCH();
+    }
+    if (max_iter > 0) {
+        const int k = max_iter - 1;
+        kr_final_kernel<<<grid, KR_THREADS, 0, st>>>(x, pbuf[(k + 1) & 1], rr[k % 3], rs[k % 3], pq[k & 1], rr[(k + 1) % 3], rs[(k + 1) % 3], bb,
+                                                     residual_history ? residual_history + (size_t)k * B : nullptr, tol2, n);
+        PCNN_CHECK_LAUNCH();
+    }
+    return PCNN_OK;
+}
+
 extern "C" int pcnn_neumann_cg_solve(const float* rhs, const float* dx, const float* guess_scale, float* x, int B, int H, int W,
                                      int max_iter, double rel_tol, double* residual_history, void* workspace, void* stream) {
     PCNN_CHECK_ARG(rhs && dx && x && workspace, "neumann_cg_solve: null pointer");
     PCNN_CHECK_ARG(B > 0 && B <= 65535 && H >= 2 && W >= 2 && max_iter >= 0 && rel_tol >= 0.0, "neumann_cg_solve: bad argument");
+    PCNN_CHECK_ARG((long long)H * W < (1ll << 31), "neumann_cg_solve: at most 2^31 - 1 points per sample");
     cudaStream_t st = (cudaStream_t)stream;
     const long long n = (long long)H * W, total = n * B;
     float* r = reinterpret_cast<float*>(workspace);
-    float* p = r + total;
-    float* q = p + total;
-    double* acc = reinterpret_cast<double*>(q + total);      // [rhs_sum | bb | pq | rr0 | rr1 | xsum | rs0 | rs1] x B
+    float* p0 = r + total;
+    float* p1 = p0 + total;
+    float* q = p1 + total;
+    double* acc = reinterpret_cast<double*>(q + total);      // [rhs_sum | bb | xsum | pq x 2 | rr x 3 | rs x 3] x B
     PCNN_CHECK_ARG(((uintptr_t)acc & 7) == 0, "neumann_cg_solve: workspace must be 8-byte aligned");
-    double *rhs_sum = acc, *bb = acc + B, *pq = acc + 2 * B, *rr0 = acc + 3 * B, *rr1 = acc + 4 * B, *xsum = acc + 5 * B;
-    double *rs0 = acc + 6 * B, *rs1 = acc + 7 * B;
-    PCNN_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 8 * B, st));
+    double *rhs_sum = acc, *bb = acc + B, *xsum = acc + 2 * B;
+    double* pq[2] = {acc + 3 * B, acc + 4 * B};
+    double* rr[3] = {acc + 5 * B, acc + 6 * B, acc + 7 * B};
+    double* rs[3] = {acc + 8 * B, acc + 9 * B, acc + 10 * B};
+    PCNN_CHECK_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 12 * B, st));
     const int gx = (int)std::min<long long>((n + KR_THREADS * 4 - 1) / (KR_THREADS * 4), 1024);
     const dim3 grid(gx, B);
     const double tol2 = rel_tol * rel_tol;
-    // float4 kernels when every row is a whole number of 16-byte vectors (r, p, q start n*B floats apart: aligned with x and the workspace)
-    const bool vec4 = (W % 4 == 0) && (((uintptr_t)x | (uintptr_t)workspace) & 15) == 0 && n / 4 < (1ll << 31);
     kr_sum_kernel<<<grid, KR_THREADS, 0, st>>>(rhs, rhs_sum, n);
     PCNN_CHECK_LAUNCH();
-    kr_init_kernel<<<grid, KR_THREADS, 0, st>>>(rhs, dx, guess_scale, x, r, p, rhs_sum, rr0, rs0, bb, H, W);
+    kr_init_kernel<<<grid, KR_THREADS, 0, st>>>(rhs, dx, guess_scale, x, r, p0, rhs_sum, rr[0], rs[0], bb, H, W);     // p_{-1} = 0
     PCNN_CHECK_LAUNCH();
     if (guess_scale) {
         const int gs = (int)std::min<long long>((total + 255) / 256, 148 * 16);
         kr_scale_kernel<<<gs, 256, 0, st>>>(x, guess_scale, n, total);
         PCNN_CHECK_LAUNCH();
     }
-    kr_direction_kernel<<<grid, KR_THREADS, 0, st>>>(p, r, rr0, rs0, rr0, rs0, bb, pq, nullptr, tol2, n, 1);     // p = r - mean(r)
-    PCNN_CHECK_LAUNCH();
-    for (int it = 0; it < max_iter; ++it) {
-        double *rr = (it & 1) ? rr1 : rr0, *rs = (it & 1) ? rs1 : rs0;
-        double *rr_next = (it & 1) ? rr0 : rr1, *rs_next = (it & 1) ? rs0 : rs1;
-        double* hist = residual_history ? residual_history + (size_t)it * B : nullptr;
-        if (vec4) {
-            kr_apply_vec4_kernel<<<grid, KR_THREADS, 0, st>>>(p, dx, q, pq, rr_next, rs_next, H, W / 4);
-            PCNN_CHECK_LAUNCH();
-            kr_update_vec4_kernel<<<grid, KR_THREADS, 0, st>>>(x, r, p, q, rr, rs, pq, bb, rr_next, rs_next, tol2, n);
-            PCNN_CHECK_LAUNCH();
-            kr_direction_vec4_kernel<<<grid, KR_THREADS, 0, st>>>(p, r, rr, rs, rr_next, rs_next, bb, pq, hist, tol2, n, 0);
-            PCNN_CHECK_LAUNCH();
-            continue;
-        }
-        kr_apply_kernel<<<grid, KR_THREADS, 0, st>>>(p, dx, q, pq, rr_next, rs_next, H, W);
-        PCNN_CHECK_LAUNCH();
-        kr_update_kernel<<<grid, KR_THREADS, 0, st>>>(x, r, p, q, rr, rs, pq, bb, rr_next, rs_next, tol2, n);
-        PCNN_CHECK_LAUNCH();
-        kr_direction_kernel<<<grid, KR_THREADS, 0, st>>>(p, r, rr, rs, rr_next, rs_next, bb, pq, hist, tol2, n, 0);
-        PCNN_CHECK_LAUNCH();
-    }
+    // float4 kernels when every row is a whole number of 16-byte vectors (r, p, q start n*B floats apart: aligned with x and the workspace)
+    const bool vec4 = (W % 4 == 0) && (((uintptr_t)x | (uintptr_t)workspace) & 15) == 0;
+    const int rc = vec4 ? cg_iterations<true>(x, r, p0, p1, q, dx, bb, rr, rs, pq, B, H, W, max_iter, tol2, residual_history, grid, st)
+                        : cg_iterations<false>(x, r, p0, p1, q, dx, bb, rr, rs, pq, B, H, W, max_iter, tol2, residual_history, grid, st);
+    if (rc != PCNN_OK) return rc;
     kr_sum_kernel<<<grid, KR_THREADS, 0, st>>>(x, xsum, n);
     PCNN_CHECK_LAUNCH();
     const int gs = (int)std::min<long long>((total + 255) / 256, 148 * 16);
