@@ -307,6 +307,34 @@ def hbm_kernel_rooflines(h, B2048=16, iters=10):
     return res, dst
 
 
+def pressure_cg_roofline(h, shapes=((64, 256), (16, 2048)), iters=100):
+    """The caller after the path: one conjugate-gradient iteration of the pressure-projection solve
+    (csrc/krylov.cu: two kernels, 36 B of fp32 vectors per grid point) by CUDA events; the difference of two solves with
+    different iteration counts removes the fixed cost of a solve."""
+    from poisson_cnn_b200.solvers import pressure_poisson_solve
+    dev, peak = h.device, h.peaks["hbm_gbs"]
+    out = {"bytes_per_pt_per_iteration": 36, "kernels_per_iteration": 2, "peak_gbs": peak}
+    for B, n in shapes:
+        g = torch.Generator(device=dev).manual_seed(3)
+        rhs = torch.randn((B, 1, n, n), device=dev, generator=g)
+        dx = torch.full((B, 1), 1.0 / (n - 1), device=dev)
+        pressure_poisson_solve(rhs, dx, max_iter=4, rel_tol=0.0)
+        ts = []
+        for k in (4, 4 + iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            pressure_poisson_solve(rhs, dx, max_iter=k, rel_tol=0.0)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = (ts[1] - ts[0]) / iters
+        gbs = 36.0 * B * n * n / ms / 1e6
+        out["%dx%dx%d" % (B, n, n)] = {"ms_per_iteration": ms, "gbs": gbs, "frac_of_hbm_peak": gbs / peak}
+        del rhs
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def run_config2(args):
     from poisson_cnn_b200 import ops, _lib
@@ -385,7 +413,7 @@ def run_config2(args):
                     "note": "achieved/frac count ALGORITHMIC conv FLOPs once; the kernel issues (k+3)/k x that in MMAs (row-group zero padding), 2x in tc2 (e4m3 correction pass), 3x in tc3"}
 
     # ---------------- accuracy + residual of what was timed (outside the timed region) ----------------
-    acc = cpu_baseline = residual = dst = None
+    acc = cpu_baseline = residual = dst = pressure_cg = None
     if rank == 0:
         from oracle import poisson_oracle as O
         from poisson_cnn_b200.losses import linear_operator_loss
@@ -409,6 +437,7 @@ def run_config2(args):
         ops.blk8_pool_clear()
         torch.cuda.empty_cache()
         residual, dst = hbm_kernel_rooflines(h)
+        pressure_cg = pressure_cg_roofline(h)
 
     # ---------------- the other precision modes, briefly (N=1 only; informational) ----------------
     other = {}
@@ -454,6 +483,7 @@ def run_config2(args):
         "accuracy": acc,
         "residual": residual,
         "dst": dst,
+        "pressure_cg": pressure_cg,
         "other_modes": other,
         "model_tflops": value / world * pcnn_flops(nx, ny) / 1e12,
         "frac_of_bf16_sustained_peak": value / world * pcnn_flops(nx, ny) / 1e12 / peaks["tflops"],
