@@ -14,7 +14,8 @@ build/%.o: poisson_cnn_b200/csrc/%.cu poisson_cnn_b200/csrc/pcnn_common.cuh incl
 	@mkdir -p build
 	$(NVCC) $(NVCCFLAGS) -Xptxas -v -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
 
-build/engine.o: poisson_cnn_b200/csrc/engine_json.h
+build/engine.o: poisson_cnn_b200/csrc/engine_json.h poisson_cnn_b200/csrc/smallmap_stack.h
+build/smallmap_stack.o: poisson_cnn_b200/csrc/smallmap_stack.h
 
 $(LIB): $(OBJ)
 	$(NVCC) -shared $(ARCH) -o $@ $(OBJ) -lcudart

@@ -23,6 +23,7 @@
 #include <cuda_fp16.h>
 
 #include "engine_json.h"
+#include "smallmap_stack.h"
 #include "pcnn_common.cuh"
 
 namespace pcnn {
@@ -1010,12 +1011,18 @@ static int check_branch_shapes(const HpnnCfg& h, int H, int W) {
 }
 
 // pool -> conv -> resnets of one branch in FP32 (blocks/bottleneck_block.py:36-50); consumes nothing (pooled stays alive)
+static int branch_stack_layers(Ctx& c, const BlockCfg& b, std::vector<std::string>* rns, StackLayers* L) {
+    const std::string name = "hpnn/" + b.name;
+    rns->clear();
+    for (int r = 1; r < b.n_convs; ++r) rns->push_back(name + "/resnet" + std::to_string(r));
+    return stack_layers(*c.m, name + "/conv0", *rns, 2, nullptr, b.use_bn, L);
+}
+
 static int branch_lowres_f32(Ctx& c, const BlockCfg& b, const F32& pooled, int Bcap, F32* out) {
     const std::string name = "hpnn/" + b.name;
     std::vector<std::string> rns;
-    for (int r = 1; r < b.n_convs; ++r) rns.push_back(name + "/resnet" + std::to_string(r));
     StackLayers L;
-    TRY(stack_layers(*c.m, name + "/conv0", rns, 2, nullptr, b.use_bn, &L));
+    TRY(branch_stack_layers(c, b, &rns, &L));
     if (smallmap_supported(pooled.H, pooled.W, L) && pooled.bs == (long long)pooled.C * pooled.H * pooled.W) {
         F32 y = c.f32(Bcap, pooled.B, L.cout.back(), pooled.H, pooled.W);
         RUN(c, pcnn_smallmap_stack_f32(pooled.p, y.p, pooled.B, pooled.H, pooled.W, pooled.C, L.n(), L.kernels.data(), L.biases.data(),
@@ -1283,12 +1290,38 @@ static int hpnn_tc(Ctx& c, const float* rhs, const float* dx, float* out, int B,
     }
     struct Branch { const BlockCfg* cfg; bool is_b8; B8 b8; F32 f32; };
     std::vector<Branch> br;
+    // tensor cores for every branch whose pooled map is at least 16 pixels a side (Python: _branch_on_tc)
+    auto branch_on_tc = [&](const BlockCfg& b) {
+        return std::min(cdiv(H, b.ds), cdiv(W, b.ds)) >= 16 && tc_kernel_ok(b.ksize, b.pad_value) && b.pad <= PCNN_PAD_SYMMETRIC;
+    };
+    // The small-map branches (pooled maps of at most 64 pixels: the FP32 stack kernel, one CTA per sample, ~0.35 ms of latency
+    // each) all go into ONE launch, side by side: 3 branches at 256 x 256, 5 at 64 x 64.  Same arithmetic as one launch per
+    // branch (the op-by-op Python program), so the results stay bit-identical.
+    std::map<const BlockCfg*, F32> small_out;
+    {
+        std::vector<StackLayers> progs;
+        std::vector<sms::StackDesc> descs;
+        progs.reserve(h.blocks.size());
+        std::vector<std::string> rns;
+        for (const BlockCfg& b : h.blocks) {
+            if (branch_on_tc(b) || (int)descs.size() == sms::MAX_PROGRAMS) continue;
+            const F32& pooled = pools[b.ds];
+            StackLayers L;
+            TRY(branch_stack_layers(c, b, &rns, &L));
+            if (!smallmap_supported(pooled.H, pooled.W, L) || pooled.bs != (long long)pooled.C * pooled.H * pooled.W) continue;
+            progs.push_back(L);
+            const StackLayers& S = progs.back();
+            F32 y = c.f32(Bcap, pooled.B, S.cout.back(), pooled.H, pooled.W);
+            descs.push_back(sms::StackDesc{pooled.p, y.p, pooled.H, pooled.W, pooled.C, S.n(), S.kernels.data(), S.biases.data(), S.bn_scale.data(),
+                                           S.bn_shift.data(), S.ksize.data(), S.cin.data(), S.cout.data(), S.flags.data(), b.act, b.pad, b.pad_value});
+            small_out[&b] = y;
+        }
+        if (!descs.empty()) RUN(c, sms::smallmap_stack_multi(descs.data(), (int)descs.size(), B, c.st));
+    }
     for (const BlockCfg& b : h.blocks) {
-        const int ph = cdiv(H, b.ds), pw = cdiv(W, b.ds);
         const std::string name = "hpnn/" + b.name;
         Branch r{&b, false, B8(), F32()};
-        // tensor cores for every branch whose pooled map is at least 16 pixels a side (Python: _branch_on_tc)
-        if (std::min(ph, pw) >= 16 && tc_kernel_ok(b.ksize, b.pad_value) && b.pad <= PCNN_PAD_SYMMETRIC) {
+        if (branch_on_tc(b)) {
             B8 hb;
             TRY(to_blk8(c, pools[b.ds], Bcap, bsplit, b.pad, nullptr, 0, &hb));
             TcArgs a; a.act = b.act; a.pad = b.pad; a.next_pad = b.pad;
@@ -1304,7 +1337,9 @@ static int hpnn_tc(Ctx& c, const float* rhs, const float* dx, float* out, int B,
             if (um_tc && b.deconv) { r.is_b8 = true; r.b8 = hb; }
             else { TRY(from_blk8(c, hb, hb.C, Bcap, nullptr, &r.f32)); c.free(hb); }      // resize branches read NCHW fp32
         } else {
-            TRY(branch_lowres_f32(c, b, pools[b.ds], Bcap, &r.f32));
+            auto done = small_out.find(&b);
+            if (done != small_out.end()) r.f32 = done->second;
+            else TRY(branch_lowres_f32(c, b, pools[b.ds], Bcap, &r.f32));
             if (um_tc && b.deconv) {      // tiny map (< 16 pixels a side) computed by the FP32 stack kernel
                 TRY(to_blk8(c, r.f32, Bcap, 1, PCNN_PAD_CONSTANT, nullptr, 0, &r.b8));
                 c.free(r.f32);

@@ -7,8 +7,10 @@
 //   per (input channel, tap) one LDS.128 of weights and four broadcast input reads feed 16 FMAs (the first version,
 //   1 channel x 8 pixels per thread, was bound by the load/store unit: 9 shared-memory reads per 8 FMAs).
 #include <algorithm>
+#include <cstring>
 
 #include "pcnn_common.cuh"
+#include "smallmap_stack.h"
 
 namespace pcnn {
 namespace sms {
@@ -39,7 +41,11 @@ struct Params {
     float pad_value;
 };
 
-__global__ void __launch_bounds__(NTHR) smallmap_stack_kernel(const Params p) {
+struct MultiParams { Params prog[MAX_PROGRAMS]; };
+
+// grid (B, programs): blockIdx.y selects the layer program (a bottleneck branch), blockIdx.x the sample
+__global__ void __launch_bounds__(NTHR) smallmap_stack_kernel(const __grid_constant__ MultiParams mp) {
+    const Params& p = mp.prog[blockIdx.y];
     extern __shared__ __align__(16) float sm[];
     const int H = p.H, W = p.W, pm = p.padmax, Wp = W + 2 * pm, Hp = H + 2 * pm, plane = p.plane;
     float* buf[3] = {sm, sm + CMAX * plane, sm + 2 * CMAX * plane};
@@ -164,41 +170,63 @@ __global__ void __launch_bounds__(NTHR) smallmap_stack_kernel(const Params p) {
 using namespace pcnn;
 using namespace pcnn::sms;
 
+static int build_program(const StackDesc& d, Params* out, size_t* smem) {
+    const int H = d.H, W = d.W, n_layers = d.n_layers;
+    PCNN_CHECK_ARG(d.in && d.out && d.kernels && d.ksize && d.cin && d.cout && d.flags && H > 0 && W > 0, "smallmap_stack_f32: bad argument");
+    PCNN_CHECK_ARG(H * W <= MAXPIX, "smallmap_stack_f32: maps of at most %d pixels (got %dx%d)", MAXPIX, H, W);
+    PCNN_CHECK_ARG(n_layers >= 1 && n_layers <= MAXL, "smallmap_stack_f32: between 1 and %d layers", MAXL);
+    PCNN_CHECK_ARG(d.pad_mode >= PCNN_PAD_CONSTANT && d.pad_mode <= PCNN_PAD_REFLECT, "smallmap_stack_f32: bad pad_mode %d", d.pad_mode);
+    PCNN_CHECK_ARG(d.Cin0 >= 1 && d.Cin0 <= CMAX && d.cin[0] == d.Cin0, "smallmap_stack_f32: first layer expects %d input channels", d.Cin0);
+    Params& p = *out;
+    p.in = d.in; p.out = d.out; p.n_layers = n_layers; p.H = H; p.W = W; p.act = d.act; p.pad_mode = d.pad_mode; p.pad_value = d.pad_value;
+    p.cin0 = d.Cin0;
+    size_t wmax = 0;
+    int depth = 0, padmax = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        const int k = d.ksize[l];
+        PCNN_CHECK_ARG(d.kernels[l] && (k & 1) && k >= 1 && k <= 7, "smallmap_stack_f32: layer %d: odd kernel size <= 7", l);
+        PCNN_CHECK_ARG(d.cin[l] >= 1 && d.cin[l] <= CMAX && d.cout[l] >= 1 && d.cout[l] <= CMAX, "smallmap_stack_f32: layer %d: channels must be <= %d", l, CMAX);
+        PCNN_CHECK_ARG(l == 0 || d.cin[l] == d.cout[l - 1], "smallmap_stack_f32: layer %d: input channels do not chain", l);
+        PCNN_CHECK_ARG((d.bn_scale && d.bn_scale[l]) ? (d.bn_shift && d.bn_shift[l]) : !(d.bn_shift && d.bn_shift[l]), "smallmap_stack_f32: bn_scale/bn_shift must come together");
+        if (d.flags[l] & 1) { PCNN_CHECK_ARG(depth == 0, "smallmap_stack_f32: nested saves are not supported"); depth = 1; }
+        if (d.flags[l] & 2) { PCNN_CHECK_ARG(depth == 1 || (d.flags[l] & 1), "smallmap_stack_f32: layer %d adds a tensor nobody saved", l); depth = 0; }
+        if (d.pad_mode == PCNN_PAD_SYMMETRIC) PCNN_CHECK_ARG(k / 2 <= std::min(H, W), "smallmap_stack_f32: SYMMETRIC pad larger than the map");
+        if (d.pad_mode == PCNN_PAD_REFLECT) PCNN_CHECK_ARG(k / 2 < std::min(H, W), "smallmap_stack_f32: REFLECT pad too large for the map");
+        p.kernel[l] = d.kernels[l]; p.bias[l] = d.biases ? d.biases[l] : nullptr;
+        p.bn_scale[l] = d.bn_scale ? d.bn_scale[l] : nullptr; p.bn_shift[l] = d.bn_shift ? d.bn_shift[l] : nullptr;
+        p.k[l] = k; p.cin[l] = d.cin[l]; p.cout[l] = d.cout[l]; p.flags[l] = d.flags[l];
+        wmax = std::max(wmax, (size_t)k * k * d.cin[l] * 32);
+        padmax = std::max(padmax, k / 2);
+    }
+    p.padmax = padmax;
+    p.plane = (H + 2 * padmax) * (W + 2 * padmax);
+    *smem = ((size_t)3 * CMAX * p.plane + wmax) * sizeof(float);
+    PCNN_CHECK_ARG(*smem <= 220 * 1024, "smallmap_stack_f32: layer program does not fit in shared memory (%zu B)", *smem);
+    return PCNN_OK;
+}
+
+int pcnn::sms::smallmap_stack_multi(const StackDesc* descs, int n, int B, cudaStream_t stream) {
+    PCNN_CHECK_ARG(descs && n >= 1 && n <= MAX_PROGRAMS && B > 0, "smallmap_stack_f32: between 1 and %d programs per launch", MAX_PROGRAMS);
+    MultiParams mp;
+    memset(&mp, 0, sizeof(mp));
+    size_t smem = 0;
+    for (int i = 0; i < n; ++i) {
+        size_t s = 0;
+        const int rc = build_program(descs[i], &mp.prog[i], &s);
+        if (rc != PCNN_OK) return rc;
+        smem = std::max(smem, s);
+    }
+    PCNN_CHECK_CUDA(cudaFuncSetAttribute(smallmap_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smallmap_stack_kernel<<<dim3(B, n), NTHR, smem, stream>>>(mp);
+    PCNN_CHECK_LAUNCH();
+    return PCNN_OK;
+}
+
 extern "C" int pcnn_smallmap_stack_f32(const float* in, float* out, int B, int H, int W, int Cin0, int n_layers,
                                        const float* const* kernels, const float* const* biases,
                                        const float* const* bn_scale, const float* const* bn_shift, const int* ksize,
                                        const int* cin, const int* cout, const int* flags, int act, int pad_mode,
                                        float pad_value, void* stream) {
-    PCNN_CHECK_ARG(in && out && kernels && ksize && cin && cout && flags && B > 0 && H > 0 && W > 0, "smallmap_stack_f32: bad argument");
-    PCNN_CHECK_ARG(H * W <= MAXPIX, "smallmap_stack_f32: maps of at most %d pixels (got %dx%d)", MAXPIX, H, W);
-    PCNN_CHECK_ARG(n_layers >= 1 && n_layers <= MAXL, "smallmap_stack_f32: between 1 and %d layers", MAXL);
-    PCNN_CHECK_ARG(pad_mode >= PCNN_PAD_CONSTANT && pad_mode <= PCNN_PAD_REFLECT, "smallmap_stack_f32: bad pad_mode %d", pad_mode);
-    PCNN_CHECK_ARG(Cin0 >= 1 && Cin0 <= CMAX && cin[0] == Cin0, "smallmap_stack_f32: first layer expects %d input channels", Cin0);
-    Params p;
-    p.in = in; p.out = out; p.n_layers = n_layers; p.H = H; p.W = W; p.act = act; p.pad_mode = pad_mode; p.pad_value = pad_value; p.cin0 = Cin0;
-    size_t wmax = 0;
-    int depth = 0, padmax = 0;
-    for (int l = 0; l < n_layers; ++l) {
-        PCNN_CHECK_ARG(kernels[l] && (ksize[l] & 1) && ksize[l] >= 1 && ksize[l] <= 7, "smallmap_stack_f32: layer %d: odd kernel size <= 7", l);
-        PCNN_CHECK_ARG(cin[l] >= 1 && cin[l] <= CMAX && cout[l] >= 1 && cout[l] <= CMAX, "smallmap_stack_f32: layer %d: channels must be <= %d", l, CMAX);
-        PCNN_CHECK_ARG(l == 0 || cin[l] == cout[l - 1], "smallmap_stack_f32: layer %d: input channels do not chain", l);
-        PCNN_CHECK_ARG((bn_scale && bn_scale[l]) ? (bn_shift && bn_shift[l]) : !(bn_shift && bn_shift[l]), "smallmap_stack_f32: bn_scale/bn_shift must come together");
-        if (flags[l] & 1) { PCNN_CHECK_ARG(depth == 0, "smallmap_stack_f32: nested saves are not supported"); depth = 1; }
-        if (flags[l] & 2) { PCNN_CHECK_ARG(depth == 1 || (flags[l] & 1), "smallmap_stack_f32: layer %d adds a tensor nobody saved", l); depth = 0; }
-        if (pad_mode == PCNN_PAD_SYMMETRIC) PCNN_CHECK_ARG(ksize[l] / 2 <= std::min(H, W), "smallmap_stack_f32: SYMMETRIC pad larger than the map");
-        if (pad_mode == PCNN_PAD_REFLECT) PCNN_CHECK_ARG(ksize[l] / 2 < std::min(H, W), "smallmap_stack_f32: REFLECT pad too large for the map");
-        p.kernel[l] = kernels[l]; p.bias[l] = biases ? biases[l] : nullptr;
-        p.bn_scale[l] = bn_scale ? bn_scale[l] : nullptr; p.bn_shift[l] = bn_shift ? bn_shift[l] : nullptr;
-        p.k[l] = ksize[l]; p.cin[l] = cin[l]; p.cout[l] = cout[l]; p.flags[l] = flags[l];
-        wmax = std::max(wmax, (size_t)ksize[l] * ksize[l] * cin[l] * 32);
-        padmax = std::max(padmax, ksize[l] / 2);
-    }
-    p.padmax = padmax;
-    p.plane = (H + 2 * padmax) * (W + 2 * padmax);
-    const size_t smem = ((size_t)3 * CMAX * p.plane + wmax) * sizeof(float);
-    PCNN_CHECK_ARG(smem <= 220 * 1024, "smallmap_stack_f32: layer program does not fit in shared memory (%zu B)", smem);
-    PCNN_CHECK_CUDA(cudaFuncSetAttribute(smallmap_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smallmap_stack_kernel<<<B, NTHR, smem, (cudaStream_t)stream>>>(p);
-    PCNN_CHECK_LAUNCH();
-    return PCNN_OK;
+    const StackDesc d{in, out, H, W, Cin0, n_layers, kernels, biases, bn_scale, bn_shift, ksize, cin, cout, flags, act, pad_mode, pad_value};
+    return smallmap_stack_multi(&d, 1, B, (cudaStream_t)stream);
 }
