@@ -34,6 +34,12 @@ def test_cabi_rejects_bad_arguments_without_gpu():
     assert b"null pointer" in _lib.lib.pcnn_last_error()
     with pytest.raises(ValueError):
         _lib.check(st, "conv2d")
+    # workspace queries are pure host arithmetic: the CG solver keeps r, two p buffers and q plus 12 double accumulators per sample
+    assert _lib.lib.pcnn_neumann_cg_workspace_bytes(3, 40, 36) == 4 * 3 * 40 * 36 * 4 + 12 * 3 * 8
+    assert _lib.lib.pcnn_neumann_cg_workspace_bytes(0, 40, 36) == 0 and _lib.lib.pcnn_neumann_cg_workspace_bytes(1, 1, 36) == 0
+    assert _lib.lib.pcnn_neumann_cg_solve(None, None, None, None, 1, 8, 8, 1, 1e-6, None, None, None) == -1
+    assert _lib.lib.pcnn_dst_fft_workspace_bytes(2, 10, 12) == (2 + 1) * 8 * 10 * 8      # (B + 1) * (nx - 2) * (ny - 2) doubles
+    assert _lib.lib.pcnn_dst_fft_passes() == 3
 
 
 def test_product_has_no_cpu_fallback():
